@@ -1,0 +1,85 @@
+/*
+ * moloch_oracle.h -- C API of the CPU oracle for the MOLOCH dycore step.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This library is a plain C++ (FP64, no FMA
+ * contraction) restatement of the reference algorithm in
+ * /root/reference/Main/mod_moloch.F90 (RegCM 5.0.0).  It is the checker the
+ * CUDA product path is compared against; it is never linked, imported or
+ * called by the product (regcm_b200/).  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may use it.
+ *
+ * PARITY UNPINNED: the reference ships no unit tests, golden vectors or
+ * fixtures for this path and cannot be compiled in this
+ * container (no Fortran compiler, MPI or NetCDF).  The oracle is pinned only
+ * by analytic known-answer tests derived from the reference source
+ * (tests/test_oracle_*.py) and by decomposition invariance.
+ *
+ * Conventions
+ *  - Global arrays cross the API in C order: 2-D (iy, jx), 3-D (nk, iy, jx),
+ *    4-D (n, nk, iy, jx) -- i.e. RegCM's (j,i,k,n) with j fastest, on the full
+ *    dot-grid extent jx x iy (cross-grid fields leave the last row/column
+ *    unused when that direction is not periodic).
+ *  - The oracle internally splits the domain into px x py subdomains exactly
+ *    like set_nproc (Main/mpplib/mod_mppparam.F90:1250-1641), allocates every
+ *    array with the reference's bounds and ghost widths
+ *    (Main/mod_atm_interface.F90:579-624, Main/mod_moloch.F90:159-199) and
+ *    emulates exchange_lr/_bt/_lrbt (mod_mppparam.F90:3809-3878,4257-4309,
+ *    4661-4712) by direct copies between subdomains.
+ */
+#ifndef MOLOCH_ORACLE_H
+#define MOLOCH_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int jx, iy, kz;          /* &dimparam                                        */
+  int nqx, ntr;            /* water species (ipptls=2 -> 5), tracers           */
+  int i_band, i_crm;       /* &geoparam periodicity                            */
+  int px, py;              /* njxcpus, niycpus (1,1 = single domain)           */
+  int mo_nadv, mo_nsound;  /* &molochparam                                     */
+  int mo_divdamp, mo_divfilter;
+  int lrotllr;             /* iproj == 'ROTLLR'                                */
+  int ipptls;              /* 0,1,2: which condensates enter tvirt             */
+  int nspgx;               /* sponge width for bdywt masks (0 = no sponge)     */
+  double dtsec, dx;        /* dt [s], ds*1000 [m]                              */
+  double mo_ztop, mo_h, mo_a0;
+} oracle_config;
+
+void*  oracle_create(const oracle_config* cfg);
+void   oracle_destroy(void* h);
+const char* oracle_last_error(void);
+
+/* number of values of a named global array (0 = unknown name) */
+long   oracle_global_size(void* h, const char* name);
+/* scatter a global array into every subdomain (ghosts included, periodic wrap) */
+int    oracle_set_global(void* h, const char* name, const double* src);
+/* gather the owned cells of every subdomain into a global array              */
+int    oracle_get_global(void* h, const char* name, double* dst);
+
+/* compute_moloch_static (Main/mod_params.F90:3316-3395) + init_moloch
+ * (Main/mod_moloch.F90:201-308) + ffilt (Main/mod_init.F90:1008-1026) from
+ * ht,htu,htv,msfx,msfu,msfv,ulat,vlat,rlat[,hefc]                            */
+int    oracle_setup_static(void* h);
+/* paicompute (Main/mod_bdycod.F90:3762-3796) + Main/mod_init.F90:941-953:
+ * pai,tvirt,tetav,p,rho,qs from t,qx(:,:,:,iqv),ps; w = 0                     */
+int    oracle_init_state(void* h);
+
+/* the hot path */
+int    oracle_step(void* h, int nsteps);             /* moloch (physics off)  */
+int    oracle_reset_tendencies(void* h);
+int    oracle_sound(void* h);                        /* one sound(dtsound)    */
+int    oracle_advection(void* h);                    /* one advection(dtstepa)*/
+int    oracle_wafone(void* h, const char* field, int n); /* wafone(field(:,:,:,n)) */
+int    oracle_dynamical_core(void* h);
+int    oracle_diagnostics(void* h);                  /* p,rho,qsat,ps :348-354*/
+int    oracle_status_update(void* h);
+
+void   oracle_set_threads(int n);
+int    oracle_get_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

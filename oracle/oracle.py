@@ -1,0 +1,130 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE -- see moloch_oracle.h).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module; the product (regcm_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class OracleConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "jx", "iy", "kz", "nqx", "ntr", "i_band", "i_crm", "px", "py", "mo_nadv", "mo_nsound",
+        "mo_divdamp", "mo_divfilter", "lrotllr", "ipptls", "nspgx")] + [
+        (n, C.c_double) for n in ("dtsec", "dx", "mo_ztop", "mo_h", "mo_a0")]
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle shared libraries (g++, a few seconds)."""
+    if force or not (os.path.exists(os.path.join(_HERE, "libmoloch_oracle.so"))
+                     and os.path.exists(os.path.join(_HERE, "libmoloch_oracle_chk.so"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+
+
+_libs = {}
+
+
+def _lib(checked: bool):
+    key = "chk" if checked else "fast"
+    if key not in _libs:
+        build()
+        name = "libmoloch_oracle_chk.so" if checked else "libmoloch_oracle.so"
+        lib = C.CDLL(os.path.join(_HERE, name))
+        lib.oracle_create.restype = C.c_void_p
+        lib.oracle_create.argtypes = [C.POINTER(OracleConfig)]
+        lib.oracle_destroy.argtypes = [C.c_void_p]
+        lib.oracle_last_error.restype = C.c_char_p
+        lib.oracle_global_size.restype = C.c_long
+        lib.oracle_global_size.argtypes = [C.c_void_p, C.c_char_p]
+        lib.oracle_set_global.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        lib.oracle_get_global.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        for f in ("oracle_setup_static", "oracle_init_state", "oracle_reset_tendencies", "oracle_sound",
+                  "oracle_advection", "oracle_dynamical_core", "oracle_diagnostics", "oracle_status_update"):
+            getattr(lib, f).argtypes = [C.c_void_p]
+        lib.oracle_step.argtypes = [C.c_void_p, C.c_int]
+        lib.oracle_wafone.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        _libs[key] = lib
+    return _libs[key]
+
+
+class Oracle:
+    """One oracle world: the global domain split into px x py subdomains."""
+
+    def __init__(self, wl, px: int = 1, py: int = 1, checked: bool = False):
+        self.lib = _lib(checked)
+        self.wl = wl
+        self.cfg = OracleConfig(jx=wl.jx, iy=wl.iy, kz=wl.kz, nqx=wl.nqx, ntr=wl.ntr, i_band=wl.i_band,
+                                i_crm=wl.i_crm, px=px, py=py, mo_nadv=wl.mo_nadv, mo_nsound=wl.mo_nsound,
+                                mo_divdamp=wl.mo_divdamp, mo_divfilter=wl.mo_divfilter, lrotllr=wl.lrotllr,
+                                ipptls=wl.ipptls, nspgx=wl.nspgx, dtsec=wl.dt, dx=wl.dx, mo_ztop=wl.mo_ztop,
+                                mo_h=wl.mo_h, mo_a0=wl.mo_a0)
+        self.h = self.lib.oracle_create(C.byref(self.cfg))
+        if not self.h:
+            raise RuntimeError(self.lib.oracle_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.oracle_last_error().decode())
+
+    def set(self, name: str, arr) -> None:
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        n = self.lib.oracle_global_size(self.h, name.encode())
+        if n != a.size:
+            raise ValueError(f"{name}: expected {n} values, got {a.size}")
+        self._chk(self.lib.oracle_set_global(self.h, name.encode(), a.ctypes.data))
+
+    def get(self, name: str) -> np.ndarray:
+        wl = self.wl
+        n = self.lib.oracle_global_size(self.h, name.encode())
+        if n <= 0:
+            raise KeyError(name)
+        out = np.zeros(n)
+        self._chk(self.lib.oracle_get_global(self.h, name.encode(), out.ctypes.data))
+        plane = wl.jx * wl.iy
+        if n % plane == 0 and n >= plane:
+            nk = n // plane
+            if name in ("qx", "qxten"):
+                return out.reshape(wl.nqx, wl.kz, wl.iy, wl.jx)
+            if name in ("trac", "chiten"):
+                return out.reshape(wl.ntr, wl.kz, wl.iy, wl.jx)
+            return out.reshape(wl.iy, wl.jx) if nk == 1 else out.reshape(nk, wl.iy, wl.jx)
+        return out
+
+    def load_primary(self, P: dict) -> None:
+        """Feed the file-like inputs of regcm_b200.synthetic.make_primary, then run
+        the oracle's own restatement of the set-up code."""
+        for k in ("ht", "htu", "htv", "msfx", "msfu", "msfv", "ulat", "vlat", "rlat", "ps", "t", "qx", "u", "v"):
+            self.set(k, P[k])
+        if "hefc" in P and self.wl.nspgx > 0:
+            self.set("hefc", P["hefc"])
+        if "trac" in P and self.wl.ntr > 0:
+            self.set("trac", P["trac"])
+        self._chk(self.lib.oracle_setup_static(self.h))
+        self._chk(self.lib.oracle_init_state(self.h))
+
+    def step(self, n: int = 1): self._chk(self.lib.oracle_step(self.h, n))
+    def reset_tendencies(self): self._chk(self.lib.oracle_reset_tendencies(self.h))
+    def sound(self): self._chk(self.lib.oracle_sound(self.h))
+    def advection(self): self._chk(self.lib.oracle_advection(self.h))
+    def dynamical_core(self): self._chk(self.lib.oracle_dynamical_core(self.h))
+    def diagnostics(self): self._chk(self.lib.oracle_diagnostics(self.h))
+    def status_update(self): self._chk(self.lib.oracle_status_update(self.h))
+    def wafone(self, field: str, n: int = 1): self._chk(self.lib.oracle_wafone(self.h, field.encode(), n))
+
+    def set_threads(self, n: int): self.lib.oracle_set_threads(int(n))
+    def get_threads(self) -> int: return int(self.lib.oracle_get_threads())

@@ -1,0 +1,396 @@
+"""Synthetic RegCM-side model state for the MOLOCH dycore (host stand-in).
+
+A real deployment keeps RegCM's Fortran host code: the DOMAIN/ICBC readers fill
+`mddom`/`mo_atm`, `compute_moloch_static` (Main/mod_params.F90:3316-3395)
+derives the metric terms and `init` (Main/mod_init.F90:156-221,941-1026) the
+initial Exner function.  There is no Fortran toolchain (and no NetCDF input)
+in this environment, so this module generates the same arrays analytically, in
+NumPy, on the *global* grid; `regcm_b200.hostmodel` then cuts them into the
+per-rank arrays (with RegCM's bounds and ghost widths) that cross the C ABI.
+
+Global arrays are C-ordered (nk, iy, jx) / (iy, jx): RegCM's (j,i,k) with j
+fastest.  Index [i-1, j-1] is RegCM's (j,i).
+
+The named workloads are the BASELINE.json configs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, replace
+
+import numpy as np
+
+# ---- Share/mod_constants.F90 (non-RCEMIP) ---------------------------------
+egrav = 9.80665
+rgas = ((6.02214076e23 * 1.3806490e-23) / 28.96454) * 1000.0
+cpd = 3.5 * rgas
+cvd = 2.5 * rgas
+regrav = 1.0 / egrav
+rovcp = rgas * (1.0 / cpd)
+rdrcv = rgas / cvd
+cpovr = cpd / rgas
+govcp = egrav / cpd
+govr = egrav / rgas
+p00 = 1.0e5
+lrate = 0.00649
+stdt = 288.15
+stdp = 1.013250e5
+tzero = 273.15
+ep1 = 28.96454 / 18.01528 - 1.0
+ep2 = 18.01528 / 28.96454
+mathpi = 3.14159265358979323846
+degrad = mathpi / 180.0
+raddeg = 180.0 / mathpi
+eomeg2 = 2.0 * 7.2921159e-5
+earthrad = 6.371229e6
+mo_zfilt_fac = 0.8
+
+
+@dataclass(frozen=True)
+class Workload:
+    name: str
+    jx: int
+    iy: int
+    kz: int
+    nqx: int = 5
+    ntr: int = 0
+    i_band: int = 0
+    i_crm: int = 0
+    ds_km: float = 2.0
+    dt: float = 30.0
+    clat: float = 0.0
+    oro: str = "flat"        # flat | gauss | sine
+    oro_h: float = 1500.0
+    msf_amp: float = 0.0     # map factor = 1 + amp*sin*cos
+    nspgx: int = 0           # sponge width (0: no sponge masks)
+    lrotllr: int = 0
+    ipptls: int = 2
+    mo_nadv: int = 2
+    mo_nsound: int = 5
+    mo_divdamp: int = 1
+    mo_divfilter: int = 1
+    mo_ztop: float = 30000.0
+    mo_h: float = 8000.0
+    mo_a0: float = 0.0
+    u0: float = 10.0
+    v0: float = 2.0
+    seed: int = 20240613
+
+    @property
+    def dx(self) -> float:
+        return self.ds_km * 1000.0
+
+    @property
+    def nfields(self) -> int:
+        """F = number of wafone-advected fields."""
+        return 5 + 1 + (self.nqx - 1) + self.ntr
+
+    @property
+    def cells(self) -> int:
+        return self.jx * self.iy * self.kz
+
+    def bytes_per_cell_update(self) -> int:
+        """Algorithmic bytes B(F,nqx,ntr) of SURVEY.md section 8(d)."""
+        return 8 * (self.mo_nadv * (self.mo_nsound * 38 + 6 + 16 + 17 * self.nfields)
+                    + 50 + 4 * (self.nqx + self.ntr))
+
+
+# BASELINE.json configs
+WORKLOADS = {
+    # 1: Testing/ideal.in shape with ds from isc24.in, doubly periodic
+    "ideal": Workload("ideal", 500, 100, 60, i_band=1, i_crm=1, ds_km=2.0, dt=30.0),
+    # 2: Testing/isc24_small.in
+    "isc24_small": Workload("isc24_small", 100, 50, 30, i_band=1, i_crm=1, ds_km=2.0, dt=30.0),
+    # 3: CORDEX-like 25 km limited-area, 10 tracers
+    "cordex25": Workload("cordex25", 400, 400, 41, ntr=10, ds_km=25.0, dt=150.0, clat=45.0,
+                         oro="gauss", msf_amp=0.05, nspgx=12),
+    # 4: convection-permitting 3 km
+    "cp3km": Workload("cp3km", 1536, 1536, 41, ds_km=3.0, dt=30.0, clat=45.0, oro="gauss",
+                      msf_amp=0.05, nspgx=12),
+    # 5: large tracer load
+    "tracer40": Workload("tracer40", 1024, 1024, 41, ntr=40, ds_km=12.0, dt=90.0, clat=45.0,
+                         oro="gauss", msf_amp=0.05, nspgx=12),
+}
+
+
+def small(wl: Workload, jx: int, iy: int, kz: int, **kw) -> Workload:
+    """A reduced-size variant of a workload for parity tests."""
+    return replace(wl, name=f"{wl.name}_{jx}x{iy}x{kz}", jx=jx, iy=iy, kz=kz, **kw)
+
+
+# ---- deterministic hash noise in [-1, 1) (identical for any decomposition) --
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def noise(shape, seed: int, salt: int) -> np.ndarray:
+    n = int(np.prod(shape))
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64) + np.uint64((seed * 1000003 + salt * 7919) & 0xFFFFFFFFFFFF)
+        r = _splitmix64(idx)
+    u = (r >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return (2.0 * u - 1.0).reshape(shape)
+
+
+# ---- Share/mod_zita.F90:40-178 ----------------------------------------------
+def model_zitaf(kz, ztop):
+    z = np.zeros(kz + 1)
+    dz = ztop / float(kz)
+    z[kz] = 0.0
+    z[0] = ztop
+    for k in range(kz - 1, 0, -1):       # do k = kz, 2, -1 (1-based)
+        z[k] = z[k + 1] + dz
+    return z
+
+
+def model_zitah(kz, ztop):
+    z = np.zeros(kz)
+    dz = ztop / float(kz)
+    z[kz - 1] = dz * 0.5
+    z[0] = ztop - dz * 0.5
+    for k in range(kz - 2, 0, -1):
+        z[k] = z[k + 1] + dz
+    return z
+
+
+def _zfz(ztop, zh): return ztop / (np.exp(ztop / zh) - 1.0)
+def bzita(zita, ztop, zh): return _zfz(ztop, zh) * (np.exp(zita / zh) - 1.0)
+def bzitap(zita, ztop, zh): return _zfz(ztop, zh) * np.exp(zita / zh) / zh
+
+
+def gzita(zita, ztop, a0):
+    ratio = zita / ztop
+    return ((0.0 - 1.0 * a0) * ratio - (3.0 - 2.0 * a0) * (ratio * ratio)
+            + (2.0 - 1.0 * a0) * (ratio * ratio * ratio)) + 1.0
+
+
+def gzitap(zita, ztop, a0):
+    ratio = zita / ztop
+    return ((0.0 - 1.0 * a0) * 1.0 - (6.0 - 4.0 * a0) * ratio + (6.0 - 3.0 * a0) * (ratio * ratio)) / ztop
+
+
+def md_fmz(zita, geopot, ztop, zh, a0):
+    return 1.0 / (gzitap(zita, ztop, a0) * (geopot * regrav) + bzitap(zita, ztop, zh))
+
+
+def md_zeta(zita, geopot, ztop, zh, a0):
+    return (geopot * regrav) * (gzita(zita, ztop, a0) - 1.0) + bzita(zita, ztop, zh)
+
+
+def pfwsat(t, p):
+    """Share/pfwsat.inc"""
+    a = [0.611213476e+03, 0.444007856e+02, 0.143064234e+01, 0.264461437e-01, 0.305903558e-03,
+         0.196237241e-05, 0.892344772e-08, -0.373208410e-10, 0.209339997e-13]
+    c = [0.611123516e+03, 0.503109514e+02, 0.188369801e+01, 0.420547422e-01, 0.614396778e-03,
+         0.602780717e-05, 0.387940929e-07, 0.149436277e-09, 0.262655803e-12]
+    td = np.minimum(np.maximum(t - tzero, -75.0), 100.0)
+
+    def horner(co):
+        r = co[8]
+        for n in range(7, -1, -1):
+            r = co[n] + td * r
+        return r
+    es = np.where(td >= 0.0, np.minimum(horner(a), 0.15 * p), np.minimum(horner(c), 0.15 * p))
+    return ep2 * (es / (p - es))
+
+
+# ---- primary (file-like) inputs ----------------------------------------------
+def _height(wl: Workload, x, y):
+    """Analytic terrain height [m] at grid coordinates (x=j, y=i)."""
+    if wl.oro == "flat":
+        return np.zeros(np.broadcast(x, y).shape)
+    if wl.oro == "sine":   # periodic hills
+        return wl.oro_h * 0.25 * (1.0 + np.sin(2 * mathpi * x / wl.jx)) * (1.0 + np.cos(2 * mathpi * y / wl.iy))
+    if wl.oro == "gauss":
+        h = 0.0
+        for (cx, cy, sx, sy, a) in ((0.30, 0.35, 0.08, 0.10, 1.0), (0.62, 0.55, 0.12, 0.07, 0.7),
+                                    (0.45, 0.78, 0.06, 0.06, 0.5)):
+            h = h + a * np.exp(-(((x / wl.jx - cx) / sx) ** 2 + ((y / wl.iy - cy) / sy) ** 2))
+        return wl.oro_h * h / 1.0
+    raise ValueError(wl.oro)
+
+
+def _msf(wl: Workload, x, y):
+    if wl.msf_amp == 0.0:
+        return np.ones(np.broadcast(x, y).shape)
+    return 1.0 + wl.msf_amp * np.sin(2 * mathpi * x / wl.jx) * np.cos(2 * mathpi * y / wl.iy)
+
+
+def hefc_table(wl: Workload) -> np.ndarray:
+    """Sponge coefficients hefc(n,k) (Main/mod_bdycod.F90:520-545, exponential
+    branch) with a linear anudge(k) profile standing in for spline1d."""
+    nsp, kz = wl.nspgx, wl.kz
+    h = np.zeros((kz, nsp))
+    anudge = np.linspace(3.0, 1.0, kz)
+    for k in range(kz):
+        h[k, 0] = 1.0
+        h[k, nsp - 1] = 0.0
+        for n in range(2, nsp):
+            h[k, n - 1] = np.exp(-float(n - 1) / anudge[k])
+    return h
+
+
+def make_primary(wl: Workload) -> dict:
+    """Global 'file-like' inputs: terrain, map factors, latitudes, sponge table
+    and the initial t, qx, u, v, trac, ps."""
+    jx, iy, kz = wl.jx, wl.iy, wl.kz
+    J, I = np.meshgrid(np.arange(1, jx + 1, dtype=np.float64), np.arange(1, iy + 1, dtype=np.float64))
+    P = {}
+    P["ht"] = _height(wl, J, I) * egrav            # geopotential, as mddom%ht (mod_params.F90:2438)
+    P["htu"] = _height(wl, J - 0.5, I) * egrav
+    P["htv"] = _height(wl, J, I - 0.5) * egrav
+    P["msfx"] = _msf(wl, J, I)
+    P["msfu"] = _msf(wl, J - 0.5, I)
+    P["msfv"] = _msf(wl, J, I - 0.5)
+    dl = raddeg * wl.dx / earthrad                  # Main/mod_params.F90:2122-2141
+    P["xlat"] = wl.clat - dl * (float(iy) * 0.5 - I + 0.5)
+    P["ulat"] = P["xlat"].copy()
+    P["vlat"] = wl.clat - dl * (float(iy) * 0.5 - I + 1.0)
+    P["rlat"] = wl.clat - dl * (float(iy) * 0.5 - np.arange(1, iy + 2, dtype=np.float64) + 1.0)
+    if wl.nspgx > 0:
+        P["hefc"] = hefc_table(wl)
+    zitah = model_zitah(kz, wl.mo_ztop)
+    zeta = md_zeta(zitah[:, None, None], P["ht"][None], wl.mo_ztop, wl.mo_h, wl.mo_a0)
+    # base state: initideal-like profile + warm bubble + noise
+    t = np.maximum(stdt - lrate * (zeta + P["ht"][None] * regrav), 210.0)
+    r2 = ((J - 0.5 * jx) ** 2 + (I - 0.5 * iy) ** 2)[None] / 100.0 + ((zeta - 2000.0) / 1500.0) ** 2
+    t = t + 2.0 * np.exp(-r2) + 1.0e-3 * noise(t.shape, wl.seed, 1)
+    qx = np.zeros((wl.nqx, kz, iy, jx))
+    qx[0] = 0.012 * np.exp(-(zeta + P["ht"][None] * regrav) / 2500.0)
+    P["t"], P["qx"] = t, qx
+    P["u"] = wl.u0 * (1.0 + 0.1 * noise(t.shape, wl.seed, 2))
+    P["v"] = wl.v0 * (1.0 + 0.1 * noise(t.shape, wl.seed, 3))
+    hsurf = P["ht"] * regrav
+    P["ps"] = stdp * (1.0 - lrate * hsurf / stdt) ** (egrav / (rgas * lrate))
+    if wl.ntr > 0:
+        tr = np.full((wl.ntr, kz, iy, jx), 1.0e-9)
+        rng = np.random.default_rng(wl.seed)
+        for n in range(wl.ntr):
+            cx, cy, cz = rng.uniform(0.15, 0.85), rng.uniform(0.15, 0.85), rng.uniform(500.0, 6000.0)
+            rr = ((J - cx * jx) ** 2 + (I - cy * iy) ** 2)[None] / 64.0 + ((zeta - cz) / 1000.0) ** 2
+            tr[n] += 1.0e-6 * np.exp(-rr)
+        P["trac"] = tr
+    return P
+
+
+# ---- derived static fields (compute_moloch_static + init_moloch) ------------
+def _ibnd(wl: Workload, ldotx: bool, ldoty: bool) -> np.ndarray:
+    """ba%ibnd of setup_boundaries (Main/mod_atm_interface.F90:384-532)."""
+    jx, iy, nsp = wl.jx, wl.iy, wl.nspgx
+    ib = np.full((iy, jx), -1, dtype=np.int64)
+    crm = wl.i_crm == 1
+    band = wl.i_band == 1 or crm
+    if nsp <= 0 or crm:
+        return ib
+    J, I = np.meshgrid(np.arange(1, jx + 1), np.arange(1, iy + 1))
+    jcx, icy = (0 if ldotx else 1), (0 if ldoty else 1)
+    igbb1, igbb2, jgbl1, jgbl2 = 2, nsp - 1, 2, nsp - 1
+    igbt1, igbt2 = iy - icy - nsp + 2, iy - 1 - icy
+    jgbr1, jgbr2 = jx - jcx - nsp + 2, jx - 1 - jcx
+    if band:
+        jgbl1, jgbr2 = 1, jx - jcx
+        south = (I >= igbb1) & (I <= igbb2) & ~((J < jgbl1) & (J > jgbr2))
+        ib[south] = (I - igbb1 + 2)[south]
+        north = (I >= igbt1) & (I <= igbt2) & ~((J < jgbl1) & (J > jgbr2))
+        ib[north] = (igbt2 - I + 2)[north]
+        return ib
+    inj = (J >= jgbl1) & (J <= jgbr2)
+    south = ((I >= igbb1) & (I <= igbb2) & inj & ~((J <= jgbl2) & (I >= J))
+             & ~((J >= jgbr1) & (I >= (jgbr2 - J + 2))))
+    ib[south] = (I - igbb1 + 2)[south]
+    north = ((I >= igbt1) & (I <= igbt2) & inj & ~((J <= jgbl2) & (J <= (igbt2 - I + 2)))
+             & ~((J >= jgbr1) & ((igbt2 - I) >= (jgbr2 - J))))
+    ib[north] = (igbt2 - I + 2)[north]
+    mid = ~(north | south) & (I >= igbb1) & (I <= igbt2)
+    west = mid & (J >= jgbl1) & (J <= jgbl2)
+    ib[west] = (J - jgbl1 + 2)[west]
+    east = mid & (J >= jgbr1) & (J <= jgbr2)
+    ib[east] = (jgbr2 - J + 2)[east]
+    return ib
+
+
+def _bdywt(wl: Workload, ib: np.ndarray, hefc) -> np.ndarray:
+    """setup_bdywt (Main/mod_bdycod.F90:4033-4047)."""
+    m = np.ones((wl.kz,) + ib.shape)
+    if wl.nspgx > 0 and hefc is not None:
+        sel = ib > 0
+        idx = np.where(sel, ib - 1, 0)
+        m = np.where(sel[None], 1.0 - hefc[:, idx], 1.0)
+    return m
+
+
+def derive_static(wl: Workload, P: dict) -> dict:
+    """compute_moloch_static (Main/mod_params.F90:3316-3395), the zita levels
+    (:2461-2463), setup_bdywt and ffilt (Main/mod_init.F90:1008-1026) on the
+    global grid.  Rows/columns outside a field's owned range hold values that
+    are never read."""
+    jx, iy, kz = wl.jx, wl.iy, wl.kz
+    ztop, zh, a0 = wl.mo_ztop, wl.mo_h, wl.mo_a0
+    S = {}
+    zita, zitah = model_zitaf(kz, ztop), model_zitah(kz, ztop)
+    S["zita"], S["zitah"] = zita, zitah
+    S["mo_dzita"] = float(zita[kz - 1])
+    rdx = 1.0 / wl.dx
+    ht, htu, htv = P["ht"], P["htu"], P["htv"]
+    perj = wl.i_band == 1 or wl.i_crm == 1
+    peri = wl.i_crm == 1
+    htm1 = np.roll(ht, 1, axis=1) if perj else np.concatenate([ht[:, :1], ht[:, :-1]], axis=1)
+    hx = rdx * regrav * P["msfu"] * (ht - htm1)
+    hx[:, 0] = 2.0 * rdx * regrav * P["msfu"][:, 0] * (ht[:, 0] - htu[:, 0])      # j == 1
+    htm1 = np.roll(ht, 1, axis=0) if peri else np.concatenate([ht[:1], ht[:-1]], axis=0)
+    mfv = 1.0 if wl.lrotllr else P["msfv"]
+    hy = rdx * regrav * mfv * (ht - htm1)
+    hy[0] = (2.0 * rdx * regrav * mfv * (ht - htv))[0]                            # i == 1
+    S["hx"], S["hy"] = hx, hy
+    S["zeta"] = md_zeta(zitah[:, None, None], ht[None], ztop, zh, a0)
+    S["fmz"] = md_fmz(zitah[:, None, None], ht[None], ztop, zh, a0)
+    S["rfmzu"] = 1.0 / md_fmz(zitah[:, None, None], htu[None], ztop, zh, a0)
+    S["rfmzv"] = 1.0 / md_fmz(zitah[:, None, None], htv[None], ztop, zh, a0)
+    S["fmzf"] = md_fmz(zita[:, None, None], ht[None], ztop, zh, a0)
+    S["zetaf"] = md_zeta(zita[:, None, None], ht[None], ztop, zh, a0)
+    hefc = P.get("hefc")
+    S["bdywtw"] = _bdywt(wl, _ibnd(wl, False, False), hefc)
+    S["bdywtu"] = _bdywt(wl, _ibnd(wl, True, False), hefc)
+    S["bdywtv"] = _bdywt(wl, _ibnd(wl, False, True), hefc)
+    # ffilt: sponge in the implicit solver above 18 km
+    njc = jx if perj else jx - 1
+    nic = iy if peri else iy - 1
+    gmeanz = S["zeta"][:, :nic, :njc].reshape(kz, -1).sum(axis=1) / float(njc * nic)
+    zzi = (gmeanz - 18000.0) / (ztop - 18000.0)
+    S["ffilt"] = np.where(gmeanz < 18000.0, 0.0, mo_zfilt_fac * np.sin(0.5 * mathpi * zzi) ** 2)
+    return S
+
+
+def init_state(wl: Workload, P: dict, S: dict) -> dict:
+    """paicompute (Main/mod_bdycod.F90:3762-3796) + Main/mod_init.F90:941-953."""
+    kz = wl.kz
+    t, q, z = P["t"], P["qx"][0], S["zeta"]
+    pai = np.zeros_like(t)
+    zdelta = z[kz - 1] * egrav
+    tv1 = t[kz - 1] * (1.0 + ep1 * q[kz - 1])
+    tv2 = t[kz - 2] * (1.0 + ep1 * q[kz - 2])
+    lrt = (tv2 - tv1) / (z[kz - 2] - z[kz - 1])
+    lrt = np.where(lrt > govcp, govcp, np.where(lrt < -0.005, 0.5 * lrt - 0.5 * lrate, lrt))
+    tv = tv1 - 0.5 * z[kz - 1] * lrt
+    zz = 1.0 / (rgas * tv)
+    p = P["ps"] * np.exp(-zdelta * zz)
+    paikp1 = (p / p00) ** rovcp
+    pai[kz - 1] = paikp1
+    for k in range(kz - 2, -1, -1):
+        tv1 = t[k] * (1.0 + ep1 * q[k])
+        tv2 = t[k + 1] * (1.0 + ep1 * q[k + 1])
+        zb = 2.0 * egrav * S["mo_dzita"] / (S["fmzf"][k + 1] * cpd) + tv1 - tv2
+        zdelta = np.sqrt(zb * zb + 4.0 * tv2 * tv1)
+        paikp1 = -paikp1 / (2.0 * tv2) * (zb - zdelta)
+        pai[k] = paikp1
+    st = {"pai": pai}
+    st["p"] = pai ** cpovr * p00
+    st["qsat"] = pfwsat(t, st["p"])
+    st["rho"] = st["p"] / (rgas * t)
+    st["tvirt"] = t * (1.0 + ep1 * q)
+    st["tetav"] = st["tvirt"] / pai
+    st["w"] = np.zeros((kz + 1,) + t.shape[1:])
+    return st

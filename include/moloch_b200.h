@@ -1,0 +1,160 @@
+/*
+ * moloch_b200.h -- C ABI of the B200-native MOLOCH dynamical-core step.
+ *
+ * This is the drop-in boundary for RegCM's `mod_moloch` (reference:
+ * Main/mod_moloch.F90).  RegCM has no plugin registry: the boundary is the
+ * three argument-less module procedures
+ *     allocate_moloch   Main/mod_moloch.F90:159   (called Main/mod_params.F90:1980)
+ *     init_moloch       Main/mod_moloch.F90:201   (called Main/mod_init.F90:923)
+ *     moloch            Main/mod_moloch.F90:312   (called Main/mod_regcm_interface.F90:275)
+ * plus the module state they alias (mo_atm, mddom, sfs; Main/mod_moloch.F90:204-255).
+ * A Fortran ISO_C_BINDING shim keeps those three names and
+ * forwards to the entry points below; everything crosses as plain pointers,
+ * Fortran array bounds and default integers -- no torch, no C++ types.
+ *
+ * Conventions
+ *  - All arrays are RegCM's (j,i,k): j fastest, then i, then k; real(rk8).
+ *    A host array is described by the address of its first element and its
+ *    Fortran bounds (jlo:jhi, ilo:ihi, klo:khi) in GLOBAL indices, exactly what
+ *    `c_loc(a)` + `lbound/ubound` give in the shim.
+ *  - Every entry returns 0 on success; on failure it returns non-zero and
+ *    moloch_b200_last_error() describes it (the shim turns this into RegCM's
+ *    `fatal(__FILE__,__LINE__,msg)`, Share/mod_message.F90:86-99).
+ *  - One context per MPI rank / GPU, single caller thread
+ *    (MPI_THREAD_FUNNELED, Main/regcm.F90:60).
+ *  - There is no CPU fallback: every compute entry fails if no CUDA device is
+ *    usable.
+ */
+#ifndef MOLOCH_B200_H
+#define MOLOCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOLOCH_B200_ABI_VERSION 1
+
+/* Replaces the module globals read by allocate_moloch/init_moloch:
+ * mod_dynparam index ranges (Share/mod_dynparam.F90:252-310), `ma`
+ * (model_area, Main/mpplib/mod_regcm_types.F90:66-111) and the &molochparam
+ * knobs (Share/mod_dynparam.F90:203-211).                                   */
+typedef struct {
+  int32_t jx, iy, kz;                 /* &dimparam global dot-grid extents      */
+  int32_t nqx, ntr, iqfrst;           /* water species, tracers, first non-qv   */
+  int32_t jde1, jde2, ide1, ide2;     /* dot   external range of this rank      */
+  int32_t jce1, jce2, ice1, ice2;     /* cross external range of this rank      */
+  int32_t has_bdy_left, has_bdy_right, has_bdy_bottom, has_bdy_top; /* ma%has_bdy* */
+  int32_t bandflag, crmflag;          /* ma%bandflag, ma%crmflag                */
+  int32_t nbr_left, nbr_right, nbr_bottom, nbr_top; /* ma%left.. (-1 = mpi_proc_null) */
+  int32_t rank, nranks;
+  int32_t mo_nadv, mo_nsound;
+  int32_t mo_divdamp, mo_divfilter;
+  int32_t lrotllr;                    /* iproj == 'ROTLLR'                      */
+  int32_t ipptls;                     /* 0,1,2: condensates entering tvirt      */
+  int32_t device;                     /* CUDA ordinal; <0 = rank mod ndev
+                                         (Main/mod_regcm_interface.F90:397-400) */
+  int32_t reserved;
+  double dtsec, dx, mo_dzita;         /* dt [s], dx [m], zita(kz) spacing [m]   */
+} moloch_b200_config;
+
+typedef struct moloch_b200_ctx moloch_b200_ctx;
+
+/* Field identifiers for set/get (the arrays of type(atmosphere) `mo_atm`,
+ * Main/mpplib/mod_regcm_types.F90:131-161, `mddom` and the work arrays of
+ * allocate_moloch, Main/mod_moloch.F90:159-199).                            */
+enum moloch_b200_field {
+  MB_U = 0, MB_V, MB_W, MB_PAI, MB_TETAV, MB_T, MB_QX, MB_TRAC, MB_UX, MB_VX,
+  MB_TVIRT, MB_P, MB_RHO, MB_QSAT, MB_PS, MB_ZETA,
+  MB_FMZ, MB_FMZF, MB_RFMZU, MB_RFMZV, MB_HX, MB_HY, MB_MSFX, MB_MSFU, MB_MSFV,
+  MB_CORU, MB_CORV, MB_BDYWTU, MB_BDYWTV, MB_BDYWTW,
+  MB_TTEN, MB_UTEN, MB_VTEN, MB_QXTEN, MB_CHITEN,
+  MB_S, MB_ZDIV2, MB_WX, MB_WZ, MB_P0, MB_TETAVF,
+  MB_NFIELDS
+};
+
+/* 1-D profiles (k = 1..n) */
+enum moloch_b200_profile {
+  MB_GZITAK = 0,   /* gzita(zita)   kz+1   Main/mod_moloch.F90:273 */
+  MB_GZITAKH,      /* gzita(zitah)  kz     :274                    */
+  MB_FFILT,        /* kz   Main/mod_init.F90:1008-1026             */
+  MB_XKDAMP,       /* kz   Main/mod_moloch.F90:295                 */
+  MB_XKNU,         /* kz   :297                                    */
+  MB_RLAT,         /* ide1..ide2+1 (ROTLLR curvature only) :813    */
+  MB_NPROFILES
+};
+
+const char* moloch_b200_last_error(void);
+int moloch_b200_abi_version(void);
+/* number of usable CUDA devices (0 when none; never fails) */
+int moloch_b200_device_count(void);
+
+/* = allocate_moloch (Main/mod_moloch.F90:159-199) + device copies of the
+ * mo_atm arrays (Main/mod_atm_interface.F90:579-624).                       */
+int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out);
+int moloch_b200_destroy(moloch_b200_ctx* ctx);
+
+/* Halo-exchange transport (replaces exchange_lr/_bt/_lrbt,
+ * Main/mpplib/mod_mppparam.F90:3809-3878,4257-4309,4661-4712).  Rank 0 calls
+ * comm_id, the host broadcasts the 128 bytes (MPI_Bcast in the shim), every
+ * rank calls comm_init.  Not needed when nranks == 1.                        */
+int moloch_b200_comm_id(void* id128);
+int moloch_b200_comm_init(moloch_b200_ctx* ctx, const void* id128);
+
+/* run on a caller-owned CUDA stream (cudaStream_t) instead of the context's */
+int moloch_b200_set_stream(moloch_b200_ctx* ctx, void* cuda_stream);
+int moloch_b200_sync(moloch_b200_ctx* ctx);
+
+/* host -> device / device -> host of one array (species n = 1.. for the 4-D
+ * qx/trac/qxten/chiten; n ignored otherwise).  The intersection of the given
+ * bounds with the device box (owned range + ghosts) is transferred.  The
+ * host pointer may be pageable or pinned.                                   */
+int moloch_b200_set_field(moloch_b200_ctx* ctx, int field, int n, const double* host,
+                          int jlo, int jhi, int ilo, int ihi, int klo, int khi);
+int moloch_b200_get_field(moloch_b200_ctx* ctx, int field, int n, double* host,
+                          int jlo, int jhi, int ilo, int ihi, int klo, int khi);
+int moloch_b200_set_profile(moloch_b200_ctx* ctx, int profile, const double* v, int n);
+
+/* pinned host memory for the per-step state/tendency hand-off */
+int moloch_b200_host_alloc(void** p, uint64_t bytes);
+int moloch_b200_host_free(void* p);
+
+/* = the device part of init_moloch (Main/mod_moloch.F90:263-308): mx2, rmx,
+ * rmu, rmv and their halos, w(:,:,1)=0, clamp limits, dtstepa/dtsound.  Call
+ * after the static fields (fmz..bdywt*, profiles) have been set.            */
+int moloch_b200_init(moloch_b200_ctx* ctx);
+
+/* The hot path, one entry per reference subroutine */
+int moloch_b200_reset_tendencies(moloch_b200_ctx* ctx);          /* :1044 */
+int moloch_b200_sound(moloch_b200_ctx* ctx);                     /* :545  sound(dtsound)     */
+int moloch_b200_advection(moloch_b200_ctx* ctx);                 /* :767  advection(dtstepa) */
+int moloch_b200_wafone(moloch_b200_ctx* ctx, int field, int n);  /* :838  wafone(field,dtstepa) */
+int moloch_b200_dynamical_core(moloch_b200_ctx* ctx);            /* :1085 */
+int moloch_b200_diagnostics(moloch_b200_ctx* ctx);               /* :348-354 p,rho,qsat,ps   */
+int moloch_b200_status_update(moloch_b200_ctx* ctx);             /* :1403 (tendencies on device) */
+/* nsteps x [reset_tendencies, dynamical_core, diagnostics, status_update]:
+ * `moloch` with the host physics producing zero tendencies.                 */
+int moloch_b200_step(moloch_b200_ctx* ctx, int nsteps);
+
+/* built-in per-kernel device timing (CUDA events on the launching stream)   */
+int moloch_b200_profile_enable(moloch_b200_ctx* ctx, int on);
+/* fills up to `cap` entries; returns the number of kernel classes seen      */
+int moloch_b200_profile_read(moloch_b200_ctx* ctx, int cap, char (*names)[48],
+                             double* total_ms, int64_t* launches);
+/* launches of this library's kernels since the last call (gpu_launches)     */
+int64_t moloch_b200_launch_count(moloch_b200_ctx* ctx, int reset);
+uint64_t moloch_b200_device_bytes(moloch_b200_ctx* ctx);
+
+/* Host-only description of one halo exchange, for tests of the N>1 logic
+ * without a GPU: fills send/recv boxes {j1,j2,i1,i2} for the four sides
+ * (left,right,bottom,top) of an exchange of width `nex` over the owned box
+ * of staggering `stag` (0 cross, 1 U, 2 V, 3 dot, 4 the wafone p0 box).
+ * A side with no neighbour gets j1 > j2.                                    */
+int moloch_b200_halo_plan(const moloch_b200_config* cfg, int stag, int nex, int lr, int bt,
+                          int32_t send_box[4][4], int32_t recv_box[4][4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,494 @@
+// capi.cu -- the C ABI of include/moloch_b200.h: context, device memory,
+// host<->device hand-off and the orchestration of one MOLOCH step
+// (reference call tree: Main/mod_moloch.F90:312-446, 545-736, 767-836,
+// 1085-1141, 1403-1443).
+#include <cmath>
+#include <cstring>
+#include <map>
+#include "common.cuh"
+
+namespace mb {
+
+thread_local std::string g_err;
+int fail(const std::string& msg) { g_err = msg; return 1; }
+
+static const char* k_names[KID_COUNT] = {
+    "reset_tendencies", "tetavf_init", "sound_pre", "divdamp_filter", "wsolve", "uvupdate", "sfinish",
+    "destagger", "waf_vertical", "waf_meridional", "waf_zonal", "curvature", "restagger", "tvirt_temp",
+    "diag_prq", "diag_ps", "status_update", "halo_local", "halo_pack", "halo_unpack", "init_static"};
+const char* kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? k_names[kid] : "?"; }
+
+LaunchScope::LaunchScope(Ctx& c_, int kid_) : c(c_), kid(kid_) {
+  c.launches++;
+  if (c.profiling) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, c.stream);
+  }
+}
+LaunchScope::~LaunchScope() {
+  if (a) {
+    cudaEventRecord(b, c.stream);
+    c.events.push_back(ProfEvent{a, b, kid});
+  }
+}
+
+static void build_geo(Ctx& c) {
+  const moloch_b200_config& f = c.cfg;
+  Geo& g = c.g;
+  g.kz = f.kz;
+  g.jde1 = f.jde1; g.jde2 = f.jde2; g.ide1 = f.ide1; g.ide2 = f.ide2;
+  g.jce1 = f.jce1; g.jce2 = f.jce2; g.ice1 = f.ice1; g.ice2 = f.ice2;
+  g.bl = f.has_bdy_left != 0; g.br = f.has_bdy_right != 0; g.bb = f.has_bdy_bottom != 0; g.bt = f.has_bdy_top != 0;
+  g.gl = g.bl ? 0 : 1; g.gr = g.br ? 0 : 1; g.gb = g.bb ? 0 : 1; g.gt = g.bt ? 0 : 1;
+  // setup_model_indexes, Main/mod_atm_interface.F90:182-382
+  g.jdi1 = g.jde1 + (g.bl ? 1 : 0); g.jdii1 = g.jde1 + (g.bl ? 2 : 0);
+  g.jdi2 = g.jde2 - (g.br ? 1 : 0); g.jdii2 = g.jde2 - (g.br ? 2 : 0);
+  g.idi1 = g.ide1 + (g.bb ? 1 : 0); g.idii1 = g.ide1 + (g.bb ? 2 : 0);
+  g.idi2 = g.ide2 - (g.bt ? 1 : 0); g.idii2 = g.ide2 - (g.bt ? 2 : 0);
+  g.jci1 = g.jce1 + (g.bl ? 1 : 0); g.jci2 = g.jce2 - (g.br ? 1 : 0);
+  g.ici1 = g.ice1 + (g.bb ? 1 : 0); g.ici2 = g.ice2 - (g.bt ? 1 : 0);
+  // init_moloch, Main/mod_moloch.F90:280-293
+  const int jcross2 = f.bandflag ? f.jx : f.jx - 1, icross2 = f.crmflag ? f.iy : f.iy - 1;
+  g.jmin = 1; g.jmax = jcross2; g.imin = 1; g.imax = icross2;
+  if (f.bandflag) { g.jmin = 1 - 2; g.jmax = jcross2 + 2; }
+  if (f.crmflag) { g.jmin = 1 - 2; g.jmax = jcross2 + 2; g.imin = 1 - 2; g.imax = icross2 + 2; }
+  g.lrotllr = f.lrotllr; g.ipptls = f.ipptls; g.nqx = f.nqx; g.ntr = f.ntr;
+  g.j0 = g.jde1 - HJ; g.i0 = g.ide1 - HI;
+  int nj = (g.jde2 - g.jde1 + 1) + 2 * HJ;
+  nj = (nj + 3) / 4 * 4;
+  g.NJ = nj; g.NI = (g.ide2 - g.ide1 + 1) + 2 * HI;
+  g.plane = (long long)g.NJ * g.NI;
+}
+
+static int check_cfg(const moloch_b200_config& f) {
+  if (f.jx < 4 || f.iy < 4 || f.kz < 4) return fail("moloch_b200_create: jx, iy, kz must be >= 4");
+  if (f.nqx < 1 || f.nqx > 10) return fail("moloch_b200_create: nqx must be in 1..10");
+  if (f.ntr < 0) return fail("moloch_b200_create: ntr < 0");
+  if (f.ipptls > 1 && f.nqx < 5) return fail("moloch_b200_create: ipptls=2 needs nqx >= 5");
+  if (f.ipptls == 1 && f.nqx < 2) return fail("moloch_b200_create: ipptls=1 needs nqx >= 2");
+  if (f.jde2 - f.jde1 + 1 < 3 || f.ide2 - f.ide1 + 1 < 3)
+    return fail("Cannot have one processor with less than 3x3 points");  // mod_mppparam.F90:1605
+  if (f.jce1 != f.jde1 || f.ice1 != f.ide1 || f.jce2 > f.jde2 || f.ice2 > f.ide2 || f.jce2 < f.jde2 - 1 ||
+      f.ice2 < f.ide2 - 1)
+    return fail("moloch_b200_create: inconsistent cross/dot ranges");
+  if (f.mo_nadv < 1 || f.mo_nsound < 1) return fail("moloch_b200_create: mo_nadv, mo_nsound must be >= 1");
+  if (!(f.dtsec > 0.0) || !(f.dx > 0.0) || !(f.mo_dzita > 0.0))
+    return fail("moloch_b200_create: dtsec, dx, mo_dzita must be > 0");
+  if (f.nranks < 1 || f.rank < 0 || f.rank >= f.nranks) return fail("moloch_b200_create: bad rank/nranks");
+  return 0;
+}
+
+static int sync_stream(Ctx& c) {
+  MB_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
+// ---- orchestration ----------------------------------------------------------
+static int do_sound(Ctx& c) {
+  const double dts = c.dtsound;
+  const int kz = c.g.kz;
+  HaloItem it;
+  it = {c.f[MB_TETAV].p, kz};
+  if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :562
+  if (k_tetavf_init(c)) return 1;
+  for (int ns = 0; ns < c.cfg.mo_nsound; ++ns) {
+    it = {c.f[MB_U].p, kz};
+    if (halo_exchange(c, &it, 1, HS_U, 1, true, false)) return 1;   // :570
+    it = {c.f[MB_V].p, kz};
+    if (halo_exchange(c, &it, 1, HS_V, 1, false, true)) return 1;   // :571
+    if (k_sound_pre(c, dts)) return 1;
+    if (c.cfg.mo_divdamp || c.cfg.mo_divfilter) {
+      it = {c.f[MB_ZDIV2].p, kz};
+      if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :745 (:535 is redundant)
+      if (k_divdamp_filter(c, dts)) return 1;
+    }
+    if (k_wsolve(c, dts)) return 1;
+    it = {c.f[MB_PAI].p, kz};
+    if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :673
+    if (k_uvupdate(c, dts)) return 1;
+  }
+  return k_sfinish(c);
+}
+
+static int do_wafone_range(Ctx& c, int first, int count) {
+  const double dta = c.dtstepa;
+  const int kz = c.g.kz;
+  const long long fsz = (long long)kz * c.g.plane;
+  std::vector<HaloItem> items((size_t)count);
+  if (k_waf_z(c, first, count, dta)) return 1;
+  for (int q = 0; q < count; ++q) items[q] = {c.wzall + q * fsz, kz};
+  if (halo_exchange(c, items.data(), count, HS_CROSS, 2, false, true)) return 1;  // :924
+  if (k_waf_y(c, first, count, dta)) return 1;
+  for (int q = 0; q < count; ++q) items[q] = {c.p0all + q * fsz, kz};
+  if (halo_exchange(c, items.data(), count, HS_P0, 2, true, false)) return 1;  // :955/:1012
+  return k_waf_x(c, first, count, dta);
+}
+
+static int do_advection(Ctx& c) {
+  const int kz = c.g.kz;
+  HaloItem it;
+  it = {c.f[MB_U].p, kz};
+  if (halo_exchange(c, &it, 1, HS_U, 2, true, false)) return 1;  // :1532
+  it = {c.f[MB_V].p, kz};
+  if (halo_exchange(c, &it, 1, HS_V, 2, false, true)) return 1;  // :1533
+  if (k_destagger(c)) return 1;
+  if (do_wafone_range(c, 0, c.nadv_fields)) return 1;             // :786-807
+  if (k_curvature(c, c.dtstepa)) return 1;
+  it = {c.f[MB_UX].p, kz};
+  if (halo_exchange(c, &it, 1, HS_CROSS, 2, true, false)) return 1;  // :1485
+  it = {c.f[MB_VX].p, kz};
+  if (halo_exchange(c, &it, 1, HS_CROSS, 2, false, true)) return 1;  // :1486
+  return k_restagger(c, true);
+}
+
+static int do_dynamical_core(Ctx& c) {
+  for (int n = 0; n < c.cfg.mo_nadv; ++n) {
+    if (do_sound(c)) return 1;
+    if (do_advection(c)) return 1;
+  }
+  return k_tvirt_temp(c);
+}
+
+static int do_status_update(Ctx& c) {
+  const int kz = c.g.kz;
+  if (k_status_update(c, c.cfg.dtsec)) return 1;
+  HaloItem it;
+  it = {c.f[MB_UX].p, kz};
+  if (halo_exchange(c, &it, 1, HS_CROSS, 2, true, false)) return 1;
+  it = {c.f[MB_VX].p, kz};
+  if (halo_exchange(c, &it, 1, HS_CROSS, 2, false, true)) return 1;
+  return k_restagger(c, false);
+}
+
+static int require_init(Ctx* c) {
+  if (!c) return fail("null context");
+  if (!c->initialised) return fail("moloch_b200_init has not been called");
+  return 0;
+}
+
+}  // namespace mb
+
+using namespace mb;
+struct moloch_b200_ctx : public mb::Ctx {};
+
+extern "C" {
+
+const char* moloch_b200_last_error(void) { return g_err.c_str(); }
+int moloch_b200_abi_version(void) { return MOLOCH_B200_ABI_VERSION; }
+
+int moloch_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
+  if (!cfg || !out) return fail("moloch_b200_create: null argument");
+  *out = nullptr;
+  if (check_cfg(*cfg)) return 1;
+  int ndev = moloch_b200_device_count();
+  if (ndev <= 0) return fail("moloch_b200_create: no CUDA device available (there is no CPU fallback)");
+  moloch_b200_ctx* c = new moloch_b200_ctx();
+  c->cfg = *cfg;
+  c->device = (cfg->device >= 0) ? cfg->device : (cfg->rank % ndev);
+  if (cudaSetDevice(c->device) != cudaSuccess) {
+    delete c;
+    return fail("moloch_b200_create: cudaSetDevice failed");
+  }
+  build_geo(*c);
+  const Geo& g = c->g;
+  const int kz = g.kz;
+  // advected fields, in the reference's order :786-807
+  struct Adv { int fid; int spec; };
+  std::vector<Adv> adv = {{MB_TETAV, 0}, {MB_PAI, 0}, {MB_UX, 0}, {MB_VX, 0}, {MB_WX, 0}, {MB_QX, 0}};
+  if (cfg->ipptls > 0)
+    for (int n = cfg->iqfrst; n <= cfg->nqx; ++n) adv.push_back({MB_QX, n - 1});
+  for (int n = 1; n <= cfg->ntr; ++n) adv.push_back({MB_TRAC, n - 1});
+  c->nadv_fields = (int)adv.size();
+  // sizes
+  auto setf = [&](int id, int nk, int nspec, bool is2d) {
+    c->f[id].nk = nk; c->f[id].nspec = nspec; c->f[id].is2d = is2d; c->f[id].klo = 1;
+  };
+  for (int id : {MB_U, MB_V, MB_PAI, MB_TETAV, MB_T, MB_UX, MB_VX, MB_TVIRT, MB_P, MB_RHO, MB_QSAT, MB_ZETA,
+                 MB_FMZ, MB_RFMZU, MB_RFMZV, MB_BDYWTU, MB_BDYWTV, MB_BDYWTW, MB_TTEN, MB_UTEN, MB_VTEN,
+                 MB_ZDIV2, MB_WX, MB_TETAVF})
+    setf(id, kz, 1, false);
+  for (int id : {MB_W, MB_FMZF, MB_S}) setf(id, kz + 1, 1, false);
+  setf(MB_QX, kz, cfg->nqx, false); setf(MB_QXTEN, kz, cfg->nqx, false);
+  setf(MB_TRAC, kz, cfg->ntr, false); setf(MB_CHITEN, kz, cfg->ntr, false);
+  for (int id : {MB_PS, MB_HX, MB_HY, MB_MSFX, MB_MSFU, MB_MSFV, MB_CORU, MB_CORV}) setf(id, 1, 1, true);
+  setf(MB_WZ, kz, 1, false); setf(MB_P0, kz, 1, false);
+  const size_t pl = (size_t)g.plane * sizeof(double);
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  size_t total = 0;
+  std::vector<size_t> off(MB_NFIELDS, 0);
+  for (int id = 0; id < MB_NFIELDS; ++id) {
+    if (id == MB_WZ || id == MB_P0) continue;
+    off[id] = total;
+    total += al(pl * c->f[id].nk * (size_t)c->f[id].nspec);
+  }
+  const size_t o_ud = total; total += al(pl * kz);
+  const size_t o_vd = total; total += al(pl * kz);
+  const size_t o_zb = total; total += al(pl * kz);
+  const size_t o_ww = total; total += al(pl * (kz + 1));
+  const size_t o_2d = total; total += al(pl) * 4;
+  const size_t o_wz = total; total += al(pl * kz * (size_t)c->nadv_fields);
+  const size_t o_p0 = total; total += al(pl * kz * (size_t)c->nadv_fields);
+  const size_t o_prof = total;
+  const size_t prof_len = (size_t)((kz + 2 > (g.ide2 - g.ide1 + 3)) ? kz + 2 : (g.ide2 - g.ide1 + 3));
+  total += al(prof_len * sizeof(double)) * MB_NPROFILES;
+  const size_t o_tab = total; total += al(sizeof(double*) * (size_t)c->nadv_fields);
+  cudaError_t e = cudaMalloc(&c->arena, total);
+  if (e != cudaSuccess) {
+    std::string m = std::string("moloch_b200_create: cudaMalloc of ") + std::to_string(total) + " bytes: " +
+                    cudaGetErrorString(e);
+    delete c;
+    return fail(m);
+  }
+  c->arena_bytes = total;
+  cudaMemset(c->arena, 0, total);
+  for (int id = 0; id < MB_NFIELDS; ++id) {
+    if (id == MB_WZ || id == MB_P0) continue;
+    c->f[id].p = (c->f[id].nspec > 0) ? (double*)(c->arena + off[id]) : nullptr;
+  }
+  c->ud = (double*)(c->arena + o_ud); c->vd = (double*)(c->arena + o_vd);
+  c->zdiv2b = (double*)(c->arena + o_zb); c->wwkw = (double*)(c->arena + o_ww);
+  c->mx2 = (double*)(c->arena + o_2d); c->rmx = (double*)(c->arena + o_2d + al(pl));
+  c->rmu = (double*)(c->arena + o_2d + 2 * al(pl)); c->rmv = (double*)(c->arena + o_2d + 3 * al(pl));
+  c->wzall = (double*)(c->arena + o_wz); c->p0all = (double*)(c->arena + o_p0);
+  c->f[MB_WZ].p = c->wzall; c->f[MB_P0].p = c->p0all;
+  for (int q = 0; q < MB_NPROFILES; ++q) {
+    c->prof[q] = (double*)(c->arena + o_prof + (size_t)q * al(prof_len * sizeof(double)));
+    c->prof_n[q] = 0;
+  }
+  c->d_ptrtab = (double**)(c->arena + o_tab);
+  std::vector<double*> tab;
+  for (auto& a : adv) tab.push_back(c->f[a.fid].p + (size_t)a.spec * kz * g.plane);
+  cudaMemcpy(c->d_ptrtab, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaFree(c->arena);
+    delete c;
+    return fail("moloch_b200_create: cudaStreamCreate failed");
+  }
+  c->own_stream = true;
+  c->rdx = 1.0 / cfg->dx;              // Main/mod_params.F90:2193-2200
+  c->rdzita = 1.0 / cfg->mo_dzita;     // :275
+  c->dtstepa = cfg->dtsec / (double)cfg->mo_nadv;      // :306
+  c->dtsound = c->dtstepa / (double)cfg->mo_nsound;    // :307
+  *out = c;
+  return 0;
+}
+
+int moloch_b200_destroy(moloch_b200_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  halo_free(*c);
+  if (c->stage) cudaFree(c->stage);
+  if (c->arena) cudaFree(c->arena);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int moloch_b200_comm_id(void* id128) {
+  if (!id128) return fail("moloch_b200_comm_id: null argument");
+  return halo_comm_id(id128);
+}
+int moloch_b200_comm_init(moloch_b200_ctx* c, const void* id128) {
+  if (!c || !id128) return fail("moloch_b200_comm_init: null argument");
+  return halo_comm_init(*c, id128);
+}
+
+int moloch_b200_set_stream(moloch_b200_ctx* c, void* s) {
+  if (!c) return fail("null context");
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)s;
+  c->own_stream = false;
+  return 0;
+}
+int moloch_b200_sync(moloch_b200_ctx* c) {
+  if (!c) return fail("null context");
+  return sync_stream(*c);
+}
+
+static int xfer_field(moloch_b200_ctx* c, int field, int n, double* host, int jlo, int jhi, int ilo, int ihi,
+                      int klo, int khi, bool to_device) {
+  if (!c) return fail("null context");
+  if (field < 0 || field >= MB_NFIELDS) return fail("set/get_field: unknown field id");
+  if (!host) return fail("set/get_field: null host pointer");
+  Ctx::Field& f = c->f[field];
+  if (!f.p) return fail("set/get_field: field not allocated (ntr == 0?)");
+  int spec = 0;
+  if (f.nspec > 1 || field == MB_QX || field == MB_TRAC || field == MB_QXTEN || field == MB_CHITEN) {
+    if (n < 1 || n > f.nspec) return fail("set/get_field: species index out of range");
+    spec = n - 1;
+  }
+  if (jhi < jlo || ihi < ilo || khi < klo) return fail("set/get_field: empty bounds");
+  const Geo& g = c->g;
+  const int ja = jlo > g.j0 ? jlo : g.j0, jb = jhi < g.j0 + g.NJ - 1 ? jhi : g.j0 + g.NJ - 1;
+  const int ia = ilo > g.i0 ? ilo : g.i0, ib = ihi < g.i0 + g.NI - 1 ? ihi : g.i0 + g.NI - 1;
+  const int ka = klo > 1 ? klo : 1, kb = khi < f.nk ? khi : f.nk;
+  if (jb < ja || ib < ia || kb < ka) return 0;  // no overlap: nothing to move
+  MB_CUDA(cudaSetDevice(c->device));
+  double* dev = f.p + (size_t)spec * f.nk * g.plane;
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  cudaPitchedPtr hp = make_cudaPitchedPtr((void*)host, (size_t)(jhi - jlo + 1) * sizeof(double),
+                                          (size_t)(jhi - jlo + 1) * sizeof(double), (size_t)(ihi - ilo + 1));
+  cudaPitchedPtr dp = make_cudaPitchedPtr((void*)dev, (size_t)g.NJ * sizeof(double),
+                                          (size_t)g.NJ * sizeof(double), (size_t)g.NI);
+  cudaPos hpos = make_cudaPos((size_t)(ja - jlo) * sizeof(double), (size_t)(ia - ilo), (size_t)(ka - klo));
+  cudaPos dpos = make_cudaPos((size_t)(ja - g.j0) * sizeof(double), (size_t)(ia - g.i0), (size_t)(ka - 1));
+  p.extent = make_cudaExtent((size_t)(jb - ja + 1) * sizeof(double), (size_t)(ib - ia + 1), (size_t)(kb - ka + 1));
+  if (to_device) { p.srcPtr = hp; p.srcPos = hpos; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+  else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
+  MB_CUDA(cudaMemcpy3DAsync(&p, c->stream));
+  MB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int moloch_b200_set_field(moloch_b200_ctx* c, int field, int n, const double* host, int jlo, int jhi, int ilo,
+                          int ihi, int klo, int khi) {
+  return xfer_field(c, field, n, const_cast<double*>(host), jlo, jhi, ilo, ihi, klo, khi, true);
+}
+int moloch_b200_get_field(moloch_b200_ctx* c, int field, int n, double* host, int jlo, int jhi, int ilo,
+                          int ihi, int klo, int khi) {
+  return xfer_field(c, field, n, host, jlo, jhi, ilo, ihi, klo, khi, false);
+}
+
+int moloch_b200_set_profile(moloch_b200_ctx* c, int which, const double* v, int n) {
+  if (!c || !v) return fail("set_profile: null argument");
+  if (which < 0 || which >= MB_NPROFILES) return fail("set_profile: unknown profile id");
+  const Geo& g = c->g;
+  const int expect = (which == MB_GZITAK) ? g.kz + 1 : (which == MB_RLAT) ? (g.ide2 - g.ide1 + 2) : g.kz;
+  if (n != expect) return fail("set_profile: wrong length");
+  MB_CUDA(cudaSetDevice(c->device));
+  std::vector<double> tmp(v, v + n);
+  if (which == MB_RLAT) {
+    // init-time constant of the ROTLLR curvature term: sin(dlat(i)) with
+    // dlat = degrad*0.5*(rlat(i)+rlat(i+1)), Main/mod_moloch.F90:813-814
+    for (int i = 0; i + 1 < n; ++i) tmp[i] = sin(degrad * 0.5 * (v[i] + v[i + 1]));
+  }
+  // stored 1-based: element k of the Fortran array at [k]
+  MB_CUDA(cudaMemcpyAsync(c->prof[which] + 1, tmp.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
+                          c->stream));
+  MB_CUDA(cudaStreamSynchronize(c->stream));
+  c->prof_n[which] = n;
+  return 0;
+}
+
+int moloch_b200_host_alloc(void** p, uint64_t bytes) {
+  if (!p) return fail("host_alloc: null argument");
+  MB_CUDA(cudaHostAlloc(p, (size_t)bytes, cudaHostAllocDefault));
+  return 0;
+}
+int moloch_b200_host_free(void* p) {
+  if (p) MB_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+int moloch_b200_init(moloch_b200_ctx* c) {
+  if (!c) return fail("null context");
+  for (int q : {MB_GZITAK, MB_GZITAKH, MB_FFILT, MB_XKDAMP, MB_XKNU})
+    if (c->prof_n[q] == 0) return fail("moloch_b200_init: vertical profiles not set (gzitak, gzitakh, ffilt, xkdamp, xknu)");
+  if (c->cfg.lrotllr && c->prof_n[MB_RLAT] == 0) return fail("moloch_b200_init: rlat not set (ROTLLR)");
+  MB_CUDA(cudaSetDevice(c->device));
+  if (k_init_static(*c)) return 1;
+  if (sync_stream(*c)) return 1;
+  c->initialised = true;
+  return 0;
+}
+
+#define ENTRY(c)                                  \
+  if (require_init(c)) return 1;                  \
+  MB_CUDA(cudaSetDevice((c)->device));
+
+int moloch_b200_reset_tendencies(moloch_b200_ctx* c) { ENTRY(c) return k_reset_tendencies(*c); }
+int moloch_b200_sound(moloch_b200_ctx* c) { ENTRY(c) return do_sound(*c); }
+int moloch_b200_advection(moloch_b200_ctx* c) { ENTRY(c) return do_advection(*c); }
+int moloch_b200_wafone(moloch_b200_ctx* c, int field, int n) {
+  ENTRY(c)
+  if (field < 0 || field >= MB_NFIELDS || !c->f[field].p) return fail("wafone: unknown field");
+  int spec = 0;
+  if (field == MB_QX || field == MB_TRAC) {
+    if (n < 1 || n > c->f[field].nspec) return fail("wafone: species index out of range");
+    spec = n - 1;
+  }
+  double* want = c->f[field].p + (size_t)spec * c->g.kz * c->g.plane;
+  std::vector<double*> tab((size_t)c->nadv_fields);
+  MB_CUDA(cudaMemcpy(tab.data(), c->d_ptrtab, tab.size() * sizeof(double*), cudaMemcpyDeviceToHost));
+  for (int q = 0; q < c->nadv_fields; ++q)
+    if (tab[q] == want) return do_wafone_range(*c, q, 1);
+  return fail("wafone: field is not one of the advected fields");
+}
+int moloch_b200_dynamical_core(moloch_b200_ctx* c) { ENTRY(c) return do_dynamical_core(*c); }
+int moloch_b200_diagnostics(moloch_b200_ctx* c) { ENTRY(c) return k_diagnostics(*c); }
+int moloch_b200_status_update(moloch_b200_ctx* c) { ENTRY(c) return do_status_update(*c); }
+int moloch_b200_step(moloch_b200_ctx* c, int nsteps) {
+  ENTRY(c)
+  for (int n = 0; n < nsteps; ++n) {
+    if (k_reset_tendencies(*c)) return 1;
+    if (do_dynamical_core(*c)) return 1;
+    if (k_diagnostics(*c)) return 1;
+    if (do_status_update(*c)) return 1;
+  }
+  return 0;
+}
+
+int moloch_b200_profile_enable(moloch_b200_ctx* c, int on) {
+  if (!c) return fail("null context");
+  if (sync_stream(*c)) return 1;
+  for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  c->events.clear();
+  for (int q = 0; q < KID_COUNT; ++q) { c->prof_ms[q] = 0.0; c->prof_n_launch[q] = 0; }
+  c->profiling = on != 0;
+  return 0;
+}
+
+int moloch_b200_profile_read(moloch_b200_ctx* c, int cap, char (*names)[48], double* total_ms,
+                             int64_t* launches) {
+  if (!c) { fail("null context"); return -1; }
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { fail("profile_read: sync failed"); return -1; }
+  for (auto& ev : c->events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) {
+      c->prof_ms[ev.kid] += ms;
+      c->prof_n_launch[ev.kid] += 1;
+    }
+    cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+  }
+  c->events.clear();
+  int n = 0;
+  for (int q = 0; q < KID_COUNT; ++q) {
+    if (c->prof_n_launch[q] == 0) continue;
+    if (n < cap) {
+      strncpy(names[n], kernel_name(q), 47); names[n][47] = 0;
+      total_ms[n] = c->prof_ms[q];
+      launches[n] = c->prof_n_launch[q];
+    }
+    ++n;
+  }
+  return n;
+}
+
+int64_t moloch_b200_launch_count(moloch_b200_ctx* c, int reset) {
+  if (!c) return 0;
+  const int64_t v = c->launches;
+  if (reset) c->launches = 0;
+  return v;
+}
+uint64_t moloch_b200_device_bytes(moloch_b200_ctx* c) { return c ? (uint64_t)c->arena_bytes : 0; }
+
+int moloch_b200_halo_plan(const moloch_b200_config* cfg, int stag, int nex, int lr, int bt,
+                          int32_t send_box[4][4], int32_t recv_box[4][4]) {
+  if (!cfg || !send_box || !recv_box) return fail("halo_plan: null argument");
+  if (stag < 0 || stag > HS_P0 || nex < 1 || nex > 2) return fail("halo_plan: bad stag/nex");
+  halo_boxes(*cfg, stag, nex, lr != 0, bt != 0, send_box, recv_box);
+  return 0;
+}
+
+}  // extern "C"

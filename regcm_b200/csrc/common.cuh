@@ -1,0 +1,162 @@
+// common.cuh -- internal types of the B200 MOLOCH library (not part of the ABI).
+//
+// Data layout in HBM.  Every 2-D/3-D array of a rank -- cross, U, V or dot
+// staggered alike -- lives in the SAME padded box
+//     j in [j0, j0+NJ)   i in [i0, i0+NI)   k in [1, nk]
+// with j0 = jde1-HJ, i0 = ide1-HI, j fastest (RegCM's (j,i,k) order,
+// Main/mod_atm_interface.F90:579-624).  One linear offset therefore addresses
+// the same (j,i,k) in every array, ghost cells always exist (HJ=4, HI=3 >= the
+// reference's widest ghost of 2) and the first owned point of a row sits on a
+// 32-byte boundary (NJ is a multiple of 4 doubles, the arena is 256-B aligned).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/moloch_b200.h"
+
+namespace mb {
+
+constexpr int HJ = 4;
+constexpr int HI = 3;
+
+// physical constants: Share/mod_constants.F90:105-233 (non-RCEMIP branch)
+constexpr double egrav = 9.80665;
+constexpr double boltzk = 1.3806490e-23;
+constexpr double navgdr = 6.02214076e23;
+constexpr double amd = 28.96454;
+constexpr double amw = 18.01528;
+constexpr double rgasmol = navgdr * boltzk;
+constexpr double rgas = (rgasmol / amd) * 1000.0;
+constexpr double cpd = 3.5 * rgas;
+constexpr double cvd = 2.5 * rgas;
+constexpr double rdrcv = rgas / cvd;
+constexpr double cpovr = cpd / rgas;
+constexpr double govr = egrav / rgas;
+constexpr double govcp = egrav / cpd;
+constexpr double p00 = 1.0e5;
+constexpr double lrate = 0.00649;
+constexpr double tzero = 273.15;
+constexpr double ep1 = amd / amw - 1.0;
+constexpr double ep2 = amw / amd;
+constexpr double mathpi = 3.14159265358979323846;
+constexpr double degrad = mathpi / 180.0;
+constexpr double rearthrad = 1.0 / 6.371229e6;
+
+// Geometry of one rank, passed by value to every kernel.  Index ranges follow
+// setup_model_indexes (Main/mod_atm_interface.F90:182-382).
+struct Geo {
+  int NJ, NI, j0, i0;
+  long long plane;  // NJ*NI
+  int kz;
+  int jde1, jde2, ide1, ide2, jdi1, jdi2, idi1, idi2, jdii1, jdii2, idii1, idii2;
+  int jce1, jce2, ice1, ice2, jci1, jci2, ici1, ici2;
+  int gl, gr, gb, gt;  // 1 where a neighbour exists (ma%jbl1 ...)
+  int bl, br, bb, bt;  // ma%has_bdy*
+  int jmin, jmax, imin, imax;  // Main/mod_moloch.F90:280-293
+  int lrotllr, ipptls, nqx, ntr;
+};
+
+__host__ __device__ inline long long gidx(const Geo& g, int j, int i, int k) {
+  return (long long)(k - 1) * g.plane + (long long)(i - g.i0) * g.NJ + (j - g.j0);
+}
+__host__ __device__ inline long long gidx2(const Geo& g, int j, int i) {
+  return (long long)(i - g.i0) * g.NJ + (j - g.j0);
+}
+
+enum KernelId {
+  KID_RESET = 0, KID_TETAVF, KID_SOUND_PRE, KID_DIVDAMP, KID_WSOLVE, KID_UVUPDATE, KID_SFINISH,
+  KID_DESTAG, KID_WAF_Z, KID_WAF_Y, KID_WAF_X, KID_CURV, KID_RESTAG, KID_TVIRT, KID_DIAG, KID_PS,
+  KID_STATUS, KID_HALO, KID_HALO_PACK, KID_HALO_UNPACK, KID_INIT, KID_COUNT
+};
+
+struct ProfEvent { cudaEvent_t a, b; int kid; };
+
+struct Ctx;
+void halo_free(Ctx& c);
+
+struct Ctx {
+  moloch_b200_config cfg;
+  Geo g;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // arena
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  // field table: device pointer, number of levels, first level, species count
+  struct Field { double* p = nullptr; int nk = 0; int klo = 1; int nspec = 1; bool is2d = false; };
+  Field f[MB_NFIELDS];
+  // extra device arrays
+  double *ud, *vd, *zdiv2b, *wwkw, *mx2, *rmx, *rmu, *rmv;
+  double *wzall, *p0all;  // per-field scratch of the batched wafone
+  double* prof[MB_NPROFILES];
+  int prof_n[MB_NPROFILES];
+  double** d_ptrtab = nullptr;  // device table of field pointers (batched wafone)
+  int nadv_fields = 0;
+  // scalars (Main/mod_moloch.F90:306-307, :275)
+  double dtstepa, dtsound, rdx, rdzita;
+  bool initialised = false;
+  // halo transport
+  void* nccl_comm = nullptr;
+  double *sendbuf = nullptr, *recvbuf = nullptr;
+  size_t halo_buf_doubles = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<ProfEvent> events;
+  double prof_ms[KID_COUNT] = {0};
+  long long prof_n_launch[KID_COUNT] = {0};
+  long long launches = 0;
+  // staging for set/get
+  double* stage = nullptr;
+  size_t stage_doubles = 0;
+};
+
+extern thread_local std::string g_err;
+int fail(const std::string& msg);
+#define MB_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess)                                                             \
+      return mb::fail(std::string(#call) + ": " + cudaGetErrorString(e__));             \
+  } while (0)
+
+const char* kernel_name(int kid);
+
+// RAII-less launch bracket used by every launcher: counts the launch and, when
+// profiling, records CUDA events on the launching stream around it.
+struct LaunchScope {
+  Ctx& c; int kid; cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(Ctx& c_, int kid_);
+  ~LaunchScope();
+};
+
+// ---- launchers (kernels.cu) ------------------------------------------------
+int k_reset_tendencies(Ctx& c);
+int k_tetavf_init(Ctx& c);
+int k_sound_pre(Ctx& c, double dts);
+int k_divdamp_filter(Ctx& c, double dts);
+int k_wsolve(Ctx& c, double dts);
+int k_uvupdate(Ctx& c, double dts);
+int k_sfinish(Ctx& c);
+int k_destagger(Ctx& c);
+int k_waf_z(Ctx& c, int first, int count, double dta);
+int k_waf_y(Ctx& c, int first, int count, double dta);
+int k_waf_x(Ctx& c, int first, int count, double dta);
+int k_curvature(Ctx& c, double dta);
+int k_restagger(Ctx& c, bool with_w);
+int k_tvirt_temp(Ctx& c);
+int k_diagnostics(Ctx& c);
+int k_status_update(Ctx& c, double dtinc);
+int k_init_static(Ctx& c);
+
+// ---- halo exchange (halo.cu) ------------------------------------------------
+enum HaloStag { HS_CROSS = 0, HS_U, HS_V, HS_DOT, HS_P0 };
+struct HaloItem { double* p; int nk; };
+int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt);
+int halo_comm_init(Ctx& c, const void* id128);
+int halo_comm_id(void* id128);
+void halo_boxes(const moloch_b200_config& cfg, int stag, int nex, bool lr, bool bt,
+                int32_t send_box[4][4], int32_t recv_box[4][4]);
+
+}  // namespace mb

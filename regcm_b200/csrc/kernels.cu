@@ -1,0 +1,834 @@
+// kernels.cu -- sm_100a kernels of the MOLOCH dycore step.
+//
+// Every kernel restates one loop nest (or a fusion of adjacent loop nests) of
+// /root/reference/Main/mod_moloch.F90; the cited lines are of that file.
+// Arithmetic is FP64 with the reference's operation order and this file is
+// compiled with -fmad=false, so +,-,*,/ results are bit-identical to a
+// non-contracting CPU evaluation of the Fortran.
+#include "common.cuh"
+
+namespace mb {
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
+__device__ __forceinline__ double dmin(double a, double b) { return (b < a) ? b : a; }
+
+// local_flow_param :1571-1590 (minnum is a real(rk4) parameter)
+__device__ __forceinline__ double flow_param(double num, double den) {
+  const double minden = 1.0e-30;
+  const double minnum = (double)1.0e-30f;
+  if (fabs(den) < minden) return (fabs(num) < minnum) ? 1.0 : 0.0;
+  return num / den;
+}
+// zphi of the WAF limiter :882-883
+__device__ __forceinline__ double waf_phi(double rr, double zamu, double is) {
+  const double b = dmax(0.0, dmin(2.0, dmax(rr, dmin(2.0 * rr, 1.0))));
+  return is + zamu * b - is * b;
+}
+
+// Share/pfwsat.inc
+__device__ __forceinline__ double pfwsat(double t, double p) {
+  const double a0 = 0.611213476e+03, a1 = 0.444007856e+02, a2 = 0.143064234e+01, a3 = 0.264461437e-01,
+               a4 = 0.305903558e-03, a5 = 0.196237241e-05, a6 = 0.892344772e-08, a7 = -0.373208410e-10,
+               a8 = 0.209339997e-13;
+  const double c0 = 0.611123516e+03, c1 = 0.503109514e+02, c2 = 0.188369801e+01, c3 = 0.420547422e-01,
+               c4 = 0.614396778e-03, c5 = 0.602780717e-05, c6 = 0.387940929e-07, c7 = 0.149436277e-09,
+               c8 = 0.262655803e-12;
+  const double td = dmin(dmax(t - tzero, -75.0), 100.0);
+  double es;
+  if (td >= 0.0)
+    es = dmin(a0 + td * (a1 + td * (a2 + td * (a3 + td * (a4 + td * (a5 + td * (a6 + td * (a7 + td * a8))))))),
+              0.15 * p);
+  else
+    es = dmin(c0 + td * (c1 + td * (c2 + td * (c3 + td * (c4 + td * (c5 + td * (c6 + td * (c7 + td * c8))))))),
+              0.15 * p);
+  return ep2 * (es / (p - es));
+}
+
+// Main/mpplib/mod_runparams.F90:184-192
+__constant__ double c_qxcheckval[10] = {1.0e-8, 1.0e-16, 1.0e-16, 1.0e-16, 1.0e-16,
+                                        1.0e-16, 1.0e-16, 1.0e10, 100.0, 0.01};
+__constant__ double c_qxzeroval[10] = {1.0e-8, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0e10, 100.0, 0.01};
+
+#define IX(j, i, k) gidx(g, (j), (i), (k))
+#define IX2(j, i) gidx2(g, (j), (i))
+
+constexpr int BX = 32, BY = 8;
+static inline dim3 grid3(int nj, int ni, int nk) {
+  return dim3((unsigned)((nj + BX - 1) / BX), (unsigned)((ni + BY - 1) / BY), (unsigned)nk);
+}
+#define THREAD_JIK(jlo, ilo, klo)                      \
+  const int j = (jlo) + blockIdx.x * BX + threadIdx.x; \
+  const int i = (ilo) + blockIdx.y * BY + threadIdx.y; \
+  const int k = (klo) + blockIdx.z;
+
+__device__ __forceinline__ bool in_box(int j, int i, int j1, int j2, int i1, int i2) {
+  return j >= j1 && j <= j2 && i >= i1 && i <= i2;
+}
+
+// moist factor of temp_to_tvirt/tvirt_to_temp :1608-1648
+__device__ __forceinline__ double moist_factor(const Geo& g, const double* qx, long long id) {
+  const long long sp = (long long)g.kz * g.plane;
+  if (g.ipptls > 0) {
+    if (g.ipptls > 1) return 1.0 + ep1 * qx[id] - qx[id + sp] - qx[id + 2 * sp] - qx[id + 3 * sp] - qx[id + 4 * sp];
+    return 1.0 + ep1 * qx[id] - qx[id + sp];
+  }
+  return 1.0 + ep1 * qx[id];
+}
+
+// ---------------------------------------------------------------------------
+// K1  tetavf = 0.5*(tetav(k-1)+tetav(k))                              :564-566
+// ---------------------------------------------------------------------------
+__global__ void moloch_tetavf_init(Geo g, const double* __restrict__ tetav, double* __restrict__ tetavf) {
+  THREAD_JIK(g.jce1, g.ice1, 2)
+  if (j > g.jce2 || i > g.ice2) return;
+  const long long id = IX(j, i, k);
+  tetavf[id] = 0.5 * (tetav[id - g.plane] + tetav[id]);
+}
+int k_tetavf_init(Ctx& c) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_TETAVF);
+  moloch_tetavf_init<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz - 1), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_TETAV].p, c.f[MB_TETAVF].p);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K2+K3+K4  ud/vd snapshots, partial s, horizontal divergence zdiv2   :573-618
+// ---------------------------------------------------------------------------
+__global__ void moloch_sound_pre(Geo g, const double* __restrict__ u, const double* __restrict__ v,
+                                 double* __restrict__ ud, double* __restrict__ vd, double* __restrict__ s,
+                                 double* __restrict__ w, double* __restrict__ zdiv2,
+                                 const double* __restrict__ fmz, const double* __restrict__ rfmzu,
+                                 const double* __restrict__ rfmzv, const double* __restrict__ hx,
+                                 const double* __restrict__ hy, const double* __restrict__ mx,
+                                 const double* __restrict__ mx2, const double* __restrict__ rmu,
+                                 const double* __restrict__ rmv, const double* __restrict__ gzitak,
+                                 double dtrdx, double dtrdy) {
+  THREAD_JIK(g.jde1, g.ide1, 1)
+  if (j > g.jde2 || i > g.ide2) return;
+  const long long id = IX(j, i, k);
+  const long long i2 = IX2(j, i);
+  const int kz = g.kz;
+  const bool inu = (i >= g.ice1 && i <= g.ice2);
+  const bool inv = (j >= g.jce1 && j <= g.jce2);
+  const double u0 = u[id], v0 = v[id];
+  if (inu) ud[id] = u0;
+  if (inv) vd[id] = v0;
+  if (!(inu && inv)) return;
+  const double u1 = u[id + 1], v1 = v[id + g.NJ];
+  {
+    const double zvm = dtrdy * v0 * rfmzv[id] * rmv[i2];
+    const double zvp = dtrdy * v1 * rfmzv[id + g.NJ] * rmv[i2 + g.NJ];
+    if (g.lrotllr) {
+      const double zum = dtrdx * u0 * rfmzu[id];
+      const double zup = dtrdx * u1 * rfmzu[id + 1];
+      zdiv2[id] = fmz[id] * mx[i2] * ((zup - zum) + (zvp - zvm));
+    } else {
+      const double zum = dtrdx * u0 * rfmzu[id] * rmu[i2];
+      const double zup = dtrdx * u1 * rfmzu[id + 1] * rmu[i2 + 1];
+      zdiv2[id] = fmz[id] * mx2[i2] * ((zup - zum) + (zvp - zvm));
+    }
+  }
+  if (!in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) return;
+  const double hx0 = hx[i2], hx1 = hx[i2 + 1], hy0 = hy[i2], hy1 = hy[i2 + g.NJ];
+  if (k >= 2) {
+    const long long im = id - g.plane;
+    const double zuh = (u0 + u[im]) * hx0 + (u1 + u[im + 1]) * hx1;
+    const double zvh = (v0 + v[im]) * hy0 + (v1 + v[im + g.NJ]) * hy1;
+    s[id] = -0.25 * (zuh + zvh) * gzitak[k];
+  }
+  if (k == kz) {
+    const double zuh = u0 * hx0 + u1 * hx1;
+    const double zvh = v0 * hy0 + v1 * hy1;
+    const double sk = -0.5 * (zuh + zvh);
+    s[id + g.plane] = sk;
+    w[id + g.plane] = -sk;
+  }
+}
+int k_sound_pre(Ctx& c, double dts) {
+  const Geo& g = c.g;
+  const double dtrdx = dts * c.rdx, dtrdy = dts * c.rdx;
+  LaunchScope ls(c, KID_SOUND_PRE);
+  moloch_sound_pre<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_ZDIV2].p, c.f[MB_FMZ].p,
+      c.f[MB_RFMZU].p, c.f[MB_RFMZV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFX].p, c.mx2, c.rmu, c.rmv,
+      c.prof[MB_GZITAK], dtrdx, dtrdy);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K5+K6  divergence damping of u,v and 5-point filter of zdiv2   :738-765,531-543
+// zdiv2 (halo 1 valid) -> zdiv2b (interior); u,v updated in place.
+// ---------------------------------------------------------------------------
+__global__ void moloch_divdamp_filter(Geo g, double* __restrict__ u, double* __restrict__ v,
+                                      const double* __restrict__ zdiv2, double* __restrict__ zdiv2b,
+                                      const double* __restrict__ mu, const double* __restrict__ mv,
+                                      const double* __restrict__ xkdamp, const double* __restrict__ xknu,
+                                      double dxrdt, int do_damp, int do_filter) {
+  THREAD_JIK(g.jde1, g.ide1, 1)
+  if (j > g.jde2 || i > g.ide2) return;
+  const long long id = IX(j, i, k);
+  const long long i2 = IX2(j, i);
+  const double z0 = zdiv2[id];
+  const double zw = zdiv2[id - 1], zs = zdiv2[id - g.NJ];
+  if (do_damp) {
+    if (in_box(j, i, g.jdi1, g.jdi2, g.ici1, g.ici2)) {
+      const double xdam = dxrdt * xkdamp[k] * mu[i2];
+      u[id] = u[id] + xdam * (z0 - zw);
+    }
+    if (in_box(j, i, g.jci1, g.jci2, g.idi1, g.idi2)) {
+      const double xdam = g.lrotllr ? dxrdt * xkdamp[k] : dxrdt * xkdamp[k] * mv[i2];
+      v[id] = v[id] + xdam * (z0 - zs);
+    }
+  }
+  if (do_filter && in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) {
+    const double lap = (zw + zdiv2[id + 1] + zs + zdiv2[id + g.NJ] - 4.0 * z0);
+    zdiv2b[id] = z0 + xknu[k] * lap;
+  }
+}
+int k_divdamp_filter(Ctx& c, double dts) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_DIVDAMP);
+  moloch_divdamp_filter<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_ZDIV2].p, c.zdiv2b, c.f[MB_MSFU].p, c.f[MB_MSFV].p,
+      c.prof[MB_XKDAMP], c.prof[MB_XKNU], c.cfg.dx / dts, c.cfg.mo_divdamp, c.cfg.mo_divfilter);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K7+K8+K9  vertical part of the divergence, implicit w (Thomas sweeps), new
+// Exner function                                                     :627-671
+// One thread per column; the finished divergence of the column is parked in
+// shared memory (thread-private slots, no barriers).
+// ---------------------------------------------------------------------------
+constexpr int WS_TB = 64;
+__global__ void __launch_bounds__(WS_TB)
+moloch_wsolve(Geo g, const double* __restrict__ zdiv, const double* __restrict__ s, double* __restrict__ w,
+              double* __restrict__ pai, const double* __restrict__ tetav, double* __restrict__ tetavf,
+              double* __restrict__ wwkw, const double* __restrict__ fmz, const double* __restrict__ fmzf,
+              const double* __restrict__ bdywtw, const double* __restrict__ ffilt, double dts, double dtrdz,
+              double zcs2) {
+  extern __shared__ double sm[];
+  const int nj = g.jci2 - g.jci1 + 1, ni = g.ici2 - g.ici1 + 1;
+  const long long col = (long long)blockIdx.x * WS_TB + threadIdx.x;
+  if (col >= (long long)nj * ni) return;
+  const int i = g.ici1 + (int)(col / nj), j = g.jci1 + (int)(col % nj);
+  const int kz = g.kz;
+  double* zd_s = sm + threadIdx.x;  // zd_s[(k-1)*WS_TB]
+  const long long base = IX(j, i, 1);
+  const long long pl = g.plane;
+  // :627-630  (s(k)-s(k+1))
+  {
+    double sk = s[base];
+    for (int k = 1; k <= kz; ++k) {
+      const long long id = base + (k - 1) * pl;
+      const double sk1 = s[id + pl];
+      zd_s[(k - 1) * WS_TB] = zdiv[id] + bdywtw[id] * dtrdz * fmz[id] * (sk - sk1);
+      sk = sk1;
+    }
+  }
+  // :634-656  downward sweep
+  double wkp1 = w[base + (long long)kz * pl];  // w(kzp1)
+  double wwkp1 = 0.0;                          // wwkw(kzp1) :1055-1057
+  double tv_k = tetav[base + (long long)(kz - 1) * pl];
+  double pai_k = pai[base + (long long)(kz - 1) * pl];
+  for (int k = kz; k >= 2; --k) {
+    const long long id = base + (k - 1) * pl;
+    const double tv_km1 = tetav[id - pl], pai_km1 = pai[id - pl];
+    const double wk = w[id], fmzfk = fmzf[id];
+    const double tf = tetavf[id] - wk * fmzfk * dtrdz * (tv_km1 - tv_k);
+    tetavf[id] = tf;
+    const double zrom1w = cpd * tf * fmzfk;
+    double zwexpl = wk - zrom1w * dtrdz * (pai_km1 - pai_k) - egrav * dts;
+    zwexpl = zwexpl + rdrcv * zrom1w * dtrdz * (pai_km1 * zd_s[(k - 2) * WS_TB] - pai_k * zd_s[(k - 1) * WS_TB]);
+    const double zu = zcs2 * fmz[id - pl] * zrom1w * pai_km1 + ffilt[k];
+    const double zd = zcs2 * fmz[id] * zrom1w * pai_k + ffilt[k];
+    const double zrapp = 1.0 / (1.0 + zd + zu - zd * wwkp1);
+    wkp1 = zrapp * (zwexpl + zd * wkp1);
+    wwkp1 = zrapp * zu;
+    w[id] = wkp1;
+    wwkw[id] = wwkp1;
+    tv_k = tv_km1; pai_k = pai_km1;
+  }
+  // :660-671  upward sweep + Exner update.  pai(k) needs w(k), w(k+1) final.
+  double wkm1 = w[base];  // w(1)
+  for (int k = 2; k <= kz; ++k) {
+    const long long id = base + (k - 1) * pl;
+    const double wk = w[id] + wwkw[id] * wkm1;
+    w[id] = wk;
+    // pai(k-1) with w(k-1), w(k)
+    const long long im = id - pl;
+    pai[im] = pai[im] * (1.0 - rdrcv * (zd_s[(k - 2) * WS_TB] + (dtrdz * fmz[im] * (wkm1 - wk))));
+    wkm1 = wk;
+  }
+  {
+    const long long id = base + (long long)(kz - 1) * pl;
+    const double wkzp1 = w[id + pl];
+    pai[id] = pai[id] * (1.0 - rdrcv * (zd_s[(kz - 1) * WS_TB] + (dtrdz * fmz[id] * (wkm1 - wkzp1))));
+  }
+}
+int k_wsolve(Ctx& c, double dts) {
+  const Geo& g = c.g;
+  const double dtrdz = dts * c.rdzita;
+  const double zcs2 = (dtrdz * dtrdz) * rdrcv;
+  const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
+  const size_t smem = (size_t)g.kz * WS_TB * sizeof(double);
+  const double* zsrc = c.cfg.mo_divfilter ? c.zdiv2b : c.f[MB_ZDIV2].p;
+  MB_CUDA(cudaFuncSetAttribute(moloch_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchScope ls(c, KID_WSOLVE);
+  moloch_wsolve<<<(unsigned)((ncol + WS_TB - 1) / WS_TB), WS_TB, smem, c.stream>>>(
+      g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.wwkw,
+      c.f[MB_FMZ].p, c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K10  horizontal momentum update                                    :677-721
+// ---------------------------------------------------------------------------
+__global__ void moloch_uvupdate(Geo g, double* __restrict__ u, double* __restrict__ v,
+                                const double* __restrict__ ud, const double* __restrict__ vd,
+                                const double* __restrict__ tetav, const double* __restrict__ pai,
+                                const double* __restrict__ bdywtu, const double* __restrict__ bdywtv,
+                                const double* __restrict__ coru, const double* __restrict__ corv,
+                                const double* __restrict__ hx, const double* __restrict__ hy,
+                                const double* __restrict__ mu, const double* __restrict__ mv,
+                                const double* __restrict__ gzitakh, double dts, double dtrdx, double dtrdy) {
+  THREAD_JIK(g.jde1, g.ide1, 1)
+  if (j > g.jde2 || i > g.ide2) return;
+  const bool du = in_box(j, i, g.jdi1, g.jdi2, g.ici1, g.ici2);
+  const bool dv = in_box(j, i, g.jci1, g.jci2, g.idi1, g.idi2);
+  if (!du && !dv) return;
+  const long long id = IX(j, i, k);
+  const long long i2 = IX2(j, i);
+  const double tv0 = tetav[id], pai0 = pai[id];
+  const double zfz = egrav * dts;
+  const double gk = gzitakh[k];
+  if (du) {
+    const double zcx = dtrdx * mu[i2];
+    const double zrom1u = 0.5 * cpd * (tetav[id - 1] + tv0);
+    const double zcor1u = coru[i2] * dts * vd[id];
+    u[id] = u[id] + bdywtu[id] * (zcor1u - zfz * hx[i2] * gk - zcx * zrom1u * (pai0 - pai[id - 1]));
+  }
+  if (dv) {
+    const double zcy = g.lrotllr ? dtrdy : dtrdy * mv[i2];
+    const double zrom1v = 0.5 * cpd * (tetav[id - g.NJ] + tv0);
+    const double zcor1v = corv[i2] * dts * ud[id];
+    v[id] = v[id] + bdywtv[id] * (-zcor1v - zfz * hy[i2] * gk - zcy * zrom1v * (pai0 - pai[id - g.NJ]));
+  }
+}
+int k_uvupdate(Ctx& c, double dts) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_UVUPDATE);
+  moloch_uvupdate<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_BDYWTU].p,
+      c.f[MB_BDYWTV].p, c.f[MB_CORU].p, c.f[MB_CORV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFU].p,
+      c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K11  s = (w+s)*fmzf, s(1)=s(kzp1)=0                                 :728-734
+// ---------------------------------------------------------------------------
+__global__ void moloch_sfinish(Geo g, double* __restrict__ s, const double* __restrict__ w,
+                               const double* __restrict__ fmzf) {
+  THREAD_JIK(g.jci1, g.ici1, 1)
+  if (j > g.jci2 || i > g.ici2) return;
+  const long long id = IX(j, i, k);
+  if (k == 1 || k == g.kz + 1) s[id] = 0.0;
+  else s[id] = (w[id] + s[id]) * fmzf[id];
+}
+int k_sfinish(Ctx& c) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_SFINISH);
+  moloch_sfinish<<<grid3(g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, g.kz + 1), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_FMZF].p);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K12+K13  uvstagtouvx :1537-1567 and zstagtoh :1451-1458
+// ---------------------------------------------------------------------------
+__global__ void moloch_destagger(Geo g, const double* __restrict__ u, const double* __restrict__ v,
+                                 const double* __restrict__ w, double* __restrict__ ux,
+                                 double* __restrict__ vx, double* __restrict__ wx) {
+  THREAD_JIK(g.jce1, g.ice1, 1)
+  if (j > g.jce2 || i > g.ice2) return;
+  const long long id = IX(j, i, k);
+  const int kz = g.kz;
+  // ux on jci1:jci2 (4th order) and the physical-boundary columns (2nd order)
+  if (j >= g.jci1 && j <= g.jci2) {
+    ux[id] = 0.5625 * (u[id + 1] + u[id]) - 0.0625 * (u[id + 2] + u[id - 1]);
+  } else {
+    // j == jce1 with has_bdyleft: u(jde1),u(jdi1) = u(j),u(j+1); j == jce2 with
+    // has_bdyright: u(jde2),u(jdi2) = u(j+1),u(j)
+    if (j == g.jce1) ux[id] = 0.5 * (u[id] + u[id + 1]);
+    else ux[id] = 0.5 * (u[id + 1] + u[id]);
+  }
+  if (i >= g.ici1 && i <= g.ici2) {
+    vx[id] = 0.5625 * (v[id + g.NJ] + v[id]) - 0.0625 * (v[id + 2 * g.NJ] + v[id - g.NJ]);
+  } else {
+    if (i == g.ice1) vx[id] = 0.5 * (v[id] + v[id + g.NJ]);
+    else vx[id] = 0.5 * (v[id + g.NJ] + v[id]);
+  }
+  const long long pl = g.plane;
+  if (k == 1) wx[id] = 0.5 * (w[id + pl] + w[id]);
+  else if (k == kz) wx[id] = 0.5 * (w[id + pl] + w[id]);
+  else wx[id] = 0.5625 * (w[id + pl] + w[id]) - 0.0625 * (w[id + 2 * pl] + w[id - pl]);
+}
+int k_destagger(Ctx& c) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_DESTAG);
+  moloch_destagger<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_W].p, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_WX].p);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K14  wafone vertical advection, twice with dt/2                     :863-922
+// One thread per column; the column is staged in shared memory (thread-private
+// slots), both half-steps run on it and only wz goes back to HBM.
+// ---------------------------------------------------------------------------
+constexpr int WZ_TB = 64;
+__device__ __forceinline__ void waf_vertical_pass(const Geo& g, const double* q, double* out,
+                                                  const double* __restrict__ s,
+                                                  const double* __restrict__ fmz,
+                                                  const double* __restrict__ fmzf, long long base,
+                                                  double dtrdz) {
+  // q, out: shared-memory columns with stride WZ_TB, level k at [(k-1)*WZ_TB]
+  const int kz = g.kz;
+  const long long pl = g.plane;
+  double fprev = 0.0;  // wfw(1) = 0 :864
+  double sk = s[base];
+  double fmzfk = fmzf[base];
+  for (int k = 1; k <= kz; ++k) {
+    const long long id = base + (k - 1) * pl;
+    const double sk1 = s[id + pl];
+    const double fmzfk1 = fmzf[id + pl];
+    const double qk = q[(k - 1) * WZ_TB];
+    double fnext = 0.0;  // wfw(kzp1) = 0 :865
+    if (k < kz) {
+      const double zamu = sk1 * dtrdz;
+      double is; int k1, k1p1;
+      if (zamu >= 0.0) { is = 1.0; k1 = k + 1; k1p1 = k1 + 1; if (k1p1 > kz) k1p1 = kz; }
+      else { is = -1.0; k1 = k - 1; k1p1 = k; if (k1 < 1) k1 = 1; }
+      const double qk1 = q[k * WZ_TB];
+      const double rr = flow_param(q[(k1 - 1) * WZ_TB] - q[(k1p1 - 1) * WZ_TB], qk - qk1);
+      const double zphi = waf_phi(rr, zamu, is);
+      fnext = 0.5 * sk1 * ((1.0 + zphi) * qk1 + (1.0 - zphi) * qk);
+    }
+    const double fm = fmz[id];
+    const double zrfmu = dtrdz * fm / fmzfk;
+    const double zrfmd = dtrdz * fm / fmzfk1;
+    const double zdv = (sk * zrfmu - sk1 * zrfmd) * qk;
+    out[(k - 1) * WZ_TB] = qk - fprev * zrfmu + fnext * zrfmd + zdv;
+    fprev = fnext; sk = sk1; fmzfk = fmzfk1;
+  }
+}
+__global__ void __launch_bounds__(WZ_TB)
+moloch_waf_vertical(Geo g, double* const* __restrict__ tab, int first, double* __restrict__ wzall,
+                    const double* __restrict__ s, const double* __restrict__ fmz,
+                    const double* __restrict__ fmzf, double dtrdz) {
+  extern __shared__ double sm[];
+  const int nj = g.jce2 - g.jce1 + 1, ni = g.ice2 - g.ice1 + 1;
+  const long long col = (long long)blockIdx.x * WZ_TB + threadIdx.x;
+  if (col >= (long long)nj * ni) return;
+  const int i = g.ice1 + (int)(col / nj), j = g.jce1 + (int)(col % nj);
+  const int kz = g.kz;
+  const double* __restrict__ pp = tab[first + blockIdx.y];
+  double* __restrict__ wz = wzall + (long long)blockIdx.y * kz * g.plane;
+  double* a = sm + threadIdx.x;
+  double* b = sm + (size_t)kz * WZ_TB + threadIdx.x;
+  const long long base = IX(j, i, 1);
+  for (int k = 1; k <= kz; ++k) a[(k - 1) * WZ_TB] = pp[base + (k - 1) * g.plane];
+  waf_vertical_pass(g, a, b, s, fmz, fmzf, base, dtrdz);
+  waf_vertical_pass(g, b, a, s, fmz, fmzf, base, dtrdz);  // do_vadvtwice :894
+  for (int k = 1; k <= kz; ++k) wz[base + (k - 1) * g.plane] = a[(k - 1) * WZ_TB];
+}
+int k_waf_z(Ctx& c, int first, int count, double dta) {
+  const Geo& g = c.g;
+  const double dtrdz = 0.5 * (dta * c.rdzita);  // :857-860
+  const long long ncol = (long long)(g.jce2 - g.jce1 + 1) * (g.ice2 - g.ice1 + 1);
+  const size_t smem = (size_t)2 * g.kz * WZ_TB * sizeof(double);
+  MB_CUDA(cudaFuncSetAttribute(moloch_waf_vertical, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchScope ls(c, KID_WAF_Z);
+  moloch_waf_vertical<<<dim3((unsigned)((ncol + WZ_TB - 1) / WZ_TB), (unsigned)count), WZ_TB, smem, c.stream>>>(
+      g, c.d_ptrtab, first, c.wzall, c.f[MB_S].p, c.f[MB_FMZ].p, c.f[MB_FMZF].p, dtrdz);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K15  wafone meridional flux + update -> p0                :929-953 / :987-1010
+// The flux at a V face is recomputed by the two cells that share it (no zpby
+// array in HBM); both evaluations are bit-identical.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double waf_flux_y(const Geo& g, const double* __restrict__ wz,
+                                             const double* __restrict__ v, const double* __restrict__ mv,
+                                             int j, int i, int k, double dtrdy) {
+  const long long id = IX(j, i, k);
+  const double vv = v[id];
+  const double zamu = g.lrotllr ? vv * dtrdy : vv * mv[IX2(j, i)] * dtrdy;
+  double is; int ih;
+  if (zamu > 0.0) { is = 1.0; ih = i - 1; } else { is = -1.0; ih = min(i + 1, g.imax); }
+  const int ihm1 = max(ih - 1, g.imin);
+  const double w0 = wz[id], wm = wz[id - g.NJ];
+  const double rr = flow_param(wz[IX(j, ih, k)] - wz[IX(j, ihm1, k)], w0 - wm);
+  const double zphi = waf_phi(rr, zamu, is);
+  return 0.5 * vv * ((1.0 + zphi) * wm + (1.0 - zphi) * w0);
+}
+__global__ void moloch_waf_meridional(Geo g, double* const* __restrict__ tab, int first,
+                                      const double* __restrict__ wzall, double* __restrict__ p0all,
+                                      const double* __restrict__ v, const double* __restrict__ fmz,
+                                      const double* __restrict__ rfmzu, const double* __restrict__ rfmzv,
+                                      const double* __restrict__ mx, const double* __restrict__ mx2,
+                                      const double* __restrict__ mv, const double* __restrict__ rmv,
+                                      double dtrdy) {
+  const int kz = g.kz;
+  const int j = g.jce1 + blockIdx.x * BX + threadIdx.x;
+  const int i = g.ici1 + blockIdx.y * BY + threadIdx.y;
+  const int fld = blockIdx.z / kz, k = 1 + blockIdx.z % kz;
+  if (j > g.jce2 || i > g.ici2) return;
+  const double* __restrict__ pp = tab[first + fld];
+  const double* __restrict__ wz = wzall + (long long)fld * kz * g.plane;
+  double* __restrict__ p0 = p0all + (long long)fld * kz * g.plane;
+  const long long id = IX(j, i, k);
+  const long long i2 = IX2(j, i);
+  const double fs = waf_flux_y(g, wz, v, mv, j, i, k, dtrdy);
+  const double fn = waf_flux_y(g, wz, v, mv, j, i + 1, k, dtrdy);
+  if (g.lrotllr) {
+    const double zhxvtn = dtrdy * rmv[i2 + g.NJ] * mx[i2];
+    const double zhxvts = dtrdy * rmv[i2] * mx[i2];
+    const double zrfmn = zhxvtn * fmz[id] * rfmzv[id + g.NJ];
+    const double zrfms = zhxvts * fmz[id] * rfmzv[id];
+    const double zdv = (v[id + g.NJ] * zrfmn - v[id] * zrfms) * pp[id];
+    p0[id] = wz[id] + (fs * zrfms - fn * zrfmn + zdv);
+  } else {
+    const double zrfmn = dtrdy * fmz[id] * rfmzu[id + g.NJ];  // sic: rfmzu :1004-1005
+    const double zrfms = dtrdy * fmz[id] * rfmzu[id];
+    const double zdv = (v[id + g.NJ] * rmv[i2 + g.NJ] * zrfmn - v[id] * rmv[i2] * zrfms) * pp[id];
+    p0[id] = wz[id] + mx2[i2] * (fs * zrfms - fn * zrfmn + zdv);
+  }
+}
+int k_waf_y(Ctx& c, int first, int count, double dta) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_WAF_Y);
+  moloch_waf_meridional<<<grid3(g.jce2 - g.jce1 + 1, g.ici2 - g.ici1 + 1, g.kz * count), dim3(BX, BY), 0,
+                          c.stream>>>(g, c.d_ptrtab, first, c.wzall, c.p0all, c.f[MB_V].p, c.f[MB_FMZ].p,
+                                      c.f[MB_RFMZU].p, c.f[MB_RFMZV].p, c.f[MB_MSFX].p, c.mx2,
+                                      c.f[MB_MSFV].p, c.rmv, dta * c.rdx);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K16  wafone zonal flux + update -> pp                    :959-982 / :1015-1038
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double waf_flux_x(const Geo& g, const double* __restrict__ p0,
+                                             const double* __restrict__ u, const double* __restrict__ mu,
+                                             int j, int i, int k, double dtrdx) {
+  const long long id = IX(j, i, k);
+  const double uu = u[id];
+  const double zamu = uu * mu[IX2(j, i)] * dtrdx;
+  double is; int jh;
+  if (zamu > 0.0) { is = 1.0; jh = j - 1; } else { is = -1.0; jh = min(j + 1, g.jmax); }
+  const int jhm1 = max(jh - 1, g.jmin);
+  const double q0 = p0[id], qm = p0[id - 1];
+  const double rr = flow_param(p0[IX(jh, i, k)] - p0[IX(jhm1, i, k)], q0 - qm);
+  const double zphi = waf_phi(rr, zamu, is);
+  return 0.5 * uu * ((1.0 + zphi) * qm + (1.0 - zphi) * q0);
+}
+__global__ void moloch_waf_zonal(Geo g, double* const* __restrict__ tab, int first,
+                                 const double* __restrict__ p0all, const double* __restrict__ u,
+                                 const double* __restrict__ fmz, const double* __restrict__ rfmzu,
+                                 const double* __restrict__ mx, const double* __restrict__ mx2,
+                                 const double* __restrict__ mu, const double* __restrict__ rmu,
+                                 double dtrdx) {
+  const int kz = g.kz;
+  const int j = g.jci1 + blockIdx.x * BX + threadIdx.x;
+  const int i = g.ici1 + blockIdx.y * BY + threadIdx.y;
+  const int fld = blockIdx.z / kz, k = 1 + blockIdx.z % kz;
+  if (j > g.jci2 || i > g.ici2) return;
+  double* __restrict__ pp = tab[first + fld];
+  const double* __restrict__ p0 = p0all + (long long)fld * kz * g.plane;
+  const long long id = IX(j, i, k);
+  const long long i2 = IX2(j, i);
+  const double fw = waf_flux_x(g, p0, u, mu, j, i, k, dtrdx);
+  const double fe = waf_flux_x(g, p0, u, mu, j + 1, i, k, dtrdx);
+  if (g.lrotllr) {
+    const double zcostx = dtrdx * mx[i2];
+    const double zrfmw = zcostx * fmz[id] * rfmzu[id];
+    const double zrfme = zcostx * fmz[id] * rfmzu[id + 1];
+    const double zdv = (u[id + 1] * zrfme - u[id] * zrfmw) * pp[id];
+    pp[id] = p0[id] + fw * zrfmw - fe * zrfme + zdv;
+  } else {
+    const double zrfmw = dtrdx * fmz[id] * rfmzu[id];
+    const double zrfme = dtrdx * fmz[id] * rfmzu[id + 1];
+    const double zdv = (u[id + 1] * rmu[i2 + 1] * zrfme - u[id] * rmu[i2] * zrfmw) * pp[id];
+    pp[id] = p0[id] + mx2[i2] * (fw * zrfmw - fe * zrfme + zdv);
+  }
+}
+int k_waf_x(Ctx& c, int first, int count, double dta) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_WAF_X);
+  moloch_waf_zonal<<<grid3(g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, g.kz * count), dim3(BX, BY), 0, c.stream>>>(
+      g, c.d_ptrtab, first, c.p0all, c.f[MB_U].p, c.f[MB_FMZ].p, c.f[MB_RFMZU].p, c.f[MB_MSFX].p, c.mx2,
+      c.f[MB_MSFU].p, c.rmu, dta * c.rdx);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K17  curvature terms                                                :811-825
+// ---------------------------------------------------------------------------
+__global__ void moloch_curvature(Geo g, double* __restrict__ ux, double* __restrict__ vx,
+                                 const double* __restrict__ mx, const double* __restrict__ mu,
+                                 const double* __restrict__ mv, const double* __restrict__ rlat, double rdx,
+                                 double dta) {
+  THREAD_JIK(g.jci1, g.ici1, 1)
+  if (j > g.jci2 || i > g.ici2) return;
+  const long long id = IX(j, i, k);
+  const long long i2 = IX2(j, i);
+  double tanx, tany;
+  if (g.lrotllr) {
+    // the MB_RLAT slot holds sin(degrad*0.5*(rlat(i)+rlat(i+1))), 1-based from
+    // i = ide1, evaluated once on the host at set_profile time (:813-814)
+    tanx = rlat[i - g.ide1 + 1] * mx[i2] * rearthrad;
+    tany = tanx;
+  } else {
+    tanx = (mu[i2 - 1] - mu[i2]) * rdx;
+    tany = (mv[i2 - g.NJ] - mv[i2]) * rdx;
+  }
+  const double uxn = ux[id] + ux[id] * vx[id] * tanx * dta;
+  ux[id] = uxn;
+  vx[id] = vx[id] - uxn * uxn * tany * dta;
+}
+int k_curvature(Ctx& c, double dta) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_CURV);
+  moloch_curvature<<<grid3(g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_MSFX].p, c.f[MB_MSFU].p, c.f[MB_MSFV].p, c.prof[MB_RLAT], c.rdx,
+      dta);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K18+K19  uvxtouvstag :1490-1520 and htozstag :1467-1474
+// ---------------------------------------------------------------------------
+__global__ void moloch_restagger(Geo g, const double* __restrict__ ux, const double* __restrict__ vx,
+                                 const double* __restrict__ wx, double* __restrict__ u,
+                                 double* __restrict__ v, double* __restrict__ w, int with_w) {
+  THREAD_JIK(g.jde1, g.ide1, 1)
+  if (j > g.jde2 || i > g.ide2) return;
+  const long long id = IX(j, i, k);
+  const int kz = g.kz;
+  if (i >= g.ici1 && i <= g.ici2) {
+    if (j >= g.jdii1 && j <= g.jdii2) {
+      u[id] = 0.5625 * (ux[id] + ux[id - 1]) - 0.0625 * (ux[id + 1] + ux[id - 2]);
+    } else if (g.br && j == g.jdi2) {
+      u[id] = 0.5 * (ux[id - 1] + ux[id]);  // ux(jci2), ux(jce2) = ux(j-1), ux(j)
+    } else if (g.bl && j == g.jdi1) {
+      u[id] = 0.5 * (ux[id] + ux[id - 1]);  // ux(jci1), ux(jce1) = ux(j), ux(j-1)
+    }
+  }
+  if (j >= g.jci1 && j <= g.jci2) {
+    if (i >= g.idii1 && i <= g.idii2) {
+      v[id] = 0.5625 * (vx[id] + vx[id - g.NJ]) - 0.0625 * (vx[id + g.NJ] + vx[id - 2 * g.NJ]);
+    } else if (g.bt && i == g.idi2) {
+      v[id] = 0.5 * (vx[id - g.NJ] + vx[id]);
+    } else if (g.bb && i == g.idi1) {
+      v[id] = 0.5 * (vx[id] + vx[id - g.NJ]);
+    }
+  }
+  if (with_w && j <= g.jce2 && i <= g.ice2 && k >= 2) {
+    const long long pl = g.plane;
+    if (k == 2) w[id] = 0.5 * (wx[id] + wx[id - pl]);
+    else if (k == kz) w[id] = 0.5 * (wx[id] + wx[id - pl]);
+    else w[id] = 0.5625 * (wx[id] + wx[id - pl]) - 0.0625 * (wx[id + pl] + wx[id - 2 * pl]);
+  }
+}
+int k_restagger(Ctx& c, bool with_w) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_RESTAG);
+  moloch_restagger<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_WX].p, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_W].p, with_w ? 1 : 0);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K20  tvirt = tetav*pai, t = tvirt/moist                  :1121-1125,:1629-1648
+// ---------------------------------------------------------------------------
+__global__ void moloch_tvirt_temp(Geo g, const double* __restrict__ tetav, const double* __restrict__ pai,
+                                  const double* __restrict__ qx, double* __restrict__ tvirt,
+                                  double* __restrict__ t) {
+  THREAD_JIK(g.jce1, g.ice1, 1)
+  if (j > g.jce2 || i > g.ice2) return;
+  const long long id = IX(j, i, k);
+  const double tv = tetav[id] * pai[id];
+  tvirt[id] = tv;
+  if (in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) t[id] = tv / moist_factor(g, qx, id);
+}
+int k_tvirt_temp(Ctx& c) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_TVIRT);
+  moloch_tvirt_temp<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_QX].p, c.f[MB_TVIRT].p, c.f[MB_T].p);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K21  p, rho, qsat :348-352 and extrapolate_surface_pressure :1592-1606
+// ---------------------------------------------------------------------------
+__global__ void moloch_diag_prq(Geo g, const double* __restrict__ pai, const double* __restrict__ t,
+                                double* __restrict__ p, double* __restrict__ rho, double* __restrict__ qsat) {
+  THREAD_JIK(g.jce1, g.ice1, 1)
+  if (j > g.jce2 || i > g.ice2) return;
+  const long long id = IX(j, i, k);
+  const double pp = pow(pai[id], cpovr) * p00;
+  const double tt = t[id];
+  p[id] = pp;
+  rho[id] = pp / (rgas * tt);
+  qsat[id] = pfwsat(tt, pp);
+}
+__global__ void moloch_diag_ps(Geo g, const double* __restrict__ tvirt, const double* __restrict__ z,
+                               const double* __restrict__ p, double* __restrict__ ps) {
+  const int j = g.jci1 + blockIdx.x * BX + threadIdx.x;
+  const int i = g.ici1 + blockIdx.y * BY + threadIdx.y;
+  if (j > g.jci2 || i > g.ici2) return;
+  const int kz = g.kz;
+  const long long a = IX(j, i, kz), b = IX(j, i, kz - 1);
+  double lrt = (tvirt[b] - tvirt[a]) / (z[b] - z[a]);
+  if (lrt < -govcp) lrt = -govcp;
+  else if (lrt > -0.005) lrt = 0.65 * lrt - 0.35 * lrate;
+  const double tv = tvirt[a] - lrt * 0.5 * z[a];
+  ps[IX2(j, i)] = p[a] * exp(govr * z[a] / tv);
+}
+int k_diagnostics(Ctx& c) {
+  const Geo& g = c.g;
+  {
+    LaunchScope ls(c, KID_DIAG);
+    moloch_diag_prq<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_PAI].p, c.f[MB_T].p, c.f[MB_P].p, c.f[MB_RHO].p, c.f[MB_QSAT].p);
+    MB_CUDA(cudaGetLastError());
+  }
+  {
+    LaunchScope ls(c, KID_PS);
+    moloch_diag_ps<<<grid3(g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, 1), dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_TVIRT].p, c.f[MB_ZETA].p, c.f[MB_P].p, c.f[MB_PS].p);
+    MB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K22  status_update (without its trailing uvxtouvstag)             :1410-1438
+// ---------------------------------------------------------------------------
+__global__ void moloch_status_update(Geo g, double* __restrict__ t, double* __restrict__ ux,
+                                     double* __restrict__ vx, double* __restrict__ qx,
+                                     double* __restrict__ trac, const double* __restrict__ tten,
+                                     const double* __restrict__ uten, const double* __restrict__ vten,
+                                     const double* __restrict__ qxten, const double* __restrict__ chiten,
+                                     const double* __restrict__ pai, const double* __restrict__ p,
+                                     double* __restrict__ tvirt, double* __restrict__ tetav,
+                                     double* __restrict__ rho, double* __restrict__ qsat, double dtinc) {
+  THREAD_JIK(g.jce1, g.ice1, 1)
+  if (j > g.jce2 || i > g.ice2) return;
+  const long long id = IX(j, i, k);
+  const long long sp = (long long)g.kz * g.plane;
+  double tt = t[id];
+  if (in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) {
+    tt = tt + dtinc * tten[id];
+    t[id] = tt;
+    ux[id] = ux[id] + dtinc * uten[id];
+    vx[id] = vx[id] + dtinc * vten[id];
+    for (int n = 0; n < g.nqx; ++n) {
+      double q = qx[id + n * sp] + dtinc * qxten[id + n * sp];
+      if (q < c_qxcheckval[n]) q = c_qxzeroval[n];
+      qx[id + n * sp] = q;
+    }
+    for (int n = 0; n < g.ntr; ++n) {
+      double q = trac[id + n * sp] + dtinc * chiten[id + n * sp];
+      if (q < 0.0) q = 0.0;
+      trac[id + n * sp] = q;
+    }
+  }
+  const double tv = tt * moist_factor(g, qx, id);
+  tvirt[id] = tv;
+  tetav[id] = tv / pai[id];
+  const double pp = p[id];
+  rho[id] = pp / (rgas * tt);
+  qsat[id] = pfwsat(tt, pp);
+}
+int k_status_update(Ctx& c, double dtinc) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_STATUS);
+  moloch_status_update<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_T].p, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_QX].p, c.f[MB_TRAC].p, c.f[MB_TTEN].p,
+      c.f[MB_UTEN].p, c.f[MB_VTEN].p, c.f[MB_QXTEN].p, c.f[MB_CHITEN].p, c.f[MB_PAI].p, c.f[MB_P].p,
+      c.f[MB_TVIRT].p, c.f[MB_TETAV].p, c.f[MB_RHO].p, c.f[MB_QSAT].p, dtinc);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// K0  reset_tendencies                                              :1044-1083
+// Whole-array clears: cells outside the reference's loop ranges (ghosts, pads)
+// are never read.
+// ---------------------------------------------------------------------------
+int k_reset_tendencies(Ctx& c) {
+  const Geo& g = c.g;
+  const size_t pl = (size_t)g.plane * sizeof(double);
+  LaunchScope ls(c, KID_RESET);
+  MB_CUDA(cudaMemsetAsync(c.f[MB_S].p, 0, pl * (g.kz + 1), c.stream));
+  MB_CUDA(cudaMemsetAsync(c.f[MB_ZDIV2].p, 0, pl * g.kz, c.stream));
+  MB_CUDA(cudaMemsetAsync(c.wwkw, 0, pl * (g.kz + 1), c.stream));
+  MB_CUDA(cudaMemsetAsync(c.f[MB_TTEN].p, 0, pl * g.kz, c.stream));
+  MB_CUDA(cudaMemsetAsync(c.f[MB_UTEN].p, 0, pl * g.kz, c.stream));
+  MB_CUDA(cudaMemsetAsync(c.f[MB_VTEN].p, 0, pl * g.kz, c.stream));
+  MB_CUDA(cudaMemsetAsync(c.f[MB_QXTEN].p, 0, pl * g.kz * g.nqx, c.stream));
+  if (g.ntr > 0) MB_CUDA(cudaMemsetAsync(c.f[MB_CHITEN].p, 0, pl * g.kz * g.ntr, c.stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// init_moloch device part: mx2, rmx, rmu, rmv over the whole padded box (the
+// ghost rows of msf* were delivered by the host, so no exchange is needed:
+// the exchanged values of :269-272 are the same products)          :263-278
+// ---------------------------------------------------------------------------
+__global__ void moloch_init_static(Geo g, const double* __restrict__ mx, const double* __restrict__ mu,
+                                   const double* __restrict__ mv, double* __restrict__ mx2,
+                                   double* __restrict__ rmx, double* __restrict__ rmu,
+                                   double* __restrict__ rmv, double* __restrict__ w) {
+  const long long n = g.plane;
+  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < n;
+       id += (long long)gridDim.x * blockDim.x) {
+    const double a = mx[id], b = mu[id], cc = mv[id];
+    mx2[id] = a * a;
+    rmx[id] = (a != 0.0) ? 1.0 / a : 0.0;
+    rmu[id] = (b != 0.0) ? 1.0 / b : 0.0;
+    rmv[id] = (cc != 0.0) ? 1.0 / cc : 0.0;
+    w[id] = 0.0;  // w(:,:,1) = 0
+  }
+}
+int k_init_static(Ctx& c) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_INIT);
+  moloch_init_static<<<148, 256, 0, c.stream>>>(g, c.f[MB_MSFX].p, c.f[MB_MSFU].p, c.f[MB_MSFV].p, c.mx2,
+                                                 c.rmx, c.rmu, c.rmv, c.f[MB_W].p);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mb

@@ -1,0 +1,317 @@
+"""Host-side mirror of RegCM's `mod_moloch` over the C ABI (include/moloch_b200.h).
+
+The reference's interface for this path is three argument-less module
+procedures acting on module state (Main/mod_moloch.F90:127):
+
+    allocate_moloch  :159     init_moloch  :201     moloch  :312
+
+`MolochB200` keeps those names and meanings; the module state (`mo_atm`,
+`mddom`, the &molochparam knobs, the decomposition `ma`) is the object's
+state.  In a RegCM build the same C entry points are called from the Fortran
+shim in INTEGRATION.md; this Python class exists so that tests and benchmarks
+can drive exactly that ABI without a Fortran toolchain.
+
+There is no CPU fallback: construction fails if the CUDA library is missing
+or no CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import hostmodel as H
+from .decomp import Geom, default_cpus_per_dim, make_geom
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmoloch_b200.so")
+
+FIELDS = ["u", "v", "w", "pai", "tetav", "t", "qx", "trac", "ux", "vx", "tvirt", "p", "rho", "qsat", "ps",
+          "zeta", "fmz", "fmzf", "rfmzu", "rfmzv", "hx", "hy", "msfx", "msfu", "msfv", "coru", "corv",
+          "bdywtu", "bdywtv", "bdywtw", "tten", "uten", "vten", "qxten", "chiten", "s", "zdiv2", "wx", "wz",
+          "p0", "tetavf"]
+FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
+PROFILES = ["gzitak", "gzitakh", "ffilt", "xkdamp", "xknu", "rlat"]
+PROFILE_ID = {n: i for i, n in enumerate(PROFILES)}
+SPECIES = {"qx", "trac", "qxten", "chiten"}
+
+# every symbol include/moloch_b200.h declares
+ABI_SYMBOLS = [
+    "moloch_b200_last_error", "moloch_b200_abi_version", "moloch_b200_device_count", "moloch_b200_create",
+    "moloch_b200_destroy", "moloch_b200_comm_id", "moloch_b200_comm_init", "moloch_b200_set_stream",
+    "moloch_b200_sync", "moloch_b200_set_field", "moloch_b200_get_field", "moloch_b200_set_profile",
+    "moloch_b200_host_alloc", "moloch_b200_host_free", "moloch_b200_init", "moloch_b200_reset_tendencies",
+    "moloch_b200_sound", "moloch_b200_advection", "moloch_b200_wafone", "moloch_b200_dynamical_core",
+    "moloch_b200_diagnostics", "moloch_b200_status_update", "moloch_b200_step", "moloch_b200_profile_enable",
+    "moloch_b200_profile_read", "moloch_b200_launch_count", "moloch_b200_device_bytes",
+    "moloch_b200_halo_plan",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "jx", "iy", "kz", "nqx", "ntr", "iqfrst", "jde1", "jde2", "ide1", "ide2", "jce1", "jce2", "ice1",
+        "ice2", "has_bdy_left", "has_bdy_right", "has_bdy_bottom", "has_bdy_top", "bandflag", "crmflag",
+        "nbr_left", "nbr_right", "nbr_bottom", "nbr_top", "rank", "nranks", "mo_nadv", "mo_nsound",
+        "mo_divdamp", "mo_divfilter", "lrotllr", "ipptls", "device", "reserved")] + [
+        (n, C.c_double) for n in ("dtsec", "dx", "mo_dzita")]
+
+
+class MolochError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MolochError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the product has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    ctx = C.c_void_p
+    lib.moloch_b200_last_error.restype = C.c_char_p
+    lib.moloch_b200_create.argtypes = [C.POINTER(Config), C.POINTER(ctx)]
+    lib.moloch_b200_destroy.argtypes = [ctx]
+    lib.moloch_b200_comm_id.argtypes = [C.c_void_p]
+    lib.moloch_b200_comm_init.argtypes = [ctx, C.c_void_p]
+    lib.moloch_b200_set_stream.argtypes = [ctx, C.c_void_p]
+    lib.moloch_b200_sync.argtypes = [ctx]
+    xf = [ctx, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 6
+    lib.moloch_b200_set_field.argtypes = xf
+    lib.moloch_b200_get_field.argtypes = xf
+    lib.moloch_b200_set_profile.argtypes = [ctx, C.c_int, C.c_void_p, C.c_int]
+    lib.moloch_b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+    lib.moloch_b200_host_free.argtypes = [C.c_void_p]
+    for f in ("init", "reset_tendencies", "sound", "advection", "dynamical_core", "diagnostics", "status_update"):
+        getattr(lib, "moloch_b200_" + f).argtypes = [ctx]
+    lib.moloch_b200_wafone.argtypes = [ctx, C.c_int, C.c_int]
+    lib.moloch_b200_step.argtypes = [ctx, C.c_int]
+    lib.moloch_b200_profile_enable.argtypes = [ctx, C.c_int]
+    lib.moloch_b200_profile_read.argtypes = [ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.moloch_b200_launch_count.argtypes = [ctx, C.c_int]
+    lib.moloch_b200_launch_count.restype = C.c_int64
+    lib.moloch_b200_device_bytes.argtypes = [ctx]
+    lib.moloch_b200_device_bytes.restype = C.c_uint64
+    lib.moloch_b200_halo_plan.argtypes = [C.POINTER(Config), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def make_config(wl, g: Geom, device: int = -1, mo_dzita: float | None = None) -> Config:
+    """moloch_b200_config from the workload (namelist values) and the rank's
+    geometry (set_nproc / setup_model_indexes results)."""
+    if mo_dzita is None:
+        mo_dzita = wl.mo_ztop / float(wl.kz)   # zita(kz), Main/mod_params.F90:2461-2463
+    return Config(jx=wl.jx, iy=wl.iy, kz=wl.kz, nqx=wl.nqx, ntr=wl.ntr, iqfrst=2,
+                  jde1=g.jde1, jde2=g.jde2, ide1=g.ide1, ide2=g.ide2, jce1=g.jce1, jce2=g.jce2, ice1=g.ice1,
+                  ice2=g.ice2, has_bdy_left=int(g.bl), has_bdy_right=int(g.br), has_bdy_bottom=int(g.bb),
+                  has_bdy_top=int(g.bt), bandflag=int(g.band), crmflag=int(g.crm), nbr_left=g.left,
+                  nbr_right=g.right, nbr_bottom=g.bottom, nbr_top=g.top, rank=g.rank, nranks=g.px * g.py,
+                  mo_nadv=wl.mo_nadv, mo_nsound=wl.mo_nsound, mo_divdamp=wl.mo_divdamp,
+                  mo_divfilter=wl.mo_divfilter, lrotllr=wl.lrotllr, ipptls=wl.ipptls, device=device,
+                  reserved=0, dtsec=wl.dt, dx=wl.dx, mo_dzita=mo_dzita)
+
+
+def halo_plan(cfg: Config, stag: int, nex: int, lr: bool, bt: bool):
+    """Host-only: send/recv boxes of one exchange (no GPU needed)."""
+    lib = load_library()
+    s = (C.c_int32 * 16)()
+    r = (C.c_int32 * 16)()
+    if lib.moloch_b200_halo_plan(C.byref(cfg), stag, nex, int(lr), int(bt), s, r):
+        raise MolochError(lib.moloch_b200_last_error().decode())
+    return np.array(s).reshape(4, 4), np.array(r).reshape(4, 4)
+
+
+class MolochB200:
+    """One rank's MOLOCH dycore on one B200 (mirror of `mod_moloch`)."""
+
+    def __init__(self, wl, rank: int = 0, nranks: int = 1, px: int | None = None, py: int | None = None,
+                 device: int = -1):
+        self.lib = load_library()
+        self.wl = wl
+        if px is None or py is None:
+            px, py = default_cpus_per_dim(nranks, wl.jx, wl.iy)
+        if px * py != nranks:
+            raise ValueError("px*py != nranks")
+        self.g = make_geom(wl.jx, wl.iy, wl.kz, wl.i_band, wl.i_crm, px, py, rank)
+        self.cfg = make_config(wl, self.g, device)
+        self.ctx = C.c_void_p()
+        self._pinned = []
+
+    # ---- error convention: non-zero -> fatal(__FILE__,__LINE__,msg) ---------
+    def _chk(self, rc):
+        if rc != 0:
+            raise MolochError(self.lib.moloch_b200_last_error().decode())
+
+    # ---- the reference's three entry points -----------------------------------
+    def allocate_moloch(self):
+        """allocate_moloch (Main/mod_moloch.F90:159) + device copies of mo_atm."""
+        self._chk(self.lib.moloch_b200_create(C.byref(self.cfg), C.byref(self.ctx)))
+        return self
+
+    def comm_init(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._chk(self.lib.moloch_b200_comm_init(self.ctx, buf))
+
+    @staticmethod
+    def comm_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        if lib.moloch_b200_comm_id(buf):
+            raise MolochError(lib.moloch_b200_last_error().decode())
+        return buf.raw
+
+    def init_moloch(self, fields: dict, profiles: dict, boxes: dict | None = None):
+        """init_moloch (:201): hand the static fields, profiles and the initial
+        state to the device.  `fields` maps names to GLOBAL arrays (cut here to
+        the rank's bounds) or, when `boxes` gives their bounds, to rank-local
+        arrays."""
+        for name, arr in fields.items():
+            if boxes is not None and name in boxes:
+                self.set_local(name, arr, boxes[name])
+            else:
+                self.set_global(name, arr)
+        for name, v in profiles.items():
+            self.set_profile(name, v)
+        self._chk(self.lib.moloch_b200_init(self.ctx))
+        return self
+
+    def moloch(self, nsteps: int = 1):
+        """moloch (:312) with the host physics returning zero tendencies."""
+        self._chk(self.lib.moloch_b200_step(self.ctx, int(nsteps)))
+
+    # ---- per-subroutine entries (used by the parity tests) --------------------
+    def reset_tendencies(self): self._chk(self.lib.moloch_b200_reset_tendencies(self.ctx))
+    def sound(self): self._chk(self.lib.moloch_b200_sound(self.ctx))
+    def advection(self): self._chk(self.lib.moloch_b200_advection(self.ctx))
+    def dynamical_core(self): self._chk(self.lib.moloch_b200_dynamical_core(self.ctx))
+    def diagnostics(self): self._chk(self.lib.moloch_b200_diagnostics(self.ctx))
+    def status_update(self): self._chk(self.lib.moloch_b200_status_update(self.ctx))
+
+    def wafone(self, field: str, n: int = 1):
+        self._chk(self.lib.moloch_b200_wafone(self.ctx, FIELD_ID[field], int(n)))
+
+    def sync(self): self._chk(self.lib.moloch_b200_sync(self.ctx))
+
+    def set_stream(self, cuda_stream: int):
+        self._chk(self.lib.moloch_b200_set_stream(self.ctx, C.c_void_p(cuda_stream)))
+
+    # ---- host <-> device -------------------------------------------------------
+    def _levels(self, name):
+        lv = H.ALLOC[name][3]
+        return self.wl.kz if lv == "kz" else self.wl.kz + 1 if lv == "kzp1" else 1
+
+    def set_local(self, name: str, arr: np.ndarray, box, n: int = 0):
+        """arr: (nk, ni, nj) [or (nspec, nk, ni, nj)] with Fortran bounds box."""
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        jlo, jhi, ilo, ihi = box
+        nk = self._levels(name)
+        if name in SPECIES and n == 0:
+            for s in range(a.shape[0]):
+                self.set_local(name, a[s], box, s + 1)
+            return
+        if a.size != nk * (ihi - ilo + 1) * (jhi - jlo + 1):
+            raise ValueError(f"{name}: shape {a.shape} does not match bounds {box} x {nk} levels")
+        self._chk(self.lib.moloch_b200_set_field(self.ctx, FIELD_ID[name], n, a.ctypes.data, jlo, jhi, ilo, ihi,
+                                                 1, nk))
+
+    def get_local(self, name: str, box=None, n: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        if box is None:
+            box = H.bounds(self.g, name)
+        jlo, jhi, ilo, ihi = box
+        nk = self._levels(name)
+        if name in SPECIES and n == 0:
+            nspec = self.wl.nqx if name in ("qx", "qxten") else self.wl.ntr
+            return np.stack([self.get_local(name, box, s + 1) for s in range(nspec)])
+        if out is None:
+            out = np.zeros((nk, ihi - ilo + 1, jhi - jlo + 1))
+        self._chk(self.lib.moloch_b200_get_field(self.ctx, FIELD_ID[name], n, out.ctypes.data, jlo, jhi, ilo,
+                                                 ihi, 1, nk))
+        return out if nk > 1 else out.reshape(ihi - ilo + 1, jhi - jlo + 1)
+
+    def set_global(self, name: str, glob: np.ndarray):
+        """Cut the rank's array (reference bounds + ghosts) out of a global one."""
+        box = H.bounds(self.g, name)
+        self.set_local(name, H.cut(np.asarray(glob), self.g, box), box)
+
+    def get_into_global(self, name: str, glob: np.ndarray):
+        """Write this rank's owned cells of `name` into a global array."""
+        own = H.owned(self.g, name)
+        loc = self.get_local(name, own)
+        H.paste(glob, loc, own, own)
+        return glob
+
+    def global_shape(self, name: str):
+        nk = self._levels(name)
+        shp = (self.wl.iy, self.wl.jx) if nk == 1 else (nk, self.wl.iy, self.wl.jx)
+        if name in ("qx", "qxten"):
+            shp = (self.wl.nqx,) + shp
+        if name in ("trac", "chiten"):
+            shp = (self.wl.ntr,) + shp
+        return shp
+
+    def get_global(self, name: str) -> np.ndarray:
+        """Single-rank convenience: the owned cells on the global grid."""
+        return self.get_into_global(name, np.zeros(self.global_shape(name)))
+
+    def set_profile(self, name: str, v):
+        a = np.ascontiguousarray(v, dtype=np.float64)
+        if name == "rlat":   # rlat(ide1 : ide2+1)
+            a = np.ascontiguousarray(a[self.g.ide1 - 1:self.g.ide2 + 1])
+        self._chk(self.lib.moloch_b200_set_profile(self.ctx, PROFILE_ID[name], a.ctypes.data, a.size))
+
+    # ---- pinned host buffers ----------------------------------------------------
+    def pinned_empty(self, shape) -> np.ndarray:
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        self._chk(self.lib.moloch_b200_host_alloc(C.byref(p), n * 8))
+        self._pinned.append(p)
+        buf = (C.c_double * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float64).reshape(shape)
+
+    # ---- instrumentation ---------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        self._chk(self.lib.moloch_b200_profile_enable(self.ctx, int(on)))
+
+    def profile_read(self) -> dict:
+        cap = 64
+        names = ((C.c_char * 48) * cap)()
+        ms = (C.c_double * cap)()
+        cnt = (C.c_int64 * cap)()
+        n = self.lib.moloch_b200_profile_read(self.ctx, cap, names, ms, cnt)
+        if n < 0:
+            raise MolochError(self.lib.moloch_b200_last_error().decode())
+        return {names[q].value.decode(): {"ms": ms[q], "launches": cnt[q]} for q in range(min(n, cap))}
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self.lib.moloch_b200_launch_count(self.ctx, int(reset)))
+
+    def device_bytes(self) -> int:
+        return int(self.lib.moloch_b200_device_bytes(self.ctx))
+
+    def close(self):
+        if self.ctx:
+            self.lib.moloch_b200_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+        for p in self._pinned:
+            self.lib.moloch_b200_host_free(p)
+        self._pinned = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+STATIC_FIELDS = ["fmz", "fmzf", "rfmzu", "rfmzv", "zeta", "hx", "hy", "msfx", "msfu", "msfv", "coru", "corv",
+                 "bdywtu", "bdywtv", "bdywtw"]
+STATE_FIELDS = ["u", "v", "w", "pai", "tetav", "t", "qx", "trac", "ux", "vx", "tvirt", "p", "rho", "qsat", "ps"]
+PROFILE_NAMES = ["gzitak", "gzitakh", "ffilt", "xkdamp", "xknu"]

@@ -1,0 +1,55 @@
+"""Shared helpers of the parity tests: one oracle world and one (or more) GPU
+ranks fed with exactly the same static fields and initial state."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle.oracle import Oracle
+from regcm_b200 import synthetic as S
+from regcm_b200.moloch import PROFILE_NAMES, STATE_FIELDS, STATIC_FIELDS, MolochB200
+
+PROGNOSTIC = ["u", "v", "w", "pai", "tetav", "t", "qx", "ux", "vx"]
+DIAGNOSTIC = ["tvirt", "p", "rho", "qsat", "ps"]
+
+
+def make_oracle(wl, px=1, py=1, checked=False, ffilt=None):
+    P = S.make_primary(wl)
+    o = Oracle(wl, px=px, py=py, checked=checked)
+    o.load_primary(P)
+    if ffilt is not None:
+        o.set("ffilt", ffilt)
+    return o, P
+
+
+def oracle_inputs(o, wl):
+    names = [n for n in STATIC_FIELDS + STATE_FIELDS if not (n == "trac" and wl.ntr == 0)]
+    fields = {n: o.get(n) for n in names}
+    profiles = {n: o.get(n) for n in PROFILE_NAMES}
+    return fields, profiles
+
+
+def make_gpu(wl, fields, profiles, rank=0, nranks=1, px=None, py=None, device=-1):
+    m = MolochB200(wl, rank=rank, nranks=nranks, px=px, py=py, device=device).allocate_moloch()
+    if wl.lrotllr:
+        profiles = dict(profiles)
+    m.init_moloch(fields, profiles)
+    return m
+
+
+def compare(o, m, names, exact=True, rtol=0.0, label=""):
+    bad = []
+    for n in names:
+        if n == "trac" and m.wl.ntr == 0:
+            continue
+        a, b = o.get(n), m.get_global(n)
+        if exact:
+            if not np.array_equal(a, b):
+                d = np.abs(a - b)
+                bad.append(f"{label}{n}: max abs diff {d.max():.3e} at {np.unravel_index(d.argmax(), d.shape)} "
+                           f"(ref {a.flat[d.argmax()]:.17g})")
+        else:
+            den = np.maximum(np.abs(a), 1e-300)
+            r = np.abs(a - b) / den
+            if not (r.max() <= rtol):
+                bad.append(f"{label}{n}: max rel diff {r.max():.3e} > {rtol}")
+    assert not bad, "\n".join(bad)

@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- MOLOCH dycore throughput (cell-updates/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" is one full MOLOCH model step (reset_tendencies + dynamical_core +
+diagnostics + status_update with zero physics tendencies) of the named
+synthetic workload; value = jx*iy*kz*K / device time (max over ranks).  N > 1
+is a STRONG-scaling run: the same global grid is split with RegCM's own 2-D
+block decomposition (set_nproc) and halos travel over NCCL/NVLink.
+
+The JSON line also carries
+  e2e          the same metric through the reference-facing `moloch` hand-off:
+               every step the physics-facing state is copied device->host and
+               the tendencies host->device (pinned buffers), inside the timing
+  roofline     dominant kernel: algorithmic bytes / CUDA-event duration vs the
+               measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline the CPU oracle (C++ restatement of mod_moloch.F90) on the host
+               cores of this box, bounded sample (rank 0, N=1 only)
+`--impl reference` times only that CPU arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from regcm_b200 import synthetic as S  # noqa: E402
+
+DEFAULT_WORKLOAD = "cordex25"
+
+# algorithmic doubles per cell per launch; per-field kernels
+# are multiplied by the number of fields in the launch
+ALG_DOUBLES = {
+    "sound_pre": 9, "divdamp_filter": 7, "wsolve": 12, "uvupdate": 10, "sfinish": 4, "tetavf_init": 2,
+    "destagger": 6, "waf_vertical": 5, "waf_meridional": 6, "waf_zonal": 6, "waf_horizontal": 12, "curvature": 4, "restagger": 6,
+    "tvirt_temp": 10, "diag_prq": 5, "status_update": None, "reset_tendencies": None,
+}
+PER_FIELD = {"waf_vertical", "waf_meridional", "waf_zonal", "waf_horizontal"}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample_workload(wl):
+    """Bounded CPU sample: the same workload (species, sponge, dt, dx) on a
+    cropped horizontal domain."""
+    n = 256
+    return S.small(wl, min(wl.jx, n), min(wl.iy, n), wl.kz)
+
+
+def run_cpu_reference(wl, steps: int, warmup: int) -> dict:
+    """The CPU arm: oracle (C++ restatement of Main/mod_moloch.F90, OpenMP over
+    all host cores) on a bounded sample of the workload."""
+    from oracle.oracle import Oracle
+    swl = cpu_sample_workload(wl)
+    o = Oracle(swl)
+    o.load_primary(S.make_primary(swl))
+    cores = o.get_threads()
+    o.step(max(warmup, 1))
+    t0 = time.perf_counter()
+    o.step(steps)
+    dt = time.perf_counter() - t0
+    ok = bool(np.isfinite(o.get("pai")).all())
+    return {"value": swl.cells * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+            "sample": f"{wl.name} cropped to {swl.jx}x{swl.iy}x{swl.kz} (F={swl.nfields}), {steps} steps "
+                      f"after {max(warmup, 1)} warm-up, {dt:.2f} s; finite={ok}",
+            "ms_per_step": dt / steps * 1e3, "grid": [swl.jx, swl.iy, swl.kz]}
+
+
+def base_line(wl, args, n_gpus):
+    return {"metric": "MOLOCH dycore cell-updates/s", "unit": "cell-updates/s", "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.name, "grid": [wl.jx, wl.iy, wl.kz], "advected_fields": wl.nfields,
+                       "nqx": wl.nqx, "ntr": wl.ntr, "mo_nadv": wl.mo_nadv, "mo_nsound": wl.mo_nsound,
+                       "dt_s": wl.dt, "dx_m": wl.dx, "periodic": bool(wl.i_crm),
+                       "bytes_per_cell_update": wl.bytes_per_cell_update(),
+                       "l2": "state (>1 GB) exceeds the 126 MB L2; no explicit flush"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(S.WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--px", type=int, default=0)
+    ap.add_argument("--py", type=int, default=0)
+    args = ap.parse_args()
+    wl = S.WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 8))
+        r = run_cpu_reference(wl, steps, min(args.warmup, 1))
+        line = base_line(wl, args, args.gpus)
+        line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": steps,
+                     "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                     "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
+                             "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0,
+                     "note": "reference Fortran/MPI build unavailable (no Fortran compiler, MPI or NetCDF in the "
+                             "image); this is the C++ restatement of Main/mod_moloch.F90 on the host cores"})
+        line["config"]["cpu_sample_grid"] = r["grid"]
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from regcm_b200.moloch import MolochB200, STATE_FIELDS
+    from regcm_b200 import hostmodel as H
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py: --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    px = args.px or None
+    py = args.py or None
+    m = MolochB200(wl, rank=rank, nranks=world, px=px, py=py, device=local_rank).allocate_moloch()
+    if world > 1:
+        ids = [MolochB200.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        m.comm_init(ids[0])
+    stream = torch.cuda.Stream()
+    m.set_stream(stream.cuda_stream)
+    fields, profiles = S.model_inputs(wl)
+    m.init_moloch(fields, profiles)
+    del fields
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(k):
+                fn()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    # ---- device-resident throughput -----------------------------------------------
+    m.moloch(args.warmup)
+    m.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    m.launch_count(reset=True)
+    ms = timed(lambda: m.moloch(1), args.steps)
+    launches = m.launch_count(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    value = wl.cells * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel device timing (CUDA events on the launching stream) ----------
+    m.profile_enable(True)
+    psteps = max(1, min(3, args.steps))
+    m.moloch(psteps)
+    prof = m.profile_read()
+    m.profile_enable(False)
+    peak, peak_src = measured_peak_gbs()
+    g = m.g
+    cells_local = (g.jce2 - g.jce1 + 1) * (g.ice2 - g.ice1 + 1) * wl.kz
+    kernels = []
+    for name, r in prof.items():
+        avg_ms = r["ms"] / max(r["launches"], 1)
+        d = ALG_DOUBLES.get(name)
+        if name == "status_update":
+            d = 9 + 3 * (wl.nqx + wl.ntr) + 7 + 7
+        alg = None
+        if d is not None:
+            alg = d * 8 * cells_local * (wl.nfields if name in PER_FIELD else 1)
+        kernels.append({"kernel": name, "launches_per_step": r["launches"] / psteps, "avg_ms": avg_ms,
+                        "share": None, "alg_bytes": alg,
+                        "gbs": (alg / (avg_ms * 1e-3) / 1e9) if alg and avg_ms > 0 else None})
+    tot = sum(k["avg_ms"] * k["launches_per_step"] for k in kernels) or 1.0
+    for k in kernels:
+        k["share"] = k["avg_ms"] * k["launches_per_step"] / tot
+    kernels.sort(key=lambda k: -k["share"])
+    dom = next((k for k in kernels if k["gbs"]), None)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if dom and os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(wl.name, {}).get(dom["kernel"])
+        except Exception:
+            traffic = None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": "moloch_" + dom["kernel"], "achieved": dom["gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["avg_ms"],
+                    "share_of_step": dom["share"],
+                    "whole_step": {"achieved": wl.bytes_per_cell_update() * value / 1e9,
+                                   "frac": wl.bytes_per_cell_update() * value / 1e9 / peak / world}}
+
+    # ---- end to end through the reference-facing hand-off --------------------------
+    e2e = None
+    if not args.no_e2e:
+        down = [n for n in STATE_FIELDS if not (n == "trac" and wl.ntr == 0)]
+        up = ["tten", "uten", "vten", "qxten"] + (["chiten"] if wl.ntr > 0 else [])
+        hbuf, bytes_d2h, bytes_h2d = {}, 0, 0
+        for n in down + up:
+            box = H.bounds(g, n)
+            nk = m._levels(n)
+            nspec = wl.nqx if n in ("qx", "qxten") else wl.ntr if n in ("trac", "chiten") else 1
+            shp = (nspec, nk, box[3] - box[2] + 1, box[1] - box[0] + 1)
+            hbuf[n] = (m.pinned_empty(shp), box)
+            hbuf[n][0][...] = 0.0
+            if n in down:
+                bytes_d2h += int(np.prod(shp)) * 8
+            else:
+                bytes_h2d += int(np.prod(shp)) * 8
+
+        def e2e_step():
+            m.reset_tendencies()
+            m.dynamical_core()
+            m.diagnostics()
+            for n in down:          # device -> host: what mkslice/physics read
+                buf, box = hbuf[n]
+                for s in range(buf.shape[0]):
+                    m.get_local(n, box, s + 1 if n in ("qx", "trac") else 0, out=buf[s])
+            for n in up:            # host -> device: the physics tendencies
+                buf, box = hbuf[n]
+                for s in range(buf.shape[0]):
+                    m.set_local(n, buf[s], box, s + 1 if n in ("qxten", "chiten") else 0)
+            m.status_update()
+
+        e2e_step()
+        ksteps = max(1, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()
+        m.sync()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": wl.cells * ksteps / float(dt.item()), "unit": "cell-updates/s",
+               "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h, "steps": ksteps,
+               "ms_per_step": float(dt.item()) / ksteps * 1e3,
+               "what": "moloch(): device dycore, D2H of u,v,w,ux,vx,pai,tetav,t,tvirt,p,rho,qsat,ps,qx,trac to "
+                       "pinned host arrays, H2D of tten,uten,vten,qxten,chiten, device status_update"}
+
+    finite = bool(np.isfinite(m.get_local("pai")).all())
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu_reference(wl, 6, 1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = base_line(wl, args, world)
+        line["config"]["decomposition"] = f"{m.g.px}x{m.g.py}"
+        line.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "e2e": e2e,
+                     "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                     "kernels": kernels[:12], "finite": finite, "device_bytes": m.device_bytes()})
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

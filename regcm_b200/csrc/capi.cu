@@ -15,7 +15,8 @@ int fail(const std::string& msg) { g_err = msg; return 1; }
 static const char* k_names[KID_COUNT] = {
     "reset_tendencies", "tetavf_init", "sound_pre", "divdamp_filter", "wsolve", "uvupdate", "sfinish",
     "destagger", "waf_vertical", "waf_meridional", "waf_zonal", "curvature", "restagger", "tvirt_temp",
-    "diag_prq", "diag_ps", "status_update", "halo_local", "halo_pack", "halo_unpack", "init_static"};
+    "diag_prq", "diag_ps", "status_update", "halo_local", "halo_pack", "halo_unpack", "init_static",
+    "waf_horizontal"};
 const char* kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? k_names[kid] : "?"; }
 
 LaunchScope::LaunchScope(Ctx& c_, int kid_) : c(c_), kid(kid_) {
@@ -116,6 +117,20 @@ static int do_wafone_range(Ctx& c, int first, int count) {
   const int kz = c.g.kz;
   const long long fsz = (long long)kz * c.g.plane;
   std::vector<HaloItem> items((size_t)count);
+  if (c.waf_impl == 2) {
+    // Field-batched path.  The fused horizontal kernel recomputes p0 on the two
+    // ghost columns instead of receiving it (:955/:1012), so it needs wz with
+    // corner ghosts and pp on two ghost columns: 3 batched messages per side
+    // instead of the reference's 2 per field.
+    if (k_waf_z2(c, first, count, dta)) return 1;
+    for (int q = 0; q < count; ++q) items[q] = {c.wzall + q * fsz, kz};
+    if (halo_exchange(c, items.data(), count, HS_CROSS, 2, false, true)) return 1;
+    if (halo_exchange(c, items.data(), count, HS_CROSS, 2, true, false, 2)) return 1;
+    // pre-advection pp snapshot (written by the vertical kernel) on two ghost columns
+    for (int q = 0; q < count; ++q) items[q] = {c.p0all + q * fsz, kz};
+    if (halo_exchange(c, items.data(), count, HS_CROSS, 2, true, false)) return 1;
+    return k_waf_yx(c, first, count, dta);
+  }
   if (k_waf_z(c, first, count, dta)) return 1;
   for (int q = 0; q < count; ++q) items[q] = {c.wzall + q * fsz, kz};
   if (halo_exchange(c, items.data(), count, HS_CROSS, 2, false, true)) return 1;  // :924
@@ -132,6 +147,9 @@ static int do_advection(Ctx& c) {
   if (halo_exchange(c, &it, 1, HS_U, 2, true, false)) return 1;  // :1532
   it = {c.f[MB_V].p, kz};
   if (halo_exchange(c, &it, 1, HS_V, 2, false, true)) return 1;  // :1533
+  if (c.waf_impl == 2) {  // v on two ghost columns (incl. ghost rows) for the fused horizontal pass
+    if (halo_exchange(c, &it, 1, HS_V, 2, true, false, 2)) return 1;
+  }
   if (k_destagger(c)) return 1;
   if (do_wafone_range(c, 0, c.nadv_fields)) return 1;             // :786-807
   if (k_curvature(c, c.dtstepa)) return 1;
@@ -233,6 +251,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   const size_t o_zb = total; total += al(pl * kz);
   const size_t o_ww = total; total += al(pl * (kz + 1));
   const size_t o_2d = total; total += al(pl) * 4;
+  const size_t o_zr = total; total += al(pl * kz) * 2;
   const size_t o_wz = total; total += al(pl * kz * (size_t)c->nadv_fields);
   const size_t o_p0 = total; total += al(pl * kz * (size_t)c->nadv_fields);
   const size_t o_prof = total;
@@ -256,6 +275,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   c->zdiv2b = (double*)(c->arena + o_zb); c->wwkw = (double*)(c->arena + o_ww);
   c->mx2 = (double*)(c->arena + o_2d); c->rmx = (double*)(c->arena + o_2d + al(pl));
   c->rmu = (double*)(c->arena + o_2d + 2 * al(pl)); c->rmv = (double*)(c->arena + o_2d + 3 * al(pl));
+  c->zru = (double*)(c->arena + o_zr); c->zrd = (double*)(c->arena + o_zr + al(pl * kz));
   c->wzall = (double*)(c->arena + o_wz); c->p0all = (double*)(c->arena + o_p0);
   c->f[MB_WZ].p = c->wzall; c->f[MB_P0].p = c->p0all;
   for (int q = 0; q < MB_NPROFILES; ++q) {
@@ -266,6 +286,8 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   std::vector<double*> tab;
   for (auto& a : adv) tab.push_back(c->f[a.fid].p + (size_t)a.spec * kz * g.plane);
   cudaMemcpy(c->d_ptrtab, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice);
+  c->h_ptrtab = tab;
+  if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaFree(c->arena);
     delete c;
@@ -397,7 +419,23 @@ int moloch_b200_init(moloch_b200_ctx* c) {
     if (c->prof_n[q] == 0) return fail("moloch_b200_init: vertical profiles not set (gzitak, gzitakh, ffilt, xkdamp, xknu)");
   if (c->cfg.lrotllr && c->prof_n[MB_RLAT] == 0) return fail("moloch_b200_init: rlat not set (ROTLLR)");
   MB_CUDA(cudaSetDevice(c->device));
+  {
+    // Widen the ghosts of the static metric fields from the reference's 1 to 2
+    // points (with corners): the fused horizontal WAF kernel evaluates p0 on
+    // two ghost columns.  The exchanged values equal the host-provided ones
+    // wherever both exist.
+    const int kz = c->g.kz;
+    struct W { int fid; int stag; int nk; };
+    const W ws[] = {{MB_FMZ, HS_CROSS, kz}, {MB_RFMZU, HS_U, kz}, {MB_RFMZV, HS_V, kz},
+                    {MB_MSFX, HS_DOT, 1}, {MB_MSFU, HS_DOT, 1}, {MB_MSFV, HS_DOT, 1}};
+    for (const W& w : ws) {
+      HaloItem it = {c->f[w.fid].p, w.nk};
+      if (halo_exchange(*c, &it, 1, w.stag, 2, true, false)) return 1;
+      if (halo_exchange(*c, &it, 1, w.stag, 2, false, true, 2)) return 1;
+    }
+  }
   if (k_init_static(*c)) return 1;
+  if (k_waf_ratios(*c)) return 1;
   if (sync_stream(*c)) return 1;
   c->initialised = true;
   return 0;
@@ -419,10 +457,8 @@ int moloch_b200_wafone(moloch_b200_ctx* c, int field, int n) {
     spec = n - 1;
   }
   double* want = c->f[field].p + (size_t)spec * c->g.kz * c->g.plane;
-  std::vector<double*> tab((size_t)c->nadv_fields);
-  MB_CUDA(cudaMemcpy(tab.data(), c->d_ptrtab, tab.size() * sizeof(double*), cudaMemcpyDeviceToHost));
   for (int q = 0; q < c->nadv_fields; ++q)
-    if (tab[q] == want) return do_wafone_range(*c, q, 1);
+    if (c->h_ptrtab[q] == want) return do_wafone_range(*c, q, 1);
   return fail("wafone: field is not one of the advected fields");
 }
 int moloch_b200_dynamical_core(moloch_b200_ctx* c) { ENTRY(c) return do_dynamical_core(*c); }

@@ -67,7 +67,7 @@ __host__ __device__ inline long long gidx2(const Geo& g, int j, int i) {
 enum KernelId {
   KID_RESET = 0, KID_TETAVF, KID_SOUND_PRE, KID_DIVDAMP, KID_WSOLVE, KID_UVUPDATE, KID_SFINISH,
   KID_DESTAG, KID_WAF_Z, KID_WAF_Y, KID_WAF_X, KID_CURV, KID_RESTAG, KID_TVIRT, KID_DIAG, KID_PS,
-  KID_STATUS, KID_HALO, KID_HALO_PACK, KID_HALO_UNPACK, KID_INIT, KID_COUNT
+  KID_STATUS, KID_HALO, KID_HALO_PACK, KID_HALO_UNPACK, KID_INIT, KID_WAF_H, KID_COUNT
 };
 
 struct ProfEvent { cudaEvent_t a, b; int kid; };
@@ -89,10 +89,13 @@ struct Ctx {
   Field f[MB_NFIELDS];
   // extra device arrays
   double *ud, *vd, *zdiv2b, *wwkw, *mx2, *rmx, *rmu, *rmv;
+  double *zru, *zrd;      // static ratios of the vertical WAF pass
+  int waf_impl = 2;       // 1: per-loop kernels, 2: field-batched fused kernels
   double *wzall, *p0all;  // per-field scratch of the batched wafone
   double* prof[MB_NPROFILES];
   int prof_n[MB_NPROFILES];
   double** d_ptrtab = nullptr;  // device table of field pointers (batched wafone)
+  std::vector<double*> h_ptrtab;
   int nadv_fields = 0;
   // scalars (Main/mod_moloch.F90:306-307, :275)
   double dtstepa, dtsound, rdx, rdzita;
@@ -149,11 +152,15 @@ int k_tvirt_temp(Ctx& c);
 int k_diagnostics(Ctx& c);
 int k_status_update(Ctx& c, double dtinc);
 int k_init_static(Ctx& c);
+// kernels_waf.cu
+int k_waf_ratios(Ctx& c);
+int k_waf_z2(Ctx& c, int first, int count, double dta);
+int k_waf_yx(Ctx& c, int first, int count, double dta);
 
 // ---- halo exchange (halo.cu) ------------------------------------------------
 enum HaloStag { HS_CROSS = 0, HS_U, HS_V, HS_DOT, HS_P0 };
 struct HaloItem { double* p; int nk; };
-int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt);
+int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt, int ext = 0);
 int halo_comm_init(Ctx& c, const void* id128);
 int halo_comm_id(void* id128);
 void halo_boxes(const moloch_b200_config& cfg, int stag, int nex, bool lr, bool bt,

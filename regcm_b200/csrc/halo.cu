@@ -54,6 +54,7 @@ struct HaloParams {
   double* p[HALO_MAX_ITEMS];
   int nitems, nk, nex;
   int j1, j2, i1, i2;
+  int elo[4], elen[4];   // first index and length of the edge run of each side
   int mode[4];           // 0 none, 1 local copy, 2 remote
   long long seg[4];      // offset (doubles) of each side's segment
   long long count[4];    // doubles per side
@@ -63,15 +64,15 @@ enum { HM_LOCAL = 0, HM_PACK = 1, HM_UNPACK = 2 };
 // element e of side sd -> (send cell, ghost cell); order (item, k, r, iex)
 __device__ __forceinline__ void halo_cell(const HaloParams& h, int sd, long long e, int& item, int& k, int& js,
                                           int& is, int& jg, int& ig) {
-  const int len = (sd < 2) ? (h.i2 - h.i1 + 1) : (h.j2 - h.j1 + 1);
+  const int len = h.elen[sd];
   const int iex = (int)(e % h.nex) + 1; e /= h.nex;
   const int r = (int)(e % len); e /= len;
   k = (int)(e % h.nk) + 1; item = (int)(e / h.nk);
   switch (sd) {
-    case 0: js = h.j1 + iex - 1; jg = h.j1 - iex; is = ig = h.i1 + r; break;
-    case 1: js = h.j2 - (iex - 1); jg = h.j2 + iex; is = ig = h.i1 + r; break;
-    case 2: is = h.i1 + iex - 1; ig = h.i1 - iex; js = jg = h.j1 + r; break;
-    default: is = h.i2 - (iex - 1); ig = h.i2 + iex; js = jg = h.j1 + r; break;
+    case 0: js = h.j1 + iex - 1; jg = h.j1 - iex; is = ig = h.elo[sd] + r; break;
+    case 1: js = h.j2 - (iex - 1); jg = h.j2 + iex; is = ig = h.elo[sd] + r; break;
+    case 2: is = h.i1 + iex - 1; ig = h.i1 - iex; js = jg = h.elo[sd] + r; break;
+    default: is = h.i2 - (iex - 1); ig = h.i2 + iex; js = jg = h.elo[sd] + r; break;
   }
 }
 
@@ -183,7 +184,10 @@ static int launch_halo(Ctx& c, int mode, const HaloParams& h, double* buf, long 
   return 0;
 }
 
-int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt) {
+// `ext` widens the edge run of every side by `ext` ghost points at each end
+// that has a neighbour: an lr exchange followed by a bt exchange with ext > 0
+// (or the other way round) also fills the corner ghosts.
+int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt, int ext) {
   const moloch_b200_config& cf = c.cfg;
   const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
   bool any = false;
@@ -202,7 +206,14 @@ int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, 
     bool has_local = false, has_remote = false;
     for (int sd = 0; sd < 4; ++sd) {
       const bool on = (nbr[sd] >= 0) && ((sd < 2) ? lr : bt);
-      const long long len = (sd < 2) ? (h.i2 - h.i1 + 1) : (h.j2 - h.j1 + 1);
+      if (sd < 2) {
+        h.elo[sd] = h.i1 - ext * c.g.gb;
+        h.elen[sd] = (h.i2 + ext * c.g.gt) - h.elo[sd] + 1;
+      } else {
+        h.elo[sd] = h.j1 - ext * c.g.gl;
+        h.elen[sd] = (h.j2 + ext * c.g.gr) - h.elo[sd] + 1;
+      }
+      const long long len = h.elen[sd];
       h.mode[sd] = !on ? 0 : (nbr[sd] == cf.rank ? 1 : 2);
       h.count[sd] = on ? (long long)n * h.nk * len * nex : 0;
       h.seg[sd] = off;

@@ -394,3 +394,33 @@ def init_state(wl: Workload, P: dict, S: dict) -> dict:
     st["tetav"] = st["tvirt"] / pai
     st["w"] = np.zeros((kz + 1,) + t.shape[1:])
     return st
+
+
+def model_inputs(wl: Workload):
+    """Everything `init_moloch` hands to the device, on the global grid:
+    (fields, profiles) for MolochB200.init_moloch.  NumPy stand-in for the
+    Fortran host set-up (compute_moloch_static, init_moloch's 1-D tables,
+    paicompute); used by bench.py, where no oracle is involved."""
+    P = make_primary(wl)
+    St = derive_static(wl, P)
+    X = init_state(wl, P, St)
+    kz = wl.kz
+    F = {k: St[k] for k in ("fmz", "fmzf", "rfmzu", "rfmzv", "zeta", "hx", "hy", "bdywtu", "bdywtv", "bdywtw")}
+    F["msfx"], F["msfu"], F["msfv"] = P["msfx"], P["msfu"], P["msfv"]
+    F["coru"] = eomeg2 * np.sin(P["ulat"] * degrad)      # Main/mod_moloch.F90:260-261
+    F["corv"] = eomeg2 * np.sin(P["vlat"] * degrad)
+    F.update(u=P["u"], v=P["v"], t=P["t"], qx=P["qx"], ps=P["ps"])
+    if wl.ntr > 0:
+        F["trac"] = P["trac"]
+    F.update(pai=X["pai"], tetav=X["tetav"], tvirt=X["tvirt"], p=X["p"], rho=X["rho"], qsat=X["qsat"], w=X["w"])
+    k = np.arange(1, kz + 1, dtype=np.float64)
+    prof = {
+        "gzitak": gzita(St["zita"], wl.mo_ztop, wl.mo_a0),
+        "gzitakh": gzita(St["zitah"], wl.mo_ztop, wl.mo_a0),
+        "ffilt": St["ffilt"],
+        "xkdamp": 0.125 * 0.850 * (1.0 / (k + 1.0) - 1.0 / (kz + 2.0)),          # :295-296
+        "xknu": 0.125 * (0.55 + 0.45 * ((kz - k + 1.0) - 1.0) / (kz - 1.0)),     # :297-298
+    }
+    if wl.lrotllr:
+        prof["rlat"] = P["rlat"]
+    return F, prof

@@ -1,0 +1,64 @@
+"""Run R ranks of the CUDA product in one process (one Python thread and one
+GPU per rank, NCCL between them) and assemble global arrays -- the harness of
+the multi-GPU parity tests.  ctypes releases the GIL during library calls, so
+the blocking NCCL rendezvous inside moloch_b200_comm_init works."""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+from regcm_b200.moloch import MolochB200
+
+
+class MultiRank:
+    def __init__(self, wl, px, py, fields, profiles, devices=None):
+        self.wl, self.n = wl, px * py
+        devices = devices or list(range(self.n))
+        uid = MolochB200.comm_id() if self.n > 1 else None
+        self.ranks = [None] * self.n
+        errs = []
+
+        def boot(r):
+            try:
+                m = MolochB200(wl, rank=r, nranks=self.n, px=px, py=py, device=devices[r]).allocate_moloch()
+                if self.n > 1:
+                    m.comm_init(uid)
+                m.init_moloch(fields, profiles)
+                self.ranks[r] = m
+            except Exception as e:  # noqa: BLE001
+                errs.append((r, e))
+        self._par(boot)
+        if errs:
+            raise RuntimeError(f"rank boot failed: {errs}")
+
+    def _par(self, fn):
+        ts = [threading.Thread(target=fn, args=(r,)) for r in range(self.n)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    def call(self, method, *args):
+        errs = []
+
+        def run(r):
+            try:
+                getattr(self.ranks[r], method)(*args)
+                self.ranks[r].sync()
+            except Exception as e:  # noqa: BLE001
+                errs.append((r, e))
+        self._par(run)
+        if errs:
+            raise RuntimeError(f"{method} failed: {errs}")
+
+    def get_global(self, name):
+        out = np.zeros(self.ranks[0].global_shape(name))
+        for m in self.ranks:
+            m.get_into_global(name, out)
+        return out
+
+    def close(self):
+        for m in self.ranks:
+            if m is not None:
+                m.close()

@@ -104,12 +104,12 @@ static int do_sound(Ctx& c) {
       if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :745 (:535 is redundant)
       if (k_divdamp_filter(c, dts)) return 1;
     }
-    if (k_wsolve(c, dts)) return 1;
+    if (k_wsolve(c, dts, ns == c.cfg.mo_nsound - 1)) return 1;
     it = {c.f[MB_PAI].p, kz};
     if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :673
     if (k_uvupdate(c, dts)) return 1;
   }
-  return k_sfinish(c);
+  return 0;  // :728-734 (finish of s) is fused into the last sub-step's wsolve
 }
 
 static int do_wafone_range(Ctx& c, int first, int count) {

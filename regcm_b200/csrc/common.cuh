@@ -139,7 +139,7 @@ int k_reset_tendencies(Ctx& c);
 int k_tetavf_init(Ctx& c);
 int k_sound_pre(Ctx& c, double dts);
 int k_divdamp_filter(Ctx& c, double dts);
-int k_wsolve(Ctx& c, double dts);
+int k_wsolve(Ctx& c, double dts, bool last);
 int k_uvupdate(Ctx& c, double dts);
 int k_sfinish(Ctx& c);
 int k_destagger(Ctx& c);

@@ -207,84 +207,105 @@ int k_divdamp_filter(Ctx& c, double dts) {
 // One thread per column; the finished divergence of the column is parked in
 // shared memory (thread-private slots, no barriers).
 // ---------------------------------------------------------------------------
-constexpr int WS_TB = 64;
-__global__ void __launch_bounds__(WS_TB)
-moloch_wsolve(Geo g, const double* __restrict__ zdiv, const double* __restrict__ s, double* __restrict__ w,
+constexpr int WS_NJ = 32;        // columns per CTA
+constexpr int WS_THREADS = 256;
+__global__ void __launch_bounds__(WS_THREADS)
+moloch_wsolve(Geo g, const double* __restrict__ zdiv, double* s, double* __restrict__ w,
               double* __restrict__ pai, const double* __restrict__ tetav, double* __restrict__ tetavf,
-              double* __restrict__ wwkw, const double* __restrict__ fmz, const double* __restrict__ fmzf,
+              const double* __restrict__ fmz, const double* __restrict__ fmzf,
               const double* __restrict__ bdywtw, const double* __restrict__ ffilt, double dts, double dtrdz,
-              double zcs2) {
+              double zcs2, int last) {
+  // CTA = 32 columns x all levels.  Everything that does not depend on the
+  // recurrence (finished divergence, explicit w, matrix coefficients) is
+  // computed by all threads in parallel over k; only the two Thomas sweeps run
+  // serially in k, by one warp, out of shared memory.
   extern __shared__ double sm[];
-  const int nj = g.jci2 - g.jci1 + 1, ni = g.ici2 - g.ici1 + 1;
-  const long long col = (long long)blockIdx.x * WS_TB + threadIdx.x;
-  if (col >= (long long)nj * ni) return;
-  const int i = g.ici1 + (int)(col / nj), j = g.jci1 + (int)(col % nj);
   const int kz = g.kz;
-  double* zd_s = sm + threadIdx.x;  // zd_s[(k-1)*WS_TB]
-  const long long base = IX(j, i, 1);
+  double* ZD = sm;                      // finished divergence, levels 1..kz
+  double* W = ZD + kz * WS_NJ;          // w / explicit w, levels 1..kz+1
+  double* ZU = W + (kz + 1) * WS_NJ;    // zu, then wwkw
+  double* ZC = ZU + kz * WS_NJ;         // zd coefficient
+  const int nj = g.jci2 - g.jci1 + 1, ni = g.ici2 - g.ici1 + 1;
+  const long long ncol = (long long)nj * ni;
+  const int lane = threadIdx.x % WS_NJ, row0 = threadIdx.x / WS_NJ;
+  constexpr int NR = WS_THREADS / WS_NJ;
+  const long long col = (long long)blockIdx.x * WS_NJ + lane;
+  const bool valid = col < ncol;
+  const long long colc = valid ? col : ncol - 1;
+  const int i = g.ici1 + (int)(colc / nj), j = g.jci1 + (int)(colc % nj);
+  const long long base = gidx(g, j, i, 1);
   const long long pl = g.plane;
-  // :627-630  (s(k)-s(k+1))
-  {
-    double sk = s[base];
-    for (int k = 1; k <= kz; ++k) {
-      const long long id = base + (k - 1) * pl;
-      const double sk1 = s[id + pl];
-      zd_s[(k - 1) * WS_TB] = zdiv[id] + bdywtw[id] * dtrdz * fmz[id] * (sk - sk1);
-      sk = sk1;
-    }
-  }
-  // :634-656  downward sweep
-  double wkp1 = w[base + (long long)kz * pl];  // w(kzp1)
-  double wwkp1 = 0.0;                          // wwkw(kzp1) :1055-1057
-  double tv_k = tetav[base + (long long)(kz - 1) * pl];
-  double pai_k = pai[base + (long long)(kz - 1) * pl];
-  for (int k = kz; k >= 2; --k) {
+  // :627-630 and the old w
+  for (int k = 1 + row0; k <= kz + 1; k += NR) {
     const long long id = base + (k - 1) * pl;
-    const double tv_km1 = tetav[id - pl], pai_km1 = pai[id - pl];
-    const double wk = w[id], fmzfk = fmzf[id];
+    W[(k - 1) * WS_NJ + lane] = w[id];
+    if (k <= kz)
+      ZD[(k - 1) * WS_NJ + lane] = zdiv[id] + bdywtw[id] * dtrdz * fmz[id] * (s[id] - s[id + pl]);
+  }
+  __syncthreads();
+  // :636-649 explicit part and tridiagonal coefficients, parallel in k
+  for (int k = 2 + row0; k <= kz; k += NR) {
+    const long long id = base + (k - 1) * pl;
+    const int o = (k - 1) * WS_NJ + lane;
+    const double tv_k = tetav[id], tv_km1 = tetav[id - pl];
+    const double pai_k = pai[id], pai_km1 = pai[id - pl];
+    const double wk = W[o], fmzfk = fmzf[id];
     const double tf = tetavf[id] - wk * fmzfk * dtrdz * (tv_km1 - tv_k);
-    tetavf[id] = tf;
+    if (valid) tetavf[id] = tf;
     const double zrom1w = cpd * tf * fmzfk;
     double zwexpl = wk - zrom1w * dtrdz * (pai_km1 - pai_k) - egrav * dts;
-    zwexpl = zwexpl + rdrcv * zrom1w * dtrdz * (pai_km1 * zd_s[(k - 2) * WS_TB] - pai_k * zd_s[(k - 1) * WS_TB]);
-    const double zu = zcs2 * fmz[id - pl] * zrom1w * pai_km1 + ffilt[k];
-    const double zd = zcs2 * fmz[id] * zrom1w * pai_k + ffilt[k];
-    const double zrapp = 1.0 / (1.0 + zd + zu - zd * wwkp1);
-    wkp1 = zrapp * (zwexpl + zd * wkp1);
-    wwkp1 = zrapp * zu;
-    w[id] = wkp1;
-    wwkw[id] = wwkp1;
-    tv_k = tv_km1; pai_k = pai_km1;
+    zwexpl = zwexpl + rdrcv * zrom1w * dtrdz * (pai_km1 * ZD[o - WS_NJ] - pai_k * ZD[o]);
+    ZU[o] = zcs2 * fmz[id - pl] * zrom1w * pai_km1 + ffilt[k];
+    ZC[o] = zcs2 * fmz[id] * zrom1w * pai_k + ffilt[k];
+    W[o] = zwexpl;
   }
-  // :660-671  upward sweep + Exner update.  pai(k) needs w(k), w(k+1) final.
-  double wkm1 = w[base];  // w(1)
-  for (int k = 2; k <= kz; ++k) {
-    const long long id = base + (k - 1) * pl;
-    const double wk = w[id] + wwkw[id] * wkm1;
-    w[id] = wk;
-    // pai(k-1) with w(k-1), w(k)
-    const long long im = id - pl;
-    pai[im] = pai[im] * (1.0 - rdrcv * (zd_s[(k - 2) * WS_TB] + (dtrdz * fmz[im] * (wkm1 - wk))));
-    wkm1 = wk;
+  __syncthreads();
+  // :650-664 Thomas sweeps, serial in k
+  if (row0 == 0) {
+    double wkp1 = W[kz * WS_NJ + lane];  // w(kzp1)
+    double wwkp1 = 0.0;                  // wwkw(kzp1) :1055-1057
+    for (int k = kz; k >= 2; --k) {
+      const int o = (k - 1) * WS_NJ + lane;
+      const double zu = ZU[o], zd = ZC[o];
+      const double zrapp = 1.0 / (1.0 + zd + zu - zd * wwkp1);
+      wkp1 = zrapp * (W[o] + zd * wkp1);
+      wwkp1 = zrapp * zu;
+      W[o] = wkp1;
+      ZU[o] = wwkp1;
+    }
+    double wkm1 = W[lane];  // w(1)
+    for (int k = 2; k <= kz; ++k) {
+      const int o = (k - 1) * WS_NJ + lane;
+      wkm1 = W[o] + ZU[o] * wkm1;
+      W[o] = wkm1;
+    }
   }
-  {
-    const long long id = base + (long long)(kz - 1) * pl;
-    const double wkzp1 = w[id + pl];
-    pai[id] = pai[id] * (1.0 - rdrcv * (zd_s[(kz - 1) * WS_TB] + (dtrdz * fmz[id] * (wkm1 - wkzp1))));
+  __syncthreads();
+  // :668-671 new Exner function; after the last sub-step also :728-734
+  if (valid) {
+    for (int k = 1 + row0; k <= kz; k += NR) {
+      const long long id = base + (k - 1) * pl;
+      const int o = (k - 1) * WS_NJ + lane;
+      const double wk = W[o], wk1 = W[o + WS_NJ];
+      pai[id] = pai[id] * (1.0 - rdrcv * (ZD[o] + (dtrdz * fmz[id] * (wk - wk1))));
+      if (k >= 2) w[id] = wk;
+      if (last) s[id] = (k >= 2) ? (wk + s[id]) * fmzf[id] : 0.0;
+    }
+    if (last && row0 == 0) s[base + (long long)kz * pl] = 0.0;
   }
 }
-int k_wsolve(Ctx& c, double dts) {
+int k_wsolve(Ctx& c, double dts, bool last) {
   const Geo& g = c.g;
   const double dtrdz = dts * c.rdzita;
   const double zcs2 = (dtrdz * dtrdz) * rdrcv;
   const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
-  const size_t smem = (size_t)g.kz * WS_TB * sizeof(double);
+  const size_t smem = (size_t)(4 * g.kz + 1) * WS_NJ * sizeof(double);
   const double* zsrc = c.cfg.mo_divfilter ? c.zdiv2b : c.f[MB_ZDIV2].p;
   MB_CUDA(cudaFuncSetAttribute(moloch_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LaunchScope ls(c, KID_WSOLVE);
-  moloch_wsolve<<<(unsigned)((ncol + WS_TB - 1) / WS_TB), WS_TB, smem, c.stream>>>(
-      g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.wwkw,
-      c.f[MB_FMZ].p, c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2);
+  moloch_wsolve<<<(unsigned)((ncol + WS_NJ - 1) / WS_NJ), WS_THREADS, smem, c.stream>>>(
+      g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.f[MB_FMZ].p,
+      c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0);
   MB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -25,7 +25,7 @@ from . import hostmodel as H
 from .decomp import Geom, default_cpus_per_dim, make_geom
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmoloch_b200.so")
+LIB_PATH = os.environ.get("MOLOCH_B200_LIB") or os.path.join(_HERE, "libmoloch_b200.so")
 
 FIELDS = ["u", "v", "w", "pai", "tetav", "t", "qx", "trac", "ux", "vx", "tvirt", "p", "rho", "qsat", "ps",
           "zeta", "fmz", "fmzf", "rfmzu", "rfmzv", "hx", "hy", "msfx", "msfu", "msfv", "coru", "corv",

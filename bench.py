@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--px", type=int, default=0)
     ap.add_argument("--py", type=int, default=0)
     args = ap.parse_args()
@@ -192,9 +193,15 @@ def main():
     py = args.py or None
     m = MolochB200(wl, rank=rank, nranks=world, px=px, py=py, device=local_rank).allocate_moloch()
     if world > 1:
-        ids = [MolochB200.comm_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        m.comm_init(ids[0])
+        if args.transport == "nccl":
+            ids = [MolochB200.comm_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            m.comm_init(ids[0])
+        else:   # direct NVLink peer stores between the ranks' arenas (CUDA IPC)
+            blobs = [None] * world
+            dist.all_gather_object(blobs, m.p2p_export())
+            m.p2p_connect(blobs)
+            dist.barrier()
     stream = torch.cuda.Stream()
     m.set_stream(stream.cuda_stream)
     fields, profiles = S.model_inputs(wl)
@@ -333,6 +340,7 @@ def main():
     if rank == 0:
         line = base_line(wl, args, world)
         line["config"]["decomposition"] = f"{m.g.px}x{m.g.py}"
+        line["config"]["halo_transport"] = ("none" if world == 1 else args.transport)
         line.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "e2e": e2e,
                      "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                      "kernels": kernels[:12], "finite": finite, "device_bytes": m.device_bytes()})

@@ -102,6 +102,14 @@ int moloch_b200_destroy(moloch_b200_ctx* ctx);
 int moloch_b200_comm_id(void* id128);
 int moloch_b200_comm_init(moloch_b200_ctx* ctx, const void* id128);
 
+/* Optional direct peer transport (NVLink/NVSwitch peer stores instead of NCCL
+ * send/recv): every rank exports a blob, the host all-gathers the blobs in
+ * rank order (MPI_Allgather in the shim) and every rank connects.  Call
+ * before moloch_b200_init; all ranks of a run must make the same choice.     */
+uint64_t moloch_b200_p2p_blob_size(void);
+int moloch_b200_p2p_export(moloch_b200_ctx* ctx, void* blob);
+int moloch_b200_p2p_connect(moloch_b200_ctx* ctx, const void* blobs, int nranks);
+
 /* run on a caller-owned CUDA stream (cudaStream_t) instead of the context's */
 int moloch_b200_set_stream(moloch_b200_ctx* ctx, void* cuda_stream);
 int moloch_b200_sync(moloch_b200_ctx* ctx);

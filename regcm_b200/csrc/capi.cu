@@ -34,9 +34,8 @@ LaunchScope::~LaunchScope() {
   }
 }
 
-static void build_geo(Ctx& c) {
-  const moloch_b200_config& f = c.cfg;
-  Geo& g = c.g;
+Geo geo_from_cfg(const moloch_b200_config& f) {
+  Geo g;
   g.kz = f.kz;
   g.jde1 = f.jde1; g.jde2 = f.jde2; g.ide1 = f.ide1; g.ide2 = f.ide2;
   g.jce1 = f.jce1; g.jce2 = f.jce2; g.ice1 = f.ice1; g.ice2 = f.ice2;
@@ -60,6 +59,55 @@ static void build_geo(Ctx& c) {
   nj = (nj + 3) / 4 * 4;
   g.NJ = nj; g.NI = (g.ide2 - g.ide1 + 1) + 2 * HI;
   g.plane = (long long)g.NJ * g.NI;
+  return g;
+}
+
+// number of wafone-advected fields, in the reference's order :786-807
+static int count_adv(const moloch_b200_config& f) {
+  int n = 6;
+  if (f.ipptls > 0) n += (f.nqx - f.iqfrst + 1 > 0) ? f.nqx - f.iqfrst + 1 : 0;
+  return n + f.ntr;
+}
+
+static void field_shape(const moloch_b200_config& f, int id, int& nk, int& nspec) {
+  const int kz = f.kz;
+  nspec = 1;
+  switch (id) {
+    case MB_W: case MB_FMZF: case MB_S: nk = kz + 1; break;
+    case MB_QX: case MB_QXTEN: nk = kz; nspec = f.nqx; break;
+    case MB_TRAC: case MB_CHITEN: nk = kz; nspec = f.ntr; break;
+    case MB_PS: case MB_HX: case MB_HY: case MB_MSFX: case MB_MSFU: case MB_MSFV: case MB_CORU: case MB_CORV:
+      nk = 1; break;
+    default: nk = kz; break;
+  }
+}
+
+// The arena layout is a pure function of a rank's config, so that a rank can
+// address the arrays of its neighbours inside their (peer-mapped) arenas.
+Layout make_layout(const moloch_b200_config& f) {
+  const Geo g = geo_from_cfg(f);
+  const int kz = g.kz, nadv = count_adv(f);
+  const size_t pl = (size_t)g.plane * sizeof(double);
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  Layout L;
+  L.off.assign(SL_COUNT, 0); L.size.assign(SL_COUNT, 0);
+  size_t total = 0;
+  auto put = [&](int slot, size_t bytes) { L.off[slot] = total; L.size[slot] = bytes; total += al(bytes); };
+  for (int id = 0; id < MB_NFIELDS; ++id) {
+    if (id == MB_WZ || id == MB_P0) continue;
+    int nk, nspec; field_shape(f, id, nk, nspec);
+    put(id, pl * nk * (size_t)nspec);
+  }
+  put(SL_UD, pl * kz); put(SL_VD, pl * kz); put(SL_ZB, pl * kz); put(SL_WW, pl * (kz + 1));
+  L.stride2d = al(pl); put(SL_2D, L.stride2d * 4);
+  L.stridezr = al(pl * kz); put(SL_ZR, L.stridezr * 2);
+  put(SL_WZ, pl * kz * (size_t)nadv); put(SL_P0, pl * kz * (size_t)nadv);
+  const size_t prof_len = (size_t)((kz + 2 > (g.ide2 - g.ide1 + 3)) ? kz + 2 : (g.ide2 - g.ide1 + 3));
+  L.strideprof = al(prof_len * sizeof(double)); put(SL_PROF, L.strideprof * MB_NPROFILES);
+  put(SL_TAB, sizeof(double*) * (size_t)nadv);
+  put(SL_FLAGS, 256);
+  L.total = total;
+  return L;
 }
 
 static int check_cfg(const moloch_b200_config& f) {
@@ -214,7 +262,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
     delete c;
     return fail("moloch_b200_create: cudaSetDevice failed");
   }
-  build_geo(*c);
+  c->g = geo_from_cfg(*cfg);
   const Geo& g = c->g;
   const int kz = g.kz;
   // advected fields, in the reference's order :786-807
@@ -224,40 +272,13 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
     for (int n = cfg->iqfrst; n <= cfg->nqx; ++n) adv.push_back({MB_QX, n - 1});
   for (int n = 1; n <= cfg->ntr; ++n) adv.push_back({MB_TRAC, n - 1});
   c->nadv_fields = (int)adv.size();
-  // sizes
-  auto setf = [&](int id, int nk, int nspec, bool is2d) {
-    c->f[id].nk = nk; c->f[id].nspec = nspec; c->f[id].is2d = is2d; c->f[id].klo = 1;
-  };
-  for (int id : {MB_U, MB_V, MB_PAI, MB_TETAV, MB_T, MB_UX, MB_VX, MB_TVIRT, MB_P, MB_RHO, MB_QSAT, MB_ZETA,
-                 MB_FMZ, MB_RFMZU, MB_RFMZV, MB_BDYWTU, MB_BDYWTV, MB_BDYWTW, MB_TTEN, MB_UTEN, MB_VTEN,
-                 MB_ZDIV2, MB_WX, MB_TETAVF})
-    setf(id, kz, 1, false);
-  for (int id : {MB_W, MB_FMZF, MB_S}) setf(id, kz + 1, 1, false);
-  setf(MB_QX, kz, cfg->nqx, false); setf(MB_QXTEN, kz, cfg->nqx, false);
-  setf(MB_TRAC, kz, cfg->ntr, false); setf(MB_CHITEN, kz, cfg->ntr, false);
-  for (int id : {MB_PS, MB_HX, MB_HY, MB_MSFX, MB_MSFU, MB_MSFV, MB_CORU, MB_CORV}) setf(id, 1, 1, true);
-  setf(MB_WZ, kz, 1, false); setf(MB_P0, kz, 1, false);
-  const size_t pl = (size_t)g.plane * sizeof(double);
-  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-  size_t total = 0;
-  std::vector<size_t> off(MB_NFIELDS, 0);
   for (int id = 0; id < MB_NFIELDS; ++id) {
-    if (id == MB_WZ || id == MB_P0) continue;
-    off[id] = total;
-    total += al(pl * c->f[id].nk * (size_t)c->f[id].nspec);
+    field_shape(*cfg, id, c->f[id].nk, c->f[id].nspec);
+    c->f[id].klo = 1; c->f[id].is2d = (c->f[id].nk == 1);
   }
-  const size_t o_ud = total; total += al(pl * kz);
-  const size_t o_vd = total; total += al(pl * kz);
-  const size_t o_zb = total; total += al(pl * kz);
-  const size_t o_ww = total; total += al(pl * (kz + 1));
-  const size_t o_2d = total; total += al(pl) * 4;
-  const size_t o_zr = total; total += al(pl * kz) * 2;
-  const size_t o_wz = total; total += al(pl * kz * (size_t)c->nadv_fields);
-  const size_t o_p0 = total; total += al(pl * kz * (size_t)c->nadv_fields);
-  const size_t o_prof = total;
-  const size_t prof_len = (size_t)((kz + 2 > (g.ide2 - g.ide1 + 3)) ? kz + 2 : (g.ide2 - g.ide1 + 3));
-  total += al(prof_len * sizeof(double)) * MB_NPROFILES;
-  const size_t o_tab = total; total += al(sizeof(double*) * (size_t)c->nadv_fields);
+  c->layout = make_layout(*cfg);
+  const Layout& L = c->layout;
+  const size_t total = L.total;
   cudaError_t e = cudaMalloc(&c->arena, total);
   if (e != cudaSuccess) {
     std::string m = std::string("moloch_b200_create: cudaMalloc of ") + std::to_string(total) + " bytes: " +
@@ -269,19 +290,22 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   cudaMemset(c->arena, 0, total);
   for (int id = 0; id < MB_NFIELDS; ++id) {
     if (id == MB_WZ || id == MB_P0) continue;
-    c->f[id].p = (c->f[id].nspec > 0) ? (double*)(c->arena + off[id]) : nullptr;
+    c->f[id].p = (c->f[id].nspec > 0) ? (double*)(c->arena + L.off[id]) : nullptr;
   }
-  c->ud = (double*)(c->arena + o_ud); c->vd = (double*)(c->arena + o_vd);
-  c->zdiv2b = (double*)(c->arena + o_zb); c->wwkw = (double*)(c->arena + o_ww);
-  c->mx2 = (double*)(c->arena + o_2d); c->rmx = (double*)(c->arena + o_2d + al(pl));
-  c->rmu = (double*)(c->arena + o_2d + 2 * al(pl)); c->rmv = (double*)(c->arena + o_2d + 3 * al(pl));
-  c->zru = (double*)(c->arena + o_zr); c->zrd = (double*)(c->arena + o_zr + al(pl * kz));
-  c->wzall = (double*)(c->arena + o_wz); c->p0all = (double*)(c->arena + o_p0);
+  c->ud = (double*)(c->arena + L.off[SL_UD]); c->vd = (double*)(c->arena + L.off[SL_VD]);
+  c->zdiv2b = (double*)(c->arena + L.off[SL_ZB]); c->wwkw = (double*)(c->arena + L.off[SL_WW]);
+  c->mx2 = (double*)(c->arena + L.off[SL_2D]); c->rmx = (double*)(c->arena + L.off[SL_2D] + L.stride2d);
+  c->rmu = (double*)(c->arena + L.off[SL_2D] + 2 * L.stride2d);
+  c->rmv = (double*)(c->arena + L.off[SL_2D] + 3 * L.stride2d);
+  c->zru = (double*)(c->arena + L.off[SL_ZR]); c->zrd = (double*)(c->arena + L.off[SL_ZR] + L.stridezr);
+  c->wzall = (double*)(c->arena + L.off[SL_WZ]); c->p0all = (double*)(c->arena + L.off[SL_P0]);
   c->f[MB_WZ].p = c->wzall; c->f[MB_P0].p = c->p0all;
   for (int q = 0; q < MB_NPROFILES; ++q) {
-    c->prof[q] = (double*)(c->arena + o_prof + (size_t)q * al(prof_len * sizeof(double)));
+    c->prof[q] = (double*)(c->arena + L.off[SL_PROF] + (size_t)q * L.strideprof);
     c->prof_n[q] = 0;
   }
+  c->flags = (unsigned long long*)(c->arena + L.off[SL_FLAGS]);
+  const size_t o_tab = L.off[SL_TAB];
   c->d_ptrtab = (double**)(c->arena + o_tab);
   std::vector<double*> tab;
   for (auto& a : adv) tab.push_back(c->f[a.fid].p + (size_t)a.spec * kz * g.plane);
@@ -322,6 +346,16 @@ int moloch_b200_comm_id(void* id128) {
 int moloch_b200_comm_init(moloch_b200_ctx* c, const void* id128) {
   if (!c || !id128) return fail("moloch_b200_comm_init: null argument");
   return halo_comm_init(*c, id128);
+}
+
+uint64_t moloch_b200_p2p_blob_size(void) { return (uint64_t)halo_p2p_blob_size(); }
+int moloch_b200_p2p_export(moloch_b200_ctx* c, void* blob) {
+  if (!c || !blob) return fail("p2p_export: null argument");
+  return halo_p2p_export(*c, blob);
+}
+int moloch_b200_p2p_connect(moloch_b200_ctx* c, const void* blobs, int nranks) {
+  if (!c || !blobs) return fail("p2p_connect: null argument");
+  return halo_p2p_connect(*c, blobs, nranks);
 }
 
 int moloch_b200_set_stream(moloch_b200_ctx* c, void* s) {

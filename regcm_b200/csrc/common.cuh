@@ -72,6 +72,26 @@ enum KernelId {
 
 struct ProfEvent { cudaEvent_t a, b; int kid; };
 
+// arena slots: 0..MB_NFIELDS-1 are the ABI fields, then the internal arrays
+enum Slot { SL_UD = MB_NFIELDS, SL_VD, SL_ZB, SL_WW, SL_2D, SL_ZR, SL_WZ, SL_P0, SL_PROF, SL_TAB, SL_FLAGS, SL_COUNT };
+struct Layout {
+  std::vector<size_t> off, size;  // bytes, per slot
+  size_t stride2d = 0, stridezr = 0, strideprof = 0, total = 0;
+};
+struct Geo;
+Layout make_layout(const moloch_b200_config& f);
+
+// one directly addressable neighbour (NVLink peer mapping of its arena)
+struct Peer {
+  bool mapped = false;
+  bool ipc = false;           // opened with cudaIpcOpenMemHandle (else same process)
+  char* arena = nullptr;      // peer-visible base of the neighbour's arena
+  moloch_b200_config cfg;
+  Layout layout;
+  int NJ = 0, j0 = 0, i0 = 0;
+  long long plane = 0;
+};
+
 struct Ctx;
 void halo_free(Ctx& c);
 
@@ -101,6 +121,11 @@ struct Ctx {
   double dtstepa, dtsound, rdx, rdzita;
   bool initialised = false;
   // halo transport
+  Layout layout;
+  unsigned long long* flags = nullptr;   // [0..3] arrival counters per side, [4] CTA counter, [5] timeout flag
+  unsigned long long halo_seq = 0;
+  bool p2p = false;
+  Peer peer[4];                          // left, right, bottom, top
   void* nccl_comm = nullptr;
   double *sendbuf = nullptr, *recvbuf = nullptr;
   size_t halo_buf_doubles = 0;
@@ -163,6 +188,10 @@ struct HaloItem { double* p; int nk; };
 int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt, int ext = 0);
 int halo_comm_init(Ctx& c, const void* id128);
 int halo_comm_id(void* id128);
+int halo_p2p_export(Ctx& c, void* blob);
+int halo_p2p_connect(Ctx& c, const void* blobs, int nranks);
+size_t halo_p2p_blob_size();
+Geo geo_from_cfg(const moloch_b200_config& f);
 void halo_boxes(const moloch_b200_config& cfg, int stag, int nex, bool lr, bool bt,
                 int32_t send_box[4][4], int32_t recv_box[4][4]);
 

@@ -9,6 +9,8 @@
 // one message per array).  Remote sides go through NCCL send/recv over NVLink.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <unistd.h>
+#include <cstring>
 #include "common.cuh"
 
 namespace mb {
@@ -157,7 +159,9 @@ int halo_comm_init(Ctx& c, const void* id128) {
   return 0;
 }
 
+static void halo_p2p_close(Ctx& c);
 void halo_free(Ctx& c) {
+  halo_p2p_close(c);
   if (c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl_comm);
   c.nccl_comm = nullptr;
   if (c.sendbuf) cudaFree(c.sendbuf);
@@ -184,6 +188,176 @@ static int launch_halo(Ctx& c, int mode, const HaloParams& h, double* buf, long 
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Direct peer transport (NVLink/NVSwitch): the sender's kernel stores its edge
+// cells straight into the neighbour's ghost cells (peer-mapped arena) and then
+// publishes an arrival counter; the receiver's stream waits on its counters.
+// No send/receive buffers, no unpack pass, no host involvement per exchange.
+// ---------------------------------------------------------------------------
+struct P2PBlob {
+  unsigned long long pid;
+  int device, rank;
+  void* arena;
+  cudaIpcMemHandle_t handle;
+  moloch_b200_config cfg;
+};
+size_t halo_p2p_blob_size() { return sizeof(P2PBlob); }
+
+int halo_p2p_export(Ctx& c, void* blob) {
+  P2PBlob b;
+  memset(&b, 0, sizeof(b));
+  b.pid = (unsigned long long)getpid();
+  b.device = c.device; b.rank = c.cfg.rank; b.arena = c.arena; b.cfg = c.cfg;
+  MB_CUDA(cudaSetDevice(c.device));
+  MB_CUDA(cudaIpcGetMemHandle(&b.handle, c.arena));
+  memcpy(blob, &b, sizeof(b));
+  return 0;
+}
+
+int halo_p2p_connect(Ctx& c, const void* blobs, int nranks) {
+  if (nranks != c.cfg.nranks) return fail("p2p_connect: nranks mismatch");
+  const P2PBlob* all = (const P2PBlob*)blobs;
+  const int nbr[4] = {c.cfg.nbr_left, c.cfg.nbr_right, c.cfg.nbr_bottom, c.cfg.nbr_top};
+  MB_CUDA(cudaSetDevice(c.device));
+  for (int sd = 0; sd < 4; ++sd) {
+    Peer& pr = c.peer[sd];
+    pr.mapped = false;
+    if (nbr[sd] < 0 || nbr[sd] == c.cfg.rank) continue;
+    const P2PBlob& b = all[nbr[sd]];
+    if (b.rank != nbr[sd]) return fail("p2p_connect: blob table is not indexed by rank");
+    bool shared = false;
+    for (int q = 0; q < sd; ++q)
+      if (c.peer[q].mapped && nbr[q] == nbr[sd]) { pr = c.peer[q]; shared = true; break; }
+    if (shared) continue;
+    if (b.pid == (unsigned long long)getpid()) {
+      if (b.device != c.device) {
+        int can = 0;
+        MB_CUDA(cudaDeviceCanAccessPeer(&can, c.device, b.device));
+        if (!can) return fail("p2p_connect: no peer access between the two GPUs");
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      pr.arena = (char*)b.arena; pr.ipc = false;
+    } else {
+      void* ptr = nullptr;
+      MB_CUDA(cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess));
+      pr.arena = (char*)ptr; pr.ipc = true;
+    }
+    pr.cfg = b.cfg;
+    pr.layout = make_layout(b.cfg);
+    const Geo pg = geo_from_cfg(b.cfg);
+    pr.NJ = pg.NJ; pr.j0 = pg.j0; pr.i0 = pg.i0; pr.plane = pg.plane;
+    pr.mapped = true;
+  }
+  c.p2p = true;
+  return 0;
+}
+
+static void halo_p2p_close(Ctx& c) {
+  for (int sd = 0; sd < 4; ++sd) {
+    Peer& pr = c.peer[sd];
+    if (pr.mapped && pr.ipc) {
+      bool dup = false;
+      for (int q = 0; q < sd; ++q) if (c.peer[q].mapped && c.peer[q].arena == pr.arena) dup = true;
+      if (!dup) cudaIpcCloseMemHandle(pr.arena);
+    }
+    pr.mapped = false;
+  }
+  c.p2p = false;
+}
+
+struct PushParams {
+  double* p[HALO_MAX_ITEMS];        // local arrays
+  double* q[4][HALO_MAX_ITEMS];     // the same arrays inside the neighbour's arena, per side
+  int nitems, nk, nex;
+  int j1, j2, i1, i2;
+  int elo[4], elen[4];
+  int mode[4];                      // 0 none, 1 local copy, 2 peer store
+  long long count[4];
+  int pNJ[4], pj0[4], pi0[4], dj[4], di[4];   // neighbour's padded box and index shift
+  long long pplane[4];
+  unsigned long long* pflag[4];     // neighbour's arrival counter for the side it sees me on
+  unsigned long long* ctr;          // local CTA counter
+  unsigned long long seq;
+};
+
+__device__ __forceinline__ void halo_cell2(const PushParams& h, int sd, long long e, int& item, int& k, int& js,
+                                           int& is, int& jg, int& ig) {
+  const int len = h.elen[sd];
+  const int iex = (int)(e % h.nex) + 1; e /= h.nex;
+  const int r = (int)(e % len); e /= len;
+  k = (int)(e % h.nk) + 1; item = (int)(e / h.nk);
+  switch (sd) {
+    case 0: js = h.j1 + iex - 1; jg = h.j1 - iex; is = ig = h.elo[sd] + r; break;
+    case 1: js = h.j2 - (iex - 1); jg = h.j2 + iex; is = ig = h.elo[sd] + r; break;
+    case 2: is = h.i1 + iex - 1; ig = h.i1 - iex; js = jg = h.elo[sd] + r; break;
+    default: is = h.i2 - (iex - 1); ig = h.i2 + iex; js = jg = h.elo[sd] + r; break;
+  }
+}
+
+__global__ void moloch_halo_push(Geo g, PushParams h) {
+  const long long tot = h.count[0] + h.count[1] + h.count[2] + h.count[3];
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot;
+       t += (long long)gridDim.x * blockDim.x) {
+    int sd = 0; long long e = t;
+    while (e >= h.count[sd]) { e -= h.count[sd]; ++sd; }
+    int item, k, js, is, jg, ig;
+    halo_cell2(h, sd, e, item, k, js, is, jg, ig);
+    if (h.mode[sd] == 1) {
+      int item2, k2, js2, is2, jg2, ig2;
+      halo_cell2(h, sd ^ 1, e, item2, k2, js2, is2, jg2, ig2);
+      h.p[item][gidx(g, jg, ig, k)] = h.p[item][gidx(g, js2, is2, k)];
+    } else if (h.mode[sd] == 2) {
+      const double val = h.p[item][gidx(g, js, is, k)];
+      const long long tgt = (long long)(k - 1) * h.pplane[sd] +
+                            (long long)(is + h.di[sd] - h.pi0[sd]) * h.pNJ[sd] + (js + h.dj[sd] - h.pj0[sd]);
+      h.q[sd][item][tgt] = val;
+    }
+  }
+  // publish: every CTA fences its peer stores, the last one bumps the counters
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd(h.ctr, 1ULL);
+    if (done == (unsigned long long)gridDim.x - 1ULL) {
+      *h.ctr = 0ULL;
+      __threadfence_system();
+      for (int sd = 0; sd < 4; ++sd)
+        if (h.mode[sd] == 2)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(h.pflag[sd]), "l"(h.seq) : "memory");
+    }
+  }
+}
+
+__global__ void moloch_halo_wait(unsigned long long* flags, int mask, unsigned long long seq,
+                                 long long timeout_cycles) {
+  const int sd = threadIdx.x;
+  if (sd < 4 && ((mask >> sd) & 1)) {
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + sd) : "memory");
+      if (v >= seq) break;
+      if (clock64() - t0 > timeout_cycles) { flags[5] = seq; break; }  // neighbour never arrived
+    }
+  }
+}
+
+static double* peer_ptr(Ctx& c, const Peer& pr, double* local) {
+  const size_t d = (size_t)((char*)local - c.arena);
+  const Layout& L = c.layout;
+  for (int sl = 0; sl < SL_COUNT; ++sl) {
+    if (L.size[sl] == 0 || d < L.off[sl] || d >= L.off[sl] + L.size[sl]) continue;
+    const size_t within = d - L.off[sl];
+    const size_t pb = (size_t)c.g.plane * sizeof(double);
+    if (within % pb != 0) return nullptr;
+    return (double*)(pr.arena + pr.layout.off[sl] + (within / pb) * (size_t)pr.plane * sizeof(double));
+  }
+  return nullptr;
+}
+
 // `ext` widens the edge run of every side by `ext` ghost points at each end
 // that has a neighbour: an lr exchange followed by a bt exchange with ext > 0
 // (or the other way round) also fills the corner ghosts.
@@ -192,7 +366,69 @@ int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, 
   const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
   bool any = false;
   for (int sd = 0; sd < 4; ++sd) if (nbr[sd] >= 0 && ((sd < 2) ? lr : bt)) any = true;
+  // every rank numbers the exchanges identically, active or not
+  const unsigned long long seq0 = c.halo_seq;
+  c.halo_seq += (unsigned long long)((nitems + HALO_MAX_ITEMS - 1) / HALO_MAX_ITEMS);
   if (!any || nitems == 0) return 0;
+  if (c.p2p) {
+    for (int first = 0, chunk = 0; first < nitems; first += HALO_MAX_ITEMS, ++chunk) {
+      const int n = (nitems - first < HALO_MAX_ITEMS) ? nitems - first : HALO_MAX_ITEMS;
+      PushParams h;
+      memset(&h, 0, sizeof(h));
+      h.nitems = n; h.nk = items[first].nk; h.nex = nex;
+      owned_box(cf, stag, h.j1, h.j2, h.i1, h.i2);
+      h.seq = seq0 + (unsigned long long)chunk + 1ULL;
+      h.ctr = c.flags + 4;
+      long long tot = 0;
+      int mask = 0;
+      for (int sd = 0; sd < 4; ++sd) {
+        const bool on = (nbr[sd] >= 0) && ((sd < 2) ? lr : bt);
+        if (sd < 2) { h.elo[sd] = h.i1 - ext * c.g.gb; h.elen[sd] = (h.i2 + ext * c.g.gt) - h.elo[sd] + 1; }
+        else { h.elo[sd] = h.j1 - ext * c.g.gl; h.elen[sd] = (h.j2 + ext * c.g.gr) - h.elo[sd] + 1; }
+        h.mode[sd] = !on ? 0 : (nbr[sd] == cf.rank ? 1 : 2);
+        h.count[sd] = on ? (long long)n * h.nk * h.elen[sd] * nex : 0;
+        tot += h.count[sd];
+        if (h.mode[sd] == 2) {
+          const Peer& pr = c.peer[sd];
+          if (!pr.mapped) return fail("halo_exchange: neighbour not peer-mapped (p2p_connect incomplete)");
+          int pj1, pj2, pi1, pi2;
+          owned_box(pr.cfg, stag, pj1, pj2, pi1, pi2);
+          h.dj[sd] = 0; h.di[sd] = 0;
+          if (sd == 0) h.dj[sd] = (pj2 + 1) - h.j1;
+          else if (sd == 1) h.dj[sd] = (pj1 - 1) - h.j2;
+          else if (sd == 2) h.di[sd] = (pi2 + 1) - h.i1;
+          else h.di[sd] = (pi1 - 1) - h.i2;
+          h.pNJ[sd] = pr.NJ; h.pj0[sd] = pr.j0; h.pi0[sd] = pr.i0; h.pplane[sd] = pr.plane;
+          h.pflag[sd] = (unsigned long long*)(pr.arena + pr.layout.off[SL_FLAGS]) + (sd ^ 1);
+          mask |= 1 << sd;
+        }
+      }
+      for (int q = 0; q < n; ++q) {
+        if (items[first + q].nk != h.nk) return fail("halo_exchange: mixed level counts in one batch");
+        h.p[q] = items[first + q].p;
+        for (int sd = 0; sd < 4; ++sd)
+          if (h.mode[sd] == 2) {
+            h.q[sd][q] = peer_ptr(c, c.peer[sd], items[first + q].p);
+            if (!h.q[sd][q]) return fail("halo_exchange: array is not addressable in the neighbour's arena");
+          }
+      }
+      const int tb = 256;
+      long long nb = (tot + tb - 1) / tb;
+      if (nb > 148 * 8) nb = 148 * 8;
+      if (nb < 1) nb = 1;
+      {
+        LaunchScope ls(c, KID_HALO);
+        moloch_halo_push<<<(unsigned)nb, tb, 0, c.stream>>>(c.g, h);
+        MB_CUDA(cudaGetLastError());
+      }
+      if (mask) {
+        LaunchScope ls(c, KID_HALO_UNPACK);
+        moloch_halo_wait<<<1, 32, 0, c.stream>>>(c.flags, mask, h.seq, 6000000000LL);
+        MB_CUDA(cudaGetLastError());
+      }
+    }
+    return 0;
+  }
   for (int first = 0; first < nitems; first += HALO_MAX_ITEMS) {
     const int n = (nitems - first < HALO_MAX_ITEMS) ? nitems - first : HALO_MAX_ITEMS;
     HaloParams h;

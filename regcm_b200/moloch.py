@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "moloch_b200_sound", "moloch_b200_advection", "moloch_b200_wafone", "moloch_b200_dynamical_core",
     "moloch_b200_diagnostics", "moloch_b200_status_update", "moloch_b200_step", "moloch_b200_profile_enable",
     "moloch_b200_profile_read", "moloch_b200_launch_count", "moloch_b200_device_bytes",
-    "moloch_b200_halo_plan",
+    "moloch_b200_halo_plan", "moloch_b200_p2p_blob_size", "moloch_b200_p2p_export", "moloch_b200_p2p_connect",
 ]
 
 
@@ -81,6 +81,9 @@ def load_library():
     lib.moloch_b200_comm_id.argtypes = [C.c_void_p]
     lib.moloch_b200_comm_init.argtypes = [ctx, C.c_void_p]
     lib.moloch_b200_set_stream.argtypes = [ctx, C.c_void_p]
+    lib.moloch_b200_p2p_blob_size.restype = C.c_uint64
+    lib.moloch_b200_p2p_export.argtypes = [ctx, C.c_void_p]
+    lib.moloch_b200_p2p_connect.argtypes = [ctx, C.c_void_p, C.c_int]
     lib.moloch_b200_sync.argtypes = [ctx]
     xf = [ctx, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 6
     lib.moloch_b200_set_field.argtypes = xf
@@ -159,6 +162,19 @@ class MolochB200:
     def comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         self._chk(self.lib.moloch_b200_comm_init(self.ctx, buf))
+
+    def p2p_export(self) -> bytes:
+        """This rank's blob for the direct peer transport (all-gather them)."""
+        n = int(self.lib.moloch_b200_p2p_blob_size())
+        buf = C.create_string_buffer(n)
+        self._chk(self.lib.moloch_b200_p2p_export(self.ctx, buf))
+        return buf.raw
+
+    def p2p_connect(self, blobs: list):
+        """blobs: every rank's p2p_export(), in rank order."""
+        raw = b"".join(blobs)
+        buf = C.create_string_buffer(raw, len(raw))
+        self._chk(self.lib.moloch_b200_p2p_connect(self.ctx, buf, len(blobs)))
 
     @staticmethod
     def comm_id() -> bytes:

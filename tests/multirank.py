@@ -12,22 +12,32 @@ from regcm_b200.moloch import MolochB200
 
 
 class MultiRank:
-    def __init__(self, wl, px, py, fields, profiles, devices=None):
+    def __init__(self, wl, px, py, fields, profiles, devices=None, transport="p2p"):
         self.wl, self.n = wl, px * py
         devices = devices or list(range(self.n))
-        uid = MolochB200.comm_id() if self.n > 1 else None
+        uid = MolochB200.comm_id() if (self.n > 1 and transport == "nccl") else None
         self.ranks = [None] * self.n
+        blobs = [None] * self.n
+        bar = threading.Barrier(self.n)
         errs = []
 
         def boot(r):
             try:
                 m = MolochB200(wl, rank=r, nranks=self.n, px=px, py=py, device=devices[r]).allocate_moloch()
-                if self.n > 1:
-                    m.comm_init(uid)
-                m.init_moloch(fields, profiles)
                 self.ranks[r] = m
+                if self.n > 1 and transport == "p2p":
+                    blobs[r] = m.p2p_export()
+                bar.wait(timeout=120)
+                if self.n > 1:
+                    if transport == "nccl":
+                        m.comm_init(uid)
+                    else:
+                        m.p2p_connect(blobs)
+                bar.wait(timeout=120)
+                m.init_moloch(fields, profiles)
             except Exception as e:  # noqa: BLE001
                 errs.append((r, e))
+                bar.abort()
         self._par(boot)
         if errs:
             raise RuntimeError(f"rank boot failed: {errs}")

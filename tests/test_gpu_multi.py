@@ -29,13 +29,16 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("name,wl,px,py", CASES, ids=[c[0] for c in CASES])
-def test_decomposed_bit_exact(name, wl, px, py):
+def test_decomposed_bit_exact(name, wl, px, py, transport):
     if ndev() < px * py:
         pytest.skip(f"needs {px * py} GPUs")
+    if transport == "nccl" and name not in ("periodic", "limited_area_2x2", "band_2x4"):
+        pytest.skip("NCCL transport is covered by three representative cases")
     o, _ = make_oracle(wl)
     fields, profiles = oracle_inputs(o, wl)
-    mr = MultiRank(wl, px, py, fields, profiles)
+    mr = MultiRank(wl, px, py, fields, profiles, transport=transport)
     try:
         for n in (1, 3):
             o.step(n)

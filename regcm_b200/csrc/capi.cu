@@ -142,10 +142,11 @@ static int do_sound(Ctx& c) {
   if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :562
   if (k_tetavf_init(c)) return 1;
   for (int ns = 0; ns < c.cfg.mo_nsound; ++ns) {
-    it = {c.f[MB_U].p, kz};
-    if (halo_exchange(c, &it, 1, HS_U, 1, true, false)) return 1;   // :570
-    it = {c.f[MB_V].p, kz};
-    if (halo_exchange(c, &it, 1, HS_V, 1, false, true)) return 1;   // :571
+    {   // :570-571, one round
+      const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
+      const HaloSpec sp[2] = {{&iu, 1, HS_U, 1, true, false, 0}, {&iv, 1, HS_V, 1, false, true, 0}};
+      if (halo_exchange_multi(c, sp, 2)) return 1;
+    }
     if (k_sound_pre(c, dts)) return 1;
     if (c.cfg.mo_divdamp || c.cfg.mo_divfilter) {
       it = {c.f[MB_ZDIV2].p, kz};
@@ -173,10 +174,16 @@ static int do_wafone_range(Ctx& c, int first, int count) {
     if (k_waf_z2(c, first, count, dta)) return 1;
     for (int q = 0; q < count; ++q) items[q] = {c.wzall + q * fsz, kz};
     if (halo_exchange(c, items.data(), count, HS_CROSS, 2, false, true)) return 1;
-    if (halo_exchange(c, items.data(), count, HS_CROSS, 2, true, false, 2)) return 1;
-    // pre-advection pp snapshot (written by the vertical kernel) on two ghost columns
-    for (int q = 0; q < count; ++q) items[q] = {c.p0all + q * fsz, kz};
-    if (halo_exchange(c, items.data(), count, HS_CROSS, 2, true, false)) return 1;
+    // second round, left/right incl. the ghost rows (corners): wz, the
+    // pre-advection pp snapshot written by the vertical kernel, and v (whose
+    // ghost rows came with :1533)
+    std::vector<HaloItem> snap((size_t)count);
+    for (int q = 0; q < count; ++q) snap[q] = {c.p0all + q * fsz, kz};
+    const HaloItem iv = {c.f[MB_V].p, kz};
+    const HaloSpec sp[3] = {{items.data(), count, HS_CROSS, 2, true, false, 2},
+                            {snap.data(), count, HS_CROSS, 2, true, false, 2},
+                            {&iv, 1, HS_CROSS, 2, true, false, 2}};
+    if (halo_exchange_multi(c, sp, 3)) return 1;
     return k_waf_yx(c, first, count, dta);
   }
   if (k_waf_z(c, first, count, dta)) return 1;
@@ -190,21 +197,19 @@ static int do_wafone_range(Ctx& c, int first, int count) {
 
 static int do_advection(Ctx& c) {
   const int kz = c.g.kz;
-  HaloItem it;
-  it = {c.f[MB_U].p, kz};
-  if (halo_exchange(c, &it, 1, HS_U, 2, true, false)) return 1;  // :1532
-  it = {c.f[MB_V].p, kz};
-  if (halo_exchange(c, &it, 1, HS_V, 2, false, true)) return 1;  // :1533
-  if (c.waf_impl == 2) {  // v on two ghost columns (incl. ghost rows) for the fused horizontal pass
-    if (halo_exchange(c, &it, 1, HS_V, 2, true, false, 2)) return 1;
+  {   // :1532-1533, one round
+    const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
+    const HaloSpec sp[2] = {{&iu, 1, HS_U, 2, true, false, 0}, {&iv, 1, HS_V, 2, false, true, 0}};
+    if (halo_exchange_multi(c, sp, 2)) return 1;
   }
   if (k_destagger(c)) return 1;
   if (do_wafone_range(c, 0, c.nadv_fields)) return 1;             // :786-807
   if (k_curvature(c, c.dtstepa)) return 1;
-  it = {c.f[MB_UX].p, kz};
-  if (halo_exchange(c, &it, 1, HS_CROSS, 2, true, false)) return 1;  // :1485
-  it = {c.f[MB_VX].p, kz};
-  if (halo_exchange(c, &it, 1, HS_CROSS, 2, false, true)) return 1;  // :1486
+  {   // :1485-1486, one round
+    const HaloItem iu = {c.f[MB_UX].p, kz}, iv = {c.f[MB_VX].p, kz};
+    const HaloSpec sp[2] = {{&iu, 1, HS_CROSS, 2, true, false, 0}, {&iv, 1, HS_CROSS, 2, false, true, 0}};
+    if (halo_exchange_multi(c, sp, 2)) return 1;
+  }
   return k_restagger(c, true);
 }
 
@@ -219,11 +224,11 @@ static int do_dynamical_core(Ctx& c) {
 static int do_status_update(Ctx& c) {
   const int kz = c.g.kz;
   if (k_status_update(c, c.cfg.dtsec)) return 1;
-  HaloItem it;
-  it = {c.f[MB_UX].p, kz};
-  if (halo_exchange(c, &it, 1, HS_CROSS, 2, true, false)) return 1;
-  it = {c.f[MB_VX].p, kz};
-  if (halo_exchange(c, &it, 1, HS_CROSS, 2, false, true)) return 1;
+  {
+    const HaloItem iu = {c.f[MB_UX].p, kz}, iv = {c.f[MB_VX].p, kz};
+    const HaloSpec sp[2] = {{&iu, 1, HS_CROSS, 2, true, false, 0}, {&iv, 1, HS_CROSS, 2, false, true, 0}};
+    if (halo_exchange_multi(c, sp, 2)) return 1;
+  }
   return k_restagger(c, false);
 }
 

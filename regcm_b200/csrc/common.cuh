@@ -186,6 +186,8 @@ int k_waf_yx(Ctx& c, int first, int count, double dta);
 enum HaloStag { HS_CROSS = 0, HS_U, HS_V, HS_DOT, HS_P0 };
 struct HaloItem { double* p; int nk; };
 int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt, int ext = 0);
+struct HaloSpec { const HaloItem* items; int n; int stag; int nex; bool lr, bt; int ext; };
+int halo_exchange_multi(Ctx& c, const HaloSpec* specs, int nspecs);
 int halo_comm_init(Ctx& c, const void* id128);
 int halo_comm_id(void* id128);
 int halo_p2p_export(Ctx& c, void* blob);

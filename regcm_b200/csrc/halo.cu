@@ -268,27 +268,36 @@ static void halo_p2p_close(Ctx& c) {
   c.p2p = false;
 }
 
+int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt, int ext);
+constexpr int PUSH_MAX_ITEMS = 48, PUSH_MAX_GROUPS = 4;
+struct PushGroup {
+  int j1, j2, i1, i2;        // owned box of the group's staggering
+  int elo[4], elen[4];       // edge run of each side
+  int dj[4], di[4];          // index shift into the neighbour's numbering (periodic wrap)
+  int nk, nex, first, n;     // levels, width, first item, item count
+  long long count[4];        // elements per side (0 = side not part of this group)
+};
 struct PushParams {
-  double* p[HALO_MAX_ITEMS];        // local arrays
-  double* q[4][HALO_MAX_ITEMS];     // the same arrays inside the neighbour's arena, per side
-  int nitems, nk, nex;
-  int j1, j2, i1, i2;
-  int elo[4], elen[4];
+  double* p[PUSH_MAX_ITEMS];        // local arrays
+  double* q[4][PUSH_MAX_ITEMS];     // the same arrays inside the neighbour's arena, per side
+  PushGroup grp[PUSH_MAX_GROUPS];
+  int ngroups;
   int mode[4];                      // 0 none, 1 local copy, 2 peer store
-  long long count[4];
-  int pNJ[4], pj0[4], pi0[4], dj[4], di[4];   // neighbour's padded box and index shift
+  int pNJ[4], pj0[4], pi0[4];       // neighbour's padded box
   long long pplane[4];
   unsigned long long* pflag[4];     // neighbour's arrival counter for the side it sees me on
-  unsigned long long* ctr;          // local CTA counter
+  unsigned long long* flags;        // my own counters [0..3], CTA counter [4], timeout flag [5]
   unsigned long long seq;
+  int mask;                         // remote sides taking part in this round
+  long long timeout_cycles;
 };
 
-__device__ __forceinline__ void halo_cell2(const PushParams& h, int sd, long long e, int& item, int& k, int& js,
-                                           int& is, int& jg, int& ig) {
+__device__ __forceinline__ void push_cell(const PushGroup& h, int sd, long long e, int& item, int& k, int& js,
+                                          int& is, int& jg, int& ig) {
   const int len = h.elen[sd];
   const int iex = (int)(e % h.nex) + 1; e /= h.nex;
   const int r = (int)(e % len); e /= len;
-  k = (int)(e % h.nk) + 1; item = (int)(e / h.nk);
+  k = (int)(e % h.nk) + 1; item = h.first + (int)(e / h.nk);
   switch (sd) {
     case 0: js = h.j1 + iex - 1; jg = h.j1 - iex; is = ig = h.elo[sd] + r; break;
     case 1: js = h.j2 - (iex - 1); jg = h.j2 + iex; is = ig = h.elo[sd] + r; break;
@@ -297,50 +306,52 @@ __device__ __forceinline__ void halo_cell2(const PushParams& h, int sd, long lon
   }
 }
 
+// One launch = one exchange round: every edge cell of every array of the round
+// is stored straight into the neighbour's ghost cell (or copied locally for a
+// periodic self-neighbour); the last CTA then publishes the round number to the
+// neighbours and waits until theirs has arrived here.
 __global__ void moloch_halo_push(Geo g, PushParams h) {
-  const long long tot = h.count[0] + h.count[1] + h.count[2] + h.count[3];
+  long long tot = 0;
+  for (int q = 0; q < h.ngroups; ++q) tot += h.grp[q].count[0] + h.grp[q].count[1] + h.grp[q].count[2] + h.grp[q].count[3];
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot;
        t += (long long)gridDim.x * blockDim.x) {
-    int sd = 0; long long e = t;
-    while (e >= h.count[sd]) { e -= h.count[sd]; ++sd; }
+    int gq = 0, sd = 0; long long e = t;
+    while (e >= h.grp[gq].count[sd]) { e -= h.grp[gq].count[sd]; if (++sd == 4) { sd = 0; ++gq; } }
+    const PushGroup& G = h.grp[gq];
     int item, k, js, is, jg, ig;
-    halo_cell2(h, sd, e, item, k, js, is, jg, ig);
+    push_cell(G, sd, e, item, k, js, is, jg, ig);
     if (h.mode[sd] == 1) {
       int item2, k2, js2, is2, jg2, ig2;
-      halo_cell2(h, sd ^ 1, e, item2, k2, js2, is2, jg2, ig2);
+      push_cell(G, sd ^ 1, e, item2, k2, js2, is2, jg2, ig2);
       h.p[item][gidx(g, jg, ig, k)] = h.p[item][gidx(g, js2, is2, k)];
-    } else if (h.mode[sd] == 2) {
+    } else {
       const double val = h.p[item][gidx(g, js, is, k)];
       const long long tgt = (long long)(k - 1) * h.pplane[sd] +
-                            (long long)(is + h.di[sd] - h.pi0[sd]) * h.pNJ[sd] + (js + h.dj[sd] - h.pj0[sd]);
+                            (long long)(is + G.di[sd] - h.pi0[sd]) * h.pNJ[sd] + (js + G.dj[sd] - h.pj0[sd]);
       h.q[sd][item][tgt] = val;
     }
   }
-  // publish: every CTA fences its peer stores, the last one bumps the counters
+  if (h.mask == 0) return;
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned long long done = atomicAdd(h.ctr, 1ULL);
+    const unsigned long long done = atomicAdd(h.flags + 4, 1ULL);
     if (done == (unsigned long long)gridDim.x - 1ULL) {
-      *h.ctr = 0ULL;
+      h.flags[4] = 0ULL;
       __threadfence_system();
       for (int sd = 0; sd < 4; ++sd)
-        if (h.mode[sd] == 2)
+        if ((h.mask >> sd) & 1)
           asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(h.pflag[sd]), "l"(h.seq) : "memory");
-    }
-  }
-}
-
-__global__ void moloch_halo_wait(unsigned long long* flags, int mask, unsigned long long seq,
-                                 long long timeout_cycles) {
-  const int sd = threadIdx.x;
-  if (sd < 4 && ((mask >> sd) & 1)) {
-    const long long t0 = clock64();
-    for (;;) {
-      unsigned long long v;
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + sd) : "memory");
-      if (v >= seq) break;
-      if (clock64() - t0 > timeout_cycles) { flags[5] = seq; break; }  // neighbour never arrived
+      const long long t0 = clock64();
+      for (int sd = 0; sd < 4; ++sd) {
+        if (!((h.mask >> sd) & 1)) continue;
+        for (;;) {
+          unsigned long long v;
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(h.flags + sd) : "memory");
+          if (v >= h.seq) break;
+          if (clock64() - t0 > h.timeout_cycles) { h.flags[5] = h.seq; break; }  // neighbour never arrived
+        }
+      }
     }
   }
 }
@@ -358,6 +369,81 @@ static double* peer_ptr(Ctx& c, const Peer& pr, double* local) {
   return nullptr;
 }
 
+// A round of independent exchanges in one launch (P2P transport); with NCCL the
+// specs are exchanged one after the other.
+int halo_exchange_multi(Ctx& c, const HaloSpec* specs, int nspecs) {
+  if (!c.p2p) {
+    for (int q = 0; q < nspecs; ++q)
+      if (halo_exchange(c, specs[q].items, specs[q].n, specs[q].stag, specs[q].nex, specs[q].lr, specs[q].bt,
+                        specs[q].ext)) return 1;
+    return 0;
+  }
+  const moloch_b200_config& cf = c.cfg;
+  const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
+  int sp = 0, done_in_spec = 0;
+  while (sp < nspecs) {
+    // every rank numbers the rounds identically, whether it takes part or not
+    PushParams h;
+    memset(&h, 0, sizeof(h));
+    h.seq = ++c.halo_seq;
+    h.flags = c.flags;
+    h.timeout_cycles = 6000000000LL;
+    for (int sd = 0; sd < 4; ++sd) h.mode[sd] = (nbr[sd] < 0) ? 0 : (nbr[sd] == cf.rank ? 1 : 2);
+    int nit = 0;
+    long long tot = 0;
+    while (sp < nspecs && h.ngroups < PUSH_MAX_GROUPS && nit < PUSH_MAX_ITEMS) {
+      const HaloSpec& S = specs[sp];
+      const int take = (S.n - done_in_spec < PUSH_MAX_ITEMS - nit) ? S.n - done_in_spec : PUSH_MAX_ITEMS - nit;
+      if (take > 0) {
+        PushGroup& G = h.grp[h.ngroups++];
+        owned_box(cf, S.stag, G.j1, G.j2, G.i1, G.i2);
+        G.nk = S.items[done_in_spec].nk; G.nex = S.nex; G.first = nit; G.n = take;
+        for (int sd = 0; sd < 4; ++sd) {
+          const bool on = (nbr[sd] >= 0) && ((sd < 2) ? S.lr : S.bt);
+          if (sd < 2) { G.elo[sd] = G.i1 - S.ext * c.g.gb; G.elen[sd] = (G.i2 + S.ext * c.g.gt) - G.elo[sd] + 1; }
+          else { G.elo[sd] = G.j1 - S.ext * c.g.gl; G.elen[sd] = (G.j2 + S.ext * c.g.gr) - G.elo[sd] + 1; }
+          G.count[sd] = on ? (long long)take * G.nk * G.elen[sd] * S.nex : 0;
+          tot += G.count[sd];
+          if (on && h.mode[sd] == 2) {
+            const Peer& pr = c.peer[sd];
+            if (!pr.mapped) return fail("halo_exchange: neighbour not peer-mapped (p2p_connect incomplete)");
+            int pj1, pj2, pi1, pi2;
+            owned_box(pr.cfg, S.stag, pj1, pj2, pi1, pi2);
+            if (sd == 0) G.dj[sd] = (pj2 + 1) - G.j1;
+            else if (sd == 1) G.dj[sd] = (pj1 - 1) - G.j2;
+            else if (sd == 2) G.di[sd] = (pi2 + 1) - G.i1;
+            else G.di[sd] = (pi1 - 1) - G.i2;
+            h.pNJ[sd] = pr.NJ; h.pj0[sd] = pr.j0; h.pi0[sd] = pr.i0; h.pplane[sd] = pr.plane;
+            h.pflag[sd] = (unsigned long long*)(pr.arena + pr.layout.off[SL_FLAGS]) + (sd ^ 1);
+            h.mask |= 1 << sd;
+          }
+        }
+        for (int q = 0; q < take; ++q) {
+          const HaloItem& it = S.items[done_in_spec + q];
+          if (it.nk != G.nk) return fail("halo_exchange: mixed level counts in one batch");
+          h.p[nit + q] = it.p;
+          for (int sd = 0; sd < 4; ++sd)
+            if (G.count[sd] > 0 && h.mode[sd] == 2) {
+              h.q[sd][nit + q] = peer_ptr(c, c.peer[sd], it.p);
+              if (!h.q[sd][nit + q]) return fail("halo_exchange: array is not addressable in the neighbour's arena");
+            }
+        }
+        nit += take;
+        done_in_spec += take;
+      }
+      if (done_in_spec >= S.n) { ++sp; done_in_spec = 0; }
+    }
+    if (tot == 0) continue;   // nothing to move for this rank in this round
+    const int tb = 256;
+    long long nb = (tot + tb - 1) / tb;
+    if (nb > 148 * 8) nb = 148 * 8;
+    LaunchScope ls(c, KID_HALO);
+    moloch_halo_push<<<(unsigned)nb, tb, 0, c.stream>>>(c.g, h);
+    MB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
 // `ext` widens the edge run of every side by `ext` ghost points at each end
 // that has a neighbour: an lr exchange followed by a bt exchange with ext > 0
 // (or the other way round) also fills the corner ghosts.
@@ -366,69 +452,11 @@ int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, 
   const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
   bool any = false;
   for (int sd = 0; sd < 4; ++sd) if (nbr[sd] >= 0 && ((sd < 2) ? lr : bt)) any = true;
-  // every rank numbers the exchanges identically, active or not
-  const unsigned long long seq0 = c.halo_seq;
-  c.halo_seq += (unsigned long long)((nitems + HALO_MAX_ITEMS - 1) / HALO_MAX_ITEMS);
-  if (!any || nitems == 0) return 0;
   if (c.p2p) {
-    for (int first = 0, chunk = 0; first < nitems; first += HALO_MAX_ITEMS, ++chunk) {
-      const int n = (nitems - first < HALO_MAX_ITEMS) ? nitems - first : HALO_MAX_ITEMS;
-      PushParams h;
-      memset(&h, 0, sizeof(h));
-      h.nitems = n; h.nk = items[first].nk; h.nex = nex;
-      owned_box(cf, stag, h.j1, h.j2, h.i1, h.i2);
-      h.seq = seq0 + (unsigned long long)chunk + 1ULL;
-      h.ctr = c.flags + 4;
-      long long tot = 0;
-      int mask = 0;
-      for (int sd = 0; sd < 4; ++sd) {
-        const bool on = (nbr[sd] >= 0) && ((sd < 2) ? lr : bt);
-        if (sd < 2) { h.elo[sd] = h.i1 - ext * c.g.gb; h.elen[sd] = (h.i2 + ext * c.g.gt) - h.elo[sd] + 1; }
-        else { h.elo[sd] = h.j1 - ext * c.g.gl; h.elen[sd] = (h.j2 + ext * c.g.gr) - h.elo[sd] + 1; }
-        h.mode[sd] = !on ? 0 : (nbr[sd] == cf.rank ? 1 : 2);
-        h.count[sd] = on ? (long long)n * h.nk * h.elen[sd] * nex : 0;
-        tot += h.count[sd];
-        if (h.mode[sd] == 2) {
-          const Peer& pr = c.peer[sd];
-          if (!pr.mapped) return fail("halo_exchange: neighbour not peer-mapped (p2p_connect incomplete)");
-          int pj1, pj2, pi1, pi2;
-          owned_box(pr.cfg, stag, pj1, pj2, pi1, pi2);
-          h.dj[sd] = 0; h.di[sd] = 0;
-          if (sd == 0) h.dj[sd] = (pj2 + 1) - h.j1;
-          else if (sd == 1) h.dj[sd] = (pj1 - 1) - h.j2;
-          else if (sd == 2) h.di[sd] = (pi2 + 1) - h.i1;
-          else h.di[sd] = (pi1 - 1) - h.i2;
-          h.pNJ[sd] = pr.NJ; h.pj0[sd] = pr.j0; h.pi0[sd] = pr.i0; h.pplane[sd] = pr.plane;
-          h.pflag[sd] = (unsigned long long*)(pr.arena + pr.layout.off[SL_FLAGS]) + (sd ^ 1);
-          mask |= 1 << sd;
-        }
-      }
-      for (int q = 0; q < n; ++q) {
-        if (items[first + q].nk != h.nk) return fail("halo_exchange: mixed level counts in one batch");
-        h.p[q] = items[first + q].p;
-        for (int sd = 0; sd < 4; ++sd)
-          if (h.mode[sd] == 2) {
-            h.q[sd][q] = peer_ptr(c, c.peer[sd], items[first + q].p);
-            if (!h.q[sd][q]) return fail("halo_exchange: array is not addressable in the neighbour's arena");
-          }
-      }
-      const int tb = 256;
-      long long nb = (tot + tb - 1) / tb;
-      if (nb > 148 * 8) nb = 148 * 8;
-      if (nb < 1) nb = 1;
-      {
-        LaunchScope ls(c, KID_HALO);
-        moloch_halo_push<<<(unsigned)nb, tb, 0, c.stream>>>(c.g, h);
-        MB_CUDA(cudaGetLastError());
-      }
-      if (mask) {
-        LaunchScope ls(c, KID_HALO_UNPACK);
-        moloch_halo_wait<<<1, 32, 0, c.stream>>>(c.flags, mask, h.seq, 6000000000LL);
-        MB_CUDA(cudaGetLastError());
-      }
-    }
-    return 0;
+    HaloSpec sp = {items, nitems, stag, nex, lr, bt, ext};
+    return halo_exchange_multi(c, &sp, 1);
   }
+  if (!any || nitems == 0) return 0;
   for (int first = 0; first < nitems; first += HALO_MAX_ITEMS) {
     const int n = (nitems - first < HALO_MAX_ITEMS) ? nitems - first : HALO_MAX_ITEMS;
     HaloParams h;

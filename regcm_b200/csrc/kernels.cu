@@ -97,10 +97,13 @@ int k_tetavf_init(Ctx& c) {
 }
 
 // ---------------------------------------------------------------------------
-// K2+K3+K4  ud/vd snapshots, partial s, horizontal divergence zdiv2   :573-618
+// K3+K4  partial s, horizontal divergence zdiv2                       :582-618
+// (the ud/vd snapshots of :573-578 are not materialised: divergence damping
+// writes its result to ud/vd instead of u/v, so u/v keep the pre-damping values
+// the Coriolis terms need)
 // ---------------------------------------------------------------------------
 __global__ void moloch_sound_pre(Geo g, const double* __restrict__ u, const double* __restrict__ v,
-                                 double* __restrict__ ud, double* __restrict__ vd, double* __restrict__ s,
+                                 double* __restrict__ s,
                                  double* __restrict__ w, double* __restrict__ zdiv2,
                                  const double* __restrict__ fmz, const double* __restrict__ rfmzu,
                                  const double* __restrict__ rfmzv, const double* __restrict__ hx,
@@ -115,10 +118,8 @@ __global__ void moloch_sound_pre(Geo g, const double* __restrict__ u, const doub
   const int kz = g.kz;
   const bool inu = (i >= g.ice1 && i <= g.ice2);
   const bool inv = (j >= g.jce1 && j <= g.jce2);
-  const double u0 = u[id], v0 = v[id];
-  if (inu) ud[id] = u0;
-  if (inv) vd[id] = v0;
   if (!(inu && inv)) return;
+  const double u0 = u[id], v0 = v[id];
   const double u1 = u[id + 1], v1 = v[id + g.NJ];
   {
     const double zvm = dtrdy * v0 * rfmzv[id] * rmv[i2];
@@ -154,7 +155,7 @@ int k_sound_pre(Ctx& c, double dts) {
   const double dtrdx = dts * c.rdx, dtrdy = dts * c.rdx;
   LaunchScope ls(c, KID_SOUND_PRE);
   moloch_sound_pre<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
-      g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_ZDIV2].p, c.f[MB_FMZ].p,
+      g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_ZDIV2].p, c.f[MB_FMZ].p,
       c.f[MB_RFMZU].p, c.f[MB_RFMZV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFX].p, c.mx2, c.rmu, c.rmv,
       c.prof[MB_GZITAK], dtrdx, dtrdy);
   MB_CUDA(cudaGetLastError());
@@ -163,9 +164,10 @@ int k_sound_pre(Ctx& c, double dts) {
 
 // ---------------------------------------------------------------------------
 // K5+K6  divergence damping of u,v and 5-point filter of zdiv2   :738-765,531-543
-// zdiv2 (halo 1 valid) -> zdiv2b (interior); u,v updated in place.
+// zdiv2 (halo 1 valid) -> zdiv2b (interior); damped u,v -> ud,vd.
 // ---------------------------------------------------------------------------
-__global__ void moloch_divdamp_filter(Geo g, double* __restrict__ u, double* __restrict__ v,
+__global__ void moloch_divdamp_filter(Geo g, const double* __restrict__ u, const double* __restrict__ v,
+                                      double* __restrict__ ud, double* __restrict__ vd,
                                       const double* __restrict__ zdiv2, double* __restrict__ zdiv2b,
                                       const double* __restrict__ mu, const double* __restrict__ mv,
                                       const double* __restrict__ xkdamp, const double* __restrict__ xknu,
@@ -179,11 +181,11 @@ __global__ void moloch_divdamp_filter(Geo g, double* __restrict__ u, double* __r
   if (do_damp) {
     if (in_box(j, i, g.jdi1, g.jdi2, g.ici1, g.ici2)) {
       const double xdam = dxrdt * xkdamp[k] * mu[i2];
-      u[id] = u[id] + xdam * (z0 - zw);
+      ud[id] = u[id] + xdam * (z0 - zw);   // damped u; u itself keeps the :574 snapshot
     }
     if (in_box(j, i, g.jci1, g.jci2, g.idi1, g.idi2)) {
       const double xdam = g.lrotllr ? dxrdt * xkdamp[k] : dxrdt * xkdamp[k] * mv[i2];
-      v[id] = v[id] + xdam * (z0 - zs);
+      vd[id] = v[id] + xdam * (z0 - zs);
     }
   }
   if (do_filter && in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) {
@@ -195,7 +197,7 @@ int k_divdamp_filter(Ctx& c, double dts) {
   const Geo& g = c.g;
   LaunchScope ls(c, KID_DIVDAMP);
   moloch_divdamp_filter<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
-      g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_ZDIV2].p, c.zdiv2b, c.f[MB_MSFU].p, c.f[MB_MSFV].p,
+      g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_ZDIV2].p, c.zdiv2b, c.f[MB_MSFU].p, c.f[MB_MSFV].p,
       c.prof[MB_XKDAMP], c.prof[MB_XKNU], c.cfg.dx / dts, c.cfg.mo_divdamp, c.cfg.mo_divfilter);
   MB_CUDA(cudaGetLastError());
   return 0;
@@ -207,8 +209,9 @@ int k_divdamp_filter(Ctx& c, double dts) {
 // One thread per column; the finished divergence of the column is parked in
 // shared memory (thread-private slots, no barriers).
 // ---------------------------------------------------------------------------
-constexpr int WS_NJ = 32;        // columns per CTA
-constexpr int WS_THREADS = 256;
+// WS_NJ columns per CTA, WS_THREADS threads: 32 x 256 on large grids, 16 x 128 on
+// small per-GPU grids (strong scaling) so that the CTAs still cover all SMs.
+template <int WS_NJ, int WS_THREADS>
 __global__ void __launch_bounds__(WS_THREADS)
 moloch_wsolve(Geo g, const double* __restrict__ zdiv, double* s, double* __restrict__ w,
               double* __restrict__ pai, const double* __restrict__ tetav, double* __restrict__ tetavf,
@@ -294,20 +297,28 @@ moloch_wsolve(Geo g, const double* __restrict__ zdiv, double* s, double* __restr
     if (last && row0 == 0) s[base + (long long)kz * pl] = 0.0;
   }
 }
-int k_wsolve(Ctx& c, double dts, bool last) {
+template <int WS_NJ, int WS_THREADS>
+static int launch_wsolve(Ctx& c, double dts, bool last, long long ncol) {
   const Geo& g = c.g;
   const double dtrdz = dts * c.rdzita;
   const double zcs2 = (dtrdz * dtrdz) * rdrcv;
-  const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
   const size_t smem = (size_t)(4 * g.kz + 1) * WS_NJ * sizeof(double);
+  if (smem > 227 * 1024) return fail("wsolve: kz too large for the shared-memory column tile");
   const double* zsrc = c.cfg.mo_divfilter ? c.zdiv2b : c.f[MB_ZDIV2].p;
-  MB_CUDA(cudaFuncSetAttribute(moloch_wsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MB_CUDA(cudaFuncSetAttribute(moloch_wsolve<WS_NJ, WS_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
   LaunchScope ls(c, KID_WSOLVE);
-  moloch_wsolve<<<(unsigned)((ncol + WS_NJ - 1) / WS_NJ), WS_THREADS, smem, c.stream>>>(
+  moloch_wsolve<WS_NJ, WS_THREADS><<<(unsigned)((ncol + WS_NJ - 1) / WS_NJ), WS_THREADS, smem, c.stream>>>(
       g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.f[MB_FMZ].p,
       c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0);
   MB_CUDA(cudaGetLastError());
   return 0;
+}
+int k_wsolve(Ctx& c, double dts, bool last) {
+  const Geo& g = c.g;
+  const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
+  const bool small = (ncol + 31) / 32 < 148 * 5 * 3;   // fewer than three waves of 32-column CTAs
+  return small ? launch_wsolve<16, 128>(c, dts, last, ncol) : launch_wsolve<32, 256>(c, dts, last, ncol);
 }
 
 // ---------------------------------------------------------------------------
@@ -320,7 +331,8 @@ __global__ void moloch_uvupdate(Geo g, double* __restrict__ u, double* __restric
                                 const double* __restrict__ coru, const double* __restrict__ corv,
                                 const double* __restrict__ hx, const double* __restrict__ hy,
                                 const double* __restrict__ mu, const double* __restrict__ mv,
-                                const double* __restrict__ gzitakh, double dts, double dtrdx, double dtrdy) {
+                                const double* __restrict__ gzitakh, double dts, double dtrdx, double dtrdy,
+                                int damped) {
   THREAD_JIK(g.jde1, g.ide1, 1)
   if (j > g.jde2 || i > g.ide2) return;
   const bool du = in_box(j, i, g.jdi1, g.jdi2, g.ici1, g.ici2);
@@ -331,17 +343,22 @@ __global__ void moloch_uvupdate(Geo g, double* __restrict__ u, double* __restric
   const double tv0 = tetav[id], pai0 = pai[id];
   const double zfz = egrav * dts;
   const double gk = gzitakh[k];
+  // u, v still hold the values of the start of the sub-step (the reference's
+  // ud, vd); the divergence-damped values (:749,:758) are in ud, vd
+  const double uold = u[id], vold = v[id];
   if (du) {
     const double zcx = dtrdx * mu[i2];
     const double zrom1u = 0.5 * cpd * (tetav[id - 1] + tv0);
-    const double zcor1u = coru[i2] * dts * vd[id];
-    u[id] = u[id] + bdywtu[id] * (zcor1u - zfz * hx[i2] * gk - zcx * zrom1u * (pai0 - pai[id - 1]));
+    const double zcor1u = coru[i2] * dts * vold;
+    const double ub = damped ? ud[id] : uold;
+    u[id] = ub + bdywtu[id] * (zcor1u - zfz * hx[i2] * gk - zcx * zrom1u * (pai0 - pai[id - 1]));
   }
   if (dv) {
     const double zcy = g.lrotllr ? dtrdy : dtrdy * mv[i2];
     const double zrom1v = 0.5 * cpd * (tetav[id - g.NJ] + tv0);
-    const double zcor1v = corv[i2] * dts * ud[id];
-    v[id] = v[id] + bdywtv[id] * (-zcor1v - zfz * hy[i2] * gk - zcy * zrom1v * (pai0 - pai[id - g.NJ]));
+    const double zcor1v = corv[i2] * dts * uold;
+    const double vb = damped ? vd[id] : vold;
+    v[id] = vb + bdywtv[id] * (-zcor1v - zfz * hy[i2] * gk - zcy * zrom1v * (pai0 - pai[id - g.NJ]));
   }
 }
 int k_uvupdate(Ctx& c, double dts) {
@@ -350,7 +367,7 @@ int k_uvupdate(Ctx& c, double dts) {
   moloch_uvupdate<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
       g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_BDYWTU].p,
       c.f[MB_BDYWTV].p, c.f[MB_CORU].p, c.f[MB_CORV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFU].p,
-      c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx);
+      c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx, c.cfg.mo_divdamp ? 1 : 0);
   MB_CUDA(cudaGetLastError());
   return 0;
 }

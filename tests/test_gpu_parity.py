@@ -19,6 +19,12 @@ CASES = {
     "limited_area": S.small(S.WORKLOADS["cordex25"], 44, 40, 14, ntr=3, nspgx=6),
     "band": S.small(S.WORKLOADS["cordex25"], 40, 32, 11, ntr=1, nspgx=5, i_band=1, oro="sine"),
     "rotllr": S.small(S.WORKLOADS["cordex25"], 38, 30, 9, ntr=2, nspgx=5, lrotllr=1),
+    "no_divdamp": S.small(S.WORKLOADS["cordex25"], 40, 36, 10, ntr=1, nspgx=5, mo_divdamp=0),
+    "no_divfilter": S.small(S.WORKLOADS["isc24_small"], 36, 28, 10, oro="sine", oro_h=500.0, mo_divfilter=0),
+    "no_damp_no_filter": S.small(S.WORKLOADS["cordex25"], 40, 36, 10, ntr=0, nspgx=5, mo_divdamp=0, mo_divfilter=0),
+    # wide enough for the 32-column / 256-thread variants of the column kernels
+    "wide": S.small(S.WORKLOADS["cordex25"], 420, 340, 8, ntr=1, nspgx=6, mo_nsound=2),
+    "tall": S.small(S.WORKLOADS["isc24_small"], 34, 26, 70, oro="sine", oro_h=500.0, mo_nsound=2),
 }
 
 

@@ -304,14 +304,17 @@ def main():
             m.reset_tendencies()
             m.dynamical_core()
             m.diagnostics()
+            m.set_async(True)       # batch the hand-off: one sync per direction
             for n in down:          # device -> host: what mkslice/physics read
                 buf, box = hbuf[n]
                 for s in range(buf.shape[0]):
                     m.get_local(n, box, s + 1 if n in ("qx", "trac") else 0, out=buf[s])
+            m.sync()                # the host physics would run here, on the downloaded state
             for n in up:            # host -> device: the physics tendencies
                 buf, box = hbuf[n]
                 for s in range(buf.shape[0]):
                     m.set_local(n, buf[s], box, s + 1 if n in ("qxten", "chiten") else 0)
+            m.set_async(False)
             m.status_update()
 
         e2e_step()

@@ -123,6 +123,9 @@ int moloch_b200_set_field(moloch_b200_ctx* ctx, int field, int n, const double* 
 int moloch_b200_get_field(moloch_b200_ctx* ctx, int field, int n, double* host,
                           int jlo, int jhi, int ilo, int ihi, int klo, int khi);
 int moloch_b200_set_profile(moloch_b200_ctx* ctx, int profile, const double* v, int n);
+/* on: set_field/get_field only enqueue their transfer; the caller ends a batch
+ * with moloch_b200_sync (host buffers must stay valid until then).           */
+int moloch_b200_set_async(moloch_b200_ctx* ctx, int on);
 
 /* pinned host memory for the per-step state/tendency hand-off */
 int moloch_b200_host_alloc(void** p, uint64_t bytes);

@@ -16,7 +16,7 @@ static const char* k_names[KID_COUNT] = {
     "reset_tendencies", "tetavf_init", "sound_pre", "divdamp_filter", "wsolve", "uvupdate", "sfinish",
     "destagger", "waf_vertical", "waf_meridional", "waf_zonal", "curvature", "restagger", "tvirt_temp",
     "diag_prq", "diag_ps", "status_update", "halo_local", "halo_pack", "halo_unpack", "init_static",
-    "waf_horizontal"};
+    "waf_horizontal", "box_copy"};
 const char* kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? k_names[kid] : "?"; }
 
 LaunchScope::LaunchScope(Ctx& c_, int kid_) : c(c_), kid(kid_) {
@@ -371,6 +371,12 @@ int moloch_b200_set_stream(moloch_b200_ctx* c, void* s) {
   c->own_stream = false;
   return 0;
 }
+int moloch_b200_set_async(moloch_b200_ctx* c, int on) {
+  if (!c) return fail("null context");
+  c->async_xfer = on != 0;
+  if (!on) return sync_stream(*c);
+  return 0;
+}
 int moloch_b200_sync(moloch_b200_ctx* c) {
   if (!c) return fail("null context");
   return sync_stream(*c);
@@ -396,19 +402,41 @@ static int xfer_field(moloch_b200_ctx* c, int field, int n, double* host, int jl
   if (jb < ja || ib < ia || kb < ka) return 0;  // no overlap: nothing to move
   MB_CUDA(cudaSetDevice(c->device));
   double* dev = f.p + (size_t)spec * f.nk * g.plane;
-  cudaMemcpy3DParms p;
-  memset(&p, 0, sizeof(p));
-  cudaPitchedPtr hp = make_cudaPitchedPtr((void*)host, (size_t)(jhi - jlo + 1) * sizeof(double),
-                                          (size_t)(jhi - jlo + 1) * sizeof(double), (size_t)(ihi - ilo + 1));
-  cudaPitchedPtr dp = make_cudaPitchedPtr((void*)dev, (size_t)g.NJ * sizeof(double),
-                                          (size_t)g.NJ * sizeof(double), (size_t)g.NI);
-  cudaPos hpos = make_cudaPos((size_t)(ja - jlo) * sizeof(double), (size_t)(ia - ilo), (size_t)(ka - klo));
-  cudaPos dpos = make_cudaPos((size_t)(ja - g.j0) * sizeof(double), (size_t)(ia - g.i0), (size_t)(ka - 1));
-  p.extent = make_cudaExtent((size_t)(jb - ja + 1) * sizeof(double), (size_t)(ib - ia + 1), (size_t)(kb - ka + 1));
-  if (to_device) { p.srcPtr = hp; p.srcPos = hpos; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
-  else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
-  MB_CUDA(cudaMemcpy3DAsync(&p, c->stream));
-  MB_CUDA(cudaStreamSynchronize(c->stream));
+  // The host box is contiguous, the device box is padded: gather/scatter on the
+  // device through a contiguous staging buffer so that the PCIe transfer is one
+  // linear copy (a strided cudaMemcpy3D reaches ~60 % of the link rate).
+  const int nj = jb - ja + 1, ni = ib - ia + 1, nk = kb - ka + 1;
+  const bool whole = (ja == jlo && jb == jhi && ia == ilo && ib == ihi && ka == klo && kb == khi);
+  if (whole) {
+    const size_t n_el = (size_t)nj * ni * nk;
+    if (n_el > c->stage_doubles) {
+      MB_CUDA(cudaStreamSynchronize(c->stream));
+      if (c->stage) cudaFree(c->stage);
+      c->stage_doubles = n_el + n_el / 8;
+      MB_CUDA(cudaMalloc(&c->stage, c->stage_doubles * sizeof(double)));
+    }
+    if (to_device) {
+      MB_CUDA(cudaMemcpyAsync(c->stage, host, n_el * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      if (k_box_copy(*c, dev, c->stage, ja, ia, ka, nj, ni, nk, false)) return 1;
+    } else {
+      if (k_box_copy(*c, dev, c->stage, ja, ia, ka, nj, ni, nk, true)) return 1;
+      MB_CUDA(cudaMemcpyAsync(host, c->stage, n_el * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+  } else {
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    cudaPitchedPtr hp = make_cudaPitchedPtr((void*)host, (size_t)(jhi - jlo + 1) * sizeof(double),
+                                            (size_t)(jhi - jlo + 1) * sizeof(double), (size_t)(ihi - ilo + 1));
+    cudaPitchedPtr dp = make_cudaPitchedPtr((void*)dev, (size_t)g.NJ * sizeof(double),
+                                            (size_t)g.NJ * sizeof(double), (size_t)g.NI);
+    cudaPos hpos = make_cudaPos((size_t)(ja - jlo) * sizeof(double), (size_t)(ia - ilo), (size_t)(ka - klo));
+    cudaPos dpos = make_cudaPos((size_t)(ja - g.j0) * sizeof(double), (size_t)(ia - g.i0), (size_t)(ka - 1));
+    p.extent = make_cudaExtent((size_t)nj * sizeof(double), (size_t)ni, (size_t)nk);
+    if (to_device) { p.srcPtr = hp; p.srcPos = hpos; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+    else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
+    MB_CUDA(cudaMemcpy3DAsync(&p, c->stream));
+  }
+  if (!c->async_xfer) MB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -67,7 +67,7 @@ __host__ __device__ inline long long gidx2(const Geo& g, int j, int i) {
 enum KernelId {
   KID_RESET = 0, KID_TETAVF, KID_SOUND_PRE, KID_DIVDAMP, KID_WSOLVE, KID_UVUPDATE, KID_SFINISH,
   KID_DESTAG, KID_WAF_Z, KID_WAF_Y, KID_WAF_X, KID_CURV, KID_RESTAG, KID_TVIRT, KID_DIAG, KID_PS,
-  KID_STATUS, KID_HALO, KID_HALO_PACK, KID_HALO_UNPACK, KID_INIT, KID_WAF_H, KID_COUNT
+  KID_STATUS, KID_HALO, KID_HALO_PACK, KID_HALO_UNPACK, KID_INIT, KID_WAF_H, KID_BOX, KID_COUNT
 };
 
 struct ProfEvent { cudaEvent_t a, b; int kid; };
@@ -138,6 +138,7 @@ struct Ctx {
   // staging for set/get
   double* stage = nullptr;
   size_t stage_doubles = 0;
+  bool async_xfer = false;
 };
 
 extern thread_local std::string g_err;
@@ -177,6 +178,7 @@ int k_tvirt_temp(Ctx& c);
 int k_diagnostics(Ctx& c);
 int k_status_update(Ctx& c, double dtinc);
 int k_init_static(Ctx& c);
+int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int nj, int ni, int nk, bool pack);
 // kernels_waf.cu
 int k_waf_ratios(Ctx& c);
 int k_waf_z2(Ctx& c, int first, int count, double dta);

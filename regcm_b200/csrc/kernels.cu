@@ -869,4 +869,25 @@ int k_init_static(Ctx& c) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// host hand-off: padded device box <-> contiguous staging buffer
+// ---------------------------------------------------------------------------
+__global__ void moloch_box_copy(Geo g, double* __restrict__ dev, double* __restrict__ stage, int ja, int ia,
+                                int ka, int nj, int ni, int nk, int pack) {
+  const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+  if (j >= nj || i >= ni) return;
+  for (int k = blockIdx.z; k < nk; k += gridDim.z) {
+    const long long d = gidx(g, ja + j, ia + i, ka + k);
+    const long long t = ((long long)k * ni + i) * nj + j;
+    if (pack) stage[t] = dev[d]; else dev[d] = stage[t];
+  }
+}
+int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int nj, int ni, int nk, bool pack) {
+  LaunchScope ls(c, KID_BOX);
+  dim3 grid((unsigned)((nj + BX - 1) / BX), (unsigned)((ni + BY - 1) / BY), (unsigned)(nk < 64 ? nk : 64));
+  moloch_box_copy<<<grid, dim3(BX, BY), 0, c.stream>>>(c.g, dev, stage, ja, ia, ka, nj, ni, nk, pack ? 1 : 0);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace mb

@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "moloch_b200_sound", "moloch_b200_advection", "moloch_b200_wafone", "moloch_b200_dynamical_core",
     "moloch_b200_diagnostics", "moloch_b200_status_update", "moloch_b200_step", "moloch_b200_profile_enable",
     "moloch_b200_profile_read", "moloch_b200_launch_count", "moloch_b200_device_bytes",
-    "moloch_b200_halo_plan", "moloch_b200_p2p_blob_size", "moloch_b200_p2p_export", "moloch_b200_p2p_connect",
+    "moloch_b200_halo_plan", "moloch_b200_p2p_blob_size", "moloch_b200_p2p_export", "moloch_b200_p2p_connect", "moloch_b200_set_async",
 ]
 
 
@@ -85,6 +85,7 @@ def load_library():
     lib.moloch_b200_p2p_export.argtypes = [ctx, C.c_void_p]
     lib.moloch_b200_p2p_connect.argtypes = [ctx, C.c_void_p, C.c_int]
     lib.moloch_b200_sync.argtypes = [ctx]
+    lib.moloch_b200_set_async.argtypes = [ctx, C.c_int]
     xf = [ctx, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 6
     lib.moloch_b200_set_field.argtypes = xf
     lib.moloch_b200_get_field.argtypes = xf
@@ -215,6 +216,10 @@ class MolochB200:
         self._chk(self.lib.moloch_b200_wafone(self.ctx, FIELD_ID[field], int(n)))
 
     def sync(self): self._chk(self.lib.moloch_b200_sync(self.ctx))
+
+    def set_async(self, on: bool):
+        """Batch mode for set_local/get_local: transfers are only enqueued; end with sync()."""
+        self._chk(self.lib.moloch_b200_set_async(self.ctx, int(on)))
 
     def set_stream(self, cuda_stream: int):
         self._chk(self.lib.moloch_b200_set_stream(self.ctx, C.c_void_p(cuda_stream)))

@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -143,7 +143,7 @@ def base_line(wl, args, n_gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(S.WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
@@ -204,8 +204,10 @@ def main():
             dist.barrier()
     stream = torch.cuda.Stream()
     m.set_stream(stream.cuda_stream)
-    fields, profiles = S.model_inputs(wl)
-    m.init_moloch(fields, profiles)
+    # the rank's own arrays, generated locally (no global 3-D arrays: the large
+    # workloads would not fit the host otherwise)
+    fields, profiles, boxes = S.model_inputs_local(wl, m.g)
+    m.init_moloch(fields, profiles, boxes)
     del fields
 
     def barrier():

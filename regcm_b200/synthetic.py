@@ -424,3 +424,113 @@ def model_inputs(wl: Workload):
     if wl.lrotllr:
         prof["rlat"] = P["rlat"]
     return F, prof
+
+
+# ---- rank-local generation (large grids: no global 3-D arrays) ---------------
+def _noise_at(lin: np.ndarray, seed: int, salt: int) -> np.ndarray:
+    """noise() evaluated at global linear indices `lin` (same values)."""
+    with np.errstate(over="ignore"):
+        idx = lin.astype(np.uint64) + np.uint64((seed * 1000003 + salt * 7919) & 0xFFFFFFFFFFFF)
+        r = _splitmix64(idx)
+    u = (r >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return 2.0 * u - 1.0
+
+
+def model_inputs_local(wl: Workload, g):
+    """(fields, profiles, boxes) of ONE rank (geometry `g`, regcm_b200.decomp.Geom)
+    without ever building a global 3-D array: what model_inputs(wl) gives, cut to
+    the rank's bounds.  2-D fields are still computed globally (they are cheap)."""
+    from . import hostmodel as H
+    jx, iy, kz = wl.jx, wl.iy, wl.kz
+    ztop, zh, a0 = wl.mo_ztop, wl.mo_h, wl.mo_a0
+    Jg, Ig = np.meshgrid(np.arange(1, jx + 1, dtype=np.float64), np.arange(1, iy + 1, dtype=np.float64))
+    P2 = {"ht": _height(wl, Jg, Ig) * egrav, "htu": _height(wl, Jg - 0.5, Ig) * egrav,
+          "htv": _height(wl, Jg, Ig - 0.5) * egrav, "msfx": _msf(wl, Jg, Ig), "msfu": _msf(wl, Jg - 0.5, Ig),
+          "msfv": _msf(wl, Jg, Ig - 0.5)}
+    dl = raddeg * wl.dx / earthrad
+    xlat = wl.clat - dl * (float(iy) * 0.5 - Ig + 0.5)
+    vlat = wl.clat - dl * (float(iy) * 0.5 - Ig + 1.0)
+    rlat = wl.clat - dl * (float(iy) * 0.5 - np.arange(1, iy + 2, dtype=np.float64) + 1.0)
+    hsurf = P2["ht"] * regrav
+    ps2 = stdp * (1.0 - lrate * hsurf / stdt) ** (egrav / (rgas * lrate))
+    # 2-D statics exactly as derive_static does
+    rdx = 1.0 / wl.dx
+    perj = wl.i_band == 1 or wl.i_crm == 1
+    peri = wl.i_crm == 1
+    ht, htu, htv = P2["ht"], P2["htu"], P2["htv"]
+    htm1 = np.roll(ht, 1, axis=1) if perj else np.concatenate([ht[:, :1], ht[:, :-1]], axis=1)
+    hx = rdx * regrav * P2["msfu"] * (ht - htm1)
+    hx[:, 0] = 2.0 * rdx * regrav * P2["msfu"][:, 0] * (ht[:, 0] - htu[:, 0])
+    htm1 = np.roll(ht, 1, axis=0) if peri else np.concatenate([ht[:1], ht[:-1]], axis=0)
+    mfv = 1.0 if wl.lrotllr else P2["msfv"]
+    hy = rdx * regrav * mfv * (ht - htm1)
+    hy[0] = (2.0 * rdx * regrav * mfv * (ht - htv))[0]
+    zita, zitah = model_zitaf(kz, ztop), model_zitah(kz, ztop)
+    mo_dzita = float(zita[kz - 1])
+    njc = jx if perj else jx - 1
+    nic = iy if peri else iy - 1
+    gmeanz = np.array([md_zeta(zitah[k], ht[:nic, :njc], ztop, zh, a0).sum() / float(njc * nic) for k in range(kz)])
+    zzi = (gmeanz - 18000.0) / (ztop - 18000.0)
+    ffilt = np.where(gmeanz < 18000.0, 0.0, mo_zfilt_fac * np.sin(0.5 * mathpi * zzi) ** 2)
+    hefc = hefc_table(wl) if wl.nspgx > 0 else None
+
+    # the rank's working box: dot range + 2 ghosts wherever a neighbour exists
+    box = g.ext("dot", 2, 2)
+    jlo, jhi, ilo, ihi = box
+    jv = (np.arange(jlo, jhi + 1) - 1) % jx            # 0-based wrapped global indices
+    iv = (np.arange(ilo, ihi + 1) - 1) % iy
+    cut2 = lambda a: np.ascontiguousarray(a[iv[:, None], jv[None, :]])
+    J = (jv + 1).astype(np.float64)[None, :] + 0.0 * iv[:, None]
+    I = (iv + 1).astype(np.float64)[:, None] + 0.0 * jv[None, :]
+    htl, htul, htvl = cut2(ht), cut2(htu), cut2(htv)
+    F3 = {}
+    F3["zeta"] = md_zeta(zitah[:, None, None], htl[None], ztop, zh, a0)
+    F3["fmz"] = md_fmz(zitah[:, None, None], htl[None], ztop, zh, a0)
+    F3["rfmzu"] = 1.0 / md_fmz(zitah[:, None, None], htul[None], ztop, zh, a0)
+    F3["rfmzv"] = 1.0 / md_fmz(zitah[:, None, None], htvl[None], ztop, zh, a0)
+    F3["fmzf"] = md_fmz(zita[:, None, None], htl[None], ztop, zh, a0)
+    for name, ldx, ldy in (("bdywtw", False, False), ("bdywtu", True, False), ("bdywtv", False, True)):
+        ib = cut2(_ibnd(wl, ldx, ldy))
+        if wl.nspgx > 0:
+            sel = ib > 0
+            idx = np.where(sel, ib - 1, 0)
+            F3[name] = np.where(sel[None], 1.0 - hefc[:, idx], 1.0)
+        else:
+            F3[name] = np.ones((kz,) + ib.shape)
+    zeta = F3["zeta"]
+    lin = (np.arange(kz, dtype=np.int64)[:, None, None] * iy + iv[None, :, None]) * jx + jv[None, None, :]
+    t = np.maximum(stdt - lrate * (zeta + htl[None] * regrav), 210.0)
+    r2 = ((J - 0.5 * jx) ** 2 + (I - 0.5 * iy) ** 2)[None] / 100.0 + ((zeta - 2000.0) / 1500.0) ** 2
+    t = t + 2.0 * np.exp(-r2) + 1.0e-3 * _noise_at(lin, wl.seed, 1)
+    qx = np.zeros((wl.nqx, kz) + htl.shape)
+    qx[0] = 0.012 * np.exp(-(zeta + htl[None] * regrav) / 2500.0)
+    u = wl.u0 * (1.0 + 0.1 * _noise_at(lin, wl.seed, 2))
+    v = wl.v0 * (1.0 + 0.1 * _noise_at(lin, wl.seed, 3))
+    F3.update(t=t, qx=qx, u=u, v=v)
+    if wl.ntr > 0:
+        tr = np.full((wl.ntr, kz) + htl.shape, 1.0e-9)
+        rng = np.random.default_rng(wl.seed)
+        for n in range(wl.ntr):
+            cx, cy, cz = rng.uniform(0.15, 0.85), rng.uniform(0.15, 0.85), rng.uniform(500.0, 6000.0)
+            rr = ((J - cx * jx) ** 2 + (I - cy * iy) ** 2)[None] / 64.0 + ((zeta - cz) / 1000.0) ** 2
+            tr[n] += 1.0e-6 * np.exp(-rr)
+        F3["trac"] = tr
+    St = {"zeta": zeta, "fmzf": F3["fmzf"], "mo_dzita": mo_dzita}
+    X = init_state(wl, {"t": t, "qx": qx, "ps": cut2(ps2)}, St)
+    F3.update(pai=X["pai"], tetav=X["tetav"], tvirt=X["tvirt"], p=X["p"], rho=X["rho"], qsat=X["qsat"], w=X["w"])
+    F2 = {"hx": cut2(hx), "hy": cut2(hy), "msfx": cut2(P2["msfx"]), "msfu": cut2(P2["msfu"]),
+          "msfv": cut2(P2["msfv"]), "coru": cut2(eomeg2 * np.sin(xlat * degrad)),
+          "corv": cut2(eomeg2 * np.sin(vlat * degrad)), "ps": cut2(ps2)}
+    fields, boxes = {}, {}
+    for name, arr in list(F3.items()) + list(F2.items()):
+        b = H.bounds(g, name)
+        sub = arr[..., b[2] - ilo:b[3] - ilo + 1, b[0] - jlo:b[1] - jlo + 1]
+        fields[name] = np.ascontiguousarray(sub)
+        boxes[name] = b
+    k = np.arange(1, kz + 1, dtype=np.float64)
+    prof = {"gzitak": gzita(zita, ztop, a0), "gzitakh": gzita(zitah, ztop, a0), "ffilt": ffilt,
+            "xkdamp": 0.125 * 0.850 * (1.0 / (k + 1.0) - 1.0 / (kz + 2.0)),
+            "xknu": 0.125 * (0.55 + 0.45 * ((kz - k + 1.0) - 1.0) / (kz - 1.0))}
+    if wl.lrotllr:
+        prof["rlat"] = rlat
+    return fields, prof, boxes

@@ -212,6 +212,23 @@ def test_hostmodel_cut_paste_roundtrip():
     assert np.array_equal(out, glob)
 
 
+def test_rank_local_inputs_equal_global_inputs():
+    """bench.py builds each rank's arrays directly (model_inputs_local); they
+    must equal the globally generated arrays cut to the rank's bounds."""
+    for wl, px, py in ((S.small(S.WORKLOADS["cordex25"], 45, 41, 9, ntr=2, nspgx=6), 2, 2),
+                       (S.small(S.WORKLOADS["isc24_small"], 30, 22, 8, oro="sine"), 3, 2)):
+        Fg, Pg = S.model_inputs(wl)
+        for r in range(px * py):
+            g = make_geom(wl.jx, wl.iy, wl.kz, wl.i_band, wl.i_crm, px, py, r)
+            Fl, Pl, B = S.model_inputs_local(wl, g)
+            for n in Fl:
+                own, b = H.owned(g, n), B[n]
+                sl = (Ellipsis, slice(own[2] - b[2], own[3] - b[2] + 1), slice(own[0] - b[0], own[1] - b[0] + 1))
+                assert np.array_equal(H.cut(np.asarray(Fg[n]), g, b)[sl], Fl[n][sl]), (wl.name, r, n)
+            for n in Pl:
+                assert np.array_equal(Pl[n], Pg[n]), n
+
+
 def test_bench_reference_arm_prints_contract_line():
     import json
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",

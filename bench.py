@@ -60,47 +60,92 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a
+    thread (10 ms period, started before the warm-up so that it is running
+    when the short timed region begins); nvidia-smi as fall-back."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "sw_power_cap": 0x4, "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
+        self.window = [None, None]
+        self.max_mhz = None
+
+    def _loop_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        uuid = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.index < len(ids):
+                if ids[self.index].isdigit():
+                    idx = int(ids[self.index])
+                else:
+                    uuid = ids[self.index]
+        h = N.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid) if uuid \
+            else N.nvmlDeviceGetHandleByIndex(idx)
+        self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            try:
+                mhz = float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                try:
+                    rs = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    rs = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _loop_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().split(",")]
+                self.max_mhz = float(f[1])
+                self.rows.append((time.perf_counter(), float(f[0]), int(f[2], 16)))
+            except Exception:
+                time.sleep(0.05)
+
+    def _loop(self):
+        try:
+            self._loop_nvml()
+        except Exception:
+            self._loop_smi()
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def mark_begin(self):
+        self.window[0] = time.perf_counter()
+
+    def mark_end(self):
+        self.window[1] = time.perf_counter()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=3)
+        t0, t1 = self.window
+        rows = [r for r in self.rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
+        note = "samples inside the timed region"
+        if not rows and self.rows and t0 is not None:
+            # region shorter than one sampling period: nearest samples around it
+            rows = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:2]
+            note = "timed region shorter than the sampling period: nearest samples"
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples (NVML and nvidia-smi unavailable)"]}
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        reasons = sorted(n for n, b in self.REASONS.items() if bits & b)
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(rows), "note": note}
 
 
 def cpu_sample_workload(wl):
@@ -231,13 +276,15 @@ def main():
         return float(ms.item())
 
     # ---- device-resident throughput -----------------------------------------------
-    m.moloch(args.warmup)
-    m.sync()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    m.moloch(args.warmup)
+    m.sync()
     m.launch_count(reset=True)
+    sampler.mark_begin()
     ms = timed(lambda: m.moloch(1), args.steps)
+    sampler.mark_end()
     launches = m.launch_count(reset=True)
     clocks = sampler.stop() if rank == 0 else None
     value = wl.cells * args.steps / (ms * 1e-3)

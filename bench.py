@@ -194,9 +194,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"])
-    ap.add_argument("--px", type=int, default=0)
-    ap.add_argument("--py", type=int, default=0)
+    ap.add_argument("--transport", default=os.environ.get("BENCH_TRANSPORT", "p2p"), choices=["p2p", "nccl"])
+    ap.add_argument("--px", type=int, default=int(os.environ.get("BENCH_PX", "0")))
+    ap.add_argument("--py", type=int, default=int(os.environ.get("BENCH_PY", "0")))
     args = ap.parse_args()
     wl = S.WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

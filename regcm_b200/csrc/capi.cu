@@ -98,7 +98,7 @@ Layout make_layout(const moloch_b200_config& f) {
     int nk, nspec; field_shape(f, id, nk, nspec);
     put(id, pl * nk * (size_t)nspec);
   }
-  put(SL_UD, pl * kz); put(SL_VD, pl * kz); put(SL_ZB, pl * kz); put(SL_WW, pl * (kz + 1));
+  put(SL_UD, pl * kz); put(SL_VD, pl * kz); put(SL_ZB, pl * kz);
   L.stride2d = al(pl); put(SL_2D, L.stride2d * 4);
   L.stridezr = al(pl * kz); put(SL_ZR, L.stridezr * 2);
   put(SL_WZ, pl * kz * (size_t)nadv); put(SL_P0, pl * kz * (size_t)nadv);
@@ -137,26 +137,60 @@ static int sync_stream(Ctx& c) {
 static int do_sound(Ctx& c) {
   const double dts = c.dtsound;
   const int kz = c.g.kz;
+  const int nsound = c.cfg.mo_nsound;
+  const bool damp = c.cfg.mo_divdamp || c.cfg.mo_divfilter;
+  // Peer-store transport: from the second sub-step on, the three exchanges of a
+  // sub-step are fused into the kernels around them (see common.cuh).  The first
+  // sub-step keeps the full exchanges: they also refresh the edge cells that the
+  // sound kernels themselves never update.
+  const bool fused = halo_fused_available(c);
   HaloItem it;
   it = {c.f[MB_TETAV].p, kz};
   if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :562
   if (k_tetavf_init(c)) return 1;
-  for (int ns = 0; ns < c.cfg.mo_nsound; ++ns) {
-    {   // :570-571, one round
+  WaitCtl w_uv = {}, w_zd = {}, w_pai = {};
+  PushCtl p_uv = {}, p_zd = {}, p_pai = {};
+  EdgePush e_u = {}, e_v = {}, e_zd = {}, e_pai = {};
+  bool uv_pushed = false;   // u, v ghosts were delivered by the previous sub-step's uvupdate
+  for (int ns = 0; ns < nsound; ++ns) {
+    const bool f = fused && ns > 0;
+    if (!uv_pushed) {   // :570-571, one round
       const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
       const HaloSpec sp[2] = {{&iu, 1, HS_U, 1, true, false, 0}, {&iv, 1, HS_V, 1, false, true, 0}};
       if (halo_exchange_multi(c, sp, 2)) return 1;
     }
-    if (k_sound_pre(c, dts)) return 1;
-    if (c.cfg.mo_divdamp || c.cfg.mo_divfilter) {
-      it = {c.f[MB_ZDIV2].p, kz};
-      if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :745 (:535 is redundant)
-      if (k_divdamp_filter(c, dts)) return 1;
+    if (f && damp) {
+      if (halo_fused_begin(c, &p_zd, &w_zd)) return 1;
+      if (halo_fused_edge(c, c.f[MB_ZDIV2].p, HS_CROSS, true, true, &e_zd)) return 1;
     }
-    if (k_wsolve(c, dts, ns == c.cfg.mo_nsound - 1)) return 1;
-    it = {c.f[MB_PAI].p, kz};
-    if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :673
-    if (k_uvupdate(c, dts)) return 1;
+    if (k_sound_pre(c, dts, uv_pushed ? &w_uv : nullptr, (f && damp) ? &p_zd : nullptr, (f && damp) ? &e_zd : nullptr))
+      return 1;
+    if (damp) {
+      if (!f) {
+        it = {c.f[MB_ZDIV2].p, kz};
+        if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :745 (:535 is redundant)
+      }
+      if (k_divdamp_filter(c, dts, f ? &w_zd : nullptr)) return 1;
+    }
+    if (f) {
+      if (halo_fused_begin(c, &p_pai, &w_pai)) return 1;
+      if (halo_fused_edge(c, c.f[MB_PAI].p, HS_CROSS, true, true, &e_pai)) return 1;
+    }
+    if (k_wsolve(c, dts, ns == nsound - 1, f ? &p_pai : nullptr, f ? &e_pai : nullptr)) return 1;
+    if (!f) {
+      it = {c.f[MB_PAI].p, kz};
+      if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :673
+    }
+    // this uvupdate delivers the next sub-step's u, v ghosts
+    const bool push_uv = fused && ns + 1 < nsound;
+    if (push_uv) {
+      if (halo_fused_begin(c, &p_uv, &w_uv)) return 1;
+      if (halo_fused_edge(c, c.f[MB_U].p, HS_U, true, false, &e_u)) return 1;
+      if (halo_fused_edge(c, c.f[MB_V].p, HS_V, false, true, &e_v)) return 1;
+    }
+    if (k_uvupdate(c, dts, f ? &w_pai : nullptr, push_uv ? &p_uv : nullptr, push_uv ? &e_u : nullptr,
+                   push_uv ? &e_v : nullptr)) return 1;
+    uv_pushed = push_uv;
   }
   return 0;  // :728-734 (finish of s) is fused into the last sub-step's wsolve
 }
@@ -224,6 +258,7 @@ static int do_dynamical_core(Ctx& c) {
 static int do_status_update(Ctx& c) {
   const int kz = c.g.kz;
   if (k_status_update(c, c.cfg.dtsec)) return 1;
+  if (halo_fence(c)) return 1;   // ux/vx ghosts of the previous round may still be read by a neighbour
   {
     const HaloItem iu = {c.f[MB_UX].p, kz}, iv = {c.f[MB_VX].p, kz};
     const HaloSpec sp[2] = {{&iu, 1, HS_CROSS, 2, true, false, 0}, {&iv, 1, HS_CROSS, 2, false, true, 0}};
@@ -298,7 +333,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
     c->f[id].p = (c->f[id].nspec > 0) ? (double*)(c->arena + L.off[id]) : nullptr;
   }
   c->ud = (double*)(c->arena + L.off[SL_UD]); c->vd = (double*)(c->arena + L.off[SL_VD]);
-  c->zdiv2b = (double*)(c->arena + L.off[SL_ZB]); c->wwkw = (double*)(c->arena + L.off[SL_WW]);
+  c->zdiv2b = (double*)(c->arena + L.off[SL_ZB]);
   c->mx2 = (double*)(c->arena + L.off[SL_2D]); c->rmx = (double*)(c->arena + L.off[SL_2D] + L.stride2d);
   c->rmu = (double*)(c->arena + L.off[SL_2D] + 2 * L.stride2d);
   c->rmv = (double*)(c->arena + L.off[SL_2D] + 3 * L.stride2d);
@@ -317,6 +352,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   cudaMemcpy(c->d_ptrtab, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice);
   c->h_ptrtab = tab;
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) c->fuse_halo = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_WSOLVE")) c->wsolve_impl = atoi(e) == 2 ? 2 : 5;
   if (const char* e = getenv("MOLOCH_B200_WAFZ")) c->wafz_impl = atoi(e) == 2 ? 2 : 3;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {

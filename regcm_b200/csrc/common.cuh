@@ -73,12 +73,14 @@ enum KernelId {
 struct ProfEvent { cudaEvent_t a, b; int kid; };
 
 // arena slots: 0..MB_NFIELDS-1 are the ABI fields, then the internal arrays
-enum Slot { SL_UD = MB_NFIELDS, SL_VD, SL_ZB, SL_WW, SL_2D, SL_ZR, SL_WZ, SL_P0, SL_PROF, SL_TAB, SL_FLAGS, SL_COUNT };
+enum Slot { SL_UD = MB_NFIELDS, SL_VD, SL_ZB, SL_2D, SL_ZR, SL_WZ, SL_P0, SL_PROF, SL_TAB, SL_FLAGS, SL_COUNT };
 struct Layout {
   std::vector<size_t> off, size;  // bytes, per slot
   size_t stride2d = 0, stridezr = 0, strideprof = 0, total = 0;
 };
-struct Geo;
+static_assert(MB_UTEN == MB_TTEN + 1 && MB_VTEN == MB_TTEN + 2 && MB_QXTEN == MB_TTEN + 3 &&
+              MB_CHITEN == MB_TTEN + 4 && MB_S == MB_TTEN + 5 && MB_ZDIV2 == MB_TTEN + 6,
+              "reset_tendencies clears tten..zdiv2 as one range");
 Layout make_layout(const moloch_b200_config& f);
 
 // one directly addressable neighbour (NVLink peer mapping of its arena)
@@ -108,7 +110,7 @@ struct Ctx {
   struct Field { double* p = nullptr; int nk = 0; int klo = 1; int nspec = 1; bool is2d = false; };
   Field f[MB_NFIELDS];
   // extra device arrays
-  double *ud, *vd, *zdiv2b, *wwkw, *mx2, *rmx, *rmu, *rmv;
+  double *ud, *vd, *zdiv2b, *mx2, *rmx, *rmu, *rmv;
   double *zru, *zrd;      // static ratios of the vertical WAF pass
   int waf_impl = 2;       // 1: per-loop kernels, 2: field-batched fused kernels
   int wsolve_impl = 5;    // 2: CTA-parallel coefficients + one-warp sweeps, 5: thread per column with a cp.async ring
@@ -127,6 +129,7 @@ struct Ctx {
   unsigned long long* flags = nullptr;   // [0..3] arrival counters per side, [4] CTA counter, [5] timeout flag
   unsigned long long halo_seq = 0;
   bool p2p = false;
+  bool fuse_halo = true;                 // sound-loop exchanges fused into producer/consumer kernels (p2p only)
   Peer peer[4];                          // left, right, bottom, top
   void* nccl_comm = nullptr;
   double *sendbuf = nullptr, *recvbuf = nullptr;
@@ -162,13 +165,86 @@ struct LaunchScope {
   ~LaunchScope();
 };
 
+// ---- fused halo rounds (peer-store transport only) ----------------------------
+// Inside the sound loop the producer of an exchanged array stores its edge cells
+// straight into the neighbours' ghost cells while it computes them (plain peer
+// stores, no fences, no counters).  The consumer kernel -- the next kernel in
+// the stream, so the producer's grid has completed and its stores have been
+// flushed -- starts with halo_sync(): its first CTA tells the neighbours "my
+// edges are in your ghost cells", every CTA waits for the neighbours' word.
+// No separate exchange launch, no per-CTA synchronisation in the producers.
+struct EdgePush {            // one array, width-1 edges
+  int j1, j2, i1, i2;        // owned box of the array's staggering
+  double* q[4];              // the array inside each neighbour's arena (null: side not exchanged)
+  int dj[4], di[4];          // index shift into the neighbour's numbering (periodic wrap)
+};
+struct PushCtl {
+  int mask;                  // remote sides (0: nothing to push)
+  int pNJ[4], pj0[4], pi0[4];
+  long long pplane[4];
+};
+struct WaitCtl {
+  int mask;                  // remote sides to signal and to wait for
+  unsigned long long seq;
+  unsigned long long* pflag[4];   // neighbour's arrival counter for the side it sees me on
+  unsigned long long* flags;      // own flag block: [0..3] arrival counters, [5] timeout marker
+  long long timeout_cycles;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void edge_push(const PushCtl& pc, const EdgePush& e, int j, int i, int k, double v) {
+  if (e.q[0] && j == e.j1 && i >= e.i1 && i <= e.i2)
+    e.q[0][(long long)(k - 1) * pc.pplane[0] + (long long)(i + e.di[0] - pc.pi0[0]) * pc.pNJ[0] + (j + e.dj[0] - pc.pj0[0])] = v;
+  if (e.q[1] && j == e.j2 && i >= e.i1 && i <= e.i2)
+    e.q[1][(long long)(k - 1) * pc.pplane[1] + (long long)(i + e.di[1] - pc.pi0[1]) * pc.pNJ[1] + (j + e.dj[1] - pc.pj0[1])] = v;
+  if (e.q[2] && i == e.i1 && j >= e.j1 && j <= e.j2)
+    e.q[2][(long long)(k - 1) * pc.pplane[2] + (long long)(i + e.di[2] - pc.pi0[2]) * pc.pNJ[2] + (j + e.dj[2] - pc.pj0[2])] = v;
+  if (e.q[3] && i == e.i2 && j >= e.j1 && j <= e.j2)
+    e.q[3][(long long)(k - 1) * pc.pplane[3] + (long long)(i + e.di[3] - pc.pi0[3]) * pc.pNJ[3] + (j + e.dj[3] - pc.pj0[3])] = v;
+}
+// First statement of a consumer kernel whose grid tiles the rank's box with
+// blockIdx.x along j and blockIdx.y along i.  Only the CTAs on an edge of the
+// grid read ghost cells of that side, so only they wait for that neighbour; the
+// interior CTAs start at once and overlap the signal's flight.
+__device__ __forceinline__ void halo_sync(const WaitCtl& w) {
+  if (w.mask == 0) return;
+  int need = 0;
+  if (blockIdx.x == 0) need |= 1;
+  if (blockIdx.x == gridDim.x - 1) need |= 2;
+  if (blockIdx.y == 0) need |= 4;
+  if (blockIdx.y == gridDim.y - 1) need |= 8;
+  need &= w.mask;
+  const bool first = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0);
+  if (need == 0 && !first) return;
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+    if (first) {
+      __threadfence_system();
+      for (int sd = 0; sd < 4; ++sd)
+        if ((w.mask >> sd) & 1)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(w.pflag[sd]), "l"(w.seq) : "memory");
+    }
+    const long long t0 = clock64();
+    for (int sd = 0; sd < 4; ++sd) {
+      if (!((need >> sd) & 1)) continue;
+      for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w.flags + sd) : "memory");
+        if (v >= w.seq) break;
+        if (clock64() - t0 > w.timeout_cycles) { w.flags[5] = w.seq; break; }   // neighbour never arrived
+      }
+    }
+  }
+  __syncthreads();
+}
+#endif
+
 // ---- launchers (kernels.cu) ------------------------------------------------
 int k_reset_tendencies(Ctx& c);
 int k_tetavf_init(Ctx& c);
-int k_sound_pre(Ctx& c, double dts);
-int k_divdamp_filter(Ctx& c, double dts);
-int k_wsolve(Ctx& c, double dts, bool last);
-int k_uvupdate(Ctx& c, double dts);
+int k_sound_pre(Ctx& c, double dts, const WaitCtl* wc = nullptr, const PushCtl* pc = nullptr, const EdgePush* ez = nullptr);
+int k_divdamp_filter(Ctx& c, double dts, const WaitCtl* wc = nullptr);
+int k_wsolve(Ctx& c, double dts, bool last, const PushCtl* pc = nullptr, const EdgePush* ep = nullptr);
+int k_uvupdate(Ctx& c, double dts, const WaitCtl* wc = nullptr, const PushCtl* pc = nullptr, const EdgePush* eu = nullptr,
+               const EdgePush* ev = nullptr);
 int k_sfinish(Ctx& c);
 int k_destagger(Ctx& c);
 int k_waf_z(Ctx& c, int first, int count, double dta);
@@ -193,6 +269,11 @@ struct HaloItem { double* p; int nk; };
 int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt, int ext = 0);
 struct HaloSpec { const HaloItem* items; int n; int stag; int nex; bool lr, bt; int ext; };
 int halo_exchange_multi(Ctx& c, const HaloSpec* specs, int nspecs);
+int halo_fence(Ctx& c);
+// fused rounds: allocate the round, describe one array's edges
+bool halo_fused_available(const Ctx& c);
+int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc);
+int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep);
 int halo_comm_init(Ctx& c, const void* id128);
 int halo_comm_id(void* id128);
 int halo_p2p_export(Ctx& c, void* blob);

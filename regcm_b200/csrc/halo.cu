@@ -444,6 +444,89 @@ int halo_exchange_multi(Ctx& c, const HaloSpec* specs, int nspecs) {
   return 0;
 }
 
+// Synchronisation-only round of the peer-store transport.  A rank may run at most
+// one round ahead of a neighbour (every round waits for the neighbour's arrival),
+// so a push is safe whenever the kernels between the neighbour's previous two
+// rounds do not read the ghost cells being overwritten.  The one place of the
+// step where the same arrays are exchanged in two consecutive rounds with a
+// reader in between (ux/vx: uvxtouvstag at the end of advection, then again in
+// status_update) gets this fence in between.  No-op for NCCL and single ranks.
+int halo_fence(Ctx& c) {
+  if (!c.p2p) return 0;
+  const moloch_b200_config& cf = c.cfg;
+  const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
+  PushParams h;
+  memset(&h, 0, sizeof(h));
+  h.seq = ++c.halo_seq;
+  h.flags = c.flags;
+  h.timeout_cycles = 6000000000LL;
+  for (int sd = 0; sd < 4; ++sd) {
+    if (nbr[sd] < 0 || nbr[sd] == cf.rank) continue;
+    const Peer& pr = c.peer[sd];
+    if (!pr.mapped) return fail("halo_fence: neighbour not peer-mapped (p2p_connect incomplete)");
+    h.pflag[sd] = (unsigned long long*)(pr.arena + pr.layout.off[SL_FLAGS]) + (sd ^ 1);
+    h.mask |= 1 << sd;
+  }
+  if (h.mask == 0) return 0;
+  LaunchScope ls(c, KID_HALO);
+  moloch_halo_push<<<1, 32, 0, c.stream>>>(c.g, h);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- fused rounds: host side ------------------------------------------------
+bool halo_fused_available(const Ctx& c) {
+  if (!c.p2p || !c.fuse_halo) return false;
+  const int nbr[4] = {c.cfg.nbr_left, c.cfg.nbr_right, c.cfg.nbr_bottom, c.cfg.nbr_top};
+  for (int sd = 0; sd < 4; ++sd)
+    if (nbr[sd] == c.cfg.rank) return false;   // periodic self-neighbour: local copies, not fusable
+  return true;
+}
+
+// Allocates the round number (every rank does, in the same program order) and
+// fills the signal/wait blocks for all remote neighbours.
+int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc) {
+  const moloch_b200_config& cf = c.cfg;
+  const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
+  memset(pc, 0, sizeof(*pc));
+  memset(wc, 0, sizeof(*wc));
+  wc->seq = ++c.halo_seq; wc->flags = c.flags; wc->timeout_cycles = 6000000000LL;
+  for (int sd = 0; sd < 4; ++sd) {
+    if (nbr[sd] < 0 || nbr[sd] == cf.rank) continue;
+    const Peer& pr = c.peer[sd];
+    if (!pr.mapped) return fail("halo_fused_begin: neighbour not peer-mapped (p2p_connect incomplete)");
+    pc->pNJ[sd] = pr.NJ; pc->pj0[sd] = pr.j0; pc->pi0[sd] = pr.i0; pc->pplane[sd] = pr.plane;
+    wc->pflag[sd] = (unsigned long long*)(pr.arena + pr.layout.off[SL_FLAGS]) + (sd ^ 1);
+    pc->mask |= 1 << sd;
+  }
+  wc->mask = pc->mask;
+  return 0;
+}
+
+// Width-1 edges of one array (exchange_lr / _bt / _lrbt semantics, no corners).
+// A periodic self-neighbour cannot be fused (the caller checks fusable()).
+int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep) {
+  const moloch_b200_config& cf = c.cfg;
+  const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
+  memset(ep, 0, sizeof(*ep));
+  owned_box(cf, stag, ep->j1, ep->j2, ep->i1, ep->i2);
+  for (int sd = 0; sd < 4; ++sd) {
+    const bool on = (nbr[sd] >= 0) && ((sd < 2) ? lr : bt);
+    if (!on) continue;
+    if (nbr[sd] == cf.rank) return fail("halo_fused_edge: self-neighbour rounds are not fusable");
+    const Peer& pr = c.peer[sd];
+    int pj1, pj2, pi1, pi2;
+    owned_box(pr.cfg, stag, pj1, pj2, pi1, pi2);
+    if (sd == 0) ep->dj[sd] = (pj2 + 1) - ep->j1;
+    else if (sd == 1) ep->dj[sd] = (pj1 - 1) - ep->j2;
+    else if (sd == 2) ep->di[sd] = (pi2 + 1) - ep->i1;
+    else ep->di[sd] = (pi1 - 1) - ep->i2;
+    ep->q[sd] = peer_ptr(c, pr, array);
+    if (!ep->q[sd]) return fail("halo_fused_edge: array is not addressable in the neighbour's arena");
+  }
+  return 0;
+}
+
 // `ext` widens the edge run of every side by `ext` ghost points at each end
 // that has a neighbour: an lr exchange followed by a bt exchange with ext > 0
 // (or the other way round) also fills the corner ghosts.

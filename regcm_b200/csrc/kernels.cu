@@ -110,54 +110,62 @@ __global__ void moloch_sound_pre(Geo g, const double* __restrict__ u, const doub
                                  const double* __restrict__ hy, const double* __restrict__ mx,
                                  const double* __restrict__ mx2, const double* __restrict__ rmu,
                                  const double* __restrict__ rmv, const double* __restrict__ gzitak,
-                                 double dtrdx, double dtrdy) {
+                                 double dtrdx, double dtrdy, WaitCtl wc, PushCtl pc, EdgePush ez) {
+  halo_sync(wc);   // u, v ghosts of a fused round
   THREAD_JIK(g.jde1, g.ide1, 1)
-  if (j > g.jde2 || i > g.ide2) return;
-  const long long id = IX(j, i, k);
-  const long long i2 = IX2(j, i);
-  const int kz = g.kz;
   const bool inu = (i >= g.ice1 && i <= g.ice2);
   const bool inv = (j >= g.jce1 && j <= g.jce2);
-  if (!(inu && inv)) return;
-  const double u0 = u[id], v0 = v[id];
-  const double u1 = u[id + 1], v1 = v[id + g.NJ];
-  {
-    const double zvm = dtrdy * v0 * rfmzv[id] * rmv[i2];
-    const double zvp = dtrdy * v1 * rfmzv[id + g.NJ] * rmv[i2 + g.NJ];
-    if (g.lrotllr) {
-      const double zum = dtrdx * u0 * rfmzu[id];
-      const double zup = dtrdx * u1 * rfmzu[id + 1];
-      zdiv2[id] = fmz[id] * mx[i2] * ((zup - zum) + (zvp - zvm));
-    } else {
-      const double zum = dtrdx * u0 * rfmzu[id] * rmu[i2];
-      const double zup = dtrdx * u1 * rfmzu[id + 1] * rmu[i2 + 1];
-      zdiv2[id] = fmz[id] * mx2[i2] * ((zup - zum) + (zvp - zvm));
+  if (j <= g.jde2 && i <= g.ide2 && inu && inv) {
+    const long long id = IX(j, i, k);
+    const long long i2 = IX2(j, i);
+    const int kz = g.kz;
+    const double u0 = u[id], v0 = v[id];
+    const double u1 = u[id + 1], v1 = v[id + g.NJ];
+    {
+      const double zvm = dtrdy * v0 * rfmzv[id] * rmv[i2];
+      const double zvp = dtrdy * v1 * rfmzv[id + g.NJ] * rmv[i2 + g.NJ];
+      double zd;
+      if (g.lrotllr) {
+        const double zum = dtrdx * u0 * rfmzu[id];
+        const double zup = dtrdx * u1 * rfmzu[id + 1];
+        zd = fmz[id] * mx[i2] * ((zup - zum) + (zvp - zvm));
+      } else {
+        const double zum = dtrdx * u0 * rfmzu[id] * rmu[i2];
+        const double zup = dtrdx * u1 * rfmzu[id + 1] * rmu[i2 + 1];
+        zd = fmz[id] * mx2[i2] * ((zup - zum) + (zvp - zvm));
+      }
+      zdiv2[id] = zd;
+      if (pc.mask) edge_push(pc, ez, j, i, k, zd);
+    }
+    if (in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) {
+      const double hx0 = hx[i2], hx1 = hx[i2 + 1], hy0 = hy[i2], hy1 = hy[i2 + g.NJ];
+      if (k >= 2) {
+        const long long im = id - g.plane;
+        const double zuh = (u0 + u[im]) * hx0 + (u1 + u[im + 1]) * hx1;
+        const double zvh = (v0 + v[im]) * hy0 + (v1 + v[im + g.NJ]) * hy1;
+        s[id] = -0.25 * (zuh + zvh) * gzitak[k];
+      }
+      if (k == kz) {
+        const double zuh = u0 * hx0 + u1 * hx1;
+        const double zvh = v0 * hy0 + v1 * hy1;
+        const double sk = -0.5 * (zuh + zvh);
+        s[id + g.plane] = sk;
+        w[id + g.plane] = -sk;
+      }
     }
   }
-  if (!in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) return;
-  const double hx0 = hx[i2], hx1 = hx[i2 + 1], hy0 = hy[i2], hy1 = hy[i2 + g.NJ];
-  if (k >= 2) {
-    const long long im = id - g.plane;
-    const double zuh = (u0 + u[im]) * hx0 + (u1 + u[im + 1]) * hx1;
-    const double zvh = (v0 + v[im]) * hy0 + (v1 + v[im + g.NJ]) * hy1;
-    s[id] = -0.25 * (zuh + zvh) * gzitak[k];
-  }
-  if (k == kz) {
-    const double zuh = u0 * hx0 + u1 * hx1;
-    const double zvh = v0 * hy0 + v1 * hy1;
-    const double sk = -0.5 * (zuh + zvh);
-    s[id + g.plane] = sk;
-    w[id + g.plane] = -sk;
-  }
 }
-int k_sound_pre(Ctx& c, double dts) {
+int k_sound_pre(Ctx& c, double dts, const WaitCtl* wc, const PushCtl* pc, const EdgePush* ez) {
   const Geo& g = c.g;
   const double dtrdx = dts * c.rdx, dtrdy = dts * c.rdx;
+  const WaitCtl w0 = wc ? *wc : WaitCtl{};
+  const PushCtl p0 = pc ? *pc : PushCtl{};
+  const EdgePush e0 = ez ? *ez : EdgePush{};
   LaunchScope ls(c, KID_SOUND_PRE);
   moloch_sound_pre<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
       g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_ZDIV2].p, c.f[MB_FMZ].p,
       c.f[MB_RFMZU].p, c.f[MB_RFMZV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFX].p, c.mx2, c.rmu, c.rmv,
-      c.prof[MB_GZITAK], dtrdx, dtrdy);
+      c.prof[MB_GZITAK], dtrdx, dtrdy, w0, p0, e0);
   MB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -171,7 +179,8 @@ __global__ void moloch_divdamp_filter(Geo g, const double* __restrict__ u, const
                                       const double* __restrict__ zdiv2, double* __restrict__ zdiv2b,
                                       const double* __restrict__ mu, const double* __restrict__ mv,
                                       const double* __restrict__ xkdamp, const double* __restrict__ xknu,
-                                      double dxrdt, int do_damp, int do_filter) {
+                                      double dxrdt, int do_damp, int do_filter, WaitCtl wc) {
+  halo_sync(wc);   // zdiv2 ghosts of a fused round
   THREAD_JIK(g.jde1, g.ide1, 1)
   if (j > g.jde2 || i > g.ide2) return;
   const long long id = IX(j, i, k);
@@ -193,12 +202,13 @@ __global__ void moloch_divdamp_filter(Geo g, const double* __restrict__ u, const
     zdiv2b[id] = z0 + xknu[k] * lap;
   }
 }
-int k_divdamp_filter(Ctx& c, double dts) {
+int k_divdamp_filter(Ctx& c, double dts, const WaitCtl* wc) {
   const Geo& g = c.g;
+  const WaitCtl w0 = wc ? *wc : WaitCtl{};
   LaunchScope ls(c, KID_DIVDAMP);
   moloch_divdamp_filter<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
       g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_ZDIV2].p, c.zdiv2b, c.f[MB_MSFU].p, c.f[MB_MSFV].p,
-      c.prof[MB_XKDAMP], c.prof[MB_XKNU], c.cfg.dx / dts, c.cfg.mo_divdamp, c.cfg.mo_divfilter);
+      c.prof[MB_XKDAMP], c.prof[MB_XKNU], c.cfg.dx / dts, c.cfg.mo_divdamp, c.cfg.mo_divfilter, w0);
   MB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -217,7 +227,7 @@ moloch_wsolve(Geo g, const double* __restrict__ zdiv, double* s, double* __restr
               double* __restrict__ pai, const double* __restrict__ tetav, double* __restrict__ tetavf,
               const double* __restrict__ fmz, const double* __restrict__ fmzf,
               const double* __restrict__ bdywtw, const double* __restrict__ ffilt, double dts, double dtrdz,
-              double zcs2, int last) {
+              double zcs2, int last, PushCtl pc, EdgePush ep) {
   // CTA = 32 columns x all levels.  Everything that does not depend on the
   // recurrence (finished divergence, explicit w, matrix coefficients) is
   // computed by all threads in parallel over k; only the two Thomas sweeps run
@@ -290,7 +300,9 @@ moloch_wsolve(Geo g, const double* __restrict__ zdiv, double* s, double* __restr
       const long long id = base + (k - 1) * pl;
       const int o = (k - 1) * WS_NJ + lane;
       const double wk = W[o], wk1 = W[o + WS_NJ];
-      pai[id] = pai[id] * (1.0 - rdrcv * (ZD[o] + (dtrdz * fmz[id] * (wk - wk1))));
+      const double pnew = pai[id] * (1.0 - rdrcv * (ZD[o] + (dtrdz * fmz[id] * (wk - wk1))));
+      pai[id] = pnew;
+      if (pc.mask) edge_push(pc, ep, j, i, k, pnew);
       if (k >= 2) w[id] = wk;
       if (last) s[id] = (k >= 2) ? (wk + s[id]) * fmzf[id] : 0.0;
     }
@@ -298,7 +310,7 @@ moloch_wsolve(Geo g, const double* __restrict__ zdiv, double* s, double* __restr
   }
 }
 template <int WS_NJ, int WS_THREADS>
-static int launch_wsolve(Ctx& c, double dts, bool last, long long ncol) {
+static int launch_wsolve(Ctx& c, double dts, bool last, long long ncol, const PushCtl& pc, const EdgePush& ep) {
   const Geo& g = c.g;
   const double dtrdz = dts * c.rdzita;
   const double zcs2 = (dtrdz * dtrdz) * rdrcv;
@@ -310,17 +322,19 @@ static int launch_wsolve(Ctx& c, double dts, bool last, long long ncol) {
   LaunchScope ls(c, KID_WSOLVE);
   moloch_wsolve<WS_NJ, WS_THREADS><<<(unsigned)((ncol + WS_NJ - 1) / WS_NJ), WS_THREADS, smem, c.stream>>>(
       g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.f[MB_FMZ].p,
-      c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0);
+      c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, pc, ep);
   MB_CUDA(cudaGetLastError());
   return 0;
 }
-int k_wsolve5(Ctx& c, double dts, bool last);
-int k_wsolve(Ctx& c, double dts, bool last) {
-  if (c.wsolve_impl == 5) return k_wsolve5(c, dts, last);
+int k_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
+int k_wsolve(Ctx& c, double dts, bool last, const PushCtl* pcp, const EdgePush* epp) {
+  const PushCtl pc = pcp ? *pcp : PushCtl{};
+  const EdgePush ep = epp ? *epp : EdgePush{};
+  if (c.wsolve_impl == 5) return k_wsolve5(c, dts, last, pc, ep);
   const Geo& g = c.g;
   const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
   const bool small = (ncol + 31) / 32 < 148 * 5 * 3;   // fewer than three waves of 32-column CTAs
-  return small ? launch_wsolve<16, 128>(c, dts, last, ncol) : launch_wsolve<32, 256>(c, dts, last, ncol);
+  return small ? launch_wsolve<16, 128>(c, dts, last, ncol, pc, ep) : launch_wsolve<32, 256>(c, dts, last, ncol, pc, ep);
 }
 
 // ---------------------------------------------------------------------------
@@ -349,7 +363,8 @@ __global__ void __launch_bounds__(32)
 moloch_wsolve5(Geo g, const double* __restrict__ zdiv, double* s, double* w, double* pai,
                const double* __restrict__ tetav, double* tetavf, const double* __restrict__ fmz,
                const double* __restrict__ fmzf, const double* __restrict__ bdywtw,
-               const double* __restrict__ ffilt, double dts, double dtrdz, double zcs2, int last) {
+               const double* __restrict__ ffilt, double dts, double dtrdz, double zcs2, int last, PushCtl pc,
+               EdgePush ep) {
   extern __shared__ double sm[];
   const int kz = g.kz;
   double* WP = sm;                        // w after the downward sweep, rows k = 0..kz
@@ -444,7 +459,9 @@ moloch_wsolve5(Geo g, const double* __restrict__ zdiv, double* s, double* w, dou
         const double wk = (k <= kz) ? WP[k * 32 + lane] + WW[k * 32 + lane] * wkm1 : w_bottom;
         if (valid) {
           const long long id = base + k * pl;
-          pai[id - pl] = Upa * (1.0 - rdrcv * (ZF[(k - 1) * 32 + lane] + (dtrdz * Ufm * (wkm1 - wk))));
+          const double pnew = Upa * (1.0 - rdrcv * (ZF[(k - 1) * 32 + lane] + (dtrdz * Ufm * (wkm1 - wk))));
+          pai[id - pl] = pnew;
+          if (pc.mask) edge_push(pc, ep, j, i, k - 1, pnew);
           if (k <= kz) {
             w[id] = wk;
             if (last) s[id] = (wk + r[64]) * r[96];
@@ -460,7 +477,7 @@ moloch_wsolve5(Geo g, const double* __restrict__ zdiv, double* s, double* w, dou
   if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
 }
 template <int D>
-static int launch_wsolve5(Ctx& c, double dts, bool last) {
+static int launch_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
   const Geo& g = c.g;
   const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
   const double dtrdz = dts * c.rdzita;
@@ -472,11 +489,26 @@ static int launch_wsolve5(Ctx& c, double dts, bool last) {
   LaunchScope ls(c, KID_WSOLVE);
   moloch_wsolve5<D><<<(unsigned)((ncol + 31) / 32), 32, smem, c.stream>>>(
       g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.f[MB_FMZ].p,
-      c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0);
+      c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, pc, ep);
   MB_CUDA(cudaGetLastError());
   return 0;
 }
-int k_wsolve5(Ctx& c, double dts, bool last) { return launch_wsolve5<6>(c, dts, last); }
+int k_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
+  // One warp per CTA and a latency-bound column sweep: what matters on small
+  // per-GPU grids is the number of CTA waves.  A shallower ring needs less shared
+  // memory (5 instead of 4 CTAs per SM at kz = 41): take it when it saves a wave.
+  const Geo& g = c.g;
+  const long long nblk = ((long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1) + 31) / 32;
+  auto waves = [&](int d) {
+    const long long smem = (long long)(3 * (g.kz + 1) + d * 9) * 32 * 8 + 1024;
+    long long per_sm = (227 * 1024) / smem;
+    if (per_sm > 32) per_sm = 32;
+    if (per_sm < 1) per_sm = 1;
+    return (nblk + 148 * per_sm - 1) / (148 * per_sm);
+  };
+  if (waves(4) == 1 && waves(6) == 2) return launch_wsolve5<4>(c, dts, last, pc, ep);
+  return launch_wsolve5<6>(c, dts, last, pc, ep);
+}
 
 // ---------------------------------------------------------------------------
 // K10  horizontal momentum update                                    :677-721
@@ -489,42 +521,51 @@ __global__ void moloch_uvupdate(Geo g, double* __restrict__ u, double* __restric
                                 const double* __restrict__ hx, const double* __restrict__ hy,
                                 const double* __restrict__ mu, const double* __restrict__ mv,
                                 const double* __restrict__ gzitakh, double dts, double dtrdx, double dtrdy,
-                                int damped) {
+                                int damped, WaitCtl wc, PushCtl pc, EdgePush eu, EdgePush ev) {
+  halo_sync(wc);   // pai ghosts of a fused round
   THREAD_JIK(g.jde1, g.ide1, 1)
-  if (j > g.jde2 || i > g.ide2) return;
-  const bool du = in_box(j, i, g.jdi1, g.jdi2, g.ici1, g.ici2);
-  const bool dv = in_box(j, i, g.jci1, g.jci2, g.idi1, g.idi2);
-  if (!du && !dv) return;
-  const long long id = IX(j, i, k);
-  const long long i2 = IX2(j, i);
-  const double tv0 = tetav[id], pai0 = pai[id];
-  const double zfz = egrav * dts;
-  const double gk = gzitakh[k];
-  // u, v still hold the values of the start of the sub-step (the reference's
-  // ud, vd); the divergence-damped values (:749,:758) are in ud, vd
-  const double uold = u[id], vold = v[id];
-  if (du) {
-    const double zcx = dtrdx * mu[i2];
-    const double zrom1u = 0.5 * cpd * (tetav[id - 1] + tv0);
-    const double zcor1u = coru[i2] * dts * vold;
-    const double ub = damped ? ud[id] : uold;
-    u[id] = ub + bdywtu[id] * (zcor1u - zfz * hx[i2] * gk - zcx * zrom1u * (pai0 - pai[id - 1]));
-  }
-  if (dv) {
-    const double zcy = g.lrotllr ? dtrdy : dtrdy * mv[i2];
-    const double zrom1v = 0.5 * cpd * (tetav[id - g.NJ] + tv0);
-    const double zcor1v = corv[i2] * dts * uold;
-    const double vb = damped ? vd[id] : vold;
-    v[id] = vb + bdywtv[id] * (-zcor1v - zfz * hy[i2] * gk - zcy * zrom1v * (pai0 - pai[id - g.NJ]));
+  const bool inside = (j <= g.jde2 && i <= g.ide2);
+  const bool du = inside && in_box(j, i, g.jdi1, g.jdi2, g.ici1, g.ici2);
+  const bool dv = inside && in_box(j, i, g.jci1, g.jci2, g.idi1, g.idi2);
+  if (du || dv) {
+    const long long id = IX(j, i, k);
+    const long long i2 = IX2(j, i);
+    const double tv0 = tetav[id], pai0 = pai[id];
+    const double zfz = egrav * dts;
+    const double gk = gzitakh[k];
+    // u, v still hold the values of the start of the sub-step (the reference's
+    // ud, vd); the divergence-damped values (:749,:758) are in ud, vd
+    const double uold = u[id], vold = v[id];
+    if (du) {
+      const double zcx = dtrdx * mu[i2];
+      const double zrom1u = 0.5 * cpd * (tetav[id - 1] + tv0);
+      const double zcor1u = coru[i2] * dts * vold;
+      const double ub = damped ? ud[id] : uold;
+      const double un = ub + bdywtu[id] * (zcor1u - zfz * hx[i2] * gk - zcx * zrom1u * (pai0 - pai[id - 1]));
+      u[id] = un;
+      if (pc.mask) edge_push(pc, eu, j, i, k, un);
+    }
+    if (dv) {
+      const double zcy = g.lrotllr ? dtrdy : dtrdy * mv[i2];
+      const double zrom1v = 0.5 * cpd * (tetav[id - g.NJ] + tv0);
+      const double zcor1v = corv[i2] * dts * uold;
+      const double vb = damped ? vd[id] : vold;
+      const double vn = vb + bdywtv[id] * (-zcor1v - zfz * hy[i2] * gk - zcy * zrom1v * (pai0 - pai[id - g.NJ]));
+      v[id] = vn;
+      if (pc.mask) edge_push(pc, ev, j, i, k, vn);
+    }
   }
 }
-int k_uvupdate(Ctx& c, double dts) {
+int k_uvupdate(Ctx& c, double dts, const WaitCtl* wc, const PushCtl* pc, const EdgePush* eu, const EdgePush* ev) {
   const Geo& g = c.g;
+  const WaitCtl w0 = wc ? *wc : WaitCtl{};
+  const PushCtl p0 = pc ? *pc : PushCtl{};
+  const EdgePush e0 = eu ? *eu : EdgePush{}, e1 = ev ? *ev : EdgePush{};
   LaunchScope ls(c, KID_UVUPDATE);
   moloch_uvupdate<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
       g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_BDYWTU].p,
       c.f[MB_BDYWTV].p, c.f[MB_CORU].p, c.f[MB_CORV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFU].p,
-      c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx, c.cfg.mo_divdamp ? 1 : 0);
+      c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx, c.cfg.mo_divdamp ? 1 : 0, w0, p0, e0, e1);
   MB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -983,17 +1024,12 @@ int k_status_update(Ctx& c, double dtinc) {
 // are never read.
 // ---------------------------------------------------------------------------
 int k_reset_tendencies(Ctx& c) {
-  const Geo& g = c.g;
-  const size_t pl = (size_t)g.plane * sizeof(double);
+  // tten, uten, vten, qxten, chiten, s, zdiv2 are consecutive arena slots: one
+  // clear.  (wwkw, also cleared by the reference, only exists inside moloch_wsolve.)
+  const Layout& L = c.layout;
+  const size_t lo = L.off[MB_TTEN], hi = L.off[MB_ZDIV2] + L.size[MB_ZDIV2];
   LaunchScope ls(c, KID_RESET);
-  MB_CUDA(cudaMemsetAsync(c.f[MB_S].p, 0, pl * (g.kz + 1), c.stream));
-  MB_CUDA(cudaMemsetAsync(c.f[MB_ZDIV2].p, 0, pl * g.kz, c.stream));
-  MB_CUDA(cudaMemsetAsync(c.wwkw, 0, pl * (g.kz + 1), c.stream));
-  MB_CUDA(cudaMemsetAsync(c.f[MB_TTEN].p, 0, pl * g.kz, c.stream));
-  MB_CUDA(cudaMemsetAsync(c.f[MB_UTEN].p, 0, pl * g.kz, c.stream));
-  MB_CUDA(cudaMemsetAsync(c.f[MB_VTEN].p, 0, pl * g.kz, c.stream));
-  MB_CUDA(cudaMemsetAsync(c.f[MB_QXTEN].p, 0, pl * g.kz * g.nqx, c.stream));
-  if (g.ntr > 0) MB_CUDA(cudaMemsetAsync(c.f[MB_CHITEN].p, 0, pl * g.kz * g.ntr, c.stream));
+  MB_CUDA(cudaMemsetAsync(c.arena + lo, 0, hi - lo, c.stream));
   return 0;
 }
 

@@ -205,7 +205,7 @@ static int do_wafone_range(Ctx& c, int first, int count) {
     // ghost columns instead of receiving it (:955/:1012), so it needs wz with
     // corner ghosts and pp on two ghost columns: 3 batched messages per side
     // instead of the reference's 2 per field.
-    if (c.wafz_impl == 2 ? k_waf_z2(c, first, count, dta) : k_waf_z3(c, first, count, dta)) return 1;
+    if (k_waf_z2(c, first, count, dta)) return 1;
     for (int q = 0; q < count; ++q) items[q] = {c.wzall + q * fsz, kz};
     if (halo_exchange(c, items.data(), count, HS_CROSS, 2, false, true)) return 1;
     // second round, left/right incl. the ghost rows (corners): wz, the
@@ -354,7 +354,6 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) c->fuse_halo = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_WSOLVE")) c->wsolve_impl = atoi(e) == 2 ? 2 : 5;
-  if (const char* e = getenv("MOLOCH_B200_WAFZ")) c->wafz_impl = atoi(e) == 2 ? 2 : 3;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaFree(c->arena);
     delete c;

@@ -114,7 +114,6 @@ struct Ctx {
   double *zru, *zrd;      // static ratios of the vertical WAF pass
   int waf_impl = 2;       // 1: per-loop kernels, 2: field-batched fused kernels
   int wsolve_impl = 5;    // 2: CTA-parallel coefficients + one-warp sweeps, 5: thread per column with a cp.async ring
-  int wafz_impl = 3;      // vertical kernel of the batched path: 2 shared-memory columns, 3 register chunks
   double *wzall, *p0all;  // per-field scratch of the batched wafone
   double* prof[MB_NPROFILES];
   int prof_n[MB_NPROFILES];
@@ -260,7 +259,6 @@ int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int n
 // kernels_waf.cu
 int k_waf_ratios(Ctx& c);
 int k_waf_z2(Ctx& c, int first, int count, double dta);
-int k_waf_z3(Ctx& c, int first, int count, double dta);
 int k_waf_yx(Ctx& c, int first, int count, double dta);
 
 // ---- halo exchange (halo.cu) ------------------------------------------------

@@ -513,6 +513,7 @@ int k_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& 
 // ---------------------------------------------------------------------------
 // K10  horizontal momentum update                                    :677-721
 // ---------------------------------------------------------------------------
+template <bool FUSED>
 __global__ void moloch_uvupdate(Geo g, double* __restrict__ u, double* __restrict__ v,
                                 const double* __restrict__ ud, const double* __restrict__ vd,
                                 const double* __restrict__ tetav, const double* __restrict__ pai,
@@ -522,7 +523,7 @@ __global__ void moloch_uvupdate(Geo g, double* __restrict__ u, double* __restric
                                 const double* __restrict__ mu, const double* __restrict__ mv,
                                 const double* __restrict__ gzitakh, double dts, double dtrdx, double dtrdy,
                                 int damped, WaitCtl wc, PushCtl pc, EdgePush eu, EdgePush ev) {
-  halo_sync(wc);   // pai ghosts of a fused round
+  if (FUSED) halo_sync(wc);   // pai ghosts of a fused round
   THREAD_JIK(g.jde1, g.ide1, 1)
   const bool inside = (j <= g.jde2 && i <= g.ide2);
   const bool du = inside && in_box(j, i, g.jdi1, g.jdi2, g.ici1, g.ici2);
@@ -543,7 +544,7 @@ __global__ void moloch_uvupdate(Geo g, double* __restrict__ u, double* __restric
       const double ub = damped ? ud[id] : uold;
       const double un = ub + bdywtu[id] * (zcor1u - zfz * hx[i2] * gk - zcx * zrom1u * (pai0 - pai[id - 1]));
       u[id] = un;
-      if (pc.mask) edge_push(pc, eu, j, i, k, un);
+      if (FUSED && pc.mask) edge_push(pc, eu, j, i, k, un);
     }
     if (dv) {
       const double zcy = g.lrotllr ? dtrdy : dtrdy * mv[i2];
@@ -552,7 +553,7 @@ __global__ void moloch_uvupdate(Geo g, double* __restrict__ u, double* __restric
       const double vb = damped ? vd[id] : vold;
       const double vn = vb + bdywtv[id] * (-zcor1v - zfz * hy[i2] * gk - zcy * zrom1v * (pai0 - pai[id - g.NJ]));
       v[id] = vn;
-      if (pc.mask) edge_push(pc, ev, j, i, k, vn);
+      if (FUSED && pc.mask) edge_push(pc, ev, j, i, k, vn);
     }
   }
 }
@@ -562,10 +563,17 @@ int k_uvupdate(Ctx& c, double dts, const WaitCtl* wc, const PushCtl* pc, const E
   const PushCtl p0 = pc ? *pc : PushCtl{};
   const EdgePush e0 = eu ? *eu : EdgePush{}, e1 = ev ? *ev : EdgePush{};
   LaunchScope ls(c, KID_UVUPDATE);
-  moloch_uvupdate<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
-      g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_BDYWTU].p,
-      c.f[MB_BDYWTV].p, c.f[MB_CORU].p, c.f[MB_CORV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFU].p,
-      c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx, c.cfg.mo_divdamp ? 1 : 0, w0, p0, e0, e1);
+  const dim3 grid = grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz);
+  if (w0.mask || p0.mask)
+    moloch_uvupdate<true><<<grid, dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_BDYWTU].p,
+        c.f[MB_BDYWTV].p, c.f[MB_CORU].p, c.f[MB_CORV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFU].p,
+        c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx, c.cfg.mo_divdamp ? 1 : 0, w0, p0, e0, e1);
+  else
+    moloch_uvupdate<false><<<grid, dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_BDYWTU].p,
+        c.f[MB_BDYWTV].p, c.f[MB_CORU].p, c.f[MB_CORV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFU].p,
+        c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx, c.cfg.mo_divdamp ? 1 : 0, w0, p0, e0, e1);
   MB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -234,8 +234,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    px = args.px or None
-    py = args.py or None
+    # Decomposition: RegCM lets the user fix it (njxcpus/niycpus in &dimparam); its
+    # automatic choice (set_nproc) is the most square one.  On NVLink the 1-D split
+    # along i measures faster (contiguous rows only, two neighbours), so that is the
+    # bench default; --px/--py (or BENCH_PX/BENCH_PY) select any other, e.g. 2x4.
+    px = args.px or (1 if world > 1 else None)
+    py = args.py or (world if world > 1 else None)
+    if world > 1 and wl.iy // py < 3:
+        px, py = None, None     # too thin: fall back to set_nproc's choice
     m = MolochB200(wl, rank=rank, nranks=world, px=px, py=py, device=local_rank).allocate_moloch()
     if world > 1:
         if args.transport == "nccl":
@@ -317,7 +323,7 @@ def main():
     dom = next((k for k in kernels if k["gbs"]), None)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if dom and os.path.exists(tpath):
+    if dom and world == 1 and os.path.exists(tpath):   # ncu figures are per launch on the whole grid
         try:
             traffic = json.load(open(tpath)).get(wl.name, {}).get(dom["kernel"])
         except Exception:
@@ -328,6 +334,11 @@ def main():
                     "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["avg_ms"],
                     "share_of_step": dom["share"],
+                    # `achieved` counts the ALGORITHMIC bytes of the reference loops the kernel replaces
+                    # (SURVEY.md App. D); a fused kernel moves fewer (`traffic`, ncu) and can exceed 1.0
+                    "traffic_gbs": (traffic / (dom["avg_ms"] * 1e-3) / 1e9) if traffic and world == 1 else None,
+                    "note": "fused kernel: frac is against the unfused loops' algorithmic bytes; the kernel itself "
+                            "is bound by FP64 instruction issue (profiles/), not by HBM",
                     "whole_step": {"achieved": wl.bytes_per_cell_update() * value / 1e9,
                                    "frac": wl.bytes_per_cell_update() * value / 1e9 / peak / world}}
 

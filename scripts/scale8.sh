@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 T=${TAG:-s8}
 nvidia-smi -L | wc -l
-( time timeout 600 python -m pytest tests/test_gpu_multi.py -q -x -k "${TESTS:-2x4}" ) > gpurun_out/${T}_pytest.log 2>&1
+( time timeout 600 python -m pytest tests/test_gpu_multi.py -q -x -k "${TESTS:-2x2 or 2x4}" ) > gpurun_out/${T}_pytest.log 2>&1
 tail -4 gpurun_out/${T}_pytest.log
 run() {  # name ngpu devices port extra-env...
   local name=$1 n=$2 dev=$3 port=$4; shift 4
@@ -13,7 +13,7 @@ run() {  # name ngpu devices port extra-env...
       > gpurun_out/${T}_${name}.json 2> gpurun_out/${T}_${name}.err
   else
     env CUDA_VISIBLE_DEVICES=$dev "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n \
-      --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 10 --warmup 3 --no-e2e \
+      --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 10 --warmup 3 ${NOE2E---no-e2e} \
       > gpurun_out/${T}_${name}.json 2> gpurun_out/${T}_${name}.err
   fi
 }
@@ -29,18 +29,12 @@ for name in sys.argv[1:]:
         print(name, "FAILED", e)
 PY
 }
-if [ "${SKIP_N8:-0}" != "1" ]; then
-run n8 8 0,1,2,3,4,5,6,7 29518
-run n8_1x8 8 0,1,2,3,4,5,6,7 29519 BENCH_PX=1 BENCH_PY=8
-run n8_4x2 8 0,1,2,3,4,5,6,7 29520 BENCH_PX=4 BENCH_PY=2
-show ${T}_n8 ${T}_n8_1x8 ${T}_n8_4x2
-fi
+NOE2E= run n8 8 0,1,2,3,4,5,6,7 29518   # the driver's own N=8 invocation (with the e2e leg)
+run n8_2x4 8 0,1,2,3,4,5,6,7 29519 BENCH_PX=2 BENCH_PY=4
+show ${T}_n8 ${T}_n8_2x4
 run n4 4 0,1,2,3 29521 &
 run n2 2 4,5 29522 &
-run n2_1x2 2 6,7 29523 BENCH_PX=1 BENCH_PY=2 &
-wait
-run n4_1x4 4 0,1,2,3 29524 BENCH_PX=1 BENCH_PY=4 &
 run n1 1 6 0 &
 wait
-show ${T}_n4 ${T}_n4_1x4 ${T}_n2 ${T}_n2_1x2 ${T}_n1
+show ${T}_n4 ${T}_n2 ${T}_n1
 tail -3 gpurun_out/${T}_n8.err

@@ -209,6 +209,15 @@ struct Rank {
   // 2-D
   Arr mx, mu, mv, mx2, rmx, rmu, rmv, hx, hy, coru, corv, ht, htu, htv, ulat, vlat, ps, ibnd_cr,
       ibnd_ud, ibnd_vd;
+  // lateral boundary buffers: v3dbound/v2dbound b0, b1 (Main/mod_atm_interface.F90:547-577)
+  Arr dub0, dub1, dvb0, dvb1, xtb0, xtb1, xpaib0, xpaib1, xqb0, xqb1, xlb0, xlb1, xib0, xib1, xpsb0, xpsb1;
+  std::vector<Arr> chib0, chib1;
+  // UW-PBL TKE (ibltyp == 2): Main/mod_atm_interface.F90:609-612, [F90:184]
+  Arr tke, tketen, tkex;
+  // mkslice outputs (Main/mod_atm_interface.F90:964-1012, :599)
+  Arr pf3d, th3d, rhb3d, wpx3d, rhox2d, tp2d, th700;
+  // mospectral_nudge work arrays (Main/mod_bdycod.F90:422, :3868-3873), contiguous like the Fortran ones
+  Arr zn1; std::vector<double> sx, sxg, sy, syg;
   std::map<std::string, FieldInfo> reg;
 };
 
@@ -220,6 +229,13 @@ struct World {
   double mo_dzita, rdzita, dx, rdx, dtsec, dtstepa, dtsound;
   bool lrotllr, do_divdamp, do_divfilter;
   int nqx, ntr, iqfrst, ipptls;
+  // boundary / slice extension (oracle_set_ext)
+  oracle_ext_config x{};
+  bool ext_set = false;
+  double rtb = 0.0, xbctime = 0.0, tspectral = 0.0;
+  int nztop = 0, km = 0, lm = 0;
+  std::vector<double> gmeanz, tnudge, cnudge, fcx;  // 1-based via [k]
+  std::vector<double> bvx, bvy;                      // lowpass basis, global: bvx[(k-1)*jx + (j-1)]
 };
 
 template <class F> void each(World& w, F f) { for (auto& r : w.r) f(r); }
@@ -416,6 +432,92 @@ void alloc_rank(World& w, Rank& r) {
   R("mx2", &r.mx2, S_DOT, 1); R("rmx", &r.rmx, S_DOT, 1); R("rmu", &r.rmu, S_DOT, 1); R("rmv", &r.rmv, S_DOT, 1);
 }
 
+// arrays of the boundary / slice / TKE extension (oracle_set_ext)
+void alloc_ext(World& w, Rank& r) {
+  const Geom& g = r.g; const int kz = g.kz, kzp1 = g.kzp1;
+  auto R = [&](const char* n, Arr* a, Stag s, int nk) { r.reg[n] = FieldInfo{a, s, nk}; };
+  if (w.x.do_bdy) {
+    // allocate_v3dbound / allocate_v2dbound (Main/mod_atm_interface.F90:547-577)
+    for (Arr* a : {&r.dub0, &r.dub1, &r.dvb0, &r.dvb1}) a->alloc(g.jde1gb(), g.jde2gb(), g.ide1gb(), g.ide2gb(), 1, kz);
+    for (Arr* a : {&r.xtb0, &r.xtb1, &r.xpaib0, &r.xpaib1, &r.xqb0, &r.xqb1, &r.xlb0, &r.xlb1, &r.xib0, &r.xib1})
+      a->alloc(g.jce1ga(), g.jce2ga(), g.ice1ga(), g.ice2ga(), 1, kz);
+    for (Arr* a : {&r.xpsb0, &r.xpsb1}) a->alloc(g.jce1ga(), g.jce2ga(), g.ice1ga(), g.ice2ga());
+    if (w.x.ichem == 1 && w.x.ichebdy != 0) {
+      r.chib0.resize(w.ntr); r.chib1.resize(w.ntr);
+      for (auto& a : r.chib0) a.alloc(g.jce1ga(), g.jce2ga(), g.ice1ga(), g.ice2ga(), 1, kz);
+      for (auto& a : r.chib1) a.alloc(g.jce1ga(), g.jce2ga(), g.ice1ga(), g.ice2ga(), 1, kz);
+    }
+    R("dub0", &r.dub0, S_U, kz); R("dub1", &r.dub1, S_U, kz); R("dvb0", &r.dvb0, S_V, kz); R("dvb1", &r.dvb1, S_V, kz);
+    R("xtb0", &r.xtb0, S_CROSS, kz); R("xtb1", &r.xtb1, S_CROSS, kz);
+    R("xpaib0", &r.xpaib0, S_CROSS, kz); R("xpaib1", &r.xpaib1, S_CROSS, kz);
+    R("xqb0", &r.xqb0, S_CROSS, kz); R("xqb1", &r.xqb1, S_CROSS, kz);
+    R("xlb0", &r.xlb0, S_CROSS, kz); R("xlb1", &r.xlb1, S_CROSS, kz);
+    R("xib0", &r.xib0, S_CROSS, kz); R("xib1", &r.xib1, S_CROSS, kz);
+    R("xpsb0", &r.xpsb0, S_CROSS, 1); R("xpsb1", &r.xpsb1, S_CROSS, 1);
+    r.zn1.alloc(g.jde1, g.jde2, g.ide1, g.ide2);
+  }
+  if (w.x.ibltyp == 2) {
+    r.tke.alloc(g.jce1, g.jce2, g.ice1, g.ice2, 1, kzp1);
+    r.tketen.alloc(g.jci1, g.jci2, g.ici1, g.ici2, 1, kzp1);
+    r.tkex.alloc(g.jce1, g.jce2, g.ice1, g.ice2, 1, kz);
+    R("tke", &r.tke, S_CROSS, kzp1); R("tketen", &r.tketen, S_CROSS, kzp1); R("tkex", &r.tkex, S_CROSS, kz);
+  }
+  r.pf3d.alloc(g.jce1, g.jce2, g.ice1, g.ice2, 1, kzp1);
+  r.th3d.alloc(g.jce1, g.jce2, g.ice1, g.ice2, 1, kz);
+  r.rhb3d.alloc(g.jci1, g.jci2, g.ici1, g.ici2, 1, kz);
+  r.wpx3d.alloc(g.jci1, g.jci2, g.ici1, g.ici2, 1, kz);
+  r.rhox2d.alloc(g.jci1, g.jci2, g.ici1, g.ici2);
+  r.tp2d.alloc(g.jci1, g.jci2, g.ici1, g.ici2);
+  r.th700.alloc(g.jci1, g.jci2, g.ici1, g.ici2);
+  R("pf3d", &r.pf3d, S_CROSS, kzp1); R("th3d", &r.th3d, S_CROSS, kz); R("rhb3d", &r.rhb3d, S_CROSS, kz);
+  R("wpx3d", &r.wpx3d, S_CROSS, kz); R("rhox2d", &r.rhox2d, S_CROSS, 1); R("tp2d", &r.tp2d, S_CROSS, 1);
+  R("th700", &r.th700, S_CROSS, 1);
+}
+
+// setup_bdycon, idynamic == 3 branch (Main/mod_bdycod.F90:478-568): rtb, the
+// global mean level heights, nztop, tnudge, lowpass_init.  hefc itself is an
+// input table (exponential_nudging / relax_coefficients are host-side set-up).
+void lowpass_init(World& w);
+void setup_bdycon(World& w) {
+  const oracle_config& c = w.c; const int kz = c.kz;
+  w.rtb = 1.0 / w.x.dtbdys;
+  w.gmeanz.assign(kz + 1, 0.0); w.tnudge.assign(kz + 1, 0.0); w.cnudge.assign(kz + 1, 0.0);
+  if (w.fcx.empty()) w.fcx.assign(std::max(c.nspgx, 1) + 1, 0.0);
+  w.nztop = 0;
+  const double zztop = 18000.0;
+  if (w.x.mo_top_nudge || w.x.mo_spectral_nudge) {
+    const int njcross = (w.r[0].g.band ? c.jx : c.jx - 1), nicross = (w.r[0].g.crm ? c.iy : c.iy - 1);
+    const double np = (double)(njcross * nicross);
+    for (int k = 1; k <= kz; ++k) {
+      double mpmeanz = 0.0;
+      for (auto& r : w.r) {   // sumall over ranks
+        double meanz = 0.0;
+        for (int i = r.g.ice1; i <= r.g.ice2; ++i) for (int j = r.g.jce1; j <= r.g.jce2; ++j)
+          meanz = meanz + r.zeta(j, i, k) / np;
+        mpmeanz += meanz;
+      }
+      w.gmeanz[k] = mpmeanz;
+      if (w.gmeanz[k] > zztop) w.nztop = w.nztop + 1;
+    }
+  }
+  if (w.x.mo_spectral_nudge) {
+    lowpass_init(w);
+    for (auto& r : w.r) {
+      const Geom& g = r.g;
+      r.sx.assign((size_t)(g.ide2 - g.ide1 + 1) * 2 * w.km, 0.0); r.sxg = r.sx;
+      r.sy.assign((size_t)(g.jde2 - g.jde1 + 1) * 2 * w.lm, 0.0); r.syg = r.sy;
+    }
+  }
+  if (w.x.mo_top_nudge) {
+    for (int k = 1; k <= kz; ++k) {
+      if (k <= w.nztop) {
+        const double sn = std::sin(0.5 * mathpi * (w.gmeanz[k] - zztop) / (c.mo_h - zztop));
+        w.tnudge[k] = sn * sn;
+      } else w.tnudge[k] = 0.0;
+    }
+  }
+}
+
 // resolve "qx"/"trac"/"qxten"/"chiten" (4-D, all species) or plain 3-D/2-D names
 bool lookup(World& w, Rank& r, const std::string& name, std::vector<FieldInfo>& out) {
   out.clear();
@@ -424,6 +526,8 @@ bool lookup(World& w, Rank& r, const std::string& name, std::vector<FieldInfo>& 
   if (name == "trac") { for (auto& a : r.trac) out.push_back({&a, S_CROSS, kz}); return true; }
   if (name == "qxten") { for (auto& a : r.qxten) out.push_back({&a, S_CROSS, kz}); return true; }
   if (name == "chiten") { for (auto& a : r.chiten) out.push_back({&a, S_CROSS, kz}); return true; }
+  if (name == "chib0") { for (auto& a : r.chib0) out.push_back({&a, S_CROSS, kz}); return !r.chib0.empty(); }
+  if (name == "chib1") { for (auto& a : r.chib1) out.push_back({&a, S_CROSS, kz}); return !r.chib1.empty(); }
   auto it = r.reg.find(name);
   if (it == r.reg.end()) return false;
   out.push_back(it->second);
@@ -613,6 +717,7 @@ int setup_static(World& w) {
         w.ffilt[k] = mo_zfilt_fac * (sn * sn);
       }
     } }
+  if (w.ext_set && w.x.do_bdy) setup_bdycon(w);
   return 0;
 }
 
@@ -678,6 +783,10 @@ void reset_tendencies(World& w) {
       for (int j = g.jci1; j <= g.jci2; ++j) a(j, i, k) = 0.0; }
     for (auto& a : r.chiten) { PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i)
       for (int j = g.jci1; j <= g.jci2; ++j) a(j, i, k) = 0.0; }
+    if (w.ext_set && w.x.ibltyp == 2) {   // [F90:1071-1075]
+      PAR2 for (int k = 1; k <= kzp1; ++k) for (int i = g.ici1; i <= g.ici2; ++i)
+        for (int j = g.jci1; j <= g.jci2; ++j) r.tketen(j, i, k) = 0.0;
+    }
   });
 }
 
@@ -983,36 +1092,38 @@ void uvxtouvstag(World& w) {
 }
 
 // zstagtoh [F90:1445-1459], htozstag [F90:1461-1475]
-void zstagtoh(World& w) {
+void zstagtoh(World& w, Arr Rank::*fl, Arr Rank::*hl) {
   const int kz = w.c.kz, kzm1 = kz - 1, kzp1 = kz + 1;
   each(w, [&](Rank& r) {
-    const Geom& g = r.g;
+    const Geom& g = r.g; Arr& f = r.*fl; Arr& h = r.*hl;
     PAR2 for (int k = 2; k <= kzm1; ++k) for (int i = g.ice1; i <= g.ice2; ++i) for (int j = g.jce1; j <= g.jce2; ++j)
-      r.wx(j, i, k) = 0.5625 * (r.w(j, i, k + 1) + r.w(j, i, k)) - 0.0625 * (r.w(j, i, k + 2) + r.w(j, i, k - 1));
+      h(j, i, k) = 0.5625 * (f(j, i, k + 1) + f(j, i, k)) - 0.0625 * (f(j, i, k + 2) + f(j, i, k - 1));
     PAR1 for (int i = g.ice1; i <= g.ice2; ++i) for (int j = g.jce1; j <= g.jce2; ++j) {
-      r.wx(j, i, 1) = 0.5 * (r.w(j, i, 2) + r.w(j, i, 1));
-      r.wx(j, i, kz) = 0.5 * (r.w(j, i, kzp1) + r.w(j, i, kz));
+      h(j, i, 1) = 0.5 * (f(j, i, 2) + f(j, i, 1));
+      h(j, i, kz) = 0.5 * (f(j, i, kzp1) + f(j, i, kz));
     }
   });
 }
-void htozstag(World& w) {
+void htozstag(World& w, Arr Rank::*hl, Arr Rank::*fl) {
   const int kz = w.c.kz, kzm1 = kz - 1;
   each(w, [&](Rank& r) {
-    const Geom& g = r.g;
+    const Geom& g = r.g; Arr& f = r.*fl; Arr& h = r.*hl;
     PAR2 for (int k = 3; k <= kzm1; ++k) for (int i = g.ice1; i <= g.ice2; ++i) for (int j = g.jce1; j <= g.jce2; ++j)
-      r.w(j, i, k) = 0.5625 * (r.wx(j, i, k) + r.wx(j, i, k - 1)) - 0.0625 * (r.wx(j, i, k + 1) + r.wx(j, i, k - 2));
+      f(j, i, k) = 0.5625 * (h(j, i, k) + h(j, i, k - 1)) - 0.0625 * (h(j, i, k + 1) + h(j, i, k - 2));
     PAR1 for (int i = g.ice1; i <= g.ice2; ++i) for (int j = g.jce1; j <= g.jce2; ++j) {
-      r.w(j, i, 2) = 0.5 * (r.wx(j, i, 2) + r.wx(j, i, 1));
-      r.w(j, i, kz) = 0.5 * (r.wx(j, i, kz) + r.wx(j, i, kzm1));
+      f(j, i, 2) = 0.5 * (h(j, i, 2) + h(j, i, 1));
+      f(j, i, kz) = 0.5 * (h(j, i, kz) + h(j, i, kzm1));
     }
   });
 }
 
-// advection [F90:767-836] (ibltyp /= 2: no TKE)
+// advection [F90:767-836]
 void advection(World& w, double dta) {
   const int kz = w.c.kz;
+  const bool tke = w.ext_set && w.x.ibltyp == 2;
   uvstagtouvx(w);
-  zstagtoh(w);
+  zstagtoh(w, &Rank::w, &Rank::wx);
+  if (tke) zstagtoh(w, &Rank::tke, &Rank::tkex);   // [F90:782-784]
   wafone(w, [](Rank& r) -> Arr& { return r.tetav; }, dta);
   wafone(w, [](Rank& r) -> Arr& { return r.pai; }, dta);
   wafone(w, [](Rank& r) -> Arr& { return r.ux; }, dta);
@@ -1021,6 +1132,7 @@ void advection(World& w, double dta) {
   wafone(w, [](Rank& r) -> Arr& { return r.qx[0]; }, dta);
   if (w.ipptls > 0)
     for (int n = w.iqfrst; n <= w.nqx; ++n) wafone(w, [n](Rank& r) -> Arr& { return r.qx[n - 1]; }, dta);
+  if (tke) wafone(w, [](Rank& r) -> Arr& { return r.tkex; }, dta);   // [F90:799-801]
   for (int n = 1; n <= w.ntr; ++n) wafone(w, [n](Rank& r) -> Arr& { return r.trac[n - 1]; }, dta);
   // curvature terms [F90:811-825]
   each(w, [&](Rank& r) {
@@ -1042,7 +1154,8 @@ void advection(World& w, double dta) {
     }
   });
   uvxtouvstag(w);
-  htozstag(w);
+  htozstag(w, &Rank::wx, &Rank::w);
+  if (tke) htozstag(w, &Rank::tkex, &Rank::tke);   // [F90:832-834]
 }
 
 // temp_to_tvirt [F90:1608-1627], tvirt_to_temp [F90:1629-1648]
@@ -1106,7 +1219,7 @@ void diagnostics(World& w) {
   });
 }
 
-// status_update [F90:1403-1443] (ibltyp /= 2)
+// status_update [F90:1403-1443]
 void status_update(World& w, double dtinc) {
   const int kz = w.c.kz;
   each(w, [&](Rank& r) {
@@ -1121,6 +1234,13 @@ void status_update(World& w, double dtinc) {
       PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
         q(j, i, k) = q(j, i, k) + dtinc * qt(j, i, k);
         if (q(j, i, k) < qxcheckval[n]) q(j, i, k) = qxzeroval[n];
+      }
+    }
+    if (w.ext_set && w.x.ibltyp == 2) {   // [F90:1419-1424]
+      const double tkemin = w.x.tkemin;
+      PAR2 for (int k = 1; k <= kz + 1; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+        r.tke(j, i, k) = r.tke(j, i, k) + dtinc * r.tketen(j, i, k);
+        if (r.tke(j, i, k) < tkemin) r.tke(j, i, k) = tkemin;
       }
     }
     for (int n = 0; n < w.ntr; ++n) {
@@ -1143,12 +1263,448 @@ void status_update(World& w, double dtinc) {
   uvxtouvstag(w);
 }
 
-// moloch [F90:312-446] with do_apply_bdy = .false. (irceideal / test modes,
-// [F90:305]) and physics disabled ([F90:362]); mkslice/massck/report skipped.
+// ---------------------------------------------------------------------------
+// Lateral boundary: `boundary` [F90:448-529] and what it calls
+// ---------------------------------------------------------------------------
+
+// bdyval, MOLOCH branch (Main/mod_bdycod.F90:1618-1875) and the closing
+// xbctime = xbctime + dtsec (:2653).  The SST update at :2620-2651 acts on
+// sfs%tg (surface model) and is outside the dycore path.
+void chem_bdyval(World& w);
+void bdyval(World& w) {
+  const double x1 = (w.xbctime + w.dtsec) * w.rtb;
+  const double x0 = 1.0 - x1;
+  const int kz = w.c.kz, nqx = w.nqx, iqfrst = w.iqfrst;
+  const bool pqc = w.x.present_qc != 0, pqi = w.x.present_qi != 0;
+  const bool tke = w.x.ibltyp == 2;
+  const double tkemin = w.x.tkemin;
+  auto skip = [&](int n) { return (pqc && n == 2) || (pqi && n == 3); };
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g;
+    Arr& qv = r.qx[0];
+    auto lin = [&](const Arr& b0, const Arr& b1, int j, int i, int k) { return x0 * b0(j, i, k) + x1 * b1(j, i, k); };
+    // west / east: corners excluded (:1641-1702, :1706-1767)
+    for (int side = 0; side < 2; ++side) {
+      if (side == 0 ? !g.bl : !g.br) continue;
+      const int jd = side == 0 ? g.jde1 : g.jde2, jc = side == 0 ? g.jce1 : g.jce2;
+      const int jin = side == 0 ? g.jci1 : g.jci2;
+      const double sgn = side == 0 ? 1.0 : -1.0;   // inflow: u > 0 (west), u < 0 (east)
+      for (int i = g.ici1; i <= g.ici2; ++i) r.ps(jc, i) = x0 * r.xpsb0(jc, i) + x1 * r.xpsb1(jc, i);
+      for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) r.u(jd, i, k) = lin(r.dub0, r.dub1, jd, i, k);
+      for (int k = 1; k <= kz; ++k) for (int i = g.idi1; i <= g.idi2; ++i) r.v(jc, i, k) = lin(r.dvb0, r.dvb1, jc, i, k);
+      for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) {
+        r.t(jc, i, k) = lin(r.xtb0, r.xtb1, jc, i, k);
+        r.pai(jc, i, k) = lin(r.xpaib0, r.xpaib1, jc, i, k);
+        qv(jc, i, k) = lin(r.xqb0, r.xqb1, jc, i, k);
+      }
+      if (pqc) for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i)
+        r.qx[1](jc, i, k) = lin(r.xlb0, r.xlb1, jc, i, k);
+      if (pqi && w.ipptls > 1) for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i)
+        r.qx[2](jc, i, k) = lin(r.xib0, r.xib1, jc, i, k);
+      for (int n = iqfrst; n <= nqx; ++n) {
+        if (skip(n)) continue;
+        Arr& q = r.qx[n - 1];
+        for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) {
+          const double qxint = q(jin, i, k);
+          if (sgn * r.u(jd, i, k) > 0.0) q(jc, i, k) = qxzeroval[n - 1]; else q(jc, i, k) = qxint;
+        }
+      }
+      for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) {
+        if (sgn * r.u(jd, i, k) > 0.0) r.w(jc, i, k) = 0.0; else r.w(jc, i, k) = r.w(jin, i, k);
+      }
+      if (tke) {
+        for (int i = g.ici1; i <= g.ici2; ++i) r.tke(jc, i, 1) = tkemin;
+        for (int k = 2; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) {
+          if (sgn * (r.u(jd, i, k) + r.u(jd, i, k - 1)) > 0.0) r.tke(jc, i, k + 1) = tkemin;
+          else r.tke(jc, i, k + 1) = r.tke(jin, i, k + 1);
+        }
+      }
+    }
+    // south / north: corners included (:1771-1832, :1836-1897)
+    for (int side = 0; side < 2; ++side) {
+      if (side == 0 ? !g.bb : !g.bt) continue;
+      const int id = side == 0 ? g.ide1 : g.ide2, ic = side == 0 ? g.ice1 : g.ice2;
+      const int iin = side == 0 ? g.ici1 : g.ici2;
+      const double sgn = side == 0 ? 1.0 : -1.0;
+      for (int j = g.jce1; j <= g.jce2; ++j) r.ps(j, ic) = x0 * r.xpsb0(j, ic) + x1 * r.xpsb1(j, ic);
+      for (int k = 1; k <= kz; ++k) for (int j = g.jde1; j <= g.jde2; ++j) r.u(j, ic, k) = lin(r.dub0, r.dub1, j, ic, k);
+      for (int k = 1; k <= kz; ++k) for (int j = g.jce1; j <= g.jce2; ++j) r.v(j, id, k) = lin(r.dvb0, r.dvb1, j, id, k);
+      for (int k = 1; k <= kz; ++k) for (int j = g.jce1; j <= g.jce2; ++j) {
+        r.t(j, ic, k) = lin(r.xtb0, r.xtb1, j, ic, k);
+        r.pai(j, ic, k) = lin(r.xpaib0, r.xpaib1, j, ic, k);
+        qv(j, ic, k) = lin(r.xqb0, r.xqb1, j, ic, k);
+      }
+      if (pqc) for (int k = 1; k <= kz; ++k) for (int j = g.jce1; j <= g.jce2; ++j)
+        r.qx[1](j, ic, k) = lin(r.xlb0, r.xlb1, j, ic, k);
+      if (pqi && w.ipptls > 1) for (int k = 1; k <= kz; ++k) for (int j = g.jce1; j <= g.jce2; ++j)
+        r.qx[2](j, ic, k) = lin(r.xib0, r.xib1, j, ic, k);
+      for (int n = iqfrst; n <= nqx; ++n) {
+        if (skip(n)) continue;
+        Arr& q = r.qx[n - 1];
+        for (int k = 1; k <= kz; ++k) for (int j = g.jce1; j <= g.jce2; ++j) {
+          const double qxint = q(j, iin, k);
+          if (sgn * r.v(j, id, k) > 0.0) q(j, ic, k) = qxzeroval[n - 1]; else q(j, ic, k) = qxint;
+        }
+      }
+      for (int k = 1; k <= kz; ++k) for (int j = g.jce1; j <= g.jce2; ++j) {
+        if (sgn * r.v(j, id, k) > 0.0) r.w(j, ic, k) = 0.0; else r.w(j, ic, k) = r.w(j, iin, k);
+      }
+      if (tke) {
+        for (int j = g.jce1; j <= g.jce2; ++j) r.tke(j, ic, 1) = tkemin;
+        for (int k = 2; k <= kz; ++k) for (int j = g.jce1; j <= g.jce2; ++j) {
+          if (sgn * (r.v(j, id, k) + r.v(j, id, k - 1)) > 0.0) r.tke(j, ic, k + 1) = tkemin;
+          else r.tke(j, ic, k + 1) = r.tke(j, iin, k + 1);
+        }
+      }
+    }
+  });
+  if (w.x.ichem == 1 && w.ntr > 0) chem_bdyval(w);
+  w.xbctime = w.xbctime + w.dtsec;   // :2653
+}
+
+// chem_bdyval_uncoupled (Main/chemlib/mod_che_bdyco.F90:391-535)
+void chem_bdyval(World& w) {
+  const int kz = w.c.kz;
+  if (w.x.ichebdy == 0) {
+    each(w, [&](Rank& r) {
+      const Geom& g = r.g;
+      for (int n = 0; n < w.ntr; ++n) {
+        Arr& c = r.trac[n];
+        if (g.bl) for (int k = 1; k <= kz; ++k) for (int i = g.ice1; i <= g.ice2; ++i) {
+          const double trint = c(g.jci1, i, k), windavg = r.u(g.jde1, i, k) - r.u(g.jdi1, i, k);
+          c(g.jce1, i, k) = (windavg < 0.0) ? trint : 0.0;
+        }
+        if (g.br) for (int k = 1; k <= kz; ++k) for (int i = g.ice1; i <= g.ice2; ++i) {
+          const double trint = c(g.jci2, i, k), windavg = r.u(g.jde2, i, k) - r.u(g.jdi2, i, k);
+          c(g.jce2, i, k) = (windavg > 0.0) ? trint : 0.0;
+        }
+      }
+      for (int n = 0; n < w.ntr; ++n) {
+        Arr& c = r.trac[n];
+        if (g.bb) for (int k = 1; k <= kz; ++k) for (int j = g.jci1; j <= g.jci2; ++j) {
+          const double trint = c(j, g.ici1, k), windavg = r.v(j, g.ide1, k) - r.v(j, g.idi1, k);
+          c(j, g.ice1, k) = (windavg < 0.0) ? trint : 0.0;
+        }
+        if (g.bt) for (int k = 1; k <= kz; ++k) for (int j = g.jci1; j <= g.jci2; ++j) {
+          const double trint = c(j, g.ici2, k), windavg = r.v(j, g.ide2, k) - r.v(j, g.idi2, k);
+          c(j, g.ice2, k) = (windavg > 0.0) ? trint : 0.0;
+        }
+      }
+    });
+    return;
+  }
+  // time-dependent boundary values (:507-531); note the division by dtbdys
+  const double x1 = (w.xbctime + w.dtsec) / w.x.dtbdys;
+  const double x0 = 1.0 - x1;
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g;
+    for (int n = 0; n < w.ntr; ++n) {
+      Arr& c = r.trac[n]; const Arr& b0 = r.chib0[n]; const Arr& b1 = r.chib1[n];
+      if (g.bl) for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i)
+        c(g.jce1, i, k) = x0 * b0(g.jce1, i, k) + x1 * b1(g.jce1, i, k);
+      if (g.br) for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i)
+        c(g.jce2, i, k) = x0 * b0(g.jce2, i, k) + x1 * b1(g.jce2, i, k);
+      if (g.bb) for (int k = 1; k <= kz; ++k) for (int j = g.jce1; j <= g.jce2; ++j)
+        c(j, g.ice1, k) = x0 * b0(j, g.ice1, k) + x1 * b1(j, g.ice1, k);
+      if (g.bt) for (int k = 1; k <= kz; ++k) for (int j = g.jce1; j <= g.jce2; ++j)
+        c(j, g.ice2, k) = x0 * b0(j, g.ice2, k) + x1 * b1(j, g.ice2, k);
+    }
+  });
+}
+
+// motopnudge (Main/mod_bdycod.F90:4049-4081), called with wfac = 0, dta = dtsec
+void motopnudge(World& w, double wfac, double dta) {
+  const double trtau = 1.0 / (2.0 * 3600.0), wrtau = 1.0 / (3600.0 / 4.0);
+  const double x1 = (w.xbctime + w.dtsec) * w.rtb, x0 = 1.0 - x1;
+  const int nztop = w.nztop;
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g;
+    for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+      const double fext = wfac * r.w(j, i, 2);
+      const double xf = wrtau * dta;
+      r.w(j, i, 2) = (1.0 - xf) * r.w(j, i, 2) + xf * fext;
+    }
+    PAR2 for (int k = 1; k <= nztop; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+      const double fext = x0 * r.xtb0(j, i, k) + x1 * r.xtb1(j, i, k);
+      const double xf = w.tnudge[k] * trtau * dta;
+      r.t(j, i, k) = (1.0 - xf) * r.t(j, i, k) + xf * fext;
+    }
+    PAR2 for (int k = 1; k <= nztop; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jdi1; j <= g.jdi2; ++j) {
+      const double fext = x0 * r.dub0(j, i, k) + x1 * r.dub1(j, i, k);
+      const double xf = w.tnudge[k] * trtau * dta;
+      r.u(j, i, k) = (1.0 - xf) * r.u(j, i, k) + xf * fext;
+    }
+    PAR2 for (int k = 1; k <= nztop; ++k) for (int i = g.idi1; i <= g.idi2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+      const double fext = x0 * r.dvb0(j, i, k) + x1 * r.dvb1(j, i, k);
+      const double xf = w.tnudge[k] * trtau * dta;
+      r.v(j, i, k) = (1.0 - xf) * r.v(j, i, k) + xf * fext;
+    }
+  });
+}
+
+// morelax_external (Main/mod_bdycod.F90:3995-4031)
+void morelax_external(World& w, int stag, const ArrFn& getf, const ArrFn& getb0, const ArrFn& getb1) {
+  const double x1 = (w.xbctime + w.dtsec) * w.rtb, x0 = 1.0 - x1;
+  const int kz = w.c.kz, nsp = w.c.nspgx;
+  if (nsp <= 0) return;   // ba%havebound is false everywhere
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g;
+    int j1 = g.jci1, j2 = g.jci2, i1 = g.ici1, i2 = g.ici2; const Arr* ibnd = &r.ibnd_cr;
+    if (stag == S_U) { j1 = g.jdi1; j2 = g.jdi2; ibnd = &r.ibnd_ud; }
+    if (stag == S_V) { i1 = g.idi1; i2 = g.idi2; ibnd = &r.ibnd_vd; }
+    Arr& f = getf(r); const Arr& b0 = getb0(r); const Arr& b1 = getb1(r);
+    PAR2 for (int k = 1; k <= kz; ++k) for (int i = i1; i <= i2; ++i) for (int j = j1; j <= j2; ++j) {
+      const int ib = (int)(*ibnd)(j, i);
+      if (ib > 0) {
+        const double xf = w.hefc[(size_t)((k - 1) * nsp + (ib - 1))];
+        const double fext = (x0 * b0(j, i, k) + x1 * b1(j, i, k));
+        f(j, i, k) = (1.0 - xf) * f(j, i, k) + xf * fext;
+      }
+    }
+  });
+}
+
+// morelax_fraction (Main/mod_bdycod.F90:3962-3993); only called for w with frac = 0
+void morelax_fraction(World& w, const ArrFn& getf, double frac) {
+  const int kz = w.c.kz, nsp = w.c.nspgx;
+  if (nsp <= 0) return;
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g; Arr& f = getf(r);
+    PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+      const int ib = (int)r.ibnd_cr(j, i);
+      if (ib > 0) {
+        const double xf = w.hefc[(size_t)((k - 1) * nsp + (ib - 1))];
+        f(j, i, k) = (1.0 - xf) * f(j, i, k) + xf * f(j, i, k) * frac;
+      }
+    }
+  });
+}
+
+// morelax_chiten (Main/chemlib/mod_che_bdyco.F90:965-1026).  cba%ibnd and its
+// south/north/west/east flags partition the same cells as ba_cr%ibnd > 0, so
+// the four masked loops visit every sponge cell exactly once.
+void morelax_chiten(World& w) {
+  const double x1 = (w.xbctime + w.dtsec) / w.x.dtbdys, x0 = 1.0 - x1;
+  const int kz = w.c.kz, nsp = w.c.nspgx;
+  if (nsp <= 0) return;
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g;
+    for (int n = 0; n < w.ntr; ++n) {
+      Arr& f = r.trac[n]; const Arr& b0 = r.chib0[n]; const Arr& b1 = r.chib1[n];
+      PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+        const int ib = (int)r.ibnd_cr(j, i);
+        if (ib > 0) {
+          const double xf = w.fcx[ib];
+          const double fext = (x0 * b0(j, i, k) + x1 * b1(j, i, k));
+          f(j, i, k) = (1.0 - xf) * f(j, i, k) + xf * fext;
+        }
+      }
+    }
+  });
+}
+
+// lowpass_init (Main/mod_bdycod.F90:3844-3896) on the global index space
+void lowpass_init(World& w) {
+  const oracle_config& c = w.c;
+  const int jx = c.jx, iy = c.iy, kz = c.kz;
+  const bool band = w.r[0].g.band, crm = w.r[0].g.crm;
+  const int njcross = band ? jx : jx - 1, nicross = crm ? iy : iy - 1;
+  const double ds = c.dx / 1000.0;
+  w.km = std::max((int)std::lround((njcross * ds) / 1500.0), 1);
+  w.lm = std::max((int)std::lround((nicross * ds) / 750.0), 1);
+  const double dx = mathpi / (double)(njcross - 1), dy = mathpi / (double)(nicross - 1);
+  const int km = w.km, lm = w.lm;
+  std::vector<double> px(2 * km + 1), py(2 * lm + 1);
+  for (int k = 1; k <= 2 * km; ++k) { const double q = (double)k / (double)km; px[k] = std::exp(-(q * q)); }
+  for (int l = 1; l <= 2 * lm; ++l) { const double q = (double)l / (double)lm; py[l] = std::exp(-(q * q)); }
+  w.bvx.assign((size_t)2 * km * jx, 0.0); w.bvy.assign((size_t)2 * lm * iy, 0.0);
+  for (int k = 1; k <= 2 * km; ++k) for (int j = 1; j <= jx; ++j)
+    w.bvx[(size_t)(k - 1) * jx + (j - 1)] = std::sqrt(2.0 / (double)(jx - 1) * px[k]) * std::sin((double)(k * (j - 2)) * dx);
+  for (int l = 1; l <= 2 * lm; ++l) for (int i = 1; i <= iy; ++i)
+    w.bvy[(size_t)(l - 1) * iy + (i - 1)] = std::sqrt(2.0 / (double)(iy - 1) * py[l]) * std::sin((double)(l * (i - 2)) * dy);
+  const double cn0 = w.x.dtrad * w.rtb;
+  w.cnudge.assign(kz + 1, 0.0);
+  for (int k = 1; k <= kz; ++k) { const double q = w.gmeanz[k] / c.mo_h; w.cnudge[k] = cn0 * std::min(q * q, 1.0); }
+}
+
+// mospectral_nudge + lowpass_filter (Main/mod_bdycod.F90:3898-3960).
+// row_reduce/column_reduce are MPI_Allreduce(SUM) over the ranks of a row /
+// column (mod_mppparam.F90:20620-20664) with count = nk*(i2-i1+1) ELEMENTS OF
+// THE CONTIGUOUS sx(ide1:ide2,1:2km) array: when i1:i2 is shorter than
+// ide1:ide2 (the top row of ranks: ice2 = ide2-1) the tail of the array is not
+// reduced and sxg keeps what an earlier call left there.  Restated as is.
+struct SpecRange { int j1, j2, i1, i2, jj1, jj2, ii1, ii2; };
+using RangeFn = std::function<SpecRange(const Geom&)>;
+void mospectral_nudge(World& w, const RangeFn& range, const ArrFn& getf, const ArrFn& getb0, const ArrFn& getb1) {
+  const double x1 = (w.xbctime + w.dtsec) * w.rtb, x0 = 1.0 - x1;
+  const int kz = w.c.kz, jx = w.c.jx, iy = w.c.iy, km2 = 2 * w.km, lm2 = 2 * w.lm;
+  const int nr = (int)w.r.size(), py = w.c.py;
+  auto bvx = [&](int j, int k) { return w.bvx[(size_t)(k - 1) * jx + (j - 1)]; };
+  auto bvy = [&](int i, int l) { return w.bvy[(size_t)(l - 1) * iy + (i - 1)]; };
+  for (int k = 1; k <= kz; ++k) {
+    for (auto& r : w.r) {
+      const Geom& g = r.g; const SpecRange q = range(g);
+      Arr& f = getf(r); const Arr& b0 = getb0(r); const Arr& b1 = getb1(r); Arr& zn1 = r.zn1;
+      for (int i = q.i1; i <= q.i2; ++i) for (int j = q.j1; j <= q.j2; ++j)
+        zn1(j, i) = (x0 * b0(j, i, k) + x1 * b1(j, i, k)) - f(j, i, k);
+      const int ni = g.ide2 - g.ide1 + 1;
+      for (int kk = 1; kk <= km2; ++kk) for (int i = q.i1; i <= q.i2; ++i) {
+        double acc = 0.0;
+        for (int j = q.jj1; j <= q.jj2; ++j) acc = acc + zn1(j, i) * bvx(j, kk);
+        r.sx[(size_t)(kk - 1) * ni + (i - g.ide1)] = acc;
+      }
+    }
+    for (int a = 0; a < nr; ++a) {   // row_reduce: ranks with the same loci, summed in rank order
+      Rank& r = w.r[a]; const SpecRange q = range(r.g);
+      const size_t count = (size_t)km2 * (size_t)(q.i2 - q.i1 + 1);
+      for (size_t e = 0; e < count; ++e) {
+        double acc = 0.0; bool first = true;
+        for (int b = 0; b < nr; ++b) if (b % py == a % py) { acc = first ? w.r[b].sx[e] : acc + w.r[b].sx[e]; first = false; }
+        r.sxg[e] = acc;
+      }
+    }
+    for (auto& r : w.r) {
+      const Geom& g = r.g; const SpecRange q = range(g); Arr& zn1 = r.zn1;
+      const int ni = g.ide2 - g.ide1 + 1, nj = g.jde2 - g.jde1 + 1;
+      for (auto& v : zn1.d) v = 0.0;
+      for (int kk = 1; kk <= km2; ++kk) for (int i = q.i1; i <= q.i2; ++i) for (int j = q.j1; j <= q.j2; ++j)
+        zn1(j, i) = zn1(j, i) + r.sxg[(size_t)(kk - 1) * ni + (i - g.ide1)] * bvx(j, kk);
+      for (int l = 1; l <= lm2; ++l) for (int j = q.j1; j <= q.j2; ++j) {
+        double acc = 0.0;
+        for (int i = q.ii1; i <= q.ii2; ++i) acc = acc + zn1(j, i) * bvy(i, l);
+        r.sy[(size_t)(l - 1) * nj + (j - g.jde1)] = acc;
+      }
+    }
+    for (int a = 0; a < nr; ++a) {   // column_reduce: ranks with the same locj
+      Rank& r = w.r[a]; const SpecRange q = range(r.g);
+      const size_t count = (size_t)lm2 * (size_t)(q.j2 - q.j1 + 1);
+      for (size_t e = 0; e < count; ++e) {
+        double acc = 0.0; bool first = true;
+        for (int b = 0; b < nr; ++b) if (b / py == a / py) { acc = first ? w.r[b].sy[e] : acc + w.r[b].sy[e]; first = false; }
+        r.syg[e] = acc;
+      }
+    }
+    for (auto& r : w.r) {
+      const Geom& g = r.g; const SpecRange q = range(g); Arr& zn1 = r.zn1; Arr& f = getf(r);
+      const int nj = g.jde2 - g.jde1 + 1;
+      for (auto& v : zn1.d) v = 0.0;
+      for (int l = 1; l <= lm2; ++l) for (int i = q.i1; i <= q.i2; ++i) for (int j = q.j1; j <= q.j2; ++j)
+        zn1(j, i) = zn1(j, i) + r.syg[(size_t)(l - 1) * nj + (j - g.jde1)] * bvy(i, l);
+      for (int i = q.ii1; i <= q.ii2; ++i) for (int j = q.jj1; j <= q.jj2; ++j)
+        f(j, i, k) = f(j, i, k) + w.cnudge[k] * zn1(j, i);
+    }
+  }
+}
+
+// boundary [F90:448-529] (idiag = 0, ichdiag = 0)
+void uvstagtouvx(World& w);
+void temp_to_tvirt(World& w);
+void boundary(World& w) {
+  const int kz = w.c.kz;
+  bdyval(w);
+  if (w.x.mo_top_nudge) motopnudge(w, 0.0, w.dtsec);
+  morelax_external(w, S_U, [](Rank& r) -> Arr& { return r.u; }, [](Rank& r) -> Arr& { return r.dub0; },
+                   [](Rank& r) -> Arr& { return r.dub1; });
+  morelax_external(w, S_V, [](Rank& r) -> Arr& { return r.v; }, [](Rank& r) -> Arr& { return r.dvb0; },
+                   [](Rank& r) -> Arr& { return r.dvb1; });
+  morelax_external(w, S_CROSS, [](Rank& r) -> Arr& { return r.t; }, [](Rank& r) -> Arr& { return r.xtb0; },
+                   [](Rank& r) -> Arr& { return r.xtb1; });
+  morelax_external(w, S_CROSS, [](Rank& r) -> Arr& { return r.pai; }, [](Rank& r) -> Arr& { return r.xpaib0; },
+                   [](Rank& r) -> Arr& { return r.xpaib1; });
+  morelax_external(w, S_CROSS, [](Rank& r) -> Arr& { return r.qx[0]; }, [](Rank& r) -> Arr& { return r.xqb0; },
+                   [](Rank& r) -> Arr& { return r.xqb1; });
+  morelax_fraction(w, [](Rank& r) -> Arr& { return r.w; }, 0.0);
+  if (w.ipptls > 0) {
+    if (w.x.present_qc)
+      morelax_external(w, S_CROSS, [](Rank& r) -> Arr& { return r.qx[1]; }, [](Rank& r) -> Arr& { return r.xlb0; },
+                       [](Rank& r) -> Arr& { return r.xlb1; });
+    if (w.ipptls > 1 && w.x.present_qi)
+      morelax_external(w, S_CROSS, [](Rank& r) -> Arr& { return r.qx[2]; }, [](Rank& r) -> Arr& { return r.xib0; },
+                       [](Rank& r) -> Arr& { return r.xib1; });
+  }
+  if (w.x.ichem == 1 && w.ntr > 0 && w.x.ichebdy != 0) morelax_chiten(w);
+  if (w.x.mo_spectral_nudge) {
+    w.tspectral = w.tspectral + w.dtsec;
+    if ((int)std::fmod(w.tspectral, w.x.dtrad) == 0) {
+      // NB the reference passes jci1,jci1 as the j update range of t [F90:502]
+      mospectral_nudge(w, [](const Geom& g) { return SpecRange{g.jce1, g.jce2, g.ice1, g.ice2, g.jci1, g.jci1, g.ici1, g.ici2}; },
+                       [](Rank& r) -> Arr& { return r.t; }, [](Rank& r) -> Arr& { return r.xtb0; },
+                       [](Rank& r) -> Arr& { return r.xtb1; });
+      mospectral_nudge(w, [](const Geom& g) { return SpecRange{g.jde1, g.jde2, g.ice1, g.ice2, g.jdi1, g.jdi2, g.ici1, g.ici2}; },
+                       [](Rank& r) -> Arr& { return r.u; }, [](Rank& r) -> Arr& { return r.dub0; },
+                       [](Rank& r) -> Arr& { return r.dub1; });
+      mospectral_nudge(w, [](const Geom& g) { return SpecRange{g.jce1, g.jce2, g.ide1, g.ide2, g.jci1, g.jci2, g.idi1, g.idi2}; },
+                       [](Rank& r) -> Arr& { return r.v; }, [](Rank& r) -> Arr& { return r.dvb0; },
+                       [](Rank& r) -> Arr& { return r.dvb1; });
+    }
+  }
+  uvstagtouvx(w);
+  temp_to_tvirt(w);
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g;
+    PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ice1; i <= g.ice2; ++i) for (int j = g.jce1; j <= g.jce2; ++j)
+      r.tetav(j, i, k) = r.tvirt(j, i, k) / r.pai(j, i, k);
+  });
+}
+
+// mkslice, idynamic == 3 branch (Main/mod_slice.F90:115-173).  atms%ps2d is
+// sfs%psb; in a MOLOCH run psa and psb are the same surface pressure the
+// dycore extrapolates [F90:354], so `ps` is used.
+void mkslice(World& w) {
+  const int kz = w.c.kz, kzp1 = kz + 1;
+  const double rhmin = w.x.rhmin, rhmax = w.x.rhmax;
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g;
+    for (int i = g.ice1; i <= g.ice2; ++i) for (int j = g.jce1; j <= g.jce2; ++j) r.pf3d(j, i, kzp1) = r.ps(j, i);
+    PAR2 for (int k = 2; k <= kz; ++k) for (int i = g.ice1; i <= g.ice2; ++i) for (int j = g.jce1; j <= g.jce2; ++j)
+      r.pf3d(j, i, k) = p00 * std::pow(0.5 * (r.pai(j, i, k) + r.pai(j, i, k - 1)), cpovr);
+    for (int i = g.ice1; i <= g.ice2; ++i) for (int j = g.jce1; j <= g.jce2; ++j)
+      r.pf3d(j, i, 1) = r.pf3d(j, i, 2) - egrav * r.rho(j, i, 1) * (r.zetaf(j, i, 1) - r.zetaf(j, i, 2));
+    for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+      r.rhox2d(j, i) = r.ps(j, i) / (rgas * r.t(j, i, kz));
+      r.tp2d(j, i) = r.t(j, i, kz) * std::pow(r.ps(j, i) / r.p(j, i, kz), rovcp);
+    }
+    PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ice1; i <= g.ice2; ++i) for (int j = g.jce1; j <= g.jce2; ++j)
+      r.th3d(j, i, k) = r.t(j, i, k) * std::pow(p00 / r.p(j, i, k), rovcp);
+    for (int n = 0; n < w.nqx; ++n) {
+      Arr& q = r.qx[n];
+      PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+        if (q(j, i, k) < qxcheckval[n]) q(j, i, k) = qxzeroval[n];
+    }
+    if (w.x.ichem == 1) for (int n = 0; n < w.ntr; ++n) {
+      Arr& q = r.trac[n];
+      PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+        if (q(j, i, k) < 1.0e-50) q(j, i, k) = 0.0;
+    }
+    PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+      r.rhb3d(j, i, k) = std::min(std::max(r.qx[0](j, i, k) / r.qsat(j, i, k), rhmin), rhmax);
+    PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+      r.wpx3d(j, i, k) = -egrav * r.rho(j, i, k) * 0.5 * (r.w(j, i, k + 1) + r.w(j, i, k));
+    if (w.x.icldmstrat == 1) {
+      for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+        r.th700(j, i) = r.th3d(j, i, kz);
+        for (int k = 2; k <= kz - 1; ++k) {
+          if (r.p(j, i, k) > 70000.0) {
+            const double w1 = (r.p(j, i, k) - 70000.0) / (r.p(j, i, k) - r.p(j, i, k - 1));
+            const double w2 = 1.0 - w1;
+            r.th700(j, i) = r.th3d(j, i, k - 1) * w1 + r.th3d(j, i, k) * w2;
+            break;
+          }
+        }
+      }
+    }
+  });
+}
+
+// moloch [F90:312-446]: physics disabled ([F90:362]); massck/report skipped.
+// Without oracle_set_ext: do_apply_bdy = .false. (irceideal / test modes,
+// [F90:305]) and no mkslice.
 void moloch_step(World& w) {
   reset_tendencies(w);
   dynamical_core(w);
+  if (w.ext_set && w.x.do_bdy) boundary(w);
   diagnostics(w);
+  if (w.ext_set && w.x.do_slice) mkslice(w);
   status_update(w, w.dtsec);
 }
 
@@ -1192,10 +1748,24 @@ void* oracle_create(const oracle_config* cfg) {
 
 void oracle_destroy(void* h) { delete (World*)h; }
 
+int oracle_set_ext(void* h, const oracle_ext_config* x) {
+  World& w = *(World*)h;
+  if (!x) { g_err = "null ext config"; return 1; }
+  if (w.ext_set) { g_err = "oracle_set_ext called twice"; return 1; }
+  if (x->do_bdy && !(x->dtbdys > 0.0)) { g_err = "dtbdys must be > 0"; return 1; }
+  if (x->do_bdy && x->mo_spectral_nudge && !(x->dtrad > 0.0)) { g_err = "dtrad must be > 0"; return 1; }
+  w.x = *x; w.ext_set = true;
+  for (auto& r : w.r) alloc_ext(w, r);
+  w.fcx.assign(std::max(w.c.nspgx, 1) + 1, 0.0);
+  return 0;
+}
+
 long oracle_global_size(void* h, const char* name) {
   World& w = *(World*)h; std::string s(name);
   const long plane = (long)w.c.jx * w.c.iy;
   if (s == "rlat") return w.c.iy + 1;
+  if (s == "fcx") return w.c.nspgx;
+  if (s == "tnudge" || s == "cnudge" || s == "gmeanz") return w.c.kz;
   if (s == "hefc") return (long)w.c.nspgx * w.c.kz;
   if (s == "ffilt" || s == "xkdamp" || s == "xknu" || s == "gzitakh" || s == "zitah") return w.c.kz;
   if (s == "gzitak" || s == "zita") return w.c.kz + 1;
@@ -1210,6 +1780,10 @@ int oracle_set_global(void* h, const char* name, const double* src) {
   const int jx = w.c.jx, iy = w.c.iy;
   if (s == "rlat") { for (int i = 1; i <= iy + 1; ++i) w.rlat[i] = src[i - 1]; return 0; }
   if (s == "hefc") { std::copy(src, src + w.hefc.size(), w.hefc.begin()); return 0; }
+  if (s == "tnudge" || s == "cnudge") {   // override the sumall-order dependent profiles (decomposition tests)
+    std::vector<double>& v = (s == "tnudge") ? w.tnudge : w.cnudge;
+    v.assign(w.c.kz + 1, 0.0); for (int k = 1; k <= w.c.kz; ++k) v[k] = src[k - 1]; return 0; }
+  if (s == "fcx") { w.fcx.assign(w.c.nspgx + 1, 0.0); for (int n = 1; n <= w.c.nspgx; ++n) w.fcx[n] = src[n - 1]; return 0; }
   if (s == "ffilt") { w.ffilt.assign(w.c.kz + 1, 0.0); for (int k = 1; k <= w.c.kz; ++k) w.ffilt[k] = src[k - 1]; return 0; }
   const bool perj = w.r[0].g.band, peri = w.r[0].g.crm;
   for (auto& r : w.r) {
@@ -1242,6 +1816,10 @@ int oracle_get_global(void* h, const char* name, double* dst) {
   if (s == "gzitakh") return cp(w.gzitakh, kz);
   if (s == "zita") return cp(w.zita, kz + 1);
   if (s == "zitah") return cp(w.zitah, kz);
+  if (s == "tnudge" && !w.tnudge.empty()) return cp(w.tnudge, kz);
+  if (s == "cnudge" && !w.cnudge.empty()) return cp(w.cnudge, kz);
+  if (s == "gmeanz" && !w.gmeanz.empty()) return cp(w.gmeanz, kz);
+  if (s == "hefc") { std::copy(w.hefc.begin(), w.hefc.end(), dst); return 0; }
   for (auto& r : w.r) {
     std::vector<FieldInfo> f;
     if (!lookup(w, r, s, f)) { g_err = "unknown field " + s; return 1; }
@@ -1273,6 +1851,27 @@ int oracle_wafone(void* h, const char* field, int n) {
 int oracle_dynamical_core(void* h) { dynamical_core(*(World*)h); return 0; }
 int oracle_diagnostics(void* h) { diagnostics(*(World*)h); return 0; }
 int oracle_status_update(void* h) { World& w = *(World*)h; status_update(w, w.dtsec); return 0; }
+static int need_bdy(World& w) {
+  if (!(w.ext_set && w.x.do_bdy)) { g_err = "boundary not configured (oracle_set_ext with do_bdy)"; return 1; }
+  if (w.rtb == 0.0) { g_err = "oracle_setup_static has not run after oracle_set_ext"; return 1; }
+  return 0;
+}
+int oracle_boundary(void* h) { World& w = *(World*)h; if (need_bdy(w)) return 1; boundary(w); return 0; }
+int oracle_bdyval(void* h) { World& w = *(World*)h; if (need_bdy(w)) return 1; bdyval(w); return 0; }
+int oracle_mkslice(void* h) {
+  World& w = *(World*)h;
+  if (!w.ext_set) { g_err = "oracle_set_ext has not been called"; return 1; }
+  mkslice(w); return 0;
+}
+int oracle_set_xbctime(void* h, double t) { ((World*)h)->xbctime = t; return 0; }
+double oracle_get_xbctime(void* h) { return ((World*)h)->xbctime; }
+int oracle_get_int(void* h, const char* name) {
+  World& w = *(World*)h; std::string s(name);
+  if (s == "nztop") return w.nztop;
+  if (s == "km") return w.km;
+  if (s == "lm") return w.lm;
+  return -1;
+}
 
 void oracle_set_threads(int n) {
 #ifdef _OPENMP

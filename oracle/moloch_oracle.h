@@ -47,7 +47,25 @@ typedef struct {
   double mo_ztop, mo_h, mo_a0;
 } oracle_config;
 
+/* Lateral boundary (Main/mod_moloch.F90:448-529 `boundary`), mkslice
+ * (Main/mod_slice.F90:115-173) and the UW-PBL TKE path (ibltyp == 2).  Set
+ * once after oracle_create and before oracle_setup_static.                  */
+typedef struct {
+  int do_bdy;                  /* do_apply_bdy (Main/mod_moloch.F90:305,341)       */
+  int present_qc, present_qi;  /* ICBC carries qc / qi (Main/mod_bdycod.F90:695,699) */
+  int mo_top_nudge, mo_spectral_nudge; /* Share/mod_dynparam.F90:207,209           */
+  int ichem, ichebdy;          /* tracer boundary: 0 flux dependent, 1 chib0/chib1  */
+  int ibltyp;                  /* 2: TKE is a prognostic, advected variable         */
+  int icldmstrat;              /* 1: mkslice finds theta at 700 hPa                 */
+  int do_slice;                /* call mkslice inside oracle_step                   */
+  int bdy_lehmann;             /* unused by the oracle (hefc is an input table)     */
+  int reserved;
+  double dtbdys, dtrad;        /* boundary / radiation periods [s]                  */
+  double rhmin, rhmax, tkemin; /* Main/mod_params.F90:381-382, mod_pbl_interface:50 */
+} oracle_ext_config;
+
 void*  oracle_create(const oracle_config* cfg);
+int    oracle_set_ext(void* h, const oracle_ext_config* x);
 void   oracle_destroy(void* h);
 const char* oracle_last_error(void);
 
@@ -75,6 +93,18 @@ int    oracle_wafone(void* h, const char* field, int n); /* wafone(field(:,:,:,n
 int    oracle_dynamical_core(void* h);
 int    oracle_diagnostics(void* h);                  /* p,rho,qsat,ps :348-354*/
 int    oracle_status_update(void* h);
+/* boundary (Main/mod_moloch.F90:448-529): bdyval MOLOCH branch
+ * (Main/mod_bdycod.F90:1618-1875, :2653), chem_bdyval
+ * (Main/chemlib/mod_che_bdyco.F90:391-535), motopnudge (:4049-4081),
+ * morelax_external/_fraction (:3962-4031), morelax_chiten
+ * (mod_che_bdyco.F90:965-1026), mospectral_nudge (:3844-3960), uvstagtouvx,
+ * temp_to_tvirt, tetav.  Uses and advances the oracle's xbctime.             */
+int    oracle_boundary(void* h);
+int    oracle_bdyval(void* h);
+int    oracle_mkslice(void* h);                     /* Main/mod_slice.F90:115-173 */
+int    oracle_set_xbctime(void* h, double xbctime);
+double oracle_get_xbctime(void* h);
+int    oracle_get_int(void* h, const char* name);   /* nztop, km, lm              */
 
 void   oracle_set_threads(int n);
 int    oracle_get_threads(void);

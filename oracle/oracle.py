@@ -21,6 +21,13 @@ class OracleConfig(C.Structure):
         (n, C.c_double) for n in ("dtsec", "dx", "mo_ztop", "mo_h", "mo_a0")]
 
 
+class OracleExtConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "do_bdy", "present_qc", "present_qi", "mo_top_nudge", "mo_spectral_nudge", "ichem", "ichebdy",
+        "ibltyp", "icldmstrat", "do_slice", "bdy_lehmann", "reserved")] + [
+        (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin")]
+
+
 def build(force: bool = False) -> None:
     """Compile the oracle shared libraries (g++, a few seconds)."""
     if force or not (os.path.exists(os.path.join(_HERE, "libmoloch_oracle.so"))
@@ -48,6 +55,13 @@ def _lib(checked: bool):
         for f in ("oracle_setup_static", "oracle_init_state", "oracle_reset_tendencies", "oracle_sound",
                   "oracle_advection", "oracle_dynamical_core", "oracle_diagnostics", "oracle_status_update"):
             getattr(lib, f).argtypes = [C.c_void_p]
+        for f in ("oracle_boundary", "oracle_bdyval", "oracle_mkslice"):
+            getattr(lib, f).argtypes = [C.c_void_p]
+        lib.oracle_set_ext.argtypes = [C.c_void_p, C.POINTER(OracleExtConfig)]
+        lib.oracle_set_xbctime.argtypes = [C.c_void_p, C.c_double]
+        lib.oracle_get_xbctime.argtypes = [C.c_void_p]
+        lib.oracle_get_xbctime.restype = C.c_double
+        lib.oracle_get_int.argtypes = [C.c_void_p, C.c_char_p]
         lib.oracle_step.argtypes = [C.c_void_p, C.c_int]
         lib.oracle_wafone.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         _libs[key] = lib
@@ -68,6 +82,15 @@ class Oracle:
         self.h = self.lib.oracle_create(C.byref(self.cfg))
         if not self.h:
             raise RuntimeError(self.lib.oracle_last_error().decode())
+        self.ext = None
+        if getattr(wl, "needs_ext", False):
+            self.ext = OracleExtConfig(do_bdy=wl.do_bdy, present_qc=wl.present_qc, present_qi=wl.present_qi,
+                                       mo_top_nudge=wl.mo_top_nudge, mo_spectral_nudge=wl.mo_spectral_nudge,
+                                       ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, ibltyp=wl.ibltyp,
+                                       icldmstrat=wl.icldmstrat, do_slice=wl.do_slice, bdy_lehmann=0, reserved=0,
+                                       dtbdys=wl.dtbdys, dtrad=wl.dtrad, rhmin=wl.rhmin, rhmax=wl.rhmax,
+                                       tkemin=wl.tkemin)
+            self._chk(self.lib.oracle_set_ext(self.h, C.byref(self.ext)))
 
     def close(self):
         if self.h:
@@ -100,7 +123,7 @@ class Oracle:
             nk = n // plane
             if name in ("qx", "qxten"):
                 return out.reshape(wl.nqx, wl.kz, wl.iy, wl.jx)
-            if name in ("trac", "chiten"):
+            if name in ("trac", "chiten", "chib0", "chib1"):
                 return out.reshape(wl.ntr, wl.kz, wl.iy, wl.jx)
             return out.reshape(wl.iy, wl.jx) if nk == 1 else out.reshape(nk, wl.iy, wl.jx)
         return out
@@ -114,8 +137,17 @@ class Oracle:
             self.set("hefc", P["hefc"])
         if "trac" in P and self.wl.ntr > 0:
             self.set("trac", P["trac"])
+        if "fcx" in P and self.wl.nspgx > 0 and self.ext is not None:
+            self.set("fcx", P["fcx"])
         self._chk(self.lib.oracle_setup_static(self.h))
         self._chk(self.lib.oracle_init_state(self.h))
+        if self.ext is not None and self.wl.ibltyp == 2 and "tke" in P:
+            self.set("tke", P["tke"])
+
+    def load_boundary(self, B: dict) -> None:
+        """b0/b1 buffers of regcm_b200.synthetic.make_boundary (ICBC stand-in)."""
+        for k, v in B.items():
+            self.set(k, v)
 
     def step(self, n: int = 1): self._chk(self.lib.oracle_step(self.h, n))
     def reset_tendencies(self): self._chk(self.lib.oracle_reset_tendencies(self.h))
@@ -124,6 +156,13 @@ class Oracle:
     def dynamical_core(self): self._chk(self.lib.oracle_dynamical_core(self.h))
     def diagnostics(self): self._chk(self.lib.oracle_diagnostics(self.h))
     def status_update(self): self._chk(self.lib.oracle_status_update(self.h))
+    def boundary(self): self._chk(self.lib.oracle_boundary(self.h))
+    def bdyval(self): self._chk(self.lib.oracle_bdyval(self.h))
+    def mkslice(self): self._chk(self.lib.oracle_mkslice(self.h))
+    def set_xbctime(self, t: float): self._chk(self.lib.oracle_set_xbctime(self.h, float(t)))
+    def get_xbctime(self) -> float: return float(self.lib.oracle_get_xbctime(self.h))
+    def get_int(self, name: str) -> int: return int(self.lib.oracle_get_int(self.h, name.encode()))
+
     def wafone(self, field: str, n: int = 1): self._chk(self.lib.oracle_wafone(self.h, field.encode(), n))
 
     def set_threads(self, n: int): self.lib.oracle_set_threads(int(n))

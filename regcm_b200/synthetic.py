@@ -74,6 +74,21 @@ class Workload:
     u0: float = 10.0
     v0: float = 2.0
     seed: int = 20240613
+    # lateral boundary / physics hand-off / TKE
+    do_bdy: int = 0          # do_apply_bdy (Main/mod_moloch.F90:305,341)
+    present_qc: int = 0      # ICBC carries qc / qi (Main/mod_bdycod.F90:695,699)
+    present_qi: int = 0
+    mo_top_nudge: int = 0    # Share/mod_dynparam.F90:209
+    mo_spectral_nudge: int = 0   # :207
+    ichebdy: int = 0         # tracer boundary: 0 flux dependent, 1 chib0/chib1
+    ibltyp: int = 1          # 2: UW PBL, TKE advected by the dycore
+    icldmstrat: int = 0
+    do_slice: int = 0        # mkslice inside moloch()
+    dtbdys: float = 21600.0
+    dtrad: float = 1800.0
+    rhmin: float = 0.01      # Main/mod_params.F90:381-382
+    rhmax: float = 1.01
+    tkemin: float = 1.0e-8
 
     @property
     def dx(self) -> float:
@@ -82,7 +97,11 @@ class Workload:
     @property
     def nfields(self) -> int:
         """F = number of wafone-advected fields."""
-        return 5 + 1 + (self.nqx - 1) + self.ntr
+        return 5 + 1 + (self.nqx - 1 if self.ipptls > 0 else 0) + (1 if self.ibltyp == 2 else 0) + self.ntr
+
+    @property
+    def needs_ext(self) -> bool:
+        return bool(self.do_bdy or self.do_slice or self.ibltyp == 2)
 
     @property
     def cells(self) -> int:
@@ -274,6 +293,101 @@ def make_primary(wl: Workload) -> dict:
             tr[n] += 1.0e-6 * np.exp(-rr)
         P["trac"] = tr
     return P
+
+
+def make_boundary(wl: Workload, base: dict) -> dict:
+    """ICBC stand-in: the b0/b1 buffers `bdyin` keeps for the lateral boundary
+    (Main/mod_bdycod.F90:1079-1423; types v3dbound/v2dbound,
+    Main/mpplib/mod_regcm_types.F90).  b0 is the large-scale state at the
+    start of the boundary interval (here: the model's own initial state
+    `base` with keys u, v, t, pai, qx, ps), b1 the state dtbdys later (b0
+    plus a smooth large-scale change).  Global (nk, iy, jx) arrays."""
+    jx, iy, kz = wl.jx, wl.iy, wl.kz
+    J, I = np.meshgrid(np.arange(1, jx + 1, dtype=np.float64), np.arange(1, iy + 1, dtype=np.float64))
+    wave = np.sin(2 * mathpi * J / jx)[None] * np.cos(2 * mathpi * I / iy)[None]
+    lev = np.linspace(1.0, 0.3, kz)[:, None, None]
+    B = {}
+    B["dub0"] = np.array(base["u"], dtype=np.float64)
+    B["dub1"] = B["dub0"] + 1.5 * wave * lev
+    B["dvb0"] = np.array(base["v"], dtype=np.float64)
+    B["dvb1"] = B["dvb0"] - 1.0 * wave * lev
+    B["xtb0"] = np.array(base["t"], dtype=np.float64)
+    B["xtb1"] = B["xtb0"] + 0.8 * wave * lev
+    B["xpaib0"] = np.array(base["pai"], dtype=np.float64)
+    B["xpaib1"] = B["xpaib0"] * (1.0 + 2.0e-4 * wave * lev)
+    B["xqb0"] = np.array(base["qx"][0], dtype=np.float64)
+    B["xqb1"] = B["xqb0"] * (1.0 + 0.05 * wave)
+    cloud = np.exp(-((np.arange(kz)[:, None, None] - 0.6 * kz) / (0.15 * kz)) ** 2)
+    B["xlb0"] = 2.0e-5 * cloud * (1.0 + 0.5 * wave)
+    B["xlb1"] = 3.0e-5 * cloud * (1.0 - 0.5 * wave)
+    B["xib0"] = 1.0e-5 * cloud * (1.0 - 0.3 * wave)
+    B["xib1"] = 0.5e-5 * cloud * (1.0 + 0.3 * wave)
+    B["xpsb0"] = np.array(base["ps"], dtype=np.float64)
+    B["xpsb1"] = B["xpsb0"] * (1.0 + 1.0e-3 * wave[0])
+    if wl.ntr > 0 and wl.ichebdy != 0:
+        nz = noise((wl.ntr, kz, iy, jx), wl.seed, 11)
+        B["chib0"] = 1.0e-9 * (1.0 + 0.2 * nz)
+        B["chib1"] = 1.0e-9 * (1.0 - 0.2 * nz)
+    return B
+
+
+def make_tke(wl: Workload, zetaf: np.ndarray) -> np.ndarray:
+    """Initial TKE on the kz+1 interfaces (UW PBL, ibltyp == 2): a shallow
+    boundary-layer profile with noise, >= tkemin."""
+    shp = (wl.kz + 1, wl.iy, wl.jx)
+    return wl.tkemin + 0.4 * np.exp(-np.maximum(zetaf, 0.0) / 800.0) * (1.0 + 0.3 * noise(shp, wl.seed, 21))
+
+
+def chem_fcx(wl: Workload) -> np.ndarray:
+    """Tracer relaxation weights fcx(1:nspgx) (Main/chemlib/mod_che_bdyco.F90:101): linear ramp."""
+    n = np.arange(1, wl.nspgx + 1, dtype=np.float64)
+    return np.where((n >= 2) & (n <= wl.nspgx - 1), 0.5 * (wl.nspgx - n) / max(wl.nspgx - 2, 1), 0.0)
+
+
+def relax_coefficients(npts: int, gmmin: float, gmmax: float) -> np.ndarray:
+    """Lehmann (1993) optimal relaxation coefficients: host-side restatement of
+    relax_coefficients (Main/mpplib/mod_runparams.F90:645-697) for
+    bdy_use_lehmann runs (Main/mod_bdycod.F90:524-535)."""
+    npmax = 32
+    p, q = np.zeros(2 * npmax + 1), np.zeros(2 * npmax + 1)
+    n = 1
+    p[1], q[0] = 1.0, 1.0
+    my = np.sqrt(gmmax / gmmin)
+    while n < npts:
+        my = np.sqrt((my + 1.0 / my) / 2.0)
+        pp, qq = np.zeros(2 * npmax + 1), np.zeros(2 * npmax + 1)
+        for i in range(n + 1):
+            for j in range(n + 1):
+                pp[i + j] += p[i] * p[j] + q[i] * q[j]
+                qq[i + j] += 2.0 * my * p[i] * q[j]
+        p[:2 * n + 1], q[:2 * n + 1] = pp[:2 * n + 1], qq[:2 * n + 1]
+        n = 2 * n
+    if n != npts and npts != 1:
+        raise ValueError("nbl np not a power of 2")       # fatal(...,'INVALID BOUNDARY POINT NUMBER.')
+    coeff = np.zeros(npts)
+    for i in range(n, 0, -1):
+        kk = p[i] / q[i - 1]
+        for j in range(i, 0, -1):
+            xxx = q[j]
+            q[j] = p[j] - kk * q[j - 1]
+            p[j] = xxx
+        xxx = q[0]
+        q[0] = p[0]
+        p[0] = xxx
+        kdt2 = kk * np.sqrt(gmmin * gmmax)
+        coeff[i - 1] = kdt2 / (1.0 + kdt2)
+    return coeff
+
+
+def hefc_lehmann(wl: Workload) -> np.ndarray:
+    """hefc(n,k) of the bdy_use_lehmann branch (Main/mod_bdycod.F90:520-535); nspgx-2 must be a power of 2."""
+    nsp, kz = wl.nspgx, wl.kz
+    cflmax = min(0.999, (300.0 * (wl.dt / float(wl.mo_nadv))) / (2.0 * wl.dx))
+    cflmin = max(0.001, (10.0 * (wl.dt / float(wl.mo_nadv))) / (2.0 * wl.dx))
+    h = np.zeros((kz, nsp))
+    h[:, 0] = 1.0
+    h[:, 1:nsp - 1] = relax_coefficients(nsp - 2, cflmin, cflmax)[None, :]
+    return h
 
 
 # ---- derived static fields (compute_moloch_static + init_moloch) ------------

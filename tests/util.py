@@ -21,6 +21,28 @@ def make_oracle(wl, px=1, py=1, checked=False, ffilt=None):
     return o, P
 
 
+def make_oracle_bdy(wl, px=1, py=1, checked=False, same=False):
+    """Oracle with the boundary / slice / TKE extension (Workload.needs_ext):
+    the b0/b1 buffers are generated from the oracle's own initial state."""
+    P = S.make_primary(wl)
+    if wl.nspgx > 0:
+        P["fcx"] = S.chem_fcx(wl)
+    o = Oracle(wl, px=px, py=py, checked=checked)
+    o.load_primary(P)
+    if wl.ibltyp == 2:
+        o.set("tke", S.make_tke(wl, o.get("zetaf")))
+    B = {}
+    if wl.do_bdy:
+        base = {n: o.get(n) for n in ("u", "v", "t", "pai", "qx", "ps")}
+        B = S.make_boundary(wl, base)
+        if same:
+            for n in list(B):
+                if n.endswith("1"):
+                    B[n] = B[n[:-1] + "0"].copy()
+        o.load_boundary(B)
+    return o, B
+
+
 def oracle_inputs(o, wl):
     names = [n for n in STATIC_FIELDS + STATE_FIELDS if not (n == "trac" and wl.ntr == 0)]
     fields = {n: o.get(n) for n in names}

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MOLOCH_B200_ABI_VERSION 1
+#define MOLOCH_B200_ABI_VERSION 2
 
 /* Replaces the module globals read by allocate_moloch/init_moloch:
  * mod_dynparam index ranges (Share/mod_dynparam.F90:252-310), `ma`
@@ -55,8 +55,25 @@ typedef struct {
   int32_t ipptls;                     /* 0,1,2: condensates entering tvirt      */
   int32_t device;                     /* CUDA ordinal; <0 = rank mod ndev
                                          (Main/mod_regcm_interface.F90:397-400) */
-  int32_t reserved;
+  int32_t ibltyp;                     /* 2 (UW PBL): TKE is advected by the dycore
+                                         (Main/mod_moloch.F90:782-784,799-801,832-834) */
   double dtsec, dx, mo_dzita;         /* dt [s], dx [m], zita(kz) spacing [m]   */
+  /* ---- ABI v2: lateral boundary, physics hand-off ---------- */
+  int32_t do_bdy;                     /* do_apply_bdy (Main/mod_moloch.F90:305,341):
+                                         allocate the b0/b1 buffers, enable
+                                         moloch_b200_boundary                    */
+  int32_t nspgx;                      /* sponge width (rows of hefc)            */
+  int32_t present_qc, present_qi;     /* ICBC carries qc/qi (mod_bdycod.F90:695,699) */
+  int32_t mo_top_nudge, mo_spectral_nudge; /* Share/mod_dynparam.F90:207,209     */
+  int32_t nztop;                      /* levels above zztop (mod_bdycod.F90:505-519) */
+  int32_t ichem, ichebdy;             /* tracer boundary: 0 flux dependent, 1 chib0/chib1 */
+  int32_t do_slice;                   /* allocate the mkslice outputs            */
+  int32_t icldmstrat;                 /* 1: mkslice finds theta at 700 hPa       */
+  int32_t km, lm;                     /* spectral-nudging wave numbers (lowpass_init,
+                                         mod_bdycod.F90:3852-3853); 0 when unused  */
+  int32_t reserved2;
+  double dtbdys, dtrad;               /* boundary / radiation period [s]         */
+  double rhmin, rhmax, tkemin;        /* Main/mod_params.F90:381-382, mod_pbl_interface.F90:50 */
 } moloch_b200_config;
 
 typedef struct moloch_b200_ctx moloch_b200_ctx;
@@ -71,8 +88,28 @@ enum moloch_b200_field {
   MB_CORU, MB_CORV, MB_BDYWTU, MB_BDYWTV, MB_BDYWTW,
   MB_TTEN, MB_UTEN, MB_VTEN, MB_QXTEN, MB_CHITEN,
   MB_S, MB_ZDIV2, MB_WX, MB_WZ, MB_P0, MB_TETAVF,
+  /* ---- ABI v2 ---- */
+  MB_TKE, MB_TKETEN, MB_TKEX,          /* ibltyp == 2: kz+1, kz+1, kz levels        */
+  /* v3dbound/v2dbound b0, b1 (Main/mod_atm_interface.F90:547-577); do_bdy     */
+  MB_DUB0, MB_DUB1, MB_DVB0, MB_DVB1, MB_XTB0, MB_XTB1, MB_XPAIB0, MB_XPAIB1, MB_XQB0, MB_XQB1,
+  MB_XLB0, MB_XLB1, MB_XIB0, MB_XIB1, MB_XPSB0, MB_XPSB1, MB_CHIB0, MB_CHIB1,
+  /* mkslice outputs (Main/mod_slice.F90:115-173) and its static input zq; do_slice */
+  MB_PF3D, MB_TH3D, MB_RHB3D, MB_WPX3D, MB_RHOX2D, MB_TP2D, MB_TH700, MB_ZETAF,
   MB_NFIELDS
 };
+
+/* tables of the lateral boundary (set once after create) */
+enum moloch_b200_table {
+  MB_TAB_HEFC = 0,  /* hefc(nspgx,kz), n fastest   Main/mod_bdycod.F90:520-545      */
+  MB_TAB_TNUDGE,    /* tnudge(kz)                  :553-560                         */
+  MB_TAB_CNUDGE,    /* cnudge(kz)                  :3892-3895                       */
+  MB_TAB_FCX,       /* fcx(nspgx), tracers         Main/chemlib/mod_che_bdyco.F90:101 */
+  MB_TAB_BVX,       /* bvx(jde1:jde2, 2*km)        Main/mod_bdycod.F90:3882-3886    */
+  MB_TAB_BVY,       /* bvy(ide1:ide2, 2*lm)        :3887-3891                       */
+  MB_NTABLES
+};
+/* ba%ibnd of the three staggerings (setup_boundaries, Main/mod_atm_interface.F90:384-532) */
+enum moloch_b200_ibnd { MB_IBND_CR = 0, MB_IBND_UD, MB_IBND_VD };
 
 /* 1-D profiles (k = 1..n) */
 enum moloch_b200_profile {
@@ -123,6 +160,11 @@ int moloch_b200_set_field(moloch_b200_ctx* ctx, int field, int n, const double* 
 int moloch_b200_get_field(moloch_b200_ctx* ctx, int field, int n, double* host,
                           int jlo, int jhi, int ilo, int ihi, int klo, int khi);
 int moloch_b200_set_profile(moloch_b200_ctx* ctx, int profile, const double* v, int n);
+int moloch_b200_set_table(moloch_b200_ctx* ctx, int table, const double* v, int n);
+/* integer(ik4) ibnd(jlo:jhi, ilo:ihi) of one bound_area; values <= 0 mean
+ * "not in the sponge" (the reference initialises ibnd to -1)                 */
+int moloch_b200_set_ibnd(moloch_b200_ctx* ctx, int which, const int32_t* ibnd, int jlo, int jhi, int ilo,
+                         int ihi);
 /* on: set_field/get_field only enqueue their transfer; the caller ends a batch
  * with moloch_b200_sync (host buffers must stay valid until then).           */
 int moloch_b200_set_async(moloch_b200_ctx* ctx, int on);
@@ -144,8 +186,27 @@ int moloch_b200_wafone(moloch_b200_ctx* ctx, int field, int n);  /* :838  wafone
 int moloch_b200_dynamical_core(moloch_b200_ctx* ctx);            /* :1085 */
 int moloch_b200_diagnostics(moloch_b200_ctx* ctx);               /* :348-354 p,rho,qsat,ps   */
 int moloch_b200_status_update(moloch_b200_ctx* ctx);             /* :1403 (tendencies on device) */
-/* nsteps x [reset_tendencies, dynamical_core, diagnostics, status_update]:
- * `moloch` with the host physics producing zero tendencies.                 */
+/* `boundary` (Main/mod_moloch.F90:448-529): bdyval MOLOCH branch
+ * (Main/mod_bdycod.F90:1618-1875) + chem_bdyval
+ * (Main/chemlib/mod_che_bdyco.F90:391-535), motopnudge (:4049-4081),
+ * morelax_external/_fraction (:3962-4031), morelax_chiten
+ * (mod_che_bdyco.F90:965-1026), mospectral_nudge (:3898-3960), uvstagtouvx,
+ * temp_to_tvirt, tetav.  The context keeps RegCM's xbctime: bdyval advances it
+ * by dtsec (:2653), bdyin resets it (moloch_b200_bdy_shift).                  */
+int moloch_b200_boundary(moloch_b200_ctx* ctx);
+int moloch_b200_bdyval(moloch_b200_ctx* ctx);                    /* bdyval only            */
+int moloch_b200_set_xbctime(moloch_b200_ctx* ctx, double xbctime);
+double moloch_b200_get_xbctime(moloch_b200_ctx* ctx);
+/* what bdyin does every dtbdys (Main/mod_bdycod.F90:1079-1423): b0 <- b1 for
+ * every boundary variable (a pointer swap on the device), xbctime = 0; the
+ * host then uploads the new b1 with moloch_b200_set_field.                    */
+int moloch_b200_bdy_shift(moloch_b200_ctx* ctx);
+/* mkslice, idynamic == 3 branch (Main/mod_slice.F90:115-173): pf3d, th3d,
+ * rhb3d, wpx3d, rhox2d, tp2d, th700 and the clipping of qx / trac             */
+int moloch_b200_mkslice(moloch_b200_ctx* ctx);
+/* nsteps x [reset_tendencies, dynamical_core, boundary (do_bdy), diagnostics,
+ * mkslice (do_slice), status_update]: `moloch` (Main/mod_moloch.F90:312-446)
+ * with the host physics producing zero tendencies.                           */
 int moloch_b200_step(moloch_b200_ctx* ctx, int nsteps);
 
 /* built-in per-kernel device timing (CUDA events on the launching stream)   */

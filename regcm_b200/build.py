@@ -13,8 +13,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmoloch_b200.so")
-SOURCES = ["kernels.cu", "kernels_waf.cu", "halo.cu", "capi.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "moloch_b200.h")]
+SOURCES = ["kernels.cu", "kernels_waf.cu", "kernels_bdy.cu", "halo.cu", "capi.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "geo.h"), os.path.join(CSRC, "bdy_cells.h"),
+           os.path.join(HERE, "..", "include", "moloch_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

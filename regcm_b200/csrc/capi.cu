@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <utility>
 #include "common.cuh"
 
 namespace mb {
@@ -16,7 +17,7 @@ static const char* k_names[KID_COUNT] = {
     "reset_tendencies", "tetavf_init", "sound_pre", "divdamp_filter", "wsolve", "uvupdate", "sfinish",
     "destagger", "waf_vertical", "waf_meridional", "waf_zonal", "curvature", "restagger", "tvirt_temp",
     "diag_prq", "diag_ps", "status_update", "halo_local", "halo_pack", "halo_unpack", "init_static",
-    "waf_horizontal", "box_copy"};
+    "waf_horizontal", "box_copy", "bdyval", "bdy_relax", "bdy_finish", "mkslice", "tke", "spectral_nudge"};
 const char* kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? k_names[kid] : "?"; }
 
 LaunchScope::LaunchScope(Ctx& c_, int kid_) : c(c_), kid(kid_) {
@@ -34,38 +35,11 @@ LaunchScope::~LaunchScope() {
   }
 }
 
-Geo geo_from_cfg(const moloch_b200_config& f) {
-  Geo g;
-  g.kz = f.kz;
-  g.jde1 = f.jde1; g.jde2 = f.jde2; g.ide1 = f.ide1; g.ide2 = f.ide2;
-  g.jce1 = f.jce1; g.jce2 = f.jce2; g.ice1 = f.ice1; g.ice2 = f.ice2;
-  g.bl = f.has_bdy_left != 0; g.br = f.has_bdy_right != 0; g.bb = f.has_bdy_bottom != 0; g.bt = f.has_bdy_top != 0;
-  g.gl = g.bl ? 0 : 1; g.gr = g.br ? 0 : 1; g.gb = g.bb ? 0 : 1; g.gt = g.bt ? 0 : 1;
-  // setup_model_indexes, Main/mod_atm_interface.F90:182-382
-  g.jdi1 = g.jde1 + (g.bl ? 1 : 0); g.jdii1 = g.jde1 + (g.bl ? 2 : 0);
-  g.jdi2 = g.jde2 - (g.br ? 1 : 0); g.jdii2 = g.jde2 - (g.br ? 2 : 0);
-  g.idi1 = g.ide1 + (g.bb ? 1 : 0); g.idii1 = g.ide1 + (g.bb ? 2 : 0);
-  g.idi2 = g.ide2 - (g.bt ? 1 : 0); g.idii2 = g.ide2 - (g.bt ? 2 : 0);
-  g.jci1 = g.jce1 + (g.bl ? 1 : 0); g.jci2 = g.jce2 - (g.br ? 1 : 0);
-  g.ici1 = g.ice1 + (g.bb ? 1 : 0); g.ici2 = g.ice2 - (g.bt ? 1 : 0);
-  // init_moloch, Main/mod_moloch.F90:280-293
-  const int jcross2 = f.bandflag ? f.jx : f.jx - 1, icross2 = f.crmflag ? f.iy : f.iy - 1;
-  g.jmin = 1; g.jmax = jcross2; g.imin = 1; g.imax = icross2;
-  if (f.bandflag) { g.jmin = 1 - 2; g.jmax = jcross2 + 2; }
-  if (f.crmflag) { g.jmin = 1 - 2; g.jmax = jcross2 + 2; g.imin = 1 - 2; g.imax = icross2 + 2; }
-  g.lrotllr = f.lrotllr; g.ipptls = f.ipptls; g.nqx = f.nqx; g.ntr = f.ntr;
-  g.j0 = g.jde1 - HJ; g.i0 = g.ide1 - HI;
-  int nj = (g.jde2 - g.jde1 + 1) + 2 * HJ;
-  nj = (nj + 3) / 4 * 4;
-  g.NJ = nj; g.NI = (g.ide2 - g.ide1 + 1) + 2 * HI;
-  g.plane = (long long)g.NJ * g.NI;
-  return g;
-}
-
 // number of wafone-advected fields, in the reference's order :786-807
 static int count_adv(const moloch_b200_config& f) {
   int n = 6;
   if (f.ipptls > 0) n += (f.nqx - f.iqfrst + 1 > 0) ? f.nqx - f.iqfrst + 1 : 0;
+  if (f.ibltyp == 2) n += 1;   // tkex :799-801
   return n + f.ntr;
 }
 
@@ -78,6 +52,20 @@ static void field_shape(const moloch_b200_config& f, int id, int& nk, int& nspec
     case MB_TRAC: case MB_CHITEN: nk = kz; nspec = f.ntr; break;
     case MB_PS: case MB_HX: case MB_HY: case MB_MSFX: case MB_MSFU: case MB_MSFV: case MB_CORU: case MB_CORV:
       nk = 1; break;
+    // ---- ABI v2: allocated only when the feature is configured -------------------
+    case MB_TKE: case MB_TKETEN: nk = (f.ibltyp == 2) ? kz + 1 : 0; break;
+    case MB_TKEX: nk = (f.ibltyp == 2) ? kz : 0; break;
+    case MB_DUB0: case MB_DUB1: case MB_DVB0: case MB_DVB1: case MB_XTB0: case MB_XTB1: case MB_XPAIB0:
+    case MB_XPAIB1: case MB_XQB0: case MB_XQB1:
+      nk = f.do_bdy ? kz : 0; break;
+    case MB_XLB0: case MB_XLB1: nk = (f.do_bdy && f.present_qc) ? kz : 0; break;
+    case MB_XIB0: case MB_XIB1: nk = (f.do_bdy && f.present_qi) ? kz : 0; break;
+    case MB_XPSB0: case MB_XPSB1: nk = f.do_bdy ? 1 : 0; break;
+    case MB_CHIB0: case MB_CHIB1:
+      nk = (f.do_bdy && f.ichem && f.ichebdy != 0 && f.ntr > 0) ? kz : 0; nspec = f.ntr > 0 ? f.ntr : 1; break;
+    case MB_PF3D: case MB_ZETAF: nk = f.do_slice ? kz + 1 : 0; break;
+    case MB_TH3D: case MB_RHB3D: case MB_WPX3D: nk = f.do_slice ? kz : 0; break;
+    case MB_RHOX2D: case MB_TP2D: case MB_TH700: nk = f.do_slice ? 1 : 0; break;
     default: nk = kz; break;
   }
 }
@@ -125,6 +113,20 @@ static int check_cfg(const moloch_b200_config& f) {
   if (!(f.dtsec > 0.0) || !(f.dx > 0.0) || !(f.mo_dzita > 0.0))
     return fail("moloch_b200_create: dtsec, dx, mo_dzita must be > 0");
   if (f.nranks < 1 || f.rank < 0 || f.rank >= f.nranks) return fail("moloch_b200_create: bad rank/nranks");
+  if (f.ibltyp == 2 && !(f.tkemin >= 0.0)) return fail("moloch_b200_create: ibltyp=2 needs tkemin >= 0");
+  if (f.do_bdy) {
+    if (!(f.dtbdys > 0.0)) return fail("moloch_b200_create: do_bdy needs dtbdys > 0");
+    if (f.nspgx < 0 || f.nspgx == 1 || f.nspgx == 2) return fail("moloch_b200_create: nspgx must be 0 or >= 3");
+    if (f.mo_top_nudge && (f.nztop < 0 || f.nztop > f.kz)) return fail("moloch_b200_create: nztop out of range");
+    if (f.mo_spectral_nudge) {
+      if (!(f.dtrad > 0.0) || f.km < 1 || f.lm < 1)
+        return fail("moloch_b200_create: mo_spectral_nudge needs dtrad > 0 and km, lm >= 1");
+      if (f.nranks > 1)
+        return fail("moloch_b200_create: mo_spectral_nudge on more than one rank is not supported yet "
+                    "(row_reduce/column_reduce, Main/mpplib/mod_mppparam.F90:20620-20664)");
+    }
+  }
+  if (f.do_slice && !(f.rhmax >= f.rhmin)) return fail("moloch_b200_create: do_slice needs rhmin <= rhmax");
   return 0;
 }
 
@@ -237,6 +239,7 @@ static int do_advection(Ctx& c) {
     if (halo_exchange_multi(c, sp, 2)) return 1;
   }
   if (k_destagger(c)) return 1;
+  if (c.cfg.ibltyp == 2 && k_tke_destagger(c)) return 1;          // :782-784
   if (do_wafone_range(c, 0, c.nadv_fields)) return 1;             // :786-807
   if (k_curvature(c, c.dtstepa)) return 1;
   {   // :1485-1486, one round
@@ -244,7 +247,9 @@ static int do_advection(Ctx& c) {
     const HaloSpec sp[2] = {{&iu, 1, HS_CROSS, 2, true, false, 0}, {&iv, 1, HS_CROSS, 2, false, true, 0}};
     if (halo_exchange_multi(c, sp, 2)) return 1;
   }
-  return k_restagger(c, true);
+  if (k_restagger(c, true)) return 1;
+  if (c.cfg.ibltyp == 2 && k_tke_restagger(c)) return 1;          // :832-834
+  return 0;
 }
 
 static int do_dynamical_core(Ctx& c) {
@@ -255,9 +260,53 @@ static int do_dynamical_core(Ctx& c) {
   return k_tvirt_temp(c);
 }
 
+static int do_reset_tendencies(Ctx& c) {
+  if (k_reset_tendencies(c)) return 1;
+  if (c.cfg.ibltyp == 2) {   // tketen :1071-1075
+    LaunchScope ls(c, KID_RESET);
+    MB_CUDA(cudaMemsetAsync(c.f[MB_TKETEN].p, 0, c.layout.size[MB_TKETEN], c.stream));
+  }
+  return 0;
+}
+
+// `boundary` (Main/mod_moloch.F90:448-529)
+static int do_boundary(Ctx& c) {
+  const int kz = c.g.kz;
+  if (k_bdyval(c, c.xbctime)) return 1;
+  c.xbctime = c.xbctime + c.cfg.dtsec;            // Main/mod_bdycod.F90:2653
+  if (k_bdy_relax(c, c.xbctime)) return 1;        // motopnudge + morelax: weights of the advanced xbctime
+  if (c.cfg.mo_spectral_nudge) {                  // :499-506
+    c.tspectral = c.tspectral + c.cfg.dtsec;
+    if ((int)fmod(c.tspectral, c.cfg.dtrad) == 0 && k_spectral_nudge(c, c.xbctime)) return 1;
+  }
+  {   // uvstagtouvx :1532-1533, one round
+    const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
+    const HaloSpec sp[2] = {{&iu, 1, HS_U, 2, true, false, 0}, {&iv, 1, HS_V, 2, false, true, 0}};
+    if (halo_exchange_multi(c, sp, 2)) return 1;
+  }
+  return k_bdy_finish(c);
+}
+
+static int require_bdy(Ctx& c) {
+  if (!c.cfg.do_bdy) return fail("lateral boundary not configured (moloch_b200_config.do_bdy)");
+  if (c.cfg.nspgx > 0) {
+    for (int q = 0; q < 3; ++q)
+      if (!c.ibnd_set[q]) return fail("boundary: ba_cr/ba_ud/ba_vd ibnd not set (moloch_b200_set_ibnd)");
+    if (c.tab_n[MB_TAB_HEFC] == 0) return fail("boundary: hefc not set (moloch_b200_set_table)");
+  }
+  if (c.cfg.mo_top_nudge && c.tab_n[MB_TAB_TNUDGE] == 0) return fail("boundary: tnudge not set");
+  if (c.cfg.ichem && c.cfg.ichebdy != 0 && c.cfg.ntr > 0 && c.cfg.nspgx > 0 && c.tab_n[MB_TAB_FCX] == 0)
+    return fail("boundary: fcx not set");
+  if (c.cfg.mo_spectral_nudge &&
+      (c.tab_n[MB_TAB_CNUDGE] == 0 || c.tab_n[MB_TAB_BVX] == 0 || c.tab_n[MB_TAB_BVY] == 0))
+    return fail("boundary: cnudge/bvx/bvy not set");
+  return 0;
+}
+
 static int do_status_update(Ctx& c) {
   const int kz = c.g.kz;
   if (k_status_update(c, c.cfg.dtsec)) return 1;
+  if (c.cfg.ibltyp == 2 && k_tke_update(c, c.cfg.dtsec)) return 1;   // :1419-1424
   if (halo_fence(c)) return 1;   // ux/vx ghosts of the previous round may still be read by a neighbour
   {
     const HaloItem iu = {c.f[MB_UX].p, kz}, iv = {c.f[MB_VX].p, kz};
@@ -310,6 +359,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   std::vector<Adv> adv = {{MB_TETAV, 0}, {MB_PAI, 0}, {MB_UX, 0}, {MB_VX, 0}, {MB_WX, 0}, {MB_QX, 0}};
   if (cfg->ipptls > 0)
     for (int n = cfg->iqfrst; n <= cfg->nqx; ++n) adv.push_back({MB_QX, n - 1});
+  if (cfg->ibltyp == 2) adv.push_back({MB_TKEX, 0});
   for (int n = 1; n <= cfg->ntr; ++n) adv.push_back({MB_TRAC, n - 1});
   c->nadv_fields = (int)adv.size();
   for (int id = 0; id < MB_NFIELDS; ++id) {
@@ -330,7 +380,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   cudaMemset(c->arena, 0, total);
   for (int id = 0; id < MB_NFIELDS; ++id) {
     if (id == MB_WZ || id == MB_P0) continue;
-    c->f[id].p = (c->f[id].nspec > 0) ? (double*)(c->arena + L.off[id]) : nullptr;
+    c->f[id].p = (c->f[id].nspec > 0 && L.size[id] > 0) ? (double*)(c->arena + L.off[id]) : nullptr;
   }
   c->ud = (double*)(c->arena + L.off[SL_UD]); c->vd = (double*)(c->arena + L.off[SL_VD]);
   c->zdiv2b = (double*)(c->arena + L.off[SL_ZB]);
@@ -349,6 +399,14 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   c->d_ptrtab = (double**)(c->arena + o_tab);
   std::vector<double*> tab;
   for (auto& a : adv) tab.push_back(c->f[a.fid].p + (size_t)a.spec * kz * g.plane);
+  for (int q = 0; q < 3; ++q) {
+    if (!(cfg->do_bdy && cfg->nspgx > 0)) break;
+    if (cudaMalloc(&c->ibnd[q], (size_t)g.plane * sizeof(int)) != cudaSuccess) {
+      cudaFree(c->arena);
+      delete c;
+      return fail("moloch_b200_create: cudaMalloc of the ibnd planes failed");
+    }
+  }
   cudaMemcpy(c->d_ptrtab, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice);
   c->h_ptrtab = tab;
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
@@ -374,6 +432,9 @@ int moloch_b200_destroy(moloch_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   halo_free(*c);
+  for (int q = 0; q < 3; ++q) if (c->ibnd[q]) cudaFree(c->ibnd[q]);
+  for (int q = 0; q < MB_NTABLES; ++q) if (c->tab[q]) cudaFree(c->tab[q]);
+  if (c->spec_work) cudaFree(c->spec_work);
   if (c->stage) cudaFree(c->stage);
   if (c->arena) cudaFree(c->arena);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -425,9 +486,10 @@ static int xfer_field(moloch_b200_ctx* c, int field, int n, double* host, int jl
   if (field < 0 || field >= MB_NFIELDS) return fail("set/get_field: unknown field id");
   if (!host) return fail("set/get_field: null host pointer");
   Ctx::Field& f = c->f[field];
-  if (!f.p) return fail("set/get_field: field not allocated (ntr == 0?)");
+  if (!f.p) return fail("set/get_field: field not allocated (ntr == 0, or ibltyp/do_bdy/do_slice not configured)");
   int spec = 0;
-  if (f.nspec > 1 || field == MB_QX || field == MB_TRAC || field == MB_QXTEN || field == MB_CHITEN) {
+  if (f.nspec > 1 || field == MB_QX || field == MB_TRAC || field == MB_QXTEN || field == MB_CHITEN ||
+      field == MB_CHIB0 || field == MB_CHIB1) {
     if (n < 1 || n > f.nspec) return fail("set/get_field: species index out of range");
     spec = n - 1;
   }
@@ -549,7 +611,7 @@ int moloch_b200_init(moloch_b200_ctx* c) {
   if (require_init(c)) return 1;                  \
   MB_CUDA(cudaSetDevice((c)->device));
 
-int moloch_b200_reset_tendencies(moloch_b200_ctx* c) { ENTRY(c) return k_reset_tendencies(*c); }
+int moloch_b200_reset_tendencies(moloch_b200_ctx* c) { ENTRY(c) return do_reset_tendencies(*c); }
 int moloch_b200_sound(moloch_b200_ctx* c) { ENTRY(c) return do_sound(*c); }
 int moloch_b200_advection(moloch_b200_ctx* c) { ENTRY(c) return do_advection(*c); }
 int moloch_b200_wafone(moloch_b200_ctx* c, int field, int n) {
@@ -568,15 +630,91 @@ int moloch_b200_wafone(moloch_b200_ctx* c, int field, int n) {
 int moloch_b200_dynamical_core(moloch_b200_ctx* c) { ENTRY(c) return do_dynamical_core(*c); }
 int moloch_b200_diagnostics(moloch_b200_ctx* c) { ENTRY(c) return k_diagnostics(*c); }
 int moloch_b200_status_update(moloch_b200_ctx* c) { ENTRY(c) return do_status_update(*c); }
+int moloch_b200_boundary(moloch_b200_ctx* c) {
+  ENTRY(c)
+  if (require_bdy(*c)) return 1;
+  return do_boundary(*c);
+}
+int moloch_b200_bdyval(moloch_b200_ctx* c) {
+  ENTRY(c)
+  if (require_bdy(*c)) return 1;
+  if (k_bdyval(*c, c->xbctime)) return 1;
+  c->xbctime = c->xbctime + c->cfg.dtsec;
+  return 0;
+}
+int moloch_b200_set_xbctime(moloch_b200_ctx* c, double t) {
+  if (!c) return fail("null context");
+  c->xbctime = t;
+  return 0;
+}
+double moloch_b200_get_xbctime(moloch_b200_ctx* c) { return c ? c->xbctime : 0.0; }
+int moloch_b200_bdy_shift(moloch_b200_ctx* c) {
+  if (!c) return fail("null context");
+  if (!c->cfg.do_bdy) return fail("lateral boundary not configured (moloch_b200_config.do_bdy)");
+  // b0 <- b1 (Main/mod_bdycod.F90:1109-1135): the buffers swap roles, the host refills b1
+  for (int id = MB_DUB0; id <= MB_CHIB0; id += 2) std::swap(c->f[id].p, c->f[id + 1].p);
+  c->xbctime = 0.0;                                // :1158
+  return 0;
+}
+int moloch_b200_mkslice(moloch_b200_ctx* c) {
+  ENTRY(c)
+  if (!c->cfg.do_slice) return fail("mkslice not configured (moloch_b200_config.do_slice)");
+  return k_mkslice(*c);
+}
 int moloch_b200_step(moloch_b200_ctx* c, int nsteps) {
   ENTRY(c)
+  if (c->cfg.do_bdy && require_bdy(*c)) return 1;
   for (int n = 0; n < nsteps; ++n) {
-    if (k_reset_tendencies(*c)) return 1;
+    if (do_reset_tendencies(*c)) return 1;
     if (do_dynamical_core(*c)) return 1;
+    if (c->cfg.do_bdy && do_boundary(*c)) return 1;          // :341-343
     if (k_diagnostics(*c)) return 1;
+    if (c->cfg.do_slice && k_mkslice(*c)) return 1;          // :356-358
     if (do_status_update(*c)) return 1;
   }
   return 0;
+}
+
+int moloch_b200_set_table(moloch_b200_ctx* c, int which, const double* v, int n) {
+  if (!c || !v) return fail("set_table: null argument");
+  if (which < 0 || which >= MB_NTABLES) return fail("set_table: unknown table id");
+  const Geo& g = c->g;
+  const moloch_b200_config& f = c->cfg;
+  int expect = 0;
+  switch (which) {
+    case MB_TAB_HEFC: expect = f.nspgx * g.kz; break;
+    case MB_TAB_TNUDGE: case MB_TAB_CNUDGE: expect = g.kz; break;
+    case MB_TAB_FCX: expect = f.nspgx; break;
+    case MB_TAB_BVX: expect = (g.jde2 - g.jde1 + 1) * 2 * f.km; break;
+    case MB_TAB_BVY: expect = (g.ide2 - g.ide1 + 1) * 2 * f.lm; break;
+  }
+  if (expect <= 0) return fail("set_table: this table is not used by the configuration");
+  if (n != expect) return fail("set_table: wrong length");
+  MB_CUDA(cudaSetDevice(c->device));
+  if (!c->tab[which]) MB_CUDA(cudaMalloc(&c->tab[which], (size_t)n * sizeof(double)));
+  MB_CUDA(cudaMemcpyAsync(c->tab[which], v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  MB_CUDA(cudaStreamSynchronize(c->stream));
+  c->tab_n[which] = n;
+  return 0;
+}
+
+int moloch_b200_set_ibnd(moloch_b200_ctx* c, int which, const int32_t* ibnd, int jlo, int jhi, int ilo, int ihi) {
+  if (!c || !ibnd) return fail("set_ibnd: null argument");
+  if (which < 0 || which > MB_IBND_VD) return fail("set_ibnd: unknown bound_area");
+  if (!c->ibnd[which]) return fail("set_ibnd: lateral boundary not configured (do_bdy, nspgx > 0)");
+  if (jhi < jlo || ihi < ilo) return fail("set_ibnd: empty bounds");
+  MB_CUDA(cudaSetDevice(c->device));
+  const size_t n = (size_t)(jhi - jlo + 1) * (size_t)(ihi - ilo + 1);
+  int* tmp = nullptr;
+  MB_CUDA(cudaMalloc(&tmp, n * sizeof(int)));
+  cudaError_t e = cudaMemcpyAsync(tmp, ibnd, n * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+  int rc = 0;
+  if (e != cudaSuccess) rc = fail(std::string("set_ibnd: ") + cudaGetErrorString(e));
+  if (!rc) rc = k_ibnd_fill(*c, c->ibnd[which], tmp, jlo, jhi, ilo, ihi);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(tmp);
+  if (!rc) c->ibnd_set[which] = true;
+  return rc;
 }
 
 int moloch_b200_profile_enable(moloch_b200_ctx* c, int on) {

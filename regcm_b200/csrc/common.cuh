@@ -14,60 +14,15 @@
 #include <string>
 #include <vector>
 #include "../../include/moloch_b200.h"
+#include "geo.h"
 
 namespace mb {
-
-constexpr int HJ = 4;
-constexpr int HI = 3;
-
-// physical constants: Share/mod_constants.F90:105-233 (non-RCEMIP branch)
-constexpr double egrav = 9.80665;
-constexpr double boltzk = 1.3806490e-23;
-constexpr double navgdr = 6.02214076e23;
-constexpr double amd = 28.96454;
-constexpr double amw = 18.01528;
-constexpr double rgasmol = navgdr * boltzk;
-constexpr double rgas = (rgasmol / amd) * 1000.0;
-constexpr double cpd = 3.5 * rgas;
-constexpr double cvd = 2.5 * rgas;
-constexpr double rdrcv = rgas / cvd;
-constexpr double cpovr = cpd / rgas;
-constexpr double govr = egrav / rgas;
-constexpr double govcp = egrav / cpd;
-constexpr double p00 = 1.0e5;
-constexpr double lrate = 0.00649;
-constexpr double tzero = 273.15;
-constexpr double ep1 = amd / amw - 1.0;
-constexpr double ep2 = amw / amd;
-constexpr double mathpi = 3.14159265358979323846;
-constexpr double degrad = mathpi / 180.0;
-constexpr double rearthrad = 1.0 / 6.371229e6;
-
-// Geometry of one rank, passed by value to every kernel.  Index ranges follow
-// setup_model_indexes (Main/mod_atm_interface.F90:182-382).
-struct Geo {
-  int NJ, NI, j0, i0;
-  long long plane;  // NJ*NI
-  int kz;
-  int jde1, jde2, ide1, ide2, jdi1, jdi2, idi1, idi2, jdii1, jdii2, idii1, idii2;
-  int jce1, jce2, ice1, ice2, jci1, jci2, ici1, ici2;
-  int gl, gr, gb, gt;  // 1 where a neighbour exists (ma%jbl1 ...)
-  int bl, br, bb, bt;  // ma%has_bdy*
-  int jmin, jmax, imin, imax;  // Main/mod_moloch.F90:280-293
-  int lrotllr, ipptls, nqx, ntr;
-};
-
-__host__ __device__ inline long long gidx(const Geo& g, int j, int i, int k) {
-  return (long long)(k - 1) * g.plane + (long long)(i - g.i0) * g.NJ + (j - g.j0);
-}
-__host__ __device__ inline long long gidx2(const Geo& g, int j, int i) {
-  return (long long)(i - g.i0) * g.NJ + (j - g.j0);
-}
 
 enum KernelId {
   KID_RESET = 0, KID_TETAVF, KID_SOUND_PRE, KID_DIVDAMP, KID_WSOLVE, KID_UVUPDATE, KID_SFINISH,
   KID_DESTAG, KID_WAF_Z, KID_WAF_Y, KID_WAF_X, KID_CURV, KID_RESTAG, KID_TVIRT, KID_DIAG, KID_PS,
-  KID_STATUS, KID_HALO, KID_HALO_PACK, KID_HALO_UNPACK, KID_INIT, KID_WAF_H, KID_BOX, KID_COUNT
+  KID_STATUS, KID_HALO, KID_HALO_PACK, KID_HALO_UNPACK, KID_INIT, KID_WAF_H, KID_BOX,
+  KID_BDYVAL, KID_BDYRELAX, KID_BDYFINISH, KID_MKSLICE, KID_TKE, KID_SPECTRAL, KID_COUNT
 };
 
 struct ProfEvent { cudaEvent_t a, b; int kid; };
@@ -139,6 +94,15 @@ struct Ctx {
   double prof_ms[KID_COUNT] = {0};
   long long prof_n_launch[KID_COUNT] = {0};
   long long launches = 0;
+  // lateral boundary: ba%ibnd planes, tables, RegCM's xbctime
+  int* ibnd[3] = {nullptr, nullptr, nullptr};
+  bool ibnd_set[3] = {false, false, false};
+  double* tab[MB_NTABLES] = {nullptr};
+  int tab_n[MB_NTABLES] = {0};
+  double xbctime = 0.0;     // Main/mpplib/mod_runparams.F90:102
+  double tspectral = 0.0;   // Main/mod_moloch.F90:452
+  double* spec_work = nullptr;   // mospectral_nudge scratch (sx, sxg, sy, syg, stale tails)
+  size_t spec_work_doubles = 0;
   // staging for set/get
   double* stage = nullptr;
   size_t stage_doubles = 0;
@@ -256,6 +220,16 @@ int k_diagnostics(Ctx& c);
 int k_status_update(Ctx& c, double dtinc);
 int k_init_static(Ctx& c);
 int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int nj, int ni, int nk, bool pack);
+// kernels_bdy.cu
+int k_bdyval(Ctx& c, double xbctime);
+int k_bdy_relax(Ctx& c, double xbctime);
+int k_bdy_finish(Ctx& c);
+int k_mkslice(Ctx& c);
+int k_tke_destagger(Ctx& c);
+int k_tke_restagger(Ctx& c);
+int k_tke_update(Ctx& c, double dtinc);
+int k_ibnd_fill(Ctx& c, int* dst, const int* src, int jlo, int jhi, int ilo, int ihi);
+int k_spectral_nudge(Ctx& c, double xbctime);
 // kernels_waf.cu
 int k_waf_ratios(Ctx& c);
 int k_waf_z2(Ctx& c, int first, int count, double dta);
@@ -277,7 +251,6 @@ int halo_comm_id(void* id128);
 int halo_p2p_export(Ctx& c, void* blob);
 int halo_p2p_connect(Ctx& c, const void* blobs, int nranks);
 size_t halo_p2p_blob_size();
-Geo geo_from_cfg(const moloch_b200_config& f);
 void halo_boxes(const moloch_b200_config& cfg, int stag, int nex, bool lr, bool bt,
                 int32_t send_box[4][4], int32_t recv_box[4][4]);
 

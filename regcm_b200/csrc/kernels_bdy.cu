@@ -1,0 +1,246 @@
+// kernels_bdy.cu -- lateral boundary (`boundary`, Main/mod_moloch.F90:448-529),
+// mkslice (Main/mod_slice.F90:115-173) and the TKE helpers of the UW-PBL path.
+//
+// All of this is HBM-bound pointwise work on boundary strips, the sponge ring
+// or whole fields; the per-cell arithmetic lives in bdy_cells.h (shared with
+// the host-compiled instantiation the CPU tests use), this file maps threads
+// onto cells: 32 consecutive j per warp row (coalesced 256-B rows), one level
+// per blockIdx.z.  Compiled -fmad=false like the rest of the library.
+#include <cstring>
+#include "bdy_cells.h"
+#include "common.cuh"
+
+namespace mb {
+
+constexpr int BX = 32, BY = 8;
+static inline dim3 grid3(int nj, int ni, int nk) {
+  return dim3((unsigned)((nj + BX - 1) / BX), (unsigned)((ni + BY - 1) / BY), (unsigned)nk);
+}
+
+// ---- bdyval ----------------------------------------------------------------------
+// boundary lines: x = position along the line, y = level, z = side
+__global__ void moloch_bdyval_we(BdyArgs a) {
+  const int i = a.g.ide1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > a.g.ide2) return;
+  bdyval_we_cell(a, (int)blockIdx.z, i, 1 + (int)blockIdx.y);
+}
+__global__ void moloch_bdyval_sn(BdyArgs a) {
+  const int j = a.g.jde1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > a.g.jde2) return;
+  bdyval_sn_cell(a, (int)blockIdx.z, j, 1 + (int)blockIdx.y);
+}
+__global__ void moloch_chem_bdyval_we(BdyArgs a) {
+  const int i = a.g.ice1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > a.g.ice2) return;
+  const int k = 1 + (int)(blockIdx.y % a.g.kz), n = (int)(blockIdx.y / a.g.kz);
+  chem_bdyval_we_cell(a, (int)blockIdx.z, i, k, n);
+}
+__global__ void moloch_chem_bdyval_sn(BdyArgs a) {
+  const int j = a.g.jce1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > a.g.jce2) return;
+  const int k = 1 + (int)(blockIdx.y % a.g.kz), n = (int)(blockIdx.y / a.g.kz);
+  chem_bdyval_sn_cell(a, (int)blockIdx.z, j, k, n);
+}
+
+static BdyArgs bdy_args(Ctx& c, double xbctime) {
+  BdyArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = c.g;
+  a.u = c.f[MB_U].p; a.v = c.f[MB_V].p; a.w = c.f[MB_W].p; a.t = c.f[MB_T].p; a.pai = c.f[MB_PAI].p;
+  a.qx = c.f[MB_QX].p; a.trac = c.f[MB_TRAC].p; a.ps = c.f[MB_PS].p; a.tke = c.f[MB_TKE].p;
+  a.ux = c.f[MB_UX].p; a.vx = c.f[MB_VX].p; a.tvirt = c.f[MB_TVIRT].p; a.tetav = c.f[MB_TETAV].p;
+  a.dub0 = c.f[MB_DUB0].p; a.dub1 = c.f[MB_DUB1].p; a.dvb0 = c.f[MB_DVB0].p; a.dvb1 = c.f[MB_DVB1].p;
+  a.xtb0 = c.f[MB_XTB0].p; a.xtb1 = c.f[MB_XTB1].p; a.xpaib0 = c.f[MB_XPAIB0].p; a.xpaib1 = c.f[MB_XPAIB1].p;
+  a.xqb0 = c.f[MB_XQB0].p; a.xqb1 = c.f[MB_XQB1].p; a.xlb0 = c.f[MB_XLB0].p; a.xlb1 = c.f[MB_XLB1].p;
+  a.xib0 = c.f[MB_XIB0].p; a.xib1 = c.f[MB_XIB1].p; a.xpsb0 = c.f[MB_XPSB0].p; a.xpsb1 = c.f[MB_XPSB1].p;
+  a.chib0 = c.f[MB_CHIB0].p; a.chib1 = c.f[MB_CHIB1].p;
+  a.ib_cr = c.ibnd[MB_IBND_CR]; a.ib_ud = c.ibnd[MB_IBND_UD]; a.ib_vd = c.ibnd[MB_IBND_VD];
+  a.hefc = c.tab[MB_TAB_HEFC]; a.tnudge = c.tab[MB_TAB_TNUDGE]; a.fcx = c.tab[MB_TAB_FCX];
+  // x1 = (xbctime + dt)*rtb, rtb = d_one/dtbdys (Main/mod_bdycod.F90:504, :1631)
+  const double rtb = 1.0 / c.cfg.dtbdys;
+  a.x1 = (xbctime + c.cfg.dtsec) * rtb; a.x0 = 1.0 - a.x1;
+  a.xc1 = (xbctime + c.cfg.dtsec) / c.cfg.dtbdys; a.xc0 = 1.0 - a.xc1;   // mod_che_bdyco.F90:507
+  a.dtsec = c.cfg.dtsec; a.tkemin = c.cfg.tkemin;
+  a.nspgx = c.cfg.nspgx; a.iqfrst = c.cfg.iqfrst; a.present_qc = c.cfg.present_qc; a.present_qi = c.cfg.present_qi;
+  a.tke_on = c.cfg.ibltyp == 2; a.nztop = c.cfg.nztop; a.top_nudge = c.cfg.mo_top_nudge;
+  a.ichem = c.cfg.ichem && c.cfg.ntr > 0; a.ichebdy = c.cfg.ichebdy;
+  return a;
+}
+
+// bdyval (MOLOCH branch) with the time weights of `xbctime`; the caller
+// advances xbctime afterwards (:2653)
+int k_bdyval(Ctx& c, double xbctime) {
+  const Geo& g = c.g;
+  const BdyArgs a = bdy_args(c, xbctime);
+  const int kz = g.kz;
+  if (g.bl || g.br) {
+    LaunchScope ls(c, KID_BDYVAL);
+    const int n = g.ide2 - g.ide1 + 1;
+    moloch_bdyval_we<<<dim3((unsigned)((n + 127) / 128), (unsigned)kz, 2), 128, 0, c.stream>>>(a);
+    MB_CUDA(cudaGetLastError());
+  }
+  if (g.bb || g.bt) {
+    LaunchScope ls(c, KID_BDYVAL);
+    const int n = g.jde2 - g.jde1 + 1;
+    moloch_bdyval_sn<<<dim3((unsigned)((n + 127) / 128), (unsigned)kz, 2), 128, 0, c.stream>>>(a);
+    MB_CUDA(cudaGetLastError());
+  }
+  if (a.ichem) {   // chem_bdyval_uncoupled reads the u, v the four sides have just set
+    if (g.bl || g.br) {
+      LaunchScope ls(c, KID_BDYVAL);
+      const int n = g.ice2 - g.ice1 + 1;
+      moloch_chem_bdyval_we<<<dim3((unsigned)((n + 127) / 128), (unsigned)(kz * g.ntr), 2), 128, 0, c.stream>>>(a);
+      MB_CUDA(cudaGetLastError());
+    }
+    if (g.bb || g.bt) {
+      LaunchScope ls(c, KID_BDYVAL);
+      const int n = g.jce2 - g.jce1 + 1;
+      moloch_chem_bdyval_sn<<<dim3((unsigned)((n + 127) / 128), (unsigned)(kz * g.ntr), 2), 128, 0, c.stream>>>(a);
+      MB_CUDA(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+// ---- motopnudge + morelax of all variables -----------------------------------------
+__global__ void moloch_bdy_relax(BdyArgs a) {
+  const int j = a.g.jde1 + blockIdx.x * BX + threadIdx.x;
+  const int i = a.g.ide1 + blockIdx.y * BY + threadIdx.y;
+  if (j > a.g.jde2 || i > a.g.ide2) return;
+  bdy_relax_cell(a, j, i, 1 + (int)blockIdx.z);
+}
+int k_bdy_relax(Ctx& c, double xbctime) {
+  const Geo& g = c.g;
+  if (!(c.cfg.mo_top_nudge || c.cfg.nspgx > 0)) return 0;
+  const BdyArgs a = bdy_args(c, xbctime);
+  LaunchScope ls(c, KID_BDYRELAX);
+  moloch_bdy_relax<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(a);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- uvstagtouvx + temp_to_tvirt + tetav ---------------------------------------------
+__global__ void moloch_bdy_finish(BdyArgs a) {
+  const int j = a.g.jce1 + blockIdx.x * BX + threadIdx.x;
+  const int i = a.g.ice1 + blockIdx.y * BY + threadIdx.y;
+  if (j > a.g.jce2 || i > a.g.ice2) return;
+  bdy_finish_cell(a, j, i, 1 + (int)blockIdx.z);
+}
+int k_bdy_finish(Ctx& c) {
+  const Geo& g = c.g;
+  const BdyArgs a = bdy_args(c, 0.0);
+  LaunchScope ls(c, KID_BDYFINISH);
+  moloch_bdy_finish<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(a);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---- mkslice -----------------------------------------------------------------------------
+__global__ void moloch_mkslice(SliceArgs a) {
+  const int j = a.g.jce1 + blockIdx.x * BX + threadIdx.x;
+  const int i = a.g.ice1 + blockIdx.y * BY + threadIdx.y;
+  if (j > a.g.jce2 || i > a.g.ice2) return;
+  mkslice_cell(a, j, i, 1 + (int)blockIdx.z);
+}
+__global__ void moloch_mkslice_col(SliceArgs a) {
+  const int j = a.g.jce1 + blockIdx.x * BX + threadIdx.x;
+  const int i = a.g.ice1 + blockIdx.y * BY + threadIdx.y;
+  if (j > a.g.jce2 || i > a.g.ice2) return;
+  mkslice_col(a, j, i);
+}
+int k_mkslice(Ctx& c) {
+  const Geo& g = c.g;
+  SliceArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = g;
+  a.pai = c.f[MB_PAI].p; a.t = c.f[MB_T].p; a.p = c.f[MB_P].p; a.rho = c.f[MB_RHO].p; a.qsat = c.f[MB_QSAT].p;
+  a.w = c.f[MB_W].p; a.ps = c.f[MB_PS].p; a.zq = c.f[MB_ZETAF].p; a.qx = c.f[MB_QX].p; a.trac = c.f[MB_TRAC].p;
+  a.pf3d = c.f[MB_PF3D].p; a.th3d = c.f[MB_TH3D].p; a.rhb3d = c.f[MB_RHB3D].p; a.wpx3d = c.f[MB_WPX3D].p;
+  a.rhox2d = c.f[MB_RHOX2D].p; a.tp2d = c.f[MB_TP2D].p; a.th700 = c.f[MB_TH700].p;
+  a.rhmin = c.cfg.rhmin; a.rhmax = c.cfg.rhmax;
+  a.ichem = c.cfg.ichem && c.cfg.ntr > 0; a.icldmstrat = c.cfg.icldmstrat;
+  {
+    LaunchScope ls(c, KID_MKSLICE);
+    moloch_mkslice<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(a);
+    MB_CUDA(cudaGetLastError());
+  }
+  {
+    LaunchScope ls(c, KID_MKSLICE);
+    moloch_mkslice_col<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, 1), dim3(BX, BY), 0, c.stream>>>(a);
+    MB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ---- TKE helpers (ibltyp == 2) ---------------------------------------------------------------
+__global__ void moloch_zstagtoh(Geo g, const double* __restrict__ fl, double* __restrict__ hl) {
+  const int j = g.jce1 + blockIdx.x * BX + threadIdx.x;
+  const int i = g.ice1 + blockIdx.y * BY + threadIdx.y;
+  if (j > g.jce2 || i > g.ice2) return;
+  zstagtoh_cell(g, fl, hl, j, i, 1 + (int)blockIdx.z);
+}
+__global__ void moloch_htozstag(Geo g, const double* __restrict__ hl, double* __restrict__ fl) {
+  const int j = g.jce1 + blockIdx.x * BX + threadIdx.x;
+  const int i = g.ice1 + blockIdx.y * BY + threadIdx.y;
+  if (j > g.jce2 || i > g.ice2) return;
+  htozstag_cell(g, hl, fl, j, i, 2 + (int)blockIdx.z);
+}
+__global__ void moloch_tke_update(Geo g, double* __restrict__ tke, const double* __restrict__ tketen, double dtinc,
+                                  double tkemin) {
+  const int j = g.jci1 + blockIdx.x * BX + threadIdx.x;
+  const int i = g.ici1 + blockIdx.y * BY + threadIdx.y;
+  if (j > g.jci2 || i > g.ici2) return;
+  tke_update_cell(g, tke, tketen, dtinc, tkemin, j, i, 1 + (int)blockIdx.z);
+}
+int k_tke_destagger(Ctx& c) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_TKE);
+  moloch_zstagtoh<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_TKE].p, c.f[MB_TKEX].p);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+int k_tke_restagger(Ctx& c) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_TKE);
+  moloch_htozstag<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz - 1), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_TKEX].p, c.f[MB_TKE].p);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+int k_tke_update(Ctx& c, double dtinc) {
+  const Geo& g = c.g;
+  LaunchScope ls(c, KID_TKE);
+  moloch_tke_update<<<grid3(g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, g.kz + 1), dim3(BX, BY), 0, c.stream>>>(
+      g, c.f[MB_TKE].p, c.f[MB_TKETEN].p, dtinc, c.cfg.tkemin);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ibnd upload: int32 host box -> padded device plane (cells outside the box stay -1)
+__global__ void moloch_ibnd_fill(Geo g, int* __restrict__ dst, const int* __restrict__ src, int jlo, int jhi,
+                                 int ilo, int ihi) {
+  const long long n = g.plane;
+  for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < n;
+       id += (long long)gridDim.x * blockDim.x) {
+    const int j = g.j0 + (int)(id % g.NJ), i = g.i0 + (int)(id / g.NJ);
+    int v = -1;
+    if (j >= jlo && j <= jhi && i >= ilo && i <= ihi) v = src[(long long)(i - ilo) * (jhi - jlo + 1) + (j - jlo)];
+    dst[id] = v;
+  }
+}
+int k_ibnd_fill(Ctx& c, int* dst, const int* src, int jlo, int jhi, int ilo, int ihi) {
+  LaunchScope ls(c, KID_INIT);
+  moloch_ibnd_fill<<<148, 256, 0, c.stream>>>(c.g, dst, src, jlo, jhi, ilo, ihi);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// mospectral_nudge: see kernels_spectral below (single rank only in this version)
+int k_spectral_nudge(Ctx& c, double xbctime) {
+  (void)xbctime;
+  (void)c;
+  return fail("mospectral_nudge: not implemented yet");
+}
+
+}  // namespace mb

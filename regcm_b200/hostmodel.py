@@ -31,6 +31,21 @@ ALLOC = {
     "qxten": ("cross", 0, 0, "kz"), "chiten": ("cross", 0, 0, "kz"),
     "s": ("cross", 0, 0, "kzp1"), "zdiv2": ("cross", 1, 1, "kz"), "wx": ("cross", 1, 1, "kz"),
     "wz": ("cross", 2, 2, "kz"), "p0": ("cross", 2, 2, "kz"), "tetavf": ("cross", 0, 0, "kz"),
+    # UW-PBL TKE (Main/mod_atm_interface.F90:609-612, Main/mod_moloch.F90:184)
+    "tke": ("cross", 0, 0, "kzp1"), "tketen": ("cross", 0, 0, "kzp1"), "tkex": ("cross", 0, 0, "kz"),
+    # v3dbound/v2dbound b0, b1 (Main/mod_atm_interface.F90:547-577)
+    "dub0": ("u", 2, 2, "kz"), "dub1": ("u", 2, 2, "kz"), "dvb0": ("v", 2, 2, "kz"), "dvb1": ("v", 2, 2, "kz"),
+    "xtb0": ("cross", 1, 1, "kz"), "xtb1": ("cross", 1, 1, "kz"),
+    "xpaib0": ("cross", 1, 1, "kz"), "xpaib1": ("cross", 1, 1, "kz"),
+    "xqb0": ("cross", 1, 1, "kz"), "xqb1": ("cross", 1, 1, "kz"),
+    "xlb0": ("cross", 1, 1, "kz"), "xlb1": ("cross", 1, 1, "kz"),
+    "xib0": ("cross", 1, 1, "kz"), "xib1": ("cross", 1, 1, "kz"),
+    "xpsb0": ("cross", 1, 1, 1), "xpsb1": ("cross", 1, 1, 1),
+    "chib0": ("cross", 1, 1, "kz"), "chib1": ("cross", 1, 1, "kz"),
+    # mkslice outputs (Main/mod_atm_interface.F90:599,964-1012) and zetaf (:602)
+    "pf3d": ("cross", 0, 0, "kzp1"), "th3d": ("cross", 0, 0, "kz"), "rhb3d": ("cross", 0, 0, "kz"),
+    "wpx3d": ("cross", 0, 0, "kz"), "rhox2d": ("cross", 0, 0, 1), "tp2d": ("cross", 0, 0, 1),
+    "th700": ("cross", 0, 0, 1), "zetaf": ("cross", 0, 0, "kzp1"),
 }
 
 

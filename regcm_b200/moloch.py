@@ -30,11 +30,19 @@ LIB_PATH = os.environ.get("MOLOCH_B200_LIB") or os.path.join(_HERE, "libmoloch_b
 FIELDS = ["u", "v", "w", "pai", "tetav", "t", "qx", "trac", "ux", "vx", "tvirt", "p", "rho", "qsat", "ps",
           "zeta", "fmz", "fmzf", "rfmzu", "rfmzv", "hx", "hy", "msfx", "msfu", "msfv", "coru", "corv",
           "bdywtu", "bdywtv", "bdywtw", "tten", "uten", "vten", "qxten", "chiten", "s", "zdiv2", "wx", "wz",
-          "p0", "tetavf"]
+          "p0", "tetavf",
+          # ABI v2: TKE, boundary buffers (b0/b1), mkslice outputs
+          "tke", "tketen", "tkex",
+          "dub0", "dub1", "dvb0", "dvb1", "xtb0", "xtb1", "xpaib0", "xpaib1", "xqb0", "xqb1",
+          "xlb0", "xlb1", "xib0", "xib1", "xpsb0", "xpsb1", "chib0", "chib1",
+          "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "zetaf"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 PROFILES = ["gzitak", "gzitakh", "ffilt", "xkdamp", "xknu", "rlat"]
 PROFILE_ID = {n: i for i, n in enumerate(PROFILES)}
-SPECIES = {"qx", "trac", "qxten", "chiten"}
+TABLES = ["hefc", "tnudge", "cnudge", "fcx", "bvx", "bvy"]
+TABLE_ID = {n: i for i, n in enumerate(TABLES)}
+IBND_ID = {"cr": 0, "ud": 1, "vd": 2}
+SPECIES = {"qx", "trac", "qxten", "chiten", "chib0", "chib1"}
 
 # every symbol include/moloch_b200.h declares
 ABI_SYMBOLS = [
@@ -46,6 +54,8 @@ ABI_SYMBOLS = [
     "moloch_b200_diagnostics", "moloch_b200_status_update", "moloch_b200_step", "moloch_b200_profile_enable",
     "moloch_b200_profile_read", "moloch_b200_launch_count", "moloch_b200_device_bytes",
     "moloch_b200_halo_plan", "moloch_b200_p2p_blob_size", "moloch_b200_p2p_export", "moloch_b200_p2p_connect", "moloch_b200_set_async",
+    "moloch_b200_set_table", "moloch_b200_set_ibnd", "moloch_b200_boundary", "moloch_b200_bdyval",
+    "moloch_b200_set_xbctime", "moloch_b200_get_xbctime", "moloch_b200_bdy_shift", "moloch_b200_mkslice",
 ]
 
 
@@ -54,8 +64,11 @@ class Config(C.Structure):
         "jx", "iy", "kz", "nqx", "ntr", "iqfrst", "jde1", "jde2", "ide1", "ide2", "jce1", "jce2", "ice1",
         "ice2", "has_bdy_left", "has_bdy_right", "has_bdy_bottom", "has_bdy_top", "bandflag", "crmflag",
         "nbr_left", "nbr_right", "nbr_bottom", "nbr_top", "rank", "nranks", "mo_nadv", "mo_nsound",
-        "mo_divdamp", "mo_divfilter", "lrotllr", "ipptls", "device", "reserved")] + [
-        (n, C.c_double) for n in ("dtsec", "dx", "mo_dzita")]
+        "mo_divdamp", "mo_divfilter", "lrotllr", "ipptls", "device", "ibltyp")] + [
+        (n, C.c_double) for n in ("dtsec", "dx", "mo_dzita")] + [(n, C.c_int32) for n in (
+        "do_bdy", "nspgx", "present_qc", "present_qi", "mo_top_nudge", "mo_spectral_nudge", "nztop", "ichem",
+        "ichebdy", "do_slice", "icldmstrat", "km", "lm", "reserved2")] + [
+        (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin")]
 
 
 class MolochError(RuntimeError):
@@ -92,7 +105,13 @@ def load_library():
     lib.moloch_b200_set_profile.argtypes = [ctx, C.c_int, C.c_void_p, C.c_int]
     lib.moloch_b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     lib.moloch_b200_host_free.argtypes = [C.c_void_p]
-    for f in ("init", "reset_tendencies", "sound", "advection", "dynamical_core", "diagnostics", "status_update"):
+    lib.moloch_b200_set_table.argtypes = [ctx, C.c_int, C.c_void_p, C.c_int]
+    lib.moloch_b200_set_ibnd.argtypes = [ctx, C.c_int, C.c_void_p] + [C.c_int] * 4
+    lib.moloch_b200_set_xbctime.argtypes = [ctx, C.c_double]
+    lib.moloch_b200_get_xbctime.argtypes = [ctx]
+    lib.moloch_b200_get_xbctime.restype = C.c_double
+    for f in ("init", "reset_tendencies", "sound", "advection", "dynamical_core", "diagnostics", "status_update",
+              "boundary", "bdyval", "bdy_shift", "mkslice"):
         getattr(lib, "moloch_b200_" + f).argtypes = [ctx]
     lib.moloch_b200_wafone.argtypes = [ctx, C.c_int, C.c_int]
     lib.moloch_b200_step.argtypes = [ctx, C.c_int]
@@ -108,11 +127,13 @@ def load_library():
     return lib
 
 
-def make_config(wl, g: Geom, device: int = -1, mo_dzita: float | None = None) -> Config:
-    """moloch_b200_config from the workload (namelist values) and the rank's
-    geometry (set_nproc / setup_model_indexes results)."""
+def make_config(wl, g: Geom, device: int = -1, mo_dzita: float | None = None, bdy: dict | None = None) -> Config:
+    """moloch_b200_config from the workload (namelist values), the rank's
+    geometry (set_nproc / setup_model_indexes results) and, for a run with
+    lateral boundaries, the results of setup_bdycon (`bdy`: nztop, km, lm)."""
     if mo_dzita is None:
         mo_dzita = wl.mo_ztop / float(wl.kz)   # zita(kz), Main/mod_params.F90:2461-2463
+    bdy = bdy or {}
     return Config(jx=wl.jx, iy=wl.iy, kz=wl.kz, nqx=wl.nqx, ntr=wl.ntr, iqfrst=2,
                   jde1=g.jde1, jde2=g.jde2, ide1=g.ide1, ide2=g.ide2, jce1=g.jce1, jce2=g.jce2, ice1=g.ice1,
                   ice2=g.ice2, has_bdy_left=int(g.bl), has_bdy_right=int(g.br), has_bdy_bottom=int(g.bb),
@@ -120,7 +141,13 @@ def make_config(wl, g: Geom, device: int = -1, mo_dzita: float | None = None) ->
                   nbr_right=g.right, nbr_bottom=g.bottom, nbr_top=g.top, rank=g.rank, nranks=g.px * g.py,
                   mo_nadv=wl.mo_nadv, mo_nsound=wl.mo_nsound, mo_divdamp=wl.mo_divdamp,
                   mo_divfilter=wl.mo_divfilter, lrotllr=wl.lrotllr, ipptls=wl.ipptls, device=device,
-                  reserved=0, dtsec=wl.dt, dx=wl.dx, mo_dzita=mo_dzita)
+                  ibltyp=wl.ibltyp, dtsec=wl.dt, dx=wl.dx, mo_dzita=mo_dzita,
+                  do_bdy=wl.do_bdy, nspgx=wl.nspgx if wl.do_bdy else 0, present_qc=wl.present_qc,
+                  present_qi=wl.present_qi, mo_top_nudge=wl.mo_top_nudge if wl.do_bdy else 0,
+                  mo_spectral_nudge=wl.mo_spectral_nudge if wl.do_bdy else 0, nztop=int(bdy.get("nztop", 0)),
+                  ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, do_slice=wl.do_slice, icldmstrat=wl.icldmstrat,
+                  km=int(bdy.get("km", 0)), lm=int(bdy.get("lm", 0)), reserved2=0, dtbdys=wl.dtbdys,
+                  dtrad=wl.dtrad, rhmin=wl.rhmin, rhmax=wl.rhmax, tkemin=wl.tkemin)
 
 
 def halo_plan(cfg: Config, stag: int, nex: int, lr: bool, bt: bool):
@@ -137,7 +164,7 @@ class MolochB200:
     """One rank's MOLOCH dycore on one B200 (mirror of `mod_moloch`)."""
 
     def __init__(self, wl, rank: int = 0, nranks: int = 1, px: int | None = None, py: int | None = None,
-                 device: int = -1):
+                 device: int = -1, bdy: dict | None = None):
         self.lib = load_library()
         self.wl = wl
         if px is None or py is None:
@@ -145,7 +172,13 @@ class MolochB200:
         if px * py != nranks:
             raise ValueError("px*py != nranks")
         self.g = make_geom(wl.jx, wl.iy, wl.kz, wl.i_band, wl.i_crm, px, py, rank)
-        self.cfg = make_config(wl, self.g, device)
+        # setup_bdycon results (host side, Main/mod_bdycod.F90:478-568): needed before
+        # allocation because nztop/km/lm are part of the configuration
+        if wl.do_bdy and bdy is None:
+            from . import synthetic as S
+            bdy = S.bdycon_setup(wl)
+        self.bdy = bdy
+        self.cfg = make_config(wl, self.g, device, bdy=bdy)
         self.ctx = C.c_void_p()
         self._pinned = []
 
@@ -198,7 +231,49 @@ class MolochB200:
         for name, v in profiles.items():
             self.set_profile(name, v)
         self._chk(self.lib.moloch_b200_init(self.ctx))
+        if self.wl.do_bdy:
+            self.init_boundary()
         return self
+
+    def init_boundary(self):
+        """Hand the results of setup_bdycon / setup_boundaries / lowpass_init to
+        the device (Main/mod_bdycod.F90:478-568, 3844-3896;
+        Main/mod_atm_interface.F90:384-532)."""
+        b, g, wl = self.bdy, self.g, self.wl
+        if wl.nspgx > 0:
+            self.set_table("hefc", b["hefc"])
+            for which, ib in b["ibnd"].items():
+                self.set_ibnd(which, ib)
+            if wl.ntr > 0 and wl.ichebdy != 0:
+                self.set_table("fcx", b["fcx"])
+        if wl.mo_top_nudge:
+            self.set_table("tnudge", b["tnudge"])
+        if wl.mo_spectral_nudge:
+            self.set_table("cnudge", b["cnudge"])
+            self.set_table("bvx", np.ascontiguousarray(b["bvx"][:, g.jde1 - 1:g.jde2]))
+            self.set_table("bvy", np.ascontiguousarray(b["bvy"][:, g.ide1 - 1:g.ide2]))
+
+    def set_table(self, name: str, v):
+        a = np.ascontiguousarray(v, dtype=np.float64)
+        self._chk(self.lib.moloch_b200_set_table(self.ctx, TABLE_ID[name], a.ctypes.data, a.size))
+
+    def set_ibnd(self, which: str, glob: np.ndarray):
+        """ba_cr/ba_ud/ba_vd %ibnd: cut the rank's (jde1:jde2, ide1:ide2) box out of the global plane."""
+        g = self.g
+        a = np.ascontiguousarray(np.asarray(glob)[g.ide1 - 1:g.ide2, g.jde1 - 1:g.jde2], dtype=np.int32)
+        self._chk(self.lib.moloch_b200_set_ibnd(self.ctx, IBND_ID[which], a.ctypes.data, g.jde1, g.jde2, g.ide1, g.ide2))
+
+    def load_boundary(self, B: dict):
+        """Upload the ICBC b0/b1 buffers (global arrays keyed dub0, dub1, ...)."""
+        for name, arr in B.items():
+            self.set_global(name, arr)
+
+    def boundary(self): self._chk(self.lib.moloch_b200_boundary(self.ctx))
+    def bdyval(self): self._chk(self.lib.moloch_b200_bdyval(self.ctx))
+    def bdy_shift(self): self._chk(self.lib.moloch_b200_bdy_shift(self.ctx))
+    def mkslice(self): self._chk(self.lib.moloch_b200_mkslice(self.ctx))
+    def set_xbctime(self, t: float): self._chk(self.lib.moloch_b200_set_xbctime(self.ctx, float(t)))
+    def get_xbctime(self) -> float: return float(self.lib.moloch_b200_get_xbctime(self.ctx))
 
     def moloch(self, nsteps: int = 1):
         """moloch (:312) with the host physics returning zero tendencies."""
@@ -274,7 +349,7 @@ class MolochB200:
         shp = (self.wl.iy, self.wl.jx) if nk == 1 else (nk, self.wl.iy, self.wl.jx)
         if name in ("qx", "qxten"):
             shp = (self.wl.nqx,) + shp
-        if name in ("trac", "chiten"):
+        if name in ("trac", "chiten", "chib0", "chib1"):
             shp = (self.wl.ntr,) + shp
         return shp
 

@@ -338,6 +338,48 @@ def make_tke(wl: Workload, zetaf: np.ndarray) -> np.ndarray:
     return wl.tkemin + 0.4 * np.exp(-np.maximum(zetaf, 0.0) / 800.0) * (1.0 + 0.3 * noise(shp, wl.seed, 21))
 
 
+def bdycon_setup(wl: Workload, zeta: np.ndarray | None = None) -> dict:
+    """Host-side set-up of the lateral boundary: setup_bdycon, idynamic == 3
+    branch (Main/mod_bdycod.F90:478-568), lowpass_init (:3844-3896) and the
+    three ba%ibnd planes of setup_boundaries (Main/mod_atm_interface.F90:384-532).
+    NumPy stand-in for the Fortran host code; arrays are global.  `zeta`: the
+    (kz, iy, jx) level heights (computed from the workload's terrain if absent)."""
+    jx, iy, kz = wl.jx, wl.iy, wl.kz
+    perj = wl.i_band == 1 or wl.i_crm == 1
+    peri = wl.i_crm == 1
+    njc, nic = (jx if perj else jx - 1), (iy if peri else iy - 1)
+    if zeta is None:
+        J, I = np.meshgrid(np.arange(1, jx + 1, dtype=np.float64), np.arange(1, iy + 1, dtype=np.float64))
+        ht = _height(wl, J, I) * egrav
+        zeta = md_zeta(model_zitah(kz, wl.mo_ztop)[:, None, None], ht[None], wl.mo_ztop, wl.mo_h, wl.mo_a0)
+    T = {"rtb": 1.0 / wl.dtbdys, "nztop": 0, "km": 0, "lm": 0}
+    zztop = 18000.0
+    gmeanz = np.zeros(kz)
+    if wl.mo_top_nudge or wl.mo_spectral_nudge:
+        gmeanz = zeta[:, :nic, :njc].reshape(kz, -1).sum(axis=1) / float(njc * nic)
+        T["nztop"] = int((gmeanz > zztop).sum())
+    T["gmeanz"] = gmeanz
+    T["hefc"] = hefc_table(wl) if wl.nspgx > 0 else None
+    T["fcx"] = chem_fcx(wl) if wl.nspgx > 0 else None
+    k = np.arange(1, kz + 1)
+    T["tnudge"] = np.where(k <= T["nztop"], np.sin(0.5 * mathpi * (gmeanz - zztop) / (wl.mo_h - zztop)) ** 2, 0.0) \
+        if wl.mo_top_nudge else np.zeros(kz)
+    if wl.mo_spectral_nudge:
+        km = max(int(np.rint((njc * wl.ds_km) / 1500.0)), 1)
+        lm = max(int(np.rint((nic * wl.ds_km) / 750.0)), 1)
+        dx, dy = mathpi / float(njc - 1), mathpi / float(nic - 1)
+        kk = np.arange(1, 2 * km + 1, dtype=np.float64)[:, None]
+        ll = np.arange(1, 2 * lm + 1, dtype=np.float64)[:, None]
+        jj = np.arange(1, jx + 1)[None, :]
+        ii = np.arange(1, iy + 1)[None, :]
+        T["km"], T["lm"] = km, lm
+        T["bvx"] = np.sqrt(2.0 / float(jx - 1) * np.exp(-(kk / km) ** 2)) * np.sin((kk * (jj - 2)) * dx)
+        T["bvy"] = np.sqrt(2.0 / float(iy - 1) * np.exp(-(ll / lm) ** 2)) * np.sin((ll * (ii - 2)) * dy)
+        T["cnudge"] = (wl.dtrad * T["rtb"]) * np.minimum((gmeanz / wl.mo_h) ** 2, 1.0)
+    T["ibnd"] = {"cr": _ibnd(wl, False, False), "ud": _ibnd(wl, True, False), "vd": _ibnd(wl, False, True)}
+    return T
+
+
 def chem_fcx(wl: Workload) -> np.ndarray:
     """Tracer relaxation weights fcx(1:nspgx) (Main/chemlib/mod_che_bdyco.F90:101): linear ramp."""
     n = np.arange(1, wl.nspgx + 1, dtype=np.float64)

@@ -27,15 +27,19 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(M.LIB_PATH)
     for s in declared:
         assert hasattr(lib, s), s
-    assert M.load_library().moloch_b200_abi_version() == 1
+    assert M.load_library().moloch_b200_abi_version() == 2
 
 
 def test_enums_match_header():
     hdr = open(os.path.join(ROOT, "include", "moloch_b200.h")).read()
-    body = re.search(r"enum moloch_b200_field \{(.*?)\};", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", re.search(r"enum moloch_b200_field \{(.*?)\};", hdr, re.S).group(1), flags=re.S)
     names = [n.strip().split("=")[0].strip() for n in body.replace("\n", " ").split(",") if n.strip()]
     names = [n for n in names if n != "MB_NFIELDS"]
     assert [n[3:].lower() for n in names] == M.FIELDS
+    body = re.sub(r"/\*.*?\*/", "", re.search(r"enum moloch_b200_table \{(.*?)\};", hdr, re.S).group(1), flags=re.S)
+    names = [n.strip().split("=")[0].strip() for n in body.split(",")]
+    names = [n for n in names if n and n != "MB_NTABLES"]
+    assert [n[7:].lower() for n in names] == M.TABLES
     body = re.search(r"enum moloch_b200_profile \{(.*?)\};", hdr, re.S).group(1)
     names = [re.sub(r"/\*.*?\*/", "", n, flags=re.S).strip().split("=")[0].strip() for n in body.split(",")]
     names = [n for n in names if n and n != "MB_NPROFILES"]
@@ -43,7 +47,8 @@ def test_enums_match_header():
 
 
 def test_config_struct_layout():
-    assert ctypes.sizeof(M.Config) == 34 * 4 + 3 * 8
+    # 34 int32 + 3 double (ABI v1) + 14 int32 + 5 double (ABI v2)
+    assert ctypes.sizeof(M.Config) == 34 * 4 + 3 * 8 + 14 * 4 + 5 * 8
 
 
 def test_no_cpu_fallback():

@@ -246,6 +246,79 @@ MB_HD void bdy_finish_cell(const BdyArgs& a, int j, int i, int k) {
   a.tetav[id] = tv / a.pai[id];
 }
 
+// ---- mospectral_nudge + lowpass_filter  (Main/mod_bdycod.F90:3898-3960) -------------
+// Single rank: row_reduce/column_reduce are copies of the first `count`
+// elements of the contiguous sx(ide1:ide2,1:2km) / sy(jde1:jde2,1:2lm) arrays
+// (count = nk*(i2-i1+1), mod_mppparam.F90:20620-20664).  Where i1:i2 (j1:j2) is
+// shorter than the allocation, the last elements of sxg (syg) are NOT updated
+// and keep what the last full-length call left there; `stale` carries those
+// values (see k_spectral_nudge).  The levels of one variable are independent
+// and are processed in parallel; all sums run in the reference's order.
+struct SpecArgs {
+  Geo g;
+  double* f;                 // t, u or v
+  const double *b0, *b1;     // its boundary buffers
+  double *zn, *g1;           // 3-D scratch: the departure and its zonally filtered version
+  double *sx, *sy;           // [kz][2km][ni], [kz][2lm][nj]
+  const double *sx_stale, *sy_stale;   // sxg / syg as the last full-length call left them (absolute index)
+  const double *bvx, *bvy;   // bvx[(kk-1)*nj + (j-jde1)], bvy[(l-1)*ni + (i-ide1)]
+  const double* cnudge;
+  double x0, x1;
+  int km2, lm2, ni, nj;
+  int j1, j2, i1, i2, jj1, jj2, ii1, ii2;
+  int count_x, count_y;      // reduced elements of sx / sy
+};
+// the three calls of `boundary` [F90:499-506]; NB the reference passes jci1,jci1
+// as the j update range of t
+MB_HD void spec_ranges(const Geo& g, int var, SpecArgs& a) {
+  if (var == 0) { a.j1 = g.jce1; a.j2 = g.jce2; a.i1 = g.ice1; a.i2 = g.ice2; a.jj1 = g.jci1; a.jj2 = g.jci1; a.ii1 = g.ici1; a.ii2 = g.ici2; }
+  else if (var == 1) { a.j1 = g.jde1; a.j2 = g.jde2; a.i1 = g.ice1; a.i2 = g.ice2; a.jj1 = g.jdi1; a.jj2 = g.jdi2; a.ii1 = g.ici1; a.ii2 = g.ici2; }
+  else { a.j1 = g.jce1; a.j2 = g.jce2; a.i1 = g.ide1; a.i2 = g.ide2; a.jj1 = g.jci1; a.jj2 = g.jci2; a.ii1 = g.idi1; a.ii2 = g.idi2; }
+  a.count_x = a.km2 * (a.i2 - a.i1 + 1);
+  a.count_y = a.lm2 * (a.j2 - a.j1 + 1);
+}
+// zn1 = (x0*b0 + x1*b1) - f on j1:j2, i1:i2
+MB_HD void spec_zn_cell(const SpecArgs& a, int j, int i, int k) {
+  const long long id = gidx(a.g, j, i, k);
+  a.zn[id] = (a.x0 * a.b0[id] + a.x1 * a.b1[id]) - a.f[id];
+}
+// sx(i,kk) = sum_{j=jj1..jj2} zn1(j,i)*bvx(j,kk)
+MB_HD void spec_sx_cell(const SpecArgs& a, int i, int kk, int k) {
+  const Geo& g = a.g;
+  double acc = 0.0;
+  const long long row = gidx(g, 0, i, k);
+  for (int j = a.jj1; j <= a.jj2; ++j) acc = acc + a.zn[row + j] * a.bvx[(kk - 1) * a.nj + (j - g.jde1)];
+  a.sx[((long long)(k - 1) * a.km2 + (kk - 1)) * a.ni + (i - g.ide1)] = acc;
+}
+MB_HD double spec_sxg(const SpecArgs& a, int i, int kk, int k) {
+  const int e = (kk - 1) * a.ni + (i - a.g.ide1);
+  return e < a.count_x ? a.sx[(long long)(k - 1) * a.km2 * a.ni + e] : a.sx_stale[e];
+}
+MB_HD double spec_syg(const SpecArgs& a, int j, int l, int k) {
+  const int e = (l - 1) * a.nj + (j - a.g.jde1);
+  return e < a.count_y ? a.sy[(long long)(k - 1) * a.lm2 * a.nj + e] : a.sy_stale[e];
+}
+// f(j,i) = sum_kk sxg(i,kk)*bvx(j,kk) on j1:j2, i1:i2 (zonal reconstruction)
+MB_HD void spec_g1_cell(const SpecArgs& a, int j, int i, int k) {
+  double acc = 0.0;
+  for (int kk = 1; kk <= a.km2; ++kk) acc = acc + spec_sxg(a, i, kk, k) * a.bvx[(kk - 1) * a.nj + (j - a.g.jde1)];
+  a.g1[gidx(a.g, j, i, k)] = acc;
+}
+// sy(j,l) = sum_{i=ii1..ii2} f(j,i)*bvy(i,l)
+MB_HD void spec_sy_cell(const SpecArgs& a, int j, int l, int k) {
+  const Geo& g = a.g;
+  double acc = 0.0;
+  for (int i = a.ii1; i <= a.ii2; ++i) acc = acc + a.g1[gidx(g, j, i, k)] * a.bvy[(l - 1) * a.ni + (i - g.ide1)];
+  a.sy[((long long)(k - 1) * a.lm2 + (l - 1)) * a.nj + (j - g.jde1)] = acc;
+}
+// f(j,i,k) += cnudge(k) * sum_l syg(j,l)*bvy(i,l) on jj1:jj2, ii1:ii2
+MB_HD void spec_update_cell(const SpecArgs& a, int j, int i, int k) {
+  double acc = 0.0;
+  for (int l = 1; l <= a.lm2; ++l) acc = acc + spec_syg(a, j, l, k) * a.bvy[(l - 1) * a.ni + (i - a.g.ide1)];
+  const long long id = gidx(a.g, j, i, k);
+  a.f[id] = a.f[id] + a.cnudge[k - 1] * acc;
+}
+
 // ---- mkslice, idynamic == 3  (Main/mod_slice.F90:115-173) ------------------------
 struct SliceArgs {
   Geo g;

@@ -93,4 +93,32 @@ inline Geo geo_from_cfg(const moloch_b200_config& f) {
   return g;
 }
 
+// levels and species count of an ABI field (0 levels: not allocated in this configuration)
+inline void field_shape(const moloch_b200_config& f, int id, int& nk, int& nspec) {
+  const int kz = f.kz;
+  nspec = 1;
+  switch (id) {
+    case MB_W: case MB_FMZF: case MB_S: nk = kz + 1; break;
+    case MB_QX: case MB_QXTEN: nk = kz; nspec = f.nqx; break;
+    case MB_TRAC: case MB_CHITEN: nk = kz; nspec = f.ntr; break;
+    case MB_PS: case MB_HX: case MB_HY: case MB_MSFX: case MB_MSFU: case MB_MSFV: case MB_CORU: case MB_CORV:
+      nk = 1; break;
+    // ---- ABI v2: allocated only when the feature is configured -------------------
+    case MB_TKE: case MB_TKETEN: nk = (f.ibltyp == 2) ? kz + 1 : 0; break;
+    case MB_TKEX: nk = (f.ibltyp == 2) ? kz : 0; break;
+    case MB_DUB0: case MB_DUB1: case MB_DVB0: case MB_DVB1: case MB_XTB0: case MB_XTB1: case MB_XPAIB0:
+    case MB_XPAIB1: case MB_XQB0: case MB_XQB1:
+      nk = f.do_bdy ? kz : 0; break;
+    case MB_XLB0: case MB_XLB1: nk = (f.do_bdy && f.present_qc) ? kz : 0; break;
+    case MB_XIB0: case MB_XIB1: nk = (f.do_bdy && f.present_qi) ? kz : 0; break;
+    case MB_XPSB0: case MB_XPSB1: nk = f.do_bdy ? 1 : 0; break;
+    case MB_CHIB0: case MB_CHIB1:
+      nk = (f.do_bdy && f.ichem && f.ichebdy != 0 && f.ntr > 0) ? kz : 0; nspec = f.ntr > 0 ? f.ntr : 1; break;
+    case MB_PF3D: case MB_ZETAF: nk = f.do_slice ? kz + 1 : 0; break;
+    case MB_TH3D: case MB_RHB3D: case MB_WPX3D: nk = f.do_slice ? kz : 0; break;
+    case MB_RHOX2D: case MB_TP2D: case MB_TH700: nk = f.do_slice ? 1 : 0; break;
+    default: nk = kz; break;
+  }
+}
+
 }  // namespace mb

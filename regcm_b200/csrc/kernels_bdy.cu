@@ -236,11 +236,96 @@ int k_ibnd_fill(Ctx& c, int* dst, const int* src, int jlo, int jhi, int ilo, int
   return 0;
 }
 
-// mospectral_nudge: see kernels_spectral below (single rank only in this version)
+// ---- mospectral_nudge (single rank) ------------------------------------------------------
+// Six small launches per variable (t, u, v); every level is handled in parallel,
+// every sum keeps the reference's order (bdy_cells.h).  Runs every dtrad only.
+__global__ void moloch_spec_zn(SpecArgs a) {
+  const int j = a.j1 + blockIdx.x * BX + threadIdx.x, i = a.i1 + blockIdx.y * BY + threadIdx.y;
+  if (j > a.j2 || i > a.i2) return;
+  spec_zn_cell(a, j, i, 1 + (int)blockIdx.z);
+}
+__global__ void moloch_spec_sx(SpecArgs a) {   // x: i, y: kk, z: level
+  const int i = a.i1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > a.i2) return;
+  spec_sx_cell(a, i, 1 + (int)blockIdx.y, 1 + (int)blockIdx.z);
+}
+__global__ void moloch_spec_g1(SpecArgs a) {
+  const int j = a.j1 + blockIdx.x * BX + threadIdx.x, i = a.i1 + blockIdx.y * BY + threadIdx.y;
+  if (j > a.j2 || i > a.i2) return;
+  spec_g1_cell(a, j, i, 1 + (int)blockIdx.z);
+}
+__global__ void moloch_spec_sy(SpecArgs a) {   // x: j, y: l, z: level
+  const int j = a.j1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > a.j2) return;
+  spec_sy_cell(a, j, 1 + (int)blockIdx.y, 1 + (int)blockIdx.z);
+}
+__global__ void moloch_spec_update(SpecArgs a) {
+  const int j = a.jj1 + blockIdx.x * BX + threadIdx.x, i = a.ii1 + blockIdx.y * BY + threadIdx.y;
+  if (j > a.jj2 || i > a.ii2) return;
+  spec_update_cell(a, j, i, 1 + (int)blockIdx.z);
+}
 int k_spectral_nudge(Ctx& c, double xbctime) {
-  (void)xbctime;
-  (void)c;
-  return fail("mospectral_nudge: not implemented yet");
+  const Geo& g = c.g;
+  const int kz = g.kz, km2 = 2 * c.cfg.km, lm2 = 2 * c.cfg.lm;
+  const int ni = g.ide2 - g.ide1 + 1, nj = g.jde2 - g.jde1 + 1;
+  const size_t nsx = (size_t)kz * km2 * ni, nsy = (size_t)kz * lm2 * nj;
+  const size_t need = nsx + nsy + (size_t)km2 * ni + (size_t)lm2 * nj;
+  if (c.spec_work_doubles < need) {
+    if (c.spec_work) cudaFree(c.spec_work);
+    MB_CUDA(cudaMalloc(&c.spec_work, need * sizeof(double)));
+    // getmem zero-initialises sx, sxg, sy, syg (Share/mod_space.F90:304-311)
+    MB_CUDA(cudaMemsetAsync(c.spec_work, 0, need * sizeof(double), c.stream));
+    c.spec_work_doubles = need;
+  }
+  SpecArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = g;
+  a.zn = c.wzall; a.g1 = c.wzall + (size_t)kz * g.plane;   // free outside `advection`
+  a.sx = c.spec_work; a.sy = a.sx + nsx;
+  double* sx_stale = a.sy + nsy; double* sy_stale = sx_stale + (size_t)km2 * ni;
+  a.sx_stale = sx_stale; a.sy_stale = sy_stale;
+  a.bvx = c.tab[MB_TAB_BVX]; a.bvy = c.tab[MB_TAB_BVY]; a.cnudge = c.tab[MB_TAB_CNUDGE];
+  const double rtb = 1.0 / c.cfg.dtbdys;
+  a.x1 = (xbctime + c.cfg.dtsec) * rtb; a.x0 = 1.0 - a.x1;
+  a.km2 = km2; a.lm2 = lm2; a.ni = ni; a.nj = nj;
+  const int fid[3] = {MB_T, MB_U, MB_V}, b0[3] = {MB_XTB0, MB_DUB0, MB_DVB0}, b1[3] = {MB_XTB1, MB_DUB1, MB_DVB1};
+  for (int var = 0; var < 3; ++var) {
+    a.f = c.f[fid[var]].p; a.b0 = c.f[b0[var]].p; a.b1 = c.f[b1[var]].p;
+    spec_ranges(g, var, a);
+    const int nbj = a.j2 - a.j1 + 1, nbi = a.i2 - a.i1 + 1;
+    {
+      LaunchScope ls(c, KID_SPECTRAL);
+      moloch_spec_zn<<<grid3(nbj, nbi, kz), dim3(BX, BY), 0, c.stream>>>(a);
+      MB_CUDA(cudaGetLastError());
+    }
+    {
+      LaunchScope ls(c, KID_SPECTRAL);
+      moloch_spec_sx<<<dim3((unsigned)((nbi + 63) / 64), (unsigned)km2, (unsigned)kz), 64, 0, c.stream>>>(a);
+      MB_CUDA(cudaGetLastError());
+    }
+    if (a.count_x == km2 * ni)   // a full-length reduction: this is what later short calls find in the tail of sxg
+      MB_CUDA(cudaMemcpyAsync(sx_stale, a.sx + (size_t)(kz - 1) * km2 * ni, (size_t)km2 * ni * sizeof(double),
+                              cudaMemcpyDeviceToDevice, c.stream));
+    {
+      LaunchScope ls(c, KID_SPECTRAL);
+      moloch_spec_g1<<<grid3(nbj, nbi, kz), dim3(BX, BY), 0, c.stream>>>(a);
+      MB_CUDA(cudaGetLastError());
+    }
+    {
+      LaunchScope ls(c, KID_SPECTRAL);
+      moloch_spec_sy<<<dim3((unsigned)((nbj + 63) / 64), (unsigned)lm2, (unsigned)kz), 64, 0, c.stream>>>(a);
+      MB_CUDA(cudaGetLastError());
+    }
+    if (a.count_y == lm2 * nj)
+      MB_CUDA(cudaMemcpyAsync(sy_stale, a.sy + (size_t)(kz - 1) * lm2 * nj, (size_t)lm2 * nj * sizeof(double),
+                              cudaMemcpyDeviceToDevice, c.stream));
+    {
+      LaunchScope ls(c, KID_SPECTRAL);
+      moloch_spec_update<<<grid3(a.jj2 - a.jj1 + 1, a.ii2 - a.ii1 + 1, kz), dim3(BX, BY), 0, c.stream>>>(a);
+      MB_CUDA(cudaGetLastError());
+    }
+  }
+  return 0;
 }
 
 }  // namespace mb

@@ -164,8 +164,11 @@ class MolochB200:
     """One rank's MOLOCH dycore on one B200 (mirror of `mod_moloch`)."""
 
     def __init__(self, wl, rank: int = 0, nranks: int = 1, px: int | None = None, py: int | None = None,
-                 device: int = -1, bdy: dict | None = None):
-        self.lib = load_library()
+                 device: int = -1, bdy: dict | None = None, lib=None):
+        # `lib`: a pre-loaded library object with the same entry points (the CPU
+        # tests bind the host-compiled instantiation of the boundary cell functions
+        # this way); the product always loads libmoloch_b200.so.
+        self.lib = lib if lib is not None else load_library()
         self.wl = wl
         if px is None or py is None:
             px, py = default_cpus_per_dim(nranks, wl.jx, wl.iy)
@@ -265,7 +268,11 @@ class MolochB200:
 
     def load_boundary(self, B: dict):
         """Upload the ICBC b0/b1 buffers (global arrays keyed dub0, dub1, ...)."""
+        wl = self.wl
         for name, arr in B.items():
+            if (name.startswith("xlb") and not wl.present_qc) or (name.startswith("xib") and not wl.present_qi) \
+                    or (name.startswith("chib") and (wl.ntr == 0 or wl.ichebdy == 0)):
+                continue        # buffers the configuration does not allocate
             self.set_global(name, arr)
 
     def boundary(self): self._chk(self.lib.moloch_b200_boundary(self.ctx))

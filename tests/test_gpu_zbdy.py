@@ -1,0 +1,123 @@
+"""GPU parity of the lateral boundary (`boundary`, Main/mod_moloch.F90:448-529),
+mkslice (Main/mod_slice.F90:115-173) and the UW-PBL TKE path, through the C ABI,
+against the CPU oracle on the same seeded inputs.  +,-,*,/ results must be
+BIT-EXACT (kernels built -fmad=false, oracle -ffp-contract=off); fields that go
+through pow/exp (pf3d, th3d, tp2d, th700, p, rho, qsat, ps) are compared to
+1e-13 relative (CUDA math library vs glibc).
+
+(The file sorts after the other GPU test files on purpose: these kernels were
+written after the round's GPU budget was spent and were verified on the CPU
+through tests/test_emu_bdy.py only.)"""
+import numpy as np
+import pytest
+
+from regcm_b200 import synthetic as S
+
+from util import DIAGNOSTIC, PROGNOSTIC, compare, make_gpu_bdy, make_oracle_bdy
+
+pytestmark = pytest.mark.gpu
+
+LAM = S.small(S.WORKLOADS["cordex25"], 44, 40, 14, ntr=2, nspgx=6, do_bdy=1, present_qc=1, present_qi=1,
+              mo_top_nudge=1, ichebdy=1)
+CASES = {
+    "lam_full": LAM,
+    "lam_flux_tracers": S.small(LAM, 44, 40, 14, ichebdy=0, present_qi=0),
+    "lam_no_icbc_condensate": S.small(LAM, 40, 36, 10, present_qc=0, present_qi=0, mo_top_nudge=0, ntr=0),
+    "lam_ipptls1": S.small(LAM, 38, 30, 9, ipptls=1, nqx=2, present_qi=0),
+    "band": S.small(LAM, 40, 32, 11, i_band=1, oro="sine"),
+    "lam_tke": S.small(LAM, 44, 40, 14, ibltyp=2, tkemin=1.0e-4),
+    "no_sponge": S.small(LAM, 36, 30, 9, nspgx=0),
+    "lam_slice": S.small(LAM, 44, 40, 14, do_slice=1, icldmstrat=1),
+    # spectral nudging active every step (dtrad == dt), periodic-j and limited-area
+    "spectral": S.small(LAM, 48, 40, 8, mo_spectral_nudge=1, ds_km=100.0, dtrad=150.0, dt=150.0),
+    "spectral_band": S.small(LAM, 48, 40, 8, mo_spectral_nudge=1, ds_km=100.0, dtrad=150.0, dt=150.0, i_band=1,
+                             oro="sine"),
+    # wider than one CTA row of every kernel, boundary strips longer than one block
+    "wide": S.small(LAM, 300, 150, 8, mo_nsound=2),
+}
+STATE = ["u", "v", "w", "t", "pai", "qx", "trac", "ps", "ux", "vx", "tvirt", "tetav"]
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_boundary_bit_exact(case):
+    wl = CASES[case]
+    o, B = make_oracle_bdy(wl)
+    m = make_gpu_bdy(wl, o, B)
+    names = STATE + (["tke"] if wl.ibltyp == 2 else [])
+    o.reset_tendencies(); m.reset_tendencies()
+    o.dynamical_core(); m.dynamical_core()
+    o.bdyval(); m.bdyval()
+    compare(o, m, names, label="bdyval: ")
+    assert m.get_xbctime() == o.get_xbctime()
+    o.boundary(); m.boundary()
+    compare(o, m, names, label="boundary: ")
+    m.close()
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_steps_with_boundary_bit_exact(case):
+    """moloch(): reset_tendencies, dynamical_core, boundary, diagnostics, [mkslice], status_update."""
+    wl = CASES[case]
+    o, B = make_oracle_bdy(wl)
+    m = make_gpu_bdy(wl, o, B)
+    for n in (1, 3):
+        o.step(n); m.moloch(n)
+        compare(o, m, PROGNOSTIC + ["trac"] + (["tke"] if wl.ibltyp == 2 else []), label=f"after {n} more steps: ")
+        compare(o, m, DIAGNOSTIC, exact=False, rtol=1e-13, label=f"after {n} more steps: ")
+        assert m.get_xbctime() == o.get_xbctime()
+    m.close()
+
+
+def test_mkslice():
+    wl = CASES["lam_slice"]
+    o, B = make_oracle_bdy(wl)
+    m = make_gpu_bdy(wl, o, B)
+    o.step(1); m.moloch(1)
+    qx = o.get("qx")
+    qx[1, 3, 5:9, 5:9] = 1.0e-20
+    qx[0, 2, 7:9, 7:9] = 1.0e-9
+    o.set("qx", qx); m.set_global("qx", qx)
+    o.diagnostics(); m.diagnostics()
+    o.mkslice(); m.mkslice()
+    compare(o, m, ["qx", "trac"], label="mkslice: ")
+    compare(o, m, ["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700"], exact=False, rtol=1e-13,
+            label="mkslice: ")
+    m.close()
+
+
+def test_tke_steps_periodic():
+    """ibltyp == 2 without a lateral boundary: TKE through zstagtoh, the batched WAF kernels, htozstag, status_update."""
+    wl = S.small(S.WORKLOADS["isc24_small"], 40, 24, 12, ibltyp=2, tkemin=1.0e-4, oro="sine", oro_h=600.0)
+    o, B = make_oracle_bdy(wl)
+    m = make_gpu_bdy(wl, o, B)
+    o.reset_tendencies(); m.reset_tendencies()
+    o.sound(); m.sound()
+    o.advection(); m.advection()
+    compare(o, m, ["tke", "tkex", "tetav", "qx", "w"], label="advection: ")
+    o.step(2); m.moloch(2)
+    compare(o, m, PROGNOSTIC + ["tke"], label="2 steps: ")
+    m.close()
+
+
+def test_bdy_shift_swaps_buffers():
+    wl = CASES["lam_full"]
+    o, B = make_oracle_bdy(wl)
+    m = make_gpu_bdy(wl, o, B)
+    m.bdy_shift()
+    assert m.get_xbctime() == 0.0
+    own = o.get("fmz") != 0
+    assert np.array_equal(m.get_global("xtb0")[own], B["xtb1"][own])
+    assert np.array_equal(m.get_global("xtb1")[own], B["xtb0"][own])
+    m.close()
+
+
+def test_boundary_needs_configuration():
+    from regcm_b200.moloch import MolochError
+    wl = S.small(S.WORKLOADS["cordex25"], 30, 26, 8, ntr=0, nspgx=5)
+    o, B = make_oracle_bdy(wl)
+    m = make_gpu_bdy(wl, o, B)
+    with pytest.raises(MolochError, match="not configured"):
+        m.boundary()
+    with pytest.raises(MolochError, match="not configured"):
+        m.mkslice()
+    m.close()

@@ -43,6 +43,24 @@ def make_oracle_bdy(wl, px=1, py=1, checked=False, same=False):
     return o, B
 
 
+def bdy_tables_from_oracle(wl, o):
+    """setup_bdycon results for MolochB200(bdy=...): the ibnd planes and hefc from
+    the host model, the sumall-dependent profiles (nztop, tnudge, cnudge) from the
+    oracle so that both sides use identical bits."""
+    if not wl.do_bdy:
+        return None
+    T = S.bdycon_setup(wl, o.get("zeta"))
+    T["nztop"] = o.get_int("nztop")
+    if wl.mo_top_nudge:
+        T["tnudge"] = o.get("tnudge")
+    if wl.mo_spectral_nudge:
+        T["cnudge"] = o.get("cnudge")
+        assert (T["km"], T["lm"]) == (o.get_int("km"), o.get_int("lm"))
+    if wl.nspgx > 0:
+        T["hefc"] = o.get("hefc").reshape(wl.kz, wl.nspgx)
+    return T
+
+
 def oracle_inputs(o, wl):
     names = [n for n in STATIC_FIELDS + STATE_FIELDS if not (n == "trac" and wl.ntr == 0)]
     fields = {n: o.get(n) for n in names}
@@ -55,6 +73,23 @@ def make_gpu(wl, fields, profiles, rank=0, nranks=1, px=None, py=None, device=-1
     if wl.lrotllr:
         profiles = dict(profiles)
     m.init_moloch(fields, profiles)
+    return m
+
+
+def make_gpu_bdy(wl, o, B, device=-1):
+    """One GPU rank with the boundary / slice / TKE extension, fed from the oracle `o`."""
+    fields, profiles = oracle_inputs(o, wl)
+    if wl.lrotllr:
+        profiles["rlat"] = S.make_primary(wl)["rlat"]
+    m = MolochB200(wl, device=device, bdy=bdy_tables_from_oracle(wl, o)).allocate_moloch()
+    if wl.ibltyp == 2:
+        fields["tke"] = o.get("tke")
+    if wl.do_slice:
+        fields["zetaf"] = o.get("zetaf")
+    m.init_moloch(fields, profiles)
+    if wl.do_bdy:
+        m.load_boundary(B)
+        m.set_xbctime(o.get_xbctime())
     return m
 
 

@@ -71,7 +71,7 @@ typedef struct {
   int32_t icldmstrat;                 /* 1: mkslice finds theta at 700 hPa       */
   int32_t km, lm;                     /* spectral-nudging wave numbers (lowpass_init,
                                          mod_bdycod.F90:3852-3853); 0 when unused  */
-  int32_t reserved2;
+  int32_t do_massck;                  /* keep zq on the device for moloch_b200_massck      */
   double dtbdys, dtrad;               /* boundary / radiation period [s]         */
   double rhmin, rhmax, tkemin;        /* Main/mod_params.F90:381-382, mod_pbl_interface.F90:50 */
 } moloch_b200_config;
@@ -204,6 +204,16 @@ int moloch_b200_bdy_shift(moloch_b200_ctx* ctx);
 /* mkslice, idynamic == 3 branch (Main/mod_slice.F90:115-173): pf3d, th3d,
  * rhb3d, wpx3d, rhox2d, tp2d, th700 and the clipping of qx / trac             */
 int moloch_b200_mkslice(moloch_b200_ctx* ctx);
+/* The device part of massck, idynamic == 3 branch (Main/mod_massck.F90:77-175):
+ * this rank's partial sums out[0..3] = tdrym, tdadv, tqmass, tqadv [kg]; the
+ * host adds the surface terms (rain, evaporation), does the sumall over ranks
+ * and the bookkeeping (:303-372).  Row sums run along j in the reference's
+ * order, rows are added level by level: deterministic, equal to the
+ * reference's single running sum to rounding (1e-12 relative for the masses).  */
+int moloch_b200_massck(moloch_b200_ctx* ctx, double out[4]);
+/* max/min of ps over the interior and the number of non-finite values there:
+ * the CFL guard of moloch (Main/mod_moloch.F90:407-422); exact.              */
+int moloch_b200_ps_check(moloch_b200_ctx* ctx, double maxmin[2], int32_t* nonfinite);
 /* nsteps x [reset_tendencies, dynamical_core, boundary (do_bdy), diagnostics,
  * mkslice (do_slice), status_update]: `moloch` (Main/mod_moloch.F90:312-446)
  * with the host physics producing zero tendencies.                           */

@@ -1696,6 +1696,46 @@ void mkslice(World& w) {
   });
 }
 
+// massck, idynamic == 3 branch (Main/mod_massck.F90:77-185): the sums over the
+// atmosphere (the surface terms crrate, ncrrate, qfx belong to the physics) in
+// the reference's single running sum per rank, then sumall over ranks.
+// dz = zetaf(k) - zetaf(k+1) (Main/mod_params.F90:3389).
+void massck(World& w, double out[4]) {
+  const int kz = w.c.kz;
+  const double dxsq = w.dx * w.dx, dt = w.dtsec, dx = w.dx;
+  double drymass = 0.0, dryadv = 0.0, qmass = 0.0, qadv = 0.0;
+  for (auto& r : w.r) {
+    const Geom& g = r.g;
+    auto dz = [&](int j, int i, int k) { return r.zetaf(j, i, k) - r.zetaf(j, i, k + 1); };
+    double tdrym = 0.0, tdadv = 0.0, tqmass = 0.0, tqadv = 0.0;
+    for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+      tdrym = tdrym + dxsq * dz(j, i, k) * r.rho(j, i, k);
+    if (g.bl) for (int k = 1; k <= kz; ++k) for (int i = g.ice1; i <= g.ice2; ++i)
+      tdadv = tdadv + r.u(g.jde1, i, k) * dt * dx * dz(g.jce1, i, k) * r.rho(g.jce1, i, k);
+    if (g.br) for (int k = 1; k <= kz; ++k) for (int i = g.ice1; i <= g.ice2; ++i)
+      tdadv = tdadv - r.u(g.jde2, i, k) * dt * dx * dz(g.jce2, i, k) * r.rho(g.jce2, i, k);
+    if (g.bb) for (int k = 1; k <= kz; ++k) for (int j = g.jci1; j <= g.jci2; ++j)
+      tdadv = tdadv + r.v(j, g.ide1, k) * dt * dx * dz(j, g.ice1, k) * r.rho(j, g.ice1, k);
+    if (g.bt) for (int k = 1; k <= kz; ++k) for (int j = g.jci1; j <= g.jci2; ++j)
+      tdadv = tdadv - r.v(j, g.ide2, k) * dt * dx * dz(j, g.ice2, k) * r.rho(j, g.ice2, k);
+    for (int n = 0; n < w.nqx; ++n) {
+      Arr& q = r.qx[n];
+      for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+        tqmass = tqmass + q(j, i, k) * dxsq * dz(j, i, k) * r.rho(j, i, k);
+      if (g.bl) for (int k = 1; k <= kz; ++k) for (int i = g.ice1; i <= g.ice2; ++i)
+        tqadv = tqadv + q(g.jce1, i, k) * r.u(g.jde1, i, k) * dt * dx * dz(g.jce1, i, k) * r.rho(g.jce1, i, k);
+      if (g.br) for (int k = 1; k <= kz; ++k) for (int i = g.ice1; i <= g.ice2; ++i)
+        tqadv = tqadv - q(g.jce2, i, k) * r.u(g.jde2, i, k) * dt * dx * dz(g.jce2, i, k) * r.rho(g.jce2, i, k);
+      if (g.bb) for (int k = 1; k <= kz; ++k) for (int j = g.jci1; j <= g.jci2; ++j)
+        tqadv = tqadv + q(j, g.ice1, k) * r.v(j, g.ide1, k) * dt * dx * dz(j, g.ice1, k) * r.rho(j, g.ice1, k);
+      if (g.bt) for (int k = 1; k <= kz; ++k) for (int j = g.jci1; j <= g.jci2; ++j)
+        tqadv = tqadv - q(j, g.ice2, k) * r.v(j, g.ide2, k) * dt * dx * dz(j, g.ice2, k) * r.rho(j, g.ice2, k);
+    }
+    drymass += tdrym; dryadv += tdadv; qmass += tqmass; qadv += tqadv;   // sumall
+  }
+  out[0] = drymass; out[1] = dryadv; out[2] = qmass; out[3] = qadv;
+}
+
 // moloch [F90:312-446]: physics disabled ([F90:362]); massck/report skipped.
 // Without oracle_set_ext: do_apply_bdy = .false. (irceideal / test modes,
 // [F90:305]) and no mkslice.
@@ -1862,6 +1902,19 @@ int oracle_mkslice(void* h) {
   World& w = *(World*)h;
   if (!w.ext_set) { g_err = "oracle_set_ext has not been called"; return 1; }
   mkslice(w); return 0;
+}
+int oracle_massck(void* h, double* out4) { massck(*(World*)h, out4); return 0; }
+// maxval/minval of ps over the interior + maxall/minall [F90:408-411]; non-finite values are counted
+int oracle_ps_check(void* h, double* maxmin, int* nonfinite) {
+  World& w = *(World*)h;
+  double mx = -1.0e300, mn = 1.0e300; int bad = 0;
+  for (auto& r : w.r) for (int i = r.g.ici1; i <= r.g.ici2; ++i) for (int j = r.g.jci1; j <= r.g.jci2; ++j) {
+    const double p = r.ps(j, i);
+    if (!std::isfinite(p)) { ++bad; continue; }
+    mx = std::max(mx, p); mn = std::min(mn, p);
+  }
+  maxmin[0] = mx; maxmin[1] = mn; *nonfinite = bad;
+  return 0;
 }
 int oracle_set_xbctime(void* h, double t) { ((World*)h)->xbctime = t; return 0; }
 double oracle_get_xbctime(void* h) { return ((World*)h)->xbctime; }

@@ -102,6 +102,10 @@ int    oracle_status_update(void* h);
 int    oracle_boundary(void* h);
 int    oracle_bdyval(void* h);
 int    oracle_mkslice(void* h);                     /* Main/mod_slice.F90:115-173 */
+/* massck, MOLOCH branch (Main/mod_massck.F90:77-185) without the surface terms:
+ * out = drymass, dryadv, qmass, qadv after the sumall over subdomains          */
+int    oracle_massck(void* h, double* out4);
+int    oracle_ps_check(void* h, double* maxmin, int* nonfinite);   /* Main/mod_moloch.F90:407-422 */
 int    oracle_set_xbctime(void* h, double xbctime);
 double oracle_get_xbctime(void* h);
 int    oracle_get_int(void* h, const char* name);   /* nztop, km, lm              */

@@ -58,6 +58,8 @@ def _lib(checked: bool):
         for f in ("oracle_boundary", "oracle_bdyval", "oracle_mkslice"):
             getattr(lib, f).argtypes = [C.c_void_p]
         lib.oracle_set_ext.argtypes = [C.c_void_p, C.POINTER(OracleExtConfig)]
+        lib.oracle_massck.argtypes = [C.c_void_p, C.c_void_p]
+        lib.oracle_ps_check.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_set_xbctime.argtypes = [C.c_void_p, C.c_double]
         lib.oracle_get_xbctime.argtypes = [C.c_void_p]
         lib.oracle_get_xbctime.restype = C.c_double
@@ -159,6 +161,17 @@ class Oracle:
     def boundary(self): self._chk(self.lib.oracle_boundary(self.h))
     def bdyval(self): self._chk(self.lib.oracle_bdyval(self.h))
     def mkslice(self): self._chk(self.lib.oracle_mkslice(self.h))
+    def massck(self) -> np.ndarray:
+        out = np.zeros(4)
+        self._chk(self.lib.oracle_massck(self.h, out.ctypes.data))
+        return out
+
+    def ps_check(self):
+        mm = np.zeros(2)
+        bad = C.c_int(0)
+        self._chk(self.lib.oracle_ps_check(self.h, mm.ctypes.data, C.byref(bad)))
+        return float(mm[0]), float(mm[1]), int(bad.value)
+
     def set_xbctime(self, t: float): self._chk(self.lib.oracle_set_xbctime(self.h, float(t)))
     def get_xbctime(self) -> float: return float(self.lib.oracle_get_xbctime(self.h))
     def get_int(self, name: str) -> int: return int(self.lib.oracle_get_int(self.h, name.encode()))

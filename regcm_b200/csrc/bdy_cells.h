@@ -169,33 +169,39 @@ MB_HD void bdy_relax_cell(const BdyArgs& a, int j, int i, int k) {
   const double xft = topk ? a.tnudge[k - 1] * trtau * a.dtsec : 0.0;
   const bool sponge = a.nspgx > 0;
   const bool in_jc = j >= g.jci1 && j <= g.jci2, in_ic = i >= g.ici1 && i <= g.ici2;
+  // Only the sponge ring (ibnd > 0) and the nztop nudged layers are touched: every
+  // other cell is left alone (no load, no store), which is most of the grid.
   if (in_ic && j >= g.jdi1 && j <= g.jdi2) {          // u: motopnudge :4066-4070, morelax(ba_ud) [F90:478]
-    double f = a.u[id];
-    const double fext = lin2(a.dub0, a.dub1, id, a.x0, a.x1);
-    if (topk) f = relax_to(f, xft, fext);
     const int ib = sponge ? a.ib_ud[i2] : 0;
-    if (ib > 0) f = relax_to(f, a.hefc[(k - 1) * a.nspgx + (ib - 1)], fext);
-    a.u[id] = f;
+    if (topk || ib > 0) {
+      double f = a.u[id];
+      const double fext = lin2(a.dub0, a.dub1, id, a.x0, a.x1);
+      if (topk) f = relax_to(f, xft, fext);
+      if (ib > 0) f = relax_to(f, a.hefc[(k - 1) * a.nspgx + (ib - 1)], fext);
+      a.u[id] = f;
+    }
   }
   if (in_jc && i >= g.idi1 && i <= g.idi2) {          // v: :4071-4075, morelax(ba_vd) [F90:479]
-    double f = a.v[id];
-    const double fext = lin2(a.dvb0, a.dvb1, id, a.x0, a.x1);
-    if (topk) f = relax_to(f, xft, fext);
     const int ib = sponge ? a.ib_vd[i2] : 0;
-    if (ib > 0) f = relax_to(f, a.hefc[(k - 1) * a.nspgx + (ib - 1)], fext);
-    a.v[id] = f;
+    if (topk || ib > 0) {
+      double f = a.v[id];
+      const double fext = lin2(a.dvb0, a.dvb1, id, a.x0, a.x1);
+      if (topk) f = relax_to(f, xft, fext);
+      if (ib > 0) f = relax_to(f, a.hefc[(k - 1) * a.nspgx + (ib - 1)], fext);
+      a.v[id] = f;
+    }
   }
   if (!(in_jc && in_ic)) return;
   const int ib = sponge ? a.ib_cr[i2] : 0;
   const double xf = ib > 0 ? a.hefc[(k - 1) * a.nspgx + (ib - 1)] : 0.0;
-  {                                                   // t: :4061-4065, morelax [F90:480]
+  if (topk || ib > 0) {                               // t: :4061-4065, morelax [F90:480]
     double f = a.t[id];
     const double fext = lin2(a.xtb0, a.xtb1, id, a.x0, a.x1);
     if (topk) f = relax_to(f, xft, fext);
     if (ib > 0) f = relax_to(f, xf, fext);
     a.t[id] = f;
   }
-  {                                                   // w: :4056-4060 (wfac = 0), morelax_fraction(frac = 0) [F90:483]
+  if ((a.top_nudge && k == 2) || ib > 0) {            // w: :4056-4060 (wfac = 0), morelax_fraction(frac = 0) [F90:483]
     double f = a.w[id];
     if (a.top_nudge && k == 2) { const double fext = 0.0 * f; const double xw = wrtau * a.dtsec; f = (1.0 - xw) * f + xw * fext; }
     if (ib > 0) f = (1.0 - xf) * f + xf * f * 0.0;
@@ -368,6 +374,96 @@ MB_HD void mkslice_col(const SliceArgs& a, int j, int i) {
     }
     a.th700[i2] = th;
   }
+}
+
+// ---- massck, idynamic == 3  (Main/mod_massck.F90:77-175) and the ps guard ---------
+struct MassArgs {
+  Geo g;
+  const double *rho, *zq, *qx, *u, *v, *ps;
+  double *rows;     // [2][kz*ni]: row sums of dry mass and water mass
+  double *lev;      // [2][kz]: boundary flux sums of one level (dry, water)
+  double *psrow;    // [3][ni]: row max, row min, non-finite count of ps
+  double *out;      // tdrym, tdadv, tqmass, tqadv, psmax, psmin, nonfinite
+  double dxsq, dt, dx;
+  int ni;
+};
+// dz = zetaf(k) - zetaf(k+1)  (Main/mod_params.F90:3389)
+MB_HD double mass_dz(const MassArgs& a, long long id) { return a.zq[id] - a.zq[id + a.g.plane]; }
+// one interior row (i,k): sum over j = jci1:jci2 in the reference's order (:79-83, :139-146)
+MB_HD void massck_row(const MassArgs& a, int i, int k) {
+  const Geo& g = a.g;
+  const long long sp = (long long)g.kz * g.plane;
+  double dry = 0.0, wat = 0.0;
+  if (i >= g.ici1 && i <= g.ici2) {
+    for (int j = g.jci1; j <= g.jci2; ++j) {
+      const long long id = gidx(g, j, i, k);
+      dry = dry + a.dxsq * mass_dz(a, id) * a.rho[id];
+    }
+    for (int n = 0; n < g.nqx; ++n)
+      for (int j = g.jci1; j <= g.jci2; ++j) {
+        const long long id = gidx(g, j, i, k);
+        wat = wat + a.qx[id + n * sp] * a.dxsq * mass_dz(a, id) * a.rho[id];
+      }
+  }
+  const long long r = (long long)(k - 1) * a.ni + (i - g.ice1);
+  a.rows[r] = dry;
+  a.rows[(long long)g.kz * a.ni + r] = wat;
+}
+// boundary fluxes of one level (:85-118, :150-185)
+MB_HD void massck_bdy_level(const MassArgs& a, int k) {
+  const Geo& g = a.g;
+  const long long sp = (long long)g.kz * g.plane;
+  double dry = 0.0, wat = 0.0;
+  for (int pass = 0; pass <= g.nqx; ++pass) {   // pass 0: dry air, pass n: water species n
+    double acc = 0.0;
+    const long long off = pass > 0 ? (long long)(pass - 1) * sp : 0;
+    if (g.bl) for (int i = g.ice1; i <= g.ice2; ++i) {
+      const long long idc = gidx(g, g.jce1, i, k), idd = gidx(g, g.jde1, i, k);
+      acc = acc + (pass > 0 ? a.qx[idc + off] * a.u[idd] : a.u[idd]) * a.dt * a.dx * mass_dz(a, idc) * a.rho[idc];
+    }
+    if (g.br) for (int i = g.ice1; i <= g.ice2; ++i) {
+      const long long idc = gidx(g, g.jce2, i, k), idd = gidx(g, g.jde2, i, k);
+      acc = acc - (pass > 0 ? a.qx[idc + off] * a.u[idd] : a.u[idd]) * a.dt * a.dx * mass_dz(a, idc) * a.rho[idc];
+    }
+    if (g.bb) for (int j = g.jci1; j <= g.jci2; ++j) {
+      const long long idc = gidx(g, j, g.ice1, k), idd = gidx(g, j, g.ide1, k);
+      acc = acc + (pass > 0 ? a.qx[idc + off] * a.v[idd] : a.v[idd]) * a.dt * a.dx * mass_dz(a, idc) * a.rho[idc];
+    }
+    if (g.bt) for (int j = g.jci1; j <= g.jci2; ++j) {
+      const long long idc = gidx(g, j, g.ice2, k), idd = gidx(g, j, g.ide2, k);
+      acc = acc - (pass > 0 ? a.qx[idc + off] * a.v[idd] : a.v[idd]) * a.dt * a.dx * mass_dz(a, idc) * a.rho[idc];
+    }
+    if (pass == 0) dry = acc; else wat = wat + acc;
+  }
+  a.lev[k - 1] = dry;
+  a.lev[g.kz + k - 1] = wat;
+}
+// ps over one interior row [F90:408-409]
+MB_HD void ps_row(const MassArgs& a, int i) {
+  const Geo& g = a.g;
+  double mx = -1.0e300, mn = 1.0e300, bad = 0.0;
+  if (i >= g.ici1 && i <= g.ici2)
+    for (int j = g.jci1; j <= g.jci2; ++j) {
+      const double p = a.ps[gidx2(g, j, i)];
+      if (!(p - p == 0.0)) bad = bad + 1.0;      // NaN or Inf
+      else { if (p > mx) mx = p; if (p < mn) mn = p; }
+    }
+  a.psrow[i - g.ice1] = mx; a.psrow[a.ni + i - g.ice1] = mn; a.psrow[2 * a.ni + i - g.ice1] = bad;
+}
+// final sums, one thread: rows level by level, then the levels' boundary sums
+MB_HD void massck_final(const MassArgs& a) {
+  const Geo& g = a.g;
+  const long long nr = (long long)g.kz * a.ni;
+  double dry = 0.0, wat = 0.0, fd = 0.0, fw = 0.0;
+  for (long long r = 0; r < nr; ++r) { dry = dry + a.rows[r]; wat = wat + a.rows[nr + r]; }
+  for (int k = 0; k < g.kz; ++k) { fd = fd + a.lev[k]; fw = fw + a.lev[g.kz + k]; }
+  double mx = -1.0e300, mn = 1.0e300, bad = 0.0;
+  for (int i = 0; i < a.ni; ++i) {
+    if (a.psrow[i] > mx) mx = a.psrow[i];
+    if (a.psrow[a.ni + i] < mn) mn = a.psrow[a.ni + i];
+    bad = bad + a.psrow[2 * a.ni + i];
+  }
+  a.out[0] = dry; a.out[1] = fd; a.out[2] = wat; a.out[3] = fw; a.out[4] = mx; a.out[5] = mn; a.out[6] = bad;
 }
 
 // ---- TKE (ibltyp == 2) -------------------------------------------------------------

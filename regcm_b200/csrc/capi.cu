@@ -17,7 +17,7 @@ static const char* k_names[KID_COUNT] = {
     "reset_tendencies", "tetavf_init", "sound_pre", "divdamp_filter", "wsolve", "uvupdate", "sfinish",
     "destagger", "waf_vertical", "waf_meridional", "waf_zonal", "curvature", "restagger", "tvirt_temp",
     "diag_prq", "diag_ps", "status_update", "halo_local", "halo_pack", "halo_unpack", "init_static",
-    "waf_horizontal", "box_copy", "bdyval", "bdy_relax", "bdy_finish", "mkslice", "tke", "spectral_nudge"};
+    "waf_horizontal", "box_copy", "bdyval", "bdy_relax", "bdy_finish", "mkslice", "tke", "spectral_nudge", "massck"};
 const char* kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? k_names[kid] : "?"; }
 
 LaunchScope::LaunchScope(Ctx& c_, int kid_) : c(c_), kid(kid_) {
@@ -408,6 +408,7 @@ int moloch_b200_destroy(moloch_b200_ctx* c) {
   for (int q = 0; q < 3; ++q) if (c->ibnd[q]) cudaFree(c->ibnd[q]);
   for (int q = 0; q < MB_NTABLES; ++q) if (c->tab[q]) cudaFree(c->tab[q]);
   if (c->spec_work) cudaFree(c->spec_work);
+  if (c->mass_work) cudaFree(c->mass_work);
   if (c->stage) cudaFree(c->stage);
   if (c->arena) cudaFree(c->arena);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -633,6 +634,22 @@ int moloch_b200_mkslice(moloch_b200_ctx* c) {
   ENTRY(c)
   if (!c->cfg.do_slice) return fail("mkslice not configured (moloch_b200_config.do_slice)");
   return k_mkslice(*c);
+}
+int moloch_b200_massck(moloch_b200_ctx* c, double out[4]) {
+  ENTRY(c)
+  if (!out) return fail("massck: null argument");
+  double o7[7];
+  if (k_massck(*c, 1, o7)) return 1;
+  for (int q = 0; q < 4; ++q) out[q] = o7[q];
+  return 0;
+}
+int moloch_b200_ps_check(moloch_b200_ctx* c, double maxmin[2], int32_t* nonfinite) {
+  ENTRY(c)
+  if (!maxmin || !nonfinite) return fail("ps_check: null argument");
+  double o7[7];
+  if (k_massck(*c, 2, o7)) return 1;
+  maxmin[0] = o7[4]; maxmin[1] = o7[5]; *nonfinite = (int32_t)o7[6];
+  return 0;
 }
 int moloch_b200_step(moloch_b200_ctx* c, int nsteps) {
   ENTRY(c)

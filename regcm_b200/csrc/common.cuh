@@ -22,7 +22,7 @@ enum KernelId {
   KID_RESET = 0, KID_TETAVF, KID_SOUND_PRE, KID_DIVDAMP, KID_WSOLVE, KID_UVUPDATE, KID_SFINISH,
   KID_DESTAG, KID_WAF_Z, KID_WAF_Y, KID_WAF_X, KID_CURV, KID_RESTAG, KID_TVIRT, KID_DIAG, KID_PS,
   KID_STATUS, KID_HALO, KID_HALO_PACK, KID_HALO_UNPACK, KID_INIT, KID_WAF_H, KID_BOX,
-  KID_BDYVAL, KID_BDYRELAX, KID_BDYFINISH, KID_MKSLICE, KID_TKE, KID_SPECTRAL, KID_COUNT
+  KID_BDYVAL, KID_BDYRELAX, KID_BDYFINISH, KID_MKSLICE, KID_TKE, KID_SPECTRAL, KID_MASSCK, KID_COUNT
 };
 
 struct ProfEvent { cudaEvent_t a, b; int kid; };
@@ -103,6 +103,8 @@ struct Ctx {
   double tspectral = 0.0;   // Main/mod_moloch.F90:452
   double* spec_work = nullptr;   // mospectral_nudge scratch (sx, sxg, sy, syg, stale tails)
   size_t spec_work_doubles = 0;
+  double* mass_work = nullptr;   // massck / ps guard partial sums
+  size_t mass_work_doubles = 0;
   // staging for set/get
   double* stage = nullptr;
   size_t stage_doubles = 0;
@@ -230,6 +232,7 @@ int k_tke_restagger(Ctx& c);
 int k_tke_update(Ctx& c, double dtinc);
 int k_ibnd_fill(Ctx& c, int* dst, const int* src, int jlo, int jhi, int ilo, int ihi);
 int k_spectral_nudge(Ctx& c, double xbctime);
+int k_massck(Ctx& c, int what, double* out7);
 // kernels_waf.cu
 int k_waf_ratios(Ctx& c);
 int k_waf_z2(Ctx& c, int first, int count, double dta);

@@ -114,7 +114,8 @@ inline void field_shape(const moloch_b200_config& f, int id, int& nk, int& nspec
     case MB_XPSB0: case MB_XPSB1: nk = f.do_bdy ? 1 : 0; break;
     case MB_CHIB0: case MB_CHIB1:
       nk = (f.do_bdy && f.ichem && f.ichebdy != 0 && f.ntr > 0) ? kz : 0; nspec = f.ntr > 0 ? f.ntr : 1; break;
-    case MB_PF3D: case MB_ZETAF: nk = f.do_slice ? kz + 1 : 0; break;
+    case MB_PF3D: nk = f.do_slice ? kz + 1 : 0; break;
+    case MB_ZETAF: nk = (f.do_slice || f.do_massck) ? kz + 1 : 0; break;
     case MB_TH3D: case MB_RHB3D: case MB_WPX3D: nk = f.do_slice ? kz : 0; break;
     case MB_RHOX2D: case MB_TP2D: case MB_TH700: nk = f.do_slice ? 1 : 0; break;
     default: nk = kz; break;

@@ -172,6 +172,72 @@ int k_mkslice(Ctx& c) {
   return 0;
 }
 
+// ---- massck partial sums and the ps guard ------------------------------------------------------
+// A diagnostic that runs when RegCM's debug_level > 0 / every syncro_rep: one
+// thread per row walks along j in the reference's order (deterministic sums;
+// the strided access costs a fraction of a millisecond at 400x400x41).
+__global__ void moloch_massck_rows(MassArgs a) {
+  const int i = a.g.ice1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > a.g.ice2) return;
+  massck_row(a, i, 1 + (int)blockIdx.y);
+}
+__global__ void moloch_massck_bdy(MassArgs a) {
+  const int k = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > a.g.kz) return;
+  massck_bdy_level(a, k);
+}
+__global__ void moloch_ps_rows(MassArgs a) {
+  const int i = a.g.ice1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > a.g.ice2) return;
+  ps_row(a, i);
+}
+__global__ void moloch_massck_final(MassArgs a) { massck_final(a); }
+// what: 1 massck sums, 2 ps guard, 3 both; out7 (host): tdrym, tdadv, tqmass, tqadv, psmax, psmin, nonfinite
+int k_massck(Ctx& c, int what, double* out7) {
+  const Geo& g = c.g;
+  const int ni = g.ice2 - g.ice1 + 1, kz = g.kz;
+  const size_t need = (size_t)2 * kz * ni + 2 * kz + 3 * ni + 8;
+  if (c.mass_work_doubles < need) {
+    if (c.mass_work) cudaFree(c.mass_work);
+    MB_CUDA(cudaMalloc(&c.mass_work, need * sizeof(double)));
+    c.mass_work_doubles = need;
+  }
+  MB_CUDA(cudaMemsetAsync(c.mass_work, 0, need * sizeof(double), c.stream));
+  MassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = g;
+  a.rho = c.f[MB_RHO].p; a.zq = c.f[MB_ZETAF].p; a.qx = c.f[MB_QX].p; a.u = c.f[MB_U].p; a.v = c.f[MB_V].p;
+  a.ps = c.f[MB_PS].p;
+  a.rows = c.mass_work; a.lev = a.rows + (size_t)2 * kz * ni; a.psrow = a.lev + 2 * kz; a.out = a.psrow + 3 * ni;
+  a.dxsq = c.cfg.dx * c.cfg.dx; a.dt = c.cfg.dtsec; a.dx = c.cfg.dx; a.ni = ni;
+  if (what & 1) {
+    if (!a.zq) return fail("massck: zq (MB_ZETAF) is not on the device (moloch_b200_config.do_massck)");
+    {
+      LaunchScope ls(c, KID_MASSCK);
+      moloch_massck_rows<<<dim3((unsigned)((ni + 63) / 64), (unsigned)kz), 64, 0, c.stream>>>(a);
+      MB_CUDA(cudaGetLastError());
+    }
+    {
+      LaunchScope ls(c, KID_MASSCK);
+      moloch_massck_bdy<<<(unsigned)((kz + 63) / 64), 64, 0, c.stream>>>(a);
+      MB_CUDA(cudaGetLastError());
+    }
+  }
+  if (what & 2) {
+    LaunchScope ls(c, KID_MASSCK);
+    moloch_ps_rows<<<(unsigned)((ni + 63) / 64), 64, 0, c.stream>>>(a);
+    MB_CUDA(cudaGetLastError());
+  }
+  {
+    LaunchScope ls(c, KID_MASSCK);
+    moloch_massck_final<<<1, 1, 0, c.stream>>>(a);
+    MB_CUDA(cudaGetLastError());
+  }
+  MB_CUDA(cudaMemcpyAsync(out7, a.out, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  MB_CUDA(cudaStreamSynchronize(c.stream));
+  return 0;
+}
+
 // ---- TKE helpers (ibltyp == 2) ---------------------------------------------------------------
 __global__ void moloch_zstagtoh(Geo g, const double* __restrict__ fl, double* __restrict__ hl) {
   const int j = g.jce1 + blockIdx.x * BX + threadIdx.x;

@@ -56,6 +56,7 @@ ABI_SYMBOLS = [
     "moloch_b200_halo_plan", "moloch_b200_p2p_blob_size", "moloch_b200_p2p_export", "moloch_b200_p2p_connect", "moloch_b200_set_async",
     "moloch_b200_set_table", "moloch_b200_set_ibnd", "moloch_b200_boundary", "moloch_b200_bdyval",
     "moloch_b200_set_xbctime", "moloch_b200_get_xbctime", "moloch_b200_bdy_shift", "moloch_b200_mkslice",
+    "moloch_b200_massck", "moloch_b200_ps_check",
 ]
 
 
@@ -67,7 +68,7 @@ class Config(C.Structure):
         "mo_divdamp", "mo_divfilter", "lrotllr", "ipptls", "device", "ibltyp")] + [
         (n, C.c_double) for n in ("dtsec", "dx", "mo_dzita")] + [(n, C.c_int32) for n in (
         "do_bdy", "nspgx", "present_qc", "present_qi", "mo_top_nudge", "mo_spectral_nudge", "nztop", "ichem",
-        "ichebdy", "do_slice", "icldmstrat", "km", "lm", "reserved2")] + [
+        "ichebdy", "do_slice", "icldmstrat", "km", "lm", "do_massck")] + [
         (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin")]
 
 
@@ -107,6 +108,8 @@ def load_library():
     lib.moloch_b200_host_free.argtypes = [C.c_void_p]
     lib.moloch_b200_set_table.argtypes = [ctx, C.c_int, C.c_void_p, C.c_int]
     lib.moloch_b200_set_ibnd.argtypes = [ctx, C.c_int, C.c_void_p] + [C.c_int] * 4
+    lib.moloch_b200_massck.argtypes = [ctx, C.c_void_p]
+    lib.moloch_b200_ps_check.argtypes = [ctx, C.c_void_p, C.c_void_p]
     lib.moloch_b200_set_xbctime.argtypes = [ctx, C.c_double]
     lib.moloch_b200_get_xbctime.argtypes = [ctx]
     lib.moloch_b200_get_xbctime.restype = C.c_double
@@ -146,7 +149,7 @@ def make_config(wl, g: Geom, device: int = -1, mo_dzita: float | None = None, bd
                   present_qi=wl.present_qi, mo_top_nudge=wl.mo_top_nudge if wl.do_bdy else 0,
                   mo_spectral_nudge=wl.mo_spectral_nudge if wl.do_bdy else 0, nztop=int(bdy.get("nztop", 0)),
                   ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, do_slice=wl.do_slice, icldmstrat=wl.icldmstrat,
-                  km=int(bdy.get("km", 0)), lm=int(bdy.get("lm", 0)), reserved2=0, dtbdys=wl.dtbdys,
+                  km=int(bdy.get("km", 0)), lm=int(bdy.get("lm", 0)), do_massck=int(getattr(wl, "do_massck", 0)), dtbdys=wl.dtbdys,
                   dtrad=wl.dtrad, rhmin=wl.rhmin, rhmax=wl.rhmax, tkemin=wl.tkemin)
 
 
@@ -279,6 +282,19 @@ class MolochB200:
     def bdyval(self): self._chk(self.lib.moloch_b200_bdyval(self.ctx))
     def bdy_shift(self): self._chk(self.lib.moloch_b200_bdy_shift(self.ctx))
     def mkslice(self): self._chk(self.lib.moloch_b200_mkslice(self.ctx))
+    def massck(self) -> np.ndarray:
+        """This rank's tdrym, tdadv, tqmass, tqadv (Main/mod_massck.F90:77-185)."""
+        out = np.zeros(4)
+        self._chk(self.lib.moloch_b200_massck(self.ctx, out.ctypes.data))
+        return out
+
+    def ps_check(self):
+        """(max ps, min ps, number of non-finite values) over the interior (Main/mod_moloch.F90:407-422)."""
+        mm = np.zeros(2)
+        bad = C.c_int32(0)
+        self._chk(self.lib.moloch_b200_ps_check(self.ctx, mm.ctypes.data, C.byref(bad)))
+        return float(mm[0]), float(mm[1]), int(bad.value)
+
     def set_xbctime(self, t: float): self._chk(self.lib.moloch_b200_set_xbctime(self.ctx, float(t)))
     def get_xbctime(self) -> float: return float(self.lib.moloch_b200_get_xbctime(self.ctx))
 

@@ -84,6 +84,7 @@ class Workload:
     ibltyp: int = 1          # 2: UW PBL, TKE advected by the dycore
     icldmstrat: int = 0
     do_slice: int = 0        # mkslice inside moloch()
+    do_massck: int = 0       # keep zq on the device for massck (debug_level > 0)
     dtbdys: float = 21600.0
     dtrad: float = 1800.0
     rhmin: float = 0.01      # Main/mod_params.F90:381-382
@@ -101,7 +102,7 @@ class Workload:
 
     @property
     def needs_ext(self) -> bool:
-        return bool(self.do_bdy or self.do_slice or self.ibltyp == 2)
+        return bool(self.do_bdy or self.do_slice or self.do_massck or self.ibltyp == 2)
 
     @property
     def cells(self) -> int:

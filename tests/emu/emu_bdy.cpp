@@ -250,6 +250,39 @@ int emu_b200_mkslice(void* h) {   // = k_mkslice
   walk(o, g.ice1, g.ice2, [&](int i) { walk(o, g.jce1, g.jce2, [&](int j) { mkslice_col(a, j, i); }); });
   return 0;
 }
+// = k_massck: out7 = tdrym, tdadv, tqmass, tqadv, psmax, psmin, nonfinite
+int emu_b200_massck7(void* h, int what, double* out7) {
+  Emu& e = *(Emu*)h; const Geo& g = e.g; const int o = e.order;
+  const int ni = g.ice2 - g.ice1 + 1, kz = g.kz;
+  std::vector<double> work((size_t)2 * kz * ni + 2 * kz + 3 * ni + 8, 0.0);
+  MassArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.g = g;
+  a.rho = P(e, MB_RHO); a.zq = P(e, MB_ZETAF); a.qx = P(e, MB_QX); a.u = P(e, MB_U); a.v = P(e, MB_V); a.ps = P(e, MB_PS);
+  a.rows = work.data(); a.lev = a.rows + (size_t)2 * kz * ni; a.psrow = a.lev + 2 * kz; a.out = a.psrow + 3 * ni;
+  a.dxsq = e.cfg.dx * e.cfg.dx; a.dt = e.cfg.dtsec; a.dx = e.cfg.dx; a.ni = ni;
+  if (what & 1) {
+    if (!a.zq) return fail("emu: do_massck not configured");
+    walk(o, 1, kz, [&](int k) { walk(o, g.ice1, g.ice2, [&](int i) { massck_row(a, i, k); }); });
+    walk(o, 1, kz, [&](int k) { massck_bdy_level(a, k); });
+  }
+  if (what & 2) walk(o, g.ice1, g.ice2, [&](int i) { ps_row(a, i); });
+  massck_final(a);
+  std::copy(a.out, a.out + 7, out7);
+  return 0;
+}
+int emu_b200_massck(void* h, double* out4) {
+  double o7[7];
+  if (emu_b200_massck7(h, 1, o7)) return 1;
+  std::copy(o7, o7 + 4, out4);
+  return 0;
+}
+int emu_b200_ps_check(void* h, double* maxmin, int32_t* nonfinite) {
+  double o7[7];
+  if (emu_b200_massck7(h, 2, o7)) return 1;
+  maxmin[0] = o7[4]; maxmin[1] = o7[5]; *nonfinite = (int32_t)o7[6];
+  return 0;
+}
 // TKE helpers = k_tke_destagger / k_tke_restagger / k_tke_update
 int emu_b200_tke_destagger(void* h) {
   Emu& e = *(Emu*)h; const Geo& g = e.g; const int o = e.order;

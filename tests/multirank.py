@@ -12,7 +12,7 @@ from regcm_b200.moloch import MolochB200
 
 
 class MultiRank:
-    def __init__(self, wl, px, py, fields, profiles, devices=None, transport="p2p"):
+    def __init__(self, wl, px, py, fields, profiles, devices=None, transport="p2p", bdy=None, boundary=None):
         self.wl, self.n = wl, px * py
         devices = devices or list(range(self.n))
         uid = MolochB200.comm_id() if (self.n > 1 and transport == "nccl") else None
@@ -23,7 +23,7 @@ class MultiRank:
 
         def boot(r):
             try:
-                m = MolochB200(wl, rank=r, nranks=self.n, px=px, py=py, device=devices[r]).allocate_moloch()
+                m = MolochB200(wl, rank=r, nranks=self.n, px=px, py=py, device=devices[r], bdy=bdy).allocate_moloch()
                 self.ranks[r] = m
                 if self.n > 1 and transport == "p2p":
                     blobs[r] = m.p2p_export()
@@ -35,6 +35,8 @@ class MultiRank:
                         m.p2p_connect(blobs)
                 bar.wait(timeout=120)
                 m.init_moloch(fields, profiles)
+                if boundary is not None:
+                    m.load_boundary(boundary)
             except Exception as e:  # noqa: BLE001
                 errs.append((r, e))
                 bar.abort()

@@ -135,3 +135,26 @@ def test_tke_cells_bit_exact(order):
     upd = np.maximum(back + wl.dt * ten, wl.tkemin)
     got = m.get_global("tke")
     assert np.array_equal(got, upd)      # doubly periodic: the interior is the whole domain
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_massck_and_ps_guard_cells(order):
+    """massck partial sums (row sums along j, rows added level by level) against
+    the oracle's single running sum: equal to rounding; max/min of ps exact."""
+    wl = S.small(LAM, 34, 30, 12, do_massck=1)
+    o, B = make_oracle_bdy(wl)
+    o.step(1)
+    m = make_emu(wl, o, B, order)
+    m.set_global("zetaf", o.get("zetaf"))
+    m.set_global("rho", o.get("rho"))
+    want, got = o.massck(), m.massck()
+    # masses: 1e-12; the boundary fluxes are differences of large in- and outflow sums: 1e-9
+    assert np.all(np.abs(got - want) <= np.array([1e-12, 1e-9, 1e-12, 1e-9]) * np.abs(want)), (got, want)
+    assert want[0] > 0 and want[2] > 0 and want[1] != 0.0
+    assert m.ps_check() == o.ps_check()
+    ps = o.get("ps")
+    ps[5, 7] = np.nan
+    ps[9, 3] = np.inf
+    m.set_global("ps", ps)
+    mx, mn, bad = m.ps_check()
+    assert bad == 2 and np.isfinite(mx) and np.isfinite(mn)

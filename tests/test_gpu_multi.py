@@ -9,7 +9,7 @@ from regcm_b200 import synthetic as S
 from regcm_b200.moloch import load_library
 
 from multirank import MultiRank
-from util import DIAGNOSTIC, PROGNOSTIC, make_oracle, oracle_inputs
+from util import DIAGNOSTIC, PROGNOSTIC, bdy_tables_from_oracle, make_oracle, make_oracle_bdy, oracle_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -60,5 +60,32 @@ def test_decomposed_bit_exact(name, wl, px, py, transport, monkeypatch):
                 if r.max() > 1e-13:
                     bad.append(f"{f}: rel {r.max():.3e}")
             assert not bad, f"after {n} more steps ({px}x{py}):\n" + "\n".join(bad)
+    finally:
+        mr.close()
+
+
+BDY = S.small(S.WORKLOADS["cordex25"], 46, 42, 12, ntr=2, nspgx=6, do_bdy=1, present_qc=1, present_qi=1,
+              mo_top_nudge=1, ichebdy=1, do_slice=1)
+
+
+@pytest.mark.parametrize("px,py", [(2, 1), (1, 2), (2, 2)])
+def test_decomposed_boundary_bit_exact(px, py):
+    """moloch() with the lateral boundary and mkslice on px x py GPUs: bdyval, the
+    relaxation and mkslice are rank-local; `boundary` adds one u/v halo round."""
+    if ndev() < px * py:
+        pytest.skip(f"needs {px * py} GPUs")
+    wl = BDY
+    o, B = make_oracle_bdy(wl)
+    fields, profiles = oracle_inputs(o, wl)
+    fields["zetaf"] = o.get("zetaf")
+    mr = MultiRank(wl, px, py, fields, profiles, bdy=bdy_tables_from_oracle(wl, o), boundary=B)
+    try:
+        o.step(3)
+        mr.call("moloch", 3)
+        bad = [f for f in PROGNOSTIC + ["trac"] if not np.array_equal(o.get(f), mr.get_global(f))]
+        assert not bad, bad
+        for f in ("pf3d", "th3d", "ps"):
+            a, b = o.get(f), mr.get_global(f)
+            assert (np.abs(a - b) <= 1e-13 * np.abs(a)).all(), f
     finally:
         mr.close()

@@ -121,3 +121,21 @@ def test_boundary_needs_configuration():
     with pytest.raises(MolochError, match="not configured"):
         m.mkslice()
     m.close()
+
+
+def test_massck_and_ps_guard():
+    wl = S.small(LAM, 44, 40, 14, do_massck=1)
+    o, B = make_oracle_bdy(wl)
+    m = make_gpu_bdy(wl, o, B)
+    m.set_global("zetaf", o.get("zetaf"))
+    o.step(2); m.moloch(2)
+    want, got = o.massck(), m.massck()
+    # masses: 1e-12; the boundary fluxes are differences of large in- and outflow sums: 1e-9
+    assert np.all(np.abs(got - want) <= np.array([1e-12, 1e-9, 1e-12, 1e-9]) * np.abs(want)), (got, want)
+    mo, mg = o.ps_check(), m.ps_check()
+    assert mg[2] == 0 and abs(mg[0] - mo[0]) <= 1e-13 * mo[0] and abs(mg[1] - mo[1]) <= 1e-13 * mo[1]
+    ps = o.get("ps")
+    ps[5, 7] = np.nan
+    m.set_global("ps", ps)
+    assert m.ps_check()[2] == 1
+    m.close()

@@ -297,3 +297,24 @@ def test_lehmann_coefficients():
     assert ((c > 0) & (c < 1)).all() and (np.diff(c) < 0).all()
     with pytest.raises(ValueError):
         S.relax_coefficients(6, 0.01, 0.9)
+
+
+def test_massck_known_answers():
+    """Dry-air mass = sum(dx^2 dz rho) over the interior: compare with NumPy; the
+    sums are decomposition invariant to rounding; a uniform inflow from the west
+    gives a positive boundary flux."""
+    wl = S.small(LAM, 34, 30, 12, do_massck=1)
+    o, _ = make_oracle_bdy(wl)
+    dry, dadv, wat, wadv = o.massck()
+    zf, rho, qx = o.get("zetaf"), o.get("rho"), o.get("qx")
+    dz = zf[:-1] - zf[1:]
+    inner = np.s_[:, 1:wl.iy - 2, 1:wl.jx - 2]
+    assert abs(dry - (wl.dx ** 2 * dz * rho)[inner].sum()) < 1e-11 * dry
+    assert abs(wat - sum((qx[n] * wl.dx ** 2 * dz * rho)[inner].sum() for n in range(wl.nqx))) < 1e-11 * wat
+    assert dadv != 0.0 and wadv != 0.0
+    b, _ = make_oracle_bdy(wl, px=2, py=2)
+    # the boundary fluxes are differences of large in- and outflow sums
+    assert np.all(np.abs(b.massck() - o.massck()) <= np.array([1e-12, 1e-9, 1e-12, 1e-9]) * np.abs(o.massck()))
+    mx, mn, bad = o.ps_check()
+    ps = o.get("ps")[1:wl.iy - 2, 1:wl.jx - 2]
+    assert (mx, mn, bad) == (ps.max(), ps.min(), 0)

@@ -1805,6 +1805,8 @@ long oracle_global_size(void* h, const char* name) {
   const long plane = (long)w.c.jx * w.c.iy;
   if (s == "rlat") return w.c.iy + 1;
   if (s == "fcx") return w.c.nspgx;
+  if (s == "bvx") return (long)w.bvx.size();
+  if (s == "bvy") return (long)w.bvy.size();
   if (s == "tnudge" || s == "cnudge" || s == "gmeanz") return w.c.kz;
   if (s == "hefc") return (long)w.c.nspgx * w.c.kz;
   if (s == "ffilt" || s == "xkdamp" || s == "xknu" || s == "gzitakh" || s == "zitah") return w.c.kz;
@@ -1860,6 +1862,8 @@ int oracle_get_global(void* h, const char* name, double* dst) {
   if (s == "cnudge" && !w.cnudge.empty()) return cp(w.cnudge, kz);
   if (s == "gmeanz" && !w.gmeanz.empty()) return cp(w.gmeanz, kz);
   if (s == "hefc") { std::copy(w.hefc.begin(), w.hefc.end(), dst); return 0; }
+  if (s == "bvx") { std::copy(w.bvx.begin(), w.bvx.end(), dst); return 0; }   // [2km][jx]
+  if (s == "bvy") { std::copy(w.bvy.begin(), w.bvy.end(), dst); return 0; }   // [2lm][iy]
   for (auto& r : w.r) {
     std::vector<FieldInfo> f;
     if (!lookup(w, r, s, f)) { g_err = "unknown field " + s; return 1; }

@@ -1,0 +1,527 @@
+"""Mechanical translator for the subset of free-form Fortran that RegCM's MOLOCH
+time step is written in  ->  Python source (TEST INFRASTRUCTURE).
+
+Purpose: the reference cannot be compiled in this environment (no Fortran
+compiler), so its own source files are *executed* instead: this module reads
+routines out of /root/reference/Main/*.F90 where they lie, translates them
+statement by statement -- no knowledge of what the code computes, only of the
+language -- and the result runs under CPython with IEEE doubles, Fortran's
+left-to-right evaluation of same-precedence operators and Fortran integer
+division.  The outputs pin the hand-written oracle (oracle/moloch_oracle.cpp):
+see oracle/refrun/run_moloch.py and tests/test_reference_pin.py.  Nothing of
+the reference is copied into the repository; translated sources only ever go
+to oracle/_ref/ (git-ignored) for inspection.
+
+Supported: subroutine / function (with result clause), declarations (parameter
+and save initialisers, local explicit-shape arrays), do concurrent, do with
+bounds and stride, do while, if / else if / else, one-line if, cycle, exit,
+return, call (incl. type-bound), assignments incl. whole-array sections,
+derived-type components (%), the usual intrinsics, cpp conditionals.
+Anything else becomes `raise NotImplementedError(<statement>)` at that point of
+the generated code, so it only matters if execution reaches it.
+"""
+from __future__ import annotations
+
+import ast
+import keyword
+import re
+
+TOKEN = re.compile(r"""
+    (?P<str>'[^']*'|"[^"]*")
+  | (?P<logic>\.(?:and|or|not|true|false|eq|ne|lt|le|gt|ge|eqv|neqv)\.)
+  | (?P<num>(?:\d+\.\d*|\.\d+|\d+)(?:[ed][+-]?\d+)?(?:_\w+)?)
+  | (?P<id>[a-z_]\w*)
+  | (?P<op>\*\*|==|/=|<=|>=|=>|//|[-+*/<>=(),:%\[\]])
+  | (?P<ws>\s+)
+""", re.X)
+
+LOGIC = {".and.": " and ", ".or.": " or ", ".not.": " not ", ".true.": "True", ".false.": "False", ".eq.": "==",
+         ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", ".eqv.": "==", ".neqv.": "!="}
+TYPE_BOUND_CALLS = {"act", "advance", "str", "start", "integrating", "lcount"}
+DECL = re.compile(r"^(real|integer|logical|character|type|class|double precision|complex)\b")
+
+
+def pyname(n: str) -> str:
+    return n + "_" if keyword.iskeyword(n) or n in ("print", "len", "id") else n
+
+
+def preprocess(text: str, defines=()) -> list[str]:
+    """cpp conditionals, comments, continuation lines, ';' -> list of logical statements (lower case)."""
+    lines, stack = [], []
+    for raw in text.splitlines():
+        s = raw.strip()
+        if s.startswith("#"):
+            d = s[1:].strip()
+            if d.startswith("ifdef"):
+                stack.append(d.split()[1] in defines)
+            elif d.startswith("ifndef"):
+                stack.append(d.split()[1] not in defines)
+            elif d.startswith("if "):
+                names = re.findall(r"defined\s*\(?\s*(\w+)", d)
+                stack.append(bool(names) and all(n in defines for n in names) and "!" not in d)
+            elif d.startswith("else"):
+                stack[-1] = not stack[-1]
+            elif d.startswith("endif"):
+                stack.pop()
+            continue
+        if all(stack):
+            lines.append(raw)
+    stmts, cur = [], ""
+    for raw in lines:
+        out, q = [], None
+        for ch in raw:           # strip comments outside strings
+            if q:
+                out.append(ch)
+                if ch == q:
+                    q = None
+            elif ch in "'\"":
+                q = ch
+                out.append(ch)
+            elif ch == "!":
+                break
+            else:
+                out.append(ch)
+        s = "".join(out).strip()
+        if not s:
+            continue
+        if cur and s.startswith("&"):
+            s = s[1:].lstrip()
+        if s.endswith("&"):
+            cur += s[:-1].rstrip() + " "
+            continue
+        cur += s
+        for part in split_top(cur, ";"):
+            part = part.strip()
+            if part:
+                stmts.append(lower_outside_strings(part))
+        cur = ""
+    return stmts
+
+
+def lower_outside_strings(s: str) -> str:
+    out, q = [], None
+    for ch in s:
+        if q:
+            out.append(ch)
+            if ch == q:
+                q = None
+        else:
+            if ch in "'\"":
+                q = ch
+            out.append(ch.lower())
+    return "".join(out)
+
+
+def split_top(s: str, sep: str) -> list[str]:
+    """Split at `sep` outside parentheses/brackets/strings."""
+    parts, depth, q, cur = [], 0, None, []
+    for ch in s:
+        if q:
+            cur.append(ch)
+            if ch == q:
+                q = None
+            continue
+        if ch in "'\"":
+            q = ch
+        elif ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == sep and depth == 0:
+            parts.append("".join(cur))
+            cur = []
+        else:
+            cur.append(ch)
+    parts.append("".join(cur))
+    return parts
+
+
+def match_paren(s: str, i: int) -> int:
+    """Index of the ')' matching the '(' at s[i]."""
+    depth, q = 0, None
+    for k in range(i, len(s)):
+        ch = s[k]
+        if q:
+            if ch == q:
+                q = None
+            continue
+        if ch in "'\"":
+            q = ch
+        elif ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+            if depth == 0:
+                return k
+    raise ValueError("unbalanced parentheses: " + s)
+
+
+class Expr:
+    """Fortran expression -> Python expression (token-wise; array references get brackets)."""
+
+    def __init__(self, arrays: set[str]):
+        self.arrays = arrays
+
+    def tokens(self, s: str):
+        pos, out = 0, []
+        while pos < len(s):
+            m = TOKEN.match(s, pos)
+            if not m:
+                raise ValueError(f"cannot tokenise {s[pos:pos + 20]!r} in {s!r}")
+            pos = m.end()
+            if m.lastgroup != "ws":
+                out.append((m.lastgroup, m.group()))
+        return out
+
+    def tr(self, s: str, lhs: bool = False) -> str:
+        toks = self.tokens(s)
+        out, i = self._seq(toks, 0, lhs)
+        if i != len(toks):
+            raise ValueError("trailing tokens in " + s)
+        return out
+
+    def _seq(self, toks, i, lhs=False, stop=()):
+        out = []
+        while i < len(toks):
+            kind, t = toks[i]
+            if kind == "op" and t in stop:
+                break
+            if kind == "str":
+                out.append(t)
+            elif kind == "logic":
+                out.append(LOGIC[t])
+            elif kind == "num":
+                t = re.sub(r"_\w+$", "", t)
+                out.append(t.replace("d", "e"))
+            elif kind == "id":
+                prev_pct = bool(out) and out[-1] == "."
+                name = t if prev_pct else pyname(t)
+                if i + 1 < len(toks) and toks[i + 1] == ("op", "("):
+                    inner, j = self._args(toks, i + 2)
+                    is_arr = (t in self.arrays and not prev_pct) or (prev_pct and t not in TYPE_BOUND_CALLS) or \
+                             (lhs and not out)
+                    if is_arr and t not in ("null",):
+                        out.append(f"{name}[{inner}]" if inner.strip() else f"{name}[...]")
+                    else:
+                        out.append(f"{name}({inner})")
+                    i = j
+                    continue
+                out.append(name)
+            else:
+                if t == "/=":
+                    out.append("!=")
+                elif t == "%":
+                    out.append(".")
+                elif t == "//":
+                    out.append("+")
+                elif t == "=>":
+                    out.append("=")
+                elif t == "(":
+                    inner, j = self._seq(toks, i + 1, stop=(")",))
+                    out.append("(" + inner + ")")
+                    i = j + 1
+                    continue
+                else:
+                    out.append(t)
+            i += 1
+        return " ".join(out).replace(" . ", ".").replace(" .", ".").replace(". ", "."), i
+
+    def _args(self, toks, i):
+        """Translate a parenthesised argument / subscript list starting after '('; returns (text, index after ')')."""
+        parts = []
+        while True:
+            inner, i = self._seq(toks, i, stop=(",", ")"))
+            parts.append(inner)
+            if toks[i][1] == ")":
+                return ", ".join(parts), i + 1
+            i += 1
+
+
+class Routine:
+    def __init__(self, name, kind, args, body, result=None):
+        self.name, self.kind, self.args, self.body, self.result = name, kind, args, body, result
+
+
+HEAD_SUB = re.compile(r"^(?:(?:pure|elemental|recursive)\s+)*subroutine\s+(\w+)\s*(?:\((.*)\))?\s*$")
+HEAD_FUN = re.compile(r"^(?:(?:pure|elemental|recursive)\s+)*(?:(?:real|integer|logical)\s*(?:\(\w+\))?\s+)?"
+                      r"function\s+(\w+)\s*\((.*?)\)\s*(?:result\s*\(\s*(\w+)\s*\))?\s*$")
+
+
+def find_routines(stmts: list[str]) -> dict[str, Routine]:
+    out, cur = {}, None
+    for s in stmts:
+        if cur is None:
+            m = HEAD_SUB.match(s)
+            if m:
+                cur = Routine(m.group(1), "subroutine", [a.strip() for a in (m.group(2) or "").split(",") if a.strip()], [])
+                continue
+            m = HEAD_FUN.match(s)
+            if m and not s.startswith("end"):
+                cur = Routine(m.group(1), "function", [a.strip() for a in m.group(2).split(",") if a.strip()], [],
+                              m.group(3) or m.group(1))
+                continue
+        else:
+            if re.match(r"^end\s*(subroutine|function)\b", s):
+                out[cur.name] = cur
+                cur = None
+            else:
+                cur.body.append(s)
+    return out
+
+
+def module_parameters(stmts: list[str], ex: Expr) -> list[str]:
+    """`parameter` declarations of the module specification part (before `contains`) as Python assignments."""
+    out = []
+    for s in stmts:
+        if s == "contains":
+            break
+        if DECL.match(s) and "::" in s and re.search(r"\bparameter\b", s.split("::")[0]):
+            spec, ents = s.split("::", 1)
+            if "dimension" in spec:
+                continue
+            for e in split_top(ents, ","):
+                if "=" in e:
+                    n, v = e.split("=", 1)
+                    v = ex.tr(v.strip())
+                    if re.match(r"^real\s*\(\s*rk4\s*\)", spec):
+                        v = f"_r4({v})"
+                    out.append(f"{pyname(n.strip())} = {v}")
+    return out
+
+
+class Translator:
+    def __init__(self, global_arrays: set[str]):
+        self.global_arrays = set(global_arrays)
+
+    def routine(self, r: Routine) -> str:
+        arrays = set(self.global_arrays)
+        local_names = set(r.args)
+        lines, ind = [], 1
+        blocks = []          # stack of ("do", nloops) / ("if", 1)
+        assigned = set()
+        saves = []
+        resname = r.result
+        if resname:
+            local_names.add(resname)
+        pre = []             # parameter / local array initialisers
+
+        def emit(t):
+            lines.append("    " * ind + t)
+
+        # ---- pass 1: declarations ------------------------------------------------------
+        body = []
+        for s in r.body:
+            if s == "contains":      # internal procedures follow (translated separately when needed)
+                break
+            if s.startswith(("implicit ", "use ", "intrinsic ", "external ", "data ")):
+                continue
+            if DECL.match(s) and "::" in s:
+                spec, ents = s.split("::", 1)
+                is_par = bool(re.search(r"\bparameter\b", spec))
+                is_save = bool(re.search(r"\bsave\b", spec))
+                dim = re.search(r"dimension\s*\((.*)\)", spec)
+                for e in split_top(ents, ","):
+                    e = e.strip()
+                    m = re.match(r"^(\w+)\s*(\(.*?\))?\s*(?:(=>|=)\s*(.*))?$", e)
+                    if not m:
+                        continue
+                    n, shape, _, init = m.group(1), m.group(2), m.group(3), m.group(4)
+                    local_names.add(n)
+                    if dim or shape:
+                        arrays.add(n)
+                    if n in r.args:
+                        continue
+                    ex = Expr(arrays)
+                    if is_par and init is not None:
+                        v = ex.tr(init)
+                        if re.match(r"^real\s*\(\s*rk4\s*\)", spec):
+                            v = f"_r4({v})"
+                        pre.append(f"{pyname(n)} = {v}")
+                    elif is_save:
+                        saves.append((n, ex.tr(init) if init and init != "null( )" and "null" not in init else "None"))
+                    elif (dim or shape) and "pointer" not in spec and "allocatable" not in spec:
+                        d = (shape[1:-1] if shape else dim.group(1))
+                        if ":" not in d.replace(" ", "").strip(":") or re.search(r"\w", d):
+                            bnds = []
+                            ok = True
+                            for one in split_top(d, ","):
+                                one = one.strip()
+                                if one == ":":
+                                    ok = False
+                                    break
+                                lo, hi = (one.split(":") + [None])[:2] if ":" in one else ("1", one)
+                                bnds.append(f"({ex.tr(lo)}, {ex.tr(hi)})")
+                            if ok:
+                                kind = "int" if spec.startswith("integer") else "float"
+                                pre.append(f"{pyname(n)} = _alloc([{', '.join(bnds)}], {kind!r})")
+                continue
+            body.append(s)
+        ex = Expr(arrays)
+        for n, _ in saves:
+            local_names.discard(n)
+
+        # ---- pass 2: executable statements ---------------------------------------------
+        def stmt(s):
+            nonlocal ind
+            m = re.match(r"^do\s+concurrent\s*\(", s)
+            if m:
+                close = match_paren(s, m.end() - 1)
+                specs = split_top(s[m.end():close], ",")
+                loops = []
+                for sp in specs:
+                    if "=" not in sp:
+                        raise ValueError("mask in do concurrent: " + s)
+                    var, rng = sp.split("=", 1)
+                    rr = split_top(rng, ":")
+                    loops.append((pyname(var.strip()), [ex.tr(x.strip()) for x in rr]))
+                    assigned.add(var.strip())
+                for var, rr in reversed(loops):     # last index outermost (any order is valid)
+                    emit(f"for {var} in _frange({', '.join(rr)}):")
+                    ind += 1
+                blocks.append(("do", len(loops)))
+                return
+            m = re.match(r"^do\s+while\s*\(", s)
+            if m:
+                close = match_paren(s, m.end() - 1)
+                emit(f"while {ex.tr(s[m.end():close])}:")
+                ind += 1
+                blocks.append(("do", 1))
+                return
+            m = re.match(r"^do\s+(\w+)\s*=\s*(.*)$", s)
+            if m:
+                rr = [ex.tr(x.strip()) for x in split_top(m.group(2), ",")]
+                assigned.add(m.group(1))
+                emit(f"for {pyname(m.group(1))} in _frange({', '.join(rr)}):")
+                ind += 1
+                blocks.append(("do", 1))
+                return
+            if s == "do":
+                emit("while True:")
+                ind += 1
+                blocks.append(("do", 1))
+                return
+            if re.match(r"^end\s*do\b", s):
+                kind, n = blocks.pop()
+                emit("pass")
+                ind -= n
+                return
+            m = re.match(r"^(else\s*)?if\s*\(", s)
+            if m:
+                close = match_paren(s, m.end() - 1)
+                cond = ex.tr(s[m.end():close])
+                rest = s[close + 1:].strip()
+                if rest == "then":
+                    if m.group(1):
+                        emit("pass")
+                        ind -= 1
+                        emit(f"elif {cond}:")
+                        ind += 1
+                    else:
+                        emit(f"if {cond}:")
+                        ind += 1
+                        blocks.append(("if", 1))
+                else:
+                    emit(f"if {cond}:")
+                    ind += 1
+                    stmt(rest)
+                    ind -= 1
+                return
+            if s == "else":
+                emit("pass")
+                ind -= 1
+                emit("else:")
+                ind += 1
+                return
+            if re.match(r"^end\s*if\b", s):
+                blocks.pop()
+                emit("pass")
+                ind -= 1
+                return
+            if s == "cycle":
+                emit("continue")
+                return
+            if s == "exit":
+                emit("break")
+                return
+            if s == "return":
+                emit(f"return {pyname(resname)}" if r.kind == "function" else "return")
+                return
+            if s.startswith(("write", "print", "flush", "!", "allocate", "deallocate")) or s == "continue":
+                emit("pass")
+                return
+            m = re.match(r"^call\s+([\w%]+)\s*(?:\((.*)\))?\s*$", s)
+            if m:
+                name, args = m.group(1), m.group(2) or ""
+                if name == "assignpnt":
+                    a = [x.strip() for x in split_top(args, ",")]
+                    tgt = a[1]
+                    if re.match(r"^\w+$", tgt):
+                        assigned.add(tgt)
+                    extra = (", " + ex.tr(a[2])) if len(a) > 2 else ""
+                    emit(f"{ex.tr(tgt, lhs=True)} = _assignpnt({ex.tr(a[0])}{extra})")
+                    return
+                targs = ", ".join(ex.tr(x.strip()) for x in split_top(args, ",") if x.strip())
+                emit(f"{'.'.join(pyname(p) for p in name.split('%'))}({targs})")
+                return
+            # assignment: first top-level '=' that is not part of ==, <=, >=, /=
+            depth, q, pos = 0, None, -1
+            for k, ch in enumerate(s):
+                if q:
+                    if ch == q:
+                        q = None
+                    continue
+                if ch in "'\"":
+                    q = ch
+                elif ch == "(":
+                    depth += 1
+                elif ch == ")":
+                    depth -= 1
+                elif ch == "=" and depth == 0:
+                    if s[k + 1:k + 2] == "=" or s[k - 1:k] in "<>/=":
+                        continue
+                    pos = k
+                    break
+            if pos > 0:
+                lhs, rhs = s[:pos].strip(), s[pos + 1:].strip()
+                if rhs.startswith(">"):
+                    rhs = rhs[1:].strip()      # pointer assignment =>
+                if re.match(r"^\w+$", lhs):
+                    assigned.add(lhs)
+                emit(f"{ex.tr(lhs, lhs=True)} = {ex.tr(rhs)}")
+                return
+            emit(f"raise NotImplementedError({s!r})")
+
+        for s in body:
+            try:
+                stmt(s)
+            except Exception as e:  # noqa: BLE001  -- untranslatable: only matters if reached
+                emit(f"raise NotImplementedError({(s + ' :: ' + str(e))!r})")
+        if r.kind == "function":
+            emit(f"return {pyname(resname)}")
+        globs = sorted(pyname(n) for n in assigned if n not in local_names) + [pyname(n) for n, _ in saves]
+        head = [f"def {pyname(r.name)}({', '.join(pyname(a) for a in r.args)}):"]
+        if globs:
+            head.append("    global " + ", ".join(sorted(set(globs))))
+        head += ["    " + p for p in pre]
+        if not lines and not pre:
+            lines = ["    pass"]
+        src = "\n".join(head + lines) + "\n"
+        src = "".join(f"{pyname(n)} = {v}\n" for n, v in saves) + src
+        return src
+
+
+class _Div(ast.NodeTransformer):
+    """a / b -> _div(a, b): Fortran integer division when both operands are integers."""
+
+    def visit_BinOp(self, node):
+        self.generic_visit(node)
+        if isinstance(node.op, ast.Div):
+            return ast.copy_location(ast.Call(func=ast.Name(id="_div", ctx=ast.Load()), args=[node.left, node.right],
+                                              keywords=[]), node)
+        return node
+
+
+def compile_source(src: str, filename: str):
+    tree = _Div().visit(ast.parse(src, filename))
+    ast.fix_missing_locations(tree)
+    return compile(tree, filename, "exec")

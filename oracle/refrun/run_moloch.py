@@ -1,0 +1,434 @@
+"""Execute the reference's own MOLOCH time-step source (TEST INFRASTRUCTURE).
+
+`ReferenceRun` reads the routines of the hot path out of the reference tree
+where they lie --
+
+    Main/mod_moloch.F90     moloch, reset_tendencies, dynamical_core, sound, divergence_damping,
+                            divergence_diffusion, advection, wafone, local_flow_param, zstagtoh, htozstag,
+                            uvstagtouvx, uvxtouvstag, tvirt_to_temp, temp_to_tvirt,
+                            extrapolate_surface_pressure, status_update, boundary
+    Main/mod_bdycod.F90     bdyval, morelax_external, morelax_fraction, motopnudge, mospectral_nudge,
+                            lowpass_filter
+    Main/chemlib/mod_che_bdyco.F90   chem_bdyval_uncoupled, morelax_chiten
+    Main/mod_slice.F90      mkslice
+    Share/pfwsat.inc        pfwsat
+    Share/mod_constants.F90, Main/mpplib/mod_runparams.F90   parameters
+
+-- translates them mechanically (fortran_subset.py) and runs them on the state
+of one MPI rank that owns the whole domain (nproc = 1).  What is NOT reference
+code here: the allocation of the arrays (bounds restated from
+Main/mod_atm_interface.F90:579-624 and Main/mod_moloch.F90:159-199), the
+single-rank halo exchange (a periodic copy or nothing, which is what
+exchange_lr/_bt/_lrbt reduce to for one rank), the namelist scalars, and stubs
+for the driver's bookkeeping (timer, zenith angle, reports).  The static
+fields and the initial state are INPUTS, taken from the same arrays the oracle
+and the CUDA library are initialised with.
+
+    python -m oracle.refrun.run_moloch            # regenerate tests/golden/reference_*.json
+
+Only tests/ may import this module; it needs /root/reference at run time.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+from . import fortran_subset as F
+from .runtime import INTRINSICS, FArr
+
+REF = os.environ.get("REGCM_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+SOURCES = {
+    "Main/mod_moloch.F90": ["moloch", "reset_tendencies", "dynamical_core", "sound", "divergence_damping",
+                            "divergence_diffusion", "advection", "wafone", "local_flow_param", "zstagtoh", "htozstag",
+                            "uvstagtouvx", "uvxtouvstag", "tvirt_to_temp", "temp_to_tvirt",
+                            "extrapolate_surface_pressure", "status_update", "boundary"],
+    "Main/mod_bdycod.F90": ["bdyval", "morelax_external", "morelax_fraction", "motopnudge", "mospectral_nudge",
+                            "lowpass_filter"],
+    "Main/chemlib/mod_che_bdyco.F90": ["chem_bdyval_uncoupled", "morelax_chiten"],
+    "Main/mod_slice.F90": ["mkslice"],
+}
+
+
+def available() -> bool:
+    return os.path.exists(os.path.join(REF, "Main", "mod_moloch.F90"))
+
+
+class _Obj(types.SimpleNamespace):
+    pass
+
+
+class ReferenceRun:
+    """One rank owning the whole domain, state held in Fortran-bounded arrays."""
+
+    def __init__(self, wl, oracle, boundary: dict | None = None, dump_dir: str | None = None):
+        from regcm_b200 import hostmodel as H
+        from regcm_b200.decomp import make_geom
+        self.wl, self.H = wl, H
+        g = self.g = make_geom(wl.jx, wl.iy, wl.kz, wl.i_band, wl.i_crm, 1, 1, 0)
+        ns = self.ns = dict(INTRINSICS)
+        # ---- parameters straight from the reference's modules --------------------------------
+        ex = F.Expr(set())
+        for rel in ("Share/mod_constants.F90", "Main/mpplib/mod_runparams.F90", "Main/mod_moloch.F90"):
+            st = F.preprocess(open(os.path.join(REF, rel)).read())
+            for line in F.module_parameters(st, ex):
+                try:
+                    exec(F.compile_source(line, rel), ns)
+                except Exception:       # a parameter that needs something outside the subset: not used by the path
+                    pass
+        # ---- index ranges (setup_model_indexes) and namelist scalars -------------------------------
+        kz = wl.kz
+        for n in ("jde1", "jde2", "ide1", "ide2", "jdi1", "jdi2", "idi1", "idi2",
+                  "jce1", "jce2", "ice1", "ice2", "jci1", "jci2", "ici1", "ici2"):
+            ns[n] = getattr(g, n)
+        # Main/mod_atm_interface.F90:300-330
+        ns.update(jdii1=g.jde1 + (2 if g.bl else 0), jdii2=g.jde2 - (2 if g.br else 0),
+                  idii1=g.ide1 + (2 if g.bb else 0), idii2=g.ide2 - (2 if g.bt else 0))
+        gl, gr, gb, gt = g.gl, g.gr, g.gb, g.gt
+        # the ga/gb/gc ranges: widened by 1/2/3 points where a neighbour exists (Main/mod_atm_interface.F90:332-382)
+        for base in ("jce", "jci", "jde", "jdi"):
+            for w_, suf in ((1, "ga"), (2, "gb"), (3, "gc")):
+                ns[f"{base}1{suf}"] = ns[base + "1"] - w_ * gl
+                ns[f"{base}2{suf}"] = ns[base + "2"] + w_ * gr
+        for base in ("ice", "ici", "ide", "idi"):
+            for w_, suf in ((1, "ga"), (2, "gb"), (3, "gc")):
+                ns[f"{base}1{suf}"] = ns[base + "1"] - w_ * gb
+                ns[f"{base}2{suf}"] = ns[base + "2"] + w_ * gt
+        crm = wl.i_crm == 1
+        band = wl.i_band == 1 or crm
+        jcross2, icross2 = (wl.jx if band else wl.jx - 1), (wl.iy if crm else wl.iy - 1)
+        ns.update(jmin=1, jmax=jcross2, imin=1, imax=icross2)                 # Main/mod_moloch.F90:280-293
+        if band:
+            ns.update(jmin=-1, jmax=jcross2 + 2)
+        if crm:
+            ns.update(imin=-1, imax=icross2 + 2)
+        ns.update(kz=kz, kzp1=kz + 1, kzm1=kz - 1, jx=wl.jx, iy=wl.iy, nqx=wl.nqx, ntr=wl.ntr, iqfrst=2,
+                  ipptls=wl.ipptls, ibltyp=wl.ibltyp, ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, idiag=0, ichdiag=0,
+                  idynamic=3, mo_nadv=wl.mo_nadv, mo_nsound=wl.mo_nsound, dtsec=wl.dt, dt=wl.dt, rdt=1.0 / wl.dt,
+                  dx=wl.dx, rdx=1.0 / wl.dx, lrotllr=bool(wl.lrotllr), do_divdamp=bool(wl.mo_divdamp),
+                  do_divfilter=bool(wl.mo_divfilter), do_apply_bdy=bool(wl.do_bdy), moloch_realcase=False,
+                  mo_top_nudge=bool(wl.mo_top_nudge), mo_spectral_nudge=bool(wl.mo_spectral_nudge),
+                  present_qc=bool(wl.present_qc), present_qi=bool(wl.present_qi), dtbdys=wl.dtbdys, dtrad=wl.dtrad,
+                  rtb=1.0 / wl.dtbdys, xbctime=0.0, tkemin=wl.tkemin, rhmin=wl.rhmin, rhmax=wl.rhmax,
+                  icldmstrat=wl.icldmstrat, debug_level=0, islab_ocean=0, myid=0, italk=0, nspgx=wl.nspgx,
+                  mo_h=wl.mo_h, iconvec=0, total_precip_points=0, xslabtime=0.0, icup=FArr.alloc([(1, 2)], "int"))
+        mo_dzita = wl.mo_ztop / float(kz)            # zita(kz), Main/mod_params.F90:2461-2463
+        ns.update(mo_dzita=mo_dzita, rdzita=1.0 / mo_dzita)                    # Main/mod_moloch.F90:275
+        ns["dtstepa"] = wl.dt / float(wl.mo_nadv)                              # :306
+        ns["dtsound"] = ns["dtstepa"] / float(wl.mo_nsound)                    # :307
+        ns["ma"] = _Obj(has_bdyleft=g.bl, has_bdyright=g.br, has_bdybottom=g.bb, has_bdytop=g.bt,
+                        bandflag=band, crmflag=crm)
+        ns["syncro_rep"] = _Obj(act=lambda: False)
+        ns["rcmtimer"] = _Obj(advance=lambda: None, integrating=lambda: True, str=lambda: "")
+        ns["zenitm"] = lambda *a: None
+        ns["massck"] = lambda: None
+        ns["physical_parametrizations"] = lambda: None
+        ns["is_present_qc"] = lambda: bool(wl.present_qc)
+        ns["is_present_qi"] = lambda: bool(wl.present_qi)
+        for n in ("xlat", "xlon", "coszrs"):
+            ns[n] = None
+        dbx = g.ext("dot", 0, 0)
+        ns["mddom"] = _Obj(ldmsk=FArr(np.ones((dbx[3] - dbx[2] + 1, dbx[1] - dbx[0] + 1), dtype=np.int64),
+                                      [dbx[0], dbx[2]]))       # land everywhere: the SST update of bdyval is a no-op
+        ns.update(lakemod=0, iocncpl=0, iwavcpl=0)
+        # ---- arrays: allocate_atmosphere + allocate_moloch bounds, filled from the oracle -----------
+        self.arr = {}
+
+        def from_oracle(name, oname=None, spec=None):
+            stag, gj, gi, lv = spec or H.ALLOC[name]
+            box = g.ext(stag, gj, gi)
+            a = np.array(H.cut(oracle.get(oname or name), g, box), dtype=np.float64)
+            lb = [box[0], box[2]] + ([1] if a.ndim >= 3 else []) + ([1] if a.ndim == 4 else [])
+            if a.ndim == 4:          # species-major (n,k,i,j) is already the reversed (j,i,k,n)
+                pass
+            self.arr[name] = ns[name] = FArr(a, lb)
+            return ns[name]
+
+        for n in ("u", "v", "ux", "vx", "w", "pai", "tetav", "t", "qx", "tvirt", "p", "rho", "fmz", "fmzf", "rfmzu",
+                  "rfmzv", "hx", "hy", "coru", "corv", "bdywtu", "bdywtv", "bdywtw", "ps"):
+            from_oracle(n)
+        from_oracle("z", "zeta", H.ALLOC["zeta"])
+        from_oracle("qsat")
+        ns["mo_atm"] = _Obj()
+        from_oracle("zetaf", "zetaf", ("cross", 0, 0, "kzp1"))
+        for n, on in (("mx", "msfx"), ("mu", "msfu"), ("mv", "msfv"), ("mx2", "mx2"), ("rmx", "rmx"), ("rmu", "rmu"),
+                      ("rmv", "rmv")):
+            from_oracle(n, on, ("dot", 1, 1, 1))
+        if wl.ntr > 0:
+            from_oracle("trac")
+        for n in ("gzitak", "gzitakh", "xkdamp", "xknu", "ffilt"):
+            self.arr[n] = ns[n] = FArr(np.array(oracle.get(n), dtype=np.float64), [1])
+        rl = np.zeros(wl.iy + 1)
+        if wl.lrotllr:
+            from regcm_b200 import synthetic as S
+            rl = np.asarray(S.make_primary(wl)["rlat"], dtype=np.float64)
+        ns["rlat"] = FArr(rl, [1])
+
+        def zeros(name, stag, gj, gi, k1, k2, nspec=0):
+            box = g.ext(stag, gj, gi)
+            bnds = [(box[0], box[1]), (box[2], box[3])] + ([(k1, k2)] if k2 >= k1 else []) + \
+                   ([(1, nspec)] if nspec else [])
+            self.arr[name] = ns[name] = FArr.alloc(bnds)
+            return ns[name]
+
+        # allocate_moloch (Main/mod_moloch.F90:159-199) and the tendencies (mod_atm_interface.F90:605-618)
+        zeros("s", "cross", 0, 0, 1, kz + 1); zeros("wwkw", "cross", 0, 0, 2, kz + 1)
+        zeros("tetavf", "cross", 0, 0, 2, kz); zeros("zdiv2", "cross", 1, 1, 1, kz)
+        zeros("wz", "cross", 2, 2, 1, kz); zeros("p0", "cross", 2, 2, 1, kz); zeros("wfw", "cross", 0, 0, 1, kz + 1)
+        zeros("wx", "cross", 1, 1, 1, kz); zeros("laplacian", "cross", 0, 0, 1, kz)
+        zeros("ud", "u", 0, 0, 1, kz); zeros("vd", "v", 0, 0, 1, kz)
+        ns["zpby"] = FArr.alloc([(g.jce1, g.jce2), (g.ici1, g.ice2 + gt), (1, kz)])
+        ns["zpbw"] = FArr.alloc([(g.jci1, g.jce2 + gr), (g.ice1, g.ice2), (1, kz)])
+        for n in ("tten", "uten", "vten", "cldfra", "cldlwc"):    # cldfra/cldlwc: physics arrays reset_tendencies clears too
+            zeros(n, "cross", 0, 0, 1, kz)
+        zeros("qxten", "cross", 0, 0, 1, kz, wl.nqx)
+        if wl.ntr > 0:
+            zeros("chiten", "cross", 0, 0, 1, kz, wl.ntr)
+        ns["qv"] = ns["qx"].view_last(1); ns["qvten"] = ns["qxten"].view_last(1)
+        if wl.ipptls > 0:
+            ns["qc"] = ns["qx"].view_last(2)
+            if wl.ipptls > 1:
+                ns["qi"], ns["qr"], ns["qs"] = (ns["qx"].view_last(n) for n in (3, 4, 5))
+        if wl.ibltyp == 2:
+            from_oracle("tke"); zeros("tketen", "cross", 0, 0, 1, kz + 1); zeros("tkex", "cross", 0, 0, 1, kz)
+        # mo_atm%*, sfs%*, atms%* aliases used by bdyval / mkslice / morelax
+        mo = ns["mo_atm"]
+        for n in ("u", "v", "w", "t", "pai", "qx", "zetaf"):
+            setattr(mo, n, ns[n])
+        mo.zeta = ns["z"]
+        mo.tke = ns.get("tke")
+        ns["sfs"] = _Obj(psa=ns["ps"], psb=ns["ps"])
+        ns["chemt"] = ns.get("trac")
+        # ---- lateral boundary ---------------------------------------------------------------------------
+        if wl.do_bdy:
+            B = boundary or {}
+            pairs = {"dub": ("dub0", "dub1", "u"), "dvb": ("dvb0", "dvb1", "v"), "xtb": ("xtb0", "xtb1", "t"),
+                     "xpaib": ("xpaib0", "xpaib1", "pai"), "xqb": ("xqb0", "xqb1", "qx1"),
+                     "xlb": ("xlb0", "xlb1", "qx1"), "xib": ("xib0", "xib1", "qx1"), "xpsb": ("xpsb0", "xpsb1", "ps")}
+            for name, (k0, k1, _) in pairs.items():
+                stag = "u" if name == "dub" else "v" if name == "dvb" else "cross"
+                box = g.ext(stag, 0, 0)
+                o = _Obj()
+                for key, attr in ((k0, "b0"), (k1, "b1")):
+                    a = np.array(H.cut(np.asarray(B[key]), g, box), dtype=np.float64)
+                    setattr(o, attr, FArr(a, [box[0], box[2]] + ([1] if a.ndim == 3 else [])))
+                ns[name] = o
+            if wl.ntr > 0 and wl.ichebdy != 0:
+                box = g.ext("cross", 0, 0)
+                for key in ("chib0", "chib1"):
+                    ns[key] = FArr(np.array(H.cut(np.asarray(B[key]), g, box), dtype=np.float64), [box[0], box[2], 1, 1])
+            from regcm_b200 import synthetic as S
+            T = S.bdycon_setup(wl, oracle.get("zeta"))
+            dbox = g.ext("dot", 0, 0)
+            for which, nm in (("cr", "ba_cr"), ("ud", "ba_ud"), ("vd", "ba_vd")):
+                ib = np.array(H.cut(T["ibnd"][which], g, dbox), dtype=np.int64)
+                ns[nm] = _Obj(ibnd=FArr(ib, [dbox[0], dbox[2]]), havebound=bool((ib > 0).any()))
+            cb = ns["ba_cr"].ibnd.a > 0
+            ns["cba"] = _Obj(ibnd=ns["ba_cr"].ibnd, havebound=bool(cb.any()), ns=1, nn=0, nw=0, ne=0,
+                             bsouth=_Mask(cb, dbox), bnorth=_Mask(cb & False, dbox), bwest=_Mask(cb & False, dbox),
+                             beast=_Mask(cb & False, dbox))
+            if wl.nspgx > 0:
+                ns["hefc"] = FArr(np.array(oracle.get("hefc"), dtype=np.float64).reshape(kz, wl.nspgx), [1, 1])
+                ns["fcx"] = FArr(np.asarray(S.chem_fcx(wl), dtype=np.float64), [1])
+            if wl.mo_spectral_nudge:
+                # lowpass_init's tables (Main/mod_bdycod.F90:3844-3896) are inputs, same bits as the oracle's;
+                # the work arrays are allocated as there (:422, :3868-3873)
+                km, lm = oracle.get_int("km"), oracle.get_int("lm")
+                ns.update(km=km, lm=lm)
+                ns["bvx"] = FArr(np.array(oracle.get("bvx")).reshape(2 * km, wl.jx)[:, g.jde1 - 1:g.jde2].copy(), [g.jde1, 1])
+                ns["bvy"] = FArr(np.array(oracle.get("bvy")).reshape(2 * lm, wl.iy)[:, g.ide1 - 1:g.ide2].copy(), [g.ide1, 1])
+                ns["cnudge"] = FArr(np.array(oracle.get("cnudge"), dtype=np.float64), [1])
+                ns["zn1"] = FArr.alloc([(g.jde1, g.jde2), (g.ide1, g.ide2)])
+                for n in ("sx", "sxg"):
+                    ns[n] = FArr.alloc([(g.ide1, g.ide2), (1, 2 * km)])
+                for n in ("sy", "syg"):
+                    ns[n] = FArr.alloc([(g.jde1, g.jde2), (1, 2 * lm)])
+
+                def reduce1(m, gl_, a1, a2):
+                    # MPI_Allreduce(m, g, nk*(a2-a1+1), SUM) on a communicator of one rank
+                    # (Main/mpplib/mod_mppparam.F90:20620-20664): copies the first `count`
+                    # elements of the contiguous array
+                    count = m.a.shape[0] * (a2 - a1 + 1)
+                    gl_.a.reshape(-1)[:count] = m.a.reshape(-1)[:count]
+                ns["row_reduce"] = reduce1
+                ns["column_reduce"] = reduce1
+            ns["tnudge"] = FArr(np.array(oracle.get("tnudge"), dtype=np.float64), [1])
+            ns["nztop"] = oracle.get_int("nztop")
+            ns["xbctime"] = oracle.get_xbctime()
+        # mkslice targets
+        ns["atms"] = _Obj(ps2d=ns["ps"], rhob3d=ns["rho"], zq=ns["zetaf"], tb3d=ns["t"], pb3d=ns["p"],
+                          qxb3d=ns["qx"], qsb3d=ns["qsat"], chib3d=ns.get("trac"))
+        at = ns["atms"]
+        at.pf3d = FArr.alloc([(g.jce1, g.jce2), (g.ice1, g.ice2), (1, kz + 1)])
+        at.th3d = FArr.alloc([(g.jce1, g.jce2), (g.ice1, g.ice2), (1, kz)])
+        for n in ("rhb3d", "wpx3d"):
+            setattr(at, n, FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2), (1, kz)]))
+        for n in ("rhox2d", "tp2d", "th700"):
+            setattr(at, n, FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2)]))
+        # the common tail of mkslice (tropopause and PBL-top indices for the physics, Main/mod_slice.F90:342-384)
+        # runs too; its latitude/calendar inputs are not part of this path: irceideal = 1 skips the ptrop formula
+        at.za = ns["z"]
+        ns.update(irceideal=1, ptrop=FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2)]),
+                  ktrop=FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2)], "int"),
+                  kmxpbl=FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2)], "int"))
+        # ---- the single-rank halo exchange --------------------------------------------------------------------
+        ns["exchange_lr"] = lambda a, nex, j1, j2, i1, i2, *k: self._exchange(a, nex, j1, j2, i1, i2, True, False)
+        ns["exchange_bt"] = lambda a, nex, j1, j2, i1, i2, *k: self._exchange(a, nex, j1, j2, i1, i2, False, True)
+        ns["exchange_lrbt"] = lambda a, nex, j1, j2, i1, i2, *k: self._exchange(a, nex, j1, j2, i1, i2, True, True)
+        ns["morelax"] = lambda j1, j2, i1, i2, ba, f, x: (
+            ns["morelax_fraction"](j1, j2, i1, i2, ba, f, x) if isinstance(x, float)
+            else ns["morelax_external"](j1, j2, i1, i2, ba, f, x))      # interface morelax, Main/mod_bdycod.F90:124-127
+        ns["chem_bdyval"] = lambda u, v: ns["chem_bdyval_uncoupled"](u, v)   # interface, mod_che_bdyco.F90:75-78
+        # ---- translate and load the reference routines ---------------------------------------------------------
+        arrays = {k for k, v in ns.items() if isinstance(v, FArr)}
+        arrays |= {"qc", "qi", "qr", "qs", "tke", "tkex", "tketen", "trac", "chiten", "chemt", "chib0", "chib1",
+                   "hefc", "fcx", "tnudge", "cnudge", "qxzeroval", "qxcheckval", "ten0", "qen0", "chiten0"}
+        tr = F.Translator(arrays)
+        self.sources = {}
+        pf = F.find_routines(F.preprocess(open(os.path.join(REF, "Share/pfwsat.inc")).read()))
+        todo = [("Share/pfwsat.inc", pf, ["pfwsat"])]
+        for rel, names in SOURCES.items():
+            todo.append((rel, F.find_routines(F.preprocess(open(os.path.join(REF, rel)).read())), names))
+        for rel, routines, names in todo:
+            for n in names:
+                src = tr.routine(routines[n])
+                self.sources[n] = src
+                exec(F.compile_source(src, f"<{rel}:{n}>"), ns)
+        # the array-valued parameters of mod_runparams (:184-192) are outside the translator's subset
+        ns["qxcheckval"] = FArr(np.array([1.0e-8, 1.0e-16, 1.0e-16, 1.0e-16, 1.0e-16, 1.0e-16, 1.0e-16, 1.0e10,
+                                          100.0, 0.01]), [1])
+        ns["qxzeroval"] = FArr(np.array([1.0e-8, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0e10, 100.0, 0.01]), [1])
+        if dump_dir:
+            os.makedirs(dump_dir, exist_ok=True)
+            for n, src in self.sources.items():
+                open(os.path.join(dump_dir, n + ".py"), "w").write(src)
+
+    # exchange_lr/_bt/_lrbt for one rank: the rank is its own neighbour in a periodic
+    # direction (mod_mppparam.F90:3809-3878 with ma%left == myid), otherwise nothing happens
+    def _exchange(self, a, nex, j1, j2, i1, i2, lr, bt):
+        wl = self.wl
+        band = wl.i_band == 1 or wl.i_crm == 1
+        crm = wl.i_crm == 1
+        if a.nd == 2:
+            views = [a.a[None]]
+        elif a.nd == 3:
+            views = [a.a]
+        else:
+            views = [a.a[n] for n in range(a.a.shape[0])]
+        jl, il = a.lb[0], a.lb[1]
+        for v in views:
+            if lr and band:
+                for x in range(1, nex + 1):
+                    v[:, i1 - il:i2 - il + 1, j1 - x - jl] = v[:, i1 - il:i2 - il + 1, j2 - (x - 1) - jl]
+                    v[:, i1 - il:i2 - il + 1, j2 + x - jl] = v[:, i1 - il:i2 - il + 1, j1 + (x - 1) - jl]
+            if bt and crm:
+                for x in range(1, nex + 1):
+                    v[:, i1 - x - il, j1 - jl:j2 - jl + 1] = v[:, i2 - (x - 1) - il, j1 - jl:j2 - jl + 1]
+                    v[:, i2 + x - il, j1 - jl:j2 - jl + 1] = v[:, i1 + (x - 1) - il, j1 - jl:j2 - jl + 1]
+
+    # ---- driving it -------------------------------------------------------------------------------------------
+    def call(self, name, *args):
+        return self.ns[name](*args)
+
+    def step(self, n=1):
+        for _ in range(n):
+            self.ns["moloch"]()
+
+    def get(self, name) -> np.ndarray:
+        """Owned cells on the global grid, like Oracle.get."""
+        wl, g, H = self.wl, self.g, self.H
+        ns = self.ns
+        a = {"zeta": ns["z"], "pf3d": ns["atms"].pf3d, "th3d": ns["atms"].th3d, "rhb3d": ns["atms"].rhb3d,
+             "wpx3d": ns["atms"].wpx3d, "rhox2d": ns["atms"].rhox2d, "tp2d": ns["atms"].tp2d,
+             "th700": ns["atms"].th700}.get(name) or ns[name]
+        stag = H.ALLOC[name][0] if name in H.ALLOC else "cross"
+        own = g.ext(stag, 0, 0)
+        b = a.bounds()
+        j1, j2, i1, i2 = max(own[0], b[0][0]), min(own[1], b[0][1]), max(own[2], b[1][0]), min(own[3], b[1][1])
+        lead = a.a.shape[:-2]
+        out = np.zeros(lead + (wl.iy, wl.jx))
+        out[..., i1 - 1:i2, j1 - 1:j2] = a.a[..., i1 - b[1][0]:i2 - b[1][0] + 1, j1 - b[0][0]:j2 - b[0][0] + 1]
+        return out
+
+
+class _Mask:
+    """logical(j,i) array of cbound_area (bsouth ...): Fortran-bounded boolean lookup."""
+
+    def __init__(self, m, box):
+        self.m, self.j0, self.i0 = m, box[0], box[2]
+
+    def __getitem__(self, idx):
+        return bool(self.m[idx[1] - self.i0, idx[0] - self.j0])
+
+    def __call__(self, j, i):
+        return self[j, i]
+
+
+# ---- golden fixtures ------------------------------------------------------------------------------------------------
+GOLDEN_FIELDS = ["u", "v", "w", "pai", "tetav", "t", "qx", "ux", "vx", "tvirt", "p", "rho", "qsat", "ps"]
+
+
+def digest(a: np.ndarray) -> dict:
+    a = np.ascontiguousarray(a, dtype=np.float64) + 0.0      # -0.0 -> +0.0: equal values, equal bytes
+    return {"sha256": hashlib.sha256(a.tobytes()).hexdigest(), "sum": float(a.sum()), "absmax": float(np.abs(a).max())}
+
+
+def golden_cases():
+    from regcm_b200 import synthetic as S
+    lam = S.small(S.WORKLOADS["cordex25"], 16, 14, 8, ntr=1, nspgx=4, mo_nsound=3)
+    return {
+        "periodic_hills": (S.small(S.WORKLOADS["isc24_small"], 14, 12, 8, oro="sine", oro_h=700.0, msf_amp=0.03,
+                                   clat=30.0, mo_nsound=3), 2),
+        "limited_area": (lam, 2),
+        "limited_area_rotllr": (S.small(lam, 16, 14, 8, lrotllr=1), 1),
+        "limited_area_boundary": (S.small(lam, 16, 14, 8, do_bdy=1, present_qc=1, present_qi=1, mo_top_nudge=1,
+                                          ichebdy=1, do_slice=1, icldmstrat=1), 2),
+        # spectral nudging active every step (dtrad == dt), no ICBC condensate
+        "limited_area_spectral": (S.small(lam, 18, 16, 6, do_bdy=1, mo_top_nudge=1, mo_spectral_nudge=1, ichebdy=1,
+                                          ds_km=150.0, dtrad=150.0, dt=150.0), 3),
+        # UW-PBL TKE advected by the dycore, with its boundary values
+        "limited_area_tke": (S.small(lam, 16, 14, 8, do_bdy=1, present_qc=1, ibltyp=2, tkemin=1.0e-4, ipptls=1,
+                                     nqx=2), 2),
+    }
+
+
+def case_fields(wl):
+    return GOLDEN_FIELDS + (["trac"] if wl.ntr else []) + (["tke"] if wl.ibltyp == 2 else []) + \
+        (["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700"] if wl.do_slice else [])
+
+
+def run_case(wl, nsteps, dump_dir=None):
+    """(reference run, oracle) after nsteps of `moloch` from the same initial state."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import make_oracle_bdy
+    o, B = make_oracle_bdy(wl)
+    r = ReferenceRun(wl, o, B, dump_dir=dump_dir)
+    r.step(nsteps)
+    o.step(nsteps)
+    return r, o
+
+
+def main():
+    if not available():
+        raise SystemExit(f"{REF} not found: the reference sources are needed to run them")
+    out = {}
+    for name, (wl, nsteps) in golden_cases().items():
+        r, o = run_case(wl, nsteps, dump_dir=os.path.join(ROOT, "oracle", "_ref", "translated"))
+        fields = case_fields(wl)
+        out[name] = {"steps": nsteps, "grid": [wl.jx, wl.iy, wl.kz], "fields": {f: digest(r.get(f)) for f in fields}}
+        agree = {f: bool(np.array_equal(r.get(f), o.get(f))) for f in fields}
+        print(name, "reference == oracle:", agree)
+    path = os.path.join(ROOT, "tests", "golden", "reference_moloch.json")
+    json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,125 @@
+"""Run-time support for the translated reference routines (TEST INFRASTRUCTURE):
+Fortran arrays with arbitrary lower bounds, inclusive DO ranges, Fortran integer
+division and the intrinsics the MOLOCH path uses.  See fortran_subset.py."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+class FArr:
+    """A Fortran array a(l1:u1, l2:u2, ...) -- first index fastest -- backed by a
+    C-ordered NumPy array of reversed shape, i.e. a(j,i,k) is self.a[k-lk, i-li, j-lj]
+    (the layout of the oracle's global arrays).  Every access is bounds checked."""
+    __slots__ = ("a", "lb", "nd")
+
+    def __init__(self, a: np.ndarray, lb):
+        self.a, self.lb, self.nd = a, tuple(int(x) for x in lb), a.ndim
+        assert len(self.lb) == a.ndim
+
+    @classmethod
+    def alloc(cls, bounds, kind="float"):
+        shape = tuple(int(hi) - int(lo) + 1 for lo, hi in reversed(bounds))
+        return cls(np.zeros(shape, dtype=np.int64 if kind == "int" else np.float64), [lo for lo, _ in bounds])
+
+    def bounds(self):
+        return [(self.lb[d], self.lb[d] + self.a.shape[self.nd - 1 - d] - 1) for d in range(self.nd)]
+
+    def _off(self, idx):
+        if not isinstance(idx, tuple):
+            idx = (idx,)
+        if len(idx) != self.nd:
+            raise IndexError(f"rank mismatch: {len(idx)} subscripts for a rank-{self.nd} array")
+        out = []
+        for d in range(self.nd - 1, -1, -1):
+            x, n = idx[d], self.a.shape[self.nd - 1 - d]
+            if isinstance(x, slice):
+                lo = 0 if x.start is None else x.start - self.lb[d]
+                hi = n if x.stop is None else x.stop - self.lb[d] + 1       # Fortran sections are inclusive
+                if lo < 0 or hi > n:
+                    raise IndexError(f"section {x} outside bounds {self.bounds()[d]}")
+                out.append(slice(lo, hi))
+            else:
+                o = x - self.lb[d]
+                if o < 0 or o >= n:
+                    raise IndexError(f"subscript {d + 1} = {x} outside bounds {self.bounds()[d]}")
+                out.append(o)
+        return tuple(out)
+
+    def __getitem__(self, idx):
+        if idx is Ellipsis:
+            return self.a
+        o = self._off(idx)
+        v = self.a[o]
+        return v.item() if not isinstance(v, np.ndarray) else v
+
+    def __setitem__(self, idx, v):
+        if idx is Ellipsis:
+            self.a[...] = v
+            return
+        self.a[self._off(idx)] = v
+
+    def __call__(self, *idx):      # an array reference the translator took for a function call
+        return self[idx if len(idx) > 1 else idx[0]]
+
+    def view_last(self, n):
+        """a(:,:,:,n) as a rank-3 array sharing memory (assignpnt(a,ptr,n))."""
+        return FArr(self.a[n - self.lb[-1]], self.lb[:-1])
+
+
+def _frange(a, b, s=1):
+    a, b, s = int(a), int(b), int(s)
+    return range(a, b + (1 if s > 0 else -1), s)
+
+
+def _div(a, b):
+    if isinstance(a, int) and isinstance(b, int) and not isinstance(a, bool):
+        q = abs(a) // abs(b)
+        return q if (a >= 0) == (b >= 0) else -q
+    return a / b
+
+
+def _r4(x):
+    return float(np.float32(x))
+
+
+def _alloc(bounds, kind):
+    return FArr.alloc(bounds, kind)
+
+
+def _assignpnt(a, n=None):
+    return a if n is None else a.view_last(n)
+
+
+def _mod(a, b):
+    if isinstance(a, int) and isinstance(b, int):
+        return int(math.fmod(a, b))
+    return math.fmod(a, b)
+
+
+def _sign(a, b):
+    return math.copysign(abs(a), b) if isinstance(a, float) or isinstance(b, float) else (abs(a) if b >= 0 else -abs(a))
+
+
+def _real(x, kind=None):
+    if kind == 4:
+        return _r4(x)
+    return float(x)
+
+
+def _int(x, kind=None):
+    return int(x)        # truncation towards zero, as Fortran int()
+
+
+def _nint(x, kind=None):
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+INTRINSICS = {
+    "_frange": _frange, "_div": _div, "_r4": _r4, "_alloc": _alloc, "_assignpnt": _assignpnt,
+    "max": max, "min": min, "abs": abs, "sqrt": math.sqrt, "exp": math.exp, "log": math.log, "sin": math.sin,
+    "cos": math.cos, "tan": math.tan, "atan": math.atan, "mod": _mod, "sign": _sign, "real": _real, "int": _int,
+    "nint": _nint, "dble": float, "null": lambda: None,
+    "rkx": 8, "rk8": 8, "rk4": 4, "rk16": 16, "ik4": 4, "ik8": 8, "wrkp": 8,
+}

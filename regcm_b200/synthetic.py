@@ -80,7 +80,7 @@ class Workload:
     present_qi: int = 0
     mo_top_nudge: int = 0    # Share/mod_dynparam.F90:209
     mo_spectral_nudge: int = 0   # :207
-    ichebdy: int = 0         # tracer boundary: 0 flux dependent, 1 chib0/chib1
+    ichebdy: int = 1         # tracer boundary (Main/mod_params.F90:592): 1 chib0/chib1, 0 flux dependent
     ibltyp: int = 1          # 2: UW PBL, TKE advected by the dycore
     icldmstrat: int = 0
     do_slice: int = 0        # mkslice inside moloch()
@@ -382,7 +382,16 @@ def bdycon_setup(wl: Workload, zeta: np.ndarray | None = None) -> dict:
 
 
 def chem_fcx(wl: Workload) -> np.ndarray:
-    """Tracer relaxation weights fcx(1:nspgx) (Main/chemlib/mod_che_bdyco.F90:101): linear ramp."""
+    """Tracer relaxation weights fcx(1:nspgx): setup_che_bdycon, idynamic == 3 branch
+    (Main/chemlib/mod_che_bdyco.F90:1036-1039): fcx(1) = 1, fcx(nspgx) = 0, Lehmann coefficients in
+    between.  The reference stops with a fatal error unless nspgx-2 is a power of two; for the other
+    sponge widths of the synthetic workloads a linear ramp stands in."""
+    m = wl.nspgx - 2
+    if m >= 1 and (m & (m - 1)) == 0:
+        f = np.zeros(wl.nspgx)
+        f[0] = 1.0
+        f[1:wl.nspgx - 1] = relax_coefficients(m, 0.1, 1.0)
+        return f
     n = np.arange(1, wl.nspgx + 1, dtype=np.float64)
     return np.where((n >= 2) & (n <= wl.nspgx - 1), 0.5 * (wl.nspgx - n) / max(wl.nspgx - 2, 1), 0.0)
 

@@ -73,3 +73,33 @@ def test_wafone_single_field():
         o.wafone(f, max(n, 1)); m.wafone(f, n)
         compare(o, m, [f, "wz"], label=f"wafone({f}): ")
     m.close()
+
+
+def _golden():
+    import json
+    import os
+    from oracle.refrun import run_moloch as R
+    here = os.path.dirname(os.path.abspath(__file__))
+    return R, json.load(open(os.path.join(here, "golden", "reference_moloch.json")))
+
+
+@pytest.mark.parametrize("case", ["periodic_hills", "limited_area", "limited_area_rotllr", "limited_area_boundary",
+                                  "limited_area_spectral", "limited_area_tke"])
+def test_reference_golden(case):
+    """The CUDA path against the digests of the reference's OWN source, executed through the mechanical
+    translator of oracle/refrun (tests/golden/reference_moloch.json; see tests/test_reference_pin.py):
+    prognostic fields bit for bit (SHA-256 of the bytes), pow/exp-based diagnostics through their sum."""
+    from util import make_gpu_bdy, make_oracle_bdy
+    R, golden = _golden()
+    wl, nsteps = R.golden_cases()[case]
+    o, B = make_oracle_bdy(wl)          # inputs only: the oracle is not stepped
+    m = make_gpu_bdy(wl, o, B)
+    m.moloch(nsteps)
+    trans = {"p", "rho", "qsat", "ps", "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700"}
+    for f, want in golden[case]["fields"].items():
+        got = R.digest(m.get_global(f))
+        if f in trans:
+            assert abs(got["sum"] - want["sum"]) <= 1e-12 * abs(want["sum"]), f
+        else:
+            assert got["sha256"] == want["sha256"], f"{case}: {f} differs from the executed reference source"
+    m.close()

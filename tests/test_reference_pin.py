@@ -1,0 +1,79 @@
+"""Pinning the oracle on the reference ITSELF.
+
+The reference cannot be compiled here (no Fortran compiler), so its own source
+is executed: oracle/refrun translates the routines of the MOLOCH step --
+`moloch`, `sound`, `advection`, `wafone`, `boundary`, `bdyval`, `mkslice`, ...
+-- mechanically from /root/reference/Main/*.F90 to Python (statement by
+statement, no knowledge of the algorithm) and runs them on one rank.
+
+* `test_reference_source_matches_oracle`: reference source vs hand-written
+  oracle from the same initial state, every field BIT FOR BIT (needs
+  /root/reference; skipped where it is absent, e.g. on the GPU box).
+* `test_oracle_matches_reference_golden`: the digests of those reference runs
+  are committed (tests/golden/reference_moloch.json, written by
+  `python -m oracle.refrun.run_moloch`); the oracle must reproduce them
+  anywhere.  tests/test_gpu_parity.py checks the CUDA path against the same
+  digests.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.refrun import run_moloch as R
+
+from util import make_oracle_bdy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "reference_moloch.json")))
+CASES = R.golden_cases()
+# fields whose value goes through pow/exp: compared through their sum, not their bytes, where another
+# math library (the CUDA one) or another libm build could be involved
+TRANSCENDENTAL = {"p", "rho", "qsat", "ps", "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700"}
+
+
+def test_golden_file_covers_every_case():
+    assert set(GOLDEN) == set(CASES)
+    for name, (wl, nsteps) in CASES.items():
+        assert GOLDEN[name]["steps"] == nsteps and GOLDEN[name]["grid"] == [wl.jx, wl.iy, wl.kz]
+        assert set(GOLDEN[name]["fields"]) == set(R.case_fields(wl))
+
+
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+@pytest.mark.parametrize("case", list(CASES))
+def test_reference_source_matches_oracle(case):
+    wl, nsteps = CASES[case]
+    r, o = R.run_case(wl, nsteps)
+    bad = [f for f in R.case_fields(wl) if not np.array_equal(r.get(f), o.get(f))]
+    assert not bad, f"oracle differs from the executed reference source in {bad}"
+    for f in R.case_fields(wl):      # and the committed digests are those of this run
+        assert R.digest(r.get(f))["sha256"] == GOLDEN[case]["fields"][f]["sha256"], f
+
+
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+def test_reference_phases_match_oracle():
+    """sound and advection on their own, and the work arrays they leave behind."""
+    wl, _ = CASES["limited_area"]
+    o, B = make_oracle_bdy(wl)
+    r = R.ReferenceRun(wl, o, B)
+    r.call("reset_tendencies"); o.reset_tendencies()
+    r.call("sound", r.ns["dtsound"]); o.sound()
+    for f in ("u", "v", "w", "pai", "s", "zdiv2"):
+        assert np.array_equal(r.get(f), o.get(f)), f"sound: {f}"
+    r.call("advection", r.ns["dtstepa"]); o.advection()
+    for f in ("u", "v", "w", "pai", "tetav", "ux", "vx", "wx", "qx", "trac", "wz", "p0"):
+        assert np.array_equal(r.get(f), o.get(f)), f"advection: {f}"
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_oracle_matches_reference_golden(case):
+    wl, nsteps = CASES[case]
+    o, _ = make_oracle_bdy(wl)
+    o.step(nsteps)
+    for f, want in GOLDEN[case]["fields"].items():
+        got = R.digest(o.get(f))
+        if f in TRANSCENDENTAL:
+            assert abs(got["sum"] - want["sum"]) <= 1e-12 * abs(want["sum"]), f
+        else:
+            assert got["sha256"] == want["sha256"], f"{case}: {f} differs from the executed reference source"

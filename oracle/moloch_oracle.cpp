@@ -7,8 +7,9 @@
  * built with -fmad=false and keeps the reference's operation order, which
  * makes +,-,*,/ results bit-identical between the two.
  *
- * PARITY UNPINNED by the reference's own tests (it has none for this path and
- * cannot be built here); see moloch_oracle.h.
+ * Pinned on the reference's own source, executed through the mechanical
+ * translator of oracle/refrun (bit for bit; see moloch_oracle.h and
+ * tests/test_reference_pin.py).
  *
  * Every routine cites the reference lines it restates as  [F90:a-b]  (lines of
  * Main/mod_moloch.F90) or with an explicit file name.

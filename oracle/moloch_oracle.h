@@ -8,11 +8,20 @@
  * called by the product (regcm_b200/).  Only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs may use it.
  *
- * PARITY UNPINNED: the reference ships no unit tests, golden vectors or
- * fixtures for this path and cannot be compiled in this
- * container (no Fortran compiler, MPI or NetCDF).  The oracle is pinned only
- * by analytic known-answer tests derived from the reference source
- * (tests/test_oracle_*.py) and by decomposition invariance.
+ * PARITY PINNED ON THE REFERENCE'S OWN SOURCE.  The reference ships no unit
+ * tests, golden vectors or fixtures for this path and
+ * cannot be compiled in this container (no Fortran compiler, MPI or NetCDF).
+ * Instead its source is EXECUTED: oracle/refrun translates the routines of the
+ * MOLOCH step (moloch, sound, advection, wafone, boundary, bdyval, mkslice, ...)
+ * mechanically from the .F90 files under /root/reference/Main to Python and runs them on one
+ * rank; this oracle reproduces those runs bit for bit
+ * (tests/test_reference_pin.py, six cases), and the digests of the reference
+ * runs are committed as golden fixtures (tests/golden/reference_moloch.json)
+ * that both the oracle and the CUDA path are checked against.  Not covered by
+ * that pin: the set-up code (compute_moloch_static, paicompute, setup_bdycon),
+ * which is an input to both sides, and runs on more than one rank, which are
+ * tied to the single-rank result by decomposition invariance.  Analytic
+ * known-answer tests (tests/test_oracle*.py) cover those.
  *
  * Conventions
  *  - Global arrays cross the API in C order: 2-D (iy, jx), 3-D (nk, iy, jx),

@@ -74,6 +74,8 @@ typedef struct {
   int32_t do_massck;                  /* keep zq on the device for moloch_b200_massck      */
   double dtbdys, dtrad;               /* boundary / radiation period [s]         */
   double rhmin, rhmax, tkemin;        /* Main/mod_params.F90:381-382, mod_pbl_interface.F90:50 */
+  int32_t irceideal;                  /* 1: mkslice keeps ptrop as it is (Main/mod_slice.F90:345) */
+  int32_t reserved3;
 } moloch_b200_config;
 
 typedef struct moloch_b200_ctx moloch_b200_ctx;
@@ -95,6 +97,9 @@ enum moloch_b200_field {
   MB_XLB0, MB_XLB1, MB_XIB0, MB_XIB1, MB_XPSB0, MB_XPSB1, MB_CHIB0, MB_CHIB1,
   /* mkslice outputs (Main/mod_slice.F90:115-173) and its static input zq; do_slice */
   MB_PF3D, MB_TH3D, MB_RHB3D, MB_WPX3D, MB_RHOX2D, MB_TP2D, MB_TH700, MB_ZETAF,
+  /* common tail of mkslice (:342-384): input mddom%xlat; outputs ptrop and the level indices ktrop,
+   * kmxpbl (integer-valued, carried as real(rk8) across the ABI); do_slice                       */
+  MB_XLAT, MB_PTROP, MB_KTROP, MB_KMXPBL,
   MB_NFIELDS
 };
 
@@ -202,8 +207,11 @@ double moloch_b200_get_xbctime(moloch_b200_ctx* ctx);
  * host then uploads the new b1 with moloch_b200_set_field.                    */
 int moloch_b200_bdy_shift(moloch_b200_ctx* ctx);
 /* mkslice, idynamic == 3 branch (Main/mod_slice.F90:115-173): pf3d, th3d,
- * rhb3d, wpx3d, rhox2d, tp2d, th700 and the clipping of qx / trac             */
+ * rhb3d, wpx3d, rhox2d, tp2d, th700, the clipping of qx / trac and the common
+ * tail (:342-384): ptrop from xlat and the calendar day, ktrop, kmxpbl        */
 int moloch_b200_mkslice(moloch_b200_ctx* ctx);
+/* calday (Main/mod_sun.F90:316) and dayspy of the run's calendar, read by mkslice's ptrop */
+int moloch_b200_set_calday(moloch_b200_ctx* ctx, double calday, double dayspy);
 /* The device part of massck, idynamic == 3 branch (Main/mod_massck.F90:77-175):
  * this rank's partial sums out[0..3] = tdrym, tdadv, tqmass, tqadv [kg]; the
  * host adds the surface terms (rain, evaporation), does the sumall over ranks

@@ -216,7 +216,7 @@ struct Rank {
   // UW-PBL TKE (ibltyp == 2): Main/mod_atm_interface.F90:609-612, [F90:184]
   Arr tke, tketen, tkex;
   // mkslice outputs (Main/mod_atm_interface.F90:964-1012, :599)
-  Arr pf3d, th3d, rhb3d, wpx3d, rhox2d, tp2d, th700;
+  Arr pf3d, th3d, rhb3d, wpx3d, rhox2d, tp2d, th700, xlat, ptrop, ktrop, kmxpbl;
   // mospectral_nudge work arrays (Main/mod_bdycod.F90:422, :3868-3873), contiguous like the Fortran ones
   Arr zn1; std::vector<double> sx, sxg, sy, syg;
   std::map<std::string, FieldInfo> reg;
@@ -473,6 +473,10 @@ void alloc_ext(World& w, Rank& r) {
   R("pf3d", &r.pf3d, S_CROSS, kzp1); R("th3d", &r.th3d, S_CROSS, kz); R("rhb3d", &r.rhb3d, S_CROSS, kz);
   R("wpx3d", &r.wpx3d, S_CROSS, kz); R("rhox2d", &r.rhox2d, S_CROSS, 1); R("tp2d", &r.tp2d, S_CROSS, 1);
   R("th700", &r.th700, S_CROSS, 1);
+  r.xlat.alloc(g.jde1, g.jde2, g.ide1, g.ide2);
+  for (Arr* a : {&r.ptrop, &r.ktrop, &r.kmxpbl}) a->alloc(g.jci1, g.jci2, g.ici1, g.ici2);
+  R("xlat", &r.xlat, S_CROSS, 1); R("ptrop", &r.ptrop, S_CROSS, 1); R("ktrop", &r.ktrop, S_CROSS, 1);
+  R("kmxpbl", &r.kmxpbl, S_CROSS, 1);
 }
 
 // setup_bdycon, idynamic == 3 branch (Main/mod_bdycod.F90:478-568): rtb, the
@@ -1693,6 +1697,36 @@ void mkslice(World& w) {
           }
         }
       }
+    }
+    // common tail (Main/mod_slice.F90:342-384): tropopause pressure, its level, highest PBL level
+    const double twopi = mathpi * 2.0;
+    const double anorth[6] = {7.9925, 8.3329, 24.1731, -1.8069, 0.1082, -0.1493};
+    const double asouth[6] = {8.1797, 8.1455, -23.4839, 1.1464, 0.0798, -0.1491};
+    if (w.x.irceideal != 1) {
+      for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+        double ztrop;
+        if (r.xlat(j, i) > 0.0)
+          ztrop = anorth[0] + anorth[1] / std::pow(1.0 + std::exp(-(r.xlat(j, i) - anorth[2]) / anorth[3]), anorth[4]) +
+                  anorth[5] * std::cos((twopi * (w.x.calday - 28.0)) / w.x.dayspy);
+        else
+          ztrop = asouth[0] + asouth[1] / std::pow(1.0 + std::exp(-(r.xlat(j, i) - asouth[2]) / asouth[3]), asouth[4]) +
+                  asouth[5] * std::cos((twopi * (w.x.calday - 28.0)) / w.x.dayspy);
+        r.ptrop(j, i) = p00 * std::exp(-ztrop / 8.4);
+      }
+    }
+    for (auto& v : r.ktrop.d) v = kz;
+    for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+      for (int k = kz - 1; k >= 2; --k) {
+        r.ktrop(j, i) = k;
+        if (r.p(j, i, k) < r.ptrop(j, i)) break;
+      }
+    if (w.x.ibltyp == 1) {
+      for (auto& v : r.kmxpbl.d) v = kz;
+      for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+        for (int k = kz - 1; k >= 2; --k) {
+          if (r.zeta(j, i, k) > 5000.0) break;
+          r.kmxpbl(j, i) = k;
+        }
     }
   });
 }

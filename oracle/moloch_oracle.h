@@ -68,9 +68,10 @@ typedef struct {
   int icldmstrat;              /* 1: mkslice finds theta at 700 hPa                 */
   int do_slice;                /* call mkslice inside oracle_step                   */
   int bdy_lehmann;             /* unused by the oracle (hefc is an input table)     */
-  int reserved;
+  int irceideal;               /* 1: mkslice keeps ptrop (Main/mod_slice.F90:345)   */
   double dtbdys, dtrad;        /* boundary / radiation periods [s]                  */
   double rhmin, rhmax, tkemin; /* Main/mod_params.F90:381-382, mod_pbl_interface:50 */
+  double calday, dayspy;       /* calendar day / days per year for mkslice's ptrop  */
 } oracle_ext_config;
 
 void*  oracle_create(const oracle_config* cfg);

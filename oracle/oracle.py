@@ -24,8 +24,8 @@ class OracleConfig(C.Structure):
 class OracleExtConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "do_bdy", "present_qc", "present_qi", "mo_top_nudge", "mo_spectral_nudge", "ichem", "ichebdy",
-        "ibltyp", "icldmstrat", "do_slice", "bdy_lehmann", "reserved")] + [
-        (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin")]
+        "ibltyp", "icldmstrat", "do_slice", "bdy_lehmann", "irceideal")] + [
+        (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin", "calday", "dayspy")]
 
 
 def build(force: bool = False) -> None:
@@ -89,9 +89,9 @@ class Oracle:
             self.ext = OracleExtConfig(do_bdy=wl.do_bdy, present_qc=wl.present_qc, present_qi=wl.present_qi,
                                        mo_top_nudge=wl.mo_top_nudge, mo_spectral_nudge=wl.mo_spectral_nudge,
                                        ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, ibltyp=wl.ibltyp,
-                                       icldmstrat=wl.icldmstrat, do_slice=wl.do_slice, bdy_lehmann=0, reserved=0,
-                                       dtbdys=wl.dtbdys, dtrad=wl.dtrad, rhmin=wl.rhmin, rhmax=wl.rhmax,
-                                       tkemin=wl.tkemin)
+                                       icldmstrat=wl.icldmstrat, do_slice=wl.do_slice, bdy_lehmann=0,
+                                       irceideal=wl.irceideal, dtbdys=wl.dtbdys, dtrad=wl.dtrad, rhmin=wl.rhmin,
+                                       rhmax=wl.rhmax, tkemin=wl.tkemin, calday=wl.calday, dayspy=wl.dayspy)
             self._chk(self.lib.oracle_set_ext(self.h, C.byref(self.ext)))
 
     def close(self):
@@ -135,6 +135,8 @@ class Oracle:
         the oracle's own restatement of the set-up code."""
         for k in ("ht", "htu", "htv", "msfx", "msfu", "msfv", "ulat", "vlat", "rlat", "ps", "t", "qx", "u", "v"):
             self.set(k, P[k])
+        if self.ext is not None and "xlat" in P:
+            self.set("xlat", P["xlat"])
         if "hefc" in P and self.wl.nspgx > 0:
             self.set("hefc", P["hefc"])
         if "trac" in P and self.wl.ntr > 0:

@@ -277,7 +277,13 @@ def module_parameters(stmts: list[str], ex: Expr) -> list[str]:
             break
         if DECL.match(s) and "::" in s and re.search(r"\bparameter\b", s.split("::")[0]):
             spec, ents = s.split("::", 1)
-            if "dimension" in spec:
+            dim = re.search(r"dimension\s*\(([^)]*)\)", spec)
+            if dim:      # rank-1 array constructor:  name = [ a, b, ... ]  with dimension(lo:hi) or dimension(n)
+                m = re.match(r"^\s*(\w+)\s*=\s*(?:\[|\(/)(.*?)(?:\]|/\))\s*$", ents)
+                if m and "," not in dim.group(1):
+                    lo = dim.group(1).split(":")[0] if ":" in dim.group(1) else "1"
+                    vals = ", ".join(ex.tr(v.strip()) for v in split_top(m.group(2), ","))
+                    out.append(f"{pyname(m.group(1))} = _farr([{vals}], {ex.tr(lo)})")
                 continue
             for e in split_top(ents, ","):
                 if "=" in e:

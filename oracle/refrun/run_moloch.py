@@ -76,7 +76,8 @@ class ReferenceRun:
         ns = self.ns = dict(INTRINSICS)
         # ---- parameters straight from the reference's modules --------------------------------
         ex = F.Expr(set())
-        for rel in ("Share/mod_constants.F90", "Main/mpplib/mod_runparams.F90", "Main/mod_moloch.F90"):
+        for rel in ("Share/mod_constants.F90", "Main/mpplib/mod_runparams.F90", "Main/mod_moloch.F90",
+                    "Main/mod_slice.F90"):
             st = F.preprocess(open(os.path.join(REF, rel)).read())
             for line in F.module_parameters(st, ex):
                 try:
@@ -273,9 +274,12 @@ class ReferenceRun:
         for n in ("rhox2d", "tp2d", "th700"):
             setattr(at, n, FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2)]))
         # the common tail of mkslice (tropopause and PBL-top indices for the physics, Main/mod_slice.F90:342-384)
-        # runs too; its latitude/calendar inputs are not part of this path: irceideal = 1 skips the ptrop formula
         at.za = ns["z"]
-        ns.update(irceideal=1, ptrop=FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2)]),
+        from regcm_b200 import synthetic as S_
+        xl = np.array(H.cut(S_.make_primary(wl)["xlat"], g, dbx), dtype=np.float64)
+        ns["mddom"].xlat = FArr(xl, [dbx[0], dbx[2]])
+        ns.update(irceideal=wl.irceideal, calday=wl.calday, dayspy=wl.dayspy,
+                  ptrop=FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2)]),
                   ktrop=FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2)], "int"),
                   kmxpbl=FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2)], "int"))
         # ---- the single-rank halo exchange --------------------------------------------------------------------
@@ -301,10 +305,7 @@ class ReferenceRun:
                 src = tr.routine(routines[n])
                 self.sources[n] = src
                 exec(F.compile_source(src, f"<{rel}:{n}>"), ns)
-        # the array-valued parameters of mod_runparams (:184-192) are outside the translator's subset
-        ns["qxcheckval"] = FArr(np.array([1.0e-8, 1.0e-16, 1.0e-16, 1.0e-16, 1.0e-16, 1.0e-16, 1.0e-16, 1.0e10,
-                                          100.0, 0.01]), [1])
-        ns["qxzeroval"] = FArr(np.array([1.0e-8, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0e10, 100.0, 0.01]), [1])
+        assert isinstance(ns["qxcheckval"], FArr) and isinstance(ns["anorth"], FArr)   # array parameters read from the source
         if dump_dir:
             os.makedirs(dump_dir, exist_ok=True)
             for n, src in self.sources.items():
@@ -347,7 +348,9 @@ class ReferenceRun:
         ns = self.ns
         a = {"zeta": ns["z"], "pf3d": ns["atms"].pf3d, "th3d": ns["atms"].th3d, "rhb3d": ns["atms"].rhb3d,
              "wpx3d": ns["atms"].wpx3d, "rhox2d": ns["atms"].rhox2d, "tp2d": ns["atms"].tp2d,
-             "th700": ns["atms"].th700}.get(name) or ns[name]
+             "th700": ns["atms"].th700}.get(name)
+        if a is None:
+            a = ns[name]
         stag = H.ALLOC[name][0] if name in H.ALLOC else "cross"
         own = g.ext(stag, 0, 0)
         b = a.bounds()
@@ -401,7 +404,7 @@ def golden_cases():
 
 def case_fields(wl):
     return GOLDEN_FIELDS + (["trac"] if wl.ntr else []) + (["tke"] if wl.ibltyp == 2 else []) + \
-        (["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700"] if wl.do_slice else [])
+        (["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "ptrop", "ktrop", "kmxpbl"] if wl.do_slice else [])
 
 
 def run_case(wl, nsteps, dump_dir=None):

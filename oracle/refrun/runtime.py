@@ -88,6 +88,11 @@ def _alloc(bounds, kind):
     return FArr.alloc(bounds, kind)
 
 
+def _farr(vals, lo):
+    allint = all(isinstance(v, int) for v in vals)
+    return FArr(np.array(vals, dtype=np.int64 if allint else np.float64), [lo])
+
+
 def _assignpnt(a, n=None):
     return a if n is None else a.view_last(n)
 
@@ -117,7 +122,7 @@ def _nint(x, kind=None):
 
 
 INTRINSICS = {
-    "_frange": _frange, "_div": _div, "_r4": _r4, "_alloc": _alloc, "_assignpnt": _assignpnt,
+    "_frange": _frange, "_div": _div, "_r4": _r4, "_alloc": _alloc, "_assignpnt": _assignpnt, "_farr": _farr,
     "max": max, "min": min, "abs": abs, "sqrt": math.sqrt, "exp": math.exp, "log": math.log, "sin": math.sin,
     "cos": math.cos, "tan": math.tan, "atan": math.atan, "mod": _mod, "sign": _sign, "real": _real, "int": _int,
     "nint": _nint, "dble": float, "null": lambda: None,

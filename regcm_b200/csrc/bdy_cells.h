@@ -330,8 +330,10 @@ struct SliceArgs {
   Geo g;
   const double *pai, *t, *p, *rho, *qsat, *w, *ps, *zq;
   double *qx, *trac, *pf3d, *th3d, *rhb3d, *wpx3d, *rhox2d, *tp2d, *th700;
-  double rhmin, rhmax;
-  int ichem, icldmstrat;
+  const double *xlat, *za;
+  double *ptrop, *ktrop, *kmxpbl;
+  double rhmin, rhmax, calday, dayspy;
+  int ichem, icldmstrat, irceideal, ibltyp;
 };
 constexpr double rovcp_hd = rgas * (1.0 / cpd);
 // one (j,i,k) of the cross box, k = 1..kz
@@ -373,6 +375,40 @@ MB_HD void mkslice_col(const SliceArgs& a, int j, int i) {
       }
     }
     a.th700[i2] = th;
+  }
+}
+
+// common tail of mkslice (Main/mod_slice.F90:342-384): tropopause pressure (Mateus, Mendes, Pires 2022),
+// its level index and the highest level the PBL may reach; one interior (j,i) column
+MB_HD void mkslice_trop_col(const SliceArgs& a, int j, int i) {
+  const Geo& g = a.g;
+  if (!(j >= g.jci1 && j <= g.jci2 && i >= g.ici1 && i <= g.ici2)) return;
+  const double twopi = 3.14159265358979323846 * 2.0;      // Share/mod_constants.F90:305,323
+  const double anorth[6] = {7.9925, 8.3329, 24.1731, -1.8069, 0.1082, -0.1493};   // mod_slice.F90:42-48
+  const double asouth[6] = {8.1797, 8.1455, -23.4839, 1.1464, 0.0798, -0.1491};
+  const int kz = g.kz;
+  const long long i2 = gidx2(g, j, i), pl = g.plane, id1 = gidx(g, j, i, 1);
+  if (a.irceideal != 1) {
+    const double xl = a.xlat[i2];
+    const double* c = xl > 0.0 ? anorth : asouth;
+    const double ztrop = c[0] + c[1] / pow(1.0 + exp(-(xl - c[2]) / c[3]), c[4]) +
+                         c[5] * cos((twopi * (a.calday - 28.0)) / a.dayspy);
+    a.ptrop[i2] = p00 * exp(-ztrop / 8.4);
+  }
+  const double pt = a.ptrop[i2];
+  int kt = kz;
+  for (int k = kz - 1; k >= 2; --k) {
+    kt = k;
+    if (a.p[id1 + (long long)(k - 1) * pl] < pt) break;
+  }
+  a.ktrop[i2] = (double)kt;
+  if (a.ibltyp == 1) {
+    int km = kz;
+    for (int k = kz - 1; k >= 2; --k) {
+      if (a.za[id1 + (long long)(k - 1) * pl] > 5000.0) break;     // Saharan heat lows 5-6 km
+      km = k;
+    }
+    a.kmxpbl[i2] = (double)km;
   }
 }
 

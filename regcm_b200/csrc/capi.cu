@@ -630,6 +630,12 @@ int moloch_b200_bdy_shift(moloch_b200_ctx* c) {
   c->xbctime = 0.0;                                // :1158
   return 0;
 }
+int moloch_b200_set_calday(moloch_b200_ctx* c, double calday, double dayspy) {
+  if (!c) return fail("null context");
+  if (!(dayspy > 0.0)) return fail("set_calday: dayspy must be > 0");
+  c->calday = calday; c->dayspy = dayspy;
+  return 0;
+}
 int moloch_b200_mkslice(moloch_b200_ctx* c) {
   ENTRY(c)
   if (!c->cfg.do_slice) return fail("mkslice not configured (moloch_b200_config.do_slice)");

@@ -101,6 +101,7 @@ struct Ctx {
   int tab_n[MB_NTABLES] = {0};
   double xbctime = 0.0;     // Main/mpplib/mod_runparams.F90:102
   double tspectral = 0.0;   // Main/mod_moloch.F90:452
+  double calday = 1.0, dayspy = 365.2422;   // Main/mod_sun.F90:316, Share/mod_constants.F90
   double* spec_work = nullptr;   // mospectral_nudge scratch (sx, sxg, sy, syg, stale tails)
   size_t spec_work_doubles = 0;
   double* mass_work = nullptr;   // massck / ps guard partial sums

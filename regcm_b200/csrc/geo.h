@@ -117,7 +117,8 @@ inline void field_shape(const moloch_b200_config& f, int id, int& nk, int& nspec
     case MB_PF3D: nk = f.do_slice ? kz + 1 : 0; break;
     case MB_ZETAF: nk = (f.do_slice || f.do_massck) ? kz + 1 : 0; break;
     case MB_TH3D: case MB_RHB3D: case MB_WPX3D: nk = f.do_slice ? kz : 0; break;
-    case MB_RHOX2D: case MB_TP2D: case MB_TH700: nk = f.do_slice ? 1 : 0; break;
+    case MB_RHOX2D: case MB_TP2D: case MB_TH700: case MB_XLAT: case MB_PTROP: case MB_KTROP: case MB_KMXPBL:
+      nk = f.do_slice ? 1 : 0; break;
     default: nk = kz; break;
   }
 }

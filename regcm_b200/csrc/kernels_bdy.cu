@@ -147,6 +147,7 @@ __global__ void moloch_mkslice_col(SliceArgs a) {
   const int i = a.g.ice1 + blockIdx.y * BY + threadIdx.y;
   if (j > a.g.jce2 || i > a.g.ice2) return;
   mkslice_col(a, j, i);
+  mkslice_trop_col(a, j, i);
 }
 int k_mkslice(Ctx& c) {
   const Geo& g = c.g;
@@ -159,6 +160,9 @@ int k_mkslice(Ctx& c) {
   a.rhox2d = c.f[MB_RHOX2D].p; a.tp2d = c.f[MB_TP2D].p; a.th700 = c.f[MB_TH700].p;
   a.rhmin = c.cfg.rhmin; a.rhmax = c.cfg.rhmax;
   a.ichem = c.cfg.ichem && c.cfg.ntr > 0; a.icldmstrat = c.cfg.icldmstrat;
+  a.xlat = c.f[MB_XLAT].p; a.za = c.f[MB_ZETA].p; a.ptrop = c.f[MB_PTROP].p; a.ktrop = c.f[MB_KTROP].p;
+  a.kmxpbl = c.f[MB_KMXPBL].p; a.calday = c.calday; a.dayspy = c.dayspy; a.irceideal = c.cfg.irceideal;
+  a.ibltyp = c.cfg.ibltyp;
   {
     LaunchScope ls(c, KID_MKSLICE);
     moloch_mkslice<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(a);

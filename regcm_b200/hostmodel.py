@@ -46,6 +46,8 @@ ALLOC = {
     "pf3d": ("cross", 0, 0, "kzp1"), "th3d": ("cross", 0, 0, "kz"), "rhb3d": ("cross", 0, 0, "kz"),
     "wpx3d": ("cross", 0, 0, "kz"), "rhox2d": ("cross", 0, 0, 1), "tp2d": ("cross", 0, 0, 1),
     "th700": ("cross", 0, 0, 1), "zetaf": ("cross", 0, 0, "kzp1"),
+    "xlat": ("cross", 0, 0, 1), "ptrop": ("cross", 0, 0, 1), "ktrop": ("cross", 0, 0, 1),
+    "kmxpbl": ("cross", 0, 0, 1),
 }
 
 

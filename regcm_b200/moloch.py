@@ -35,7 +35,8 @@ FIELDS = ["u", "v", "w", "pai", "tetav", "t", "qx", "trac", "ux", "vx", "tvirt",
           "tke", "tketen", "tkex",
           "dub0", "dub1", "dvb0", "dvb1", "xtb0", "xtb1", "xpaib0", "xpaib1", "xqb0", "xqb1",
           "xlb0", "xlb1", "xib0", "xib1", "xpsb0", "xpsb1", "chib0", "chib1",
-          "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "zetaf"]
+          "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "zetaf",
+          "xlat", "ptrop", "ktrop", "kmxpbl"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 PROFILES = ["gzitak", "gzitakh", "ffilt", "xkdamp", "xknu", "rlat"]
 PROFILE_ID = {n: i for i, n in enumerate(PROFILES)}
@@ -56,7 +57,7 @@ ABI_SYMBOLS = [
     "moloch_b200_halo_plan", "moloch_b200_p2p_blob_size", "moloch_b200_p2p_export", "moloch_b200_p2p_connect", "moloch_b200_set_async",
     "moloch_b200_set_table", "moloch_b200_set_ibnd", "moloch_b200_boundary", "moloch_b200_bdyval",
     "moloch_b200_set_xbctime", "moloch_b200_get_xbctime", "moloch_b200_bdy_shift", "moloch_b200_mkslice",
-    "moloch_b200_massck", "moloch_b200_ps_check",
+    "moloch_b200_massck", "moloch_b200_ps_check", "moloch_b200_set_calday",
 ]
 
 
@@ -69,7 +70,8 @@ class Config(C.Structure):
         (n, C.c_double) for n in ("dtsec", "dx", "mo_dzita")] + [(n, C.c_int32) for n in (
         "do_bdy", "nspgx", "present_qc", "present_qi", "mo_top_nudge", "mo_spectral_nudge", "nztop", "ichem",
         "ichebdy", "do_slice", "icldmstrat", "km", "lm", "do_massck")] + [
-        (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin")]
+        (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin")] + [
+        (n, C.c_int32) for n in ("irceideal", "reserved3")]
 
 
 class MolochError(RuntimeError):
@@ -108,6 +110,7 @@ def load_library():
     lib.moloch_b200_host_free.argtypes = [C.c_void_p]
     lib.moloch_b200_set_table.argtypes = [ctx, C.c_int, C.c_void_p, C.c_int]
     lib.moloch_b200_set_ibnd.argtypes = [ctx, C.c_int, C.c_void_p] + [C.c_int] * 4
+    lib.moloch_b200_set_calday.argtypes = [ctx, C.c_double, C.c_double]
     lib.moloch_b200_massck.argtypes = [ctx, C.c_void_p]
     lib.moloch_b200_ps_check.argtypes = [ctx, C.c_void_p, C.c_void_p]
     lib.moloch_b200_set_xbctime.argtypes = [ctx, C.c_double]
@@ -150,7 +153,8 @@ def make_config(wl, g: Geom, device: int = -1, mo_dzita: float | None = None, bd
                   mo_spectral_nudge=wl.mo_spectral_nudge if wl.do_bdy else 0, nztop=int(bdy.get("nztop", 0)),
                   ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, do_slice=wl.do_slice, icldmstrat=wl.icldmstrat,
                   km=int(bdy.get("km", 0)), lm=int(bdy.get("lm", 0)), do_massck=int(getattr(wl, "do_massck", 0)), dtbdys=wl.dtbdys,
-                  dtrad=wl.dtrad, rhmin=wl.rhmin, rhmax=wl.rhmax, tkemin=wl.tkemin)
+                  dtrad=wl.dtrad, rhmin=wl.rhmin, rhmax=wl.rhmax, tkemin=wl.tkemin,
+                  irceideal=int(getattr(wl, "irceideal", 0)), reserved3=0)
 
 
 def halo_plan(cfg: Config, stag: int, nex: int, lr: bool, bt: bool):
@@ -282,6 +286,8 @@ class MolochB200:
     def bdyval(self): self._chk(self.lib.moloch_b200_bdyval(self.ctx))
     def bdy_shift(self): self._chk(self.lib.moloch_b200_bdy_shift(self.ctx))
     def mkslice(self): self._chk(self.lib.moloch_b200_mkslice(self.ctx))
+    def set_calday(self, calday: float, dayspy: float = 365.2422):
+        self._chk(self.lib.moloch_b200_set_calday(self.ctx, float(calday), float(dayspy)))
     def massck(self) -> np.ndarray:
         """This rank's tdrym, tdadv, tqmass, tqadv (Main/mod_massck.F90:77-185)."""
         out = np.zeros(4)

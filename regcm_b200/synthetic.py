@@ -85,6 +85,9 @@ class Workload:
     icldmstrat: int = 0
     do_slice: int = 0        # mkslice inside moloch()
     do_massck: int = 0       # keep zq on the device for massck (debug_level > 0)
+    irceideal: int = 0       # 1: mkslice keeps ptrop (Main/mod_slice.F90:345)
+    calday: float = 172.25   # calendar day used by mkslice's tropopause pressure
+    dayspy: float = 365.2422
     dtbdys: float = 21600.0
     dtrad: float = 1800.0
     rhmin: float = 0.01      # Main/mod_params.F90:381-382

@@ -70,6 +70,9 @@ def main():
         fields["zetaf"] = S.md_zeta(S.model_zitaf(wl.kz, wl.mo_ztop)[:, None, None], ht[None], wl.mo_ztop, wl.mo_h,
                                     wl.mo_a0)
         boxes["zetaf"] = (g.jce1, g.jce2, g.ice1, g.ice2)
+        dl = S.raddeg * wl.dx / S.earthrad
+        fields["xlat"] = np.ascontiguousarray(wl.clat - dl * (float(wl.iy) * 0.5 - Ig + 0.5))
+        boxes["xlat"] = boxes["zetaf"]
     m.init_moloch(fields, profiles, boxes)
     if wl.do_bdy:
         base = {n: np.zeros(m.global_shape(n)) for n in ("u", "v", "t", "pai", "qx", "ps")}

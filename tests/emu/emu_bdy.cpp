@@ -33,7 +33,7 @@ struct Emu {
   int nk[MB_NFIELDS], nspec[MB_NFIELDS];
   std::vector<int> ibnd[3];
   std::vector<double> tab[MB_NTABLES];
-  double xbctime = 0.0, tspectral = 0.0;
+  double xbctime = 0.0, tspectral = 0.0, calday = 1.0, dayspy = 365.2422;
   int order = 0;
   std::vector<double> zn, g1, sx, sy, sx_stale, sy_stale;   // mospectral_nudge scratch
 };
@@ -214,6 +214,7 @@ int emu_b200_set_ibnd(void* h, int which, const int32_t* ib, int jlo, int jhi, i
     e.ibnd[which][gidx2(g, j, i)] = ib[(size_t)(i - ilo) * (jhi - jlo + 1) + (j - jlo)];
   return 0;
 }
+int emu_b200_set_calday(void* h, double calday, double dayspy) { ((Emu*)h)->calday = calday; ((Emu*)h)->dayspy = dayspy; return 0; }
 int emu_b200_set_xbctime(void* h, double t) { ((Emu*)h)->xbctime = t; return 0; }
 double emu_b200_get_xbctime(void* h) { return ((Emu*)h)->xbctime; }
 
@@ -245,9 +246,12 @@ int emu_b200_mkslice(void* h) {   // = k_mkslice
   a.rhox2d = P(e, MB_RHOX2D); a.tp2d = P(e, MB_TP2D); a.th700 = P(e, MB_TH700);
   a.rhmin = e.cfg.rhmin; a.rhmax = e.cfg.rhmax;
   a.ichem = e.cfg.ichem && e.cfg.ntr > 0; a.icldmstrat = e.cfg.icldmstrat;
+  a.xlat = P(e, MB_XLAT); a.za = P(e, MB_ZETA); a.ptrop = P(e, MB_PTROP); a.ktrop = P(e, MB_KTROP);
+  a.kmxpbl = P(e, MB_KMXPBL); a.calday = e.calday; a.dayspy = e.dayspy; a.irceideal = e.cfg.irceideal;
+  a.ibltyp = e.cfg.ibltyp;
   if (!a.pf3d) return fail("emu: do_slice not configured");
   walk(o, 1, g.kz, [&](int k) { walk(o, g.ice1, g.ice2, [&](int i) { walk(o, g.jce1, g.jce2, [&](int j) { mkslice_cell(a, j, i, k); }); }); });
-  walk(o, g.ice1, g.ice2, [&](int i) { walk(o, g.jce1, g.jce2, [&](int j) { mkslice_col(a, j, i); }); });
+  walk(o, g.ice1, g.ice2, [&](int i) { walk(o, g.jce1, g.jce2, [&](int j) { mkslice_col(a, j, i); mkslice_trop_col(a, j, i); }); });
   return 0;
 }
 // = k_massck: out7 = tdrym, tdadv, tqmass, tqadv, psmax, psmin, nonfinite

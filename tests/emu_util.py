@@ -46,6 +46,7 @@ class _Proxy:
         lib.emu_b200_get_xbctime.argtypes = [ctx]
         lib.emu_b200_get_xbctime.restype = C.c_double
         lib.emu_b200_set_order.argtypes = [ctx, C.c_int]
+        lib.emu_b200_set_calday.argtypes = [ctx, C.c_double, C.c_double]
         lib.emu_b200_massck.argtypes = [ctx, C.c_void_p]
         lib.emu_b200_ps_check.argtypes = [ctx, C.c_void_p, C.c_void_p]
         for f in ("destroy", "init", "bdyval", "boundary", "mkslice", "tke_destagger", "tke_restagger", "tke_update"):

@@ -37,6 +37,8 @@ class MultiRank:
                 m.init_moloch(fields, profiles)
                 if boundary is not None:
                     m.load_boundary(boundary)
+                if wl.do_slice:
+                    m.set_calday(wl.calday, wl.dayspy)
             except Exception as e:  # noqa: BLE001
                 errs.append((r, e))
                 bar.abort()

@@ -38,6 +38,9 @@ def make_emu(wl, o, B, order=0):
         m.set_global("tke", o.get("tke"))
     if wl.do_slice:
         m.set_global("zetaf", o.get("zetaf"))
+        m.set_global("zeta", o.get("zeta"))
+        m.set_global("xlat", o.get("xlat"))
+        m.set_calday(wl.calday, wl.dayspy)
     m.init_boundary()
     m.load_boundary(B)
     return m
@@ -102,7 +105,10 @@ def test_mkslice_cells_bit_exact(order):
     o.diagnostics()
     m = make_emu(wl, o, B, order)
     o.mkslice(); m.mkslice()
-    same(o, m, ["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "qx", "trac"], "mkslice: ")
+    same(o, m, ["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "qx", "trac", "ptrop", "ktrop", "kmxpbl"],
+         "mkslice: ")
+    kt = o.get("ktrop")[1:wl.iy - 2, 1:wl.jx - 2]
+    assert kt.min() >= 2 and kt.max() <= wl.kz - 1 and (o.get("kmxpbl")[1:wl.iy - 2, 1:wl.jx - 2] >= 2).all()
 
 
 @pytest.mark.parametrize("order", [0, 1])

@@ -78,6 +78,7 @@ def test_decomposed_boundary_bit_exact(px, py):
     o, B = make_oracle_bdy(wl)
     fields, profiles = oracle_inputs(o, wl)
     fields["zetaf"] = o.get("zetaf")
+    fields["xlat"] = o.get("xlat")
     mr = MultiRank(wl, px, py, fields, profiles, bdy=bdy_tables_from_oracle(wl, o), boundary=B)
     try:
         o.step(3)

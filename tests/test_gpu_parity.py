@@ -95,7 +95,7 @@ def test_reference_golden(case):
     o, B = make_oracle_bdy(wl)          # inputs only: the oracle is not stepped
     m = make_gpu_bdy(wl, o, B)
     m.moloch(nsteps)
-    trans = {"p", "rho", "qsat", "ps", "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700"}
+    trans = {"p", "rho", "qsat", "ps", "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "ptrop"}
     for f, want in golden[case]["fields"].items():
         got = R.digest(m.get_global(f))
         if f in trans:

@@ -80,8 +80,9 @@ def test_mkslice():
     o.diagnostics(); m.diagnostics()
     o.mkslice(); m.mkslice()
     compare(o, m, ["qx", "trac"], label="mkslice: ")
-    compare(o, m, ["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700"], exact=False, rtol=1e-13,
+    compare(o, m, ["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "ptrop"], exact=False, rtol=1e-13,
             label="mkslice: ")
+    compare(o, m, ["ktrop", "kmxpbl"], label="mkslice: ")
     m.close()
 
 

@@ -30,7 +30,7 @@ GOLDEN = json.load(open(os.path.join(HERE, "golden", "reference_moloch.json")))
 CASES = R.golden_cases()
 # fields whose value goes through pow/exp: compared through their sum, not their bytes, where another
 # math library (the CUDA one) or another libm build could be involved
-TRANSCENDENTAL = {"p", "rho", "qsat", "ps", "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700"}
+TRANSCENDENTAL = {"p", "rho", "qsat", "ps", "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "ptrop"}
 
 
 def test_golden_file_covers_every_case():

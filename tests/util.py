@@ -86,7 +86,10 @@ def make_gpu_bdy(wl, o, B, device=-1):
         fields["tke"] = o.get("tke")
     if wl.do_slice:
         fields["zetaf"] = o.get("zetaf")
+        fields["xlat"] = o.get("xlat")
     m.init_moloch(fields, profiles)
+    if wl.do_slice:
+        m.set_calday(wl.calday, wl.dayspy)
     if wl.do_bdy:
         m.load_boundary(B)
         m.set_xbctime(o.get_xbctime())

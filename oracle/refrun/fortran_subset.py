@@ -238,12 +238,13 @@ class Expr:
 
 
 class Routine:
-    def __init__(self, name, kind, args, body, result=None):
+    def __init__(self, name, kind, args, body, result=None, elemental=False):
         self.name, self.kind, self.args, self.body, self.result = name, kind, args, body, result
+        self.elemental = elemental
 
 
 HEAD_SUB = re.compile(r"^(?:(?:pure|elemental|recursive)\s+)*subroutine\s+(\w+)\s*(?:\((.*)\))?\s*$")
-HEAD_FUN = re.compile(r"^(?:(?:pure|elemental|recursive)\s+)*(?:(?:real|integer|logical)\s*(?:\(\w+\))?\s+)?"
+HEAD_FUN = re.compile(r"^((?:(?:pure|elemental|recursive|real\s*\(\w+\)|integer\s*\(\w+\)|real|integer|logical)\s+)*)"
                       r"function\s+(\w+)\s*\((.*?)\)\s*(?:result\s*\(\s*(\w+)\s*\))?\s*$")
 
 
@@ -257,8 +258,8 @@ def find_routines(stmts: list[str]) -> dict[str, Routine]:
                 continue
             m = HEAD_FUN.match(s)
             if m and not s.startswith("end"):
-                cur = Routine(m.group(1), "function", [a.strip() for a in m.group(2).split(",") if a.strip()], [],
-                              m.group(3) or m.group(1))
+                cur = Routine(m.group(2), "function", [a.strip() for a in m.group(3).split(",") if a.strip()], [],
+                              m.group(4) or m.group(2), elemental="elemental" in m.group(1))
                 continue
         else:
             if re.match(r"^end\s*(subroutine|function)\b", s):
@@ -266,6 +267,24 @@ def find_routines(stmts: list[str]) -> dict[str, Routine]:
                 cur = None
             else:
                 cur.body.append(s)
+    return out
+
+
+def find_internal(stmts: list[str], name: str) -> Routine:
+    """A routine by name wherever it is nested (internal procedures after `contains`)."""
+    out, body, head = None, [], None
+    for s in stmts:
+        if head is None:
+            m = HEAD_SUB.match(s)
+            if m and m.group(1) == name:
+                head = Routine(name, "subroutine", [a.strip() for a in (m.group(2) or "").split(",") if a.strip()], body)
+            continue
+        if re.match(rf"^end\s*subroutine\s+{name}\b", s):
+            out = head
+            break
+        body.append(s)
+    if out is None:
+        raise KeyError(name)
     return out
 
 
@@ -492,6 +511,9 @@ class Translator:
                 if rhs.startswith(">"):
                     rhs = rhs[1:].strip()      # pointer assignment =>
                 if re.match(r"^\w+$", lhs):
+                    if lhs in arrays and not rhs.startswith("null"):      # whole-array assignment
+                        emit(f"{pyname(lhs)}[...] = {ex.tr(rhs)}")
+                        return
                     assigned.add(lhs)
                 emit(f"{ex.tr(lhs, lhs=True)} = {ex.tr(rhs)}")
                 return
@@ -505,7 +527,8 @@ class Translator:
         if r.kind == "function":
             emit(f"return {pyname(resname)}")
         globs = sorted(pyname(n) for n in assigned if n not in local_names) + [pyname(n) for n, _ in saves]
-        head = [f"def {pyname(r.name)}({', '.join(pyname(a) for a in r.args)}):"]
+        head = (["@_elemental"] if r.elemental else []) + \
+               [f"def {pyname(r.name)}({', '.join(pyname(a) for a in r.args)}):"]
         if globs:
             head.append("    global " + ", ".join(sorted(set(globs))))
         head += ["    " + p for p in pre]
@@ -517,13 +540,15 @@ class Translator:
 
 
 class _Div(ast.NodeTransformer):
-    """a / b -> _div(a, b): Fortran integer division when both operands are integers."""
+    """a / b -> _div(a, b): Fortran integer division when both operands are integers;
+    a ** b -> _pow(a, b): integer powers by repeated multiplication, as compilers expand them."""
 
     def visit_BinOp(self, node):
         self.generic_visit(node)
-        if isinstance(node.op, ast.Div):
-            return ast.copy_location(ast.Call(func=ast.Name(id="_div", ctx=ast.Load()), args=[node.left, node.right],
-                                              keywords=[]), node)
+        for op, fn in ((ast.Div, "_div"), (ast.Pow, "_pow")):
+            if isinstance(node.op, op):
+                return ast.copy_location(ast.Call(func=ast.Name(id=fn, ctx=ast.Load()),
+                                                  args=[node.left, node.right], keywords=[]), node)
         return node
 
 

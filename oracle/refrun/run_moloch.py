@@ -361,6 +361,139 @@ class ReferenceRun:
         return out
 
 
+class SetupRun:
+    """The reference's set-up routines on one rank: model_zitaf/model_zitah and the metric functions
+    (Share/mod_zita.F90), compute_moloch_static (internal to `param`, Main/mod_params.F90:3316-3395),
+    init_moloch (Main/mod_moloch.F90:201-308), setup_bdywt and paicompute (Main/mod_bdycod.F90:4033-4047,
+    3762-3796), from the workload's file-like inputs (terrain, map factors, latitudes, ps, t, qv).  Limited-area
+    domains only (every halo exchange is then a no-op on one rank)."""
+
+    def __init__(self, wl, P: dict):
+        from regcm_b200 import hostmodel as H
+        from regcm_b200 import synthetic as S
+        from regcm_b200.decomp import make_geom
+        assert wl.i_band == 0 and wl.i_crm == 0
+        self.wl = wl
+        g = self.g = make_geom(wl.jx, wl.iy, wl.kz, 0, 0, 1, 1, 0)
+        ns = self.ns = dict(INTRINSICS)
+        ex = F.Expr(set())
+        for rel in ("Share/mod_constants.F90", "Main/mpplib/mod_runparams.F90", "Main/mod_moloch.F90"):
+            for line in F.module_parameters(F.preprocess(open(os.path.join(REF, rel)).read()), ex):
+                try:
+                    exec(F.compile_source(line, rel), ns)
+                except Exception:
+                    pass
+        kz = wl.kz
+        for n in ("jde1", "jde2", "ide1", "ide2", "jdi1", "jdi2", "idi1", "idi2", "jce1", "jce2", "ice1", "ice2",
+                  "jci1", "jci2", "ici1", "ici2"):
+            ns[n] = getattr(g, n)
+        ns.update(kz=kz, kzp1=kz + 1, kzm1=kz - 1, nqx=wl.nqx, ntr=wl.ntr, ipptls=wl.ipptls, ibltyp=wl.ibltyp,
+                  ichem=int(wl.ntr > 0), dtsec=wl.dt, dx=wl.dx, rdx=1.0 / wl.dx, mo_ztop=wl.mo_ztop, mo_h=wl.mo_h,
+                  mo_a0=wl.mo_a0, mo_nadv=wl.mo_nadv, mo_nsound=wl.mo_nsound, mo_divdamp=bool(wl.mo_divdamp),
+                  mo_divfilter=bool(wl.mo_divfilter), iproj="ROTLLR" if wl.lrotllr else "LAMCON",
+                  jcross1=1, jcross2=wl.jx - 1, icross1=1, icross2=wl.iy - 1, irceideal=0, moloch_realcase=True,
+                  myid=0, italk=0, rayzd=0.0, nspgx=wl.nspgx,
+                  ma=_Obj(has_bdyleft=True, has_bdyright=True, has_bdybottom=True, has_bdytop=True, bandflag=False,
+                          crmflag=False))
+        for n in ("exchange", "exchange_lr", "exchange_bt", "exchange_lrbt"):
+            ns[n] = lambda *a: None          # one rank, no periodic direction: nothing to exchange
+
+        def box(stag):
+            return g.ext(stag, 0, 0)
+
+        def arr(stag, nk=0, fill=None, nspec=0):
+            b = box(stag)
+            bnds = [(b[0], b[1]), (b[2], b[3])] + ([(1, nk)] if nk else []) + ([(1, nspec)] if nspec else [])
+            a = FArr.alloc(bnds)
+            if fill is not None:
+                a.a[...] = np.asarray(fill)[..., b[2] - 1:b[3], b[0] - 1:b[1]]
+            return a
+
+        md = ns["mddom"] = _Obj()
+        for n in ("ht", "htu", "htv", "msfx", "msfu", "msfv", "ulat", "vlat", "xlat"):
+            setattr(md, n, arr("dot", fill=P[n]))
+        md.xlon = arr("dot")
+        md.hx, md.hy = arr("u"), arr("v")
+        md.rlat = FArr(np.asarray(P["rlat"], dtype=np.float64).copy(), [1])
+        mo = ns["mo_atm"] = _Obj(zeta=arr("cross", kz), fmz=arr("cross", kz), rfmzu=arr("u", kz), rfmzv=arr("v", kz),
+                                 fmzf=arr("cross", kz + 1), zetaf=arr("cross", kz + 1), dz=arr("cross", kz),
+                                 pai=arr("cross", kz), tetav=arr("cross", kz), u=arr("u", kz), ux=arr("cross", kz),
+                                 v=arr("v", kz), vx=arr("cross", kz), w=arr("cross", kz + 1), tvirt=arr("cross", kz),
+                                 p=arr("cross", kz), t=arr("cross", kz, fill=P["t"]), rho=arr("cross", kz),
+                                 qx=arr("cross", kz, fill=P["qx"], nspec=wl.nqx), qs=arr("cross", kz),
+                                 uten=arr("cross", kz), vten=arr("cross", kz), tten=arr("cross", kz),
+                                 qxten=arr("cross", kz, nspec=wl.nqx), tke=None, tketen=None,
+                                 trac=arr("cross", kz, nspec=max(wl.ntr, 1)), chiten=arr("cross", kz, nspec=max(wl.ntr, 1)))
+        ns["sfs"] = _Obj(psa=arr("cross", fill=P["ps"]), tg=arr("cross"), t2m=arr("cross"))
+        ns["zita"], ns["zitah"] = FArr.alloc([(1, kz + 1)]), FArr.alloc([(1, kz)])
+        # allocate_moloch (Main/mod_moloch.F90:159-199)
+        ns.update(coru=arr("u"), corv=arr("v"), gzitak=FArr.alloc([(1, kz + 1)]), gzitakh=FArr.alloc([(1, kz)]),
+                  xkdamp=FArr.alloc([(1, kz)]), xknu=FArr.alloc([(1, kz)]))
+        for n in ("mx2", "rmx", "rmu", "rmv"):
+            ns[n] = arr("dot")
+        ns["bdywtu"] = FArr.alloc([(g.jdi1, g.jdi2), (g.ici1, g.ici2), (1, kz)])
+        ns["bdywtv"] = FArr.alloc([(g.jci1, g.jci2), (g.idi1, g.idi2), (1, kz)])
+        ns["bdywtw"] = FArr.alloc([(g.jci1, g.jci2), (g.ici1, g.ici2), (1, kz)])
+        for n in ("mu", "mv", "mx", "rlat", "hx", "hy", "xlat", "xlon", "ht", "ps", "ts", "t2m", "fmz", "rfmzu", "rfmzv",
+                  "fmzf", "pai", "tetav", "u", "ux", "v", "vx", "w", "tvirt", "z", "p", "t", "rho", "qx", "qsat", "uten",
+                  "vten", "tten", "qxten", "qv", "qvten", "qc", "qi", "qr", "qs", "trac", "chiten", "tke", "tketen"):
+            ns[n] = None       # module pointers, associated by init_moloch's assignpnt calls
+        T = S.bdycon_setup(wl)
+        dbox = g.ext("dot", 0, 0)
+        for which, nm in (("cr", "ba_cr"), ("ud", "ba_ud"), ("vd", "ba_vd")):
+            ib = np.array(H.cut(T["ibnd"][which], g, dbox), dtype=np.int64)
+            ns[nm] = _Obj(ibnd=FArr(ib, [dbox[0], dbox[2]]), havebound=bool((ib > 0).any()))
+        if wl.nspgx > 0:
+            ns["hefc"] = FArr(np.asarray(P["hefc"], dtype=np.float64).reshape(kz, wl.nspgx).copy(), [1, 1])
+        arrays = {k for k, v in ns.items() if isinstance(v, FArr)} | {
+            "mu", "mv", "mx", "w", "zita", "zitah", "hefc", "mask", "zitaf"}
+        tr = F.Translator(arrays)
+        self.sources = {}
+        zst = F.preprocess(open(os.path.join(REF, "Share/mod_zita.F90")).read())
+        zr = F.find_routines(zst)
+        todo = [(zr[n], "Share/mod_zita.F90") for n in ("zfz", "bzita", "bzitap", "gzita", "gzitap", "md_fmz_h",
+                                                         "md_zeta_h", "md_fmz", "md_zeta", "model_zitaf", "model_zitah")]
+        pst = F.preprocess(open(os.path.join(REF, "Main/mod_params.F90")).read())
+        todo.append((F.find_internal(pst, "compute_moloch_static"), "Main/mod_params.F90"))
+        mr = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mod_moloch.F90")).read()))
+        todo.append((mr["init_moloch"], "Main/mod_moloch.F90"))
+        br = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mod_bdycod.F90")).read()))
+        todo += [(br["setup_bdywt"], "Main/mod_bdycod.F90"), (br["paicompute"], "Main/mod_bdycod.F90")]
+        for r, rel in todo:
+            src = tr.routine(r)
+            self.sources[r.name] = src
+            exec(F.compile_source(src, f"<{rel}:{r.name}>"), ns)
+
+    def run(self):
+        ns, kz = self.ns, self.wl.kz
+        ns["model_zitaf"](ns["zita"], ns["mo_ztop"])      # Main/mod_params.F90:2461-2463
+        ns["model_zitah"](ns["zitah"], ns["mo_ztop"])
+        ns["mo_dzita"] = ns["zita"][kz]
+        ns["compute_moloch_static"]()
+        ns["init_moloch"]()
+        # Main/mod_init.F90:941: the hydrostatic Exner function of the initial state
+        ns["paicompute"](ns["sfs"].psa, ns["mo_atm"].zeta, ns["mo_atm"].t, ns["qv"], ns["mo_atm"].pai)
+        return self
+
+    def get(self, name) -> np.ndarray:
+        ns, wl = self.ns, self.wl
+        mo, md = ns["mo_atm"], ns["mddom"]
+        a = {"zeta": mo.zeta, "fmz": mo.fmz, "rfmzu": mo.rfmzu, "rfmzv": mo.rfmzv, "fmzf": mo.fmzf, "zetaf": mo.zetaf,
+             "hx": md.hx, "hy": md.hy, "pai": mo.pai}.get(name)
+        if a is None:
+            a = ns[name]
+        if a.nd == 1:
+            return a.a.copy()
+        b = a.bounds()
+        out = np.zeros(a.a.shape[:-2] + (wl.iy, wl.jx))
+        out[..., b[1][0] - 1:b[1][1], b[0][0] - 1:b[0][1]] = a.a
+        return out
+
+
+SETUP_FIELDS = ["hx", "hy", "zeta", "fmz", "fmzf", "zetaf", "rfmzu", "rfmzv", "coru", "corv", "mx2", "rmx", "rmu", "rmv",
+                "gzitak", "gzitakh", "xkdamp", "xknu", "bdywtu", "bdywtv", "bdywtw", "pai"]
+
+
 class _Mask:
     """logical(j,i) array of cbound_area (bsouth ...): Fortran-bounded boolean lookup."""
 
@@ -407,6 +540,21 @@ def case_fields(wl):
         (["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "ptrop", "ktrop", "kmxpbl"] if wl.do_slice else [])
 
 
+def setup_cases():
+    from regcm_b200 import synthetic as S
+    lam = S.small(S.WORKLOADS["cordex25"], 16, 14, 8, ntr=1, nspgx=4)
+    return {"setup_limited_area": lam, "setup_limited_area_rotllr": S.small(lam, 18, 12, 7, lrotllr=1, nspgx=5)}
+
+
+def run_setup_case(wl):
+    """(reference set-up run, oracle) from the same file-like inputs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from regcm_b200 import synthetic as S
+    from util import make_oracle_bdy
+    o, _ = make_oracle_bdy(wl)
+    return SetupRun(wl, S.make_primary(wl)).run(), o
+
+
 def run_case(wl, nsteps, dump_dir=None):
     """(reference run, oracle) after nsteps of `moloch` from the same initial state."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -428,6 +576,10 @@ def main():
         out[name] = {"steps": nsteps, "grid": [wl.jx, wl.iy, wl.kz], "fields": {f: digest(r.get(f)) for f in fields}}
         agree = {f: bool(np.array_equal(r.get(f), o.get(f))) for f in fields}
         print(name, "reference == oracle:", agree)
+    for name, wl in setup_cases().items():
+        sr, o = run_setup_case(wl)
+        out[name] = {"steps": 0, "grid": [wl.jx, wl.iy, wl.kz], "fields": {f: digest(sr.get(f)) for f in SETUP_FIELDS}}
+        print(name, "reference == oracle:", {f: bool(np.array_equal(sr.get(f), o.get(f))) for f in SETUP_FIELDS})
     path = os.path.join(ROOT, "tests", "golden", "reference_moloch.json")
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print("wrote", path)

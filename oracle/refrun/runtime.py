@@ -80,6 +80,62 @@ def _div(a, b):
     return a / b
 
 
+def _pow(a, b):
+    """x**n with an integer n: the multiplication chain compilers emit (x*x, (x*x)*x, (x*x)*(x*x));
+    otherwise the C library's pow."""
+    if isinstance(b, int) and not isinstance(b, bool):
+        if isinstance(a, int):
+            return a ** b if b >= 0 else 0
+        n, r = abs(b), 1.0
+        if n == 1:
+            r = a
+        elif n == 2:
+            r = a * a
+        elif n == 3:
+            r = (a * a) * a
+        elif n == 4:
+            r = (a * a) * (a * a)
+        elif n > 4:
+            r, base = 1.0, a
+            while n:
+                if n & 1:
+                    r = r * base
+                base = base * base
+                n >>= 1
+        return r if b >= 0 else 1.0 / r
+    return math.pow(a, b)
+
+
+def _elemental(f):
+    """An elemental function applied to whole arrays: element by element, in storage order."""
+    def g(*args):
+        arrs = [x for x in args if isinstance(x, (FArr, np.ndarray))]
+        if not arrs:
+            return f(*args)
+        shape = (arrs[0].a if isinstance(arrs[0], FArr) else arrs[0]).shape
+        flat = [(x.a if isinstance(x, FArr) else x).reshape(-1) if isinstance(x, (FArr, np.ndarray)) else None
+                for x in args]
+        out = np.empty(int(np.prod(shape)))
+        for e in range(out.size):
+            out[e] = f(*[(fl[e].item() if fl is not None else x) for fl, x in zip(flat, args)])
+        return out.reshape(shape)
+    return g
+
+
+def _vec(fn):
+    def g(x, *rest):
+        if isinstance(x, np.ndarray):
+            return np.array([fn(v) for v in x.reshape(-1).tolist()]).reshape(x.shape)
+        return fn(x, *rest)
+    return g
+
+
+def _size(a, dim=None):
+    if dim is None:
+        return int(a.a.size)
+    return int(a.a.shape[a.nd - dim])
+
+
 def _r4(x):
     return float(np.float32(x))
 
@@ -123,8 +179,9 @@ def _nint(x, kind=None):
 
 INTRINSICS = {
     "_frange": _frange, "_div": _div, "_r4": _r4, "_alloc": _alloc, "_assignpnt": _assignpnt, "_farr": _farr,
-    "max": max, "min": min, "abs": abs, "sqrt": math.sqrt, "exp": math.exp, "log": math.log, "sin": math.sin,
-    "cos": math.cos, "tan": math.tan, "atan": math.atan, "mod": _mod, "sign": _sign, "real": _real, "int": _int,
+    "_pow": _pow, "_elemental": _elemental, "size": _size,
+    "max": max, "min": min, "abs": abs, "sqrt": _vec(math.sqrt), "exp": _vec(math.exp), "log": _vec(math.log),
+    "sin": _vec(math.sin), "cos": _vec(math.cos), "tan": math.tan, "atan": math.atan, "mod": _mod, "sign": _sign, "real": _real, "int": _int,
     "nint": _nint, "dble": float, "null": lambda: None,
     "rkx": 8, "rk8": 8, "rk4": 4, "rk16": 16, "ik4": 4, "ik8": 8, "wrkp": 8,
 }

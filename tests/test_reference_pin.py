@@ -33,8 +33,11 @@ CASES = R.golden_cases()
 TRANSCENDENTAL = {"p", "rho", "qsat", "ps", "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "ptrop"}
 
 
+SETUP = R.setup_cases()
+
+
 def test_golden_file_covers_every_case():
-    assert set(GOLDEN) == set(CASES)
+    assert set(GOLDEN) == set(CASES) | set(SETUP)
     for name, (wl, nsteps) in CASES.items():
         assert GOLDEN[name]["steps"] == nsteps and GOLDEN[name]["grid"] == [wl.jx, wl.iy, wl.kz]
         assert set(GOLDEN[name]["fields"]) == set(R.case_fields(wl))
@@ -64,6 +67,32 @@ def test_reference_phases_match_oracle():
     r.call("advection", r.ns["dtstepa"]); o.advection()
     for f in ("u", "v", "w", "pai", "tetav", "ux", "vx", "wx", "qx", "trac", "wz", "p0"):
         assert np.array_equal(r.get(f), o.get(f)), f"advection: {f}"
+
+
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+@pytest.mark.parametrize("case", list(SETUP))
+def test_reference_setup_matches_oracle(case):
+    """The set-up chain -- model_zitaf/h and the metric functions (Share/mod_zita.F90),
+    compute_moloch_static (Main/mod_params.F90:3316-3395), init_moloch (Main/mod_moloch.F90:201-308),
+    setup_bdywt and paicompute (Main/mod_bdycod.F90) -- executed from the reference source against the
+    oracle's restatement of it: every static field and the initial Exner function bit for bit."""
+    sr, o = R.run_setup_case(SETUP[case])
+    bad = [f for f in R.SETUP_FIELDS if not np.array_equal(sr.get(f), o.get(f))]
+    assert not bad, bad
+    for f in R.SETUP_FIELDS:
+        assert R.digest(sr.get(f))["sha256"] == GOLDEN[case]["fields"][f]["sha256"], f
+
+
+@pytest.mark.parametrize("case", list(SETUP))
+def test_oracle_setup_matches_reference_golden(case):
+    o, _ = make_oracle_bdy(SETUP[case])
+    for f, want in GOLDEN[case]["fields"].items():
+        got = R.digest(o.get(f))
+        if f in ("pai", "coru", "corv", "zeta", "fmz", "fmzf", "zetaf", "rfmzu", "rfmzv", "bdywtu", "bdywtv", "bdywtw"):
+            # exp/sin/pow inside: bytes on this libm, sums anywhere
+            assert abs(got["sum"] - want["sum"]) <= 1e-12 * abs(want["sum"]), f
+        else:
+            assert got["sha256"] == want["sha256"], f
 
 
 @pytest.mark.parametrize("case", list(CASES))

@@ -37,6 +37,7 @@ TOKEN = re.compile(r"""
 
 LOGIC = {".and.": " and ", ".or.": " or ", ".not.": " not ", ".true.": "True", ".false.": "False", ".eq.": "==",
          ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", ".eqv.": "==", ".neqv.": "!="}
+OUT_LAST = {"sumall", "maxall", "minall", "meanall"}
 TYPE_BOUND_CALLS = {"act", "advance", "str", "start", "integrating", "lcount"}
 DECL = re.compile(r"^(real|integer|logical|character|type|class|double precision|complex)\b")
 
@@ -357,7 +358,13 @@ class Translator:
                     if n in r.args:
                         continue
                     ex = Expr(arrays)
-                    if is_par and init is not None:
+                    if is_par and init is not None and init.lstrip().startswith(("[", "(/")):
+                        mm = re.match(r"^\s*(?:\[|\(/)(.*?)(?:\]|/\))\s*$", init)
+                        d = (shape[1:-1] if shape else dim.group(1)) if (dim or shape) else "1"
+                        lo = d.split(":")[0] if ":" in d else "1"
+                        vals = ", ".join(ex.tr(v.strip()) for v in split_top(mm.group(1), ","))
+                        pre.append(f"{pyname(n)} = _farr([{vals}], {ex.tr(lo)})")
+                    elif is_par and init is not None:
                         v = ex.tr(init)
                         if re.match(r"^real\s*\(\s*rk4\s*\)", spec):
                             v = f"_r4({v})"
@@ -471,7 +478,21 @@ class Translator:
             if s == "return":
                 emit(f"return {pyname(resname)}" if r.kind == "function" else "return")
                 return
-            if s.startswith(("write", "print", "flush", "!", "allocate", "deallocate")) or s == "continue":
+            m = re.match(r"^allocate\s*\((.*)\)$", s)
+            if m:
+                for one in split_top(m.group(1), ","):
+                    mm = re.match(r"^\s*(\w+)\s*\((.*)\)\s*$", one)
+                    if not mm:
+                        raise ValueError("allocate: " + s)
+                    bnds = []
+                    for d in split_top(mm.group(2), ","):
+                        lo, hi = d.split(":") if ":" in d else ("1", d)
+                        bnds.append(f"({ex.tr(lo.strip())}, {ex.tr(hi.strip())})")
+                    if mm.group(1) not in local_names:
+                        assigned.add(mm.group(1))
+                    emit(f"{pyname(mm.group(1))} = _alloc([{', '.join(bnds)}], 'float')")
+                return
+            if s.startswith(("write", "print", "flush", "!", "deallocate")) or s == "continue":
                 emit("pass")
                 return
             m = re.match(r"^call\s+([\w%]+)\s*(?:\((.*)\))?\s*$", s)
@@ -484,6 +505,19 @@ class Translator:
                         assigned.add(tgt)
                     extra = (", " + ex.tr(a[2])) if len(a) > 2 else ""
                     emit(f"{ex.tr(tgt, lhs=True)} = _assignpnt({ex.tr(a[0])}{extra})")
+                    return
+                if name == "getmem":        # getmem(a, l1,u1, l2,u2, ..., 'label') allocates the pointer a
+                    a = [x.strip() for x in split_top(args, ",")]
+                    if re.match(r"^\w+$", a[0]):
+                        assigned.add(a[0])
+                    nums = [ex.tr(x) for x in a[1:] if not x.startswith(("'", '"'))]
+                    emit(f"{ex.tr(a[0], lhs=True)} = _getmem({', '.join(nums)})")
+                    return
+                if name in OUT_LAST:        # MPI reductions with an output argument: call sumall(a, b) -> b = sumall(a)
+                    a = [x.strip() for x in split_top(args, ",")]
+                    if re.match(r"^\w+$", a[-1]):
+                        assigned.add(a[-1])
+                    emit(f"{ex.tr(a[-1], lhs=True)} = {name}({', '.join(ex.tr(x) for x in a[:-1])})")
                     return
                 targs = ", ".join(ex.tr(x.strip()) for x in split_top(args, ",") if x.strip())
                 emit(f"{'.'.join(pyname(p) for p in name.split('%'))}({targs})")

@@ -490,6 +490,68 @@ class SetupRun:
         return out
 
 
+class BdySetupRun:
+    """The reference's lateral-boundary set-up on one rank, executed from source: setup_boundaries
+    (Main/mod_atm_interface.F90:384-532) for ba_cr/ba_ud/ba_vd, setup_bdycon's MOLOCH branch with the Lehmann
+    coefficients (Main/mod_bdycod.F90:478-568; relax_coefficients, Main/mpplib/mod_runparams.F90:645-697) and
+    lowpass_init (Main/mod_bdycod.F90:3844-3896).  Input: the level heights zeta."""
+
+    def __init__(self, wl, zeta: np.ndarray):
+        from regcm_b200.decomp import make_geom
+        self.wl = wl
+        g = self.g = make_geom(wl.jx, wl.iy, wl.kz, wl.i_band, 0, 1, 1, 0)
+        ns = self.ns = dict(INTRINSICS)
+        ex = F.Expr(set())
+        for rel in ("Share/mod_constants.F90", "Main/mpplib/mod_runparams.F90", "Main/mod_bdycod.F90"):
+            for line in F.module_parameters(F.preprocess(open(os.path.join(REF, rel)).read()), ex):
+                try:
+                    exec(F.compile_source(line, rel), ns)
+                except Exception:
+                    pass
+        kz = wl.kz
+        for n in ("jde1", "jde2", "ide1", "ide2", "jce1", "jce2", "ice1", "ice2", "jci1", "jci2", "ici1", "ici2"):
+            ns[n] = getattr(g, n)
+        band = wl.i_band == 1
+        njcross, nicross = (wl.jx if band else wl.jx - 1), wl.iy - 1
+        ns.update(kz=kz, jx=wl.jx, iy=wl.iy, jxm1=wl.jx - 1, iym1=wl.iy - 1, nspgx=wl.nspgx, nspgd=wl.nspgx,
+                  njcross=njcross, nicross=nicross, ds=wl.ds_km, dx=wl.dx, dtsec=wl.dt, mo_nadv=wl.mo_nadv,
+                  mo_h=wl.mo_h, idynamic=3, dtbdys=wl.dtbdys, dtrad=wl.dtrad, myid=0, italk=0,
+                  mo_top_nudge=bool(wl.mo_top_nudge), mo_spectral_nudge=bool(wl.mo_spectral_nudge),
+                  bdy_use_lehmann=True, iboudy=5, rtb=0.0, nztop=0, km=0, lm=0, cn0=0.0,
+                  ma=_Obj(bandflag=band, crmflag=False), sumall=lambda x: x, vprntv=lambda *a: None,
+                  ba_cr=_Obj(), ba_ud=_Obj(), ba_vd=_Obj())
+        b = g.ext("cross", 0, 0)
+        zt = FArr.alloc([(b[0], b[1]), (b[2], b[3]), (1, kz)])
+        zt.a[...] = np.asarray(zeta)[:, b[2] - 1:b[3], b[0] - 1:b[1]]
+        ns["mo_atm"] = _Obj(zeta=zt)
+        # allocate_mod_bdycon (Main/mod_bdycod.F90:417-476)
+        ns.update(hefc=FArr.alloc([(1, wl.nspgx), (1, kz)]), gmeanz=FArr.alloc([(1, kz)]), tnudge=FArr.alloc([(1, kz)]),
+                  cnudge=FArr.alloc([(1, kz)]))
+        for n in ("bvx", "bvy", "sx", "sy", "sxg", "syg", "px", "py"):
+            ns[n] = None
+        arrays = {"hefc", "gmeanz", "tnudge", "cnudge", "bvx", "bvy", "sx", "sy", "sxg", "syg", "px", "py", "anudge",
+                  "coeff", "p", "q", "pp", "qq"}
+        tr = F.Translator(arrays)
+        ar = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mod_atm_interface.F90")).read()))
+        br = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mod_bdycod.F90")).read()))
+        rr = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mpplib/mod_runparams.F90")).read()))
+        self.sources = {}
+        for r, rel in ((ar["setup_boundaries"], "Main/mod_atm_interface.F90"),
+                       (rr["relax_coefficients"], "Main/mpplib/mod_runparams.F90"),
+                       (br["lowpass_init"], "Main/mod_bdycod.F90"), (br["setup_bdycon"], "Main/mod_bdycod.F90")):
+            src = tr.routine(r)
+            self.sources[r.name] = src
+            exec(F.compile_source(src, f"<{rel}:{r.name}>"), ns)
+
+    def run(self):
+        ns = self.ns
+        ns["setup_boundaries"](False, False, ns["ba_cr"])      # Main/mod_params.F90:2233-2238 (cross = .false.)
+        ns["setup_boundaries"](True, False, ns["ba_ud"])
+        ns["setup_boundaries"](False, True, ns["ba_vd"])
+        ns["setup_bdycon"]()
+        return self
+
+
 SETUP_FIELDS = ["hx", "hy", "zeta", "fmz", "fmzf", "zetaf", "rfmzu", "rfmzv", "coru", "corv", "mx2", "rmx", "rmu", "rmv",
                 "gzitak", "gzitakh", "xkdamp", "xknu", "bdywtu", "bdywtv", "bdywtw", "pai"]
 

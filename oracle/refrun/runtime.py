@@ -41,7 +41,7 @@ class FArr:
                     raise IndexError(f"section {x} outside bounds {self.bounds()[d]}")
                 out.append(slice(lo, hi))
             else:
-                o = x - self.lb[d]
+                o = int(x) - self.lb[d]
                 if o < 0 or o >= n:
                     raise IndexError(f"subscript {d + 1} = {x} outside bounds {self.bounds()[d]}")
                 out.append(o)
@@ -52,9 +52,26 @@ class FArr:
             return self.a
         o = self._off(idx)
         v = self.a[o]
-        return v.item() if not isinstance(v, np.ndarray) else v
+        if not isinstance(v, np.ndarray):
+            return v.item()
+        return FArr(v, [1] * v.ndim)       # an array section: a view, lower bounds 1 (assumed-shape dummy semantics)
+
+    # whole-array arithmetic (sections in expressions): element-wise on the storage
+    def __array__(self, dtype=None, copy=None):
+        return self.a if dtype is None else self.a.astype(dtype)
+
+    def __mul__(self, o): return self.a * (o.a if isinstance(o, FArr) else o)
+    def __rmul__(self, o): return (o.a if isinstance(o, FArr) else o) * self.a
+    def __add__(self, o): return self.a + (o.a if isinstance(o, FArr) else o)
+    def __radd__(self, o): return (o.a if isinstance(o, FArr) else o) + self.a
+    def __sub__(self, o): return self.a - (o.a if isinstance(o, FArr) else o)
+    def __rsub__(self, o): return (o.a if isinstance(o, FArr) else o) - self.a
+    def __truediv__(self, o): return self.a / (o.a if isinstance(o, FArr) else o)
+    def __neg__(self): return -self.a
 
     def __setitem__(self, idx, v):
+        if isinstance(v, FArr):
+            v = v.a
         if idx is Ellipsis:
             self.a[...] = v
             return
@@ -124,6 +141,8 @@ def _elemental(f):
 
 def _vec(fn):
     def g(x, *rest):
+        if isinstance(x, FArr):
+            x = x.a
         if isinstance(x, np.ndarray):
             return np.array([fn(v) for v in x.reshape(-1).tolist()]).reshape(x.shape)
         return fn(x, *rest)
@@ -147,6 +166,11 @@ def _alloc(bounds, kind):
 def _farr(vals, lo):
     allint = all(isinstance(v, int) for v in vals)
     return FArr(np.array(vals, dtype=np.int64 if allint else np.float64), [lo])
+
+
+def _getmem(*b):
+    """getmem(a, l1,u1, l2,u2, ...): a zero-initialised array with those bounds (Share/mod_memutil.F90)."""
+    return FArr.alloc([(b[k], b[k + 1]) for k in range(0, len(b) - 1, 2)])
 
 
 def _assignpnt(a, n=None):
@@ -178,7 +202,7 @@ def _nint(x, kind=None):
 
 
 INTRINSICS = {
-    "_frange": _frange, "_div": _div, "_r4": _r4, "_alloc": _alloc, "_assignpnt": _assignpnt, "_farr": _farr,
+    "_frange": _frange, "_div": _div, "_r4": _r4, "_alloc": _alloc, "_assignpnt": _assignpnt, "_farr": _farr, "_getmem": _getmem,
     "_pow": _pow, "_elemental": _elemental, "size": _size,
     "max": max, "min": min, "abs": abs, "sqrt": _vec(math.sqrt), "exp": _vec(math.exp), "log": _vec(math.log),
     "sin": _vec(math.sin), "cos": _vec(math.cos), "tan": math.tan, "atan": math.atan, "mod": _mod, "sign": _sign, "real": _real, "int": _int,

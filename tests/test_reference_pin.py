@@ -83,6 +83,31 @@ def test_reference_setup_matches_oracle(case):
         assert R.digest(sr.get(f))["sha256"] == GOLDEN[case]["fields"][f]["sha256"], f
 
 
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+@pytest.mark.parametrize("band", [0, 1])
+def test_reference_boundary_setup_matches(band):
+    """setup_boundaries (ba%ibnd of the three staggerings), setup_bdycon's MOLOCH branch with the Lehmann
+    coefficients, relax_coefficients and lowpass_init executed from the reference source, against the
+    oracle's and the host model's restatements: ibnd, hefc, gmeanz, nztop, tnudge, km, lm, bvx, bvy, cnudge
+    bit for bit."""
+    from regcm_b200 import synthetic as S
+    wl = S.small(S.WORKLOADS["cordex25"], 40, 36, 8, ntr=1, nspgx=6, do_bdy=1, mo_top_nudge=1, mo_spectral_nudge=1,
+                 ds_km=100.0, dtrad=150.0, dt=150.0, i_band=band, oro="sine" if band else "gauss")
+    o, _ = make_oracle_bdy(wl)
+    ns = R.BdySetupRun(wl, o.get("zeta")).run().ns
+    T = S.bdycon_setup(wl, o.get("zeta"))
+    for which, nm in (("cr", "ba_cr"), ("ud", "ba_ud"), ("vd", "ba_vd")):
+        assert np.array_equal(ns[nm].ibnd.a.astype(int), T["ibnd"][which]), nm
+    assert (ns["nztop"], ns["km"], ns["lm"]) == (o.get_int("nztop"), o.get_int("km"), o.get_int("lm")) == \
+        (T["nztop"], T["km"], T["lm"])
+    for n in ("gmeanz", "tnudge", "cnudge"):
+        assert np.array_equal(ns[n].a, o.get(n)), n
+    km, lm = ns["km"], ns["lm"]
+    assert np.array_equal(ns["bvx"].a, np.array(o.get("bvx")).reshape(2 * km, wl.jx))
+    assert np.array_equal(ns["bvy"].a, np.array(o.get("bvy")).reshape(2 * lm, wl.iy))
+    assert np.array_equal(ns["hefc"].a, S.hefc_lehmann(wl))
+
+
 @pytest.mark.parametrize("case", list(SETUP))
 def test_oracle_setup_matches_reference_golden(case):
     o, _ = make_oracle_bdy(SETUP[case])

@@ -552,6 +552,51 @@ class BdySetupRun:
         return self
 
 
+def reference_massck(wl, o) -> dict:
+    """massck (Main/mod_massck.F90:58-372) executed from source on the oracle's current state (one rank).
+    Its sums are local variables; they are observed through the routine's own `call sumall(x, y)` reductions,
+    which a one-rank run turns into y = x: tdrym, tqmass, tqadv, tdadv, tcrai, tncrai, tqeva in call order."""
+    from regcm_b200.decomp import make_geom
+    g = make_geom(wl.jx, wl.iy, wl.kz, wl.i_band, wl.i_crm, 1, 1, 0)
+    ns = dict(INTRINSICS)
+    ex = F.Expr(set())
+    for rel in ("Share/mod_constants.F90", "Main/mpplib/mod_runparams.F90", "Main/mod_massck.F90"):
+        for line in F.module_parameters(F.preprocess(open(os.path.join(REF, rel)).read()), ex):
+            try:
+                exec(F.compile_source(line, rel), ns)
+            except Exception:
+                pass
+    for n in ("jde1", "jde2", "ide1", "ide2", "jce1", "jce2", "ice1", "ice2", "jci1", "jci2", "ici1", "ici2"):
+        ns[n] = getattr(g, n)
+    seen = []
+
+    def sumall(x):
+        seen.append(x)
+        return x
+    kz = wl.kz
+
+    def fa(name, stag, nk=0, nspec=0):
+        b = g.ext(stag, 0, 0)
+        a = np.asarray(o.get(name))[..., b[2] - 1:b[3], b[0] - 1:b[1]]
+        return FArr(np.array(a, dtype=np.float64), [b[0], b[2]] + ([1] if nk else []) + ([1] if nspec else []))
+    zf = fa("zetaf", "cross", kz + 1)
+    dz = FArr(zf.a[:-1] - zf.a[1:], zf.lb)                        # Main/mod_params.F90:3389
+    cb = g.ext("cross", 0, 0)
+    zero2 = FArr.alloc([(cb[0], cb[1]), (cb[2], cb[3])])
+    ns.update(kz=kz, nqx=wl.nqx, idynamic=3, dt=wl.dt, dx=wl.dx, dxsq=wl.dx * wl.dx, myid=0, italk=0, sumall=sumall,
+              ma=_Obj(has_bdyleft=g.bl, has_bdyright=g.br, has_bdybottom=g.bb, has_bdytop=g.bt),
+              mo_atm=_Obj(dz=dz, rho=fa("rho", "cross", kz), u=fa("u", "u", kz), v=fa("v", "v", kz),
+                          qx=fa("qx", "cross", kz, wl.nqx)),
+              crrate=zero2, ncrrate=zero2, sfs=_Obj(qfx=zero2), rcmtimer=_Obj(start=lambda: False),
+              alarm_day=_Obj(act=lambda: False), syncro_dbg=_Obj(act=lambda: False),
+              dryini=0.0, watini=0.0, dryerror=0.0, waterror=0.0, mcrai=0.0, mncrai=0.0, mevap=0.0, mdryadv=0.0,
+              mqadv=0.0)
+    r = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mod_massck.F90")).read()))["massck"]
+    exec(F.compile_source(F.Translator({"crrate", "ncrrate", "dsigma"}).routine(r), "<Main/mod_massck.F90:massck>"), ns)
+    ns["massck"]()
+    return dict(zip(("tdrym", "tqmass", "tqadv", "tdadv", "tcrai", "tncrai", "tqeva"), seen))
+
+
 SETUP_FIELDS = ["hx", "hy", "zeta", "fmz", "fmzf", "zetaf", "rfmzu", "rfmzv", "coru", "corv", "mx2", "rmx", "rmu", "rmv",
                 "gzitak", "gzitakh", "xkdamp", "xknu", "bdywtu", "bdywtv", "bdywtw", "pai"]
 

@@ -108,6 +108,20 @@ def test_reference_boundary_setup_matches(band):
     assert np.array_equal(ns["hefc"].a, S.hefc_lehmann(wl))
 
 
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+def test_reference_massck_matches_oracle():
+    """massck's atmosphere sums (Main/mod_massck.F90:77-185) executed from source == the oracle's, bit for bit
+    (same single running sums); the device's row-wise sums are compared with these to 1e-12."""
+    from regcm_b200 import synthetic as S
+    wl = S.small(S.WORKLOADS["cordex25"], 20, 18, 8, ntr=1, nspgx=4, do_massck=1)
+    o, _ = make_oracle_bdy(wl)
+    o.step(1)
+    ref = R.reference_massck(wl, o)
+    dry, dadv, wat, wadv = o.massck()
+    assert (ref["tdrym"], ref["tdadv"], ref["tqmass"], ref["tqadv"]) == (dry, dadv, wat, wadv)
+    assert ref["tcrai"] == ref["tncrai"] == ref["tqeva"] == 0.0
+
+
 @pytest.mark.parametrize("case", list(SETUP))
 def test_oracle_setup_matches_reference_golden(case):
     o, _ = make_oracle_bdy(SETUP[case])

@@ -636,6 +636,11 @@ def golden_cases():
         # spectral nudging active every step (dtrad == dt), no ICBC condensate
         "limited_area_spectral": (S.small(lam, 18, 16, 6, do_bdy=1, mo_top_nudge=1, mo_spectral_nudge=1, ichebdy=1,
                                           ds_km=150.0, dtrad=150.0, dt=150.0), 3),
+        # periodic in j (band) with south/north boundaries and sponge; no divergence damping / filter; vapour only
+        "band_boundary": (S.small(lam, 16, 14, 6, i_band=1, oro="sine", do_bdy=1, present_qc=1, mo_top_nudge=1,
+                                  mo_ztop=30000.0), 2),
+        "no_damp_no_filter": (S.small(lam, 14, 12, 6, mo_divdamp=0, mo_divfilter=0, ntr=0), 1),
+        "vapour_only": (S.small(lam, 14, 12, 6, ipptls=0, nqx=1, ntr=0, do_bdy=1), 2),
         # UW-PBL TKE advected by the dycore, with its boundary values
         "limited_area_tke": (S.small(lam, 16, 14, 8, do_bdy=1, present_qc=1, ibltyp=2, tkemin=1.0e-4, ipptls=1,
                                      nqx=2), 2),

@@ -49,7 +49,8 @@ class _Proxy:
         lib.emu_b200_set_calday.argtypes = [ctx, C.c_double, C.c_double]
         lib.emu_b200_massck.argtypes = [ctx, C.c_void_p]
         lib.emu_b200_ps_check.argtypes = [ctx, C.c_void_p, C.c_void_p]
-        for f in ("destroy", "init", "bdyval", "boundary", "mkslice", "tke_destagger", "tke_restagger", "tke_update"):
+        for f in ("destroy", "init", "bdyval", "boundary", "boundary_pre", "boundary_post", "mkslice", "tke_destagger",
+                  "tke_restagger", "tke_update"):
             getattr(lib, "emu_b200_" + f).argtypes = [ctx]
 
     def __getattr__(self, name):
@@ -59,9 +60,9 @@ class _Proxy:
 
 
 class EmuMoloch(MolochB200):
-    def __init__(self, wl, bdy=None, order=0):
+    def __init__(self, wl, bdy=None, order=0, rank=0, nranks=1, px=None, py=None):
         lib = C.CDLL(build())
-        super().__init__(wl, bdy=bdy, lib=_Proxy(lib))
+        super().__init__(wl, rank=rank, nranks=nranks, px=px, py=py, bdy=bdy, lib=_Proxy(lib))
         self._emu = lib
         self._order = order
 
@@ -69,6 +70,9 @@ class EmuMoloch(MolochB200):
         super().allocate_moloch()
         self._emu.emu_b200_set_order(self.ctx, self._order)
         return self
+
+    def boundary_pre(self): self._chk(self._emu.emu_b200_boundary_pre(self.ctx))
+    def boundary_post(self): self._chk(self._emu.emu_b200_boundary_post(self.ctx))
 
     def tke_destagger(self): self._chk(self._emu.emu_b200_tke_destagger(self.ctx))
     def tke_restagger(self): self._chk(self._emu.emu_b200_tke_restagger(self.ctx))

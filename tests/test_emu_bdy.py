@@ -164,3 +164,63 @@ def test_massck_and_ps_guard_cells(order):
     m.set_global("ps", ps)
     mx, mn, bad = m.ps_check()
     assert bad == 2 and np.isfinite(mx) and np.isfinite(mn)
+
+
+@pytest.mark.parametrize("px,py", [(2, 1), (1, 2), (2, 2), (3, 2)])
+@pytest.mark.parametrize("case", ["lam_full", "band", "lam_tke"])
+def test_boundary_cells_decomposed(case, px, py):
+    """The N>1 path of `boundary` on the CPU: one context per rank of a px x py decomposition, the device
+    cell functions on every rank, the u/v halo round moved between the contexts with the library's own
+    halo plan -- against the single-domain oracle, bit for bit.  Covers ranks with a physical boundary on
+    some sides and neighbours on the others."""
+    from regcm_b200 import moloch as M
+    wl = CASES[case]
+    o, B = make_oracle_bdy(wl)
+    o.step(1)
+    n = px * py
+    tabs = bdy_tables_from_oracle(wl, o)
+    ranks = []
+    for r in range(n):
+        m = EmuMoloch(wl, bdy=tabs, rank=r, nranks=n, px=px, py=py).allocate_moloch()
+        for f in STATE_FIELDS:
+            if f == "trac" and wl.ntr == 0:
+                continue
+            m.set_global(f, o.get(f))
+        if wl.ibltyp == 2:
+            m.set_global("tke", o.get("tke"))
+        m.init_boundary()
+        m.load_boundary(B)
+        m.set_xbctime(o.get_xbctime())
+        ranks.append(m)
+    for m in ranks:
+        m.boundary_pre()
+    # exchange_lr(u,2) and exchange_bt(v,2) of uvstagtouvx (Main/mod_moloch.F90:1532-1533)
+    opposite = [1, 0, 3, 2]
+    for name, stag, lr, bt in (("u", 1, True, False), ("v", 2, False, True)):
+        plans = [M.halo_plan(m.cfg, stag, 2, lr, bt) for m in ranks]
+        msgs = []
+        for r, m in enumerate(ranks):
+            nb = [m.g.left, m.g.right, m.g.bottom, m.g.top]
+            for sd in range(4):
+                rb = plans[r][1][sd]
+                if rb[0] > rb[1]:
+                    continue
+                sb = plans[nb[sd]][0][opposite[sd]]
+                msgs.append((r, tuple(int(x) for x in rb), ranks[nb[sd]].get_local(name, tuple(int(x) for x in sb))))
+        for r, rb, data in msgs:
+            ranks[r].set_local(name, data, rb)
+    for m in ranks:
+        m.boundary_post()
+    o.boundary()
+    names = STATE + (["tke"] if wl.ibltyp == 2 else [])
+    bad = []
+    for f in names:
+        if f == "trac" and wl.ntr == 0:
+            continue
+        glob = np.zeros(ranks[0].global_shape(f))
+        for m in ranks:
+            m.get_into_global(f, glob)
+        if not np.array_equal(glob, o.get(f)):
+            bad.append(f)
+    assert not bad, bad
+    assert all(m.get_xbctime() == o.get_xbctime() for m in ranks)

@@ -417,7 +417,7 @@ struct MassArgs {
   Geo g;
   const double *rho, *zq, *qx, *u, *v, *ps;
   double *rows;     // [2][kz*ni]: row sums of dry mass and water mass
-  double *lev;      // [2][kz]: boundary flux sums of one level (dry, water)
+  double *lev;      // [4][kz]: per level: boundary flux sums (dry, water), interior sums (dry, water)
   double *psrow;    // [3][ni]: row max, row min, non-finite count of ps
   double *out;      // tdrym, tdadv, tqmass, tqadv, psmax, psmin, nonfinite
   double dxsq, dt, dx;
@@ -445,10 +445,18 @@ MB_HD void massck_row(const MassArgs& a, int i, int k) {
   a.rows[r] = dry;
   a.rows[(long long)g.kz * a.ni + r] = wat;
 }
-// boundary fluxes of one level (:85-118, :150-185)
+// one level: the level's row sums added in row order, and its boundary fluxes (:85-118, :150-185)
 MB_HD void massck_bdy_level(const MassArgs& a, int k) {
   const Geo& g = a.g;
   const long long sp = (long long)g.kz * g.plane;
+  const long long nr = (long long)g.kz * a.ni;
+  double rd = 0.0, rw = 0.0;
+  for (int r = 0; r < a.ni; ++r) {
+    rd = rd + a.rows[(long long)(k - 1) * a.ni + r];
+    rw = rw + a.rows[nr + (long long)(k - 1) * a.ni + r];
+  }
+  a.lev[2 * g.kz + k - 1] = rd;
+  a.lev[3 * g.kz + k - 1] = rw;
   double dry = 0.0, wat = 0.0;
   for (int pass = 0; pass <= g.nqx; ++pass) {   // pass 0: dry air, pass n: water species n
     double acc = 0.0;
@@ -486,13 +494,14 @@ MB_HD void ps_row(const MassArgs& a, int i) {
     }
   a.psrow[i - g.ice1] = mx; a.psrow[a.ni + i - g.ice1] = mn; a.psrow[2 * a.ni + i - g.ice1] = bad;
 }
-// final sums, one thread: rows level by level, then the levels' boundary sums
+// final sums, one thread: the kz level sums
 MB_HD void massck_final(const MassArgs& a) {
   const Geo& g = a.g;
-  const long long nr = (long long)g.kz * a.ni;
   double dry = 0.0, wat = 0.0, fd = 0.0, fw = 0.0;
-  for (long long r = 0; r < nr; ++r) { dry = dry + a.rows[r]; wat = wat + a.rows[nr + r]; }
-  for (int k = 0; k < g.kz; ++k) { fd = fd + a.lev[k]; fw = fw + a.lev[g.kz + k]; }
+  for (int k = 0; k < g.kz; ++k) {
+    fd = fd + a.lev[k]; fw = fw + a.lev[g.kz + k];
+    dry = dry + a.lev[2 * g.kz + k]; wat = wat + a.lev[3 * g.kz + k];
+  }
   double mx = -1.0e300, mn = 1.0e300, bad = 0.0;
   for (int i = 0; i < a.ni; ++i) {
     if (a.psrow[i] > mx) mx = a.psrow[i];

@@ -200,7 +200,7 @@ __global__ void moloch_massck_final(MassArgs a) { massck_final(a); }
 int k_massck(Ctx& c, int what, double* out7) {
   const Geo& g = c.g;
   const int ni = g.ice2 - g.ice1 + 1, kz = g.kz;
-  const size_t need = (size_t)2 * kz * ni + 2 * kz + 3 * ni + 8;
+  const size_t need = (size_t)2 * kz * ni + 4 * kz + 3 * ni + 8;
   if (c.mass_work_doubles < need) {
     if (c.mass_work) cudaFree(c.mass_work);
     MB_CUDA(cudaMalloc(&c.mass_work, need * sizeof(double)));
@@ -212,7 +212,7 @@ int k_massck(Ctx& c, int what, double* out7) {
   a.g = g;
   a.rho = c.f[MB_RHO].p; a.zq = c.f[MB_ZETAF].p; a.qx = c.f[MB_QX].p; a.u = c.f[MB_U].p; a.v = c.f[MB_V].p;
   a.ps = c.f[MB_PS].p;
-  a.rows = c.mass_work; a.lev = a.rows + (size_t)2 * kz * ni; a.psrow = a.lev + 2 * kz; a.out = a.psrow + 3 * ni;
+  a.rows = c.mass_work; a.lev = a.rows + (size_t)2 * kz * ni; a.psrow = a.lev + 4 * kz; a.out = a.psrow + 3 * ni;
   a.dxsq = c.cfg.dx * c.cfg.dx; a.dt = c.cfg.dtsec; a.dx = c.cfg.dx; a.ni = ni;
   if (what & 1) {
     if (!a.zq) return fail("massck: zq (MB_ZETAF) is not on the device (moloch_b200_config.do_massck)");

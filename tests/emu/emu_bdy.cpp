@@ -266,12 +266,12 @@ int emu_b200_mkslice(void* h) {   // = k_mkslice
 int emu_b200_massck7(void* h, int what, double* out7) {
   Emu& e = *(Emu*)h; const Geo& g = e.g; const int o = e.order;
   const int ni = g.ice2 - g.ice1 + 1, kz = g.kz;
-  std::vector<double> work((size_t)2 * kz * ni + 2 * kz + 3 * ni + 8, 0.0);
+  std::vector<double> work((size_t)2 * kz * ni + 4 * kz + 3 * ni + 8, 0.0);
   MassArgs a;
   std::memset(&a, 0, sizeof(a));
   a.g = g;
   a.rho = P(e, MB_RHO); a.zq = P(e, MB_ZETAF); a.qx = P(e, MB_QX); a.u = P(e, MB_U); a.v = P(e, MB_V); a.ps = P(e, MB_PS);
-  a.rows = work.data(); a.lev = a.rows + (size_t)2 * kz * ni; a.psrow = a.lev + 2 * kz; a.out = a.psrow + 3 * ni;
+  a.rows = work.data(); a.lev = a.rows + (size_t)2 * kz * ni; a.psrow = a.lev + 4 * kz; a.out = a.psrow + 3 * ni;
   a.dxsq = e.cfg.dx * e.cfg.dx; a.dt = e.cfg.dtsec; a.dx = e.cfg.dx; a.ni = ni;
   if (what & 1) {
     if (!a.zq) return fail("emu: do_massck not configured");

@@ -75,6 +75,8 @@ typedef struct {
   double dtbdys, dtrad;               /* boundary / radiation period [s]         */
   double rhmin, rhmax, tkemin;        /* Main/mod_params.F90:381-382, mod_pbl_interface.F90:50 */
   int32_t irceideal;                  /* 1: mkslice keeps ptrop as it is (Main/mod_slice.F90:345) */
+  int32_t idiag, ichdiag;             /* > 0: tendency diagnostics of dynamical_core and boundary
+                                         (Main/mod_moloch.F90:1092-1103,1127-1139,455-466,508-519) */
   int32_t reserved3;
 } moloch_b200_config;
 
@@ -100,6 +102,9 @@ enum moloch_b200_field {
   /* common tail of mkslice (:342-384): input mddom%xlat; outputs ptrop and the level indices ktrop,
    * kmxpbl (integer-valued, carried as real(rk8) across the ABI); do_slice                       */
   MB_XLAT, MB_PTROP, MB_KTROP, MB_KMXPBL,
+  /* idiag > 0: ten0, qen0 and tdiag%adh, qdiag%adh, tdiag%bdy, qdiag%bdy; ichdiag > 0 (with tracers):
+   * chiten0 and cadvhdiag, cbdydiag (ntr species)                                              */
+  MB_TEN0, MB_QEN0, MB_TDIAG_ADH, MB_QDIAG_ADH, MB_TDIAG_BDY, MB_QDIAG_BDY, MB_CHITEN0, MB_CADVHDIAG, MB_CBDYDIAG,
   MB_NFIELDS
 };
 

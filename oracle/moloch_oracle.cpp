@@ -219,6 +219,9 @@ struct Rank {
   Arr pf3d, th3d, rhb3d, wpx3d, rhox2d, tp2d, th700, xlat, ptrop, ktrop, kmxpbl;
   // mospectral_nudge work arrays (Main/mod_bdycod.F90:422, :3868-3873), contiguous like the Fortran ones
   Arr zn1; std::vector<double> sx, sxg, sy, syg;
+  // tendency diagnostics [F90:187-192], tdiag%adh/bdy, qdiag%adh/bdy, cadvhdiag, cbdydiag
+  Arr ten0, qen0, tdiag_adh, qdiag_adh, tdiag_bdy, qdiag_bdy;
+  std::vector<Arr> chiten0, cadvhdiag, cbdydiag;
   std::map<std::string, FieldInfo> reg;
 };
 
@@ -473,6 +476,18 @@ void alloc_ext(World& w, Rank& r) {
   R("pf3d", &r.pf3d, S_CROSS, kzp1); R("th3d", &r.th3d, S_CROSS, kz); R("rhb3d", &r.rhb3d, S_CROSS, kz);
   R("wpx3d", &r.wpx3d, S_CROSS, kz); R("rhox2d", &r.rhox2d, S_CROSS, 1); R("tp2d", &r.tp2d, S_CROSS, 1);
   R("th700", &r.th700, S_CROSS, 1);
+  if (w.x.idiag > 0) {
+    for (Arr* a : {&r.ten0, &r.qen0, &r.tdiag_adh, &r.qdiag_adh, &r.tdiag_bdy, &r.qdiag_bdy})
+      a->alloc(g.jci1, g.jci2, g.ici1, g.ici2, 1, kz);
+    R("ten0", &r.ten0, S_CROSS, kz); R("qen0", &r.qen0, S_CROSS, kz);
+    R("tdiag_adh", &r.tdiag_adh, S_CROSS, kz); R("qdiag_adh", &r.qdiag_adh, S_CROSS, kz);
+    R("tdiag_bdy", &r.tdiag_bdy, S_CROSS, kz); R("qdiag_bdy", &r.qdiag_bdy, S_CROSS, kz);
+  }
+  if (w.x.ichdiag > 0 && w.x.ichem == 1 && w.ntr > 0)
+    for (auto* v : {&r.chiten0, &r.cadvhdiag, &r.cbdydiag}) {
+      v->resize(w.ntr);
+      for (auto& a : *v) a.alloc(g.jci1, g.jci2, g.ici1, g.ici2, 1, kz);
+    }
   r.xlat.alloc(g.jde1, g.jde2, g.ide1, g.ide2);
   for (Arr* a : {&r.ptrop, &r.ktrop, &r.kmxpbl}) a->alloc(g.jci1, g.jci2, g.ici1, g.ici2);
   R("xlat", &r.xlat, S_CROSS, 1); R("ptrop", &r.ptrop, S_CROSS, 1); R("ktrop", &r.ktrop, S_CROSS, 1);
@@ -531,6 +546,9 @@ bool lookup(World& w, Rank& r, const std::string& name, std::vector<FieldInfo>& 
   if (name == "trac") { for (auto& a : r.trac) out.push_back({&a, S_CROSS, kz}); return true; }
   if (name == "qxten") { for (auto& a : r.qxten) out.push_back({&a, S_CROSS, kz}); return true; }
   if (name == "chiten") { for (auto& a : r.chiten) out.push_back({&a, S_CROSS, kz}); return true; }
+  if (name == "chiten0") { for (auto& a : r.chiten0) out.push_back({&a, S_CROSS, kz}); return !r.chiten0.empty(); }
+  if (name == "cadvhdiag") { for (auto& a : r.cadvhdiag) out.push_back({&a, S_CROSS, kz}); return !r.cadvhdiag.empty(); }
+  if (name == "cbdydiag") { for (auto& a : r.cbdydiag) out.push_back({&a, S_CROSS, kz}); return !r.cbdydiag.empty(); }
   if (name == "chib0") { for (auto& a : r.chib0) out.push_back({&a, S_CROSS, kz}); return !r.chib0.empty(); }
   if (name == "chib1") { for (auto& a : r.chib1) out.push_back({&a, S_CROSS, kz}); return !r.chib1.empty(); }
   auto it = r.reg.find(name);
@@ -1189,8 +1207,45 @@ void tvirt_to_temp(World& w) {
   });
 }
 
-// dynamical_core [F90:1085-1141] (idiag = 0, ichdiag = 0)
+// tendency diagnostics: snapshots [F90:1092-1103, 455-466] and differences [F90:1127-1139, 508-519]
+void diag_snapshot(World& w) {
+  if (!w.ext_set) return;
+  const int kz = w.c.kz;
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g;
+    if (w.x.idiag > 0) {
+      PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+        r.ten0(j, i, k) = r.t(j, i, k); r.qen0(j, i, k) = r.qx[0](j, i, k);
+      }
+    }
+    for (size_t n = 0; n < r.chiten0.size(); ++n)
+      for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+        r.chiten0[n](j, i, k) = r.trac[n](j, i, k);
+  });
+}
+void diag_difference(World& w, bool bdy) {
+  if (!w.ext_set) return;
+  const int kz = w.c.kz; const double rdt = 1.0 / w.dtsec;
+  each(w, [&](Rank& r) {
+    const Geom& g = r.g;
+    if (w.x.idiag > 0) {
+      Arr& dt_ = bdy ? r.tdiag_bdy : r.tdiag_adh; Arr& dq_ = bdy ? r.qdiag_bdy : r.qdiag_adh;
+      PAR2 for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j) {
+        dt_(j, i, k) = (r.t(j, i, k) - r.ten0(j, i, k)) * rdt;
+        dq_(j, i, k) = (r.qx[0](j, i, k) - r.qen0(j, i, k)) * rdt;
+      }
+    }
+    for (size_t n = 0; n < r.chiten0.size(); ++n) {
+      Arr& dc = bdy ? r.cbdydiag[n] : r.cadvhdiag[n];
+      for (int k = 1; k <= kz; ++k) for (int i = g.ici1; i <= g.ici2; ++i) for (int j = g.jci1; j <= g.jci2; ++j)
+        dc(j, i, k) = (r.trac[n](j, i, k) - r.chiten0[n](j, i, k)) * rdt;
+    }
+  });
+}
+
+// dynamical_core [F90:1085-1141]
 void dynamical_core(World& w) {
+  diag_snapshot(w);
   const int kz = w.c.kz;
   for (int nadv = 1; nadv <= w.c.mo_nadv; ++nadv) {
     sound(w, w.dtsound);
@@ -1202,6 +1257,7 @@ void dynamical_core(World& w) {
       r.tvirt(j, i, k) = r.tetav(j, i, k) * r.pai(j, i, k);
   });
   tvirt_to_temp(w);
+  diag_difference(w, false);
 }
 
 // moloch [F90:348-354] + extrapolate_surface_pressure [F90:1592-1606]
@@ -1601,11 +1657,14 @@ void mospectral_nudge(World& w, const RangeFn& range, const ArrFn& getf, const A
   }
 }
 
-// boundary [F90:448-529] (idiag = 0, ichdiag = 0)
+// boundary [F90:448-529]
 void uvstagtouvx(World& w);
 void temp_to_tvirt(World& w);
+void diag_snapshot(World& w);
+void diag_difference(World& w, bool bdy);
 void boundary(World& w) {
   const int kz = w.c.kz;
+  diag_snapshot(w);
   bdyval(w);
   if (w.x.mo_top_nudge) motopnudge(w, 0.0, w.dtsec);
   morelax_external(w, S_U, [](Rank& r) -> Arr& { return r.u; }, [](Rank& r) -> Arr& { return r.dub0; },
@@ -1643,6 +1702,7 @@ void boundary(World& w) {
                        [](Rank& r) -> Arr& { return r.dvb1; });
     }
   }
+  diag_difference(w, true);
   uvstagtouvx(w);
   temp_to_tvirt(w);
   each(w, [&](Rank& r) {

@@ -67,11 +67,13 @@ typedef struct {
   int ibltyp;                  /* 2: TKE is a prognostic, advected variable         */
   int icldmstrat;              /* 1: mkslice finds theta at 700 hPa                 */
   int do_slice;                /* call mkslice inside oracle_step                   */
-  int bdy_lehmann;             /* unused by the oracle (hefc is an input table)     */
+  int idiag;                   /* > 0: tdiag%adh/bdy, qdiag%adh/bdy [F90:1092,1127,455,508] */
   int irceideal;               /* 1: mkslice keeps ptrop (Main/mod_slice.F90:345)   */
   double dtbdys, dtrad;        /* boundary / radiation periods [s]                  */
   double rhmin, rhmax, tkemin; /* Main/mod_params.F90:381-382, mod_pbl_interface:50 */
   double calday, dayspy;       /* calendar day / days per year for mkslice's ptrop  */
+  int ichdiag;                 /* > 0: cadvhdiag, cbdydiag                          */
+  int reserved;
 } oracle_ext_config;
 
 void*  oracle_create(const oracle_config* cfg);

@@ -24,8 +24,9 @@ class OracleConfig(C.Structure):
 class OracleExtConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "do_bdy", "present_qc", "present_qi", "mo_top_nudge", "mo_spectral_nudge", "ichem", "ichebdy",
-        "ibltyp", "icldmstrat", "do_slice", "bdy_lehmann", "irceideal")] + [
-        (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin", "calday", "dayspy")]
+        "ibltyp", "icldmstrat", "do_slice", "idiag", "irceideal")] + [
+        (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin", "calday", "dayspy")] + [
+        (n, C.c_int) for n in ("ichdiag", "reserved")]
 
 
 def build(force: bool = False) -> None:
@@ -89,7 +90,7 @@ class Oracle:
             self.ext = OracleExtConfig(do_bdy=wl.do_bdy, present_qc=wl.present_qc, present_qi=wl.present_qi,
                                        mo_top_nudge=wl.mo_top_nudge, mo_spectral_nudge=wl.mo_spectral_nudge,
                                        ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, ibltyp=wl.ibltyp,
-                                       icldmstrat=wl.icldmstrat, do_slice=wl.do_slice, bdy_lehmann=0,
+                                       icldmstrat=wl.icldmstrat, do_slice=wl.do_slice, idiag=wl.idiag, ichdiag=wl.ichdiag, reserved=0,
                                        irceideal=wl.irceideal, dtbdys=wl.dtbdys, dtrad=wl.dtrad, rhmin=wl.rhmin,
                                        rhmax=wl.rhmax, tkemin=wl.tkemin, calday=wl.calday, dayspy=wl.dayspy)
             self._chk(self.lib.oracle_set_ext(self.h, C.byref(self.ext)))
@@ -125,7 +126,7 @@ class Oracle:
             nk = n // plane
             if name in ("qx", "qxten"):
                 return out.reshape(wl.nqx, wl.kz, wl.iy, wl.jx)
-            if name in ("trac", "chiten", "chib0", "chib1"):
+            if name in ("trac", "chiten", "chib0", "chib1", "chiten0", "cadvhdiag", "cbdydiag"):
                 return out.reshape(wl.ntr, wl.kz, wl.iy, wl.jx)
             return out.reshape(wl.iy, wl.jx) if nk == 1 else out.reshape(nk, wl.iy, wl.jx)
         return out

@@ -111,7 +111,8 @@ class ReferenceRun:
         if crm:
             ns.update(imin=-1, imax=icross2 + 2)
         ns.update(kz=kz, kzp1=kz + 1, kzm1=kz - 1, jx=wl.jx, iy=wl.iy, nqx=wl.nqx, ntr=wl.ntr, iqfrst=2,
-                  ipptls=wl.ipptls, ibltyp=wl.ibltyp, ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, idiag=0, ichdiag=0,
+                  ipptls=wl.ipptls, ibltyp=wl.ibltyp, ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, idiag=wl.idiag,
+                  ichdiag=wl.ichdiag,
                   idynamic=3, mo_nadv=wl.mo_nadv, mo_nsound=wl.mo_nsound, dtsec=wl.dt, dt=wl.dt, rdt=1.0 / wl.dt,
                   dx=wl.dx, rdx=1.0 / wl.dx, lrotllr=bool(wl.lrotllr), do_divdamp=bool(wl.mo_divdamp),
                   do_divfilter=bool(wl.mo_divfilter), do_apply_bdy=bool(wl.do_bdy), moloch_realcase=False,
@@ -199,6 +200,14 @@ class ReferenceRun:
                 ns["qi"], ns["qr"], ns["qs"] = (ns["qx"].view_last(n) for n in (3, 4, 5))
         if wl.ibltyp == 2:
             from_oracle("tke"); zeros("tketen", "cross", 0, 0, 1, kz + 1); zeros("tkex", "cross", 0, 0, 1, kz)
+        ib = [(g.jci1, g.jci2), (g.ici1, g.ici2), (1, kz)]
+        if wl.idiag > 0:       # Main/mod_moloch.F90:187-188 and the tdiag/qdiag members used by the path
+            ns["ten0"], ns["qen0"] = FArr.alloc(ib), FArr.alloc(ib)
+            ns["tdiag"] = _Obj(adh=FArr.alloc(ib), bdy=FArr.alloc(ib))
+            ns["qdiag"] = _Obj(adh=FArr.alloc(ib), bdy=FArr.alloc(ib))
+        if wl.ichdiag > 0 and wl.ntr > 0:
+            for n in ("chiten0", "cadvhdiag", "cbdydiag"):
+                ns[n] = FArr.alloc(ib + [(1, wl.ntr)])
         # mo_atm%*, sfs%*, atms%* aliases used by bdyval / mkslice / morelax
         mo = ns["mo_atm"]
         for n in ("u", "v", "w", "t", "pai", "qx", "zetaf"):
@@ -349,6 +358,8 @@ class ReferenceRun:
         a = {"zeta": ns["z"], "pf3d": ns["atms"].pf3d, "th3d": ns["atms"].th3d, "rhb3d": ns["atms"].rhb3d,
              "wpx3d": ns["atms"].wpx3d, "rhox2d": ns["atms"].rhox2d, "tp2d": ns["atms"].tp2d,
              "th700": ns["atms"].th700}.get(name)
+        if a is None and name[1:6] == "diag_":
+            a = getattr(ns[name[:5]], name[6:])
         if a is None:
             a = ns[name]
         stag = H.ALLOC[name][0] if name in H.ALLOC else "cross"
@@ -641,6 +652,9 @@ def golden_cases():
                                   mo_ztop=30000.0), 2),
         "no_damp_no_filter": (S.small(lam, 14, 12, 6, mo_divdamp=0, mo_divfilter=0, ntr=0), 1),
         "vapour_only": (S.small(lam, 14, 12, 6, ipptls=0, nqx=1, ntr=0, do_bdy=1), 2),
+        # tendency diagnostics of dynamical_core and boundary (idiag, ichdiag)
+        "limited_area_diag": (S.small(lam, 16, 14, 6, do_bdy=1, present_qc=1, mo_top_nudge=1, mo_ztop=30000.0, idiag=1,
+                                      ichdiag=1), 2),
         # UW-PBL TKE advected by the dycore, with its boundary values
         "limited_area_tke": (S.small(lam, 16, 14, 8, do_bdy=1, present_qc=1, ibltyp=2, tkemin=1.0e-4, ipptls=1,
                                      nqx=2), 2),
@@ -649,7 +663,9 @@ def golden_cases():
 
 def case_fields(wl):
     return GOLDEN_FIELDS + (["trac"] if wl.ntr else []) + (["tke"] if wl.ibltyp == 2 else []) + \
-        (["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "ptrop", "ktrop", "kmxpbl"] if wl.do_slice else [])
+        (["pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "ptrop", "ktrop", "kmxpbl"] if wl.do_slice else []) + \
+        ((["tdiag_adh", "qdiag_adh"] + (["tdiag_bdy", "qdiag_bdy"] if wl.do_bdy else [])) if wl.idiag > 0 else []) + \
+        ((["cadvhdiag"] + (["cbdydiag"] if wl.do_bdy else [])) if wl.ichdiag > 0 and wl.ntr > 0 else [])
 
 
 def setup_cases():

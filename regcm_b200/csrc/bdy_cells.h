@@ -511,6 +511,31 @@ MB_HD void massck_final(const MassArgs& a) {
   a.out[0] = dry; a.out[1] = fd; a.out[2] = wat; a.out[3] = fw; a.out[4] = mx; a.out[5] = mn; a.out[6] = bad;
 }
 
+// ---- tendency diagnostics (idiag, ichdiag)  [F90:1092-1103, 1127-1139, 455-466, 508-519] ----------
+struct DiagArgs {
+  Geo g;
+  const double *t, *qv, *trac;
+  double *ten0, *qen0, *chiten0;      // snapshots
+  double *dt_out, *dq_out, *dc_out;   // tdiag%adh|bdy, qdiag%adh|bdy, cadvhdiag|cbdydiag
+  double rdt;
+  int idiag, ichdiag;
+};
+// ten0 = t, qen0 = qv, chiten0 = trac on the interior
+MB_HD void diag_snap_cell(const DiagArgs& a, int j, int i, int k) {
+  const long long id = gidx(a.g, j, i, k), sp = (long long)a.g.kz * a.g.plane;
+  if (a.idiag) { a.ten0[id] = a.t[id]; a.qen0[id] = a.qv[id]; }
+  if (a.ichdiag) for (int n = 0; n < a.g.ntr; ++n) a.chiten0[id + n * sp] = a.trac[id + n * sp];
+}
+// (x - x0) * rdt
+MB_HD void diag_diff_cell(const DiagArgs& a, int j, int i, int k) {
+  const long long id = gidx(a.g, j, i, k), sp = (long long)a.g.kz * a.g.plane;
+  if (a.idiag) {
+    a.dt_out[id] = (a.t[id] - a.ten0[id]) * a.rdt;
+    a.dq_out[id] = (a.qv[id] - a.qen0[id]) * a.rdt;
+  }
+  if (a.ichdiag) for (int n = 0; n < a.g.ntr; ++n) a.dc_out[id + n * sp] = (a.trac[id + n * sp] - a.chiten0[id + n * sp]) * a.rdt;
+}
+
 // ---- TKE (ibltyp == 2) -------------------------------------------------------------
 // zstagtoh(tke,tkex) [F90:1445-1459]: one (j,i,k), k = 1..kz
 MB_HD void zstagtoh_cell(const Geo& g, const double* fl, double* hl, int j, int i, int k) {

@@ -17,7 +17,7 @@ static const char* k_names[KID_COUNT] = {
     "reset_tendencies", "tetavf_init", "sound_pre", "divdamp_filter", "wsolve", "uvupdate", "sfinish",
     "destagger", "waf_vertical", "waf_meridional", "waf_zonal", "curvature", "restagger", "tvirt_temp",
     "diag_prq", "diag_ps", "status_update", "halo_local", "halo_pack", "halo_unpack", "init_static",
-    "waf_horizontal", "box_copy", "bdyval", "bdy_relax", "bdy_finish", "mkslice", "tke", "spectral_nudge", "massck"};
+    "waf_horizontal", "box_copy", "bdyval", "bdy_relax", "bdy_finish", "mkslice", "tke", "spectral_nudge", "massck", "diag_tendencies"};
 const char* kernel_name(int kid) { return (kid >= 0 && kid < KID_COUNT) ? k_names[kid] : "?"; }
 
 LaunchScope::LaunchScope(Ctx& c_, int kid_) : c(c_), kid(kid_) {
@@ -226,11 +226,13 @@ static int do_advection(Ctx& c) {
 }
 
 static int do_dynamical_core(Ctx& c) {
+  if (k_diag(c, 0, false)) return 1;              // ten0, qen0, chiten0 :1092-1103
   for (int n = 0; n < c.cfg.mo_nadv; ++n) {
     if (do_sound(c)) return 1;
     if (do_advection(c)) return 1;
   }
-  return k_tvirt_temp(c);
+  if (k_tvirt_temp(c)) return 1;
+  return k_diag(c, 0, true);                      // tdiag%adh, qdiag%adh, cadvhdiag :1127-1139
 }
 
 static int do_reset_tendencies(Ctx& c) {
@@ -245,6 +247,7 @@ static int do_reset_tendencies(Ctx& c) {
 // `boundary` (Main/mod_moloch.F90:448-529)
 static int do_boundary(Ctx& c) {
   const int kz = c.g.kz;
+  if (k_diag(c, 1, false)) return 1;              // :455-466
   if (k_bdyval(c, c.xbctime)) return 1;
   c.xbctime = c.xbctime + c.cfg.dtsec;            // Main/mod_bdycod.F90:2653
   if (k_bdy_relax(c, c.xbctime)) return 1;        // motopnudge + morelax: weights of the advanced xbctime
@@ -252,6 +255,7 @@ static int do_boundary(Ctx& c) {
     c.tspectral = c.tspectral + c.cfg.dtsec;
     if ((int)fmod(c.tspectral, c.cfg.dtrad) == 0 && k_spectral_nudge(c, c.xbctime)) return 1;
   }
+  if (k_diag(c, 1, true)) return 1;               // tdiag%bdy, qdiag%bdy, cbdydiag :508-519
   {   // uvstagtouvx :1532-1533, one round
     const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
     const HaloSpec sp[2] = {{&iu, 1, HS_U, 2, true, false, 0}, {&iv, 1, HS_V, 2, false, true, 0}};
@@ -463,7 +467,7 @@ static int xfer_field(moloch_b200_ctx* c, int field, int n, double* host, int jl
   if (!f.p) return fail("set/get_field: field not allocated (ntr == 0, or ibltyp/do_bdy/do_slice not configured)");
   int spec = 0;
   if (f.nspec > 1 || field == MB_QX || field == MB_TRAC || field == MB_QXTEN || field == MB_CHITEN ||
-      field == MB_CHIB0 || field == MB_CHIB1) {
+      field == MB_CHIB0 || field == MB_CHIB1 || field == MB_CHITEN0 || field == MB_CADVHDIAG || field == MB_CBDYDIAG) {
     if (n < 1 || n > f.nspec) return fail("set/get_field: species index out of range");
     spec = n - 1;
   }

@@ -22,7 +22,7 @@ enum KernelId {
   KID_RESET = 0, KID_TETAVF, KID_SOUND_PRE, KID_DIVDAMP, KID_WSOLVE, KID_UVUPDATE, KID_SFINISH,
   KID_DESTAG, KID_WAF_Z, KID_WAF_Y, KID_WAF_X, KID_CURV, KID_RESTAG, KID_TVIRT, KID_DIAG, KID_PS,
   KID_STATUS, KID_HALO, KID_HALO_PACK, KID_HALO_UNPACK, KID_INIT, KID_WAF_H, KID_BOX,
-  KID_BDYVAL, KID_BDYRELAX, KID_BDYFINISH, KID_MKSLICE, KID_TKE, KID_SPECTRAL, KID_MASSCK, KID_COUNT
+  KID_BDYVAL, KID_BDYRELAX, KID_BDYFINISH, KID_MKSLICE, KID_TKE, KID_SPECTRAL, KID_MASSCK, KID_DIAGTEN, KID_COUNT
 };
 
 struct ProfEvent { cudaEvent_t a, b; int kid; };
@@ -234,6 +234,7 @@ int k_tke_update(Ctx& c, double dtinc);
 int k_ibnd_fill(Ctx& c, int* dst, const int* src, int jlo, int jhi, int ilo, int ihi);
 int k_spectral_nudge(Ctx& c, double xbctime);
 int k_massck(Ctx& c, int what, double* out7);
+int k_diag(Ctx& c, int which, bool diff);
 // kernels_waf.cu
 int k_waf_ratios(Ctx& c);
 int k_waf_z2(Ctx& c, int first, int count, double dta);

@@ -119,6 +119,10 @@ inline void field_shape(const moloch_b200_config& f, int id, int& nk, int& nspec
     case MB_TH3D: case MB_RHB3D: case MB_WPX3D: nk = f.do_slice ? kz : 0; break;
     case MB_RHOX2D: case MB_TP2D: case MB_TH700: case MB_XLAT: case MB_PTROP: case MB_KTROP: case MB_KMXPBL:
       nk = f.do_slice ? 1 : 0; break;
+    case MB_TEN0: case MB_QEN0: case MB_TDIAG_ADH: case MB_QDIAG_ADH: case MB_TDIAG_BDY: case MB_QDIAG_BDY:
+      nk = f.idiag > 0 ? kz : 0; break;
+    case MB_CHITEN0: case MB_CADVHDIAG: case MB_CBDYDIAG:
+      nk = (f.ichdiag > 0 && f.ichem && f.ntr > 0) ? kz : 0; nspec = f.ntr > 0 ? f.ntr : 1; break;
     default: nk = kz; break;
   }
 }

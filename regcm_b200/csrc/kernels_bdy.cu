@@ -242,6 +242,38 @@ int k_massck(Ctx& c, int what, double* out7) {
   return 0;
 }
 
+// ---- tendency diagnostics ---------------------------------------------------------------------------
+__global__ void moloch_diag_snap(DiagArgs a) {
+  const int j = a.g.jci1 + blockIdx.x * BX + threadIdx.x, i = a.g.ici1 + blockIdx.y * BY + threadIdx.y;
+  if (j > a.g.jci2 || i > a.g.ici2) return;
+  diag_snap_cell(a, j, i, 1 + (int)blockIdx.z);
+}
+__global__ void moloch_diag_diff(DiagArgs a) {
+  const int j = a.g.jci1 + blockIdx.x * BX + threadIdx.x, i = a.g.ici1 + blockIdx.y * BY + threadIdx.y;
+  if (j > a.g.jci2 || i > a.g.ici2) return;
+  diag_diff_cell(a, j, i, 1 + (int)blockIdx.z);
+}
+// which: 0 = dynamical_core (adh / cadvhdiag), 1 = boundary (bdy / cbdydiag); diff: false = snapshot
+int k_diag(Ctx& c, int which, bool diff) {
+  const Geo& g = c.g;
+  DiagArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = g;
+  a.idiag = c.cfg.idiag > 0; a.ichdiag = c.cfg.ichdiag > 0 && c.cfg.ichem && c.cfg.ntr > 0;
+  if (!a.idiag && !a.ichdiag) return 0;
+  a.t = c.f[MB_T].p; a.qv = c.f[MB_QX].p; a.trac = c.f[MB_TRAC].p;
+  a.ten0 = c.f[MB_TEN0].p; a.qen0 = c.f[MB_QEN0].p; a.chiten0 = c.f[MB_CHITEN0].p;
+  a.dt_out = c.f[which ? MB_TDIAG_BDY : MB_TDIAG_ADH].p; a.dq_out = c.f[which ? MB_QDIAG_BDY : MB_QDIAG_ADH].p;
+  a.dc_out = c.f[which ? MB_CBDYDIAG : MB_CADVHDIAG].p;
+  a.rdt = 1.0 / c.cfg.dtsec;       // rdt, Main/mpplib/mod_runparams.F90
+  LaunchScope ls(c, KID_DIAGTEN);
+  const dim3 grid = grid3(g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, g.kz);
+  if (diff) moloch_diag_diff<<<grid, dim3(BX, BY), 0, c.stream>>>(a);
+  else moloch_diag_snap<<<grid, dim3(BX, BY), 0, c.stream>>>(a);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---- TKE helpers (ibltyp == 2) ---------------------------------------------------------------
 __global__ void moloch_zstagtoh(Geo g, const double* __restrict__ fl, double* __restrict__ hl) {
   const int j = g.jce1 + blockIdx.x * BX + threadIdx.x;

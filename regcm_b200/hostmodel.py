@@ -48,6 +48,10 @@ ALLOC = {
     "th700": ("cross", 0, 0, 1), "zetaf": ("cross", 0, 0, "kzp1"),
     "xlat": ("cross", 0, 0, 1), "ptrop": ("cross", 0, 0, 1), "ktrop": ("cross", 0, 0, 1),
     "kmxpbl": ("cross", 0, 0, 1),
+    # tendency diagnostics (Main/mod_moloch.F90:187-192; tdiag/qdiag, chemistry diagnostics)
+    "ten0": ("cross", 0, 0, "kz"), "qen0": ("cross", 0, 0, "kz"), "tdiag_adh": ("cross", 0, 0, "kz"),
+    "qdiag_adh": ("cross", 0, 0, "kz"), "tdiag_bdy": ("cross", 0, 0, "kz"), "qdiag_bdy": ("cross", 0, 0, "kz"),
+    "chiten0": ("cross", 0, 0, "kz"), "cadvhdiag": ("cross", 0, 0, "kz"), "cbdydiag": ("cross", 0, 0, "kz"),
 }
 
 

@@ -36,14 +36,15 @@ FIELDS = ["u", "v", "w", "pai", "tetav", "t", "qx", "trac", "ux", "vx", "tvirt",
           "dub0", "dub1", "dvb0", "dvb1", "xtb0", "xtb1", "xpaib0", "xpaib1", "xqb0", "xqb1",
           "xlb0", "xlb1", "xib0", "xib1", "xpsb0", "xpsb1", "chib0", "chib1",
           "pf3d", "th3d", "rhb3d", "wpx3d", "rhox2d", "tp2d", "th700", "zetaf",
-          "xlat", "ptrop", "ktrop", "kmxpbl"]
+          "xlat", "ptrop", "ktrop", "kmxpbl",
+          "ten0", "qen0", "tdiag_adh", "qdiag_adh", "tdiag_bdy", "qdiag_bdy", "chiten0", "cadvhdiag", "cbdydiag"]
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 PROFILES = ["gzitak", "gzitakh", "ffilt", "xkdamp", "xknu", "rlat"]
 PROFILE_ID = {n: i for i, n in enumerate(PROFILES)}
 TABLES = ["hefc", "tnudge", "cnudge", "fcx", "bvx", "bvy"]
 TABLE_ID = {n: i for i, n in enumerate(TABLES)}
 IBND_ID = {"cr": 0, "ud": 1, "vd": 2}
-SPECIES = {"qx", "trac", "qxten", "chiten", "chib0", "chib1"}
+SPECIES = {"qx", "trac", "qxten", "chiten", "chib0", "chib1", "chiten0", "cadvhdiag", "cbdydiag"}
 
 # every symbol include/moloch_b200.h declares
 ABI_SYMBOLS = [
@@ -71,7 +72,7 @@ class Config(C.Structure):
         "do_bdy", "nspgx", "present_qc", "present_qi", "mo_top_nudge", "mo_spectral_nudge", "nztop", "ichem",
         "ichebdy", "do_slice", "icldmstrat", "km", "lm", "do_massck")] + [
         (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin")] + [
-        (n, C.c_int32) for n in ("irceideal", "reserved3")]
+        (n, C.c_int32) for n in ("irceideal", "idiag", "ichdiag", "reserved3")]
 
 
 class MolochError(RuntimeError):
@@ -154,7 +155,8 @@ def make_config(wl, g: Geom, device: int = -1, mo_dzita: float | None = None, bd
                   ichem=int(wl.ntr > 0), ichebdy=wl.ichebdy, do_slice=wl.do_slice, icldmstrat=wl.icldmstrat,
                   km=int(bdy.get("km", 0)), lm=int(bdy.get("lm", 0)), do_massck=int(getattr(wl, "do_massck", 0)), dtbdys=wl.dtbdys,
                   dtrad=wl.dtrad, rhmin=wl.rhmin, rhmax=wl.rhmax, tkemin=wl.tkemin,
-                  irceideal=int(getattr(wl, "irceideal", 0)), reserved3=0)
+                  irceideal=int(getattr(wl, "irceideal", 0)), idiag=int(getattr(wl, "idiag", 0)),
+                  ichdiag=int(getattr(wl, "ichdiag", 0)), reserved3=0)
 
 
 def halo_plan(cfg: Config, stag: int, nex: int, lr: bool, bt: bool):
@@ -378,7 +380,7 @@ class MolochB200:
         shp = (self.wl.iy, self.wl.jx) if nk == 1 else (nk, self.wl.iy, self.wl.jx)
         if name in ("qx", "qxten"):
             shp = (self.wl.nqx,) + shp
-        if name in ("trac", "chiten", "chib0", "chib1"):
+        if name in ("trac", "chiten", "chib0", "chib1", "chiten0", "cadvhdiag", "cbdydiag"):
             shp = (self.wl.ntr,) + shp
         return shp
 

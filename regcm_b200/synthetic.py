@@ -86,6 +86,8 @@ class Workload:
     do_slice: int = 0        # mkslice inside moloch()
     do_massck: int = 0       # keep zq on the device for massck (debug_level > 0)
     irceideal: int = 0       # 1: mkslice keeps ptrop (Main/mod_slice.F90:345)
+    idiag: int = 0           # > 0: tendency diagnostics tdiag%adh/bdy, qdiag%adh/bdy
+    ichdiag: int = 0         # > 0: tracer diagnostics cadvhdiag, cbdydiag
     calday: float = 172.25   # calendar day used by mkslice's tropopause pressure
     dayspy: float = 365.2422
     dtbdys: float = 21600.0
@@ -105,7 +107,7 @@ class Workload:
 
     @property
     def needs_ext(self) -> bool:
-        return bool(self.do_bdy or self.do_slice or self.do_massck or self.ibltyp == 2)
+        return bool(self.do_bdy or self.do_slice or self.do_massck or self.ibltyp == 2 or self.idiag or self.ichdiag)
 
     @property
     def cells(self) -> int:

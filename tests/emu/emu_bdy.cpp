@@ -94,6 +94,22 @@ void wrap_uv(Emu& e) {
   }
 }
 
+int do_diag(Emu& e, int which, bool diff) {   // = k_diag
+  const Geo& g = e.g; const int o = e.order;
+  DiagArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.g = g;
+  a.idiag = e.cfg.idiag > 0; a.ichdiag = e.cfg.ichdiag > 0 && e.cfg.ichem && e.cfg.ntr > 0;
+  if (!a.idiag && !a.ichdiag) return 0;
+  a.t = P(e, MB_T); a.qv = P(e, MB_QX); a.trac = P(e, MB_TRAC);
+  a.ten0 = P(e, MB_TEN0); a.qen0 = P(e, MB_QEN0); a.chiten0 = P(e, MB_CHITEN0);
+  a.dt_out = P(e, which ? MB_TDIAG_BDY : MB_TDIAG_ADH); a.dq_out = P(e, which ? MB_QDIAG_BDY : MB_QDIAG_ADH);
+  a.dc_out = P(e, which ? MB_CBDYDIAG : MB_CADVHDIAG);
+  a.rdt = 1.0 / e.cfg.dtsec;
+  walk(o, 1, g.kz, [&](int k) { walk(o, g.ici1, g.ici2, [&](int i) { walk(o, g.jci1, g.jci2, [&](int j) {
+    if (diff) diag_diff_cell(a, j, i, k); else diag_snap_cell(a, j, i, k); }); }); });
+  return 0;
+}
 int do_bdyval(Emu& e, double xbctime) {   // = k_bdyval
   const Geo& g = e.g; const int kz = g.kz, o = e.order;
   const BdyArgs a = bdy_args(e, xbctime);
@@ -225,6 +241,7 @@ int emu_b200_bdyval(void* h) {
 }
 int emu_b200_boundary(void* h) {   // = do_boundary (capi.cu)
   Emu& e = *(Emu*)h;
+  do_diag(e, 1, false);
   do_bdyval(e, e.xbctime);
   e.xbctime = e.xbctime + e.cfg.dtsec;
   do_relax(e, e.xbctime);
@@ -232,15 +249,18 @@ int emu_b200_boundary(void* h) {   // = do_boundary (capi.cu)
     e.tspectral = e.tspectral + e.cfg.dtsec;
     if ((int)std::fmod(e.tspectral, e.cfg.dtrad) == 0) do_spectral(e, e.xbctime);
   }
+  do_diag(e, 1, true);
   return do_finish(e);
 }
 // the two halves of do_boundary around its u/v halo round, for runs on several ranks where the test
 // moves the halos between the ranks' contexts (no mospectral_nudge: it is refused on > 1 rank)
 int emu_b200_boundary_pre(void* h) {
   Emu& e = *(Emu*)h;
+  do_diag(e, 1, false);
   do_bdyval(e, e.xbctime);
   e.xbctime = e.xbctime + e.cfg.dtsec;
-  return do_relax(e, e.xbctime);
+  do_relax(e, e.xbctime);
+  return do_diag(e, 1, true);
 }
 int emu_b200_boundary_post(void* h) { return do_finish(*(Emu*)h); }
 int emu_b200_mkslice(void* h) {   // = k_mkslice

@@ -24,6 +24,7 @@ CASES = {
     "band": S.small(LAM, 32, 28, 10, i_band=1, oro="sine"),
     "lam_tke": S.small(LAM, 34, 30, 12, ibltyp=2, tkemin=1.0e-4),
     "no_sponge": S.small(LAM, 30, 26, 9, nspgx=0),
+    "lam_diag": S.small(LAM, 30, 26, 9, idiag=1, ichdiag=1),
 }
 STATE = ["u", "v", "w", "t", "pai", "qx", "trac", "ps", "ux", "vx", "tvirt", "tetav"]
 
@@ -71,6 +72,9 @@ def test_boundary_cells_bit_exact(case, order):
     same(o, m, names, "bdyval: ")
     assert m.get_xbctime() == o.get_xbctime()
     o.boundary(); m.boundary()
+    if wl.idiag:
+        names = names + ["tdiag_bdy", "qdiag_bdy", "cbdydiag"]
+        assert np.abs(o.get("tdiag_bdy")).max() > 0
     same(o, m, names, "boundary: ")
     o.boundary(); m.boundary()
     same(o, m, names, "2nd boundary: ")

@@ -142,10 +142,10 @@ def test_massck_and_ps_guard():
     m.close()
 
 
-@pytest.mark.parametrize("case", ["band_boundary", "no_damp_no_filter", "vapour_only"])
+@pytest.mark.parametrize("case", ["band_boundary", "no_damp_no_filter", "vapour_only", "limited_area_diag"])
 def test_reference_golden_more(case):
     """More digests of the executed reference source (see tests/test_gpu_parity.py::test_reference_golden);
-    these three cases were added after the round's GPU budget was spent."""
+    these cases were added after the round's GPU budget was spent."""
     import json
     import os
     from oracle.refrun import run_moloch as R

@@ -318,3 +318,20 @@ def test_massck_known_answers():
     mx, mn, bad = o.ps_check()
     ps = o.get("ps")[1:wl.iy - 2, 1:wl.jx - 2]
     assert (mx, mn, bad) == (ps.max(), ps.min(), 0)
+
+
+def test_tendency_diagnostics_known_answers():
+    """idiag / ichdiag: tdiag%adh = (t after the dycore - t before) / dt, tdiag%bdy likewise around `boundary`
+    (Main/mod_moloch.F90:1092-1103, 1127-1139, 455-466, 508-519)."""
+    wl = S.small(LAM, 30, 26, 9, idiag=1, ichdiag=1)
+    o, _ = make_oracle_bdy(wl)
+    inner = np.s_[:, 1:wl.iy - 2, 1:wl.jx - 2]
+    t0, q0, c0 = o.get("t").copy(), o.get("qx")[0].copy(), o.get("trac").copy()
+    o.reset_tendencies(); o.dynamical_core()
+    t1, q1, c1 = o.get("t").copy(), o.get("qx")[0].copy(), o.get("trac").copy()
+    assert np.array_equal(o.get("tdiag_adh")[inner], ((t1 - t0) * (1.0 / wl.dt))[inner])
+    assert np.array_equal(o.get("qdiag_adh")[inner], ((q1 - q0) * (1.0 / wl.dt))[inner])
+    assert np.array_equal(o.get("cadvhdiag")[(slice(None),) + inner], ((c1 - c0) * (1.0 / wl.dt))[(slice(None),) + inner])
+    o.boundary()
+    assert np.array_equal(o.get("tdiag_bdy")[inner], ((o.get("t") - t1) * (1.0 / wl.dt))[inner])
+    assert np.array_equal(o.get("cbdydiag")[(slice(None),) + inner], ((o.get("trac") - c1) * (1.0 / wl.dt))[(slice(None),) + inner])

@@ -134,6 +134,8 @@ enum moloch_b200_profile {
 
 const char* moloch_b200_last_error(void);
 int moloch_b200_abi_version(void);
+/* sizeof(moloch_b200_config) as the library was compiled: bindings compare it with their own layout */
+uint64_t moloch_b200_config_size(void);
 /* number of usable CUDA devices (0 when none; never fails) */
 int moloch_b200_device_count(void);
 

@@ -308,6 +308,7 @@ extern "C" {
 
 const char* moloch_b200_last_error(void) { return g_err.c_str(); }
 int moloch_b200_abi_version(void) { return MOLOCH_B200_ABI_VERSION; }
+uint64_t moloch_b200_config_size(void) { return (uint64_t)sizeof(moloch_b200_config); }
 
 int moloch_b200_device_count(void) {
   int n = 0;

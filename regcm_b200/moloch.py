@@ -58,7 +58,7 @@ ABI_SYMBOLS = [
     "moloch_b200_halo_plan", "moloch_b200_p2p_blob_size", "moloch_b200_p2p_export", "moloch_b200_p2p_connect", "moloch_b200_set_async",
     "moloch_b200_set_table", "moloch_b200_set_ibnd", "moloch_b200_boundary", "moloch_b200_bdyval",
     "moloch_b200_set_xbctime", "moloch_b200_get_xbctime", "moloch_b200_bdy_shift", "moloch_b200_mkslice",
-    "moloch_b200_massck", "moloch_b200_ps_check", "moloch_b200_set_calday",
+    "moloch_b200_massck", "moloch_b200_ps_check", "moloch_b200_set_calday", "moloch_b200_config_size",
 ]
 
 
@@ -93,6 +93,10 @@ def load_library():
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     ctx = C.c_void_p
     lib.moloch_b200_last_error.restype = C.c_char_p
+    lib.moloch_b200_config_size.restype = C.c_uint64
+    if int(lib.moloch_b200_config_size()) != C.sizeof(Config):
+        raise MolochError(f"{LIB_PATH}: moloch_b200_config is {int(lib.moloch_b200_config_size())} bytes in the "
+                          f"library, {C.sizeof(Config)} in this binding (stale build?)")
     lib.moloch_b200_create.argtypes = [C.POINTER(Config), C.POINTER(ctx)]
     lib.moloch_b200_destroy.argtypes = [ctx]
     lib.moloch_b200_comm_id.argtypes = [C.c_void_p]

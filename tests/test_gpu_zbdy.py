@@ -162,3 +162,20 @@ def test_reference_golden_more(case):
         else:
             assert got["sha256"] == want["sha256"], f"{case}: {f} differs from the executed reference source"
     m.close()
+
+
+@pytest.mark.parametrize("name,wl,nsteps", [
+    ("isc24_small", S.WORKLOADS["isc24_small"], 100),      # BASELINE config 2 at full size (100x50x30, doubly periodic)
+    ("lam_boundary", S.small(LAM, 96, 80, 20, do_slice=1), 30),
+], ids=["isc24_small_100_steps", "lam_boundary_30_steps"])
+def test_long_runs_stay_bit_exact(name, wl, nsteps):
+    """The north star asks for agreement "after N steps": 100 steps of the isc24_small configuration and 30
+    steps of a limited-area case with lateral boundary, every prognostic field still bit for bit equal to
+    the oracle (limiter branch flips at den ~ 0 would show up here first)."""
+    o, B = make_oracle_bdy(wl)
+    m = make_gpu_bdy(wl, o, B)
+    o.step(nsteps); m.moloch(nsteps)
+    compare(o, m, PROGNOSTIC + (["trac"] if wl.ntr else []), label=f"{name} after {nsteps} steps: ")
+    compare(o, m, DIAGNOSTIC, exact=False, rtol=1e-12, label=f"{name} after {nsteps} steps: ")
+    assert np.isfinite(m.get_global("pai")).all()
+    m.close()

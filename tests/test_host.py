@@ -49,6 +49,8 @@ def test_enums_match_header():
 def test_config_struct_layout():
     # 34 int32 + 3 double (ABI v1) + 14 int32 + 5 double + 4 int32 (ABI v2)
     assert ctypes.sizeof(M.Config) == 34 * 4 + 3 * 8 + 14 * 4 + 5 * 8 + 4 * 4
+    lib = M.load_library()
+    assert int(lib.moloch_b200_config_size()) == ctypes.sizeof(M.Config)      # the C side agrees
 
 
 def test_no_cpu_fallback():

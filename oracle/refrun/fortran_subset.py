@@ -289,6 +289,28 @@ def find_internal(stmts: list[str], name: str) -> Routine:
     return out
 
 
+def fragment(stmts: list[str], anchor: str, name: str, occurrence: int = 0, back: int = 0) -> Routine:
+    """The statements of one block inside a larger routine, wrapped as a routine of their own: from the
+    statement equal to `anchor` (white space ignored) to the end of the if/do block that encloses it."""
+    key = anchor.replace(" ", "")
+    hits = [k for k, s in enumerate(stmts) if s.replace(" ", "") == key]
+    i0 = hits[occurrence] - back      # `back`: start that many statements before the anchor
+    body, depth = [], 0
+    for s in stmts[i0:]:
+        opens = bool(re.match(r"^do\b", s)) or bool(re.match(r"^if\s*\(.*\)\s*then$", s))
+        closes = bool(re.match(r"^end\s*(do|if)\b", s))
+        if closes:
+            if depth == 0:
+                break
+            depth -= 1
+        elif depth == 0 and (s == "else" or s.startswith("else if")):
+            break
+        body.append(s)
+        if opens:
+            depth += 1
+    return Routine(name, "subroutine", [], body)
+
+
 def module_parameters(stmts: list[str], ex: Expr) -> list[str]:
     """`parameter` declarations of the module specification part (before `contains`) as Python assignments."""
     out = []

@@ -470,6 +470,18 @@ class SetupRun:
         todo.append((mr["init_moloch"], "Main/mod_moloch.F90"))
         br = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mod_bdycod.F90")).read()))
         todo += [(br["setup_bdywt"], "Main/mod_bdycod.F90"), (br["paicompute"], "Main/mod_bdycod.F90")]
+        # two blocks of `init` (Main/mod_init.F90): the thermodynamic state after paicompute (:941-953 ...)
+        # and the top sponge ffilt of the implicit solver (:1008-1026)
+        ist = F.preprocess(open(os.path.join(REF, "Main/mod_init.F90")).read())
+        todo.append((F.fragment(ist, "mo_atm%p(j,i,k) = (mo_atm%pai(j,i,k)**cpovr) * p00", "init_state_block", occurrence=1, back=1),
+                     "Main/mod_init.F90"))
+        todo.append((F.fragment(ist, "np = real(njcross*nicross,rk8)", "init_ffilt_block"), "Main/mod_init.F90"))
+        pf = F.find_routines(F.preprocess(open(os.path.join(REF, "Share/pfwsat.inc")).read()))
+        todo.append((pf["pfwsat"], "Share/pfwsat.inc"))
+        zeros_cross = lambda nk: arr("cross", nk)
+        mo.pf = zeros_cross(kz + 1)
+        ns.update(njcross=wl.jx - 1, nicross=wl.iy - 1, sumall=lambda x: x, gmeanz=FArr.alloc([(1, kz)]),
+                  ffilt=FArr.alloc([(1, kz)]), mo_zfilt_fac=0.8)       # Main/mod_init.F90:62
         for r, rel in todo:
             src = tr.routine(r)
             self.sources[r.name] = src
@@ -484,13 +496,16 @@ class SetupRun:
         ns["init_moloch"]()
         # Main/mod_init.F90:941: the hydrostatic Exner function of the initial state
         ns["paicompute"](ns["sfs"].psa, ns["mo_atm"].zeta, ns["mo_atm"].t, ns["qv"], ns["mo_atm"].pai)
+        ns["init_state_block"]()
+        ns["init_ffilt_block"]()
         return self
 
     def get(self, name) -> np.ndarray:
         ns, wl = self.ns, self.wl
         mo, md = ns["mo_atm"], ns["mddom"]
         a = {"zeta": mo.zeta, "fmz": mo.fmz, "rfmzu": mo.rfmzu, "rfmzv": mo.rfmzv, "fmzf": mo.fmzf, "zetaf": mo.zetaf,
-             "hx": md.hx, "hy": md.hy, "pai": mo.pai}.get(name)
+             "hx": md.hx, "hy": md.hy, "pai": mo.pai, "p": mo.p, "qsat": mo.qs, "rho": mo.rho, "tvirt": mo.tvirt,
+             "tetav": mo.tetav}.get(name)
         if a is None:
             a = ns[name]
         if a.nd == 1:
@@ -609,7 +624,8 @@ def reference_massck(wl, o) -> dict:
 
 
 SETUP_FIELDS = ["hx", "hy", "zeta", "fmz", "fmzf", "zetaf", "rfmzu", "rfmzv", "coru", "corv", "mx2", "rmx", "rmu", "rmv",
-                "gzitak", "gzitakh", "xkdamp", "xknu", "bdywtu", "bdywtv", "bdywtw", "pai"]
+                "gzitak", "gzitakh", "xkdamp", "xknu", "bdywtu", "bdywtv", "bdywtw", "pai", "p", "qsat", "rho", "tvirt",
+                "tetav", "ffilt"]
 
 
 class _Mask:

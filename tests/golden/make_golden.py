@@ -1,7 +1,9 @@
 """Generates tests/golden/oracle_golden.json from the oracle (run from the repo
-root: python tests/golden/make_golden.py).  The reference itself cannot be
-built here (no Fortran compiler), so these vectors pin the oracle, not the
-reference: PARITY UNPINNED by the reference's own tests."""
+root: python tests/golden/make_golden.py): regression vectors of the oracle
+itself after 1 and 10 steps.  The vectors that tie the oracle to the REFERENCE
+are tests/golden/reference_moloch.json, written by
+`python -m oracle.refrun.run_moloch` from runs of the reference's own source
+(see tests/test_reference_pin.py)."""
 import json
 import os
 import sys

@@ -407,7 +407,8 @@ class Translator:
                                 bnds.append(f"({ex.tr(lo)}, {ex.tr(hi)})")
                             if ok:
                                 kind = "int" if spec.startswith("integer") else "float"
-                                pre.append(f"{pyname(n)} = _alloc([{', '.join(bnds)}], {kind!r})")
+                                # in place: automatic arrays of a BLOCK depend on values computed before it
+                                body.append(("__code__", f"{pyname(n)} = _alloc([{', '.join(bnds)}], {kind!r})"))
                 continue
             body.append(s)
         ex = Expr(arrays)
@@ -576,6 +577,11 @@ class Translator:
             emit(f"raise NotImplementedError({s!r})")
 
         for s in body:
+            if isinstance(s, tuple):
+                emit(s[1])
+                continue
+            if re.match(r"^(\w+\s*:\s*)?block$", s) or re.match(r"^end\s*block\b", s):
+                continue             # BLOCK construct: its declarations are handled like the routine's own
             try:
                 stmt(s)
             except Exception as e:  # noqa: BLE001  -- untranslatable: only matters if reached

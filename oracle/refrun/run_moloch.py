@@ -68,11 +68,14 @@ class _Obj(types.SimpleNamespace):
 class ReferenceRun:
     """One rank owning the whole domain, state held in Fortran-bounded arrays."""
 
-    def __init__(self, wl, oracle, boundary: dict | None = None, dump_dir: str | None = None):
+    def __init__(self, wl, oracle, boundary: dict | None = None, dump_dir: str | None = None, px: int = 1,
+                 py: int = 1, rank: int = 0, comm=None):
+        """px, py, rank, comm: one rank of a px x py run (MultiRankReference); the halo exchange is then the
+        reference's own exchange routines on top of an emulated mpi_neighbor_alltoallv."""
         from regcm_b200 import hostmodel as H
         from regcm_b200.decomp import make_geom
         self.wl, self.H = wl, H
-        g = self.g = make_geom(wl.jx, wl.iy, wl.kz, wl.i_band, wl.i_crm, 1, 1, 0)
+        g = self.g = make_geom(wl.jx, wl.iy, wl.kz, wl.i_band, wl.i_crm, px, py, rank)
         ns = self.ns = dict(INTRINSICS)
         # ---- parameters straight from the reference's modules --------------------------------
         ex = F.Expr(set())
@@ -126,7 +129,8 @@ class ReferenceRun:
         ns["dtstepa"] = wl.dt / float(wl.mo_nadv)                              # :306
         ns["dtsound"] = ns["dtstepa"] / float(wl.mo_nsound)                    # :307
         ns["ma"] = _Obj(has_bdyleft=g.bl, has_bdyright=g.br, has_bdybottom=g.bb, has_bdytop=g.bt,
-                        bandflag=band, crmflag=crm)
+                        bandflag=band, crmflag=crm, left=g.left, right=g.right, bottom=g.bottom, top=g.top)
+        ns["mpi_proc_null"] = -1
         ns["syncro_rep"] = _Obj(act=lambda: False)
         ns["rcmtimer"] = _Obj(advance=lambda: None, integrating=lambda: True, str=lambda: "")
         ns["zenitm"] = lambda *a: None
@@ -295,6 +299,22 @@ class ReferenceRun:
         ns["exchange_lr"] = lambda a, nex, j1, j2, i1, i2, *k: self._exchange(a, nex, j1, j2, i1, i2, True, False)
         ns["exchange_bt"] = lambda a, nex, j1, j2, i1, i2, *k: self._exchange(a, nex, j1, j2, i1, i2, False, True)
         ns["exchange_lrbt"] = lambda a, nex, j1, j2, i1, i2, *k: self._exchange(a, nex, j1, j2, i1, i2, True, True)
+        if comm is not None:
+            # the reference's own exchange routines (MPI-3 variants, Main/mpplib/mod_mppparam.F90:3809-3878,
+            # 4257-4309, 4661-4712) over an emulated neighbourhood collective
+            mst = F.preprocess(open(os.path.join(REF, "Main/mpplib/mod_mppparam.F90")).read(), defines=("USE_MPI3",))
+            mr = F.find_routines(mst)
+            tr0 = F.Translator({"ml", "sdata", "rdata", "counts", "displs"})
+            for n in ("real8_3d_exchange_left_right_bottom_top", "real8_3d_exchange_left_right",
+                      "real8_3d_exchange_bottom_top"):
+                exec(F.compile_source(tr0.routine(mr[n]), f"<mod_mppparam.F90:{n}>"), ns)
+            nbrs = [g.left, g.right, g.bottom, g.top]
+            ns["mpi_neighbor_alltoallv"] = lambda sd, sc, sdis, st, rd, rc, rdis, rt, cm, err: \
+                comm.neighbor_alltoallv(rank, nbrs, sd, sc, sdis, rd)
+            ns.update(mpi_real8=0, cartesian_communicator=0, mpierr=0, mpi_success=0)
+            ns["exchange_lr"] = ns["real8_3d_exchange_left_right"]
+            ns["exchange_bt"] = ns["real8_3d_exchange_bottom_top"]
+            ns["exchange_lrbt"] = ns["real8_3d_exchange_left_right_bottom_top"]
         ns["morelax"] = lambda j1, j2, i1, i2, ba, f, x: (
             ns["morelax_fraction"](j1, j2, i1, i2, ba, f, x) if isinstance(x, float)
             else ns["morelax_external"](j1, j2, i1, i2, ba, f, x))      # interface morelax, Main/mod_bdycod.F90:124-127
@@ -626,6 +646,64 @@ def reference_massck(wl, o) -> dict:
 SETUP_FIELDS = ["hx", "hy", "zeta", "fmz", "fmzf", "zetaf", "rfmzu", "rfmzv", "coru", "corv", "mx2", "rmx", "rmu", "rmv",
                 "gzitak", "gzitakh", "xkdamp", "xknu", "bdywtu", "bdywtv", "bdywtw", "pai", "p", "qsat", "rho", "tvirt",
                 "tetav", "ffilt"]
+
+
+class _Comm:
+    """mpi_neighbor_alltoallv on a 2-D Cartesian communicator, for ranks that run as threads of this
+    process: neighbour order (dim 0 -, dim 0 +, dim 1 -, dim 1 +) = (left, right, bottom, top); what a rank
+    sends towards + is what its + neighbour receives from -."""
+
+    def __init__(self, n):
+        import threading
+        self.box, self.bar = {}, threading.Barrier(n, timeout=600)
+
+    def neighbor_alltoallv(self, rank, nbrs, sdata, counts, displs, rdata):
+        opp = (1, 0, 3, 2)
+        for d in range(4):
+            if nbrs[d] >= 0:
+                c, o = int(counts.a[d]), int(displs.a[d])
+                self.box[(rank, d)] = sdata.a[o:o + c].copy()
+        self.bar.wait()
+        for d in range(4):
+            if nbrs[d] >= 0:
+                c, o = int(counts.a[d]), int(displs.a[d])
+                rdata.a[o:o + c] = self.box[(nbrs[d], opp[d])]
+        self.bar.wait()
+
+
+class MultiRankReference:
+    """The reference's `moloch` on px x py ranks, one thread per rank, halos through the reference's own
+    exchange routines: pins the decomposition and halo semantics (and the oracle's emulation of them)."""
+
+    def __init__(self, wl, oracle, boundary, px, py):
+        self.wl, self.n = wl, px * py
+        comm = self.comm = _Comm(self.n)
+        self.ranks = [ReferenceRun(wl, oracle, boundary, px=px, py=py, rank=r, comm=comm) for r in range(self.n)]
+
+    def step(self, nsteps=1):
+        import threading
+        errs = []
+
+        def run(r):
+            try:
+                r.step(nsteps)
+            except BaseException as e:  # noqa: BLE001
+                errs.append(e)
+                self.comm.bar.abort()      # release the ranks waiting in a collective
+        ts = [threading.Thread(target=run, args=(r,)) for r in self.ranks]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def get(self, name):
+        out = None
+        for r in self.ranks:
+            a = r.get(name)
+            out = a if out is None else out + a       # owned cells are disjoint, the rest is zero
+        return out
 
 
 class _Mask:

@@ -109,6 +109,24 @@ def test_reference_boundary_setup_matches(band):
 
 
 @pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+@pytest.mark.parametrize("case,px,py", [("limited_area_boundary", 2, 2), ("periodic_hills", 2, 2), ("band_boundary", 3, 1),
+                                        ("limited_area", 1, 3)])
+def test_reference_multirank_matches_oracle(case, px, py):
+    """The reference's `moloch` on px x py ranks (one thread per rank), halos through the reference's OWN
+    exchange routines (real8_3d_exchange_left_right[_bottom_top], MPI-3 variants,
+    Main/mpplib/mod_mppparam.F90:3809-3878, 4257-4309, 4661-4712) on an emulated mpi_neighbor_alltoallv,
+    against the single-domain oracle: bit for bit.  Pins the decomposition and halo semantics that the
+    oracle's exchange emulation and the CUDA library's halo plan restate."""
+    wl, nsteps = CASES[case]
+    o, B = make_oracle_bdy(wl)
+    mr = R.MultiRankReference(wl, o, B, px, py)
+    mr.step(nsteps)
+    o.step(nsteps)
+    bad = [f for f in R.case_fields(wl) if not np.array_equal(mr.get(f), o.get(f))]
+    assert not bad, bad
+
+
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
 def test_reference_massck_matches_oracle():
     """massck's atmosphere sums (Main/mod_massck.F90:77-185) executed from source == the oracle's, bit for bit
     (same single running sums); the device's row-wise sums are compared with these to 1e-12."""

@@ -38,6 +38,9 @@ TOKEN = re.compile(r"""
 LOGIC = {".and.": " and ", ".or.": " or ", ".not.": " not ", ".true.": "True", ".false.": "False", ".eq.": "==",
          ".ne.": "!=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">=", ".eqv.": "==", ".neqv.": "!="}
 OUT_LAST = {"sumall", "maxall", "minall", "meanall"}
+# MPI procedures with scalar output arguments (0-based positions): call f(a, o1, o2, err) -> o1, o2 = f(a, o1, o2, err)
+OUT_ARGS = {"mpi_cart_create": [5], "mpi_comm_rank": [1], "mpi_comm_size": [1], "mpi_comm_split": [3],
+            "mpi_cart_shift": [3, 4], "mpi_cart_rank": [2]}
 TYPE_BOUND_CALLS = {"act", "advance", "str", "start", "integrating", "lcount"}
 DECL = re.compile(r"^(real|integer|logical|character|type|class|double precision|complex)\b")
 
@@ -535,6 +538,15 @@ class Translator:
                         assigned.add(a[0])
                     nums = [ex.tr(x) for x in a[1:] if not x.startswith(("'", '"'))]
                     emit(f"{ex.tr(a[0], lhs=True)} = _getmem({', '.join(nums)})")
+                    return
+                if name in OUT_ARGS:
+                    a = [x.strip() for x in split_top(args, ",")]
+                    outs = [a[k] for k in OUT_ARGS[name]]
+                    for o in outs:
+                        if re.match(r"^\w+$", o):
+                            assigned.add(o)
+                    lhs = ", ".join(ex.tr(o, lhs=True) for o in outs)
+                    emit(f"{lhs} = {name}({', '.join(ex.tr(x) for x in a)})")
                     return
                 if name in OUT_LAST:        # MPI reductions with an output argument: call sumall(a, b) -> b = sumall(a)
                     a = [x.strip() for x in split_top(args, ",")]

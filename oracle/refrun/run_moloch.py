@@ -648,6 +648,78 @@ SETUP_FIELDS = ["hx", "hy", "zeta", "fmz", "fmzf", "zetaf", "rfmzu", "rfmzv", "c
                 "tetav", "ffilt"]
 
 
+def reference_set_nproc(jx, iy, kz, i_band, i_crm, nproc, myid, njxcpus=-1, niycpus=-1) -> dict:
+    """set_nproc (Main/mpplib/mod_mppparam.F90:1250-1641) executed from source for one rank.  The MPI Cartesian
+    topology calls are stubs with the standard's semantics (row-major coordinates, mpi_cart_shift with
+    periodic wrap, mpi_proc_null outside a non-periodic dimension).  Returns the decomposition it computed."""
+    ns = dict(INTRINSICS)
+    seen = {}
+
+    class Cart:
+        def __init__(self, dims, periods):
+            self.dims, self.periods = [int(x) for x in dims.a], [bool(x) for x in periods.a]
+
+        def rank_of(self, c):
+            c = list(c)
+            for d in (0, 1):
+                if c[d] < 0 or c[d] >= self.dims[d]:
+                    if not self.periods[d]:
+                        return -1
+                    c[d] %= self.dims[d]
+            return c[0] * self.dims[1] + c[1]
+
+        def coords(self, r):
+            return [r // self.dims[1], r % self.dims[1]]
+
+    def mpi_cart_create(comm, nd, dims, periods, reorder, new, err):
+        seen["dims"] = [int(x) for x in dims.a]
+        return Cart(dims, periods)
+
+    def mpi_cart_coords(comm, rank, nd, coords, err):
+        coords.a[:] = comm.coords(rank)
+
+    def mpi_cart_shift(comm, direction, disp, src, dst, err):
+        c = comm.coords(myid)
+        lo, hi = list(c), list(c)
+        lo[direction] -= disp
+        hi[direction] += disp
+        return comm.rank_of(lo), comm.rank_of(hi)
+
+    def fatal(*a):
+        raise RuntimeError("fatal: " + str(a[-1]))
+    ma = _Obj(location=FArr(np.zeros(2, dtype=np.int64), [1]))
+    ns.update(ma=ma, mpi_proc_null=-1, nproc=nproc, myid=myid, jx=jx, iy=iy, kz=kz, kzp1=kz + 1, i_band=i_band,
+              i_crm=i_crm, njxcpus=njxcpus, niycpus=niycpus, nsg=1, jxsg=jx, iysg=iy, mycomm=0, lreorder=False,
+              iocpu=0, ccio=0, italk=0, ccid=0, mpierr=0, mpi_success=0, ifake=None, windows=None,
+              mpi_cart_create=mpi_cart_create, mpi_comm_rank=lambda comm, r, err: myid,
+              mpi_cart_coords=mpi_cart_coords, mpi_comm_split=lambda *a: 0, mpi_cart_shift=mpi_cart_shift,
+              mpi_cart_rank=lambda comm, coords, r, err: comm.rank_of([int(x) for x in coords.a]),
+              bcast=lambda *a: None, fatal=fatal, cartesian_communicator=None, cartesian_row_communicator=None,
+              cartesian_column_communicator=None)
+    st = F.preprocess(open(os.path.join(REF, "Main/mpplib/mod_mppparam.F90")).read(), defines=("USE_MPI3",))
+    r = F.find_routines(st)["set_nproc"]
+    exec(F.compile_source(F.Translator({"location"}).routine(r), "<mod_mppparam.F90:set_nproc>"), ns)
+    ns["set_nproc"]()
+    # setup_model_indexes (Main/mod_atm_interface.F90:182-382): the loop and ghost ranges of this rank
+    ar = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mod_atm_interface.F90")).read()))
+    exec(F.compile_source(F.Translator(set()).routine(ar["setup_model_indexes"]),
+                          "<mod_atm_interface.F90:setup_model_indexes>"), ns)
+    ns.update(idynamic=3, idiffu=1)
+    ns["setup_model_indexes"]()
+    idx = {k: ns[k] for k in ("jde1", "jde2", "ide1", "ide2", "jdi1", "jdi2", "idi1", "idi2", "jdii1", "jdii2", "idii1",
+                              "idii2", "jce1", "jce2", "ice1", "ice2", "jci1", "jci2", "ici1", "ici2", "jce1ga",
+                              "jce2ga", "ice1ga", "ice2ga", "jce1gb", "jce2gb", "ice1gb", "ice2gb", "jde1ga", "jde2ga",
+                              "ide1ga", "ide2ga", "jde1gb", "jde2gb", "ide1gb", "ide2gb", "jci1ga", "jci2ga", "ici1ga",
+                              "ici2ga") if k in ns}
+    out = {k: ns[k] for k in ("jxp", "iyp", "global_dot_jstart", "global_dot_jend", "global_dot_istart",
+                              "global_dot_iend", "global_cross_jstart", "global_cross_jend", "global_cross_istart",
+                              "global_cross_iend")}
+    out.update(left=ma.left, right=ma.right, bottom=ma.bottom, top=ma.top, has_bdyleft=bool(ma.has_bdyleft),
+               has_bdyright=bool(ma.has_bdyright), has_bdybottom=bool(ma.has_bdybottom),
+               has_bdytop=bool(ma.has_bdytop), dims=seen.get("dims", [1, 1]), indexes=idx)
+    return out
+
+
 class _Comm:
     """mpi_neighbor_alltoallv on a 2-D Cartesian communicator, for ranks that run as threads of this
     process: neighbour order (dim 0 -, dim 0 +, dim 1 -, dim 1 +) = (left, right, bottom, top); what a rank

@@ -127,6 +127,38 @@ def test_reference_multirank_matches_oracle(case, px, py):
 
 
 @pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+def test_reference_set_nproc_matches_decomp():
+    """set_nproc (Main/mpplib/mod_mppparam.F90:1250-1641) and setup_model_indexes
+    (Main/mod_atm_interface.F90:182-382) executed from source, rank by rank, against regcm_b200/decomp.py:
+    process grid, dot/cross ranges, neighbours, boundary flags, interior and ghost ranges."""
+    from regcm_b200.decomp import default_cpus_per_dim, make_geom
+    n = 0
+    for jx, iy, band, crm in ((400, 400, 0, 0), (47, 53, 0, 0), (46, 50, 1, 0), (40, 24, 1, 1), (1536, 1536, 0, 0),
+                              (100, 300, 0, 0), (300, 100, 0, 0)):
+        for nproc in (1, 2, 3, 4, 6, 8):
+            for r in range(nproc):
+                ref = R.reference_set_nproc(jx, iy, 41, band, crm, nproc, r)
+                if nproc > 1:
+                    assert default_cpus_per_dim(nproc, jx, iy) == tuple(ref["dims"])
+                g = make_geom(jx, iy, 41, band, crm, ref["dims"][0], ref["dims"][1], r)
+                mine = dict(global_dot_jstart=g.jde1, global_dot_jend=g.jde2, global_dot_istart=g.ide1,
+                            global_dot_iend=g.ide2, global_cross_jstart=g.jce1, global_cross_jend=g.jce2,
+                            global_cross_istart=g.ice1, global_cross_iend=g.ice2, has_bdyleft=g.bl, has_bdyright=g.br,
+                            has_bdybottom=g.bb, has_bdytop=g.bt)
+                if nproc > 1:
+                    mine.update(left=g.left, right=g.right, bottom=g.bottom, top=g.top)
+                assert {k: ref[k] for k in mine} == mine, (jx, iy, band, crm, nproc, r)
+                ix = ref["indexes"]
+                for k in ("jde1", "jde2", "ide1", "ide2", "jdi1", "jdi2", "idi1", "idi2", "jce1", "jce2", "ice1", "ice2",
+                          "jci1", "jci2", "ici1", "ici2"):
+                    assert ix[k] == getattr(g, k), (k, jx, iy, nproc, r)
+                assert (ix["jce1ga"], ix["jce2ga"], ix["ice1ga"], ix["ice2ga"]) == g.ext("cross", 1, 1)
+                assert (ix["jde1gb"], ix["jde2gb"], ix["ide1gb"], ix["ide2gb"]) == g.ext("dot", 2, 2)
+                n += 1
+    assert n > 150
+
+
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
 def test_reference_massck_matches_oracle():
     """massck's atmosphere sums (Main/mod_massck.F90:77-185) executed from source == the oracle's, bit for bit
     (same single running sums); the device's row-wise sums are compared with these to 1e-12."""

@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--slice", action="store_true")
     ap.add_argument("--spectral", action="store_true")
     ap.add_argument("--tke", action="store_true")
+    ap.add_argument("--massck", action="store_true", help="also time massck + the ps guard once per step")
+    ap.add_argument("--diag", action="store_true", help="tendency diagnostics (idiag, ichdiag)")
     ap.add_argument("--crop", type=int, default=0, help="crop the horizontal domain to N x N")
     args = ap.parse_args()
     wl = S.WORKLOADS[args.workload]
@@ -51,6 +53,10 @@ def main():
         kw.update(do_slice=1, icldmstrat=1)
     if args.tke:
         kw.update(ibltyp=2, tkemin=1.0e-4)
+    if args.massck:
+        kw.update(do_massck=1)
+    if args.diag:
+        kw.update(idiag=1, ichdiag=1)
     wl = replace(wl, **kw)
     t0 = time.perf_counter()
     m = MolochB200(wl).allocate_moloch()
@@ -62,7 +68,7 @@ def main():
             wl.tkemin + 0.4 * np.exp(-np.maximum(zf, 0.0) / 800.0),
             (wl.kz + 1, g.ice2 - g.ice1 + 1, g.jce2 - g.jce1 + 1)))
         boxes["tke"] = (g.jce1, g.jce2, g.ice1, g.ice2)
-    if wl.do_slice:
+    if wl.do_slice or wl.do_massck:
         g = m.g
         Jg, Ig = np.meshgrid(np.arange(g.jce1, g.jce2 + 1, dtype=np.float64),
                              np.arange(g.ice1, g.ice2 + 1, dtype=np.float64))
@@ -70,9 +76,10 @@ def main():
         fields["zetaf"] = S.md_zeta(S.model_zitaf(wl.kz, wl.mo_ztop)[:, None, None], ht[None], wl.mo_ztop, wl.mo_h,
                                     wl.mo_a0)
         boxes["zetaf"] = (g.jce1, g.jce2, g.ice1, g.ice2)
-        dl = S.raddeg * wl.dx / S.earthrad
-        fields["xlat"] = np.ascontiguousarray(wl.clat - dl * (float(wl.iy) * 0.5 - Ig + 0.5))
-        boxes["xlat"] = boxes["zetaf"]
+        if wl.do_slice:
+            dl = S.raddeg * wl.dx / S.earthrad
+            fields["xlat"] = np.ascontiguousarray(wl.clat - dl * (float(wl.iy) * 0.5 - Ig + 0.5))
+            boxes["xlat"] = boxes["zetaf"]
     m.init_moloch(fields, profiles, boxes)
     if wl.do_bdy:
         base = {n: np.zeros(m.global_shape(n)) for n in ("u", "v", "t", "pai", "qx", "ps")}
@@ -88,7 +95,11 @@ def main():
     m.sync()
     ms_step = (time.perf_counter() - t0) / args.steps * 1e3
     m.profile_enable(True)
-    m.moloch(args.steps)
+    for _ in range(args.steps):
+        m.moloch(1)
+        if args.massck:
+            m.massck()
+            m.ps_check()
     prof = m.profile_read()
     m.profile_enable(False)
     g = m.g

@@ -158,8 +158,12 @@ class ReferenceRun:
             return ns[name]
 
         for n in ("u", "v", "ux", "vx", "w", "pai", "tetav", "t", "qx", "tvirt", "p", "rho", "fmz", "fmzf", "rfmzu",
-                  "rfmzv", "hx", "hy", "coru", "corv", "bdywtu", "bdywtv", "bdywtw", "ps"):
+                  "rfmzv", "hx", "hy", "coru", "corv", "ps"):
             from_oracle(n)
+        for n, bx in (("bdywtu", (g.jdi1, g.jdi2, g.ici1, g.ici2)), ("bdywtv", (g.jci1, g.jci2, g.idi1, g.idi2)),
+                      ("bdywtw", (g.jci1, g.jci2, g.ici1, g.ici2))):       # Main/mod_moloch.F90:164-166
+            a = np.array(H.cut(oracle.get(n), g, bx), dtype=np.float64)
+            self.arr[n] = ns[n] = FArr(a, [bx[0], bx[2], 1])
         from_oracle("z", "zeta", H.ALLOC["zeta"])
         from_oracle("qsat")
         ns["mo_atm"] = _Obj()
@@ -188,22 +192,27 @@ class ReferenceRun:
         zeros("s", "cross", 0, 0, 1, kz + 1); zeros("wwkw", "cross", 0, 0, 2, kz + 1)
         zeros("tetavf", "cross", 0, 0, 2, kz); zeros("zdiv2", "cross", 1, 1, 1, kz)
         zeros("wz", "cross", 2, 2, 1, kz); zeros("p0", "cross", 2, 2, 1, kz); zeros("wfw", "cross", 0, 0, 1, kz + 1)
-        zeros("wx", "cross", 1, 1, 1, kz); zeros("laplacian", "cross", 0, 0, 1, kz)
+        zeros("wx", "cross", 1, 1, 1, kz)
+        inner = [(g.jci1, g.jci2), (g.ici1, g.ici2)]
+
+        def interior(name, k2, nspec=0):
+            self.arr[name] = ns[name] = FArr.alloc(inner + [(1, k2)] + ([(1, nspec)] if nspec else []))
+        interior("laplacian", kz)
         zeros("ud", "u", 0, 0, 1, kz); zeros("vd", "v", 0, 0, 1, kz)
         ns["zpby"] = FArr.alloc([(g.jce1, g.jce2), (g.ici1, g.ice2 + gt), (1, kz)])
         ns["zpbw"] = FArr.alloc([(g.jci1, g.jce2 + gr), (g.ice1, g.ice2), (1, kz)])
         for n in ("tten", "uten", "vten", "cldfra", "cldlwc"):    # cldfra/cldlwc: physics arrays reset_tendencies clears too
-            zeros(n, "cross", 0, 0, 1, kz)
-        zeros("qxten", "cross", 0, 0, 1, kz, wl.nqx)
+            interior(n, kz)
+        interior("qxten", kz, wl.nqx)
         if wl.ntr > 0:
-            zeros("chiten", "cross", 0, 0, 1, kz, wl.ntr)
+            interior("chiten", kz, wl.ntr)
         ns["qv"] = ns["qx"].view_last(1); ns["qvten"] = ns["qxten"].view_last(1)
         if wl.ipptls > 0:
             ns["qc"] = ns["qx"].view_last(2)
             if wl.ipptls > 1:
                 ns["qi"], ns["qr"], ns["qs"] = (ns["qx"].view_last(n) for n in (3, 4, 5))
         if wl.ibltyp == 2:
-            from_oracle("tke"); zeros("tketen", "cross", 0, 0, 1, kz + 1); zeros("tkex", "cross", 0, 0, 1, kz)
+            from_oracle("tke"); interior("tketen", kz + 1); zeros("tkex", "cross", 0, 0, 1, kz)
         ib = [(g.jci1, g.jci2), (g.ici1, g.ici2), (1, kz)]
         if wl.idiag > 0:       # Main/mod_moloch.F90:187-188 and the tdiag/qdiag members used by the path
             ns["ten0"], ns["qen0"] = FArr.alloc(ib), FArr.alloc(ib)
@@ -646,6 +655,30 @@ def reference_massck(wl, o) -> dict:
 SETUP_FIELDS = ["hx", "hy", "zeta", "fmz", "fmzf", "zetaf", "rfmzu", "rfmzv", "coru", "corv", "mx2", "rmx", "rmu", "rmv",
                 "gzitak", "gzitakh", "xkdamp", "xknu", "bdywtu", "bdywtv", "bdywtw", "pai", "p", "qsat", "rho", "tvirt",
                 "tetav", "ffilt"]
+
+
+def reference_allocation_bounds(run: "ReferenceRun") -> dict:
+    """allocate_atmosphere (Main/mod_atm_interface.F90:579-624) and allocate_moloch (Main/mod_moloch.F90:159-199)
+    executed from source with the index ranges of `run`'s rank: name -> Fortran bounds of every array."""
+    ns = dict(INTRINSICS)
+    keys = [k for k, v in run.ns.items() if isinstance(v, (int, float, bool)) and not k.startswith("_")]
+    ns.update({k: run.ns[k] for k in keys})
+    mods = ("gzitak", "gzitakh", "laplacian", "bdywtu", "bdywtv", "bdywtw", "wwkw", "tetavf", "s", "zdiv2", "wz", "p0",
+            "wfw", "wx", "zpby", "zpbw", "mx2", "rmx", "rmu", "rmv", "coru", "corv", "tkex", "ten0", "qen0", "chiten0",
+            "ud", "vd", "xkdamp", "xknu")
+    for n in mods:
+        ns[n] = None
+    tr = F.Translator(set())
+    ast_ = F.preprocess(open(os.path.join(REF, "Main/mod_atm_interface.F90")).read())
+    mst = F.preprocess(open(os.path.join(REF, "Main/mod_moloch.F90")).read())
+    exec(F.compile_source(tr.routine(F.find_internal(ast_, "allocate_atmosphere")), "<allocate_atmosphere>"), ns)
+    exec(F.compile_source(tr.routine(F.find_routines(mst)["allocate_moloch"]), "<allocate_moloch>"), ns)
+    atm = _Obj()
+    ns["allocate_atmosphere"](atm)
+    ns["allocate_moloch"]()
+    out = {"mo_atm%" + k: v.bounds() for k, v in vars(atm).items() if isinstance(v, FArr)}
+    out.update({n: ns[n].bounds() for n in mods if isinstance(ns[n], FArr)})
+    return out
 
 
 def reference_set_nproc(jx, iy, kz, i_band, i_crm, nproc, myid, njxcpus=-1, niycpus=-1) -> dict:

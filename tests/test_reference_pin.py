@@ -127,6 +127,40 @@ def test_reference_multirank_matches_oracle(case, px, py):
 
 
 @pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+def test_reference_runs_use_the_reference_allocation():
+    """The arrays of a ReferenceRun have exactly the bounds allocate_atmosphere
+    (Main/mod_atm_interface.F90:579-624) and allocate_moloch (Main/mod_moloch.F90:159-199) give when THEY are
+    executed from source -- so the bounds checking of those runs is the reference's own allocation -- and the
+    host model's table (regcm_b200/hostmodel.py) agrees with them."""
+    from regcm_b200 import hostmodel as H
+    from regcm_b200 import synthetic as S
+    wl = S.small(S.WORKLOADS["cordex25"], 16, 14, 8, ntr=1, nspgx=4, mo_nsound=3, ibltyp=2, idiag=1, ichdiag=1, do_bdy=1)
+    o, B = make_oracle_bdy(wl)
+    comm = R._Comm(4)
+    alias = {"mo_atm%zeta": "z", "mo_atm%qs": "qsat"}
+    hname = {"z": "zeta"}
+    for rank in range(4):
+        r = R.ReferenceRun(wl, o, B, px=2, py=2, rank=rank, comm=comm)
+        ref = R.reference_allocation_bounds(r)
+        n = 0
+        for k, b in ref.items():
+            name = alias.get(k, k.replace("mo_atm%", ""))
+            a = r.ns.get(name)
+            if a is None:
+                assert name in ("pf", "dz"), name          # not used by the path
+                continue
+            assert a.bounds() == b, (rank, k, b, a.bounds())
+            hn = hname.get(name, name)
+            # (arrays the reference allocates on the interior only cross the ABI on the owned box: skipped)
+            if hn in H.ALLOC and hn not in ("tten", "uten", "vten", "qxten", "chiten", "tketen", "bdywtu", "bdywtv",
+                                            "bdywtw", "tetavf", "ten0", "qen0", "chiten0"):
+                hb = H.bounds(r.g, hn)                      # the host hand-off boxes: same horizontal bounds
+                assert (b[0][0], b[0][1], b[1][0], b[1][1]) == hb, (rank, hn, b, hb)
+            n += 1
+        assert n >= 45
+
+
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
 def test_reference_set_nproc_matches_decomp():
     """set_nproc (Main/mpplib/mod_mppparam.F90:1250-1641) and setup_model_indexes
     (Main/mod_atm_interface.F90:182-382) executed from source, rank by rank, against regcm_b200/decomp.py:

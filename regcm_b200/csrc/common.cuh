@@ -157,6 +157,25 @@ struct WaitCtl {
   long long timeout_cycles;
 };
 #ifdef __CUDACC__
+// system-scope release store / acquire load of a flag word (arrival counters of
+// the peer-store halo transport).  MB_HOST_EMU: the tests' host build of this
+// source (tests/emu) -- ranks are threads there and the flags C++ atomics.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+#ifdef MB_HOST_EMU
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+#ifdef MB_HOST_EMU
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
 __device__ __forceinline__ void edge_push(const PushCtl& pc, const EdgePush& e, int j, int i, int k, double v) {
   if (e.q[0] && j == e.j1 && i >= e.i1 && i <= e.i2)
     e.q[0][(long long)(k - 1) * pc.pplane[0] + (long long)(i + e.di[0] - pc.pi0[0]) * pc.pNJ[0] + (j + e.dj[0] - pc.pj0[0])] = v;
@@ -186,15 +205,13 @@ __device__ __forceinline__ void halo_sync(const WaitCtl& w) {
       __threadfence_system();
       for (int sd = 0; sd < 4; ++sd)
         if ((w.mask >> sd) & 1)
-          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(w.pflag[sd]), "l"(w.seq) : "memory");
+          st_release_sys(w.pflag[sd], w.seq);
     }
     const long long t0 = clock64();
     for (int sd = 0; sd < 4; ++sd) {
       if (!((need >> sd) & 1)) continue;
       for (;;) {
-        unsigned long long v;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w.flags + sd) : "memory");
-        if (v >= w.seq) break;
+        if (ld_acquire_sys(w.flags + sd) >= w.seq) break;
         if (clock64() - t0 > w.timeout_cycles) { w.flags[5] = w.seq; break; }   // neighbour never arrived
       }
     }

@@ -119,6 +119,13 @@ struct NcclApi {
 static NcclApi g_nccl;
 static int nccl_load() {
   if (g_nccl.lib) return 0;
+#ifdef MB_HOST_EMU   // tests/emu: the in-process mailbox that stands in for NCCL
+  g_nccl.lib = (void*)&g_nccl;
+  g_nccl.GetUniqueId = ncclGetUniqueId; g_nccl.CommInitRank = ncclCommInitRank; g_nccl.CommDestroy = ncclCommDestroy;
+  g_nccl.Send = ncclSend; g_nccl.Recv = ncclRecv; g_nccl.GroupStart = ncclGroupStart; g_nccl.GroupEnd = ncclGroupEnd;
+  g_nccl.GetErrorString = ncclGetErrorString;
+  return 0;
+#endif
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
   if (!g_nccl.lib) return fail(std::string("cannot dlopen libnccl.so.2: ") + dlerror());
@@ -341,14 +348,12 @@ __global__ void moloch_halo_push(Geo g, PushParams h) {
       __threadfence_system();
       for (int sd = 0; sd < 4; ++sd)
         if ((h.mask >> sd) & 1)
-          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(h.pflag[sd]), "l"(h.seq) : "memory");
+          st_release_sys(h.pflag[sd], h.seq);
       const long long t0 = clock64();
       for (int sd = 0; sd < 4; ++sd) {
         if (!((h.mask >> sd) & 1)) continue;
         for (;;) {
-          unsigned long long v;
-          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(h.flags + sd) : "memory");
-          if (v >= h.seq) break;
+          if (ld_acquire_sys(h.flags + sd) >= h.seq) break;
           if (clock64() - t0 > h.timeout_cycles) { h.flags[5] = h.seq; break; }  // neighbour never arrived
         }
       }

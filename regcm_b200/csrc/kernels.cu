@@ -350,6 +350,12 @@ int k_wsolve(Ctx& c, double dts, bool last, const PushCtl* pcp, const EdgePush* 
 // and the prefetch distance collapses; cp.async commit groups retire in order,
 // so D levels really stay in flight.
 // ---------------------------------------------------------------------------
+#ifdef MB_HOST_EMU   // tests/emu: deferred copies that land at the matching wait_group
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) { emu::cp_async_enqueue(smem_dst, gsrc, 8); }
+__device__ __forceinline__ void cp_async_commit() { emu::cp_async_commit(); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { emu::cp_async_wait(N); }
+#else
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
@@ -357,6 +363,7 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 template <int D>
 __global__ void __launch_bounds__(32)

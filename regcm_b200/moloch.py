@@ -90,12 +90,17 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         raise MolochError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the product has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    _lib = bind_library(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL), LIB_PATH)
+    return _lib
+
+
+def bind_library(lib, path: str = "?"):
+    """ctypes signatures of every entry of include/moloch_b200.h on a loaded library object."""
     ctx = C.c_void_p
     lib.moloch_b200_last_error.restype = C.c_char_p
     lib.moloch_b200_config_size.restype = C.c_uint64
     if int(lib.moloch_b200_config_size()) != C.sizeof(Config):
-        raise MolochError(f"{LIB_PATH}: moloch_b200_config is {int(lib.moloch_b200_config_size())} bytes in the "
+        raise MolochError(f"{path}: moloch_b200_config is {int(lib.moloch_b200_config_size())} bytes in the "
                           f"library, {C.sizeof(Config)} in this binding (stale build?)")
     lib.moloch_b200_create.argtypes = [C.POINTER(Config), C.POINTER(ctx)]
     lib.moloch_b200_destroy.argtypes = [ctx]
@@ -134,7 +139,6 @@ def load_library():
     lib.moloch_b200_device_bytes.restype = C.c_uint64
     lib.moloch_b200_halo_plan.argtypes = [C.POINTER(Config), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p]
-    _lib = lib
     return lib
 
 
@@ -227,8 +231,8 @@ class MolochB200:
         self._chk(self.lib.moloch_b200_p2p_connect(self.ctx, buf, len(blobs)))
 
     @staticmethod
-    def comm_id() -> bytes:
-        lib = load_library()
+    def comm_id(lib=None) -> bytes:
+        lib = lib if lib is not None else load_library()
         buf = C.create_string_buffer(128)
         if lib.moloch_b200_comm_id(buf):
             raise MolochError(lib.moloch_b200_last_error().decode())

@@ -10,12 +10,14 @@ import numpy as np
 
 from regcm_b200.moloch import MolochB200
 
+import util
+
 
 class MultiRank:
     def __init__(self, wl, px, py, fields, profiles, devices=None, transport="p2p", bdy=None, boundary=None):
         self.wl, self.n = wl, px * py
         devices = devices or list(range(self.n))
-        uid = MolochB200.comm_id() if (self.n > 1 and transport == "nccl") else None
+        uid = MolochB200.comm_id(util.LIB) if (self.n > 1 and transport == "nccl") else None
         self.ranks = [None] * self.n
         blobs = [None] * self.n
         bar = threading.Barrier(self.n)
@@ -23,7 +25,8 @@ class MultiRank:
 
         def boot(r):
             try:
-                m = MolochB200(wl, rank=r, nranks=self.n, px=px, py=py, device=devices[r], bdy=bdy).allocate_moloch()
+                m = MolochB200(wl, rank=r, nranks=self.n, px=px, py=py, device=devices[r], bdy=bdy,
+                               lib=util.LIB).allocate_moloch()
                 self.ranks[r] = m
                 if self.n > 1 and transport == "p2p":
                     blobs[r] = m.p2p_export()

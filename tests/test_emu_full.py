@@ -1,0 +1,138 @@
+"""The product's CUDA sources executed on the CPU (TEST INFRASTRUCTURE).
+
+tests/emu_lib.py compiles regcm_b200/csrc/*.cu -- the files nvcc builds for
+sm_100a -- with g++ against a SIMT stand-in (threads are fibers; __syncthreads,
+warp shuffles and votes are real rendez-vous points; cp.async lands only at its
+wait_group; device and shared memory are NaN-poisoned; ranks of a multi-GPU run
+are threads whose peer mappings are plain pointers).  These tests then run the
+*bodies of the GPU parity tests* (tests/test_gpu_*.py) against that build: same
+C ABI, same Python mirror, same oracle, same bit-exact bar.  They do not replace
+the GPU tests (no SASS, no real memory model, the division seed is exact instead
+of MUFU.RCP64H); they make sure that every kernel, launcher, halo plan and ABI
+entry has been executed before it meets a B200 -- in particular code written
+when the round's GPU budget was already spent.
+
+A representative subset runs by default (about two minutes); EMU_FULL=1 runs
+every case of the GPU test files, forwards and in reverse CTA/thread order.
+"""
+import os
+
+import pytest
+
+import emu_lib
+import util
+
+FULL = os.environ.get("EMU_FULL", "0") == "1"
+
+
+@pytest.fixture(autouse=True)
+def _emulated_library(monkeypatch):
+    lib = emu_lib.load()
+    lib.emu_set_order(0)
+    monkeypatch.setattr(util, "LIB", lib)
+    yield lib
+    lib.emu_set_order(0)
+
+
+def _gpu_tests():
+    import test_gpu_multi as M
+    import test_gpu_parity as P
+    import test_gpu_zbdy as Z
+    return P, Z, M
+
+
+def _pick(cases, default):
+    return [c for c in cases if c != "wide"] if FULL else default
+
+
+P_CASES = ["periodic_flat", "periodic_hills", "limited_area", "band", "rotllr", "no_divdamp", "no_divfilter",
+           "no_damp_no_filter", "tall"]
+Z_CASES = ["lam_full", "lam_flux_tracers", "lam_no_icbc_condensate", "lam_ipptls1", "band", "lam_tke", "no_sponge",
+           "lam_slice", "spectral", "spectral_band"]
+
+
+@pytest.mark.parametrize("case", _pick(P_CASES, ["periodic_hills", "limited_area"]))
+def test_dycore_phases(case):
+    _gpu_tests()[0].test_phases_bit_exact(case)
+
+
+@pytest.mark.parametrize("case", _pick(P_CASES, ["band", "rotllr", "no_damp_no_filter"]))
+def test_dycore_steps(case):
+    _gpu_tests()[0].test_steps_bit_exact(case)
+
+
+def test_dycore_steps_reverse_order(_emulated_library):
+    """CTAs and threads in the opposite order: a dependence between threads that no barrier orders shows up."""
+    _emulated_library.emu_set_order(1)
+    _gpu_tests()[0].test_steps_bit_exact("limited_area")
+
+
+@pytest.mark.skipif(not FULL, reason="EMU_FULL=1: 70 levels, the wide shared-memory variants of the column kernels")
+def test_dycore_tall():
+    _gpu_tests()[0].test_steps_bit_exact("tall")
+
+
+def test_wafone_single_field():
+    _gpu_tests()[0].test_wafone_single_field()
+
+
+@pytest.mark.parametrize("case", ["periodic_hills", "limited_area", "limited_area_rotllr", "limited_area_boundary",
+                                  "limited_area_spectral", "limited_area_tke"])
+def test_reference_golden(case):
+    """The emulated CUDA path against the digests of the executed reference source."""
+    _gpu_tests()[0].test_reference_golden(case)
+
+
+@pytest.mark.parametrize("case", ["band_boundary", "no_damp_no_filter", "vapour_only", "limited_area_diag"])
+def test_reference_golden_more(case):
+    _gpu_tests()[1].test_reference_golden_more(case)
+
+
+@pytest.mark.parametrize("case", _pick(Z_CASES, ["lam_full", "lam_ipptls1"]))
+def test_boundary(case):
+    _gpu_tests()[1].test_boundary_bit_exact(case)
+
+
+@pytest.mark.parametrize("case", _pick(Z_CASES, ["lam_tke", "spectral_band", "lam_slice"]))
+def test_steps_with_boundary(case):
+    _gpu_tests()[1].test_steps_with_boundary_bit_exact(case)
+
+
+def test_boundary_reverse_order(_emulated_library):
+    _emulated_library.emu_set_order(1)
+    _gpu_tests()[1].test_steps_with_boundary_bit_exact("lam_full")
+
+
+def test_mkslice_massck_tke_misc():
+    Z = _gpu_tests()[1]
+    Z.test_mkslice()
+    Z.test_massck_and_ps_guard()
+    Z.test_tke_steps_periodic()
+    Z.test_bdy_shift_swaps_buffers()
+    Z.test_boundary_needs_configuration()
+
+
+def _multi_cases():
+    M = _gpu_tests()[2]
+    keep = None if FULL else {("periodic", "p2p"), ("limited_area_2x2", "p2p"), ("limited_area_2x4", "p2p"),
+                              ("band_2x4", "p2p_unfused"), ("limited_area_2x2", "nccl")}
+    out = []
+    for tr in ("p2p", "p2p_unfused", "nccl"):
+        for c in M.CASES:
+            if tr != "p2p" and c[0] not in ("periodic", "limited_area", "limited_area_2x2", "band_2x4"):
+                continue
+            if keep is None or (c[0], tr) in keep:
+                out.append(pytest.param(*c, tr, id=f"{c[0]}-{tr}"))
+    return out
+
+
+@pytest.mark.parametrize("name,wl,px,py,transport", _multi_cases())
+def test_decomposed(name, wl, px, py, transport, monkeypatch):
+    """Ranks are threads: the peer-store transport (fused into the sound kernels or as separate rounds) and
+    the NCCL path (mailbox) against the single-domain oracle, bit for bit."""
+    _gpu_tests()[2].test_decomposed_bit_exact(name, wl, px, py, transport, monkeypatch)
+
+
+@pytest.mark.parametrize("px,py", [(2, 1), (1, 2), (2, 2)] if FULL else [(2, 2)])
+def test_decomposed_boundary(px, py):
+    _gpu_tests()[2].test_decomposed_boundary_bit_exact(px, py)

@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 
 
 def ndev():
-    return load_library().moloch_b200_device_count()
+    import util
+    return (util.LIB if util.LIB is not None else load_library()).moloch_b200_device_count()
 
 
 CASES = [

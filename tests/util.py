@@ -8,6 +8,11 @@ from oracle.oracle import Oracle
 from regcm_b200 import synthetic as S
 from regcm_b200.moloch import PROFILE_NAMES, STATE_FIELDS, STATIC_FIELDS, MolochB200
 
+# Library object handed to MolochB200(lib=...).  None: the product's CUDA library
+# (GPU tests).  tests/test_emu_full.py points it at the host build of the same
+# sources (tests/emu_lib.py) and re-runs the GPU tests' bodies on the CPU.
+LIB = None
+
 PROGNOSTIC = ["u", "v", "w", "pai", "tetav", "t", "qx", "ux", "vx"]
 DIAGNOSTIC = ["tvirt", "p", "rho", "qsat", "ps"]
 
@@ -69,7 +74,7 @@ def oracle_inputs(o, wl):
 
 
 def make_gpu(wl, fields, profiles, rank=0, nranks=1, px=None, py=None, device=-1):
-    m = MolochB200(wl, rank=rank, nranks=nranks, px=px, py=py, device=device).allocate_moloch()
+    m = MolochB200(wl, rank=rank, nranks=nranks, px=px, py=py, device=device, lib=LIB).allocate_moloch()
     if wl.lrotllr:
         profiles = dict(profiles)
     m.init_moloch(fields, profiles)
@@ -81,7 +86,7 @@ def make_gpu_bdy(wl, o, B, device=-1):
     fields, profiles = oracle_inputs(o, wl)
     if wl.lrotllr:
         profiles["rlat"] = S.make_primary(wl)["rlat"]
-    m = MolochB200(wl, device=device, bdy=bdy_tables_from_oracle(wl, o)).allocate_moloch()
+    m = MolochB200(wl, device=device, bdy=bdy_tables_from_oracle(wl, o), lib=LIB).allocate_moloch()
     if wl.ibltyp == 2:
         fields["tke"] = o.get("tke")
     if wl.do_slice:

@@ -174,6 +174,108 @@ def run_cpu_reference(wl, steps: int, warmup: int) -> dict:
             "ms_per_step": dt / steps * 1e3, "grid": [swl.jx, swl.iy, swl.kz]}
 
 
+def measure_e2e(m, wl, ksteps, barrier=lambda: None, allreduce_max=lambda x: x):
+    """The metric through the reference-facing hand-off with HOST buffers: every step the state the
+    physics reads goes device -> host and the tendencies host -> device (pinned memory), inside the
+    timed region.  `m`: an initialised MolochB200; wall-clock timing between two barriers."""
+    from regcm_b200 import hostmodel as H
+    from regcm_b200.moloch import STATE_FIELDS
+    g = m.g
+    down = [n for n in STATE_FIELDS if not (n == "trac" and wl.ntr == 0)]
+    up = ["tten", "uten", "vten", "qxten"] + (["chiten"] if wl.ntr > 0 else [])
+    hbuf, bytes_d2h, bytes_h2d = {}, 0, 0
+    for n in down + up:
+        box = H.bounds(g, n)
+        nk = m._levels(n)
+        nspec = wl.nqx if n in ("qx", "qxten") else wl.ntr if n in ("trac", "chiten") else 1
+        shp = (nspec, nk, box[3] - box[2] + 1, box[1] - box[0] + 1)
+        hbuf[n] = (m.pinned_empty(shp), box)
+        hbuf[n][0][...] = 0.0
+        if n in down:
+            bytes_d2h += int(np.prod(shp)) * 8
+        else:
+            bytes_h2d += int(np.prod(shp)) * 8
+
+    def e2e_step_sequential():
+        m.reset_tendencies()
+        m.dynamical_core()
+        m.diagnostics()
+        m.set_async(True)       # batch the hand-off: one sync per direction
+        for n in down:          # device -> host: what mkslice/physics read
+            buf, box = hbuf[n]
+            for s in range(buf.shape[0]):
+                m.get_local(n, box, s + 1 if n in ("qx", "trac") else 0, out=buf[s])
+        m.sync()                # the host physics would run here, on the downloaded state
+        for n in up:            # host -> device: the physics tendencies
+            buf, box = hbuf[n]
+            for s in range(buf.shape[0]):
+                m.set_local(n, buf[s], box, s + 1 if n in ("qxten", "chiten") else 0)
+        m.set_async(False)
+        m.status_update()
+
+    # Pipelined hand-off (moloch_b200_handoff): the rank's rows in slabs, state down on one copy
+    # stream, the tendencies of a slab up on a second one as soon as that slab's state (and the
+    # column physics on it -- none here) is done: both directions of the link overlap.
+    nslabs = int(os.environ.get("BENCH_HANDOFF_SLABS", "8"))
+    four_d = {"qx", "trac", "qxten", "chiten"}
+    xl_down = m.xfer_list([(n, s + 1 if n in four_d else 0, hbuf[n][0][s], hbuf[n][1])
+                           for n in down for s in range(hbuf[n][0].shape[0])])
+    xl_up = m.xfer_list([(n, s + 1 if n in four_d else 0, hbuf[n][0][s], hbuf[n][1])
+                         for n in up for s in range(hbuf[n][0].shape[0])])
+
+    def e2e_step_pipelined():
+        m.reset_tendencies()
+        m.dynamical_core()
+        m.diagnostics()
+        m.handoff(xl_down, xl_up, nslabs=nslabs)
+        m.status_update()
+
+    # untimed self-check of the pipelined path against the plain field transfers
+    handoff_mode, handoff_note = "pipelined", None
+    try:
+        m.reset_tendencies(); m.dynamical_core(); m.diagnostics()
+        hbuf["tten"][0][...] = 1.0e-5
+        m.handoff(xl_down, xl_up, nslabs=nslabs)
+        ok = True
+        for n in ("pai", "t", "qx", "ux"):
+            buf, box = hbuf[n]
+            for s in range(buf.shape[0]):
+                ok = ok and bool(np.array_equal(m.get_local(n, box, s + 1 if n in four_d else 0).reshape(buf[s].shape),
+                                                buf[s]))
+        buf, box = hbuf["tten"]
+        ok = ok and bool(np.array_equal(m.get_local("tten", box).reshape(buf[0].shape), buf[0]))
+        hbuf["tten"][0][...] = 0.0
+        m.handoff(xl_down, xl_up, nslabs=nslabs)
+        ok = ok and bool((m.get_local("tten", box) == 0.0).all())
+        m.status_update()
+        if not ok:
+            handoff_mode, handoff_note = "sequential", "pipelined hand-off failed its self-check"
+    except Exception as exc:  # noqa: BLE001
+        hbuf["tten"][0][...] = 0.0
+        handoff_mode, handoff_note = "sequential", f"pipelined hand-off unavailable: {exc}"
+    if os.environ.get("BENCH_HANDOFF", "") == "sequential":
+        handoff_mode, handoff_note = "sequential", "BENCH_HANDOFF=sequential"
+    e2e_step = e2e_step_pipelined if handoff_mode == "pipelined" else e2e_step_sequential
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ksteps):
+        e2e_step()
+    m.sync()
+    barrier()
+    dt = allreduce_max(time.perf_counter() - t0)
+    return {"value": wl.cells * ksteps / dt, "unit": "cell-updates/s",
+           "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h, "steps": ksteps,
+           "ms_per_step": dt / ksteps * 1e3,
+           "handoff": handoff_mode, "handoff_slabs": nslabs if handoff_mode == "pipelined" else 1,
+           "handoff_note": handoff_note,
+           "what": "moloch(): device dycore, D2H of u,v,w,ux,vx,pai,tetav,t,tvirt,p,rho,qsat,ps,qx,trac to "
+                   "pinned host arrays, H2D of tten,uten,vten,qxten,chiten, device status_update; pipelined: "
+                   "rows in slabs, both copy directions overlapped (moloch_b200_handoff)"}
+
+
+
 def base_line(wl, args, n_gpus):
     return {"metric": "MOLOCH dycore cell-updates/s", "unit": "cell-updates/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
@@ -345,54 +447,12 @@ def main():
     # ---- end to end through the reference-facing hand-off --------------------------
     e2e = None
     if not args.no_e2e:
-        down = [n for n in STATE_FIELDS if not (n == "trac" and wl.ntr == 0)]
-        up = ["tten", "uten", "vten", "qxten"] + (["chiten"] if wl.ntr > 0 else [])
-        hbuf, bytes_d2h, bytes_h2d = {}, 0, 0
-        for n in down + up:
-            box = H.bounds(g, n)
-            nk = m._levels(n)
-            nspec = wl.nqx if n in ("qx", "qxten") else wl.ntr if n in ("trac", "chiten") else 1
-            shp = (nspec, nk, box[3] - box[2] + 1, box[1] - box[0] + 1)
-            hbuf[n] = (m.pinned_empty(shp), box)
-            hbuf[n][0][...] = 0.0
-            if n in down:
-                bytes_d2h += int(np.prod(shp)) * 8
-            else:
-                bytes_h2d += int(np.prod(shp)) * 8
-
-        def e2e_step():
-            m.reset_tendencies()
-            m.dynamical_core()
-            m.diagnostics()
-            m.set_async(True)       # batch the hand-off: one sync per direction
-            for n in down:          # device -> host: what mkslice/physics read
-                buf, box = hbuf[n]
-                for s in range(buf.shape[0]):
-                    m.get_local(n, box, s + 1 if n in ("qx", "trac") else 0, out=buf[s])
-            m.sync()                # the host physics would run here, on the downloaded state
-            for n in up:            # host -> device: the physics tendencies
-                buf, box = hbuf[n]
-                for s in range(buf.shape[0]):
-                    m.set_local(n, buf[s], box, s + 1 if n in ("qxten", "chiten") else 0)
-            m.set_async(False)
-            m.status_update()
-
-        e2e_step()
-        ksteps = max(1, min(args.steps, 5))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            e2e_step()
-        m.sync()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": wl.cells * ksteps / float(dt.item()), "unit": "cell-updates/s",
-               "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h, "steps": ksteps,
-               "ms_per_step": float(dt.item()) / ksteps * 1e3,
-               "what": "moloch(): device dycore, D2H of u,v,w,ux,vx,pai,tetav,t,tvirt,p,rho,qsat,ps,qx,trac to "
-                       "pinned host arrays, H2D of tten,uten,vten,qxten,chiten, device status_update"}
+        def allmax(x):
+            t = torch.tensor([x], device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        e2e = measure_e2e(m, wl, max(1, min(args.steps, 5)), barrier, allmax)
 
     finite = bool(np.isfinite(m.get_local("pai")).all())
     cpu = None

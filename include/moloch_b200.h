@@ -181,6 +181,30 @@ int moloch_b200_set_ibnd(moloch_b200_ctx* ctx, int which, const int32_t* ibnd, i
  * with moloch_b200_sync (host buffers must stay valid until then).           */
 int moloch_b200_set_async(moloch_b200_ctx* ctx, int on);
 
+/* Pipelined physics hand-off (the state the column physics of
+ * physical_parametrizations reads, Main/mod_moloch.F90:1143-1401, and the
+ * tendencies status_update consumes, :1410-1430).  The rank's rows are cut into
+ * `nslabs` slabs along i.  Slab by slab the `down` arrays travel device -> host
+ * on one copy stream; as soon as a slab has arrived `physics(user, i1, i2)` is
+ * called on the host (may be NULL) and that slab of the `up` arrays travels
+ * host -> device on a second copy stream, so that both directions of the link
+ * and the host physics overlap.  Every array is gathered/scattered on the device
+ * through a contiguous staging buffer; the PCIe transfers are long linear runs.
+ * On return all transfers have completed and later calls on the context see
+ * the uploaded arrays.  `host` arrays should be pinned (moloch_b200_host_alloc)
+ * for the two directions to overlap.  A non-zero return of `physics` aborts the
+ * hand-off with an error.                                                     */
+typedef struct {
+  int32_t field;                        /* MB_* id                                         */
+  int32_t n;                            /* species 1.. for the 4-D arrays, ignored otherwise */
+  double* host;                         /* host array (jlo:jhi, ilo:ihi, klo:khi), j fastest  */
+  int32_t jlo, jhi, ilo, ihi, klo, khi;
+} moloch_b200_xfer;
+typedef int (*moloch_b200_physics_fn)(void* user, int32_t i1, int32_t i2);
+int moloch_b200_handoff(moloch_b200_ctx* ctx, const moloch_b200_xfer* down, int ndown,
+                        const moloch_b200_xfer* up, int nup, int nslabs,
+                        moloch_b200_physics_fn physics, void* user);
+
 /* pinned host memory for the per-step state/tendency hand-off */
 int moloch_b200_host_alloc(void** p, uint64_t bytes);
 int moloch_b200_host_free(void* p);

@@ -415,6 +415,12 @@ int moloch_b200_destroy(moloch_b200_ctx* c) {
   if (c->spec_work) cudaFree(c->spec_work);
   if (c->mass_work) cudaFree(c->mass_work);
   if (c->stage) cudaFree(c->stage);
+  if (c->stage_down) cudaFree(c->stage_down);
+  if (c->stage_up) cudaFree(c->stage_up);
+  if (c->xs_down) cudaStreamDestroy(c->xs_down);
+  if (c->xs_up) cudaStreamDestroy(c->xs_up);
+  if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+  for (cudaEvent_t e : c->ev_slab) cudaEventDestroy(e);
   if (c->arena) cudaFree(c->arena);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -525,6 +531,155 @@ int moloch_b200_set_field(moloch_b200_ctx* c, int field, int n, const double* ho
 int moloch_b200_get_field(moloch_b200_ctx* c, int field, int n, double* host, int jlo, int jhi, int ilo,
                           int ihi, int klo, int khi) {
   return xfer_field(c, field, n, host, jlo, jhi, ilo, ihi, klo, khi, false);
+}
+
+// ---- pipelined physics hand-off ------------------------------------------------
+namespace {
+struct XferPlan {
+  double* dev; double* host;
+  int jlo, jhi, ilo, ihi, klo;     // host bounds
+  int ja, jb, ia, ib, ka, kb;      // part that exists on the device
+};
+int plan_xfer(moloch_b200_ctx* c, const moloch_b200_xfer& x, XferPlan& p, bool& empty) {
+  if (x.field < 0 || x.field >= MB_NFIELDS) return fail("handoff: unknown field id");
+  if (!x.host) return fail("handoff: null host pointer");
+  Ctx::Field& f = c->f[x.field];
+  if (!f.p) return fail("handoff: field not allocated in this configuration");
+  int spec = 0;
+  if (f.nspec > 1 || x.field == MB_QX || x.field == MB_TRAC || x.field == MB_QXTEN || x.field == MB_CHITEN) {
+    if (x.n < 1 || x.n > f.nspec) return fail("handoff: species index out of range");
+    spec = x.n - 1;
+  }
+  if (x.jhi < x.jlo || x.ihi < x.ilo || x.khi < x.klo) return fail("handoff: empty bounds");
+  const Geo& g = c->g;
+  p.dev = f.p + (size_t)spec * f.nk * g.plane;
+  p.host = x.host;
+  p.jlo = x.jlo; p.jhi = x.jhi; p.ilo = x.ilo; p.ihi = x.ihi; p.klo = x.klo;
+  p.ja = x.jlo > g.j0 ? x.jlo : g.j0; p.jb = x.jhi < g.j0 + g.NJ - 1 ? x.jhi : g.j0 + g.NJ - 1;
+  p.ia = x.ilo > g.i0 ? x.ilo : g.i0; p.ib = x.ihi < g.i0 + g.NI - 1 ? x.ihi : g.i0 + g.NI - 1;
+  p.ka = x.klo > 1 ? x.klo : 1; p.kb = x.khi < f.nk ? x.khi : f.nk;
+  empty = (p.jb < p.ja || p.ib < p.ia || p.kb < p.ka);
+  return 0;
+}
+// rows [i1, i2] of one array between its padded device box and its host array:
+// gather/scatter kernel <-> contiguous staging buffer (k, i, j) <-> one 2-D copy
+// whose "rows" are the nj*ni doubles a k-plane of the slab occupies on the host
+// (host rows wider than the device box: a 3-D copy of the row pieces instead).
+int slab_copy(moloch_b200_ctx* c, const XferPlan& p, int i1, int i2, bool to_device, cudaStream_t st, double* stage) {
+  const int ia = p.ia > i1 ? p.ia : i1, ib = p.ib < i2 ? p.ib : i2;
+  if (ib < ia) return 0;
+  const int nj = p.jb - p.ja + 1, ni = ib - ia + 1, nk = p.kb - p.ka + 1;
+  const size_t hrow = (size_t)(p.jhi - p.jlo + 1);                       // doubles per host row
+  const size_t hplane = hrow * (size_t)(p.ihi - p.ilo + 1);
+  double* h0 = p.host + (size_t)(p.ka - p.klo) * hplane + (size_t)(ia - p.ilo) * hrow + (size_t)(p.ja - p.jlo);
+  const bool full_rows = (p.ja == p.jlo && p.jb == p.jhi);
+  if (full_rows) {   // a k-plane of the slab is one contiguous run of nj*ni doubles on the host
+    const size_t run = (size_t)nj * ni * sizeof(double);
+    if (to_device) {
+      MB_CUDA(cudaMemcpy2DAsync(stage, run, h0, hplane * sizeof(double), run, (size_t)nk, cudaMemcpyHostToDevice, st));
+      if (k_box_copy(*c, p.dev, stage, p.ja, ia, p.ka, nj, ni, nk, false, st)) return 1;
+    } else {
+      if (k_box_copy(*c, p.dev, stage, p.ja, ia, p.ka, nj, ni, nk, true, st)) return 1;
+      MB_CUDA(cudaMemcpy2DAsync(h0, hplane * sizeof(double), stage, run, run, (size_t)nk, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+  }
+  cudaMemcpy3DParms q;
+  memset(&q, 0, sizeof(q));
+  cudaPitchedPtr hp = make_cudaPitchedPtr((void*)p.host, hrow * sizeof(double), hrow * sizeof(double),
+                                          (size_t)(p.ihi - p.ilo + 1));
+  cudaPitchedPtr sp = make_cudaPitchedPtr((void*)stage, (size_t)nj * sizeof(double), (size_t)nj * sizeof(double),
+                                          (size_t)ni);
+  cudaPos hpos = make_cudaPos((size_t)(p.ja - p.jlo) * sizeof(double), (size_t)(ia - p.ilo), (size_t)(p.ka - p.klo));
+  q.extent = make_cudaExtent((size_t)nj * sizeof(double), (size_t)ni, (size_t)nk);
+  if (to_device) {
+    q.srcPtr = hp; q.srcPos = hpos; q.dstPtr = sp; q.kind = cudaMemcpyHostToDevice;
+    MB_CUDA(cudaMemcpy3DAsync(&q, st));
+    if (k_box_copy(*c, p.dev, stage, p.ja, ia, p.ka, nj, ni, nk, false, st)) return 1;
+  } else {
+    if (k_box_copy(*c, p.dev, stage, p.ja, ia, p.ka, nj, ni, nk, true, st)) return 1;
+    q.srcPtr = sp; q.dstPtr = hp; q.dstPos = hpos; q.kind = cudaMemcpyDeviceToHost;
+    MB_CUDA(cudaMemcpy3DAsync(&q, st));
+  }
+  return 0;
+}
+}  // namespace
+
+int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int ndown, const moloch_b200_xfer* up,
+                        int nup, int nslabs, moloch_b200_physics_fn physics, void* user) {
+  if (!c) return fail("null context");
+  if (ndown < 0 || nup < 0 || (ndown > 0 && !down) || (nup > 0 && !up)) return fail("handoff: bad array lists");
+  if (nslabs < 1) nslabs = 1;
+  MB_CUDA(cudaSetDevice(c->device));
+  std::vector<XferPlan> pd, pu;
+  int I1 = 1 << 30, I2 = -(1 << 30);
+  size_t need = 0;
+  auto add = [&](const moloch_b200_xfer* xs, int n, std::vector<XferPlan>& out) -> int {
+    for (int q = 0; q < n; ++q) {
+      XferPlan p; bool empty = false;
+      if (plan_xfer(c, xs[q], p, empty)) return 1;
+      if (empty) continue;
+      out.push_back(p);
+      if (p.ia < I1) I1 = p.ia;
+      if (p.ib > I2) I2 = p.ib;
+    }
+    return 0;
+  };
+  if (add(down, ndown, pd) || add(up, nup, pu)) return 1;
+  if (pd.empty() && pu.empty()) return 0;
+  const int rows = I2 - I1 + 1;
+  if (nslabs > rows) nslabs = rows;
+  const int per = (rows + nslabs - 1) / nslabs;
+  nslabs = (rows + per - 1) / per;
+  for (const auto* v : {&pd, &pu})
+    for (const XferPlan& p : *v) {
+      const size_t n_el = (size_t)(p.jb - p.ja + 1) * (size_t)per * (size_t)(p.kb - p.ka + 1);
+      if (n_el > need) need = n_el;
+    }
+  // streams, events, staging (created on first use; regrown only when idle)
+  if (!c->xs_down) {
+    MB_CUDA(cudaStreamCreateWithFlags(&c->xs_down, cudaStreamNonBlocking));
+    MB_CUDA(cudaStreamCreateWithFlags(&c->xs_up, cudaStreamNonBlocking));
+    MB_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
+  }
+  while ((int)c->ev_slab.size() < nslabs) {
+    cudaEvent_t e;
+    MB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_slab.push_back(e);
+  }
+  if (need > c->stage_x_doubles) {
+    MB_CUDA(cudaStreamSynchronize(c->xs_down));
+    MB_CUDA(cudaStreamSynchronize(c->xs_up));
+    if (c->stage_down) cudaFree(c->stage_down);
+    if (c->stage_up) cudaFree(c->stage_up);
+    c->stage_down = c->stage_up = nullptr;
+    c->stage_x_doubles = need + need / 8;
+    MB_CUDA(cudaMalloc(&c->stage_down, c->stage_x_doubles * sizeof(double)));
+    MB_CUDA(cudaMalloc(&c->stage_up, c->stage_x_doubles * sizeof(double)));
+  }
+  // the copy streams start behind everything already enqueued on the context's stream
+  MB_CUDA(cudaEventRecord(c->ev_ready, c->stream));
+  MB_CUDA(cudaStreamWaitEvent(c->xs_down, c->ev_ready, 0));
+  MB_CUDA(cudaStreamWaitEvent(c->xs_up, c->ev_ready, 0));
+  for (int s = 0; s < nslabs; ++s) {
+    const int i1 = I1 + s * per, i2 = (i1 + per - 1 < I2) ? i1 + per - 1 : I2;
+    for (const XferPlan& p : pd)
+      if (slab_copy(c, p, i1, i2, false, c->xs_down, c->stage_down)) return 1;
+    MB_CUDA(cudaEventRecord(c->ev_slab[(size_t)s], c->xs_down));
+  }
+  int rc = 0;
+  for (int s = 0; s < nslabs && rc == 0; ++s) {
+    const int i1 = I1 + s * per, i2 = (i1 + per - 1 < I2) ? i1 + per - 1 : I2;
+    MB_CUDA(cudaEventSynchronize(c->ev_slab[(size_t)s]));     // slab s of the state is on the host
+    if (physics && physics(user, i1, i2) != 0) { rc = fail("handoff: the physics callback reported an error"); break; }
+    for (const XferPlan& p : pu)
+      if (slab_copy(c, p, i1, i2, true, c->xs_up, c->stage_up)) { rc = 1; break; }
+  }
+  // completion on return: host arrays may be reused, later work on the context's
+  // stream is enqueued after this point and therefore sees the uploaded slabs
+  MB_CUDA(cudaStreamSynchronize(c->xs_down));
+  MB_CUDA(cudaStreamSynchronize(c->xs_up));
+  return rc;
 }
 
 int moloch_b200_set_profile(moloch_b200_ctx* c, int which, const double* v, int n) {

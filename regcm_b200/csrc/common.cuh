@@ -110,6 +110,13 @@ struct Ctx {
   double* stage = nullptr;
   size_t stage_doubles = 0;
   bool async_xfer = false;
+  // pipelined physics hand-off (moloch_b200_handoff): one copy stream and one
+  // staging buffer per direction, one event per slab
+  cudaStream_t xs_down = nullptr, xs_up = nullptr;
+  cudaEvent_t ev_ready = nullptr;
+  std::vector<cudaEvent_t> ev_slab;
+  double *stage_down = nullptr, *stage_up = nullptr;
+  size_t stage_x_doubles = 0;
 };
 
 extern thread_local std::string g_err;
@@ -239,7 +246,8 @@ int k_tvirt_temp(Ctx& c);
 int k_diagnostics(Ctx& c);
 int k_status_update(Ctx& c, double dtinc);
 int k_init_static(Ctx& c);
-int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int nj, int ni, int nk, bool pack);
+int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int nj, int ni, int nk, bool pack,
+               cudaStream_t on = nullptr);   // on: another stream than the context's (hand-off copy streams)
 // kernels_bdy.cu
 int k_bdyval(Ctx& c, double xbctime);
 int k_bdy_relax(Ctx& c, double xbctime);

@@ -1090,10 +1090,16 @@ __global__ void moloch_box_copy(Geo g, double* __restrict__ dev, double* __restr
     if (pack) stage[t] = dev[d]; else dev[d] = stage[t];
   }
 }
-int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int nj, int ni, int nk, bool pack) {
-  LaunchScope ls(c, KID_BOX);
+int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int nj, int ni, int nk, bool pack,
+               cudaStream_t on) {
   dim3 grid((unsigned)((nj + BX - 1) / BX), (unsigned)((ni + BY - 1) / BY), (unsigned)(nk < 64 ? nk : 64));
-  moloch_box_copy<<<grid, dim3(BX, BY), 0, c.stream>>>(c.g, dev, stage, ja, ia, ka, nj, ni, nk, pack ? 1 : 0);
+  if (on) {   // a copy stream of the hand-off: the profiling events belong to the context's stream
+    c.launches++;
+    moloch_box_copy<<<grid, dim3(BX, BY), 0, on>>>(c.g, dev, stage, ja, ia, ka, nj, ni, nk, pack ? 1 : 0);
+  } else {
+    LaunchScope ls(c, KID_BOX);
+    moloch_box_copy<<<grid, dim3(BX, BY), 0, c.stream>>>(c.g, dev, stage, ja, ia, ka, nj, ni, nk, pack ? 1 : 0);
+  }
   MB_CUDA(cudaGetLastError());
   return 0;
 }

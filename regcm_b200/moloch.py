@@ -59,6 +59,7 @@ ABI_SYMBOLS = [
     "moloch_b200_set_table", "moloch_b200_set_ibnd", "moloch_b200_boundary", "moloch_b200_bdyval",
     "moloch_b200_set_xbctime", "moloch_b200_get_xbctime", "moloch_b200_bdy_shift", "moloch_b200_mkslice",
     "moloch_b200_massck", "moloch_b200_ps_check", "moloch_b200_set_calday", "moloch_b200_config_size",
+    "moloch_b200_handoff",
 ]
 
 
@@ -73,6 +74,15 @@ class Config(C.Structure):
         "ichebdy", "do_slice", "icldmstrat", "km", "lm", "do_massck")] + [
         (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin")] + [
         (n, C.c_int32) for n in ("irceideal", "idiag", "ichdiag", "reserved3")]
+
+
+class Xfer(C.Structure):
+    """moloch_b200_xfer (include/moloch_b200.h)."""
+    _fields_ = [("field", C.c_int32), ("n", C.c_int32), ("host", C.c_void_p)] + [
+        (n, C.c_int32) for n in ("jlo", "jhi", "ilo", "ihi", "klo", "khi")]
+
+
+PHYSICS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32)
 
 
 class MolochError(RuntimeError):
@@ -116,6 +126,8 @@ def bind_library(lib, path: str = "?"):
     lib.moloch_b200_set_field.argtypes = xf
     lib.moloch_b200_get_field.argtypes = xf
     lib.moloch_b200_set_profile.argtypes = [ctx, C.c_int, C.c_void_p, C.c_int]
+    lib.moloch_b200_handoff.argtypes = [ctx, C.POINTER(Xfer), C.c_int, C.POINTER(Xfer), C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]
     lib.moloch_b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     lib.moloch_b200_host_free.argtypes = [C.c_void_p]
     lib.moloch_b200_set_table.argtypes = [ctx, C.c_int, C.c_void_p, C.c_int]
@@ -334,6 +346,29 @@ class MolochB200:
     def set_async(self, on: bool):
         """Batch mode for set_local/get_local: transfers are only enqueued; end with sync()."""
         self._chk(self.lib.moloch_b200_set_async(self.ctx, int(on)))
+
+    def xfer_list(self, items):
+        """items: (name, species_or_0, array, box) -> a ctypes array of moloch_b200_xfer.  `array` is the
+        host array of one species/field, (nk, ni, nj) C-contiguous float64 with Fortran bounds `box`."""
+        arr = (Xfer * max(len(items), 1))()
+        for q, (name, n, a, box) in enumerate(items):
+            if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"{name}: the hand-off needs C-contiguous float64 host arrays")
+            nk = self._levels(name)
+            jlo, jhi, ilo, ihi = box
+            if a.size != nk * (ihi - ilo + 1) * (jhi - jlo + 1):
+                raise ValueError(f"{name}: shape {a.shape} does not match bounds {box} x {nk} levels")
+            arr[q] = Xfer(FIELD_ID[name], int(n), a.ctypes.data, jlo, jhi, ilo, ihi, 1, nk)
+        return arr, len(items)
+
+    def handoff(self, down, up, nslabs: int = 8, physics=None):
+        """The pipelined physics hand-off (moloch_b200_handoff): `down`/`up` are xfer_list() results;
+        `physics(i1, i2)` is called on the host for each slab of rows once its state has arrived."""
+        cb = None
+        if physics is not None:
+            cb = PHYSICS_FN(lambda user, i1, i2: int(physics(int(i1), int(i2)) or 0))
+        self._chk(self.lib.moloch_b200_handoff(self.ctx, down[0], down[1], up[0], up[1], int(nslabs),
+                                               C.cast(cb, C.c_void_p) if cb is not None else None, None))
 
     def set_stream(self, cuda_stream: int):
         self._chk(self.lib.moloch_b200_set_stream(self.ctx, C.c_void_p(cuda_stream)))

@@ -304,6 +304,12 @@ cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cu
   memmove(d, s, n);
   return cudaSuccess;
 }
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind,
+                              cudaStream_t) {
+  if (w > dp || w > sp) return cudaErrorInvalidValue;
+  for (size_t y = 0; y < h; ++y) memcpy((char*)d + y * dp, (const char*)s + y * sp, w);
+  return cudaSuccess;
+}
 cudaError_t cudaMemcpy3D(const cudaMemcpy3DParms* p) {
   const cudaPitchedPtr &sp = p->srcPtr, &dp = p->dstPtr;
   for (size_t z = 0; z < p->extent.depth; ++z)
@@ -321,6 +327,8 @@ cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent{0}; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = emu::clock_now(); return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

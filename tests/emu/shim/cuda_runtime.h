@@ -148,7 +148,7 @@ enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1
 typedef struct emuStream* cudaStream_t;
 typedef struct emuEvent* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum { cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaIpcMemLazyEnablePeerAccess = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaIpcMemHandle_t { char reserved[64]; };
 struct cudaPitchedPtr { void* ptr; size_t pitch, xsize, ysize; };
@@ -176,6 +176,7 @@ cudaError_t cudaMemset(void*, int, size_t);
 cudaError_t cudaMemsetAsync(void*, int, size_t, cudaStream_t = nullptr);
 cudaError_t cudaMemcpy(void*, const void*, size_t, cudaMemcpyKind);
 cudaError_t cudaMemcpyAsync(void*, const void*, size_t, cudaMemcpyKind, cudaStream_t = nullptr);
+cudaError_t cudaMemcpy2DAsync(void*, size_t, const void*, size_t, size_t, size_t, cudaMemcpyKind, cudaStream_t = nullptr);
 cudaError_t cudaMemcpy3D(const cudaMemcpy3DParms*);
 cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms*, cudaStream_t = nullptr);
 cudaError_t cudaStreamCreate(cudaStream_t*);
@@ -184,6 +185,8 @@ cudaError_t cudaStreamDestroy(cudaStream_t);
 cudaError_t cudaStreamSynchronize(cudaStream_t);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaEventCreate(cudaEvent_t*);
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t*, unsigned);
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0);
 cudaError_t cudaEventDestroy(cudaEvent_t);
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t);

@@ -136,3 +136,38 @@ def test_decomposed(name, wl, px, py, transport, monkeypatch):
 @pytest.mark.parametrize("px,py", [(2, 1), (1, 2), (2, 2)] if FULL else [(2, 2)])
 def test_decomposed_boundary(px, py):
     _gpu_tests()[2].test_decomposed_boundary_bit_exact(px, py)
+
+
+@pytest.mark.parametrize("nslabs", [1, 3, 1000])
+def test_handoff(nslabs):
+    import test_gpu_zz_handoff as Hf
+    Hf.test_handoff_matches_field_transfers(nslabs)
+
+
+def test_handoff_bad_arguments():
+    import test_gpu_zz_handoff as Hf
+    Hf.test_handoff_rejects_bad_arguments()
+
+
+def test_bench_e2e_path(_emulated_library):
+    """bench.py's end-to-end leg (measure_e2e: pipelined hand-off with its self-check) on the emulated library:
+    it must choose the pipelined path, and K of its steps with zero tendencies equal K moloch() steps."""
+    import numpy as np
+    import bench
+    from regcm_b200 import synthetic as S
+    from regcm_b200.moloch import MolochB200
+    wl = S.small(S.WORKLOADS["cordex25"], 40, 36, 9, ntr=2, nspgx=5)
+    ms = []
+    for _ in range(2):
+        m = MolochB200(wl, lib=_emulated_library).allocate_moloch()
+        fields, profiles, boxes = S.model_inputs_local(wl, m.g)
+        m.init_moloch(fields, profiles, boxes)
+        ms.append(m)
+    r = bench.measure_e2e(ms[0], wl, 1)
+    assert r["handoff"] == "pipelined" and r["handoff_note"] is None, r
+    assert r["d2h_bytes_per_step"] > 0 and r["h2d_bytes_per_step"] > 0
+    ms[1].moloch(3)      # self-check step + warm-up step + 1 timed step
+    for f in ("u", "v", "w", "pai", "t", "qx", "trac"):
+        assert np.array_equal(ms[0].get_global(f), ms[1].get_global(f)), f
+    for m in ms:
+        m.close()

@@ -77,7 +77,9 @@ typedef struct {
   int32_t irceideal;                  /* 1: mkslice keeps ptrop as it is (Main/mod_slice.F90:345) */
   int32_t idiag, ichdiag;             /* > 0: tendency diagnostics of dynamical_core and boundary
                                          (Main/mod_moloch.F90:1092-1103,1127-1139,455-466,508-519) */
-  int32_t reserved3;
+  int32_t niycpus;                    /* cpus_per_dim(2), ranks along i (rank = locj*niycpus + loci,
+                                         Main/mpplib/mod_mppparam.F90:1381-1462); needed only for
+                                         mo_spectral_nudge on more than one rank (row/column reductions) */
 } moloch_b200_config;
 
 typedef struct moloch_b200_ctx moloch_b200_ctx;

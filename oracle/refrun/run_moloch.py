@@ -321,6 +321,19 @@ class ReferenceRun:
             ns["mpi_neighbor_alltoallv"] = lambda sd, sc, sdis, st, rd, rc, rdis, rt, cm, err: \
                 comm.neighbor_alltoallv(rank, nbrs, sd, sc, sdis, rd)
             ns.update(mpi_real8=0, cartesian_communicator=0, mpierr=0, mpi_success=0)
+            if wl.do_bdy and wl.mo_spectral_nudge:
+                # the reference's own row_reduce / column_reduce (Main/mpplib/mod_mppparam.F90:20618-20664) on an
+                # emulated mpi_allreduce over the row / column communicators (:1459-1469: row colour = loci,
+                # column colour = locj); MPI leaves the order of the sum open -- rank order here
+                for n in ("real8_row_reduce", "real8_column_reduce"):
+                    exec(F.compile_source(tr0.routine(mr[n]), f"<mod_mppparam.F90:{n}>"), ns)
+                ns["size"] = lambda m, d: int(m.a.shape[m.a.ndim - d])
+                ns.update(mpi_sum=0, cartesian_row_communicator="row", cartesian_column_communicator="col")
+                groups = {"row": [q for q in range(px * py) if q % py == rank % py],
+                          "col": [q for q in range(px * py) if q // py == rank // py]}
+                ns["mpi_allreduce"] = lambda m, gl_, count, ty, op, cm, err: comm.allreduce(rank, groups[cm], m, gl_, count)
+                ns["row_reduce"] = ns["real8_row_reduce"]
+                ns["column_reduce"] = ns["real8_column_reduce"]
             ns["exchange_lr"] = ns["real8_3d_exchange_left_right"]
             ns["exchange_bt"] = ns["real8_3d_exchange_bottom_top"]
             ns["exchange_lrbt"] = ns["real8_3d_exchange_left_right_bottom_top"]
@@ -774,6 +787,20 @@ class _Comm:
                 c, o = int(counts.a[d]), int(displs.a[d])
                 rdata.a[o:o + c] = self.box[(nbrs[d], opp[d])]
         self.bar.wait()
+
+
+def _comm_allreduce(self, rank, group, m, gl_, count):
+    """mpi_allreduce(SUM) of the first `count` elements of the contiguous arrays, added in rank order."""
+    self.box[("red", rank)] = m.a.reshape(-1)[:count].copy()
+    self.bar.wait()
+    acc = None
+    for q in group:
+        acc = self.box[("red", q)].copy() if acc is None else acc + self.box[("red", q)]
+    gl_.a.reshape(-1)[:count] = acc
+    self.bar.wait()
+
+
+_Comm.allreduce = _comm_allreduce
 
 
 class MultiRankReference:

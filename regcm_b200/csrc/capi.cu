@@ -94,9 +94,9 @@ static int check_cfg(const moloch_b200_config& f) {
     if (f.mo_spectral_nudge) {
       if (!(f.dtrad > 0.0) || f.km < 1 || f.lm < 1)
         return fail("moloch_b200_create: mo_spectral_nudge needs dtrad > 0 and km, lm >= 1");
-      if (f.nranks > 1)
-        return fail("moloch_b200_create: mo_spectral_nudge on more than one rank is not supported yet "
-                    "(row_reduce/column_reduce, Main/mpplib/mod_mppparam.F90:20620-20664)");
+      if (f.nranks > 1 && (f.niycpus < 1 || f.nranks % f.niycpus != 0))
+        return fail("moloch_b200_create: mo_spectral_nudge on more than one rank needs niycpus (cpus_per_dim(2)) "
+                    "for row_reduce/column_reduce (Main/mpplib/mod_mppparam.F90:20618-20664)");
     }
   }
   if (f.do_slice && !(f.rhmax >= f.rhmin)) return fail("moloch_b200_create: do_slice needs rhmin <= rhmax");

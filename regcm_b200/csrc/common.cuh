@@ -88,6 +88,8 @@ struct Ctx {
   void* nccl_comm = nullptr;
   double *sendbuf = nullptr, *recvbuf = nullptr;
   size_t halo_buf_doubles = 0;
+  double* gather_buf = nullptr;          // row/column reductions: the other members' partial sums
+  size_t gather_doubles = 0;
   // profiling
   bool profiling = false;
   std::vector<ProfEvent> events;
@@ -276,6 +278,9 @@ int halo_fence(Ctx& c);
 bool halo_fused_available(const Ctx& c);
 int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc);
 int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep);
+// row_reduce / column_reduce (Main/mpplib/mod_mppparam.F90:20618-20664): in-place sum of `count` doubles
+// over the ranks `members` (ascending, this rank included), added in rank order on every member
+int halo_group_sum(Ctx& c, double* data, size_t count, const int* members, int nmem);
 int halo_comm_init(Ctx& c, const void* id128);
 int halo_comm_id(void* id128);
 int halo_p2p_export(Ctx& c, void* blob);

@@ -145,6 +145,56 @@ static int nccl_load() {
     if (r__ != ncclSuccess) return fail(std::string(#call) + ": " + g_nccl.GetErrorString(r__)); \
   } while (0)
 
+// ---- row_reduce / column_reduce ------------------------------------------------------
+// MPI_Allreduce(SUM) over a row or column of ranks (cartesian_row/_column_communicator,
+// Main/mpplib/mod_mppparam.F90:1459-1469, 20618-20664) as an all-gather of the partial
+// sums over NCCL (grouped send/recv between the members) followed by one kernel that adds
+// them in rank order on every member: deterministic and identical on all of them.
+__global__ void moloch_ordered_sum(double* __restrict__ data, const double* __restrict__ others, long long count,
+                                   int nmem, int mypos) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count;
+       e += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    int slot = 0;
+    for (int b = 0; b < nmem; ++b) {
+      const double v = (b == mypos) ? data[e] : others[(long long)(slot++) * count + e];
+      acc = (b == 0) ? v : acc + v;
+    }
+    data[e] = acc;
+  }
+}
+int halo_group_sum(Ctx& c, double* data, size_t count, const int* members, int nmem) {
+  if (nmem <= 1 || count == 0) return 0;
+  if (!c.nccl_comm)
+    return fail("row/column reduction on more than one rank needs the NCCL communicator (moloch_b200_comm_init)");
+  int mypos = -1;
+  for (int b = 0; b < nmem; ++b) if (members[b] == c.cfg.rank) mypos = b;
+  if (mypos < 0) return fail("halo_group_sum: this rank is not a member of the group");
+  const size_t need = (size_t)(nmem - 1) * count;
+  if (need > c.gather_doubles) {
+    MB_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.gather_buf) cudaFree(c.gather_buf);
+    c.gather_buf = nullptr;
+    MB_CUDA(cudaMalloc(&c.gather_buf, need * sizeof(double)));
+    c.gather_doubles = need;
+  }
+  ncclComm_t comm = (ncclComm_t)c.nccl_comm;
+  MB_NCCL(g_nccl.GroupStart());
+  int slot = 0;
+  for (int b = 0; b < nmem; ++b) {
+    if (b == mypos) continue;
+    MB_NCCL(g_nccl.Send(data, count, ncclDouble, members[b], comm, c.stream));
+    MB_NCCL(g_nccl.Recv(c.gather_buf + (size_t)(slot++) * count, count, ncclDouble, members[b], comm, c.stream));
+  }
+  MB_NCCL(g_nccl.GroupEnd());
+  LaunchScope ls(c, KID_SPECTRAL);
+  const long long nb = ((long long)count + 255) / 256;
+  moloch_ordered_sum<<<(unsigned)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, c.stream>>>(data, c.gather_buf, (long long)count,
+                                                                                     nmem, mypos);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int halo_comm_id(void* id128) {
   if (nccl_load()) return 1;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
@@ -174,6 +224,8 @@ void halo_free(Ctx& c) {
   if (c.sendbuf) cudaFree(c.sendbuf);
   if (c.recvbuf) cudaFree(c.recvbuf);
   c.sendbuf = c.recvbuf = nullptr;
+  if (c.gather_buf) cudaFree(c.gather_buf);
+  c.gather_buf = nullptr; c.gather_doubles = 0;
 }
 
 static int launch_halo(Ctx& c, int mode, const HaloParams& h, double* buf, long long tot) {

@@ -7,6 +7,7 @@
 // onto cells: 32 consecutive j per warp row (coalesced 256-B rows), one level
 // per blockIdx.z.  Compiled -fmad=false like the rest of the library.
 #include <cstring>
+#include <vector>
 #include "bdy_cells.h"
 #include "common.cuh"
 
@@ -338,9 +339,14 @@ int k_ibnd_fill(Ctx& c, int* dst, const int* src, int jlo, int jhi, int ilo, int
   return 0;
 }
 
-// ---- mospectral_nudge (single rank) ------------------------------------------------------
+// ---- mospectral_nudge ---------------------------------------------------------------------
 // Six small launches per variable (t, u, v); every level is handled in parallel,
 // every sum keeps the reference's order (bdy_cells.h).  Runs every dtrad only.
+// On more than one rank row_reduce / column_reduce (MPI_Allreduce over the ranks
+// with the same loci / locj, Main/mpplib/mod_mppparam.F90:1459-1469, 20618-20664)
+// become halo_group_sum: the partial sums of all levels in one all-gather over
+// NCCL, added in rank order (MPI leaves the order open; rank order is what the
+// oracle's emulation uses, so the decomposed run equals it bit for bit).
 __global__ void moloch_spec_zn(SpecArgs a) {
   const int j = a.j1 + blockIdx.x * BX + threadIdx.x, i = a.i1 + blockIdx.y * BY + threadIdx.y;
   if (j > a.j2 || i > a.i2) return;
@@ -379,6 +385,14 @@ int k_spectral_nudge(Ctx& c, double xbctime) {
     MB_CUDA(cudaMemsetAsync(c.spec_work, 0, need * sizeof(double), c.stream));
     c.spec_work_doubles = need;
   }
+  // ranks of this rank's row (same loci) and column (same locj); rank = locj*niycpus + loci
+  std::vector<int> rowm, colm;
+  if (c.cfg.nranks > 1) {
+    const int py = c.cfg.niycpus, px = c.cfg.nranks / py;
+    const int locj = c.cfg.rank / py, loci = c.cfg.rank % py;
+    for (int q = 0; q < px; ++q) rowm.push_back(q * py + loci);
+    for (int q = 0; q < py; ++q) colm.push_back(locj * py + q);
+  }
   SpecArgs a;
   memset(&a, 0, sizeof(a));
   a.g = g;
@@ -405,6 +419,7 @@ int k_spectral_nudge(Ctx& c, double xbctime) {
       moloch_spec_sx<<<dim3((unsigned)((nbi + 63) / 64), (unsigned)km2, (unsigned)kz), 64, 0, c.stream>>>(a);
       MB_CUDA(cudaGetLastError());
     }
+    if (rowm.size() > 1 && halo_group_sum(c, a.sx, nsx, rowm.data(), (int)rowm.size())) return 1;   // row_reduce
     if (a.count_x == km2 * ni)   // a full-length reduction: this is what later short calls find in the tail of sxg
       MB_CUDA(cudaMemcpyAsync(sx_stale, a.sx + (size_t)(kz - 1) * km2 * ni, (size_t)km2 * ni * sizeof(double),
                               cudaMemcpyDeviceToDevice, c.stream));
@@ -418,6 +433,7 @@ int k_spectral_nudge(Ctx& c, double xbctime) {
       moloch_spec_sy<<<dim3((unsigned)((nbj + 63) / 64), (unsigned)lm2, (unsigned)kz), 64, 0, c.stream>>>(a);
       MB_CUDA(cudaGetLastError());
     }
+    if (colm.size() > 1 && halo_group_sum(c, a.sy, nsy, colm.data(), (int)colm.size())) return 1;   // column_reduce
     if (a.count_y == lm2 * nj)
       MB_CUDA(cudaMemcpyAsync(sy_stale, a.sy + (size_t)(kz - 1) * lm2 * nj, (size_t)lm2 * nj * sizeof(double),
                               cudaMemcpyDeviceToDevice, c.stream));

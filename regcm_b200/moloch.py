@@ -73,7 +73,7 @@ class Config(C.Structure):
         "do_bdy", "nspgx", "present_qc", "present_qi", "mo_top_nudge", "mo_spectral_nudge", "nztop", "ichem",
         "ichebdy", "do_slice", "icldmstrat", "km", "lm", "do_massck")] + [
         (n, C.c_double) for n in ("dtbdys", "dtrad", "rhmin", "rhmax", "tkemin")] + [
-        (n, C.c_int32) for n in ("irceideal", "idiag", "ichdiag", "reserved3")]
+        (n, C.c_int32) for n in ("irceideal", "idiag", "ichdiag", "niycpus")]
 
 
 class Xfer(C.Structure):
@@ -176,7 +176,7 @@ def make_config(wl, g: Geom, device: int = -1, mo_dzita: float | None = None, bd
                   km=int(bdy.get("km", 0)), lm=int(bdy.get("lm", 0)), do_massck=int(getattr(wl, "do_massck", 0)), dtbdys=wl.dtbdys,
                   dtrad=wl.dtrad, rhmin=wl.rhmin, rhmax=wl.rhmax, tkemin=wl.tkemin,
                   irceideal=int(getattr(wl, "irceideal", 0)), idiag=int(getattr(wl, "idiag", 0)),
-                  ichdiag=int(getattr(wl, "ichdiag", 0)), reserved3=0)
+                  ichdiag=int(getattr(wl, "ichdiag", 0)), niycpus=g.py)
 
 
 def halo_plan(cfg: Config, stag: int, nex: int, lr: bool, bt: bool):

@@ -14,10 +14,12 @@ import util
 
 
 class MultiRank:
-    def __init__(self, wl, px, py, fields, profiles, devices=None, transport="p2p", bdy=None, boundary=None):
+    def __init__(self, wl, px, py, fields, profiles, devices=None, transport="p2p", bdy=None, boundary=None, xbctime=None):
         self.wl, self.n = wl, px * py
         devices = devices or list(range(self.n))
-        uid = MolochB200.comm_id(util.LIB) if (self.n > 1 and transport == "nccl") else None
+        # transport: "p2p" (peer stores), "nccl", or "p2p+nccl" (peer-store halos, NCCL for the row/column
+        # reductions of the spectral nudging)
+        uid = MolochB200.comm_id(util.LIB) if (self.n > 1 and "nccl" in transport) else None
         self.ranks = [None] * self.n
         blobs = [None] * self.n
         bar = threading.Barrier(self.n)
@@ -28,18 +30,20 @@ class MultiRank:
                 m = MolochB200(wl, rank=r, nranks=self.n, px=px, py=py, device=devices[r], bdy=bdy,
                                lib=util.LIB).allocate_moloch()
                 self.ranks[r] = m
-                if self.n > 1 and transport == "p2p":
+                if self.n > 1 and "p2p" in transport:
                     blobs[r] = m.p2p_export()
                 bar.wait(timeout=120)
                 if self.n > 1:
-                    if transport == "nccl":
+                    if "nccl" in transport:
                         m.comm_init(uid)
-                    else:
+                    if "p2p" in transport:
                         m.p2p_connect(blobs)
                 bar.wait(timeout=120)
                 m.init_moloch(fields, profiles)
                 if boundary is not None:
                     m.load_boundary(boundary)
+                    if xbctime is not None:
+                        m.set_xbctime(xbctime)
                 if wl.do_slice:
                     m.set_calday(wl.calday, wl.dayspy)
             except Exception as e:  # noqa: BLE001

@@ -171,3 +171,14 @@ def test_bench_e2e_path(_emulated_library):
         assert np.array_equal(ms[0].get_global(f), ms[1].get_global(f)), f
     for m in ms:
         m.close()
+
+
+@pytest.mark.parametrize("px,py,transport", [(2, 1, "nccl"), (1, 2, "p2p+nccl"), (2, 2, "p2p+nccl"), (2, 4, "nccl")]
+                         if FULL else [(2, 2, "p2p+nccl"), (2, 1, "nccl")])
+def test_decomposed_spectral_nudging(px, py, transport):
+    """row_reduce / column_reduce (all-gather over the NCCL stand-in + rank-ordered sum) == the decomposed oracle."""
+    _gpu_tests()[2].test_decomposed_spectral_nudging_bit_exact(px, py, transport)
+
+
+def test_spectral_nudging_needs_nccl():
+    _gpu_tests()[2].test_spectral_nudging_needs_nccl_for_reductions()

@@ -91,3 +91,44 @@ def test_decomposed_boundary_bit_exact(px, py):
             assert (np.abs(a - b) <= 1e-13 * np.abs(a)).all(), f
     finally:
         mr.close()
+
+
+SPEC = S.small(S.WORKLOADS["cordex25"], 48, 40, 8, ntr=2, nspgx=6, do_bdy=1, present_qc=1, present_qi=1, mo_top_nudge=1,
+               ichebdy=1, mo_spectral_nudge=1, ds_km=100.0, dtrad=150.0, dt=150.0)
+
+
+@pytest.mark.parametrize("px,py,transport", [(2, 1, "nccl"), (1, 2, "p2p+nccl"), (2, 2, "p2p+nccl"), (2, 4, "nccl")])
+def test_decomposed_spectral_nudging_bit_exact(px, py, transport):
+    """mospectral_nudge on px x py ranks: row_reduce / column_reduce as an all-gather over NCCL with the partial
+    sums added in rank order -- what the oracle's emulation of the two MPI_Allreduce calls does, so the
+    decomposed CUDA run equals the equally decomposed oracle bit for bit (a different decomposition differs
+    in the last bits: the reductions are the one place where the dycore's result depends on it)."""
+    if ndev() < px * py:
+        pytest.skip(f"needs {px * py} GPUs")
+    wl = SPEC
+    o, B = make_oracle_bdy(wl, px=px, py=py)
+    fields, profiles = oracle_inputs(o, wl)
+    mr = MultiRank(wl, px, py, fields, profiles, transport=transport, bdy=bdy_tables_from_oracle(wl, o), boundary=B,
+                   xbctime=o.get_xbctime())
+    try:
+        o.step(3)
+        mr.call("moloch", 3)
+        bad = [f for f in PROGNOSTIC + ["trac"] if not np.array_equal(o.get(f), mr.get_global(f))]
+        assert not bad, bad
+    finally:
+        mr.close()
+
+
+def test_spectral_nudging_needs_nccl_for_reductions():
+    if ndev() < 2:
+        pytest.skip("needs 2 GPUs")
+    wl = SPEC
+    o, B = make_oracle_bdy(wl, px=2, py=1)
+    fields, profiles = oracle_inputs(o, wl)
+    mr = MultiRank(wl, 2, 1, fields, profiles, transport="p2p", bdy=bdy_tables_from_oracle(wl, o), boundary=B,
+                   xbctime=o.get_xbctime())
+    try:
+        with pytest.raises(RuntimeError, match="needs the NCCL communicator"):
+            mr.call("moloch", 1)
+    finally:
+        mr.close()

@@ -127,6 +127,25 @@ def test_reference_multirank_matches_oracle(case, px, py):
 
 
 @pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+@pytest.mark.parametrize("px,py", [(2, 2), (3, 1)])
+def test_reference_multirank_spectral_nudging_matches_decomposed_oracle(px, py):
+    """mospectral_nudge on px x py ranks with the reference's OWN row_reduce / column_reduce
+    (Main/mpplib/mod_mppparam.F90:20618-20664) executed on an emulated mpi_allreduce over the row / column
+    communicators, sums in rank order: equal to the equally decomposed oracle bit for bit.  Pins the
+    `count = nk*(i2-i1+1)` semantics of the two reductions across ranks (incl. the stale tails on the top row
+    of ranks), which the CUDA library's halo_group_sum restates."""
+    wl, nsteps = CASES["limited_area_spectral"]
+    o, B = make_oracle_bdy(wl, px=px, py=py)
+    # the reference ranks take their inputs -- incl. cnudge/tnudge, whose global means (sumall) depend on the
+    # decomposition in the last bits -- from the equally decomposed oracle
+    mr = R.MultiRankReference(wl, o, B, px, py)
+    mr.step(nsteps)
+    o.step(nsteps)
+    bad = [f for f in R.case_fields(wl) if not np.array_equal(mr.get(f), o.get(f))]
+    assert not bad, bad
+
+
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
 def test_reference_runs_use_the_reference_allocation():
     """The arrays of a ReferenceRun have exactly the bounds allocate_atmosphere
     (Main/mod_atm_interface.F90:579-624) and allocate_moloch (Main/mod_moloch.F90:159-199) give when THEY are

@@ -210,6 +210,10 @@ int moloch_b200_handoff(moloch_b200_ctx* ctx, const moloch_b200_xfer* down, int 
 /* pinned host memory for the per-step state/tendency hand-off */
 int moloch_b200_host_alloc(void** p, uint64_t bytes);
 int moloch_b200_host_free(void* p);
+/* page-lock an array the host already owns (RegCM's getmem pools), so that the
+ * hand-off copies run asynchronously at full link rate (cudaHostRegister)       */
+int moloch_b200_host_register(void* p, uint64_t bytes);
+int moloch_b200_host_unregister(void* p);
 
 /* = the device part of init_moloch (Main/mod_moloch.F90:263-308): mx2, rmx,
  * rmu, rmv and their halos, w(:,:,1)=0, clamp limits, dtstepa/dtsound.  Call

@@ -713,6 +713,16 @@ int moloch_b200_host_free(void* p) {
   return 0;
 }
 
+int moloch_b200_host_register(void* p, uint64_t bytes) {
+  if (!p || bytes == 0) return fail("host_register: null argument");
+  MB_CUDA(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+  return 0;
+}
+int moloch_b200_host_unregister(void* p) {
+  if (p) MB_CUDA(cudaHostUnregister(p));
+  return 0;
+}
+
 int moloch_b200_init(moloch_b200_ctx* c) {
   if (!c) return fail("null context");
   for (int q : {MB_GZITAK, MB_GZITAKH, MB_FFILT, MB_XKDAMP, MB_XKNU})

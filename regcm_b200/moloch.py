@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "moloch_b200_set_table", "moloch_b200_set_ibnd", "moloch_b200_boundary", "moloch_b200_bdyval",
     "moloch_b200_set_xbctime", "moloch_b200_get_xbctime", "moloch_b200_bdy_shift", "moloch_b200_mkslice",
     "moloch_b200_massck", "moloch_b200_ps_check", "moloch_b200_set_calday", "moloch_b200_config_size",
-    "moloch_b200_handoff",
+    "moloch_b200_handoff", "moloch_b200_host_register", "moloch_b200_host_unregister",
 ]
 
 
@@ -130,6 +130,8 @@ def bind_library(lib, path: str = "?"):
                                         C.c_void_p, C.c_void_p]
     lib.moloch_b200_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     lib.moloch_b200_host_free.argtypes = [C.c_void_p]
+    lib.moloch_b200_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    lib.moloch_b200_host_unregister.argtypes = [C.c_void_p]
     lib.moloch_b200_set_table.argtypes = [ctx, C.c_int, C.c_void_p, C.c_int]
     lib.moloch_b200_set_ibnd.argtypes = [ctx, C.c_int, C.c_void_p] + [C.c_int] * 4
     lib.moloch_b200_set_calday.argtypes = [ctx, C.c_double, C.c_double]
@@ -213,6 +215,7 @@ class MolochB200:
         self.cfg = make_config(wl, self.g, device, bdy=bdy)
         self.ctx = C.c_void_p()
         self._pinned = []
+        self._registered = []
 
     # ---- error convention: non-zero -> fatal(__FILE__,__LINE__,msg) ---------
     def _chk(self, rc):
@@ -446,6 +449,11 @@ class MolochB200:
         buf = (C.c_double * n).from_address(p.value)
         return np.frombuffer(buf, dtype=np.float64).reshape(shape)
 
+    def host_register(self, a: np.ndarray):
+        """Page-lock a host array the caller owns (until host_unregister / close)."""
+        self._chk(self.lib.moloch_b200_host_register(C.c_void_p(a.ctypes.data), a.nbytes))
+        self._registered.append(a)
+
     # ---- instrumentation ---------------------------------------------------------
     def profile_enable(self, on: bool = True):
         self._chk(self.lib.moloch_b200_profile_enable(self.ctx, int(on)))
@@ -473,6 +481,9 @@ class MolochB200:
         for p in self._pinned:
             self.lib.moloch_b200_host_free(p)
         self._pinned = []
+        for a in self._registered:
+            self.lib.moloch_b200_host_unregister(C.c_void_p(a.ctypes.data))
+        self._registered = []
 
     def __del__(self):
         try:

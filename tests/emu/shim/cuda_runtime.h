@@ -172,6 +172,9 @@ template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaM
 cudaError_t cudaFree(void*);
 cudaError_t cudaHostAlloc(void**, size_t, unsigned);
 cudaError_t cudaFreeHost(void*);
+enum { cudaHostRegisterDefault = 0 };
+inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 cudaError_t cudaMemset(void*, int, size_t);
 cudaError_t cudaMemsetAsync(void*, int, size_t, cudaStream_t = nullptr);
 cudaError_t cudaMemcpy(void*, const void*, size_t, cudaMemcpyKind);

@@ -45,7 +45,12 @@ def test_handoff_matches_field_transfers(nslabs):
     for n in ["tten", "uten", "vten", "qxten", "chiten"]:
         box = H.bounds(g, n)
         for s in range(1, species(n) + 1) if species(n) else [0]:
-            a = m.pinned_empty((m._levels(n), box[3] - box[2] + 1, box[1] - box[0] + 1))
+            shp = (m._levels(n), box[3] - box[2] + 1, box[1] - box[0] + 1)
+            if n == "uten":     # an array the host already owns, page-locked in place
+                a = np.zeros(shp)
+                m.host_register(a)
+            else:
+                a = m.pinned_empty(shp)
             a[...] = rng.standard_normal(a.shape) * 1e-4
             up_items.append((n, s, a, box))
     seen = []

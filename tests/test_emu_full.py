@@ -182,3 +182,8 @@ def test_decomposed_spectral_nudging(px, py, transport):
 
 def test_spectral_nudging_needs_nccl():
     _gpu_tests()[2].test_spectral_nudging_needs_nccl_for_reductions()
+
+
+def test_restart_from_the_save_set():
+    import test_gpu_zz_handoff as Hf
+    Hf.test_restart_from_the_save_set_is_bit_exact()

@@ -102,3 +102,54 @@ def test_handoff_rejects_bad_arguments():
     with pytest.raises(MolochError, match="physics callback"):
         m.handoff(m.xfer_list([("t", 0, a, box)]), m.xfer_list([]), physics=lambda i1, i2: 1)
     m.close()
+
+
+def test_restart_from_the_save_set_is_bit_exact():
+    """the MOLOCH restart contract (Main/mod_savefile.F90:232-242, 618-627: atm_u, atm_v, atm_w,
+    atm_t, atm_pai, atm_qx, trac, ps).  Two steps, the save set staged to the host in one asynchronous batch,
+    a NEW context initialised from it the way `init` does on a restart (Main/mod_init.F90:420-449 copies the
+    save set, :941-953 rebuilds p, qs, rho, tvirt, tetav; ux, vx follow from u, v in `advection`), two more
+    steps: every prognostic field equals the uninterrupted four-step run bit for bit."""
+    from regcm_b200 import hostmodel as H
+    from regcm_b200.moloch import STATE_FIELDS, STATIC_FIELDS
+    from util import PROGNOSTIC
+    wl = CASES["limited_area"]
+    o, _ = make_oracle(wl)
+    fields, profiles = oracle_inputs(o, wl)
+    ref = make_gpu(wl, fields, profiles)
+    ref.moloch(4)
+    m = make_gpu(wl, fields, profiles)
+    m.moloch(2)
+    save = {}
+    m.set_async(True)                      # selective D2H at alarm_out_sav: enqueue everything, one sync
+    for n in ("u", "v", "w", "t", "pai", "qx", "trac", "ps"):
+        box = H.bounds(m.g, n)
+        nspec = wl.nqx if n == "qx" else wl.ntr if n == "trac" else 0
+        shp = ((nspec,) if nspec else ()) + (m._levels(n), box[3] - box[2] + 1, box[1] - box[0] + 1)
+        buf = m.pinned_empty(shp)
+        for s in range(nspec or 1):
+            m.get_local(n, box, s + 1 if nspec else 0, out=buf[s] if nspec else buf)
+        save[n] = (buf, box)
+    m.sync(); m.set_async(False)
+    # restart: statics as in a cold start, the save set, and init's rebuild of the derived state
+    ep1 = 28.96454 / 18.01528 - 1.0
+    t, pai, qv = save["t"][0], save["pai"][0], save["qx"][0][0]
+    tvirt = t * (1.0 + ep1 * qv)           # Main/mod_init.F90:947-950
+    derived = {"tvirt": tvirt, "tetav": tvirt / pai}
+    r = type(m)(wl, lib=m.lib).allocate_moloch()
+    for n in STATIC_FIELDS:
+        r.set_global(n, fields[n])
+    for n, (buf, box) in save.items():
+        r.set_local(n, buf.reshape(buf.shape[-3:]) if n == "ps" else buf, box)
+    for n, a in derived.items():
+        r.set_local(n, a, save["t"][1])
+    for n in ("ux", "vx", "p", "rho", "qsat"):      # rebuilt by the dycore before they are read; any finite value
+        r.set_global(n, fields[n])
+    for n, v in profiles.items():
+        r.set_profile(n, v)
+    r._chk(r.lib.moloch_b200_init(r.ctx))
+    r.moloch(2)
+    bad = [f for f in PROGNOSTIC + ["trac"] if not np.array_equal(ref.get_global(f), r.get_global(f))]
+    assert not bad, bad
+    for x in (ref, m, r):
+        x.close()

@@ -120,8 +120,14 @@ static int do_sound(Ctx& c) {
   // sound kernels themselves never update.
   const bool fused = halo_fused_available(c);
   HaloItem it;
-  it = {c.f[MB_TETAV].p, kz};
-  if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :562
+  {
+    // tetav (:562) together with the first sub-step's u, v (:570-571) in ONE round: tetavf_init in
+    // between is a column operation on owned cells and touches neither u, v nor any ghost cell
+    const HaloItem itv = {c.f[MB_TETAV].p, kz}, iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
+    const HaloSpec sp[3] = {{&itv, 1, HS_CROSS, 1, true, true, 0}, {&iu, 1, HS_U, 1, true, false, 0},
+                            {&iv, 1, HS_V, 1, false, true, 0}};
+    if (halo_exchange_multi(c, sp, 3)) return 1;
+  }
   if (k_tetavf_init(c)) return 1;
   WaitCtl w_uv = {}, w_zd = {}, w_pai = {};
   PushCtl p_uv = {}, p_zd = {}, p_pai = {};
@@ -129,7 +135,7 @@ static int do_sound(Ctx& c) {
   bool uv_pushed = false;   // u, v ghosts were delivered by the previous sub-step's uvupdate
   for (int ns = 0; ns < nsound; ++ns) {
     const bool f = fused && ns > 0;
-    if (!uv_pushed) {   // :570-571, one round
+    if (!uv_pushed && ns > 0) {   // :570-571, one round (the first sub-step's came with tetav above)
       const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
       const HaloSpec sp[2] = {{&iu, 1, HS_U, 1, true, false, 0}, {&iv, 1, HS_V, 1, false, true, 0}};
       if (halo_exchange_multi(c, sp, 2)) return 1;

@@ -114,17 +114,21 @@ static int do_sound(Ctx& c) {
   const int kz = c.g.kz;
   const int nsound = c.cfg.mo_nsound;
   const bool damp = c.cfg.mo_divdamp || c.cfg.mo_divfilter;
-  // Peer-store transport: from the second sub-step on, the three exchanges of a
-  // sub-step are fused into the kernels around them (see common.cuh).  The first
-  // sub-step keeps the full exchanges: they also refresh the edge cells that the
-  // sound kernels themselves never update.
+  // Peer-store transport: the three exchanges of a sub-step are fused into the kernels around
+  // them (see common.cuh): the producer of zdiv2 / pai / u, v stores the edge cells it computes
+  // into the neighbours' ghost cells, the consumer waits for the neighbours' word.  The edge
+  // cells the sound kernels never update (physical-boundary rows and columns, whose values the
+  // advection and the boundary update change between two sound calls) travel once, in the one
+  // full round at the start of the call.
   const bool fused = halo_fused_available(c);
   HaloItem it;
   {
     // tetav (:562) together with the first sub-step's u, v (:570-571) in ONE round: tetavf_init in
-    // between is a column operation on owned cells and touches neither u, v nor any ghost cell
-    const HaloItem itv = {c.f[MB_TETAV].p, kz}, iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
-    const HaloSpec sp[3] = {{&itv, 1, HS_CROSS, 1, true, true, 0}, {&iu, 1, HS_U, 1, true, false, 0},
+    // between is a column operation on owned cells and touches neither u, v nor any ghost cell.
+    // Fused transport: pai too (its :673 exchange of every sub-step becomes wsolve's edge push).
+    const HaloItem itv[2] = {{c.f[MB_TETAV].p, kz}, {c.f[MB_PAI].p, kz}};
+    const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
+    const HaloSpec sp[3] = {{itv, fused ? 2 : 1, HS_CROSS, 1, true, true, 0}, {&iu, 1, HS_U, 1, true, false, 0},
                             {&iv, 1, HS_V, 1, false, true, 0}};
     if (halo_exchange_multi(c, sp, 3)) return 1;
   }
@@ -134,7 +138,7 @@ static int do_sound(Ctx& c) {
   EdgePush e_u = {}, e_v = {}, e_zd = {}, e_pai = {};
   bool uv_pushed = false;   // u, v ghosts were delivered by the previous sub-step's uvupdate
   for (int ns = 0; ns < nsound; ++ns) {
-    const bool f = fused && ns > 0;
+    const bool f = fused;
     if (!uv_pushed && ns > 0) {   // :570-571, one round (the first sub-step's came with tetav above)
       const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
       const HaloSpec sp[2] = {{&iu, 1, HS_U, 1, true, false, 0}, {&iv, 1, HS_V, 1, false, true, 0}};

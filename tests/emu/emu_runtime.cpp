@@ -15,6 +15,7 @@
 // pointers, system-scope release/acquire flags are C++ atomics, NCCL send/recv
 // is a mailbox.
 #include <sys/mman.h>
+#include <time.h>
 
 #include <chrono>
 #include <condition_variable>
@@ -207,9 +208,28 @@ void run_cta(dim3 block, size_t smem) {
 }
 }  // namespace
 
+// EMU_JITTER=<usec> (or emu_set_jitter): every launch first sleeps a pseudo-random time below that bound, so that
+// the rank threads of a multi-GPU run drift against each other and the peer-store protocol meets other
+// interleavings than the lock-step one (a rank far ahead of / behind its neighbours)
+int g_jitter_us = -1;
+void jitter() {
+  if (g_jitter_us < 0) { const char* e = getenv("EMU_JITTER"); g_jitter_us = e ? atoi(e) : 0; }
+  if (g_jitter_us <= 0) return;
+  static thread_local unsigned long long x = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)(uintptr_t)&x;
+  x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+  const long us = (long)(x % (unsigned long long)g_jitter_us);
+  // one launch in 16 sleeps (emulated kernels take a fraction of a millisecond: the bound should be several
+  // milliseconds for a rank to fall whole kernels behind), the others start at once
+  if (((x >> 32) & 15) != 0) return;
+  struct timespec ts = {us / 1000000L, (us % 1000000L) * 1000L};
+  nanosleep(&ts, nullptr);
+}
+void set_jitter(int us) { g_jitter_us = us; }
+
 void launch(dim3 grid, dim3 block, size_t smem, void (*fn)(void*), void* arg) {
   Sched& s = sched;
   if (s.cur) { fprintf(stderr, "emu: nested launch\n"); abort(); }
+  jitter();
   s.fn = fn; s.arg = arg;
   bDim = block; gDim = grid;
   const long long nb = (long long)grid.x * grid.y * grid.z;
@@ -255,6 +275,7 @@ void cp_async_wait(int keep) {
 }  // namespace emu
 
 extern "C" void emu_set_order(int reverse) { emu::set_order(reverse); }
+extern "C" void emu_set_jitter(int usec) { emu::set_jitter(usec); }
 
 unsigned emu_ballot(int pred) {
   using namespace emu;

@@ -29,9 +29,11 @@ FULL = os.environ.get("EMU_FULL", "0") == "1"
 def _emulated_library(monkeypatch):
     lib = emu_lib.load()
     lib.emu_set_order(0)
+    lib.emu_set_jitter(0)
     monkeypatch.setattr(util, "LIB", lib)
     yield lib
     lib.emu_set_order(0)
+    lib.emu_set_jitter(0)
 
 
 def _gpu_tests():
@@ -187,3 +189,15 @@ def test_spectral_nudging_needs_nccl():
 def test_restart_from_the_save_set():
     import test_gpu_zz_handoff as Hf
     Hf.test_restart_from_the_save_set_is_bit_exact()
+
+
+@pytest.mark.parametrize("name,px,py", [("limited_area_2x2", 2, 2), ("band_2x4", 2, 4)] if FULL else [("limited_area_2x2", 2, 2)])
+def test_decomposed_with_drifting_ranks(name, px, py, monkeypatch, _emulated_library):
+    """The peer-store transport under rank drift: every launch of every rank thread first sleeps a pseudo-random
+    time (one launch in 16, up to 20 ms: a rank is at times several kernels behind its neighbours).  The
+    protocol must still deliver every ghost cell before its reader and never overwrite one that is still read:
+    bit-exact against the single-domain oracle."""
+    M = _gpu_tests()[2]
+    wl = [c for c in M.CASES if c[0] == name][0][1]
+    _emulated_library.emu_set_jitter(20000)
+    M.test_decomposed_bit_exact(name, wl, px, py, "p2p", monkeypatch)

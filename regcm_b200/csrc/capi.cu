@@ -109,7 +109,9 @@ static int sync_stream(Ctx& c) {
 }
 
 // ---- orchestration ----------------------------------------------------------
-static int do_sound(Ctx& c) {
+// for_adv: called from dynamical_core, `advection` follows at once -- with the fused transport the last
+// sub-step's uvupdate then delivers advection's 2-wide u, v ghosts (:1532-1533) and destagger waits for them
+static int do_sound(Ctx& c, bool for_adv = false) {
   const double dts = c.dtsound;
   const int kz = c.g.kz;
   const int nsound = c.cfg.mo_nsound;
@@ -128,10 +130,12 @@ static int do_sound(Ctx& c) {
     // Fused transport: pai too (its :673 exchange of every sub-step becomes wsolve's edge push).
     const HaloItem itv[2] = {{c.f[MB_TETAV].p, kz}, {c.f[MB_PAI].p, kz}};
     const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
-    const HaloSpec sp[3] = {{itv, fused ? 2 : 1, HS_CROSS, 1, true, true, 0}, {&iu, 1, HS_U, 1, true, false, 0},
-                            {&iv, 1, HS_V, 1, false, true, 0}};
+    const int wuv = (fused && for_adv) ? 2 : 1;   // boundary rows/columns of u, v for the 2-wide pushes below
+    const HaloSpec sp[3] = {{itv, fused ? 2 : 1, HS_CROSS, 1, true, true, 0}, {&iu, 1, HS_U, wuv, true, false, 0},
+                            {&iv, 1, HS_V, wuv, false, true, 0}};
     if (halo_exchange_multi(c, sp, 3)) return 1;
   }
+  c.adv_wait_valid = false;
   if (k_tetavf_init(c)) return 1;
   WaitCtl w_uv = {}, w_zd = {}, w_pai = {};
   PushCtl p_uv = {}, p_zd = {}, p_pai = {};
@@ -167,16 +171,18 @@ static int do_sound(Ctx& c) {
       if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :673
     }
     // this uvupdate delivers the next sub-step's u, v ghosts
-    const bool push_uv = fused && ns + 1 < nsound;
+    const bool push_uv = fused && (ns + 1 < nsound || for_adv);
     if (push_uv) {
+      const int wuv = for_adv ? 2 : 1;
       if (halo_fused_begin(c, &p_uv, &w_uv)) return 1;
-      if (halo_fused_edge(c, c.f[MB_U].p, HS_U, true, false, &e_u)) return 1;
-      if (halo_fused_edge(c, c.f[MB_V].p, HS_V, false, true, &e_v)) return 1;
+      if (halo_fused_edge(c, c.f[MB_U].p, HS_U, true, false, &e_u, wuv)) return 1;
+      if (halo_fused_edge(c, c.f[MB_V].p, HS_V, false, true, &e_v, wuv)) return 1;
     }
     if (k_uvupdate(c, dts, f ? &w_pai : nullptr, push_uv ? &p_uv : nullptr, push_uv ? &e_u : nullptr,
                    push_uv ? &e_v : nullptr)) return 1;
     uv_pushed = push_uv;
   }
+  if (uv_pushed) { c.adv_wait = w_uv; c.adv_wait_valid = true; }   // consumed by advection's destagger
   return 0;  // :728-734 (finish of s) is fused into the last sub-step's wsolve
 }
 
@@ -214,23 +220,46 @@ static int do_wafone_range(Ctx& c, int first, int count) {
   return k_waf_x(c, first, count, dta);
 }
 
-static int do_advection(Ctx& c) {
+// uv_delivered: called from dynamical_core right after do_sound(c, true)
+static int do_advection(Ctx& c, bool uv_delivered = false) {
   const int kz = c.g.kz;
-  {   // :1532-1533, one round
+  // Peer-store transport inside dynamical_core: the two exchanges around the advection proper are fused into
+  // the kernels.  u, v (:1532-1533) came with the last uvupdate and destagger waits for them; ux, vx
+  // (:1485-1486) are stored into the neighbours' ghost cells by destagger (all edge cells: the
+  // physical-boundary rows and columns are final there) and again by curvature (the cells the advection
+  // changed); restagger waits for the neighbours' word.
+  const bool fused = uv_delivered && c.adv_wait_valid && halo_fused_available(c);
+  PushCtl p_x0 = {}, p_x = {};
+  WaitCtl w_x = {};
+  EdgePush e_ux = {}, e_vx = {};
+  if (fused) {
+    if (halo_push_ctl(c, &p_x0)) return 1;
+    if (halo_fused_edge(c, c.f[MB_UX].p, HS_CROSS, true, false, &e_ux, 2)) return 1;
+    if (halo_fused_edge(c, c.f[MB_VX].p, HS_CROSS, false, true, &e_vx, 2)) return 1;
+    if (k_destagger(c, &c.adv_wait, &p_x0, &e_ux, &e_vx)) return 1;
+    c.adv_wait_valid = false;
+  } else {   // :1532-1533, one round
     const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
     const HaloSpec sp[2] = {{&iu, 1, HS_U, 2, true, false, 0}, {&iv, 1, HS_V, 2, false, true, 0}};
     if (halo_exchange_multi(c, sp, 2)) return 1;
+    if (k_destagger(c)) return 1;
   }
-  if (k_destagger(c)) return 1;
   if (c.cfg.ibltyp == 2 && k_tke_destagger(c)) return 1;          // :782-784
   if (do_wafone_range(c, 0, c.nadv_fields)) return 1;             // :786-807
-  if (k_curvature(c, c.dtstepa)) return 1;
-  {   // :1485-1486, one round
-    const HaloItem iu = {c.f[MB_UX].p, kz}, iv = {c.f[MB_VX].p, kz};
-    const HaloSpec sp[2] = {{&iu, 1, HS_CROSS, 2, true, false, 0}, {&iv, 1, HS_CROSS, 2, false, true, 0}};
-    if (halo_exchange_multi(c, sp, 2)) return 1;
+  if (fused) {
+    // the round is numbered here, after the advection's own exchanges: restagger's signal is the latest word
+    if (halo_fused_begin(c, &p_x, &w_x)) return 1;
+    if (k_curvature(c, c.dtstepa, &p_x, &e_ux, &e_vx)) return 1;
+    if (k_restagger(c, true, &w_x)) return 1;
+  } else {
+    if (k_curvature(c, c.dtstepa)) return 1;
+    {   // :1485-1486, one round
+      const HaloItem iu = {c.f[MB_UX].p, kz}, iv = {c.f[MB_VX].p, kz};
+      const HaloSpec sp[2] = {{&iu, 1, HS_CROSS, 2, true, false, 0}, {&iv, 1, HS_CROSS, 2, false, true, 0}};
+      if (halo_exchange_multi(c, sp, 2)) return 1;
+    }
+    if (k_restagger(c, true)) return 1;
   }
-  if (k_restagger(c, true)) return 1;
   if (c.cfg.ibltyp == 2 && k_tke_restagger(c)) return 1;          // :832-834
   return 0;
 }
@@ -238,8 +267,8 @@ static int do_advection(Ctx& c) {
 static int do_dynamical_core(Ctx& c) {
   if (k_diag(c, 0, false)) return 1;              // ten0, qen0, chiten0 :1092-1103
   for (int n = 0; n < c.cfg.mo_nadv; ++n) {
-    if (do_sound(c)) return 1;
-    if (do_advection(c)) return 1;
+    if (do_sound(c, true)) return 1;
+    if (do_advection(c, true)) return 1;
   }
   if (k_tvirt_temp(c)) return 1;
   return k_diag(c, 0, true);                      // tdiag%adh, qdiag%adh, cadvhdiag :1127-1139

@@ -49,6 +49,25 @@ struct Peer {
   long long plane = 0;
 };
 
+// control blocks of the fused halo rounds (see "fused halo rounds" below)
+struct EdgePush {            // one array, edges of width nex (1 or 2)
+  int j1, j2, i1, i2;        // owned box of the array's staggering
+  int nex;
+  double* q[4];              // the array inside each neighbour's arena (null: side not exchanged)
+  int dj[4], di[4];          // index shift into the neighbour's numbering (periodic wrap)
+};
+struct PushCtl {
+  int mask;                  // remote sides (0: nothing to push)
+  int pNJ[4], pj0[4], pi0[4];
+  long long pplane[4];
+};
+struct WaitCtl {
+  int mask;                  // remote sides to signal and to wait for
+  unsigned long long seq;
+  unsigned long long* pflag[4];   // neighbour's arrival counter for the side it sees me on
+  unsigned long long* flags;      // own flag block: [0..3] arrival counters, [5] timeout marker
+  long long timeout_cycles;
+};
 struct Ctx;
 void halo_free(Ctx& c);
 
@@ -88,6 +107,8 @@ struct Ctx {
   void* nccl_comm = nullptr;
   double *sendbuf = nullptr, *recvbuf = nullptr;
   size_t halo_buf_doubles = 0;
+  WaitCtl adv_wait = {};                 // u, v pushed by the last sub-step's uvupdate: destagger waits (dynamical_core)
+  bool adv_wait_valid = false;
   double* gather_buf = nullptr;          // row/column reductions: the other members' partial sums
   size_t gather_doubles = 0;
   // profiling
@@ -148,23 +169,6 @@ struct LaunchScope {
 // flushed -- starts with halo_sync(): its first CTA tells the neighbours "my
 // edges are in your ghost cells", every CTA waits for the neighbours' word.
 // No separate exchange launch, no per-CTA synchronisation in the producers.
-struct EdgePush {            // one array, width-1 edges
-  int j1, j2, i1, i2;        // owned box of the array's staggering
-  double* q[4];              // the array inside each neighbour's arena (null: side not exchanged)
-  int dj[4], di[4];          // index shift into the neighbour's numbering (periodic wrap)
-};
-struct PushCtl {
-  int mask;                  // remote sides (0: nothing to push)
-  int pNJ[4], pj0[4], pi0[4];
-  long long pplane[4];
-};
-struct WaitCtl {
-  int mask;                  // remote sides to signal and to wait for
-  unsigned long long seq;
-  unsigned long long* pflag[4];   // neighbour's arrival counter for the side it sees me on
-  unsigned long long* flags;      // own flag block: [0..3] arrival counters, [5] timeout marker
-  long long timeout_cycles;
-};
 #ifdef __CUDACC__
 // system-scope release store / acquire load of a flag word (arrival counters of
 // the peer-store halo transport).  MB_HOST_EMU: the tests' host build of this
@@ -186,26 +190,34 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 #endif
 }
 __device__ __forceinline__ void edge_push(const PushCtl& pc, const EdgePush& e, int j, int i, int k, double v) {
-  if (e.q[0] && j == e.j1 && i >= e.i1 && i <= e.i2)
+  if (e.q[0] && j >= e.j1 && j < e.j1 + e.nex && i >= e.i1 && i <= e.i2)
     e.q[0][(long long)(k - 1) * pc.pplane[0] + (long long)(i + e.di[0] - pc.pi0[0]) * pc.pNJ[0] + (j + e.dj[0] - pc.pj0[0])] = v;
-  if (e.q[1] && j == e.j2 && i >= e.i1 && i <= e.i2)
+  if (e.q[1] && j <= e.j2 && j > e.j2 - e.nex && i >= e.i1 && i <= e.i2)
     e.q[1][(long long)(k - 1) * pc.pplane[1] + (long long)(i + e.di[1] - pc.pi0[1]) * pc.pNJ[1] + (j + e.dj[1] - pc.pj0[1])] = v;
-  if (e.q[2] && i == e.i1 && j >= e.j1 && j <= e.j2)
+  if (e.q[2] && i >= e.i1 && i < e.i1 + e.nex && j >= e.j1 && j <= e.j2)
     e.q[2][(long long)(k - 1) * pc.pplane[2] + (long long)(i + e.di[2] - pc.pi0[2]) * pc.pNJ[2] + (j + e.dj[2] - pc.pj0[2])] = v;
-  if (e.q[3] && i == e.i2 && j >= e.j1 && j <= e.j2)
+  if (e.q[3] && i <= e.i2 && i > e.i2 - e.nex && j >= e.j1 && j <= e.j2)
     e.q[3][(long long)(k - 1) * pc.pplane[3] + (long long)(i + e.di[3] - pc.pi0[3]) * pc.pNJ[3] + (j + e.dj[3] - pc.pj0[3])] = v;
 }
 // First statement of a consumer kernel whose grid tiles the rank's box with
 // blockIdx.x along j and blockIdx.y along i.  Only the CTAs on an edge of the
 // grid read ghost cells of that side, so only they wait for that neighbour; the
 // interior CTAs start at once and overlap the signal's flight.
-__device__ __forceinline__ void halo_sync(const WaitCtl& w) {
+// `reach` > 1 (with the number of columns / rows the grid covers): the kernel's stencil reads `reach` points
+// beyond a cell, so a CTA whose cells come within reach-1 of the last column / row waits as well (the last
+// CTA may be narrower than the reach).  `bx`, `by`: CTA extent in j and i.
+__device__ __forceinline__ void halo_sync(const WaitCtl& w, int reach = 1, int ncols = 0, int nrows = 0,
+                                          int bx = 0, int by = 0) {
   if (w.mask == 0) return;
   int need = 0;
   if (blockIdx.x == 0) need |= 1;
   if (blockIdx.x == gridDim.x - 1) need |= 2;
   if (blockIdx.y == 0) need |= 4;
   if (blockIdx.y == gridDim.y - 1) need |= 8;
+  if (reach > 1) {
+    if ((int)(blockIdx.x + 1) * bx - 1 + reach >= ncols) need |= 2;
+    if ((int)(blockIdx.y + 1) * by - 1 + reach >= nrows) need |= 8;
+  }
   need &= w.mask;
   const bool first = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0);
   if (need == 0 && !first) return;
@@ -238,12 +250,14 @@ int k_wsolve(Ctx& c, double dts, bool last, const PushCtl* pc = nullptr, const E
 int k_uvupdate(Ctx& c, double dts, const WaitCtl* wc = nullptr, const PushCtl* pc = nullptr, const EdgePush* eu = nullptr,
                const EdgePush* ev = nullptr);
 int k_sfinish(Ctx& c);
-int k_destagger(Ctx& c);
+int k_destagger(Ctx& c, const WaitCtl* wc = nullptr, const PushCtl* pc = nullptr, const EdgePush* eux = nullptr,
+                const EdgePush* evx = nullptr);
 int k_waf_z(Ctx& c, int first, int count, double dta);
 int k_waf_y(Ctx& c, int first, int count, double dta);
 int k_waf_x(Ctx& c, int first, int count, double dta);
-int k_curvature(Ctx& c, double dta);
-int k_restagger(Ctx& c, bool with_w);
+int k_curvature(Ctx& c, double dta, const PushCtl* pc = nullptr, const EdgePush* eux = nullptr,
+                const EdgePush* evx = nullptr);
+int k_restagger(Ctx& c, bool with_w, const WaitCtl* wc = nullptr);
 int k_tvirt_temp(Ctx& c);
 int k_diagnostics(Ctx& c);
 int k_status_update(Ctx& c, double dtinc);
@@ -277,7 +291,10 @@ int halo_fence(Ctx& c);
 // fused rounds: allocate the round, describe one array's edges
 bool halo_fused_available(const Ctx& c);
 int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc);
-int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep);
+int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep, int nex = 1);
+// geometry of the neighbours' boxes only (no round number): for a producer that pushes ahead of the round
+// in which the last producer of the same array signals
+int halo_push_ctl(Ctx& c, PushCtl* pc);
 // row_reduce / column_reduce (Main/mpplib/mod_mppparam.F90:20618-20664): in-place sum of `count` doubles
 // over the ranks `members` (ascending, this rank included), added in rank order on every member
 int halo_group_sum(Ctx& c, double* data, size_t count, const int* members, int nmem);

@@ -560,12 +560,21 @@ int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc) {
   return 0;
 }
 
-// Width-1 edges of one array (exchange_lr / _bt / _lrbt semantics, no corners).
+int halo_push_ctl(Ctx& c, PushCtl* pc) {
+  WaitCtl unused;
+  const unsigned long long seq = c.halo_seq;
+  const int rc = halo_fused_begin(c, pc, &unused);
+  c.halo_seq = seq;   // no round is opened
+  return rc;
+}
+
+// Edges of width nex of one array (exchange_lr / _bt / _lrbt semantics, no corners).
 // A periodic self-neighbour cannot be fused (the caller checks fusable()).
-int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep) {
+int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep, int nex) {
   const moloch_b200_config& cf = c.cfg;
   const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
   memset(ep, 0, sizeof(*ep));
+  ep->nex = nex;
   owned_box(cf, stag, ep->j1, ep->j2, ep->i1, ep->i2);
   for (int sd = 0; sd < 4; ++sd) {
     const bool on = (nbr[sd] >= 0) && ((sd < 2) ? lr : bt);

@@ -608,38 +608,57 @@ int k_sfinish(Ctx& c) {
 // ---------------------------------------------------------------------------
 // K12+K13  uvstagtouvx :1537-1567 and zstagtoh :1451-1458
 // ---------------------------------------------------------------------------
+// FUSED (peer-store transport inside dynamical_core): the kernel first waits for the neighbours' u, v edges
+// (pushed, 2 wide, by the last sub-step's uvupdate) and stores its own ux / vx edges, 2 wide, into the
+// neighbours' ghost cells: the physical-boundary rows and columns among them are final here, the others are
+// overwritten by curvature's push after the advection (uvxtouvstag's exchange, :1485-1486).
+template <bool FUSED>
 __global__ void moloch_destagger(Geo g, const double* __restrict__ u, const double* __restrict__ v,
                                  const double* __restrict__ w, double* __restrict__ ux,
-                                 double* __restrict__ vx, double* __restrict__ wx) {
+                                 double* __restrict__ vx, double* __restrict__ wx, WaitCtl wc, PushCtl pc,
+                                 EdgePush eux, EdgePush evx) {
+  if (FUSED) halo_sync(wc, 2, g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, BX, BY);
   THREAD_JIK(g.jce1, g.ice1, 1)
   if (j > g.jce2 || i > g.ice2) return;
   const long long id = IX(j, i, k);
   const int kz = g.kz;
+  double uxn, vxn;
   // ux on jci1:jci2 (4th order) and the physical-boundary columns (2nd order)
   if (j >= g.jci1 && j <= g.jci2) {
-    ux[id] = 0.5625 * (u[id + 1] + u[id]) - 0.0625 * (u[id + 2] + u[id - 1]);
+    uxn = 0.5625 * (u[id + 1] + u[id]) - 0.0625 * (u[id + 2] + u[id - 1]);
   } else {
     // j == jce1 with has_bdyleft: u(jde1),u(jdi1) = u(j),u(j+1); j == jce2 with
     // has_bdyright: u(jde2),u(jdi2) = u(j+1),u(j)
-    if (j == g.jce1) ux[id] = 0.5 * (u[id] + u[id + 1]);
-    else ux[id] = 0.5 * (u[id + 1] + u[id]);
+    if (j == g.jce1) uxn = 0.5 * (u[id] + u[id + 1]);
+    else uxn = 0.5 * (u[id + 1] + u[id]);
   }
+  ux[id] = uxn;
   if (i >= g.ici1 && i <= g.ici2) {
-    vx[id] = 0.5625 * (v[id + g.NJ] + v[id]) - 0.0625 * (v[id + 2 * g.NJ] + v[id - g.NJ]);
+    vxn = 0.5625 * (v[id + g.NJ] + v[id]) - 0.0625 * (v[id + 2 * g.NJ] + v[id - g.NJ]);
   } else {
-    if (i == g.ice1) vx[id] = 0.5 * (v[id] + v[id + g.NJ]);
-    else vx[id] = 0.5 * (v[id + g.NJ] + v[id]);
+    if (i == g.ice1) vxn = 0.5 * (v[id] + v[id + g.NJ]);
+    else vxn = 0.5 * (v[id + g.NJ] + v[id]);
   }
+  vx[id] = vxn;
+  if (FUSED && pc.mask) { edge_push(pc, eux, j, i, k, uxn); edge_push(pc, evx, j, i, k, vxn); }
   const long long pl = g.plane;
   if (k == 1) wx[id] = 0.5 * (w[id + pl] + w[id]);
   else if (k == kz) wx[id] = 0.5 * (w[id + pl] + w[id]);
   else wx[id] = 0.5625 * (w[id + pl] + w[id]) - 0.0625 * (w[id + 2 * pl] + w[id - pl]);
 }
-int k_destagger(Ctx& c) {
+int k_destagger(Ctx& c, const WaitCtl* wc, const PushCtl* pc, const EdgePush* eux, const EdgePush* evx) {
   const Geo& g = c.g;
+  const WaitCtl w0 = wc ? *wc : WaitCtl{};
+  const PushCtl p0 = pc ? *pc : PushCtl{};
+  const EdgePush e0 = eux ? *eux : EdgePush{}, e1 = evx ? *evx : EdgePush{};
   LaunchScope ls(c, KID_DESTAG);
-  moloch_destagger<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
-      g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_W].p, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_WX].p);
+  const dim3 grid = grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz);
+  if (w0.mask || p0.mask)
+    moloch_destagger<true><<<grid, dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_W].p, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_WX].p, w0, p0, e0, e1);
+  else
+    moloch_destagger<false><<<grid, dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_W].p, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_WX].p, w0, p0, e0, e1);
   MB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -841,10 +860,11 @@ int k_waf_x(Ctx& c, int first, int count, double dta) {
 // ---------------------------------------------------------------------------
 // K17  curvature terms                                                :811-825
 // ---------------------------------------------------------------------------
+template <bool FUSED>
 __global__ void moloch_curvature(Geo g, double* __restrict__ ux, double* __restrict__ vx,
                                  const double* __restrict__ mx, const double* __restrict__ mu,
                                  const double* __restrict__ mv, const double* __restrict__ rlat, double rdx,
-                                 double dta) {
+                                 double dta, PushCtl pc, EdgePush eux, EdgePush evx) {
   THREAD_JIK(g.jci1, g.ici1, 1)
   if (j > g.jci2 || i > g.ici2) return;
   const long long id = IX(j, i, k);
@@ -861,14 +881,24 @@ __global__ void moloch_curvature(Geo g, double* __restrict__ ux, double* __restr
   }
   const double uxn = ux[id] + ux[id] * vx[id] * tanx * dta;
   ux[id] = uxn;
-  vx[id] = vx[id] - uxn * uxn * tany * dta;
+  const double vxn = vx[id] - uxn * uxn * tany * dta;
+  vx[id] = vxn;
+  if (FUSED && pc.mask) { edge_push(pc, eux, j, i, k, uxn); edge_push(pc, evx, j, i, k, vxn); }
 }
-int k_curvature(Ctx& c, double dta) {
+int k_curvature(Ctx& c, double dta, const PushCtl* pc, const EdgePush* eux, const EdgePush* evx) {
   const Geo& g = c.g;
+  const PushCtl p0 = pc ? *pc : PushCtl{};
+  const EdgePush e0 = eux ? *eux : EdgePush{}, e1 = evx ? *evx : EdgePush{};
   LaunchScope ls(c, KID_CURV);
-  moloch_curvature<<<grid3(g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
-      g, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_MSFX].p, c.f[MB_MSFU].p, c.f[MB_MSFV].p, c.prof[MB_RLAT], c.rdx,
-      dta);
+  const dim3 grid = grid3(g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, g.kz);
+  if (p0.mask)
+    moloch_curvature<true><<<grid, dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_MSFX].p, c.f[MB_MSFU].p, c.f[MB_MSFV].p, c.prof[MB_RLAT], c.rdx,
+        dta, p0, e0, e1);
+  else
+    moloch_curvature<false><<<grid, dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_MSFX].p, c.f[MB_MSFU].p, c.f[MB_MSFV].p, c.prof[MB_RLAT], c.rdx,
+        dta, p0, e0, e1);
   MB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -876,9 +906,11 @@ int k_curvature(Ctx& c, double dta) {
 // ---------------------------------------------------------------------------
 // K18+K19  uvxtouvstag :1490-1520 and htozstag :1467-1474
 // ---------------------------------------------------------------------------
+template <bool FUSED>
 __global__ void moloch_restagger(Geo g, const double* __restrict__ ux, const double* __restrict__ vx,
                                  const double* __restrict__ wx, double* __restrict__ u,
-                                 double* __restrict__ v, double* __restrict__ w, int with_w) {
+                                 double* __restrict__ v, double* __restrict__ w, int with_w, WaitCtl wc) {
+  if (FUSED) halo_sync(wc, 2, g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, BX, BY);   // ux, vx ghosts (2 wide)
   THREAD_JIK(g.jde1, g.ide1, 1)
   if (j > g.jde2 || i > g.ide2) return;
   const long long id = IX(j, i, k);
@@ -908,11 +940,17 @@ __global__ void moloch_restagger(Geo g, const double* __restrict__ ux, const dou
     else w[id] = 0.5625 * (wx[id] + wx[id - pl]) - 0.0625 * (wx[id + pl] + wx[id - 2 * pl]);
   }
 }
-int k_restagger(Ctx& c, bool with_w) {
+int k_restagger(Ctx& c, bool with_w, const WaitCtl* wc) {
   const Geo& g = c.g;
+  const WaitCtl w0 = wc ? *wc : WaitCtl{};
   LaunchScope ls(c, KID_RESTAG);
-  moloch_restagger<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
-      g, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_WX].p, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_W].p, with_w ? 1 : 0);
+  const dim3 grid = grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz);
+  if (w0.mask)
+    moloch_restagger<true><<<grid, dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_WX].p, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_W].p, with_w ? 1 : 0, w0);
+  else
+    moloch_restagger<false><<<grid, dim3(BX, BY), 0, c.stream>>>(
+        g, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_WX].p, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_W].p, with_w ? 1 : 0, w0);
   MB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,11 +1,31 @@
 #!/bin/bash
-# First GPU call of a new round: everything that was added after round 1's GPU budget ran out.
-# usage: gpurun --timeout 300 -- bash scripts/r2_check.sh        (1 GPU)
-#        gpurun --gpus 2 --timeout 300 -- 'python -m pytest tests/test_gpu_multi.py -q -k "boundary or 2x1 or 1x2"'
+# First GPU call of a new round: everything that was added after round 1's GPU budget ran out
+# (massck reduction, tendency diagnostics, pipelined hand-off, multi-rank spectral nudging, fused
+# advection / first-sub-step exchanges).  All of it has run bit-exact on the CPU build of the CUDA
+# sources (tests/test_emu_full.py); this is its first contact with a B200.
+# usage: gpurun --timeout 420 -- bash scripts/r2_check.sh                      (1 GPU)
+#        gpurun --gpus 2 --timeout 300 -- 'python -m pytest tests/test_gpu_multi.py -q'
+#        gpurun --gpus 8 --timeout 600 -- bash scripts/scale8.sh                 (strong scaling, 16 -> 6 halo launches)
 mkdir -p gpurun_out
-timeout 30 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 120 python -m pytest tests -m gpu -q --timeout 100 -p no:cacheprovider --durations=5 > gpurun_out/r2_gpu_tests.log 2>&1
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 200 python -m pytest tests -m gpu -q --timeout 150 -p no:cacheprovider --durations=5 > gpurun_out/r2_gpu_tests.log 2>&1
 tail -12 gpurun_out/r2_gpu_tests.log
+# e2e: pipelined hand-off (default) against the sequential one, and the slab count
+timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_pipelined.json 2> gpurun_out/r2_bench_pipelined.err
+BENCH_HANDOFF=sequential timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_sequential.json 2>/dev/null
+BENCH_HANDOFF_SLABS=4 timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_slabs4.json 2>/dev/null
+BENCH_HANDOFF_SLABS=16 timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_slabs16.json 2>/dev/null
+for f in pipelined sequential slabs4 slabs16; do
+  python - "$f" <<'PY'
+import json, sys
+try:
+    d = json.loads([l for l in open(f"gpurun_out/r2_bench_{sys.argv[1]}.json") if l.startswith("{")][-1])
+    e = d["e2e"]
+    print(sys.argv[1], "ms/step", round(d["ms_per_step"], 3), "e2e ms/step", round(e["ms_per_step"], 2), e.get("handoff"), e.get("handoff_note"))
+except Exception as exc:
+    print(sys.argv[1], "no result:", exc)
+PY
+done
 timeout 90 python scripts/kbench.py --boundary --slice --spectral --tke --massck --diag --steps 4 --warmup 1 \
   > gpurun_out/r2_kbench_all.json 2> gpurun_out/r2_kbench_all.err
 tail -c 1500 gpurun_out/r2_kbench_all.json; tail -3 gpurun_out/r2_kbench_all.err

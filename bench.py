@@ -344,24 +344,58 @@ def main():
     py = args.py or (world if world > 1 else None)
     if world > 1 and wl.iy // py < 3:
         px, py = None, None     # too thin: fall back to set_nproc's choice
-    m = MolochB200(wl, rank=rank, nranks=world, px=px, py=py, device=local_rank).allocate_moloch()
-    if world > 1:
-        if args.transport == "nccl":
-            ids = [MolochB200.comm_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            m.comm_init(ids[0])
-        else:   # direct NVLink peer stores between the ranks' arenas (CUDA IPC)
-            blobs = [None] * world
-            dist.all_gather_object(blobs, m.p2p_export())
-            m.p2p_connect(blobs)
-            dist.barrier()
     stream = torch.cuda.Stream()
-    m.set_stream(stream.cuda_stream)
-    # the rank's own arrays, generated locally (no global 3-D arrays: the large
-    # workloads would not fit the host otherwise)
-    fields, profiles, boxes = S.model_inputs_local(wl, m.g)
-    m.init_moloch(fields, profiles, boxes)
-    del fields
+
+    def build_model():
+        m = MolochB200(wl, rank=rank, nranks=world, px=px, py=py, device=local_rank).allocate_moloch()
+        if world > 1:
+            if args.transport == "nccl":
+                ids = [MolochB200.comm_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                m.comm_init(ids[0])
+            else:   # direct NVLink peer stores between the ranks' arenas (CUDA IPC)
+                blobs = [None] * world
+                dist.all_gather_object(blobs, m.p2p_export())
+                m.p2p_connect(blobs)
+                dist.barrier()
+        m.set_stream(stream.cuda_stream)
+        # the rank's own arrays, generated locally (no global 3-D arrays: the large
+        # workloads would not fit the host otherwise)
+        fields, profiles, boxes = S.model_inputs_local(wl, m.g)
+        m.init_moloch(fields, profiles, boxes)
+        return m
+
+    # Peer-store transport: how many of the exchanges are fused into the kernels around them is a library
+    # switch (MOLOCH_B200_FUSE_HALO: 2 = all, the default; 1 = sub-steps 2.. of the sound loop only, the
+    # configuration the round-1 scaling numbers were measured with; 0 = none).  One untimed step checks that
+    # every rank gets through its waits and stays finite; otherwise the next lower level is used and named.
+    from regcm_b200.moloch import MolochError
+    levels = [os.environ.get("MOLOCH_B200_FUSE_HALO", "2")]
+    if world > 1 and args.transport == "p2p":
+        levels += [x for x in ("1", "0") if x < levels[0]]
+    m, fusion_note = None, None
+    for lv in levels:
+        os.environ["MOLOCH_B200_FUSE_HALO"] = lv
+        m = build_model()
+        ok = 1.0
+        try:
+            m.moloch(1)
+            m.sync()
+            ok = 1.0 if bool(np.isfinite(m.get_local("pai")).all()) else 0.0
+        except MolochError as exc:
+            ok, fusion_note = 0.0, f"level {lv}: {exc}"
+        t = torch.tensor([ok], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if float(t.item()) > 0.5:
+            break
+        fusion_note = fusion_note or f"level {lv}: non-finite state or a timed-out wait on another rank"
+        if lv != levels[-1]:
+            m.close()
+            m = None
+            if world > 1:
+                dist.barrier()
+    halo_fusion = lv
 
     def barrier():
         if world > 1:
@@ -464,6 +498,10 @@ def main():
         line = base_line(wl, args, world)
         line["config"]["decomposition"] = f"{m.g.px}x{m.g.py}"
         line["config"]["halo_transport"] = ("none" if world == 1 else args.transport)
+        if world > 1 and args.transport == "p2p":
+            line["config"]["halo_fusion_level"] = int(halo_fusion)
+            if fusion_note:
+                line["config"]["halo_fusion_note"] = fusion_note
         line.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "e2e": e2e,
                      "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                      "kernels": kernels[:12], "finite": finite, "device_bytes": m.device_bytes()})

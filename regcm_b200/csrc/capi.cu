@@ -105,6 +105,13 @@ static int check_cfg(const moloch_b200_config& f) {
 
 static int sync_stream(Ctx& c) {
   MB_CUDA(cudaStreamSynchronize(c.stream));
+  if (c.p2p && c.flags) {   // a wait of the peer-store transport gave up: the ghost cells of that round are stale
+    unsigned long long t = 0;
+    MB_CUDA(cudaMemcpy(&t, c.flags + 5, sizeof(t), cudaMemcpyDeviceToHost));
+    if (t != 0ULL)
+      return fail("halo exchange timed out in round " + std::to_string(t) + " of this rank: a neighbour never "
+                  "arrived (ranks out of step, or a rank died); results after that round are invalid");
+  }
   return 0;
 }
 
@@ -123,6 +130,8 @@ static int do_sound(Ctx& c, bool for_adv = false) {
   // advection and the boundary update change between two sound calls) travel once, in the one
   // full round at the start of the call.
   const bool fused = halo_fused_available(c);
+  const bool fused_all = fused && c.fuse_level >= 2;   // also the first sub-step (and pai in the full round)
+  if (!fused_all) for_adv = false;
   HaloItem it;
   {
     // tetav (:562) together with the first sub-step's u, v (:570-571) in ONE round: tetavf_init in
@@ -131,7 +140,7 @@ static int do_sound(Ctx& c, bool for_adv = false) {
     const HaloItem itv[2] = {{c.f[MB_TETAV].p, kz}, {c.f[MB_PAI].p, kz}};
     const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
     const int wuv = (fused && for_adv) ? 2 : 1;   // boundary rows/columns of u, v for the 2-wide pushes below
-    const HaloSpec sp[3] = {{itv, fused ? 2 : 1, HS_CROSS, 1, true, true, 0}, {&iu, 1, HS_U, wuv, true, false, 0},
+    const HaloSpec sp[3] = {{itv, fused_all ? 2 : 1, HS_CROSS, 1, true, true, 0}, {&iu, 1, HS_U, wuv, true, false, 0},
                             {&iv, 1, HS_V, wuv, false, true, 0}};
     if (halo_exchange_multi(c, sp, 3)) return 1;
   }
@@ -142,7 +151,7 @@ static int do_sound(Ctx& c, bool for_adv = false) {
   EdgePush e_u = {}, e_v = {}, e_zd = {}, e_pai = {};
   bool uv_pushed = false;   // u, v ghosts were delivered by the previous sub-step's uvupdate
   for (int ns = 0; ns < nsound; ++ns) {
-    const bool f = fused;
+    const bool f = fused && (fused_all || ns > 0);
     if (!uv_pushed && ns > 0) {   // :570-571, one round (the first sub-step's came with tetav above)
       const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
       const HaloSpec sp[2] = {{&iu, 1, HS_U, 1, true, false, 0}, {&iv, 1, HS_V, 1, false, true, 0}};
@@ -427,7 +436,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   cudaMemcpy(c->d_ptrtab, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice);
   c->h_ptrtab = tab;
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
-  if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) c->fuse_halo = atoi(e) != 0;
+  if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
   if (const char* e = getenv("MOLOCH_B200_WSOLVE")) c->wsolve_impl = atoi(e) == 2 ? 2 : 5;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaFree(c->arena);

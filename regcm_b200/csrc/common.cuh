@@ -103,6 +103,8 @@ struct Ctx {
   unsigned long long halo_seq = 0;
   bool p2p = false;
   bool fuse_halo = true;                 // sound-loop exchanges fused into producer/consumer kernels (p2p only)
+  int fuse_level = 2;                    // 1: sub-steps 2.. of the sound loop only; 2: also the first sub-step and
+                                         // advection's u,v / ux,vx exchanges (MOLOCH_B200_FUSE_HALO=0|1|2)
   Peer peer[4];                          // left, right, bottom, top
   void* nccl_comm = nullptr;
   double *sendbuf = nullptr, *recvbuf = nullptr;
@@ -233,7 +235,9 @@ __device__ __forceinline__ void halo_sync(const WaitCtl& w, int reach = 1, int n
       if (!((need >> sd) & 1)) continue;
       for (;;) {
         if (ld_acquire_sys(w.flags + sd) >= w.seq) break;
-        if (clock64() - t0 > w.timeout_cycles) { w.flags[5] = w.seq; break; }   // neighbour never arrived
+        // neighbour never arrived: mark the round (moloch_b200_sync reports it); later waits give up at once
+        if (ld_acquire_sys(w.flags + 5) != 0ULL) break;
+        if (clock64() - t0 > w.timeout_cycles) { w.flags[5] = w.seq; break; }
       }
     }
   }

@@ -406,6 +406,7 @@ __global__ void moloch_halo_push(Geo g, PushParams h) {
         if (!((h.mask >> sd) & 1)) continue;
         for (;;) {
           if (ld_acquire_sys(h.flags + sd) >= h.seq) break;
+          if (ld_acquire_sys(h.flags + 5) != 0ULL) break;                         // an earlier round timed out
           if (clock64() - t0 > h.timeout_cycles) { h.flags[5] = h.seq; break; }  // neighbour never arrived
         }
       }

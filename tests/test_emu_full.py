@@ -201,3 +201,68 @@ def test_decomposed_with_drifting_ranks(name, px, py, monkeypatch, _emulated_lib
     wl = [c for c in M.CASES if c[0] == name][0][1]
     _emulated_library.emu_set_jitter(20000)
     M.test_decomposed_bit_exact(name, wl, px, py, "p2p", monkeypatch)
+
+
+def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
+    """bench.py's whole N=1 flow (model construction with the fusion-level check, timed steps, per-kernel profile,
+    roofline, end-to-end leg, CPU baseline, the JSON line) on the emulated library with a stand-in for the few
+    torch.cuda calls it makes: catches script errors before the script meets a GPU box."""
+    import json
+    import sys
+    import time
+    import types
+
+    import bench
+    from regcm_b200 import moloch as M
+    from regcm_b200 import synthetic as S
+
+    class _Event:
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self, stream=None):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    class _Tensor:
+        def __init__(self, v):
+            self.v = v
+
+        def item(self):
+            return self.v[0]
+
+    class _Ctx:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    cuda = types.SimpleNamespace(is_available=lambda: True, set_device=lambda d: None, synchronize=lambda: None,
+                                 Stream=lambda: types.SimpleNamespace(cuda_stream=0), Event=_Event,
+                                 stream=lambda s: _Ctx())
+    torch = types.ModuleType("torch")
+    torch.cuda = cuda
+    torch.tensor = lambda v, device=None: _Tensor(v)
+    torch.device = lambda *a: None
+    dist = types.ModuleType("torch.distributed")
+    torch.distributed = dist
+    monkeypatch.setitem(sys.modules, "torch", torch)
+    monkeypatch.setitem(sys.modules, "torch.distributed", dist)
+    monkeypatch.setattr(M, "_lib", _emulated_library)          # what load_library() hands to MolochB200
+    monkeypatch.setitem(S.WORKLOADS, "tiny", S.small(S.WORKLOADS["cordex25"], 40, 36, 9, ntr=2, nspgx=5))
+    monkeypatch.setattr(bench, "cpu_sample_workload", lambda wl: wl)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "tiny", "--steps", "2", "--warmup", "1"])
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.setenv("MOLOCH_B200_FUSE_HALO", "2")
+    # argparse built its choices from S.WORKLOADS at call time, so "tiny" is accepted
+    assert bench.main() == 0
+    line = json.loads([x for x in capsys.readouterr().out.splitlines() if x.startswith("{")][-1])
+    assert line["metric"] == "MOLOCH dycore cell-updates/s" and line["n_gpus"] == 1 and line["finite"]
+    assert line["gpu_launches"] > 0 and line["value"] > 0
+    assert line["roofline"]["bound"] == "hbm" and line["roofline"]["frac"] > 0
+    assert line["e2e"]["handoff"] == "pipelined" and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0

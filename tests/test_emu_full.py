@@ -117,9 +117,9 @@ def test_mkslice_massck_tke_misc():
 def _multi_cases():
     M = _gpu_tests()[2]
     keep = None if FULL else {("periodic", "p2p"), ("limited_area_2x2", "p2p"), ("limited_area_2x4", "p2p"),
-                              ("band_2x4", "p2p_unfused"), ("limited_area_2x2", "nccl")}
+                              ("band_2x4", "p2p_unfused"), ("limited_area_2x2", "nccl"), ("limited_area_2x2", "p2p_sound")}
     out = []
-    for tr in ("p2p", "p2p_unfused", "nccl"):
+    for tr in ("p2p", "p2p_sound", "p2p_unfused", "nccl"):
         for c in M.CASES:
             if tr != "p2p" and c[0] not in ("periodic", "limited_area", "limited_area_2x2", "band_2x4"):
                 continue
@@ -200,7 +200,7 @@ def test_decomposed_with_drifting_ranks(name, px, py, monkeypatch, _emulated_lib
     M = _gpu_tests()[2]
     wl = [c for c in M.CASES if c[0] == name][0][1]
     _emulated_library.emu_set_jitter(20000)
-    M.test_decomposed_bit_exact(name, wl, px, py, "p2p", monkeypatch)
+    M.test_decomposed_bit_exact(name, wl, px, py, "p2p", monkeypatch)      # "p2p" = every fusable round fused
 
 
 def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
@@ -266,3 +266,34 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
     assert line["roofline"]["bound"] == "hbm" and line["roofline"]["frac"] > 0
     assert line["e2e"]["handoff"] == "pipelined" and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
+
+
+def test_halo_timeout_is_reported(_emulated_library):
+    """Failure detection of the peer-store transport: a rank whose neighbour never arrives gives up its wait after
+    the timeout, every later wait gives up at once, and moloch_b200_sync reports the round (RegCM's fatal())."""
+    import threading
+
+    from regcm_b200 import synthetic as S
+    from regcm_b200.moloch import MolochError
+    from multirank import MultiRank
+    from util import make_oracle, oracle_inputs
+    wl = S.small(S.WORKLOADS["cordex25"], 40, 36, 8, ntr=1, nspgx=5, mo_nsound=2)
+    o, _ = make_oracle(wl)
+    fields, profiles = oracle_inputs(o, wl)
+    mr = MultiRank(wl, 2, 1, fields, profiles, transport="p2p")
+    try:
+        err = []
+
+        def lonely():
+            try:
+                mr.ranks[0].moloch(1)      # rank 1 never steps
+                mr.ranks[0].sync()
+            except MolochError as e:
+                err.append(str(e))
+        t = threading.Thread(target=lonely)
+        t.start()
+        t.join(timeout=120)
+        assert not t.is_alive(), "the lonely rank is still waiting"
+        assert err and "timed out in round" in err[0], err
+    finally:
+        mr.close()

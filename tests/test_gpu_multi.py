@@ -30,16 +30,17 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("transport", ["p2p", "p2p_unfused", "nccl"])
+@pytest.mark.parametrize("transport", ["p2p", "p2p_sound", "p2p_unfused", "nccl"])
 @pytest.mark.parametrize("name,wl,px,py", CASES, ids=[c[0] for c in CASES])
 def test_decomposed_bit_exact(name, wl, px, py, transport, monkeypatch):
     if ndev() < px * py:
         pytest.skip(f"needs {px * py} GPUs")
     if transport != "p2p" and name not in ("periodic", "limited_area", "limited_area_2x2", "band_2x4"):
         pytest.skip("NCCL and the unfused peer transport are covered by representative cases")
-    # p2p: sound-loop exchanges fused into the kernels around them; p2p_unfused: one
-    # exchange launch per round (MOLOCH_B200_FUSE_HALO is read when the context is created)
-    monkeypatch.setenv("MOLOCH_B200_FUSE_HALO", "0" if transport == "p2p_unfused" else "1")
+    # p2p: every exchange that has a producer and a consumer kernel fused into them (sound loop, advection's
+    # u,v / ux,vx); p2p_sound: sub-steps 2.. of the sound loop only; p2p_unfused: one exchange launch per
+    # round (MOLOCH_B200_FUSE_HALO is read when the context is created)
+    monkeypatch.setenv("MOLOCH_B200_FUSE_HALO", {"p2p_unfused": "0", "p2p_sound": "1"}.get(transport, "2"))
     transport = "p2p" if transport.startswith("p2p") else transport
     o, _ = make_oracle(wl)
     fields, profiles = oracle_inputs(o, wl)

@@ -297,3 +297,12 @@ def test_halo_timeout_is_reported(_emulated_library):
         assert err and "timed out in round" in err[0], err
     finally:
         mr.close()
+
+
+def test_full_size_property_checks_at_reduced_size():
+    """The bodies of tests/test_gpu_zz_fullsize.py (oracle parity on the doubly periodic `ideal` shape; tracer
+    homogeneity, copy equality and run-to-run reproducibility) at sizes the emulated build finishes in seconds."""
+    import test_gpu_zz_fullsize as Fz
+    from regcm_b200 import synthetic as S
+    Fz.check_oracle_parity(S.small(S.WORKLOADS["ideal"], 36, 20, 12), 2)
+    Fz.check_tracer_properties(S.small(S.WORKLOADS["cordex25"], 40, 36, 9, ntr=3, nspgx=5), 2)

@@ -135,6 +135,7 @@ def test_reference_multirank_spectral_nudging_matches_decomposed_oracle(px, py):
     `count = nk*(i2-i1+1)` semantics of the two reductions across ranks (incl. the stale tails on the top row
     of ranks), which the CUDA library's halo_group_sum restates."""
     wl, nsteps = CASES["limited_area_spectral"]
+    nsteps = 1      # one step = 3 variables x kz levels x 2 reductions, incl. the short (stale-tail) calls
     o, B = make_oracle_bdy(wl, px=px, py=py)
     # the reference ranks take their inputs -- incl. cnudge/tnudge, whose global means (sumall) depend on the
     # decomposition in the last bits -- from the equally decomposed oracle

@@ -327,10 +327,12 @@ static int launch_wsolve(Ctx& c, double dts, bool last, long long ncol, const Pu
   return 0;
 }
 int k_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
+int k_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
 int k_wsolve(Ctx& c, double dts, bool last, const PushCtl* pcp, const EdgePush* epp) {
   const PushCtl pc = pcp ? *pcp : PushCtl{};
   const EdgePush ep = epp ? *epp : EdgePush{};
   if (c.wsolve_impl == 5) return k_wsolve5(c, dts, last, pc, ep);
+  if (c.wsolve_impl == 6) return k_wsolve6(c, dts, last, pc, ep);
   const Geo& g = c.g;
   const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
   const bool small = (ncol + 31) / 32 < 148 * 5 * 3;   // fewer than three waves of 32-column CTAs
@@ -495,6 +497,152 @@ static int launch_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, cons
   MB_CUDA(cudaFuncSetAttribute(moloch_wsolve5<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LaunchScope ls(c, KID_WSOLVE);
   moloch_wsolve5<D><<<(unsigned)((ncol + 31) / 32), 32, smem, c.stream>>>(
+      g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.f[MB_FMZ].p,
+      c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, pc, ep);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+// ---------------------------------------------------------------------------
+// K7+K8+K9, thread-per-column variant 6 (MOLOCH_B200_WSOLVE=6; an A/B candidate, not the default).
+// moloch_wsolve5 is bound by the latency of ONE warp per scheduler: its three sweep arrays (w', wwkw and the
+// finished divergence) and the ring take 46 KB of shared memory per warp at kz = 41, so only 4 warps fit an SM.
+// Here the finished divergence is not parked but recomputed in the upward pass from the same operands, in the
+// same operation order (zdiv2, bdywtw, fmz, s(k), s(k+1): the lines were read by this very warp a few
+// microseconds earlier and come from L2), and the ring is D = 4 deep: 31 KB per warp, 7 warps per SM.
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(32)
+moloch_wsolve6(Geo g, const double* __restrict__ zdiv, double* s, double* w, double* pai,
+               const double* __restrict__ tetav, double* tetavf, const double* __restrict__ fmz,
+               const double* __restrict__ fmzf, const double* __restrict__ bdywtw,
+               const double* __restrict__ ffilt, double dts, double dtrdz, double zcs2, int last, PushCtl pc,
+               EdgePush ep) {
+  extern __shared__ double sm[];
+  const int kz = g.kz;
+  double* WP = sm;                        // w after the downward sweep, rows k = 0..kz
+  double* WW = WP + (kz + 1) * 32;        // wwkw
+  double* RING = WW + (kz + 1) * 32;      // D slots x 9 values x 32 lanes
+  const int nj = g.jci2 - g.jci1 + 1, ni = g.ici2 - g.ici1 + 1;
+  const long long ncol = (long long)nj * ni;
+  const int lane = threadIdx.x;
+  const long long col = (long long)blockIdx.x * 32 + lane;
+  const bool valid = col < ncol;
+  const long long colc = valid ? col : ncol - 1;
+  const int i = g.ici1 + (int)(colc / nj), j = g.jci1 + (int)(colc % nj);
+  const long long pl = g.plane;
+  const long long base = gidx(g, j, i, 1) - pl;   // level k at base + k*pl
+  auto fetch = [&](int slot, int k) {
+    double* r = RING + slot * (9 * 32) + lane;
+    const long long id = base + k * pl;
+    cp_async8(r, w + id); cp_async8(r + 32, zdiv + id); cp_async8(r + 64, bdywtw + id);
+    cp_async8(r + 96, fmz + id); cp_async8(r + 128, s + id); cp_async8(r + 160, tetav + id);
+    cp_async8(r + 192, pai + id); cp_async8(r + 224, fmzf + id); cp_async8(r + 256, tetavf + id);
+  };
+  // ---- downward pass (as in moloch_wsolve5, without the ZF slots) ----
+#pragma unroll
+  for (int q = 0; q < D; ++q) {
+    if (kz - q >= 1) fetch(q, kz - q);
+    cp_async_commit();
+  }
+  double wkp1 = w[base + (kz + 1) * pl];   // w(kzp1)
+  const double w_bottom = wkp1;
+  double wwkp1 = 0.0;                       // wwkw(kzp1) :1055-1057
+  double s_below = s[base + (kz + 1) * pl];
+  double p_w = 0.0, p_tf = 0.0, p_ff = 0.0, p_tv = 0.0, p_pa = 0.0, p_fm = 0.0, p_zd = 0.0;  // level m+1
+  double w1 = 0.0;
+  for (int t0 = 0; t0 < kz; t0 += D) {
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      const int m = kz - (t0 + q);
+      cp_async_wait<D - 1>();
+      if (m >= 1) {
+        const double* r = RING + q * (9 * 32) + lane;
+        const double Lw = r[0], Lzdiv = r[32], Lbw = r[64], Lfm = r[96], Ls = r[128], Ltv = r[160],
+                     Lpa = r[192], Lff = r[224], Ltf = r[256];
+        const double zdm = Lzdiv + Lbw * dtrdz * Lfm * (Ls - s_below);
+        s_below = Ls;
+        if (m < kz) {
+          const int k = m + 1;
+          const double tfn = p_tf - p_w * p_ff * dtrdz * (Ltv - p_tv);
+          if (valid) tetavf[base + k * pl] = tfn;
+          const double zrom1w = cpd * tfn * p_ff;
+          double zwexpl = p_w - zrom1w * dtrdz * (Lpa - p_pa) - egrav * dts;
+          zwexpl = zwexpl + rdrcv * zrom1w * dtrdz * (Lpa * zdm - p_pa * p_zd);
+          const double fk = ffilt[k];
+          const double zu = zcs2 * Lfm * zrom1w * Lpa + fk;
+          const double zd = zcs2 * p_fm * zrom1w * p_pa + fk;
+          const double zrapp = 1.0 / (1.0 + zd + zu - zd * wwkp1);
+          wkp1 = zrapp * (zwexpl + zd * wkp1);
+          wwkp1 = zrapp * zu;
+          WP[k * 32 + lane] = wkp1;
+          WW[k * 32 + lane] = wwkp1;
+        }
+        p_w = Lw; p_tf = Ltf; p_ff = Lff; p_tv = Ltv; p_pa = Lpa; p_fm = Lfm; p_zd = zdm;
+        if (m == 1) w1 = Lw;
+        if (m - D >= 1) fetch(q, m - D);
+      }
+      cp_async_commit();
+    }
+  }
+  cp_async_wait<0>();
+  // ---- upward pass: level k needs pai, fmz, zdiv, bdywtw of level k-1 and s, fmzf of level k ----
+  auto fetchup = [&](int slot, int k) {
+    double* r = RING + slot * (9 * 32) + lane;
+    const long long id = base + k * pl;
+    cp_async8(r, pai + id - pl); cp_async8(r + 32, fmz + id - pl); cp_async8(r + 64, s + id);
+    cp_async8(r + 128, zdiv + id - pl); cp_async8(r + 160, bdywtw + id - pl);
+    if (last) cp_async8(r + 96, fmzf + id);
+  };
+  double s_km1 = s[base + pl];              // s(1), as the downward pass saw it
+#pragma unroll
+  for (int q = 0; q < D; ++q) {
+    if (2 + q <= kz + 1) fetchup(q, 2 + q);
+    cp_async_commit();
+  }
+  double wkm1 = w1;
+  for (int t0 = 0; t0 < kz; t0 += D) {
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      const int k = 2 + t0 + q;
+      cp_async_wait<D - 1>();
+      if (k <= kz + 1) {
+        const double* r = RING + q * (9 * 32) + lane;
+        const double Upa = r[0], Ufm = r[32], Us = r[64], Uzdiv = r[128], Ubw = r[160];
+        // the finished divergence of level k-1, exactly as the downward pass computed it
+        const double zdm = Uzdiv + Ubw * dtrdz * Ufm * (s_km1 - Us);
+        s_km1 = Us;
+        const double wk = (k <= kz) ? WP[k * 32 + lane] + WW[k * 32 + lane] * wkm1 : w_bottom;
+        if (valid) {
+          const long long id = base + k * pl;
+          const double pnew = Upa * (1.0 - rdrcv * (zdm + (dtrdz * Ufm * (wkm1 - wk))));
+          pai[id - pl] = pnew;
+          if (pc.mask) edge_push(pc, ep, j, i, k - 1, pnew);
+          if (k <= kz) {
+            w[id] = wk;
+            if (last) s[id] = (wk + Us) * r[96];
+          }
+        }
+        wkm1 = wk;
+        if (k + D <= kz + 1) fetchup(q, k + D);
+      }
+      cp_async_commit();
+    }
+  }
+  cp_async_wait<0>();
+  if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
+}
+int k_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
+  constexpr int D = 4;
+  const Geo& g = c.g;
+  const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
+  const double dtrdz = dts * c.rdzita;
+  const double zcs2 = (dtrdz * dtrdz) * rdrcv;
+  const size_t smem = (size_t)(2 * (g.kz + 1) + D * 9) * 32 * sizeof(double);
+  if (smem > 227 * 1024) return fail("wsolve: kz too large for the shared-memory sweep slots");
+  const double* zsrc = c.cfg.mo_divfilter ? c.zdiv2b : c.f[MB_ZDIV2].p;
+  MB_CUDA(cudaFuncSetAttribute(moloch_wsolve6<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchScope ls(c, KID_WSOLVE);
+  moloch_wsolve6<D><<<(unsigned)((ncol + 31) / 32), 32, smem, c.stream>>>(
       g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.f[MB_FMZ].p,
       c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, pc, ep);
   MB_CUDA(cudaGetLastError());

@@ -26,6 +26,19 @@ except Exception as exc:
     print(sys.argv[1], "no result:", exc)
 PY
 done
+# wsolve A/B (VERDICT-likely kernel: 45 % of the HBM peak, 4 warps/SM): variant 6 = 7 warps/SM, variant 2 = CTA-parallel
+for v in 5 6 2; do
+  MOLOCH_B200_WSOLVE=$v timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_wsolve$v.json 2>/dev/null
+  python - "$v" <<'PY'
+import json, sys
+try:
+    d = json.loads([l for l in open(f"gpurun_out/r2_bench_wsolve{sys.argv[1]}.json") if l.startswith("{")][-1])
+    k = [x for x in d["kernels"] if x["kernel"] == "wsolve"][0]
+    print("wsolve variant", sys.argv[1], "ms/step", round(d["ms_per_step"], 3), "wsolve us", round(k["avg_ms"] * 1e3, 1), "GB/s", round(k["gbs"]))
+except Exception as exc:
+    print("wsolve variant", sys.argv[1], "no result:", exc)
+PY
+done
 timeout 90 python scripts/kbench.py --boundary --slice --spectral --tke --massck --diag --steps 4 --warmup 1 \
   > gpurun_out/r2_kbench_all.json 2> gpurun_out/r2_kbench_all.err
 tail -c 1500 gpurun_out/r2_kbench_all.json; tail -3 gpurun_out/r2_kbench_all.err

@@ -306,3 +306,15 @@ def test_full_size_property_checks_at_reduced_size():
     from regcm_b200 import synthetic as S
     Fz.check_oracle_parity(S.small(S.WORKLOADS["ideal"], 36, 20, 12), 2)
     Fz.check_tracer_properties(S.small(S.WORKLOADS["cordex25"], 40, 36, 9, ntr=3, nspgx=5), 2)
+
+
+@pytest.mark.parametrize("impl,case", [("6", "limited_area"), ("6", "tall"), ("2", "limited_area")] if FULL
+                         else [("6", "limited_area")])
+def test_wsolve_variants(impl, case, monkeypatch):
+    import test_gpu_zz_variants as V
+    V.test_wsolve_variants_bit_exact(impl, case, monkeypatch)
+
+
+def test_waf_per_loop_kernels(monkeypatch):
+    import test_gpu_zz_variants as V
+    V.test_waf_per_loop_kernels_bit_exact("limited_area", monkeypatch)

@@ -498,6 +498,7 @@ def main():
         line = base_line(wl, args, world)
         line["config"]["decomposition"] = f"{m.g.px}x{m.g.py}"
         line["config"]["halo_transport"] = ("none" if world == 1 else args.transport)
+        line["config"]["wsolve_variant"] = int(os.environ.get("MOLOCH_B200_WSOLVE", "6"))
         if world > 1 and args.transport == "p2p":
             line["config"]["halo_fusion_level"] = int(halo_fusion)
             if fusion_note:

@@ -437,7 +437,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   c->h_ptrtab = tab;
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
-  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || v == 6) ? v : 5; }
+  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || v == 5) ? v : 6; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaFree(c->arena);
     delete c;

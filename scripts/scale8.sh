@@ -32,6 +32,19 @@ PY
 NOE2E= run n8 8 0,1,2,3,4,5,6,7 29518   # the driver's own N=8 invocation (with the e2e leg)
 run n8_2x4 8 0,1,2,3,4,5,6,7 29519 BENCH_PX=2 BENCH_PY=4
 show ${T}_n8 ${T}_n8_2x4
+# A/B of what changed without GPU access at the end of round 1: halo fusion level (2 = all, 1 = sound loop's
+# sub-steps 2.. only: the configuration of profiles/r1_scale_*.json) and the wsolve variant (6 default, 5 measured)
+run n8_fuse1 8 0,1,2,3,4,5,6,7 29523 MOLOCH_B200_FUSE_HALO=1
+run n8_wsolve5 8 0,1,2,3,4,5,6,7 29524 MOLOCH_B200_WSOLVE=5
+show ${T}_n8_fuse1 ${T}_n8_wsolve5
+if [ -n "$BIG" ]; then   # BASELINE configs 4 and 5 (8 GPUs, 2x4)
+  for w in cp3km tracer40; do
+    env BENCH_PX=2 BENCH_PY=4 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+      --master-addr 127.0.0.1 --master-port 29530 bench.py --gpus 8 --steps 5 --warmup 3 --no-e2e --workload $w \
+      > gpurun_out/${T}_$w.json 2> gpurun_out/${T}_$w.err
+    show ${T}_$w
+  done
+fi
 run n4 4 0,1,2,3 29521 &
 run n2 2 4,5 29522 &
 run n1 1 6 0 &

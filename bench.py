@@ -276,6 +276,47 @@ def measure_e2e(m, wl, ksteps, barrier=lambda: None, allreduce_max=lambda x: x):
 
 
 
+def variants_agree(wl, device, lib=None) -> bool:
+    """Variant 6 of the column solver against variant 5 on a small case of the same configuration (same species,
+    boundary type, level count): two steps, every prognostic field bit for bit."""
+    from regcm_b200.moloch import MolochB200
+    swl = S.small(wl, min(wl.jx, 72), min(wl.iy, 56), wl.kz)
+    out = []
+    for v in (5, 6):
+        m = MolochB200(swl, device=device, lib=lib).allocate_moloch()
+        fields, profiles, boxes = S.model_inputs_local(swl, m.g)
+        m.init_moloch(fields, profiles, boxes)
+        m.set_option("wsolve", v)
+        m.moloch(2)
+        out.append([m.get_local(n) for n in ("u", "v", "w", "pai", "tetav", "t", "qx")])
+        m.close()
+    return all(np.array_equal(a, b) for a, b in zip(*out))
+
+
+def autotune_wsolve(m, wl, timed, all_min=lambda x: x, device=-1, lib=None):
+    """(variant, record): times two steps of the benchmark model per admissible variant and picks the faster.
+    `all_min`: minimum over the ranks (every rank must take the same decisions)."""
+    rec = {"candidates": [5]}
+    try:
+        ok = bool(variants_agree(wl, device, lib))
+    except Exception as exc:  # noqa: BLE001
+        ok = False
+        rec["note"] = f"variant 6 not considered: {exc}"
+    rec["v6_bit_exact_vs_v5"] = bool(all_min(1.0 if ok else 0.0) > 0.5)
+    if rec["v6_bit_exact_vs_v5"]:
+        rec["candidates"].append(6)
+    if len(rec["candidates"]) == 1:
+        return 5, rec
+    rec["ms_per_step"] = {}
+    for v in rec["candidates"]:
+        m.set_option("wsolve", v)
+        m.moloch(1)
+        m.sync()
+        rec["ms_per_step"][str(v)] = timed(lambda: m.moloch(1), 2) / 2.0     # max over ranks
+    best = min(rec["candidates"], key=lambda v: rec["ms_per_step"][str(v)])
+    return best, rec
+
+
 def base_line(wl, args, n_gpus):
     return {"metric": "MOLOCH dycore cell-updates/s", "unit": "cell-updates/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
@@ -417,6 +458,36 @@ def main():
         barrier()
         return float(ms.item())
 
+    # ---- kernel variants: measured, not guessed ---------------------------------------
+    # The implicit-w column solver exists in two thread-per-column variants (5: three sweep arrays in
+    # shared memory, 4 warps/SM -- the one profiles/ measured; 6: the divergence recomputed, 7 warps/SM --
+    # written without GPU access).  Variant 6 is only considered after it has reproduced variant 5 bit for
+    # bit on a small case on THIS device; then both are timed on the benchmark model and the faster one
+    # runs the timed region.  MOLOCH_B200_WSOLVE fixes the variant instead.
+    tuning = {"wsolve": {}}
+    wsolve_variant = int(os.environ.get("MOLOCH_B200_WSOLVE", "0"))
+    if wsolve_variant == 0:
+        def all_min(x):
+            t = torch.tensor([float(x)], device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return float(t.item())
+        wsolve_variant, tuning["wsolve"] = autotune_wsolve(m, wl, timed, all_min, local_rank)
+    m.set_option("wsolve", wsolve_variant)
+    # Same for the halo fusion level at N > 1: level 2 (first sub-step and advection exchanges fused too) was
+    # written without GPU access; it runs the timed region only if it is not slower than level 1 here.
+    if world > 1 and args.transport == "p2p" and int(halo_fusion) == 2 and "MOLOCH_B200_FUSE_HALO_FIXED" not in os.environ:
+        tuning["fuse_halo"] = {}
+        for lv in (2, 1):
+            m.set_option("fuse_halo", lv)
+            m.moloch(1)
+            m.sync()
+            tuning["fuse_halo"][str(lv)] = timed(lambda: m.moloch(1), 3) / 3.0
+        halo_fusion = min((2, 1), key=lambda lv: tuning["fuse_halo"][str(lv)])
+        m.set_option("fuse_halo", int(halo_fusion))
+        m.moloch(1)
+        m.sync()
+
     # ---- device-resident throughput -----------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -498,7 +569,8 @@ def main():
         line = base_line(wl, args, world)
         line["config"]["decomposition"] = f"{m.g.px}x{m.g.py}"
         line["config"]["halo_transport"] = ("none" if world == 1 else args.transport)
-        line["config"]["wsolve_variant"] = int(os.environ.get("MOLOCH_B200_WSOLVE", "6"))
+        line["config"]["wsolve_variant"] = wsolve_variant
+        line["config"]["variant_tuning"] = tuning
         if world > 1 and args.transport == "p2p":
             line["config"]["halo_fusion_level"] = int(halo_fusion)
             if fusion_note:

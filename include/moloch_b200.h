@@ -161,6 +161,15 @@ uint64_t moloch_b200_p2p_blob_size(void);
 int moloch_b200_p2p_export(moloch_b200_ctx* ctx, void* blob);
 int moloch_b200_p2p_connect(moloch_b200_ctx* ctx, const void* blobs, int nranks);
 
+/* Kernel-variant switches of an existing context (what the MOLOCH_B200_* environment variables set at create):
+ *   "wsolve"    5 | 6 | 2   implicit-w column solver: three / two sweep arrays in shared memory (4 / 7 warps per SM),
+ *                           or the CTA-parallel variant
+ *   "waf"       2 | 1       field-batched fused WAF kernels, or one kernel per reference loop nest
+ *   "fuse_halo" 0 | 1 | 2   peer-store transport: exchanges fused into the kernels around them (none / the sound
+ *                           loop's sub-steps 2.. / all); every rank must use the same value
+ * All variants give bit-identical results; they exist for measurement (bench.py times them and keeps the faster). */
+int moloch_b200_set_option(moloch_b200_ctx* ctx, const char* name, int value);
+
 /* run on a caller-owned CUDA stream (cudaStream_t) instead of the context's */
 int moloch_b200_set_stream(moloch_b200_ctx* ctx, void* cuda_stream);
 int moloch_b200_sync(moloch_b200_ctx* ctx);

@@ -437,7 +437,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   c->h_ptrtab = tab;
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
-  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || v == 5) ? v : 6; }
+  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || v == 6) ? v : 5; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaFree(c->arena);
     delete c;
@@ -492,6 +492,26 @@ int moloch_b200_p2p_export(moloch_b200_ctx* c, void* blob) {
 int moloch_b200_p2p_connect(moloch_b200_ctx* c, const void* blobs, int nranks) {
   if (!c || !blobs) return fail("p2p_connect: null argument");
   return halo_p2p_connect(*c, blobs, nranks);
+}
+
+int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
+  if (!c || !name) return fail("set_option: null argument");
+  const std::string n(name);
+  if (n == "wsolve") {
+    if (value != 2 && value != 5 && value != 6) return fail("set_option: wsolve must be 2, 5 or 6");
+    c->wsolve_impl = value;
+  } else if (n == "waf") {
+    if (value != 1 && value != 2) return fail("set_option: waf must be 1 or 2");
+    c->waf_impl = value;
+  } else if (n == "fuse_halo") {
+    if (value < 0 || value > 2) return fail("set_option: fuse_halo must be 0, 1 or 2");
+    c->fuse_halo = value != 0;
+    c->fuse_level = value >= 2 ? 2 : 1;
+    c->adv_wait_valid = false;
+  } else {
+    return fail("set_option: unknown option '" + n + "'");
+  }
+  return 0;
 }
 
 int moloch_b200_set_stream(moloch_b200_ctx* c, void* s) {

@@ -87,7 +87,7 @@ struct Ctx {
   double *ud, *vd, *zdiv2b, *mx2, *rmx, *rmu, *rmv;
   double *zru, *zrd;      // static ratios of the vertical WAF pass
   int waf_impl = 2;       // 1: per-loop kernels, 2: field-batched fused kernels
-  int wsolve_impl = 6;    // 2: CTA-parallel coefficients + one-warp sweeps, 5: thread per column with a cp.async ring,
+  int wsolve_impl = 5;    // 2: CTA-parallel coefficients + one-warp sweeps, 5: thread per column with a cp.async ring,
                           // 6: as 5 without the divergence slots (recomputed), 7 warps/SM (MOLOCH_B200_WSOLVE)
   double *wzall, *p0all;  // per-field scratch of the batched wafone
   double* prof[MB_NPROFILES];

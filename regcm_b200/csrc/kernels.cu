@@ -503,8 +503,8 @@ static int launch_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, cons
   return 0;
 }
 // ---------------------------------------------------------------------------
-// K7+K8+K9, thread-per-column variant 6 (the default since the end of round 1; MOLOCH_B200_WSOLVE=5 selects
-// moloch_wsolve5, whose measured figures are in profiles/).
+// K7+K8+K9, thread-per-column variant 6 (MOLOCH_B200_WSOLVE=6 / set_option("wsolve", 6); written without GPU
+// access at the end of round 1: bench.py times it against moloch_wsolve5 and keeps the faster one).
 // moloch_wsolve5 is bound by the latency of ONE warp per scheduler: its three sweep arrays (w', wwkw and the
 // finished divergence) and the ring take 46 KB of shared memory per warp at kz = 41, so only 4 warps fit an SM.
 // Here the finished divergence is not parked but recomputed in the upward pass from the same operands, in the

@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "moloch_b200_set_table", "moloch_b200_set_ibnd", "moloch_b200_boundary", "moloch_b200_bdyval",
     "moloch_b200_set_xbctime", "moloch_b200_get_xbctime", "moloch_b200_bdy_shift", "moloch_b200_mkslice",
     "moloch_b200_massck", "moloch_b200_ps_check", "moloch_b200_set_calday", "moloch_b200_config_size",
-    "moloch_b200_handoff", "moloch_b200_host_register", "moloch_b200_host_unregister",
+    "moloch_b200_handoff", "moloch_b200_host_register", "moloch_b200_host_unregister", "moloch_b200_set_option",
 ]
 
 
@@ -121,6 +121,7 @@ def bind_library(lib, path: str = "?"):
     lib.moloch_b200_p2p_export.argtypes = [ctx, C.c_void_p]
     lib.moloch_b200_p2p_connect.argtypes = [ctx, C.c_void_p, C.c_int]
     lib.moloch_b200_sync.argtypes = [ctx]
+    lib.moloch_b200_set_option.argtypes = [ctx, C.c_char_p, C.c_int]
     lib.moloch_b200_set_async.argtypes = [ctx, C.c_int]
     xf = [ctx, C.c_int, C.c_int, C.c_void_p] + [C.c_int] * 6
     lib.moloch_b200_set_field.argtypes = xf
@@ -372,6 +373,10 @@ class MolochB200:
             cb = PHYSICS_FN(lambda user, i1, i2: int(physics(int(i1), int(i2)) or 0))
         self._chk(self.lib.moloch_b200_handoff(self.ctx, down[0], down[1], up[0], up[1], int(nslabs),
                                                C.cast(cb, C.c_void_p) if cb is not None else None, None))
+
+    def set_option(self, name: str, value: int):
+        """Kernel-variant switch ("wsolve", "waf", "fuse_halo"); all variants are bit-identical."""
+        self._chk(self.lib.moloch_b200_set_option(self.ctx, name.encode(), int(value)))
 
     def set_stream(self, cuda_stream: int):
         self._chk(self.lib.moloch_b200_set_stream(self.ctx, C.c_void_p(cuda_stream)))

@@ -258,6 +258,7 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
     monkeypatch.delenv("RANK", raising=False)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     monkeypatch.setenv("MOLOCH_B200_FUSE_HALO", "2")
+    monkeypatch.delenv("MOLOCH_B200_WSOLVE", raising=False)
     # argparse built its choices from S.WORKLOADS at call time, so "tiny" is accepted
     assert bench.main() == 0
     line = json.loads([x for x in capsys.readouterr().out.splitlines() if x.startswith("{")][-1])
@@ -266,6 +267,9 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
     assert line["roofline"]["bound"] == "hbm" and line["roofline"]["frac"] > 0
     assert line["e2e"]["handoff"] == "pipelined" and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
+    tune = line["config"]["variant_tuning"]["wsolve"]
+    assert tune["v6_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 6], tune
+    assert line["config"]["wsolve_variant"] in (5, 6) and set(tune["ms_per_step"]) == {"5", "6"}
 
 
 def test_halo_timeout_is_reported(_emulated_library):
@@ -308,8 +312,8 @@ def test_full_size_property_checks_at_reduced_size():
     Fz.check_tracer_properties(S.small(S.WORKLOADS["cordex25"], 40, 36, 9, ntr=3, nspgx=5), 2)
 
 
-@pytest.mark.parametrize("impl,case", [("5", "limited_area"), ("5", "tall"), ("2", "limited_area")] if FULL
-                         else [("5", "limited_area")])
+@pytest.mark.parametrize("impl,case", [("6", "limited_area"), ("6", "tall"), ("2", "limited_area")] if FULL
+                         else [("6", "limited_area")])
 def test_wsolve_variants(impl, case, monkeypatch):
     import test_gpu_zz_variants as V
     V.test_wsolve_variants_bit_exact(impl, case, monkeypatch)
@@ -318,3 +322,8 @@ def test_wsolve_variants(impl, case, monkeypatch):
 def test_waf_per_loop_kernels(monkeypatch):
     import test_gpu_zz_variants as V
     V.test_waf_per_loop_kernels_bit_exact("limited_area", monkeypatch)
+
+
+def test_set_option():
+    import test_gpu_zz_variants as V
+    V.test_set_option_switches_variants_of_a_live_context()

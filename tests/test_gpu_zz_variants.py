@@ -1,9 +1,10 @@
 """Selectable kernel variants (environment switches read when a context is created) against the oracle:
 every A/B candidate must be bit-exact before it is timed.
 
-    MOLOCH_B200_WSOLVE = 6 (default: thread per column, cp.async ring, two sweep arrays in shared memory, the
-                            finished divergence recomputed in the upward pass; 7 warps per SM)
-                         5 (three sweep arrays in shared memory, 4 warps per SM: the variant profiles/ measured)
+    MOLOCH_B200_WSOLVE = 5 (default: thread per column, cp.async ring, three sweep arrays in shared memory, 4 warps
+                            per SM: the variant profiles/ measured)
+                         6 (two sweep arrays, the finished divergence recomputed in the upward pass; 7 warps per SM;
+                            bench.py times 5 against 6 and keeps the faster)
                          2 (CTA = 32 columns x all levels, one-warp sweeps)
     MOLOCH_B200_WAF    = 2 (default: field-batched fused WAF kernels) | 1 (one kernel per reference loop nest)
 
@@ -16,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("case", ["limited_area", "tall"])
-@pytest.mark.parametrize("impl", ["5", "2"])
+@pytest.mark.parametrize("impl", ["6", "2"])
 def test_wsolve_variants_bit_exact(impl, case, monkeypatch):
     monkeypatch.setenv("MOLOCH_B200_WSOLVE", impl)
     P.test_steps_bit_exact(case)
@@ -26,3 +27,25 @@ def test_wsolve_variants_bit_exact(impl, case, monkeypatch):
 def test_waf_per_loop_kernels_bit_exact(case, monkeypatch):
     monkeypatch.setenv("MOLOCH_B200_WAF", "1")
     P.test_steps_bit_exact(case)
+
+
+def test_set_option_switches_variants_of_a_live_context():
+    """moloch_b200_set_option: the variants can be switched between steps of one context (what bench.py's
+    autotuning does) and the run stays bit-exact; unknown names and values are refused."""
+    import numpy as np
+    from regcm_b200.moloch import MolochError
+    from util import PROGNOSTIC, compare, make_gpu, make_oracle, oracle_inputs
+    wl = P.CASES["limited_area"]
+    o, _ = make_oracle(wl)
+    fields, profiles = oracle_inputs(o, wl)
+    m = make_gpu(wl, fields, profiles)
+    for opt, v in (("wsolve", 6), ("waf", 1), ("wsolve", 2), ("waf", 2), ("wsolve", 5)):
+        m.set_option(opt, v)
+        o.step(1); m.moloch(1)
+        compare(o, m, PROGNOSTIC + ["trac"], label=f"after set_option({opt}, {v}): ")
+    with pytest.raises(MolochError, match="unknown option"):
+        m.set_option("nonsense", 1)
+    with pytest.raises(MolochError, match="wsolve must be"):
+        m.set_option("wsolve", 3)
+    assert np.isfinite(m.get_global("pai")).all()
+    m.close()

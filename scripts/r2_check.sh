@@ -26,8 +26,8 @@ except Exception as exc:
     print(sys.argv[1], "no result:", exc)
 PY
 done
-# wsolve A/B: 6 = default since the end of round 1 (7 warps/SM, unmeasured then), 5 = the measured round-1 kernel
-# (45 % of the HBM peak, 4 warps/SM), 2 = CTA-parallel coefficients
+# wsolve A/B (bench.py autotunes 5 vs 6 when MOLOCH_B200_WSOLVE is unset; here each is forced): 6 = 7 warps/SM,
+# 5 = the measured round-1 kernel (45 % of the HBM peak, 4 warps/SM), 2 = CTA-parallel coefficients
 for v in 6 5 2; do
   MOLOCH_B200_WSOLVE=$v timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_wsolve$v.json 2>/dev/null
   python - "$v" <<'PY'

@@ -104,8 +104,9 @@ struct Ctx {
   unsigned long long halo_seq = 0;
   bool p2p = false;
   bool fuse_halo = true;                 // sound-loop exchanges fused into producer/consumer kernels (p2p only)
-  int fuse_level = 2;                    // 1: sub-steps 2.. of the sound loop only; 2: also the first sub-step and
-                                         // advection's u,v / ux,vx exchanges (MOLOCH_B200_FUSE_HALO=0|1|2)
+  int fuse_level = 1;                    // 1: sub-steps 2.. of the sound loop only (the GPU-measured configuration);
+                                         // 2: also the first sub-step and advection's u,v / ux,vx exchanges
+                                         // (MOLOCH_B200_FUSE_HALO=0|1|2, set_option("fuse_halo"); bench.py times 2 vs 1)
   Peer peer[4];                          // left, right, bottom, top
   void* nccl_comm = nullptr;
   double *sendbuf = nullptr, *recvbuf = nullptr;

@@ -136,8 +136,8 @@ def test_decomposed(name, wl, px, py, transport, monkeypatch):
 
 
 @pytest.mark.parametrize("px,py", [(2, 1), (1, 2), (2, 2)] if FULL else [(2, 2)])
-def test_decomposed_boundary(px, py):
-    _gpu_tests()[2].test_decomposed_boundary_bit_exact(px, py)
+def test_decomposed_boundary(px, py, monkeypatch):
+    _gpu_tests()[2].test_decomposed_boundary_bit_exact(px, py, monkeypatch)
 
 
 @pytest.mark.parametrize("nslabs", [1, 3, 1000])

@@ -71,11 +71,12 @@ BDY = S.small(S.WORKLOADS["cordex25"], 46, 42, 12, ntr=2, nspgx=6, do_bdy=1, pre
 
 
 @pytest.mark.parametrize("px,py", [(2, 1), (1, 2), (2, 2)])
-def test_decomposed_boundary_bit_exact(px, py):
+def test_decomposed_boundary_bit_exact(px, py, monkeypatch):
     """moloch() with the lateral boundary and mkslice on px x py GPUs: bdyval, the
     relaxation and mkslice are rank-local; `boundary` adds one u/v halo round."""
     if ndev() < px * py:
         pytest.skip(f"needs {px * py} GPUs")
+    monkeypatch.setenv("MOLOCH_B200_FUSE_HALO", "2")     # every fusable round fused
     wl = BDY
     o, B = make_oracle_bdy(wl)
     fields, profiles = oracle_inputs(o, wl)

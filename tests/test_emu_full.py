@@ -166,9 +166,10 @@ def test_bench_e2e_path(_emulated_library):
         m.init_moloch(fields, profiles, boxes)
         ms.append(m)
     r = bench.measure_e2e(ms[0], wl, 1)
-    assert r["handoff"] == "pipelined" and r["handoff_note"] is None, r
+    assert r["handoff_note"] is None and set(r["ms_per_step_by_handoff"]) == {"sequential", "pipelined"}, r
+    assert r["handoff"] in ("pipelined", "sequential")      # the faster of the two (on a GPU: the link decides)
     assert r["d2h_bytes_per_step"] > 0 and r["h2d_bytes_per_step"] > 0
-    ms[1].moloch(3)      # self-check step + warm-up step + 1 timed step
+    ms[1].moloch(5)      # self-check step + (warm-up + 1 timed step) per hand-off mode
     for f in ("u", "v", "w", "pai", "t", "qx", "trac"):
         assert np.array_equal(ms[0].get_global(f), ms[1].get_global(f)), f
     for m in ms:
@@ -265,7 +266,8 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
     assert line["metric"] == "MOLOCH dycore cell-updates/s" and line["n_gpus"] == 1 and line["finite"]
     assert line["gpu_launches"] > 0 and line["value"] > 0
     assert line["roofline"]["bound"] == "hbm" and line["roofline"]["frac"] > 0
-    assert line["e2e"]["handoff"] == "pipelined" and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(line["e2e"]["ms_per_step_by_handoff"]) == {"sequential", "pipelined"}
+    assert line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
     tune = line["config"]["variant_tuning"]["wsolve"]
     assert tune["v6_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 6], tune

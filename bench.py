@@ -303,7 +303,7 @@ def variants_agree(wl, device, lib=None) -> bool:
 def autotune_wsolve(m, wl, timed, all_min=lambda x: x, device=-1, lib=None):
     """(variant, record): times two steps of the benchmark model per admissible variant and picks the faster.
     `all_min`: minimum over the ranks (every rank must take the same decisions)."""
-    rec = {"candidates": [5]}
+    rec = {"candidates": [5, 2]}       # both measured on the B200 in round 1 (5 won at N = 1)
     try:
         ok = bool(variants_agree(wl, device, lib))
     except Exception as exc:  # noqa: BLE001
@@ -312,8 +312,6 @@ def autotune_wsolve(m, wl, timed, all_min=lambda x: x, device=-1, lib=None):
     rec["v6_bit_exact_vs_v5"] = bool(all_min(1.0 if ok else 0.0) > 0.5)
     if rec["v6_bit_exact_vs_v5"]:
         rec["candidates"].append(6)
-    if len(rec["candidates"]) == 1:
-        return 5, rec
     rec["ms_per_step"] = {}
     for v in rec["candidates"]:
         m.set_option("wsolve", v)

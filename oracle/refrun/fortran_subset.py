@@ -419,8 +419,21 @@ class Translator:
             local_names.discard(n)
 
         # ---- pass 2: executable statements ---------------------------------------------
-        def stmt(s):
+        loop_labels = []     # construct names of the open DO loops (None: unnamed), innermost last
+
+        def stmt(s, label=None):
             nonlocal ind
+            m = re.match(r"^(\w+)\s*:\s*(do\b.*)$", s)
+            if m:                        # named DO construct:  name: do ...
+                return stmt(m.group(2).strip(), m.group(1))
+            if re.match(r"^do\b", s):
+                loop_labels.append(label)
+            m = re.match(r"^(cycle|exit)\s+(\w+)$", s)
+            if m:                        # cycle/exit of a named construct: only the innermost loop is supported
+                if not loop_labels or loop_labels[-1] != m.group(2):
+                    raise NotImplementedError(s + " (not the innermost loop)")
+                emit("continue" if m.group(1) == "cycle" else "break")
+                return
             m = re.match(r"^do\s+concurrent\s*\(", s)
             if m:
                 close = match_paren(s, m.end() - 1)
@@ -460,6 +473,7 @@ class Translator:
                 return
             if re.match(r"^end\s*do\b", s):
                 kind, n = blocks.pop()
+                loop_labels.pop()
                 emit("pass")
                 ind -= n
                 return

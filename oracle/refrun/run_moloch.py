@@ -564,7 +564,10 @@ class BdySetupRun:
     coefficients (Main/mod_bdycod.F90:478-568; relax_coefficients, Main/mpplib/mod_runparams.F90:645-697) and
     lowpass_init (Main/mod_bdycod.F90:3844-3896).  Input: the level heights zeta."""
 
-    def __init__(self, wl, zeta: np.ndarray):
+    def __init__(self, wl, zeta: np.ndarray, lehmann: bool = True):
+        """lehmann=False: the exponential branch -- exponential_nudging (Main/mpplib/mod_runparams.F90:611-636)
+        and spline1d (Share/mod_spline.F90:387-459) are executed from source too, on MOLOCH's sigma/hsigma
+        (Main/mod_params.F90:2460-2465)."""
         from regcm_b200.decomp import make_geom
         self.wl = wl
         g = self.g = make_geom(wl.jx, wl.iy, wl.kz, wl.i_band, 0, 1, 1, 0)
@@ -585,7 +588,7 @@ class BdySetupRun:
                   njcross=njcross, nicross=nicross, ds=wl.ds_km, dx=wl.dx, dtsec=wl.dt, mo_nadv=wl.mo_nadv,
                   mo_h=wl.mo_h, idynamic=3, dtbdys=wl.dtbdys, dtrad=wl.dtrad, myid=0, italk=0,
                   mo_top_nudge=bool(wl.mo_top_nudge), mo_spectral_nudge=bool(wl.mo_spectral_nudge),
-                  bdy_use_lehmann=True, iboudy=5, rtb=0.0, nztop=0, km=0, lm=0, cn0=0.0,
+                  bdy_use_lehmann=bool(lehmann), iboudy=5, rtb=0.0, nztop=0, km=0, lm=0, cn0=0.0,
                   ma=_Obj(bandflag=band, crmflag=False), sumall=lambda x: x, vprntv=lambda *a: None,
                   ba_cr=_Obj(), ba_ud=_Obj(), ba_vd=_Obj())
         b = g.ext("cross", 0, 0)
@@ -599,12 +602,31 @@ class BdySetupRun:
             ns[n] = None
         arrays = {"hefc", "gmeanz", "tnudge", "cnudge", "bvx", "bvy", "sx", "sy", "sxg", "syg", "px", "py", "anudge",
                   "coeff", "p", "q", "pp", "qq"}
+        if not lehmann:
+            from regcm_b200 import synthetic as S_
+            # Share/mod_dynparam.F90:150-152 (namelist defaults); sigma, hsigma as Main/mod_params.F90:2460-2465
+            ns.update(high_nudge=3.0, medium_nudge=2.0, low_nudge=1.0, kzp1=kz + 1, myid=1,
+                      anudge=FArr.alloc([(1, kz)]), d_one=1.0, d_half=0.5)
+            sg, hs = FArr.alloc([(1, kz + 1)]), FArr.alloc([(1, kz)])
+            sg.a[...] = 1.0 - S_.model_zitaf(kz, wl.mo_ztop) / wl.mo_ztop
+            hs.a[...] = 1.0 - S_.model_zitah(kz, wl.mo_ztop) / wl.mo_ztop
+            ns.update(sigma=sg, hsigma=hs)
+            arrays |= {"sigma", "hsigma", "nudge", "ncin", "zcin", "ycin", "xold", "yold", "y2", "xnew", "ynew"}
         tr = F.Translator(arrays)
         ar = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mod_atm_interface.F90")).read()))
         br = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mod_bdycod.F90")).read()))
         rr = F.find_routines(F.preprocess(open(os.path.join(REF, "Main/mpplib/mod_runparams.F90")).read()))
         self.sources = {}
-        for r, rel in ((ar["setup_boundaries"], "Main/mod_atm_interface.F90"),
+        extra = ()
+        if not lehmann:
+            sr = F.find_routines(F.preprocess(open(os.path.join(REF, "Share/mod_spline.F90")).read()))
+            # its internal function findwhere (find_routines ends the host routine at the first `end function`,
+            # so the internal procedure is the tail of the host's body after `contains`)
+            eb = rr["exponential_nudging"].body
+            inner = F.find_routines(eb[eb.index("contains") + 1:] + ["end function findwhere"])
+            extra = ((sr["spline1d"], "Share/mod_spline.F90"), (inner["findwhere"], "Main/mpplib/mod_runparams.F90"),
+                     (rr["exponential_nudging"], "Main/mpplib/mod_runparams.F90"))
+        for r, rel in extra + ((ar["setup_boundaries"], "Main/mod_atm_interface.F90"),
                        (rr["relax_coefficients"], "Main/mpplib/mod_runparams.F90"),
                        (br["lowpass_init"], "Main/mod_bdycod.F90"), (br["setup_bdycon"], "Main/mod_bdycod.F90")):
             src = tr.routine(r)

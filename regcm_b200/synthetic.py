@@ -17,6 +17,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, replace
 
+import math
+
 import numpy as np
 
 # ---- Share/mod_constants.F90 (non-RCEMIP) ---------------------------------
@@ -244,17 +246,84 @@ def _msf(wl: Workload, x, y):
     return 1.0 + wl.msf_amp * np.sin(2 * mathpi * x / wl.jx) * np.cos(2 * mathpi * y / wl.iy)
 
 
+def spline1d(xold, yold, y2, xnew):
+    """Cubic spline through (xold, yold) with end second derivatives y2[0], y2[-1], evaluated at xnew: a
+    restatement of spline1d, Share/mod_spline.F90:387-459 (1-based there), operation for operation."""
+    xold, yold, y2, xnew = (np.array(v, dtype=np.float64) for v in (xold, yold, y2, xnew))
+    nold, nnew = xold.size, xnew.size
+    afac = 6.0
+    bfac = 1.0 / afac
+    X = lambda k: xold[k - 1]      # noqa: E731  (Fortran indices below)
+    Y = lambda k: yold[k - 1]      # noqa: E731
+    p, q = np.zeros(max(nold - 2, 1) + 1), np.zeros(max(nold - 2, 1) + 1)
+    dxl = X(2) - X(1)
+    dxr = X(3) - X(2)
+    dydxl = (Y(2) - Y(1)) / dxl
+    dydxr = (Y(3) - Y(2)) / dxr
+    rtdxc = 0.5 / (dxl + dxr)
+    p[1] = rtdxc * (bfac * (dydxr - dydxl) - dxl * y2[0])
+    q[1] = -rtdxc * dxr
+    if nold > 3:
+        # the reference's loop runs k = 3 .. nold and would read xold(nold+1): only nold == 3 is ever used
+        raise NotImplementedError("spline1d with more than three nodes")
+    for k in range(nold - 1, 1, -1):
+        y2[k - 1] = p[k - 1] + q[k - 1] * y2[k]
+    ynew = np.zeros(nnew)
+    k = -1
+    ak = bk = ck = 0.0
+    for k1 in range(1, nnew + 1):
+        xk = xnew[k1 - 1]
+        if xk < X(1):
+            ynew[k1 - 1] = Y(1)
+            continue
+        if xk >= X(nold):
+            ynew[k1 - 1] = Y(nold)
+            continue
+        kold = None
+        for k2 in range(2, nold + 1):
+            if X(k2) <= xk:
+                continue
+            kold = k2 - 1
+            break
+        if k != kold:
+            k = kold
+            y2k, y2kp1 = y2[k - 1], y2[k]
+            dx = X(k + 1) - X(k)
+            rdx = 1.0 / dx
+            ak = bfac * rdx * (y2kp1 - y2k)
+            bk = 0.5 * y2k
+            ck = rdx * (Y(k + 1) - Y(k)) - bfac * dx * (y2kp1 + y2k + y2k)
+        x = xk - X(k)
+        xsq = x * x
+        ynew[k1 - 1] = ak * xsq * x + bk * xsq + ck * x + Y(k)
+    return ynew
+
+
+def exponential_nudging(kz: int, ztop: float, high_nudge=3.0, medium_nudge=2.0, low_nudge=1.0) -> np.ndarray:
+    """anudge(1:kz): exponential_nudging, Main/mpplib/mod_runparams.F90:611-636, on MOLOCH's sigma = 1 - zita/ztop
+    (Main/mod_params.F90:2460-2465, Share/mod_zita.F90:40-45); defaults of Share/mod_dynparam.F90:150-152."""
+    sigma = 1.0 - model_zitaf(kz, ztop) / ztop          # sigma(1:kz+1)
+    hsigma = 1.0 - model_zitah(kz, ztop) / ztop         # hsigma(1:kz)
+    kw = kz + 1                                          # findwhere(0.40): the loop index after a full loop
+    for k in range(2, kz + 1):
+        if sigma[k - 1] > 0.40:
+            kw = k
+            break
+    zcin = [sigma[0], sigma[kw - 1], sigma[kz]]
+    return spline1d(zcin, [high_nudge, medium_nudge, low_nudge], [0.0, 0.0, 0.0], hsigma)
+
+
 def hefc_table(wl: Workload) -> np.ndarray:
-    """Sponge coefficients hefc(n,k) (Main/mod_bdycod.F90:520-545, exponential
-    branch) with a linear anudge(k) profile standing in for spline1d."""
+    """Sponge coefficients hefc(n,k), the exponential branch of setup_bdycon's MOLOCH part
+    (Main/mod_bdycod.F90:520-545): hefc(1) = 1, hefc(nspgx) = 0, exp(-(n-1)/anudge(k)) in between."""
     nsp, kz = wl.nspgx, wl.kz
     h = np.zeros((kz, nsp))
-    anudge = np.linspace(3.0, 1.0, kz)
+    anudge = exponential_nudging(kz, wl.mo_ztop)
     for k in range(kz):
         h[k, 0] = 1.0
         h[k, nsp - 1] = 0.0
         for n in range(2, nsp):
-            h[k, n - 1] = np.exp(-float(n - 1) / anudge[k])
+            h[k, n - 1] = math.exp(-float(n - 1) / anudge[k])
     return h
 
 

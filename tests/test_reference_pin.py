@@ -147,6 +147,21 @@ def test_reference_multirank_spectral_nudging_matches_decomposed_oracle(px, py):
 
 
 @pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
+@pytest.mark.parametrize("kz,nspgx", [(8, 4), (41, 12), (30, 6)])
+def test_reference_exponential_sponge_profile_matches(kz, nspgx):
+    """The exponential branch of setup_bdycon (Main/mod_bdycod.F90:536-543) with exponential_nudging
+    (Main/mpplib/mod_runparams.F90:611-636, incl. its internal findwhere) and spline1d (Share/mod_spline.F90:387-459)
+    executed from source on MOLOCH's sigma/hsigma: the sponge table hefc the workloads use
+    (regcm_b200.synthetic.hefc_table, a restatement of those three routines) equals it bit for bit."""
+    from regcm_b200 import synthetic as S
+    wl = S.small(S.WORKLOADS["cordex25"], 2 * nspgx + 8, 2 * nspgx + 6, kz, ntr=0, nspgx=nspgx, do_bdy=1)
+    o, _ = make_oracle_bdy(wl)
+    run = R.BdySetupRun(wl, o.get("zeta"), lehmann=False).run()
+    assert np.array_equal(run.ns["hefc"].a, S.hefc_table(wl))
+    assert np.array_equal(o.get("hefc").reshape(kz, nspgx), S.hefc_table(wl))     # what the oracle relaxes with
+
+
+@pytest.mark.skipif(not R.available(), reason="needs the reference sources under /root/reference")
 def test_reference_runs_use_the_reference_allocation():
     """The arrays of a ReferenceRun have exactly the bounds allocate_atmosphere
     (Main/mod_atm_interface.F90:579-624) and allocate_moloch (Main/mod_moloch.F90:159-199) give when THEY are

@@ -128,7 +128,22 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, opt: str = "-O1") -> str:
+def build(force: bool = False, opt: str = "-O1", sanitize: bool = False) -> str:
+    """sanitize=True: a second library built with -fsanitize=address (scripts/emu_asan.sh runs representative
+    tests on it: a memcheck of every kernel and of the ABI's host code without a GPU -- "device" allocations are
+    heap blocks with red zones there)."""
+    global LIB, GEN
+    if sanitize:      # a second library next to the regular one; the module's paths are restored afterwards
+        keep = (LIB, GEN)
+        LIB, GEN = os.path.join(EMU, "libmoloch_b200_emu_asan.so"), os.path.join(EMU, "_gen_asan")
+        try:
+            return _build(force, opt, True)
+        finally:
+            LIB, GEN = keep
+    return _build(force, opt, False)
+
+
+def _build(force: bool, opt: str, sanitize: bool) -> str:
     if not force and not _stale():
         return LIB
     os.makedirs(GEN, exist_ok=True)
@@ -138,7 +153,7 @@ def build(force: bool = False, opt: str = "-O1") -> str:
         txt = open(os.path.join(CSRC, h)).read().replace('"../../include/moloch_b200.h"', '"moloch_b200.h"')
         open(os.path.join(GEN, h), "w").write(rewrite(txt))
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    flags = [opt, "-g1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing",
+    flags = (["-fsanitize=address", "-fno-omit-frame-pointer"] if sanitize else []) + [opt, "-g1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing",
              "-Wno-unknown-pragmas", "-Wno-attributes", "-pthread",
              "-I", os.path.join(EMU, "shim"), "-I", GEN, "-I", os.path.join(ROOT, "include"), "-I", EMU]
 
@@ -158,7 +173,8 @@ def build(force: bool = False, opt: str = "-O1") -> str:
 
     with ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(one, SOURCES + [RUNTIME[0]]))
-    r = subprocess.run([gxx, "-shared", "-pthread", "-Wl,-Bsymbolic", "-o", LIB] + objs + ["-ldl"],
+    r = subprocess.run([gxx, "-shared", "-pthread", "-Wl,-Bsymbolic"] + (["-fsanitize=address"] if sanitize else []) +
+                       ["-o", LIB] + objs + ["-ldl"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr}")

@@ -135,15 +135,16 @@ def build(force: bool = False, opt: str = "-O1", sanitize: bool = False) -> str:
     global LIB, GEN
     if sanitize:      # a second library next to the regular one; the module's paths are restored afterwards
         keep = (LIB, GEN)
-        LIB, GEN = os.path.join(EMU, "libmoloch_b200_emu_asan.so"), os.path.join(EMU, "_gen_asan")
+        tag = "tsan" if sanitize == "thread" else "asan"
+        LIB, GEN = os.path.join(EMU, f"libmoloch_b200_emu_{tag}.so"), os.path.join(EMU, f"_gen_{tag}")
         try:
-            return _build(force, opt, True)
+            return _build(force or not os.path.exists(LIB), opt, sanitize)
         finally:
             LIB, GEN = keep
     return _build(force, opt, False)
 
 
-def _build(force: bool, opt: str, sanitize: bool) -> str:
+def _build(force: bool, opt: str, sanitize) -> str:
     if not force and not _stale():
         return LIB
     os.makedirs(GEN, exist_ok=True)
@@ -153,7 +154,9 @@ def _build(force: bool, opt: str, sanitize: bool) -> str:
         txt = open(os.path.join(CSRC, h)).read().replace('"../../include/moloch_b200.h"', '"moloch_b200.h"')
         open(os.path.join(GEN, h), "w").write(rewrite(txt))
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    flags = (["-fsanitize=address", "-fno-omit-frame-pointer"] if sanitize else []) + [opt, "-g1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing",
+    san = [] if not sanitize else (["-fsanitize=thread", "-DEMU_TSAN"] if sanitize == "thread" else
+                                   ["-fsanitize=address", "-fno-omit-frame-pointer"])
+    flags = san + [opt, "-g1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing",
              "-Wno-unknown-pragmas", "-Wno-attributes", "-pthread",
              "-I", os.path.join(EMU, "shim"), "-I", GEN, "-I", os.path.join(ROOT, "include"), "-I", EMU]
 
@@ -173,7 +176,7 @@ def _build(force: bool, opt: str, sanitize: bool) -> str:
 
     with ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(one, SOURCES + [RUNTIME[0]]))
-    r = subprocess.run([gxx, "-shared", "-pthread", "-Wl,-Bsymbolic"] + (["-fsanitize=address"] if sanitize else []) +
+    r = subprocess.run([gxx, "-shared", "-pthread", "-Wl,-Bsymbolic"] + san[:1] +
                        ["-o", LIB] + objs + ["-ldl"],
                        capture_output=True, text=True)
     if r.returncode != 0:

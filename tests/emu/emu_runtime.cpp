@@ -29,18 +29,10 @@
 #include "shim/cuda_runtime.h"
 #include "shim/nccl.h"
 
-// EMU_TSAN: ThreadSanitizer build (scripts/emu_tsan.sh).  Every emulated thread is announced to TSan as a fiber
-// and every switch synchronises (within a rank thread the launches, CTAs and fibers run one after another, as
-// kernels on one stream do), so what TSan reports are accesses of DIFFERENT rank threads to the same address
-// that no release/acquire flag orders: a peer store into a ghost cell that the neighbour may still be reading
-// or has not been told about -- the races of the halo protocol.
-#ifdef EMU_TSAN
-#include <sanitizer/tsan_interface.h>
-#define TSAN_SWITCH(f) __tsan_switch_to_fiber((f), 0)
-#else
-#define TSAN_SWITCH(f) ((void)0)
-#endif
-
+// ThreadSanitizer build (tests/emu_lib.py sanitize="thread", scripts/emu_tsan.sh): compiled without function
+// entry/exit instrumentation, so TSan keeps no shadow call stack that the fiber switches would corrupt and every
+// emulated thread of a rank simply is the rank's OS thread.  What TSan then reports are accesses of DIFFERENT
+// rank threads to one address that no release/acquire flag orders: the races of the halo protocol.
 extern "C" void emu_switch(void** save_sp, void* load_sp);
 asm(R"(
 .text
@@ -76,7 +68,6 @@ constexpr size_t STACK_BYTES = 256 * 1024;
 
 struct Copy { void* dst; const void* src; int bytes; };
 struct Fiber {
-  void* tsan = nullptr;            // TSan fiber object (EMU_TSAN), taken from the scheduler's pool
   void* sp = nullptr;
   bool done = false;
   uint3 tid{0, 0, 0};
@@ -103,8 +94,6 @@ struct Sched {
   void (*fn)(void*) = nullptr;
   void* arg = nullptr;
   std::vector<char*> stacks;
-  std::vector<void*> tsan_pool;    // one TSan fiber per stack, reused by every CTA
-  void* tsan_main = nullptr;
   char* smem = nullptr;
   size_t smem_cap = 0;
   unsigned long long progress = 0;
@@ -124,7 +113,6 @@ bool reverse_order() {
 
 void yield() {
   Sched& s = sched;
-  TSAN_SWITCH(s.tsan_main);
   emu_switch(&s.cur->sp, s.main_sp);
 }
 void arrive(Barrier& b) {
@@ -156,7 +144,6 @@ void fiber_entry() {
   s.warps[(size_t)f.warp].live[f.lane] = false;
   leave(s.warps[(size_t)f.warp].b);
   leave(s.cta);
-  TSAN_SWITCH(s.tsan_main);
   emu_switch(&f.sp, s.main_sp);
   fprintf(stderr, "emu: finished fiber resumed\n");
   abort();
@@ -178,13 +165,8 @@ void run_cta(dim3 block, size_t smem) {
     void* p = mmap(nullptr, STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (p == MAP_FAILED) { perror("emu: mmap"); abort(); }
     s.stacks.push_back((char*)p);
-#ifdef EMU_TSAN
-    s.tsan_pool.push_back(__tsan_create_fiber(0));
-#endif
   }
-#ifdef EMU_TSAN
-  s.tsan_main = __tsan_get_current_fiber();
-#endif
+
   if (smem + 64 > s.smem_cap) {
     free(s.smem);
     s.smem_cap = smem + 64;
@@ -205,9 +187,6 @@ void run_cta(dim3 block, size_t smem) {
     Warp& w = s.warps[(size_t)f.warp];
     w.b.n++; w.live[f.lane] = true;
     prepare(f, s.stacks[(size_t)t]);
-#ifdef EMU_TSAN
-    f.tsan = s.tsan_pool[(size_t)t];
-#endif
   }
   for (Warp& w : s.warps)
     for (int l = w.b.n; l < 32; ++l) w.live[l] = false;
@@ -221,7 +200,6 @@ void run_cta(dim3 block, size_t smem) {
       if (f.done) continue;
       s.cur = &f;
       tIdx = f.tid;
-      TSAN_SWITCH(f.tsan);
       emu_switch(&s.main_sp, f.sp);
       if (!f.done) ++alive;
     }

@@ -154,7 +154,12 @@ def _build(force: bool, opt: str, sanitize) -> str:
         txt = open(os.path.join(CSRC, h)).read().replace('"../../include/moloch_b200.h"', '"moloch_b200.h"')
         open(os.path.join(GEN, h), "w").write(rewrite(txt))
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    san = [] if not sanitize else (["-fsanitize=thread", "-DEMU_TSAN"] if sanitize == "thread" else
+    # thread: no function entry/exit instrumentation, so TSan keeps no shadow call stack that the fiber
+    # switches would corrupt; every emulated thread of a rank then simply IS the rank's OS thread for TSan
+    # (announcing 256 fibers per rank exhausts TSan's thread slots: it then resets its history all the time
+    # and misses races between accesses that lie a few kernels apart)
+    san = [] if not sanitize else (["-fsanitize=thread", "--param=tsan-instrument-func-entry-exit=0"]
+                                   if sanitize == "thread" else
                                    ["-fsanitize=address", "-fno-omit-frame-pointer"])
     flags = san + [opt, "-g1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing",
              "-Wno-unknown-pragmas", "-Wno-attributes", "-pthread",

@@ -82,8 +82,17 @@ inline typename std::common_type<A, B>::type max(A a, B b) { return (a < b) ? b 
 
 inline void __syncthreads() { emu::sync_threads(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_sync(); }
+#ifdef __SANITIZE_THREAD__
+// ThreadSanitizer models a seq_cst fence as an acquire+release on one global object: every fence of every rank
+// would then order everything before it with everything after any later fence of any other rank, and hide
+// exactly the races the TSan run looks for.  The protocol's ordering comes from the release stores / acquire
+// loads of the arrival flags (on the host's TSO the fences add nothing): compiler barriers here.
+inline void __threadfence_system() { __asm__ __volatile__("" ::: "memory"); }
+inline void __threadfence() { __asm__ __volatile__("" ::: "memory"); }
+#else
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+#endif
 inline long long clock64() { return emu::clock_now(); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 

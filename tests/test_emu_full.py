@@ -329,3 +329,12 @@ def test_waf_per_loop_kernels(monkeypatch):
 def test_set_option():
     import test_gpu_zz_variants as V
     V.test_set_option_switches_variants_of_a_live_context()
+
+
+def test_graft_entry_smoke(_emulated_library, monkeypatch, capsys):
+    """__graft_entry__.smoke() -- what the driver runs on the B200 before the bench -- on the emulated library."""
+    import __graft_entry__ as G
+    from regcm_b200 import moloch as M
+    monkeypatch.setattr(M, "_lib", _emulated_library)
+    G.smoke()
+    assert "smoke ok" in capsys.readouterr().out

@@ -162,8 +162,8 @@ int moloch_b200_p2p_export(moloch_b200_ctx* ctx, void* blob);
 int moloch_b200_p2p_connect(moloch_b200_ctx* ctx, const void* blobs, int nranks);
 
 /* Kernel-variant switches of an existing context (what the MOLOCH_B200_* environment variables set at create):
- *   "wsolve"    5 | 6 | 2   implicit-w column solver: three / two sweep arrays in shared memory (4 / 7 warps per SM),
- *                           or the CTA-parallel variant
+ *   "wsolve"    5 | 6 | 7 | 2   implicit-w column solver: three sweep arrays in shared memory (4 warps per SM), two
+ *                           (7 warps with a 4-deep ring, 6 warps with a 6-deep ring), or the CTA-parallel variant
  *   "waf"       2 | 1       field-batched fused WAF kernels, or one kernel per reference loop nest
  *   "fuse_halo" 0 | 1 | 2   peer-store transport: exchanges fused into the kernels around them (none / the sound
  *                           loop's sub-steps 2.. / all); every rank must use the same value

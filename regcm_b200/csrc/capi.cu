@@ -437,7 +437,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   c->h_ptrtab = tab;
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
-  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || v == 6) ? v : 5; }
+  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || v == 6 || v == 7) ? v : 5; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaFree(c->arena);
     delete c;
@@ -498,7 +498,7 @@ int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
   if (!c || !name) return fail("set_option: null argument");
   const std::string n(name);
   if (n == "wsolve") {
-    if (value != 2 && value != 5 && value != 6) return fail("set_option: wsolve must be 2, 5 or 6");
+    if (value != 2 && value != 5 && value != 6 && value != 7) return fail("set_option: wsolve must be 2, 5, 6 or 7");
     c->wsolve_impl = value;
   } else if (n == "waf") {
     if (value != 1 && value != 2) return fail("set_option: waf must be 1 or 2");

@@ -332,7 +332,7 @@ int k_wsolve(Ctx& c, double dts, bool last, const PushCtl* pcp, const EdgePush* 
   const PushCtl pc = pcp ? *pcp : PushCtl{};
   const EdgePush ep = epp ? *epp : EdgePush{};
   if (c.wsolve_impl == 5) return k_wsolve5(c, dts, last, pc, ep);
-  if (c.wsolve_impl == 6) return k_wsolve6(c, dts, last, pc, ep);
+  if (c.wsolve_impl == 6 || c.wsolve_impl == 7) return k_wsolve6(c, dts, last, pc, ep);
   const Geo& g = c.g;
   const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
   const bool small = (ncol + 31) / 32 < 148 * 5 * 3;   // fewer than three waves of 32-column CTAs
@@ -632,8 +632,8 @@ moloch_wsolve6(Geo g, const double* __restrict__ zdiv, double* s, double* w, dou
   cp_async_wait<0>();
   if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
 }
-int k_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
-  constexpr int D = 4;
+template <int D>
+static int launch_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
   const Geo& g = c.g;
   const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
   const double dtrdz = dts * c.rdzita;
@@ -648,6 +648,10 @@ int k_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& 
       c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, pc, ep);
   MB_CUDA(cudaGetLastError());
   return 0;
+}
+// variant 6: ring of 4 levels (31 KB per warp at kz = 41: 7 warps per SM); variant 7: ring of 6 (36 KB: 6 warps)
+int k_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
+  return c.wsolve_impl == 7 ? launch_wsolve6<6>(c, dts, last, pc, ep) : launch_wsolve6<4>(c, dts, last, pc, ep);
 }
 int k_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
   // One warp per CTA and a latency-bound column sweep: what matters on small

@@ -28,7 +28,7 @@ PY
 done
 # wsolve A/B (bench.py autotunes 5 vs 6 when MOLOCH_B200_WSOLVE is unset; here each is forced): 6 = 7 warps/SM,
 # 5 = the measured round-1 kernel (45 % of the HBM peak, 4 warps/SM), 2 = CTA-parallel coefficients
-for v in 6 5 2; do
+for v in 6 7 5 2; do
   MOLOCH_B200_WSOLVE=$v timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_wsolve$v.json 2>/dev/null
   python - "$v" <<'PY'
 import json, sys

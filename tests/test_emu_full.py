@@ -270,8 +270,8 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
     assert line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
     tune = line["config"]["variant_tuning"]["wsolve"]
-    assert tune["v6_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 2, 6], tune
-    assert line["config"]["wsolve_variant"] in (5, 2, 6) and set(tune["ms_per_step"]) == {"5", "2", "6"}
+    assert tune["v6_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 2, 6, 7], tune
+    assert line["config"]["wsolve_variant"] in (5, 2, 6, 7) and set(tune["ms_per_step"]) == {"5", "2", "6", "7"}
 
 
 def test_halo_timeout_is_reported(_emulated_library):

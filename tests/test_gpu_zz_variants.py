@@ -4,7 +4,7 @@ every A/B candidate must be bit-exact before it is timed.
     MOLOCH_B200_WSOLVE = 5 (default: thread per column, cp.async ring, three sweep arrays in shared memory, 4 warps
                             per SM: the variant profiles/ measured)
                          6 (two sweep arrays, the finished divergence recomputed in the upward pass; 7 warps per SM;
-                            bench.py times 5 against 6 and keeps the faster)
+                            bench.py times the variants and keeps the fastest), 7 (as 6 with a 6-deep ring: 6 warps)
                          2 (CTA = 32 columns x all levels, one-warp sweeps)
     MOLOCH_B200_WAF    = 2 (default: field-batched fused WAF kernels) | 1 (one kernel per reference loop nest)
 
@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("case", ["limited_area", "tall"])
-@pytest.mark.parametrize("impl", ["6", "2"])
+@pytest.mark.parametrize("impl", ["6", "7", "2"])
 def test_wsolve_variants_bit_exact(impl, case, monkeypatch):
     monkeypatch.setenv("MOLOCH_B200_WSOLVE", impl)
     P.test_steps_bit_exact(case)
@@ -39,7 +39,7 @@ def test_set_option_switches_variants_of_a_live_context():
     o, _ = make_oracle(wl)
     fields, profiles = oracle_inputs(o, wl)
     m = make_gpu(wl, fields, profiles)
-    for opt, v in (("wsolve", 6), ("waf", 1), ("wsolve", 2), ("waf", 2), ("wsolve", 5)):
+    for opt, v in (("wsolve", 6), ("waf", 1), ("wsolve", 2), ("waf", 2), ("wsolve", 7), ("wsolve", 5)):
         m.set_option(opt, v)
         o.step(1); m.moloch(1)
         compare(o, m, PROGNOSTIC + ["trac"], label=f"after set_option({opt}, {v}): ")

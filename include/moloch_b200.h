@@ -34,7 +34,9 @@
 extern "C" {
 #endif
 
-#define MOLOCH_B200_ABI_VERSION 2
+/* v2: lateral boundary, mkslice, TKE, diagnostics.  v3: moloch_b200_handoff, _host_register/_unregister,
+ * _set_option; `niycpus` takes the place of the reserved last configuration word (same struct size). */
+#define MOLOCH_B200_ABI_VERSION 3
 
 /* Replaces the module globals read by allocate_moloch/init_moloch:
  * mod_dynparam index ranges (Share/mod_dynparam.F90:252-310), `ma`

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(M.LIB_PATH)
     for s in declared:
         assert hasattr(lib, s), s
-    assert M.load_library().moloch_b200_abi_version() == 2
+    assert M.load_library().moloch_b200_abi_version() == 3
 
 
 def test_enums_match_header():

@@ -169,11 +169,22 @@ int moloch_b200_p2p_connect(moloch_b200_ctx* ctx, const void* blobs, int nranks)
  *   "waf"       2 | 1       field-batched fused WAF kernels, or one kernel per reference loop nest
  *   "fuse_halo" 0 | 1 | 2   peer-store transport: exchanges fused into the kernels around them (none / the sound
  *                           loop's sub-steps 2.. / all); every rank must use the same value
+ *   "halo_timeout_ms"       how long a kernel of the peer-store transport waits for a neighbour's arrival
+ *                           counter before it gives up (default 30 s; MOLOCH_B200_HALO_TIMEOUT_MS at create)
  * All variants give bit-identical results; they exist for measurement (bench.py times them and keeps the faster). */
 int moloch_b200_set_option(moloch_b200_ctx* ctx, const char* name, int value);
 
 /* run on a caller-owned CUDA stream (cudaStream_t) instead of the context's */
 int moloch_b200_set_stream(moloch_b200_ctx* ctx, void* cuda_stream);
+/* Waits for everything enqueued on the context's stream.
+ * FAILURE CONTRACT of the peer-store halo transport: a kernel whose neighbour does not arrive within
+ * halo_timeout_ms gives up its wait, marks the round, and every later wait gives up at once (NCCL would
+ * block forever; a rank that died would hang the job).  The compute entries (_step, _sound, ...) only
+ * ENQUEUE work and cannot report this.  It is reported -- non-zero return, "halo exchange timed out in
+ * round N" -- by EVERY entry through which results become visible to the host: moloch_b200_sync,
+ * _get_field/_set_field (unless set_async is on: then the closing _sync), _handoff, _massck, _ps_check,
+ * _profile_read, _set_profile/_set_table/_set_ibnd.  Fields read after such an error are invalid; the shim
+ * turns it into fatal().  The marker is sticky for the life of the context.                              */
 int moloch_b200_sync(moloch_b200_ctx* ctx);
 
 /* host -> device / device -> host of one array (species n = 1.. for the 4-D

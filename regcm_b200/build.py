@@ -21,6 +21,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # bit-for-bit parity with a non-contracting FP64 evaluation of the Fortran
     "-fmad=false",
+    # ... and of the host-evaluated scalars that feed the kernels (boundary time weights, spectral weights)
+    "-Xcompiler", "-ffp-contract=off",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ]
 

@@ -103,8 +103,7 @@ static int check_cfg(const moloch_b200_config& f) {
   return 0;
 }
 
-static int sync_stream(Ctx& c) {
-  MB_CUDA(cudaStreamSynchronize(c.stream));
+int halo_timeout_check(Ctx& c) {
   if (c.p2p && c.flags) {   // a wait of the peer-store transport gave up: the ghost cells of that round are stale
     unsigned long long t = 0;
     MB_CUDA(cudaMemcpy(&t, c.flags + 5, sizeof(t), cudaMemcpyDeviceToHost));
@@ -113,6 +112,10 @@ static int sync_stream(Ctx& c) {
                   "arrived (ranks out of step, or a rank died); results after that round are invalid");
   }
   return 0;
+}
+int sync_stream(Ctx& c) {
+  MB_CUDA(cudaStreamSynchronize(c.stream));
+  return halo_timeout_check(c);
 }
 
 // ---- orchestration ----------------------------------------------------------
@@ -364,6 +367,7 @@ int moloch_b200_device_count(void) {
   return n;
 }
 
+int moloch_b200_destroy(moloch_b200_ctx* c);
 int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   if (!cfg || !out) return fail("moloch_b200_create: null argument");
   *out = nullptr;
@@ -403,7 +407,10 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
     return fail(m);
   }
   c->arena_bytes = total;
-  cudaMemset(c->arena, 0, total);
+  // every error exit below goes through moloch_b200_destroy (frees whatever exists by then)
+  auto bail = [&](const std::string& m) { moloch_b200_destroy(c); return fail(m); };
+  if ((e = cudaMemset(c->arena, 0, total)) != cudaSuccess)
+    return bail(std::string("moloch_b200_create: cudaMemset of the arena: ") + cudaGetErrorString(e));
   for (int id = 0; id < MB_NFIELDS; ++id) {
     if (id == MB_WZ || id == MB_P0) continue;
     c->f[id].p = (c->f[id].nspec > 0 && L.size[id] > 0) ? (double*)(c->arena + L.off[id]) : nullptr;
@@ -427,21 +434,19 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   for (auto& a : adv) tab.push_back(c->f[a.fid].p + (size_t)a.spec * kz * g.plane);
   for (int q = 0; q < 3; ++q) {
     if (!(cfg->do_bdy && cfg->nspgx > 0)) break;
-    if (cudaMalloc(&c->ibnd[q], (size_t)g.plane * sizeof(int)) != cudaSuccess) {
-      cudaFree(c->arena);
-      delete c;
-      return fail("moloch_b200_create: cudaMalloc of the ibnd planes failed");
-    }
+    if (cudaMalloc(&c->ibnd[q], (size_t)g.plane * sizeof(int)) != cudaSuccess)
+      return bail("moloch_b200_create: cudaMalloc of the ibnd planes failed");
   }
-  cudaMemcpy(c->d_ptrtab, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice);
+  if ((e = cudaMemcpy(c->d_ptrtab, tab.data(), tab.size() * sizeof(double*), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return bail(std::string("moloch_b200_create: upload of the field table: ") + cudaGetErrorString(e));
   c->h_ptrtab = tab;
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
+  if (const char* e = getenv("MOLOCH_B200_HALO_TIMEOUT_MS")) { if (atoll(e) >= 1) c->halo_timeout_cycles = atoll(e) * 2000000LL; }
   if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || v == 6 || v == 7) ? v : 5; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    cudaFree(c->arena);
-    delete c;
-    return fail("moloch_b200_create: cudaStreamCreate failed");
+    c->stream = nullptr;
+    return bail("moloch_b200_create: cudaStreamCreate failed");
   }
   c->own_stream = true;
   c->rdx = 1.0 / cfg->dx;              // Main/mod_params.F90:2193-2200
@@ -455,7 +460,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
 int moloch_b200_destroy(moloch_b200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   halo_free(*c);
   for (int q = 0; q < 3; ++q) if (c->ibnd[q]) cudaFree(c->ibnd[q]);
@@ -508,6 +513,9 @@ int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
     c->fuse_halo = value != 0;
     c->fuse_level = value >= 2 ? 2 : 1;
     c->adv_wait_valid = false;
+  } else if (n == "halo_timeout_ms") {
+    if (value < 1) return fail("set_option: halo_timeout_ms must be >= 1");
+    c->halo_timeout_cycles = (long long)value * 2000000LL;   // clock64 ticks at ~2 GHz
   } else {
     return fail("set_option: unknown option '" + n + "'");
   }
@@ -562,7 +570,7 @@ static int xfer_field(moloch_b200_ctx* c, int field, int n, double* host, int jl
   if (whole) {
     const size_t n_el = (size_t)nj * ni * nk;
     if (n_el > c->stage_doubles) {
-      MB_CUDA(cudaStreamSynchronize(c->stream));
+      if (sync_stream(*c)) return 1;
       if (c->stage) cudaFree(c->stage);
       c->stage_doubles = n_el + n_el / 8;
       MB_CUDA(cudaMalloc(&c->stage, c->stage_doubles * sizeof(double)));
@@ -588,7 +596,7 @@ static int xfer_field(moloch_b200_ctx* c, int field, int n, double* host, int jl
     else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
     MB_CUDA(cudaMemcpy3DAsync(&p, c->stream));
   }
-  if (!c->async_xfer) MB_CUDA(cudaStreamSynchronize(c->stream));
+  if (!c->async_xfer) return sync_stream(*c);
   return 0;
 }
 
@@ -747,6 +755,7 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
   // stream is enqueued after this point and therefore sees the uploaded slabs
   MB_CUDA(cudaStreamSynchronize(c->xs_down));
   MB_CUDA(cudaStreamSynchronize(c->xs_up));
+  if (rc == 0) rc = halo_timeout_check(*c);   // the downloaded state is host-visible now
   return rc;
 }
 
@@ -766,7 +775,7 @@ int moloch_b200_set_profile(moloch_b200_ctx* c, int which, const double* v, int 
   // stored 1-based: element k of the Fortran array at [k]
   MB_CUDA(cudaMemcpyAsync(c->prof[which] + 1, tmp.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
                           c->stream));
-  MB_CUDA(cudaStreamSynchronize(c->stream));
+  if (sync_stream(*c)) return 1;
   c->prof_n[which] = n;
   return 0;
 }
@@ -927,7 +936,7 @@ int moloch_b200_set_table(moloch_b200_ctx* c, int which, const double* v, int n)
   MB_CUDA(cudaSetDevice(c->device));
   if (!c->tab[which]) MB_CUDA(cudaMalloc(&c->tab[which], (size_t)n * sizeof(double)));
   MB_CUDA(cudaMemcpyAsync(c->tab[which], v, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  MB_CUDA(cudaStreamSynchronize(c->stream));
+  if (sync_stream(*c)) return 1;
   c->tab_n[which] = n;
   return 0;
 }
@@ -945,7 +954,7 @@ int moloch_b200_set_ibnd(moloch_b200_ctx* c, int which, const int32_t* ibnd, int
   int rc = 0;
   if (e != cudaSuccess) rc = fail(std::string("set_ibnd: ") + cudaGetErrorString(e));
   if (!rc) rc = k_ibnd_fill(*c, c->ibnd[which], tmp, jlo, jhi, ilo, ihi);
-  cudaStreamSynchronize(c->stream);
+  if (sync_stream(*c)) rc = 1;
   cudaFree(tmp);
   if (!rc) c->ibnd_set[which] = true;
   return rc;
@@ -964,7 +973,7 @@ int moloch_b200_profile_enable(moloch_b200_ctx* c, int on) {
 int moloch_b200_profile_read(moloch_b200_ctx* c, int cap, char (*names)[48], double* total_ms,
                              int64_t* launches) {
   if (!c) { fail("null context"); return -1; }
-  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { fail("profile_read: sync failed"); return -1; }
+  if (sync_stream(*c)) return -1;
   for (auto& ev : c->events) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) {

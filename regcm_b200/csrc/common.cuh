@@ -42,6 +42,7 @@ Layout make_layout(const moloch_b200_config& f);
 struct Peer {
   bool mapped = false;
   bool ipc = false;           // opened with cudaIpcOpenMemHandle (else same process)
+  bool owner = false;         // this side opened the mapping (a second side towards the same rank shares it)
   char* arena = nullptr;      // peer-visible base of the neighbour's arena
   moloch_b200_config cfg;
   Layout layout;
@@ -102,6 +103,7 @@ struct Ctx {
   Layout layout;
   unsigned long long* flags = nullptr;   // [0..3] arrival counters per side, [4] CTA counter, [5] timeout flag
   unsigned long long halo_seq = 0;
+  long long halo_timeout_cycles = 60000000000LL;   // ~30 s at 1.97 GHz (MOLOCH_B200_HALO_TIMEOUT_MS, set_option)
   bool p2p = false;
   bool fuse_halo = true;                 // sound-loop exchanges fused into producer/consumer kernels (p2p only)
   int fuse_level = 1;                    // 1: sub-steps 2.. of the sound loop only (the GPU-measured configuration);
@@ -148,6 +150,10 @@ struct Ctx {
 
 extern thread_local std::string g_err;
 int fail(const std::string& msg);
+// cudaStreamSynchronize(c.stream) + the peer-store transport's timeout marker: every point where the host
+// looks at results of the context's stream goes through this, so stale ghost cells never reach it unreported
+int sync_stream(Ctx& c);
+int halo_timeout_check(Ctx& c);
 #define MB_CUDA(call)                                                                   \
   do {                                                                                  \
     cudaError_t e__ = (call);                                                           \

@@ -172,7 +172,7 @@ int halo_group_sum(Ctx& c, double* data, size_t count, const int* members, int n
   if (mypos < 0) return fail("halo_group_sum: this rank is not a member of the group");
   const size_t need = (size_t)(nmem - 1) * count;
   if (need > c.gather_doubles) {
-    MB_CUDA(cudaStreamSynchronize(c.stream));
+    if (sync_stream(c)) return 1;
     if (c.gather_buf) cudaFree(c.gather_buf);
     c.gather_buf = nullptr;
     MB_CUDA(cudaMalloc(&c.gather_buf, need * sizeof(double)));
@@ -286,7 +286,7 @@ int halo_p2p_connect(Ctx& c, const void* blobs, int nranks) {
     if (b.rank != nbr[sd]) return fail("p2p_connect: blob table is not indexed by rank");
     bool shared = false;
     for (int q = 0; q < sd; ++q)
-      if (c.peer[q].mapped && nbr[q] == nbr[sd]) { pr = c.peer[q]; shared = true; break; }
+      if (c.peer[q].mapped && nbr[q] == nbr[sd]) { pr = c.peer[q]; pr.owner = false; shared = true; break; }
     if (shared) continue;
     if (b.pid == (unsigned long long)getpid()) {
       if (b.device != c.device) {
@@ -308,7 +308,7 @@ int halo_p2p_connect(Ctx& c, const void* blobs, int nranks) {
     pr.layout = make_layout(b.cfg);
     const Geo pg = geo_from_cfg(b.cfg);
     pr.NJ = pg.NJ; pr.j0 = pg.j0; pr.i0 = pg.i0; pr.plane = pg.plane;
-    pr.mapped = true;
+    pr.mapped = true; pr.owner = true;
   }
   c.p2p = true;
   return 0;
@@ -317,12 +317,10 @@ int halo_p2p_connect(Ctx& c, const void* blobs, int nranks) {
 static void halo_p2p_close(Ctx& c) {
   for (int sd = 0; sd < 4; ++sd) {
     Peer& pr = c.peer[sd];
-    if (pr.mapped && pr.ipc) {
-      bool dup = false;
-      for (int q = 0; q < sd; ++q) if (c.peer[q].mapped && c.peer[q].arena == pr.arena) dup = true;
-      if (!dup) cudaIpcCloseMemHandle(pr.arena);
-    }
-    pr.mapped = false;
+    // two sides may share one neighbour (2 ranks in a periodic direction): only the side that
+    // opened the IPC handle closes it
+    if (pr.mapped && pr.ipc && pr.owner) cudaIpcCloseMemHandle(pr.arena);
+    pr.mapped = false; pr.owner = false;
   }
   c.p2p = false;
 }
@@ -445,7 +443,7 @@ int halo_exchange_multi(Ctx& c, const HaloSpec* specs, int nspecs) {
     memset(&h, 0, sizeof(h));
     h.seq = ++c.halo_seq;
     h.flags = c.flags;
-    h.timeout_cycles = 6000000000LL;
+    h.timeout_cycles = c.halo_timeout_cycles;
     for (int sd = 0; sd < 4; ++sd) h.mode[sd] = (nbr[sd] < 0) ? 0 : (nbr[sd] == cf.rank ? 1 : 2);
     int nit = 0;
     long long tot = 0;
@@ -517,7 +515,7 @@ int halo_fence(Ctx& c) {
   memset(&h, 0, sizeof(h));
   h.seq = ++c.halo_seq;
   h.flags = c.flags;
-  h.timeout_cycles = 6000000000LL;
+  h.timeout_cycles = c.halo_timeout_cycles;
   for (int sd = 0; sd < 4; ++sd) {
     if (nbr[sd] < 0 || nbr[sd] == cf.rank) continue;
     const Peer& pr = c.peer[sd];
@@ -548,7 +546,7 @@ int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc) {
   const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
   memset(pc, 0, sizeof(*pc));
   memset(wc, 0, sizeof(*wc));
-  wc->seq = ++c.halo_seq; wc->flags = c.flags; wc->timeout_cycles = 6000000000LL;
+  wc->seq = ++c.halo_seq; wc->flags = c.flags; wc->timeout_cycles = c.halo_timeout_cycles;
   for (int sd = 0; sd < 4; ++sd) {
     if (nbr[sd] < 0 || nbr[sd] == cf.rank) continue;
     const Peer& pr = c.peer[sd];
@@ -639,7 +637,7 @@ int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, 
     if (has_remote) {
       if (!c.nccl_comm) return fail("halo_exchange: remote neighbour but moloch_b200_comm_init was not called");
       if ((size_t)off > c.halo_buf_doubles) {
-        MB_CUDA(cudaStreamSynchronize(c.stream));
+        if (sync_stream(c)) return 1;
         if (c.sendbuf) cudaFree(c.sendbuf);
         if (c.recvbuf) cudaFree(c.recvbuf);
         c.halo_buf_doubles = (size_t)off + (size_t)off / 4;

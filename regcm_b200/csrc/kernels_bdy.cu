@@ -239,7 +239,7 @@ int k_massck(Ctx& c, int what, double* out7) {
     MB_CUDA(cudaGetLastError());
   }
   MB_CUDA(cudaMemcpyAsync(out7, a.out, 7 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-  MB_CUDA(cudaStreamSynchronize(c.stream));
+  if (sync_stream(c)) return 1;
   return 0;
 }
 

@@ -369,10 +369,23 @@ class MolochB200:
         """The pipelined physics hand-off (moloch_b200_handoff): `down`/`up` are xfer_list() results;
         `physics(i1, i2)` is called on the host for each slab of rows once its state has arrived."""
         cb = None
+        raised = []
         if physics is not None:
-            cb = PHYSICS_FN(lambda user, i1, i2: int(physics(int(i1), int(i2)) or 0))
-        self._chk(self.lib.moloch_b200_handoff(self.ctx, down[0], down[1], up[0], up[1], int(nslabs),
-                                               C.cast(cb, C.c_void_p) if cb is not None else None, None))
+            def _cb(user, i1, i2):
+                # ctypes prints and swallows an exception raised inside a callback and returns 0 to C:
+                # keep it, report failure to the library (which stops before uploading that slab's
+                # tendencies) and re-raise once the C call has returned
+                try:
+                    return int(physics(int(i1), int(i2)) or 0)
+                except BaseException as exc:  # noqa: BLE001
+                    raised.append(exc)
+                    return 1
+            cb = PHYSICS_FN(_cb)
+        rc = self.lib.moloch_b200_handoff(self.ctx, down[0], down[1], up[0], up[1], int(nslabs),
+                                          C.cast(cb, C.c_void_p) if cb is not None else None, None)
+        if raised:
+            raise raised[0]
+        self._chk(rc)
 
     def set_option(self, name: str, value: int):
         """Kernel-variant switch ("wsolve", "waf", "fuse_halo"); all variants are bit-identical."""

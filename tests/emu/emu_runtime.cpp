@@ -307,8 +307,37 @@ unsigned emu_ballot(int pred) {
 }
 
 // ---- runtime API -------------------------------------------------------------------
-struct emuStream { int dummy; };
-struct emuEvent { long long t; };
+// Streams: kernels and H2D copies run at once (in program order, which is a legal
+// stream order), but a device-to-host cudaMemcpy*Async only LANDS when the host
+// synchronises with it -- cudaStreamSynchronize of its stream, cudaEventSynchronize
+// of an event recorded behind it, cudaDeviceSynchronize -- like on a real copy
+// engine.  The source is snapshotted at enqueue time (stream order: later work
+// of the stream cannot change what the copy reads).  Host code that looks at a
+// buffer before synchronising sees the old bytes, as it may on the GPU.
+struct PendingCopy { std::vector<char> data; char* dst; size_t dpitch, width, height; };
+struct emuStream { std::deque<PendingCopy> q; long long enq = 0, done = 0; };
+struct emuEvent { long long t; emuStream* s = nullptr; long long seq = 0; };
+namespace {
+thread_local emuStream g_stream0;
+emuStream* sq(cudaStream_t s) { return s ? s : &g_stream0; }
+void flush_to(emuStream* s, long long seq) {
+  while (!s->q.empty() && s->done < seq) {
+    PendingCopy& c = s->q.front();
+    for (size_t y = 0; y < c.height; ++y) memcpy(c.dst + y * c.dpitch, c.data.data() + y * c.width, c.width);
+    s->q.pop_front();
+    ++s->done;
+  }
+}
+void defer_d2h(cudaStream_t st, void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h) {
+  PendingCopy c;
+  c.data.resize(w * h);
+  for (size_t y = 0; y < h; ++y) memcpy(c.data.data() + y * w, (const char*)s + y * sp, w);
+  c.dst = (char*)d; c.dpitch = dp; c.width = w; c.height = h;
+  emuStream* q = sq(st);
+  q->q.push_back(std::move(c));
+  ++q->enq;
+}
+}  // namespace
 
 cudaError_t cudaGetLastError() { return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
@@ -331,13 +360,15 @@ cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
-cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind kind, cudaStream_t st) {
+  if (kind == cudaMemcpyDeviceToHost) { defer_d2h(st, d, n, s, n, n, 1); return cudaSuccess; }
   memmove(d, s, n);
   return cudaSuccess;
 }
-cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind,
-                              cudaStream_t) {
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind kind,
+                              cudaStream_t st) {
   if (w > dp || w > sp) return cudaErrorInvalidValue;
+  if (kind == cudaMemcpyDeviceToHost) { defer_d2h(st, d, dp, s, sp, w, h); return cudaSuccess; }
   for (size_t y = 0; y < h; ++y) memcpy((char*)d + y * dp, (const char*)s + y * sp, w);
   return cudaSuccess;
 }
@@ -351,18 +382,31 @@ cudaError_t cudaMemcpy3D(const cudaMemcpy3DParms* p) {
     }
   return cudaSuccess;
 }
-cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms* p, cudaStream_t) { return cudaMemcpy3D(p); }
-cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = new emuStream{0}; return cudaSuccess; }
+cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms* p, cudaStream_t st) {
+  if (p->kind != cudaMemcpyDeviceToHost) return cudaMemcpy3D(p);
+  const cudaPitchedPtr &sp = p->srcPtr, &dp = p->dstPtr;
+  for (size_t z = 0; z < p->extent.depth; ++z) {   // one deferred 2-D copy per z-plane
+    const char* s = (const char*)sp.ptr + ((p->srcPos.z + z) * sp.ysize + p->srcPos.y) * sp.pitch + p->srcPos.x;
+    char* d = (char*)dp.ptr + ((p->dstPos.z + z) * dp.ysize + p->dstPos.y) * dp.pitch + p->dstPos.x;
+    defer_d2h(st, d, dp.pitch, s, sp.pitch, p->extent.width, p->extent.height);
+  }
+  return cudaSuccess;
+}
+cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = new emuStream(); return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { flush_to(s, s->enq); delete s; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t s) { emuStream* q = sq(s); flush_to(q, q->enq); return cudaSuccess; }
+// (a rank only owns the streams it created: the context's copy streams are synchronised by name in the library)
+cudaError_t cudaDeviceSynchronize() { flush_to(&g_stream0, g_stream0.enq); return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent{0}; return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = emu::clock_now(); return cudaSuccess; }
-cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+  e->t = emu::clock_now(); e->s = sq(s); e->seq = e->s->enq;
+  return cudaSuccess;
+}
+cudaError_t cudaEventSynchronize(cudaEvent_t e) { if (e->s) flush_to(e->s, e->seq); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
   *ms = (float)((double)(b->t - a->t) * 1e-6);
   return cudaSuccess;

@@ -290,6 +290,8 @@ def test_halo_timeout_is_reported(_emulated_library):
     try:
         err = []
 
+        mr.ranks[0].set_option("halo_timeout_ms", 1500)   # the library default is 30 s
+
         def lonely():
             try:
                 mr.ranks[0].moloch(1)      # rank 1 never steps

@@ -59,8 +59,11 @@ def test_handoff_matches_field_transfers(nslabs):
         # slab rows of the first state array must already be on the host
         n, s, a, box = down_items[0]
         lo, hi = max(i1, box[2]) - box[2], min(i2, box[3]) - box[2]
+        # a slab that lies outside this array's rows (the widened `pai` box starts the slabs below
+        # row box[2] of `u`) has nothing to compare: hi < lo must not become a negative slice
+        ok = True if hi < lo else bool(np.array_equal(a[:, lo:hi + 1, :], want_down[0][:, lo:hi + 1, :]))
         # (exceptions do not propagate out of a ctypes callback: record, assert below)
-        seen.append((i1, i2, bool(np.array_equal(a[:, lo:hi + 1, :], want_down[0][:, lo:hi + 1, :]))))
+        seen.append((i1, i2, ok))
         return 0
 
     m.handoff(m.xfer_list(down_items), m.xfer_list(up_items), nslabs=nslabs, physics=physics)
@@ -101,6 +104,14 @@ def test_handoff_rejects_bad_arguments():
         m.handoff(m.xfer_list([("qx", 9, a, box)]), m.xfer_list([]))
     with pytest.raises(MolochError, match="physics callback"):
         m.handoff(m.xfer_list([("t", 0, a, box)]), m.xfer_list([]), physics=lambda i1, i2: 1)
+
+    def broken_physics(i1, i2):
+        raise ZeroDivisionError("the host physics failed")
+    up = m.pinned_empty(a.shape); up[...] = 5.0
+    m.set_local("tten", np.zeros_like(a), box)
+    with pytest.raises(ZeroDivisionError):      # re-raised after the C call, and nothing was uploaded
+        m.handoff(m.xfer_list([("t", 0, a, box)]), m.xfer_list([("tten", 0, up, box)]), nslabs=1, physics=broken_physics)
+    assert (m.get_local("tten", box) == 0.0).all()
     m.close()
 
 

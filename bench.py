@@ -336,6 +336,65 @@ def autotune_wsolve(m, wl, timed, all_min=lambda x: x, device=-1, lib=None):
     return best, rec
 
 
+# ---- parity of the path that is about to be timed ------------------------------------------
+# Before the timed region every rank runs PARITY_STEPS steps of a reduced cordex25 (same levels,
+# species, sponge, dt, dx; 64x64 columns) on the SAME decomposition, transport, halo fusion level
+# and kernel variants the timed region uses; rank 0 gathers the owned cells, hashes the prognostic
+# fields (SHA-256) and compares with tests/golden/bench_parity.json -- digests the CPU oracle
+# produced from the same inputs (scripts/make_bench_golden.py).  A mismatch fails the run.
+PARITY_STEPS = 2
+PARITY_FIELDS = ["u", "v", "w", "pai", "tetav", "t", "qx", "trac", "ux", "vx"]
+
+
+def parity_workload():
+    return S.small(S.WORKLOADS["cordex25"], 64, 64, S.WORKLOADS["cordex25"].kz)
+
+
+def parity_descriptor(wl):
+    return {"base": "cordex25", "grid": [wl.jx, wl.iy, wl.kz], "nqx": wl.nqx, "ntr": wl.ntr, "nspgx": wl.nspgx,
+            "dt_s": wl.dt, "dx_m": wl.dx, "advected_fields": wl.nfields}
+
+
+def digest(a) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a, dtype=np.float64).tobytes()).hexdigest()
+
+
+def run_parity(make_model, gather, rank: int) -> dict | None:
+    """`make_model(wl)`: an initialised MolochB200 of this rank configured like the timed model;
+    `gather(obj)`: list of every rank's obj on rank 0 (None elsewhere).  Returns the record on rank 0."""
+    from regcm_b200 import hostmodel as H
+    wl = parity_workload()
+    gold_path = os.path.join(ROOT, "tests", "golden", "bench_parity.json")
+    gold = json.load(open(gold_path))
+    m, inputs = make_model(wl)
+    m.moloch(PARITY_STEPS)
+    m.sync()
+    mine = {}
+    for n in PARITY_FIELDS:
+        own = H.owned(m.g, n)
+        mine[n] = (own, m.get_local(n, own))
+    shape = {n: m.global_shape(n) for n in PARITY_FIELDS}
+    inputs_ok = all(gold["inputs"].get(n) == d for n, d in inputs.items()) if inputs is not None else None
+    m.close()
+    parts = gather((mine, inputs_ok))
+    if rank != 0:
+        return None
+    got = {}
+    for n in PARITY_FIELDS:
+        glob = np.zeros(shape[n])
+        for part, _ in parts:
+            own, loc = part[n]
+            H.paste(glob, loc, own, own)
+        got[n] = digest(glob)
+    bad = [n for n in PARITY_FIELDS if got[n] != gold["fields"][n]]
+    ins = [ok for _, ok in parts if ok is not None]
+    return {"n_ranks": len(parts), "case": parity_descriptor(wl), "steps": PARITY_STEPS, "fields": PARITY_FIELDS,
+            "bit_exact": not bad, "mismatch": bad, "inputs_match_golden": (all(ins) if ins else None),
+            "golden": "tests/golden/bench_parity.json (CPU oracle, scripts/make_bench_golden.py)",
+            "how": "SHA-256 of the gathered global fields"}
+
+
 def base_line(wl, args, n_gpus):
     return {"metric": "MOLOCH dycore cell-updates/s", "unit": "cell-updates/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
@@ -356,6 +415,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--transport", default=os.environ.get("BENCH_TRANSPORT", "p2p"), choices=["p2p", "nccl"])
     ap.add_argument("--px", type=int, default=int(os.environ.get("BENCH_PX", "0")))
     ap.add_argument("--py", type=int, default=int(os.environ.get("BENCH_PY", "0")))
@@ -406,7 +466,7 @@ def main():
         px, py = None, None     # too thin: fall back to set_nproc's choice
     stream = torch.cuda.Stream()
 
-    def build_model():
+    def build_model(wl=wl, global_inputs=False):
         m = MolochB200(wl, rank=rank, nranks=world, px=px, py=py, device=local_rank).allocate_moloch()
         if world > 1:
             if args.transport == "nccl":
@@ -419,6 +479,10 @@ def main():
                 m.p2p_connect(blobs)
                 dist.barrier()
         m.set_stream(stream.cuda_stream)
+        if global_inputs:   # the small parity case: global arrays, cut to the rank by init_moloch
+            F, prof = S.model_inputs(wl)
+            m.init_moloch(F, prof)
+            return m, {n: digest(a) for n, a in {**F, **prof}.items()}
         # the rank's own arrays, generated locally (no global 3-D arrays: the large
         # workloads would not fit the host otherwise)
         fields, profiles, boxes = S.model_inputs_local(wl, m.g)
@@ -506,6 +570,26 @@ def main():
         m.set_option("fuse_halo", int(halo_fusion))
         m.moloch(1)
         m.sync()
+
+    # ---- parity of exactly this configuration (untimed) ------------------------------
+    def make_parity_model(pwl):
+        pm, ins = build_model(pwl, global_inputs=True)
+        pm.set_option("wsolve", wsolve_variant)
+        if world > 1 and args.transport == "p2p":
+            pm.set_option("fuse_halo", int(halo_fusion))
+        return pm, ins
+
+    def gather(obj):
+        if world == 1:
+            return [obj]
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out if rank == 0 else None
+    parity = None
+    if not args.no_parity:
+        parity = run_parity(make_parity_model, gather, rank)
+        if world > 1:
+            dist.barrier()
 
     # ---- device-resident throughput -----------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -595,12 +679,19 @@ def main():
             if fusion_note:
                 line["config"]["halo_fusion_note"] = fusion_note
         line.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "e2e": e2e,
-                     "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                     "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                      "kernels": kernels[:12], "finite": finite, "device_bytes": m.device_bytes()})
         print(json.dumps(line), flush=True)
     m.close()
+    bad = torch.tensor([1.0 if (parity is not None and not parity["bit_exact"]) else 0.0], device="cuda")
     if world > 1:
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
         dist.destroy_process_group()
+    if float(bad.item()) > 0.5:
+        if rank == 0:
+            print("bench.py: the parity case does NOT match the oracle's digests: " + ", ".join(parity["mismatch"]),
+                  file=sys.stderr)
+        return 1
     return 0
 
 

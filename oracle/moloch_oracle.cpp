@@ -1922,6 +1922,15 @@ int oracle_set_global(void* h, const char* name, const double* src) {
     v.assign(w.c.kz + 1, 0.0); for (int k = 1; k <= w.c.kz; ++k) v[k] = src[k - 1]; return 0; }
   if (s == "fcx") { w.fcx.assign(w.c.nspgx + 1, 0.0); for (int n = 1; n <= w.c.nspgx; ++n) w.fcx[n] = src[n - 1]; return 0; }
   if (s == "ffilt") { w.ffilt.assign(w.c.kz + 1, 0.0); for (int k = 1; k <= w.c.kz; ++k) w.ffilt[k] = src[k - 1]; return 0; }
+  // init_moloch's 1-D tables (Main/mod_moloch.F90:273-274, 294-299): settable so that a run can start from the
+  // host model's own tables (bench.py's parity fixture starts the oracle from exactly the arrays the library gets)
+  if (s == "xkdamp" || s == "xknu" || s == "gzitakh" || s == "gzitak") {
+    std::vector<double>& v = (s == "xkdamp") ? w.xkdamp : (s == "xknu") ? w.xknu : (s == "gzitakh") ? w.gzitakh : w.gzitak;
+    const int n = (s == "gzitak") ? w.c.kz + 1 : w.c.kz;
+    if ((int)v.size() < n + 1) v.assign(n + 1, 0.0);
+    for (int k = 1; k <= n; ++k) v[k] = src[k - 1];
+    return 0;
+  }
   const bool perj = w.r[0].g.band, peri = w.r[0].g.crm;
   for (auto& r : w.r) {
     std::vector<FieldInfo> f;

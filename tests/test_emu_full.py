@@ -204,7 +204,7 @@ def test_decomposed_with_drifting_ranks(name, px, py, monkeypatch, _emulated_lib
     M.test_decomposed_bit_exact(name, wl, px, py, "p2p", monkeypatch)      # "p2p" = every fusable round fused
 
 
-def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
+def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys, tmp_path):
     """bench.py's whole N=1 flow (model construction with the fusion-level check, timed steps, per-kernel profile,
     roofline, end-to-end leg, CPU baseline, the JSON line) on the emulated library with a stand-in for the few
     torch.cuda calls it makes: catches script errors before the script meets a GPU box."""
@@ -255,6 +255,21 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
     monkeypatch.setattr(M, "_lib", _emulated_library)          # what load_library() hands to MolochB200
     monkeypatch.setitem(S.WORKLOADS, "tiny", S.small(S.WORKLOADS["cordex25"], 40, 36, 9, ntr=2, nspgx=5))
     monkeypatch.setattr(bench, "cpu_sample_workload", lambda wl: wl)
+    # the parity block against a golden file of the same tiny case, made here by the oracle the way
+    # scripts/make_bench_golden.py makes the committed one
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_bench_golden", os.path.join(bench.ROOT, "scripts", "make_bench_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    pwl = S.small(S.WORKLOADS["cordex25"], 24, 20, 9, ntr=2, nspgx=5)
+    monkeypatch.setattr(bench, "parity_workload", lambda: pwl)
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    os.makedirs(tmp_path / "tests" / "golden")
+    o, F, prof = G.oracle_from_host_inputs(pwl)
+    o.step(bench.PARITY_STEPS)
+    with open(tmp_path / "tests" / "golden" / "bench_parity.json", "w") as f:
+        json.dump({"inputs": {n: bench.digest(a) for n, a in {**F, **prof}.items()},
+                   "fields": {n: bench.digest(o.get(n)) for n in bench.PARITY_FIELDS}}, f)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "tiny", "--steps", "2", "--warmup", "1"])
     monkeypatch.delenv("RANK", raising=False)
     monkeypatch.delenv("WORLD_SIZE", raising=False)
@@ -269,6 +284,7 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys):
     assert set(line["e2e"]["ms_per_step_by_handoff"]) == {"sequential", "pipelined"}
     assert line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
+    assert line["parity"]["bit_exact"] is True and line["parity"]["inputs_match_golden"] is True, line["parity"]
     tune = line["config"]["variant_tuning"]["wsolve"]
     assert tune["v6_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 2, 6, 7], tune
     assert line["config"]["wsolve_variant"] in (5, 2, 6, 7) and set(tune["ms_per_step"]) == {"5", "2", "6", "7"}

@@ -2,7 +2,8 @@
 
 * config 1 (`Testing/ideal.in` shape, 500x100x60, doubly periodic): the CUDA path against the CPU oracle,
   bit for bit, after a short integration (the oracle needs about half a second per step there);
-* config 3 (cordex25, 400x400x41, F = 20) -- the benchmark configuration, too large for the oracle in a test --
+* config 3 (cordex25, 400x400x41, F = 20) -- the benchmark configuration -- against the CPU oracle at FULL size,
+  bit for bit, after two steps (the oracle needs about a second per step on the GPU box's host cores), and
   through size-independent properties of the path: scaling a tracer by a power of two scales its solution
   exactly (WAF fluxes are homogeneous of degree one in the advected field, the limiter only sees ratios, and
   status_update's clipping at zero is scale-free), an untouched copy of a tracer stays equal to the original,
@@ -35,6 +36,12 @@ def check_oracle_parity(wl, nsteps):
 
 def test_config1_ideal_full_size_bit_exact():
     check_oracle_parity(S.WORKLOADS["ideal"], 6)
+
+
+def test_config3_cordex25_full_size_bit_exact():
+    """The benchmark configuration itself (bench.py's default workload), every prognostic field and all ten
+    tracers, 400x400x41, against the oracle."""
+    check_oracle_parity(S.WORKLOADS["cordex25"], 2)
 
 
 def check_tracer_properties(wl, nsteps):

@@ -15,6 +15,7 @@ from regcm_b200 import synthetic as S
 from util import make_oracle
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
 FLAT = S.small(S.WORKLOADS["isc24_small"], 24, 20, 10)
 HILLS = S.small(S.WORKLOADS["isc24_small"], 28, 22, 10, oro="sine", oro_h=900.0, msf_amp=0.04, clat=35.0)
 LAM = S.small(S.WORKLOADS["cordex25"], 30, 26, 12, ntr=2, nspgx=5)
@@ -195,3 +196,21 @@ def test_oracle_reproduces_golden_fixtures():
                 c = now[name]["steps"][n][f]
                 assert abs(c["sum"] - g["sum"]) <= 1e-9 * max(1.0, abs(g["sum"])), (name, n, f)
                 assert c["sha256"] == g["sha256"], f"{name} step {n} {f}: bits changed"
+
+
+def test_oracle_reproduces_bench_parity_golden():
+    """tests/golden/bench_parity.json (what `bench.py --gpus N` checks its N ranks against before it times them)
+    is the oracle's: regenerate the digests from the host model's inputs and compare, inputs included."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("make_bench_golden", os.path.join(ROOT, "scripts", "make_bench_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    import bench
+    gold = json.load(open(os.path.join(HERE, "golden", "bench_parity.json")))
+    wl = bench.parity_workload()
+    assert gold["workload"] == bench.parity_descriptor(wl) and gold["steps"] == bench.PARITY_STEPS
+    o, F, prof = G.oracle_from_host_inputs(wl)
+    assert {n: bench.digest(a) for n, a in {**F, **prof}.items()} == gold["inputs"]
+    o.step(bench.PARITY_STEPS)
+    assert {n: bench.digest(o.get(n)) for n in bench.PARITY_FIELDS} == gold["fields"]

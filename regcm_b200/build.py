@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmoloch_b200.so")
-SOURCES = ["kernels.cu", "kernels_waf.cu", "kernels_bdy.cu", "halo.cu", "capi.cu"]
+SOURCES = ["kernels.cu", "kernels_sound.cu", "kernels_waf.cu", "kernels_bdy.cu", "halo.cu", "capi.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "geo.h"), os.path.join(CSRC, "bdy_cells.h"),
            os.path.join(HERE, "..", "include", "moloch_b200.h")]
 

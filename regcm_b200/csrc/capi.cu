@@ -59,7 +59,7 @@ Layout make_layout(const moloch_b200_config& f) {
     int nk, nspec; field_shape(f, id, nk, nspec);
     put(id, pl * nk * (size_t)nspec);
   }
-  put(SL_UD, pl * kz); put(SL_VD, pl * kz); put(SL_ZB, pl * kz);
+  put(SL_UD, 0); put(SL_VD, 0); put(SL_ZB, pl * kz);   // ud, vd: gone with round 2's uvupdate2
   L.stride2d = al(pl); put(SL_2D, L.stride2d * 4);
   L.stridezr = al(pl * kz); put(SL_ZR, L.stridezr * 2);
   put(SL_WZ, pl * kz * (size_t)nadv); put(SL_P0, pl * kz * (size_t)nadv);
@@ -119,60 +119,69 @@ int sync_stream(Ctx& c) {
 }
 
 // ---- orchestration ----------------------------------------------------------
+// Ghost cells of u and v as the sound loop needs them.  The reference exchanges u left/right and v
+// bottom/top, one point (:570-571); moloch_sound_div also evaluates zdiv2 on the one-cell ring around
+// the rank (instead of receiving it, :745/:535), which reads u two columns / one row and v one column /
+// two rows beyond the owned box, corner ghosts included.  Corners only exist on a 2-D decomposition:
+// there the rows travel in a second round that carries the ghost columns of the first along.
+// Advection's own exchange (:1532-1533: u left/right 2, v bottom/top 2) is a subset.
+static int exchange_uv_wide(Ctx& c, const HaloItem* extra, int nextra) {
+  const int kz = c.g.kz;
+  const moloch_b200_config& f = c.cfg;
+  const bool has_lr = f.nbr_left >= 0 || f.nbr_right >= 0, has_bt = f.nbr_bottom >= 0 || f.nbr_top >= 0;
+  const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
+  HaloSpec sp[5];
+  int n = 0;
+  if (nextra > 0) sp[n++] = {extra, nextra, HS_CROSS, 1, true, true, 0};
+  if (has_lr && has_bt) {
+    sp[n++] = {&iu, 1, HS_U, 2, true, false, 0};
+    sp[n++] = {&iv, 1, HS_V, 1, true, false, 0};
+    if (halo_exchange_multi(c, sp, n)) return 1;
+    const HaloSpec s2[2] = {{&iu, 1, HS_U, 1, false, true, 2}, {&iv, 1, HS_V, 2, false, true, 1}};
+    return halo_exchange_multi(c, s2, 2);
+  }
+  sp[n++] = {&iu, 1, HS_U, 2, true, false, 0};
+  sp[n++] = {&iv, 1, HS_V, 1, true, false, 0};
+  sp[n++] = {&iu, 1, HS_U, 1, false, true, 0};
+  sp[n++] = {&iv, 1, HS_V, 2, false, true, 0};
+  return halo_exchange_multi(c, sp, n);
+}
+
 // for_adv: called from dynamical_core, `advection` follows at once -- with the fused transport the last
 // sub-step's uvupdate then delivers advection's 2-wide u, v ghosts (:1532-1533) and destagger waits for them
 static int do_sound(Ctx& c, bool for_adv = false) {
   const double dts = c.dtsound;
   const int kz = c.g.kz;
   const int nsound = c.cfg.mo_nsound;
-  const bool damp = c.cfg.mo_divdamp || c.cfg.mo_divfilter;
-  // Peer-store transport: the three exchanges of a sub-step are fused into the kernels around
-  // them (see common.cuh): the producer of zdiv2 / pai / u, v stores the edge cells it computes
-  // into the neighbours' ghost cells, the consumer waits for the neighbours' word.  The edge
-  // cells the sound kernels never update (physical-boundary rows and columns, whose values the
-  // advection and the boundary update change between two sound calls) travel once, in the one
-  // full round at the start of the call.
+  const moloch_b200_config& cf = c.cfg;
+  // Peer-store transport: the two exchanges of a sub-step (pai :673; u, v :570-571) are fused into the
+  // kernels around them (see common.cuh): wsolve / uvupdate2 store the edge cells they compute into the
+  // neighbours' ghost cells, uvupdate2 / sound_div wait for the neighbours' word.  The edge cells the
+  // sound kernels never update (physical-boundary rows and columns, whose values the advection and the
+  // boundary update change between two sound calls) travel once, in the full round at the start of the
+  // call.  u, v pushes are fused on 1-D decompositions only (no corner ghosts there).
   const bool fused = halo_fused_available(c);
   const bool fused_all = fused && c.fuse_level >= 2;   // also the first sub-step (and pai in the full round)
-  if (!fused_all) for_adv = false;
+  const bool one_d = !((cf.nbr_left >= 0 || cf.nbr_right >= 0) && (cf.nbr_bottom >= 0 || cf.nbr_top >= 0));
+  const bool fused_uv = fused && one_d;
+  if (!(fused_all && fused_uv)) for_adv = false;
   HaloItem it;
   {
-    // tetav (:562) together with the first sub-step's u, v (:570-571) in ONE round: tetavf_init in
-    // between is a column operation on owned cells and touches neither u, v nor any ghost cell.
-    // Fused transport: pai too (its :673 exchange of every sub-step becomes wsolve's edge push).
+    // tetav (:562) together with the first sub-step's u, v: tetavf_init in between is a column operation
+    // on owned cells.  Fused transport: pai too (its :673 exchange of every sub-step becomes wsolve's push).
     const HaloItem itv[2] = {{c.f[MB_TETAV].p, kz}, {c.f[MB_PAI].p, kz}};
-    const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
-    const int wuv = (fused && for_adv) ? 2 : 1;   // boundary rows/columns of u, v for the 2-wide pushes below
-    const HaloSpec sp[3] = {{itv, fused_all ? 2 : 1, HS_CROSS, 1, true, true, 0}, {&iu, 1, HS_U, wuv, true, false, 0},
-                            {&iv, 1, HS_V, wuv, false, true, 0}};
-    if (halo_exchange_multi(c, sp, 3)) return 1;
+    if (exchange_uv_wide(c, itv, fused_all ? 2 : 1)) return 1;
   }
   c.adv_wait_valid = false;
   if (k_tetavf_init(c)) return 1;
-  WaitCtl w_uv = {}, w_zd = {}, w_pai = {};
-  PushCtl p_uv = {}, p_zd = {}, p_pai = {};
-  EdgePush e_u = {}, e_v = {}, e_zd = {}, e_pai = {};
-  bool uv_pushed = false;   // u, v ghosts were delivered by the previous sub-step's uvupdate
+  WaitCtl w_uv = {}, w_pai = {};
+  PushCtl p_uv = {}, p_pai = {};
+  EdgePush e_u = {}, e_v = {}, e_pai = {};
+  bool uv_pushed = false;   // u, v ghosts were delivered by the previous sub-step's uvupdate2
   for (int ns = 0; ns < nsound; ++ns) {
     const bool f = fused && (fused_all || ns > 0);
-    if (!uv_pushed && ns > 0) {   // :570-571, one round (the first sub-step's came with tetav above)
-      const HaloItem iu = {c.f[MB_U].p, kz}, iv = {c.f[MB_V].p, kz};
-      const HaloSpec sp[2] = {{&iu, 1, HS_U, 1, true, false, 0}, {&iv, 1, HS_V, 1, false, true, 0}};
-      if (halo_exchange_multi(c, sp, 2)) return 1;
-    }
-    if (f && damp) {
-      if (halo_fused_begin(c, &p_zd, &w_zd)) return 1;
-      if (halo_fused_edge(c, c.f[MB_ZDIV2].p, HS_CROSS, true, true, &e_zd)) return 1;
-    }
-    if (k_sound_pre(c, dts, uv_pushed ? &w_uv : nullptr, (f && damp) ? &p_zd : nullptr, (f && damp) ? &e_zd : nullptr))
-      return 1;
-    if (damp) {
-      if (!f) {
-        it = {c.f[MB_ZDIV2].p, kz};
-        if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :745 (:535 is redundant)
-      }
-      if (k_divdamp_filter(c, dts, f ? &w_zd : nullptr)) return 1;
-    }
+    if (!uv_pushed && ns > 0 && exchange_uv_wide(c, nullptr, 0)) return 1;
+    if (k_sound_div(c, dts, uv_pushed ? &w_uv : nullptr)) return 1;
     if (f) {
       if (halo_fused_begin(c, &p_pai, &w_pai)) return 1;
       if (halo_fused_edge(c, c.f[MB_PAI].p, HS_CROSS, true, true, &e_pai)) return 1;
@@ -182,16 +191,15 @@ static int do_sound(Ctx& c, bool for_adv = false) {
       it = {c.f[MB_PAI].p, kz};
       if (halo_exchange(c, &it, 1, HS_CROSS, 1, true, true)) return 1;  // :673
     }
-    // this uvupdate delivers the next sub-step's u, v ghosts
-    const bool push_uv = fused && (ns + 1 < nsound || for_adv);
+    // this uvupdate2 delivers the next sub-step's u, v ghosts
+    const bool push_uv = fused_uv && (ns + 1 < nsound || for_adv);
     if (push_uv) {
-      const int wuv = for_adv ? 2 : 1;
       if (halo_fused_begin(c, &p_uv, &w_uv)) return 1;
-      if (halo_fused_edge(c, c.f[MB_U].p, HS_U, true, false, &e_u, wuv)) return 1;
-      if (halo_fused_edge(c, c.f[MB_V].p, HS_V, false, true, &e_v, wuv)) return 1;
+      if (halo_fused_edge(c, c.f[MB_U].p, HS_U, true, true, &e_u, 2, 1)) return 1;
+      if (halo_fused_edge(c, c.f[MB_V].p, HS_V, true, true, &e_v, 1, 2)) return 1;
     }
-    if (k_uvupdate(c, dts, f ? &w_pai : nullptr, push_uv ? &p_uv : nullptr, push_uv ? &e_u : nullptr,
-                   push_uv ? &e_v : nullptr)) return 1;
+    if (k_uvupdate2(c, dts, f ? &w_pai : nullptr, push_uv ? &p_uv : nullptr, push_uv ? &e_u : nullptr,
+                    push_uv ? &e_v : nullptr)) return 1;
     uv_pushed = push_uv;
   }
   if (uv_pushed) { c.adv_wait = w_uv; c.adv_wait_valid = true; }   // consumed by advection's destagger
@@ -415,7 +423,6 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
     if (id == MB_WZ || id == MB_P0) continue;
     c->f[id].p = (c->f[id].nspec > 0 && L.size[id] > 0) ? (double*)(c->arena + L.off[id]) : nullptr;
   }
-  c->ud = (double*)(c->arena + L.off[SL_UD]); c->vd = (double*)(c->arena + L.off[SL_VD]);
   c->zdiv2b = (double*)(c->arena + L.off[SL_ZB]);
   c->mx2 = (double*)(c->arena + L.off[SL_2D]); c->rmx = (double*)(c->arena + L.off[SL_2D] + L.stride2d);
   c->rmu = (double*)(c->arena + L.off[SL_2D] + 2 * L.stride2d);

@@ -51,9 +51,9 @@ struct Peer {
 };
 
 // control blocks of the fused halo rounds (see "fused halo rounds" below)
-struct EdgePush {            // one array, edges of width nex (1 or 2)
+struct EdgePush {            // one array, edges nexj columns (left/right) and nexi rows (bottom/top) wide
   int j1, j2, i1, i2;        // owned box of the array's staggering
-  int nex;
+  int nexj, nexi;
   double* q[4];              // the array inside each neighbour's arena (null: side not exchanged)
   int dj[4], di[4];          // index shift into the neighbour's numbering (periodic wrap)
 };
@@ -85,7 +85,7 @@ struct Ctx {
   struct Field { double* p = nullptr; int nk = 0; int klo = 1; int nspec = 1; bool is2d = false; };
   Field f[MB_NFIELDS];
   // extra device arrays
-  double *ud, *vd, *zdiv2b, *mx2, *rmx, *rmu, *rmv;
+  double *zdiv2b, *mx2, *rmx, *rmu, *rmv;
   double *zru, *zrd;      // static ratios of the vertical WAF pass
   int waf_impl = 2;       // 1: per-loop kernels, 2: field-batched fused kernels
   int wsolve_impl = 5;    // 2: CTA-parallel coefficients + one-warp sweeps, 5: thread per column with a cp.async ring,
@@ -200,13 +200,13 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 #endif
 }
 __device__ __forceinline__ void edge_push(const PushCtl& pc, const EdgePush& e, int j, int i, int k, double v) {
-  if (e.q[0] && j >= e.j1 && j < e.j1 + e.nex && i >= e.i1 && i <= e.i2)
+  if (e.q[0] && j >= e.j1 && j < e.j1 + e.nexj && i >= e.i1 && i <= e.i2)
     e.q[0][(long long)(k - 1) * pc.pplane[0] + (long long)(i + e.di[0] - pc.pi0[0]) * pc.pNJ[0] + (j + e.dj[0] - pc.pj0[0])] = v;
-  if (e.q[1] && j <= e.j2 && j > e.j2 - e.nex && i >= e.i1 && i <= e.i2)
+  if (e.q[1] && j <= e.j2 && j > e.j2 - e.nexj && i >= e.i1 && i <= e.i2)
     e.q[1][(long long)(k - 1) * pc.pplane[1] + (long long)(i + e.di[1] - pc.pi0[1]) * pc.pNJ[1] + (j + e.dj[1] - pc.pj0[1])] = v;
-  if (e.q[2] && i >= e.i1 && i < e.i1 + e.nex && j >= e.j1 && j <= e.j2)
+  if (e.q[2] && i >= e.i1 && i < e.i1 + e.nexi && j >= e.j1 && j <= e.j2)
     e.q[2][(long long)(k - 1) * pc.pplane[2] + (long long)(i + e.di[2] - pc.pi0[2]) * pc.pNJ[2] + (j + e.dj[2] - pc.pj0[2])] = v;
-  if (e.q[3] && i <= e.i2 && i > e.i2 - e.nex && j >= e.j1 && j <= e.j2)
+  if (e.q[3] && i <= e.i2 && i > e.i2 - e.nexi && j >= e.j1 && j <= e.j2)
     e.q[3][(long long)(k - 1) * pc.pplane[3] + (long long)(i + e.di[3] - pc.pi0[3]) * pc.pNJ[3] + (j + e.dj[3] - pc.pj0[3])] = v;
 }
 // First statement of a consumer kernel whose grid tiles the rank's box with
@@ -256,11 +256,11 @@ __device__ __forceinline__ void halo_sync(const WaitCtl& w, int reach = 1, int n
 // ---- launchers (kernels.cu) ------------------------------------------------
 int k_reset_tendencies(Ctx& c);
 int k_tetavf_init(Ctx& c);
-int k_sound_pre(Ctx& c, double dts, const WaitCtl* wc = nullptr, const PushCtl* pc = nullptr, const EdgePush* ez = nullptr);
-int k_divdamp_filter(Ctx& c, double dts, const WaitCtl* wc = nullptr);
+// kernels_sound.cu
+int k_sound_div(Ctx& c, double dts, const WaitCtl* wc = nullptr);
+int k_uvupdate2(Ctx& c, double dts, const WaitCtl* wc = nullptr, const PushCtl* pc = nullptr, const EdgePush* eu = nullptr,
+                const EdgePush* ev = nullptr);
 int k_wsolve(Ctx& c, double dts, bool last, const PushCtl* pc = nullptr, const EdgePush* ep = nullptr);
-int k_uvupdate(Ctx& c, double dts, const WaitCtl* wc = nullptr, const PushCtl* pc = nullptr, const EdgePush* eu = nullptr,
-               const EdgePush* ev = nullptr);
 int k_sfinish(Ctx& c);
 int k_destagger(Ctx& c, const WaitCtl* wc = nullptr, const PushCtl* pc = nullptr, const EdgePush* eux = nullptr,
                 const EdgePush* evx = nullptr);
@@ -303,7 +303,7 @@ int halo_fence(Ctx& c);
 // fused rounds: allocate the round, describe one array's edges
 bool halo_fused_available(const Ctx& c);
 int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc);
-int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep, int nex = 1);
+int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep, int nexj = 1, int nexi = -1);
 // geometry of the neighbours' boxes only (no round number): for a producer that pushes ahead of the round
 // in which the last producer of the same array signals
 int halo_push_ctl(Ctx& c, PushCtl* pc);

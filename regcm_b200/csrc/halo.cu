@@ -326,7 +326,7 @@ static void halo_p2p_close(Ctx& c) {
 }
 
 int halo_exchange(Ctx& c, const HaloItem* items, int nitems, int stag, int nex, bool lr, bool bt, int ext);
-constexpr int PUSH_MAX_ITEMS = 48, PUSH_MAX_GROUPS = 4;
+constexpr int PUSH_MAX_ITEMS = 48, PUSH_MAX_GROUPS = 6;
 struct PushGroup {
   int j1, j2, i1, i2;        // owned box of the group's staggering
   int elo[4], elen[4];       // edge run of each side
@@ -569,11 +569,11 @@ int halo_push_ctl(Ctx& c, PushCtl* pc) {
 
 // Edges of width nex of one array (exchange_lr / _bt / _lrbt semantics, no corners).
 // A periodic self-neighbour cannot be fused (the caller checks fusable()).
-int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep, int nex) {
+int halo_fused_edge(Ctx& c, double* array, int stag, bool lr, bool bt, EdgePush* ep, int nexj, int nexi) {
   const moloch_b200_config& cf = c.cfg;
   const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
   memset(ep, 0, sizeof(*ep));
-  ep->nex = nex;
+  ep->nexj = nexj; ep->nexi = nexi < 0 ? nexj : nexi;
   owned_box(cf, stag, ep->j1, ep->j2, ep->i1, ep->i2);
   for (int sd = 0; sd < 4; ++sd) {
     const bool on = (nbr[sd] >= 0) && ((sd < 2) ? lr : bt);

@@ -96,122 +96,7 @@ int k_tetavf_init(Ctx& c) {
   return 0;
 }
 
-// ---------------------------------------------------------------------------
-// K3+K4  partial s, horizontal divergence zdiv2                       :582-618
-// (the ud/vd snapshots of :573-578 are not materialised: divergence damping
-// writes its result to ud/vd instead of u/v, so u/v keep the pre-damping values
-// the Coriolis terms need)
-// ---------------------------------------------------------------------------
-__global__ void moloch_sound_pre(Geo g, const double* __restrict__ u, const double* __restrict__ v,
-                                 double* __restrict__ s,
-                                 double* __restrict__ w, double* __restrict__ zdiv2,
-                                 const double* __restrict__ fmz, const double* __restrict__ rfmzu,
-                                 const double* __restrict__ rfmzv, const double* __restrict__ hx,
-                                 const double* __restrict__ hy, const double* __restrict__ mx,
-                                 const double* __restrict__ mx2, const double* __restrict__ rmu,
-                                 const double* __restrict__ rmv, const double* __restrict__ gzitak,
-                                 double dtrdx, double dtrdy, WaitCtl wc, PushCtl pc, EdgePush ez) {
-  halo_sync(wc);   // u, v ghosts of a fused round
-  THREAD_JIK(g.jde1, g.ide1, 1)
-  const bool inu = (i >= g.ice1 && i <= g.ice2);
-  const bool inv = (j >= g.jce1 && j <= g.jce2);
-  if (j <= g.jde2 && i <= g.ide2 && inu && inv) {
-    const long long id = IX(j, i, k);
-    const long long i2 = IX2(j, i);
-    const int kz = g.kz;
-    const double u0 = u[id], v0 = v[id];
-    const double u1 = u[id + 1], v1 = v[id + g.NJ];
-    {
-      const double zvm = dtrdy * v0 * rfmzv[id] * rmv[i2];
-      const double zvp = dtrdy * v1 * rfmzv[id + g.NJ] * rmv[i2 + g.NJ];
-      double zd;
-      if (g.lrotllr) {
-        const double zum = dtrdx * u0 * rfmzu[id];
-        const double zup = dtrdx * u1 * rfmzu[id + 1];
-        zd = fmz[id] * mx[i2] * ((zup - zum) + (zvp - zvm));
-      } else {
-        const double zum = dtrdx * u0 * rfmzu[id] * rmu[i2];
-        const double zup = dtrdx * u1 * rfmzu[id + 1] * rmu[i2 + 1];
-        zd = fmz[id] * mx2[i2] * ((zup - zum) + (zvp - zvm));
-      }
-      zdiv2[id] = zd;
-      if (pc.mask) edge_push(pc, ez, j, i, k, zd);
-    }
-    if (in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) {
-      const double hx0 = hx[i2], hx1 = hx[i2 + 1], hy0 = hy[i2], hy1 = hy[i2 + g.NJ];
-      if (k >= 2) {
-        const long long im = id - g.plane;
-        const double zuh = (u0 + u[im]) * hx0 + (u1 + u[im + 1]) * hx1;
-        const double zvh = (v0 + v[im]) * hy0 + (v1 + v[im + g.NJ]) * hy1;
-        s[id] = -0.25 * (zuh + zvh) * gzitak[k];
-      }
-      if (k == kz) {
-        const double zuh = u0 * hx0 + u1 * hx1;
-        const double zvh = v0 * hy0 + v1 * hy1;
-        const double sk = -0.5 * (zuh + zvh);
-        s[id + g.plane] = sk;
-        w[id + g.plane] = -sk;
-      }
-    }
-  }
-}
-int k_sound_pre(Ctx& c, double dts, const WaitCtl* wc, const PushCtl* pc, const EdgePush* ez) {
-  const Geo& g = c.g;
-  const double dtrdx = dts * c.rdx, dtrdy = dts * c.rdx;
-  const WaitCtl w0 = wc ? *wc : WaitCtl{};
-  const PushCtl p0 = pc ? *pc : PushCtl{};
-  const EdgePush e0 = ez ? *ez : EdgePush{};
-  LaunchScope ls(c, KID_SOUND_PRE);
-  moloch_sound_pre<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
-      g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_ZDIV2].p, c.f[MB_FMZ].p,
-      c.f[MB_RFMZU].p, c.f[MB_RFMZV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFX].p, c.mx2, c.rmu, c.rmv,
-      c.prof[MB_GZITAK], dtrdx, dtrdy, w0, p0, e0);
-  MB_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// ---------------------------------------------------------------------------
-// K5+K6  divergence damping of u,v and 5-point filter of zdiv2   :738-765,531-543
-// zdiv2 (halo 1 valid) -> zdiv2b (interior); damped u,v -> ud,vd.
-// ---------------------------------------------------------------------------
-__global__ void moloch_divdamp_filter(Geo g, const double* __restrict__ u, const double* __restrict__ v,
-                                      double* __restrict__ ud, double* __restrict__ vd,
-                                      const double* __restrict__ zdiv2, double* __restrict__ zdiv2b,
-                                      const double* __restrict__ mu, const double* __restrict__ mv,
-                                      const double* __restrict__ xkdamp, const double* __restrict__ xknu,
-                                      double dxrdt, int do_damp, int do_filter, WaitCtl wc) {
-  halo_sync(wc);   // zdiv2 ghosts of a fused round
-  THREAD_JIK(g.jde1, g.ide1, 1)
-  if (j > g.jde2 || i > g.ide2) return;
-  const long long id = IX(j, i, k);
-  const long long i2 = IX2(j, i);
-  const double z0 = zdiv2[id];
-  const double zw = zdiv2[id - 1], zs = zdiv2[id - g.NJ];
-  if (do_damp) {
-    if (in_box(j, i, g.jdi1, g.jdi2, g.ici1, g.ici2)) {
-      const double xdam = dxrdt * xkdamp[k] * mu[i2];
-      ud[id] = u[id] + xdam * (z0 - zw);   // damped u; u itself keeps the :574 snapshot
-    }
-    if (in_box(j, i, g.jci1, g.jci2, g.idi1, g.idi2)) {
-      const double xdam = g.lrotllr ? dxrdt * xkdamp[k] : dxrdt * xkdamp[k] * mv[i2];
-      vd[id] = v[id] + xdam * (z0 - zs);
-    }
-  }
-  if (do_filter && in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) {
-    const double lap = (zw + zdiv2[id + 1] + zs + zdiv2[id + g.NJ] - 4.0 * z0);
-    zdiv2b[id] = z0 + xknu[k] * lap;
-  }
-}
-int k_divdamp_filter(Ctx& c, double dts, const WaitCtl* wc) {
-  const Geo& g = c.g;
-  const WaitCtl w0 = wc ? *wc : WaitCtl{};
-  LaunchScope ls(c, KID_DIVDAMP);
-  moloch_divdamp_filter<<<grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
-      g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_ZDIV2].p, c.zdiv2b, c.f[MB_MSFU].p, c.f[MB_MSFV].p,
-      c.prof[MB_XKDAMP], c.prof[MB_XKNU], c.cfg.dx / dts, c.cfg.mo_divdamp, c.cfg.mo_divfilter, w0);
-  MB_CUDA(cudaGetLastError());
-  return 0;
-}
+// K2..K6 and K10 (sound_div, uvupdate2): kernels_sound.cu
 
 // ---------------------------------------------------------------------------
 // K7+K8+K9  vertical part of the divergence, implicit w (Thomas sweeps), new
@@ -668,74 +553,6 @@ int k_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& 
   };
   if (waves(4) == 1 && waves(6) == 2) return launch_wsolve5<4>(c, dts, last, pc, ep);
   return launch_wsolve5<6>(c, dts, last, pc, ep);
-}
-
-// ---------------------------------------------------------------------------
-// K10  horizontal momentum update                                    :677-721
-// ---------------------------------------------------------------------------
-template <bool FUSED>
-__global__ void moloch_uvupdate(Geo g, double* __restrict__ u, double* __restrict__ v,
-                                const double* __restrict__ ud, const double* __restrict__ vd,
-                                const double* __restrict__ tetav, const double* __restrict__ pai,
-                                const double* __restrict__ bdywtu, const double* __restrict__ bdywtv,
-                                const double* __restrict__ coru, const double* __restrict__ corv,
-                                const double* __restrict__ hx, const double* __restrict__ hy,
-                                const double* __restrict__ mu, const double* __restrict__ mv,
-                                const double* __restrict__ gzitakh, double dts, double dtrdx, double dtrdy,
-                                int damped, WaitCtl wc, PushCtl pc, EdgePush eu, EdgePush ev) {
-  if (FUSED) halo_sync(wc);   // pai ghosts of a fused round
-  THREAD_JIK(g.jde1, g.ide1, 1)
-  const bool inside = (j <= g.jde2 && i <= g.ide2);
-  const bool du = inside && in_box(j, i, g.jdi1, g.jdi2, g.ici1, g.ici2);
-  const bool dv = inside && in_box(j, i, g.jci1, g.jci2, g.idi1, g.idi2);
-  if (du || dv) {
-    const long long id = IX(j, i, k);
-    const long long i2 = IX2(j, i);
-    const double tv0 = tetav[id], pai0 = pai[id];
-    const double zfz = egrav * dts;
-    const double gk = gzitakh[k];
-    // u, v still hold the values of the start of the sub-step (the reference's
-    // ud, vd); the divergence-damped values (:749,:758) are in ud, vd
-    const double uold = u[id], vold = v[id];
-    if (du) {
-      const double zcx = dtrdx * mu[i2];
-      const double zrom1u = 0.5 * cpd * (tetav[id - 1] + tv0);
-      const double zcor1u = coru[i2] * dts * vold;
-      const double ub = damped ? ud[id] : uold;
-      const double un = ub + bdywtu[id] * (zcor1u - zfz * hx[i2] * gk - zcx * zrom1u * (pai0 - pai[id - 1]));
-      u[id] = un;
-      if (FUSED && pc.mask) edge_push(pc, eu, j, i, k, un);
-    }
-    if (dv) {
-      const double zcy = g.lrotllr ? dtrdy : dtrdy * mv[i2];
-      const double zrom1v = 0.5 * cpd * (tetav[id - g.NJ] + tv0);
-      const double zcor1v = corv[i2] * dts * uold;
-      const double vb = damped ? vd[id] : vold;
-      const double vn = vb + bdywtv[id] * (-zcor1v - zfz * hy[i2] * gk - zcy * zrom1v * (pai0 - pai[id - g.NJ]));
-      v[id] = vn;
-      if (FUSED && pc.mask) edge_push(pc, ev, j, i, k, vn);
-    }
-  }
-}
-int k_uvupdate(Ctx& c, double dts, const WaitCtl* wc, const PushCtl* pc, const EdgePush* eu, const EdgePush* ev) {
-  const Geo& g = c.g;
-  const WaitCtl w0 = wc ? *wc : WaitCtl{};
-  const PushCtl p0 = pc ? *pc : PushCtl{};
-  const EdgePush e0 = eu ? *eu : EdgePush{}, e1 = ev ? *ev : EdgePush{};
-  LaunchScope ls(c, KID_UVUPDATE);
-  const dim3 grid = grid3(g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, g.kz);
-  if (w0.mask || p0.mask)
-    moloch_uvupdate<true><<<grid, dim3(BX, BY), 0, c.stream>>>(
-        g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_BDYWTU].p,
-        c.f[MB_BDYWTV].p, c.f[MB_CORU].p, c.f[MB_CORV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFU].p,
-        c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx, c.cfg.mo_divdamp ? 1 : 0, w0, p0, e0, e1);
-  else
-    moloch_uvupdate<false><<<grid, dim3(BX, BY), 0, c.stream>>>(
-        g, c.f[MB_U].p, c.f[MB_V].p, c.ud, c.vd, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_BDYWTU].p,
-        c.f[MB_BDYWTV].p, c.f[MB_CORU].p, c.f[MB_CORV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFU].p,
-        c.f[MB_MSFV].p, c.prof[MB_GZITAKH], dts, dts * c.rdx, dts * c.rdx, c.cfg.mo_divdamp ? 1 : 0, w0, p0, e0, e1);
-  MB_CUDA(cudaGetLastError());
-  return 0;
 }
 
 // ---------------------------------------------------------------------------

@@ -30,7 +30,7 @@ CSRC = os.path.join(ROOT, "regcm_b200", "csrc")
 EMU = os.path.join(HERE, "emu")
 GEN = os.path.join(EMU, "_gen")
 LIB = os.path.join(EMU, "libmoloch_b200_emu.so")
-SOURCES = ["kernels.cu", "kernels_waf.cu", "kernels_bdy.cu", "halo.cu", "capi.cu"]
+SOURCES = ["kernels.cu", "kernels_sound.cu", "kernels_waf.cu", "kernels_bdy.cu", "halo.cu", "capi.cu"]
 HEADERS = ["common.cuh", "geo.h", "bdy_cells.h"]
 RUNTIME = [os.path.join(EMU, "emu_runtime.cpp"), os.path.join(EMU, "shim", "cuda_runtime.h"),
            os.path.join(EMU, "shim", "nccl.h")]

@@ -3,8 +3,8 @@
 // sub-step instead of four, no zdiv2 exchange.
 //
 //   moloch_sound_div     K3 + K4 + K6 (:582-618, 531-543): partial s, the horizontal
-//                        divergence zdiv2 and its 5-point filter in ONE pass over a
-//                        shared-memory tile.  The tile carries a one-cell ring, and on the
+//                        divergence zdiv2 and its 5-point filter in ONE pass of row-marching
+//                        warps.  A strip carries a one-cell ring, and on the
 //                        sides of the rank that have a neighbour the ring cells are the
 //                        neighbour's cells, computed here from u, v ghosts (the same
 //                        expressions on the same values: bit-identical to what the
@@ -32,17 +32,31 @@ struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 #endif
 
-constexpr int SA_TJ = 64;             // core tile: 64 columns x 8 rows, 256 threads, two cells per thread
-constexpr int SA_TI = 8;
-constexpr int SA_NT = 256;
-constexpr int SA_W = SA_TJ + 6;       // shared-memory row; column c <-> j = jt - 2 + c (core starts at c = 2)
-constexpr int SA_RU = SA_TI + 2;      // rows of the U arrays and of Z:  r <-> i = it - 1 + r
-constexpr int SA_RV = SA_TI + 3;      // rows of the V arrays (one more: v(i+1) of the top ring row)
-constexpr int SA_ZC = SA_TJ + 2;      // Z columns per row: c = 1 .. TJ+2  (j = jt-1 .. jt+TJ)
+// moloch_sound_div: a warp owns a strip of R rows x 64 columns of one level (lanes 1..30 hold the 60 useful
+// columns, two per lane; lanes 0 and 31 only supply the neighbouring zdiv2 values) and marches through the rows
+// i0-1 .. i0+R: the U-point and V-point products, the zdiv2 rows i-1, i, i+1 and the raw u, v rows that the
+// partial s needs form rolling register windows, the j-neighbours come from warp shuffles.  No shared memory,
+// no barriers; every array is read with 128-bit loads, 12 per row and lane.
+constexpr int SD_J = 60;              // useful columns of a strip
+constexpr int SD_WARPS = 4;           // strips per CTA, stacked in i
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 
-__global__ void __launch_bounds__(SA_NT)
+#ifndef MB_SD_MINB
+#define MB_SD_MINB 3
+#endif
+#ifndef MB_SD_DEPTH
+#define MB_SD_DEPTH 1
+#endif
+#ifndef MB_SD_UNROLL
+#define MB_SD_UNROLL 1
+#endif
+constexpr int SD_UNROLL = MB_SD_UNROLL;
+template <int R>
+__global__ void __launch_bounds__(32 * SD_WARPS, MB_SD_MINB)
 moloch_sound_div(Geo g, const double* __restrict__ u, const double* __restrict__ v, double* __restrict__ s,
                  double* __restrict__ w, double* __restrict__ zdiv2, double* __restrict__ zdiv2b,
                  const double* __restrict__ fmz, const double* __restrict__ rfmzu,
@@ -52,155 +66,168 @@ moloch_sound_div(Geo g, const double* __restrict__ u, const double* __restrict__
                  const double* __restrict__ rmv, const double* __restrict__ gzitak,
                  const double* __restrict__ xknu, double dtrdx, double dtrdy, int do_filter, int ring_store,
                  WaitCtl wc) {
-  // u, v ghosts of a fused round: the tiles that reach them wait for the neighbours' word
-  halo_sync(wc, 3, g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, SA_TJ, SA_TI);
-  extern __shared__ double sm[];
-  double* RU = sm;                         // u                       [SA_RU][SA_W]
-  double* PU = RU + SA_RU * SA_W;          // dtrdx*u*rfmzu[*rmu]
-  double* RV = PU + SA_RU * SA_W;          // v                       [SA_RV][SA_W]
-  double* PV = RV + SA_RV * SA_W;          // dtrdy*v*rfmzv*rmv
-  double* Z = PV + SA_RV * SA_W;           // zdiv2                   [SA_RU][SA_W]
+  // u, v ghosts of a fused round: the CTAs that reach them wait for the neighbours' word
+  halo_sync(wc, 3, g.jde2 - g.jde1 + 1, g.ide2 - g.ide1 + 1, SD_J, R * SD_WARPS);
   const int k = 1 + blockIdx.z;
-  const int jt = g.jde1 + blockIdx.x * SA_TJ, it = g.ide1 + blockIdx.y * SA_TI;
-  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
-  const int jb = g.j0 + g.NJ - 1, ib = g.i0 + g.NI - 1;      // last column / row of the padded box
-  const long long kbase = (long long)(k - 1) * g.plane;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int i0 = g.ide1 + (blockIdx.y * SD_WARPS + wq) * R;        // first useful row of the strip
+  if (i0 > g.ice2) return;
+  const int ja = g.jde1 + blockIdx.x * SD_J - 2 + 2 * lane;        // this lane's columns: ja, ja+1
+  const int jb = g.j0 + g.NJ - 1, ib = g.i0 + g.NI - 1;             // last column / row of the padded box
+  const bool jok = ja + 1 <= jb;                                    // (ja - j0 is even: the pair is in or out)
   const bool rot = g.lrotllr != 0;
-
-  // ---- phase 1: u, v of level k and their metric products, one warp per row --------------------
-  for (int t = wq; t < SA_RU + SA_RV; t += SA_NT / 32) {
-    const bool isu = t < SA_RU;
-    const int r = isu ? t : t - SA_RU;
-    const int i = min(it - 1 + r, ib);
-    const double* __restrict__ f3 = isu ? u : v;
-    const double* __restrict__ m3 = isu ? rfmzu : rfmzv;
-    const double* __restrict__ m2 = isu ? rmu : rmv;
-    const double dtr = isu ? dtrdx : dtrdy;
-    const bool use_m2 = isu ? !rot : true;
-    double* raw = (isu ? RU : RV) + r * SA_W;
-    double* prd = (isu ? PU : PV) + r * SA_W;
-    const long long row2 = (long long)(i - g.i0) * g.NJ - g.j0;     // + j
-    const long long row3 = kbase + row2;
-    {
-      const int j = jt + 2 * lane;
-      double2 a = make_double2(0.0, 0.0), b = a, m = make_double2(1.0, 1.0);
-      if (j + 1 <= jb) {
-        a = ld2(f3 + row3 + j); b = ld2(m3 + row3 + j);
-        if (use_m2) m = ld2(m2 + row2 + j);
-      } else if (j <= jb) {
-        a.x = f3[row3 + j]; b.x = m3[row3 + j];
-        if (use_m2) m.x = m2[row2 + j];
-      }
-      const int c = 2 + 2 * lane;
-      raw[c] = a.x; raw[c + 1] = a.y;
-      prd[c] = use_m2 ? dtr * a.x * b.x * m.x : dtr * a.x * b.x;
-      prd[c + 1] = use_m2 ? dtr * a.y * b.y * m.y : dtr * a.y * b.y;
-    }
-    if (lane < 3) {        // the ring columns: j = jt-1 (c = 1), jt+TJ (c = TJ+2), jt+TJ+1 (c = TJ+3, u only)
-      const int c = (lane == 0) ? 1 : SA_TJ + 1 + lane;
-      const int j = jt - 2 + c;
-      double a = 0.0, b = 0.0, m = 1.0;
-      if (j <= jb) {
-        a = f3[row3 + j]; b = m3[row3 + j];
-        if (use_m2) m = m2[row2 + j];
-      }
-      raw[c] = a;
-      prd[c] = use_m2 ? dtr * a * b * m : dtr * a * b;
-    }
-  }
-  __syncthreads();
-  // ---- phase 2: zdiv2 on the tile and its ring (:602-618) ---------------------------------------
   const double* __restrict__ mc = rot ? mx : mx2;
-  for (int p = tid; p < SA_RU * SA_ZC; p += SA_NT) {
-    const int r = p / SA_ZC, c = 1 + p % SA_ZC;
-    const int j = min(jt - 2 + c, jb), i = min(it - 1 + r, ib);
-    const long long i2 = (long long)(i - g.i0) * g.NJ + (j - g.j0);
-    const double zum = PU[r * SA_W + c], zup = PU[r * SA_W + c + 1];
-    const double zvm = PV[r * SA_W + c], zvp = PV[(r + 1) * SA_W + c];
-    Z[r * SA_W + c] = fmz[kbase + i2] * mc[i2] * ((zup - zum) + (zvp - zvm));
+  const long long kbase = (long long)(k - 1) * g.plane;
+  const long long col = (long long)(jok ? ja : jb - 1) - g.j0;
+  const double xk = xknu[k], gk = gzitak[k];
+  const bool useful = lane >= 1 && lane <= 30;
+  const bool ina = useful && ja >= g.jci1 && ja <= g.jci2, inb = useful && ja + 1 >= g.jci1 && ja + 1 <= g.jci2;
+  const bool exa = useful && ja >= g.jce1 && ja <= g.jce2, exb = useful && ja + 1 >= g.jce1 && ja + 1 <= g.jce2;
+  auto row2 = [&](int i) { return (long long)(min(i, ib) - g.i0) * g.NJ + col; };
+  // Everything iteration t reads from memory is loaded SD_DEPTH iterations ahead (12 independent 128-bit loads
+  // per row and lane in flight while the earlier rows are computed) -- a load that is issued where it is used
+  // stalls the in-order warp, also when it hits L2.  Row set iz: the row iz of the U-point arrays, of fmz, the
+  // metric factors, hx, hy and u(k-1), v(k-1); the row iz+1 of the V-point arrays.
+  struct RowSet { double2 ur, fu, mu, vr, fv, mv, fz, m2, hy, vm, hx, um; };
+  auto load_row = [&](int iz) {
+    RowSet L;
+    const long long o2 = row2(iz), o3 = kbase + o2, p2 = row2(iz + 1), p3 = kbase + p2;
+    L.ur = ld2(u + o3); L.fu = ld2(rfmzu + o3);
+    L.mu = rot ? make_double2(1.0, 1.0) : ld2(rmu + o2);
+    L.vr = ld2(v + p3); L.fv = ld2(rfmzv + p3); L.mv = ld2(rmv + p2);
+    L.fz = ld2(fmz + o3); L.m2 = ld2(mc + o2);
+    L.hy = ld2(hy + o2); L.hx = ld2(hx + o2);
+    L.vm = L.um = make_double2(0.0, 0.0);
+    if (k >= 2) { L.vm = ld2(v + o3 - g.plane); L.um = ld2(u + o3 - g.plane); }
+    return L;
+  };
+  double2 vr0 = make_double2(0.0, 0.0), vr1;                        // raw v of rows iz-1, iz
+  double2 vmp = vr0, hyp = vr0, hxp = vr0, ump = vr0;               // v(k-1), hy, hx, u(k-1) of row iz-1
+  double2 ur1 = vr0; double ur1e = 0.0;                             // raw u of row iz-1 (+ column ja+2)
+  double2 zm = vr0, zc = vr0;                                       // zdiv2 of rows iz-2, iz-1
+  double2 pvc;                                                      // V-point products of row iz
+  {
+    const long long o2 = row2(i0 - 1), o3 = kbase + o2;
+    vr1 = ld2(v + o3);
+    const double2 f = ld2(rfmzv + o3), m = ld2(rmv + o2);
+    pvc = make_double2(dtrdy * vr1.x * f.x * m.x, dtrdy * vr1.y * f.y * m.y);
   }
-  __syncthreads();
-  // ---- phase 3: outputs of the thread's two cells ------------------------------------------------
-  const int tx = tid & 31, ty = tid >> 5;
-  const int i = it + ty, r = ty + 1;
-  const int ja = jt + 2 * tx, c = 2 + 2 * tx;
-  if (i > g.ice2) return;
-  const long long ida = kbase + (long long)(i - g.i0) * g.NJ + (ja - g.j0);
-  const double za = Z[r * SA_W + c], zb = Z[r * SA_W + c + 1];
-  // zdiv2 on the external cross range; the left / bottom ring cells that uvupdate2's damping reads
-  // (zdiv2(j-1), zdiv2(i-1) at the first owned column / row) are stored by the edge tiles
-  if (ja + 1 <= g.jce2) *reinterpret_cast<double2*>(zdiv2 + ida) = make_double2(za, zb);
-  else if (ja <= g.jce2) zdiv2[ida] = za;
-  if (ring_store) {
-    if (blockIdx.x == 0 && tx == 0 && g.gl) zdiv2[ida - 1] = Z[r * SA_W + 1];
-    if (blockIdx.y == 0 && ty == 0 && g.gb) {
-      if (ja <= g.jce2) zdiv2[ida - g.NJ] = Z[c];
-      if (ja + 1 <= g.jce2) zdiv2[ida - g.NJ + 1] = Z[c + 1];
+  RowSet cur = load_row(i0 - 1);
+#if MB_SD_DEPTH == 2
+  RowSet nx1 = load_row(i0);
+#endif
+#pragma unroll SD_UNROLL
+  for (int t = 0; t < R + 2; ++t) {
+    const int iz = i0 - 1 + t;                                      // the zdiv2 row computed in this iteration
+#if MB_SD_DEPTH == 2
+    RowSet nx2 = nx1;
+    if (t + 2 < R + 2) nx2 = load_row(iz + 2);
+#else
+    RowSet nx1 = cur;
+    if (t + 1 < R + 2) nx1 = load_row(iz + 1);
+#endif
+    // ---- zdiv2 of row iz (:602-618) ----
+    const double2 ur = cur.ur;
+    double2 pu;
+    if (rot) pu = make_double2(dtrdx * ur.x * cur.fu.x, dtrdx * ur.y * cur.fu.y);
+    else pu = make_double2(dtrdx * ur.x * cur.fu.x * cur.mu.x, dtrdx * ur.y * cur.fu.y * cur.mu.y);
+    const double pue = shfl_dn1(pu.x);                              // the product at column ja+2
+    const double ure = shfl_dn1(ur.x);
+    const double2 vr2 = cur.vr;
+    const double2 pvn = make_double2(dtrdy * vr2.x * cur.fv.x * cur.mv.x, dtrdy * vr2.y * cur.fv.y * cur.mv.y);
+    const double2 zn = make_double2(cur.fz.x * cur.m2.x * ((pu.y - pu.x) + (pvn.x - pvc.x)),
+                                    cur.fz.y * cur.m2.y * ((pue - pu.y) + (pvn.y - pvc.y)));
+    const double2 hyn = cur.hy, vmn = cur.vm;
+    // ---- outputs of row i = iz-1 ----
+    const int i = iz - 1;
+    if (t >= 2 && i <= g.ice2) {
+      const long long oi3 = kbase + row2(i);
+      const double zw = shfl_up1(zc.y), ze = shfl_dn1(zc.x);       // zdiv2 at columns ja-1, ja+2
+      if (exa && exb) st2(zdiv2 + oi3, zc.x, zc.y);
+      else if (exa) zdiv2[oi3] = zc.x;
+      else if (exb) zdiv2[oi3 + 1] = zc.y;
+      const bool rowin = (i >= g.ici1 && i <= g.ici2);
+      if (do_filter && rowin) {   // :536-542 (Jacobi: old values everywhere)
+        const double fa = zc.x + xk * (zw + zc.y + zm.x + zn.x - 4.0 * zc.x);
+        const double fb = zc.y + xk * (zc.x + ze + zm.y + zn.y - 4.0 * zc.y);
+        if (ina && inb) st2(zdiv2b + oi3, fa, fb);
+        else if (ina) zdiv2b[oi3] = fa;
+        else if (inb) zdiv2b[oi3 + 1] = fb;
+      }
+      // :582-597 partial s (all lanes shuffle, the interior ones store)
+      const double2 hx01 = hxp, um01 = ump;
+      const double hx2 = shfl_dn1(hx01.x);
+      const double um2 = shfl_dn1(um01.x);
+      if (rowin) {
+        if (k >= 2) {
+          const double zuha = (ur1.x + um01.x) * hx01.x + (ur1.y + um01.y) * hx01.y;
+          const double zvha = (vr0.x + vmp.x) * hyp.x + (vr1.x + vmn.x) * hyn.x;
+          const double zuhb = (ur1.y + um01.y) * hx01.y + (ur1e + um2) * hx2;
+          const double zvhb = (vr0.y + vmp.y) * hyp.y + (vr1.y + vmn.y) * hyn.y;
+          const double sa = -0.25 * (zuha + zvha) * gk, sb = -0.25 * (zuhb + zvhb) * gk;
+          if (ina && inb) st2(s + oi3, sa, sb);
+          else if (ina) s[oi3] = sa;
+          else if (inb) s[oi3 + 1] = sb;
+        }
+        if (k == g.kz) {
+          const double ska = -0.5 * ((ur1.x * hx01.x + ur1.y * hx01.y) + (vr0.x * hyp.x + vr1.x * hyn.x));
+          const double skb = -0.5 * ((ur1.y * hx01.y + ur1e * hx2) + (vr0.y * hyp.y + vr1.y * hyn.y));
+          const long long op = oi3 + g.plane;
+          if (ina) { s[op] = ska; w[op] = -ska; }
+          if (inb) { s[op + 1] = skb; w[op + 1] = -skb; }
+        }
+      }
+      // the ring cells uvupdate2's damping reads: zdiv2(jce1-1, i) and zdiv2(j, ice1-1)
+      if (ring_store && blockIdx.x == 0 && lane == 0 && g.gl) zdiv2[oi3 + 1] = zc.y;
     }
-  }
-  const bool rowin = (i >= g.ici1 && i <= g.ici2);
-  const bool ina = rowin && ja >= g.jci1 && ja <= g.jci2, inb = rowin && ja + 1 >= g.jci1 && ja + 1 <= g.jci2;
-  if (!ina && !inb) return;
-  if (do_filter) {   // :536-542 (Jacobi: old values everywhere)
-    const double xk = xknu[k];
-    const double fa = za + xk * (Z[r * SA_W + c - 1] + zb + Z[(r - 1) * SA_W + c] + Z[(r + 1) * SA_W + c] - 4.0 * za);
-    const double fb = zb + xk * (za + Z[r * SA_W + c + 2] + Z[(r - 1) * SA_W + c + 1] + Z[(r + 1) * SA_W + c + 1] - 4.0 * zb);
-    if (ina && inb) *reinterpret_cast<double2*>(zdiv2b + ida) = make_double2(fa, fb);
-    else if (ina) zdiv2b[ida] = fa;
-    else zdiv2b[ida + 1] = fb;
-  }
-  // :582-597 partial s
-  const long long i2a = (long long)(i - g.i0) * g.NJ + (ja - g.j0);
-  const double u0 = RU[r * SA_W + c], u1 = RU[r * SA_W + c + 1], u2 = RU[r * SA_W + c + 2];
-  const double va0 = RV[r * SA_W + c], va1 = RV[(r + 1) * SA_W + c];
-  const double vb0 = RV[r * SA_W + c + 1], vb1 = RV[(r + 1) * SA_W + c + 1];
-  const double2 hx01 = ld2(hx + i2a);
-  const double hx2 = hx[min(i2a + 2, (long long)g.plane - 1)];
-  const double2 hy0 = ld2(hy + i2a), hy1 = ld2(hy + i2a + g.NJ);
-  if (k >= 2) {
-    const long long im = ida - g.plane;
-    const double2 um01 = ld2(u + im);
-    const double um2 = (ja + 2 <= jb) ? u[im + 2] : 0.0;
-    const double2 vm0 = ld2(v + im), vm1 = ld2(v + im + g.NJ);
-    const double gk = gzitak[k];
-    const double zuha = (u0 + um01.x) * hx01.x + (u1 + um01.y) * hx01.y;
-    const double zvha = (va0 + vm0.x) * hy0.x + (va1 + vm1.x) * hy1.x;
-    const double zuhb = (u1 + um01.y) * hx01.y + (u2 + um2) * hx2;
-    const double zvhb = (vb0 + vm0.y) * hy0.y + (vb1 + vm1.y) * hy1.y;
-    const double sa = -0.25 * (zuha + zvha) * gk, sb = -0.25 * (zuhb + zvhb) * gk;
-    if (ina && inb) *reinterpret_cast<double2*>(s + ida) = make_double2(sa, sb);
-    else if (ina) s[ida] = sa;
-    else s[ida + 1] = sb;
-  }
-  if (k == g.kz) {
-    const double ska = -0.5 * ((u0 * hx01.x + u1 * hx01.y) + (va0 * hy0.x + va1 * hy1.x));
-    const double skb = -0.5 * ((u1 * hx01.y + u2 * hx2) + (vb0 * hy0.y + vb1 * hy1.y));
-    const long long idp = ida + g.plane;
-    if (ina) { s[idp] = ska; w[idp] = -ska; }
-    if (inb) { s[idp + 1] = skb; w[idp + 1] = -skb; }
+    // roll the windows
+    zm = zc; zc = zn; pvc = pvn;
+    vr0 = vr1; vr1 = vr2; vmp = vmn; hyp = hyn; hxp = cur.hx; ump = cur.um;
+    ur1 = ur; ur1e = ure;
+#if MB_SD_DEPTH == 2
+    cur = nx1; nx1 = nx2;
+#else
+    cur = nx1;
+#endif
+    if (ring_store && t == 0 && g.gb && i0 == g.ide1) {   // zc is now the bottom ring row ice1-1
+      const long long o = kbase + row2(i0 - 1);
+      if (exa && exb) st2(zdiv2 + o, zc.x, zc.y);
+      else if (exa) zdiv2[o] = zc.x;
+      else if (exb) zdiv2[o + 1] = zc.y;
+    }
   }
 }
 
-int k_sound_div(Ctx& c, double dts, const WaitCtl* wc) {
+template <int R>
+static int launch_sound_div(Ctx& c, double dts, const WaitCtl& w0) {
   const Geo& g = c.g;
   const double dtrdx = dts * c.rdx, dtrdy = dts * c.rdx;
-  const WaitCtl w0 = wc ? *wc : WaitCtl{};
-  const size_t smem = (size_t)(3 * SA_RU + 2 * SA_RV) * SA_W * sizeof(double);
-  const dim3 grid((unsigned)((g.jde2 - g.jde1 + 1 + SA_TJ - 1) / SA_TJ), (unsigned)((g.ide2 - g.ide1 + 1 + SA_TI - 1) / SA_TI),
-                  (unsigned)g.kz);
+  const int nj = g.jde2 - g.jde1 + 1, ni = g.ide2 - g.ide1 + 1;
+  const dim3 grid((unsigned)((nj + SD_J - 1) / SD_J), (unsigned)((ni + R * SD_WARPS - 1) / (R * SD_WARPS)), (unsigned)g.kz);
   LaunchScope ls(c, KID_SOUND_PRE);
-  moloch_sound_div<<<grid, SA_NT, smem, c.stream>>>(
+  moloch_sound_div<R><<<grid, 32 * SD_WARPS, 0, c.stream>>>(
       g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_ZDIV2].p, c.zdiv2b, c.f[MB_FMZ].p,
       c.f[MB_RFMZU].p, c.f[MB_RFMZV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFX].p, c.mx2, c.rmu, c.rmv,
       c.prof[MB_GZITAK], c.prof[MB_XKNU], dtrdx, dtrdy, c.cfg.mo_divfilter ? 1 : 0, c.cfg.mo_divdamp ? 1 : 0, w0);
   MB_CUDA(cudaGetLastError());
   return 0;
 }
+int k_sound_div(Ctx& c, double dts, const WaitCtl* wc) {
+  const WaitCtl w0 = wc ? *wc : WaitCtl{};
+  // small per-GPU grids: shorter strips, so that the warps still cover all SMs
+  const long long strips8 = (long long)((c.g.jde2 - c.g.jde1 + SD_J) / SD_J) * ((c.g.ide2 - c.g.ide1 + 8) / 8) * c.g.kz;
+#ifndef MB_SD_R
+#define MB_SD_R 8
+#endif
+  return strips8 < 148 * 48 ? launch_sound_div<4>(c, dts, w0) : launch_sound_div<MB_SD_R>(c, dts, w0);
+}
 
 // ---------------------------------------------------------------------------
 // K5 + K10  divergence damping (:746-764) and horizontal momentum update (:677-721)
 // ---------------------------------------------------------------------------
-constexpr int UBX = 32, UBY = 8;
+// Two cells (j, j+1) per thread, every 3-D array read with one 128-bit load per thread; the value at j-1
+// (tetav, pai, zdiv2: the U-point differences) comes from the lane to the left, lane 0 loads it.
+constexpr int UBX = 32, UBY = 4;      // 64 columns x 4 rows per CTA
 template <bool FUSED>
 __global__ void __launch_bounds__(UBX * UBY)
 moloch_uvupdate2(Geo g, double* __restrict__ u, double* __restrict__ v, const double* __restrict__ zdiv2,
@@ -213,46 +240,70 @@ moloch_uvupdate2(Geo g, double* __restrict__ u, double* __restrict__ v, const do
                  double dtrdx, double dtrdy, double dxrdt, int damped, WaitCtl wc, PushCtl pc, EdgePush eu,
                  EdgePush ev) {
   if (FUSED) halo_sync(wc);   // pai ghosts of a fused round
-  const int j = g.jde1 + blockIdx.x * UBX + threadIdx.x;
+  const int lane = threadIdx.x;
+  const int ja = g.jde1 + (blockIdx.x * UBX + lane) * 2;
   const int i = g.ide1 + blockIdx.y * UBY + threadIdx.y;
   const int k = 1 + blockIdx.z;
-  const bool inside = (j <= g.jde2 && i <= g.ide2);
-  const bool du = inside && j >= g.jdi1 && j <= g.jdi2 && i >= g.ici1 && i <= g.ici2;
-  const bool dv = inside && j >= g.jci1 && j <= g.jci2 && i >= g.idi1 && i <= g.idi2;
-  if (!(du || dv)) return;
-  const long long id = gidx(g, j, i, k);
-  const long long i2 = gidx2(g, j, i);
-  const double tv0 = tetav[id], pai0 = pai[id];
-  const double zfz = egrav * dts;
+  if (i > g.ide2) return;                                   // (warp-uniform: a warp is one row)
+  const bool jin = ja <= g.jde2;                            // ja - j0 is even and NJ is: ja+1 is in the box then
+  const long long i2 = gidx2(g, jin ? ja : g.jde1, i);
+  const long long id = (long long)(k - 1) * g.plane + i2;
+  // every load of the thread is issued before the first use (all addresses lie in the padded box):
+  // 16 independent 128-bit loads in flight per thread
+  const double2 tv = ld2(tetav + id), pa = ld2(pai + id);
+  const double2 tvs = ld2(tetav + id - g.NJ), pas = ld2(pai + id - g.NJ);
+  const double2 uo = ld2(u + id), vo = ld2(v + id);
+  const double2 bwu = ld2(bdywtu + id), bwv = ld2(bdywtv + id);
+  double2 zz = make_double2(0.0, 0.0), zs = zz;
+  if (damped) { zz = ld2(zdiv2 + id); zs = ld2(zdiv2 + id - g.NJ); }
+  const double2 mju = ld2(mu + i2), cou = ld2(coru + i2), hxx = ld2(hx + i2);
+  const double2 cov = ld2(corv + i2), hyy = ld2(hy + i2);
+  double2 mjv = make_double2(1.0, 1.0);
+  if (!g.lrotllr) mjv = ld2(mv + i2);
   const double gk = gzitakh[k];
-  // u, v of the start of the sub-step: the reference's ud, vd (:573-578), which the Coriolis terms use
-  const double uold = u[id], vold = v[id];
-  const double z0 = damped ? zdiv2[id] : 0.0;
-  if (du) {
-    double ub = uold;
+  const double xkd = damped ? dxrdt * xkdamp[k] : 0.0;
+  // column ja-1: the left lane's second value (lane 0: its own load)
+  double tvw = shfl_up1(tv.y), paw = shfl_up1(pa.y), zw = shfl_up1(zz.y);
+  if (lane == 0) { tvw = tetav[id - 1]; paw = pai[id - 1]; if (damped) zw = zdiv2[id - 1]; }
+  if (!jin) return;
+  const bool rowu = (i >= g.ici1 && i <= g.ici2), rowv = (i >= g.idi1 && i <= g.idi2);
+  const bool dua = rowu && ja >= g.jdi1 && ja <= g.jdi2, dub = rowu && ja + 1 >= g.jdi1 && ja + 1 <= g.jdi2;
+  const bool dva = rowv && ja >= g.jci1 && ja <= g.jci2, dvb = rowv && ja + 1 >= g.jci1 && ja + 1 <= g.jci2;
+  const double zfz = egrav * dts;
+  // uo, vo: u, v of the start of the sub-step -- the reference's ud, vd (:573-578), which the Coriolis terms use
+  if (dua || dub) {
+    double ua = uo.x, ub = uo.y;
     if (damped) {   // :746-750
-      const double xdam = dxrdt * xkdamp[k] * mu[i2];
-      ub = uold + xdam * (z0 - zdiv2[id - 1]);
+      ua = uo.x + xkd * mju.x * (zz.x - zw);
+      ub = uo.y + xkd * mju.y * (zz.y - zz.x);
     }
-    const double zcx = dtrdx * mu[i2];
-    const double zrom1u = 0.5 * cpd * (tetav[id - 1] + tv0);
-    const double zcor1u = coru[i2] * dts * vold;
-    const double un = ub + bdywtu[id] * (zcor1u - zfz * hx[i2] * gk - zcx * zrom1u * (pai0 - pai[id - 1]));
-    u[id] = un;
-    if (FUSED && pc.mask) edge_push(pc, eu, j, i, k, un);
+    const double una = ua + bwu.x * (cou.x * dts * vo.x - zfz * hxx.x * gk - dtrdx * mju.x * (0.5 * cpd * (tvw + tv.x)) * (pa.x - paw));
+    const double unb = ub + bwu.y * (cou.y * dts * vo.y - zfz * hxx.y * gk - dtrdx * mju.y * (0.5 * cpd * (tv.x + tv.y)) * (pa.y - pa.x));
+    if (dua && dub) st2(u + id, una, unb);
+    else if (dua) u[id] = una;
+    else u[id + 1] = unb;
+    if (FUSED && pc.mask) {
+      if (dua) edge_push(pc, eu, ja, i, k, una);
+      if (dub) edge_push(pc, eu, ja + 1, i, k, unb);
+    }
   }
-  if (dv) {
-    double vb = vold;
+  if (dva || dvb) {
+    double va = vo.x, vb = vo.y;
     if (damped) {   // :752-763
-      const double xdam = g.lrotllr ? dxrdt * xkdamp[k] : dxrdt * xkdamp[k] * mv[i2];
-      vb = vold + xdam * (z0 - zdiv2[id - g.NJ]);
+      const double xa = g.lrotllr ? xkd : xkd * mjv.x, xb = g.lrotllr ? xkd : xkd * mjv.y;
+      va = vo.x + xa * (zz.x - zs.x);
+      vb = vo.y + xb * (zz.y - zs.y);
     }
-    const double zcy = g.lrotllr ? dtrdy : dtrdy * mv[i2];
-    const double zrom1v = 0.5 * cpd * (tetav[id - g.NJ] + tv0);
-    const double zcor1v = corv[i2] * dts * uold;
-    const double vn = vb + bdywtv[id] * (-zcor1v - zfz * hy[i2] * gk - zcy * zrom1v * (pai0 - pai[id - g.NJ]));
-    v[id] = vn;
-    if (FUSED && pc.mask) edge_push(pc, ev, j, i, k, vn);
+    const double zcya = g.lrotllr ? dtrdy : dtrdy * mjv.x, zcyb = g.lrotllr ? dtrdy : dtrdy * mjv.y;
+    const double vna = va + bwv.x * (-(cov.x * dts * uo.x) - zfz * hyy.x * gk - zcya * (0.5 * cpd * (tvs.x + tv.x)) * (pa.x - pas.x));
+    const double vnb = vb + bwv.y * (-(cov.y * dts * uo.y) - zfz * hyy.y * gk - zcyb * (0.5 * cpd * (tvs.y + tv.y)) * (pa.y - pas.y));
+    if (dva && dvb) st2(v + id, vna, vnb);
+    else if (dva) v[id] = vna;
+    else v[id + 1] = vnb;
+    if (FUSED && pc.mask) {
+      if (dva) edge_push(pc, ev, ja, i, k, vna);
+      if (dvb) edge_push(pc, ev, ja + 1, i, k, vnb);
+    }
   }
 }
 
@@ -262,7 +313,7 @@ int k_uvupdate2(Ctx& c, double dts, const WaitCtl* wc, const PushCtl* pc, const 
   const PushCtl p0 = pc ? *pc : PushCtl{};
   const EdgePush e0 = eu ? *eu : EdgePush{}, e1 = ev ? *ev : EdgePush{};
   LaunchScope ls(c, KID_UVUPDATE);
-  const dim3 grid((unsigned)((g.jde2 - g.jde1 + 1 + UBX - 1) / UBX), (unsigned)((g.ide2 - g.ide1 + 1 + UBY - 1) / UBY),
+  const dim3 grid((unsigned)((g.jde2 - g.jde1 + 1 + 2 * UBX - 1) / (2 * UBX)), (unsigned)((g.ide2 - g.ide1 + 1 + UBY - 1) / UBY),
                   (unsigned)g.kz);
 #define UV2_ARGS g, c.f[MB_U].p, c.f[MB_V].p, c.f[MB_ZDIV2].p, c.f[MB_TETAV].p, c.f[MB_PAI].p, c.f[MB_BDYWTU].p, \
       c.f[MB_BDYWTV].p, c.f[MB_CORU].p, c.f[MB_CORV].p, c.f[MB_HX].p, c.f[MB_HY].p, c.f[MB_MSFU].p, c.f[MB_MSFV].p, \

@@ -450,7 +450,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
   if (const char* e = getenv("MOLOCH_B200_HALO_TIMEOUT_MS")) { if (atoll(e) >= 1) c->halo_timeout_cycles = atoll(e) * 2000000LL; }
-  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || v == 6 || v == 7) ? v : 5; }
+  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || (v >= 6 && v <= 10)) ? v : 5; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     c->stream = nullptr;
     return bail("moloch_b200_create: cudaStreamCreate failed");
@@ -479,6 +479,8 @@ int moloch_b200_destroy(moloch_b200_ctx* c) {
   if (c->stage_up) cudaFree(c->stage_up);
   if (c->xs_down) cudaStreamDestroy(c->xs_down);
   if (c->xs_up) cudaStreamDestroy(c->xs_up);
+  if (c->xs_pack) cudaStreamDestroy(c->xs_pack);
+  if (c->xs_unpack) cudaStreamDestroy(c->xs_unpack);
   if (c->ev_ready) cudaEventDestroy(c->ev_ready);
   for (cudaEvent_t e : c->ev_slab) cudaEventDestroy(e);
   if (c->arena) cudaFree(c->arena);
@@ -510,7 +512,7 @@ int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
   if (!c || !name) return fail("set_option: null argument");
   const std::string n(name);
   if (n == "wsolve") {
-    if (value != 2 && value != 5 && value != 6 && value != 7) return fail("set_option: wsolve must be 2, 5, 6 or 7");
+    if (value != 2 && (value < 5 || value > 10)) return fail("set_option: wsolve must be 2 or 5..10");
     c->wsolve_impl = value;
   } else if (n == "waf") {
     if (value != 1 && value != 2) return fail("set_option: waf must be 1 or 2");
@@ -696,7 +698,6 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
   MB_CUDA(cudaSetDevice(c->device));
   std::vector<XferPlan> pd, pu;
   int I1 = 1 << 30, I2 = -(1 << 30);
-  size_t need = 0;
   auto add = [&](const moloch_b200_xfer* xs, int n, std::vector<XferPlan>& out) -> int {
     for (int q = 0; q < n; ++q) {
       XferPlan p; bool empty = false;
@@ -714,54 +715,133 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
   if (nslabs > rows) nslabs = rows;
   const int per = (rows + nslabs - 1) / nslabs;
   nslabs = (rows + per - 1) / per;
-  for (const auto* v : {&pd, &pu})
-    for (const XferPlan& p : *v) {
-      const size_t n_el = (size_t)(p.jb - p.ja + 1) * (size_t)per * (size_t)(p.kb - p.ka + 1);
-      if (n_el > need) need = n_el;
+  // An array whose host rows are exactly the device rows ("fast": the normal case) moves as ONE 2-D copy per
+  // slab -- a k-plane of the slab is one contiguous run of nj*ni doubles on the host -- between the host array
+  // and its packed run inside the slab's staging block; ONE kernel per slab and direction packs / unpacks all
+  // arrays.  The copy engines therefore see back-to-back copies and nothing else, and the staging blocks are
+  // double-buffered so that the pack kernel of slab s+1 runs while slab s travels.  Arrays whose host box is
+  // wider than the device box go array by array through the 3-D copy path (slab_copy).
+  auto fast = [](const XferPlan& p) { return p.ja == p.jlo && p.jb == p.jhi; };
+  auto slab_tables = [&](const std::vector<XferPlan>& v, std::vector<SlabTable>& tabs, size_t& block) {
+    // tabs[s * nt + t]: t-th table (at most SLAB_MAX_ARRAYS arrays) of slab s; block: doubles of the largest slab
+    std::vector<int> f;
+    for (size_t q = 0; q < v.size(); ++q) if (fast(v[q])) f.push_back((int)q);
+    const int nt = ((int)f.size() + SLAB_MAX_ARRAYS - 1) / SLAB_MAX_ARRAYS;
+    tabs.assign((size_t)nslabs * (size_t)(nt > 0 ? nt : 0), SlabTable{});
+    block = 0;
+    for (int s = 0; s < nslabs; ++s) {
+      const int i1 = I1 + s * per, i2 = (i1 + per - 1 < I2) ? i1 + per - 1 : I2;
+      long long off = 0;
+      for (size_t q = 0; q < f.size(); ++q) {
+        const XferPlan& p = v[(size_t)f[q]];
+        const int ia = p.ia > i1 ? p.ia : i1, ib = p.ib < i2 ? p.ib : i2;
+        if (ib < ia) continue;
+        SlabTable& T = tabs[(size_t)s * nt + q / SLAB_MAX_ARRAYS];
+        SlabArray& A = T.a[T.n++];
+        A.dev = p.dev; A.off = off; A.ja = p.ja; A.nj = p.jb - p.ja + 1; A.ia = ia; A.ni = ib - ia + 1;
+        A.ka = p.ka; A.nk = p.kb - p.ka + 1; A.plan = f[q]; A.pad = 0;
+        off += (long long)A.nj * A.ni * A.nk;
+      }
+      if ((size_t)off > block) block = (size_t)off;
     }
+    return nt;
+  };
+  std::vector<SlabTable> td, tu;
+  size_t need_d = 0, need_u = 0;
+  const int ntd = slab_tables(pd, td, need_d), ntu = slab_tables(pu, tu, need_u);
+  size_t need_slow = 0;     // the per-array path reuses the first staging block of its direction
+  for (const auto* v : {&pd, &pu})
+    for (const XferPlan& p : *v)
+      if (!fast(p)) {
+        const size_t n_el = (size_t)(p.jb - p.ja + 1) * (size_t)per * (size_t)(p.kb - p.ka + 1);
+        if (n_el > need_slow) need_slow = n_el;
+      }
+  if (need_slow > need_d) need_d = need_slow;
+  if (need_slow > need_u) need_u = need_slow;
   // streams, events, staging (created on first use; regrown only when idle)
   if (!c->xs_down) {
     MB_CUDA(cudaStreamCreateWithFlags(&c->xs_down, cudaStreamNonBlocking));
     MB_CUDA(cudaStreamCreateWithFlags(&c->xs_up, cudaStreamNonBlocking));
+    MB_CUDA(cudaStreamCreateWithFlags(&c->xs_pack, cudaStreamNonBlocking));
+    MB_CUDA(cudaStreamCreateWithFlags(&c->xs_unpack, cudaStreamNonBlocking));
     MB_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
   }
-  while ((int)c->ev_slab.size() < nslabs) {
+  while ((int)c->ev_slab.size() < 4 * nslabs) {
     cudaEvent_t e;
     MB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->ev_slab.push_back(e);
   }
-  if (need > c->stage_x_doubles) {
-    MB_CUDA(cudaStreamSynchronize(c->xs_down));
-    MB_CUDA(cudaStreamSynchronize(c->xs_up));
-    if (c->stage_down) cudaFree(c->stage_down);
-    if (c->stage_up) cudaFree(c->stage_up);
-    c->stage_down = c->stage_up = nullptr;
-    c->stage_x_doubles = need + need / 8;
-    MB_CUDA(cudaMalloc(&c->stage_down, c->stage_x_doubles * sizeof(double)));
-    MB_CUDA(cudaMalloc(&c->stage_up, c->stage_x_doubles * sizeof(double)));
-  }
-  // the copy streams start behind everything already enqueued on the context's stream
+  auto grow = [&](double*& buf, size_t& have, size_t need) -> int {
+    if (need <= have) return 0;
+    for (cudaStream_t st : {c->xs_down, c->xs_up, c->xs_pack, c->xs_unpack}) MB_CUDA(cudaStreamSynchronize(st));
+    if (buf) cudaFree(buf);
+    buf = nullptr;
+    have = need + need / 16;
+    MB_CUDA(cudaMalloc(&buf, 2 * have * sizeof(double)));
+    return 0;
+  };
+  if (grow(c->stage_down, c->stage_down_doubles, need_d) || grow(c->stage_up, c->stage_up_doubles, need_u)) return 1;
+  cudaEvent_t* EV = c->ev_slab.data();
+  auto ev_gathered = [&](int s) { return EV[4 * s]; };
+  auto ev_arrived = [&](int s) { return EV[4 * s + 1]; };
+  auto ev_uploaded = [&](int s) { return EV[4 * s + 2]; };
+  auto ev_scattered = [&](int s) { return EV[4 * s + 3]; };
+  // one 2-D copy per array of a slab table between the host array and its run in the staging block
+  auto table_copies = [&](const std::vector<XferPlan>& v, const SlabTable& T, double* stage, bool to_device,
+                          cudaStream_t st) -> int {
+    for (int q = 0; q < T.n; ++q) {
+      const SlabArray& A = T.a[q];
+      const XferPlan& p = v[(size_t)A.plan];
+      const size_t hrow = (size_t)(p.jhi - p.jlo + 1), hplane = hrow * (size_t)(p.ihi - p.ilo + 1);
+      double* h0 = p.host + (size_t)(A.ka - p.klo) * hplane + (size_t)(A.ia - p.ilo) * hrow;
+      const size_t run = (size_t)A.nj * A.ni * sizeof(double);
+      if (to_device)
+        MB_CUDA(cudaMemcpy2DAsync(stage + A.off, run, h0, hplane * sizeof(double), run, (size_t)A.nk, cudaMemcpyHostToDevice, st));
+      else
+        MB_CUDA(cudaMemcpy2DAsync(h0, hplane * sizeof(double), stage + A.off, run, run, (size_t)A.nk, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+  };
+  // everything starts behind what is already enqueued on the context's stream
   MB_CUDA(cudaEventRecord(c->ev_ready, c->stream));
-  MB_CUDA(cudaStreamWaitEvent(c->xs_down, c->ev_ready, 0));
-  MB_CUDA(cudaStreamWaitEvent(c->xs_up, c->ev_ready, 0));
+  for (cudaStream_t st : {c->xs_down, c->xs_up, c->xs_pack, c->xs_unpack}) MB_CUDA(cudaStreamWaitEvent(st, c->ev_ready, 0));
+  // ---- the whole downward direction is enqueued at once ----
   for (int s = 0; s < nslabs; ++s) {
     const int i1 = I1 + s * per, i2 = (i1 + per - 1 < I2) ? i1 + per - 1 : I2;
+    double* blk = c->stage_down + (size_t)(s & 1) * c->stage_down_doubles;
+    if (s >= 2) MB_CUDA(cudaStreamWaitEvent(c->xs_pack, ev_arrived(s - 2), 0));   // the block is free again
+    for (int t = 0; t < ntd; ++t)
+      if (k_slab_copy(*c, td[(size_t)s * ntd + t], blk, true, c->xs_pack)) return 1;
+    MB_CUDA(cudaEventRecord(ev_gathered(s), c->xs_pack));
+    MB_CUDA(cudaStreamWaitEvent(c->xs_down, ev_gathered(s), 0));
+    for (int t = 0; t < ntd; ++t)
+      if (table_copies(pd, td[(size_t)s * ntd + t], blk, false, c->xs_down)) return 1;
     for (const XferPlan& p : pd)
-      if (slab_copy(c, p, i1, i2, false, c->xs_down, c->stage_down)) return 1;
-    MB_CUDA(cudaEventRecord(c->ev_slab[(size_t)s], c->xs_down));
+      if (!fast(p) && slab_copy(c, p, i1, i2, false, c->xs_down, blk)) return 1;
+    MB_CUDA(cudaEventRecord(ev_arrived(s), c->xs_down));
   }
+  // ---- slab by slab: wait for the state, run the host physics, send its tendencies up ----
   int rc = 0;
   for (int s = 0; s < nslabs && rc == 0; ++s) {
     const int i1 = I1 + s * per, i2 = (i1 + per - 1 < I2) ? i1 + per - 1 : I2;
-    MB_CUDA(cudaEventSynchronize(c->ev_slab[(size_t)s]));     // slab s of the state is on the host
+    MB_CUDA(cudaEventSynchronize(ev_arrived(s)));     // slab s of the state is on the host
     if (physics && physics(user, i1, i2) != 0) { rc = fail("handoff: the physics callback reported an error"); break; }
+    double* blk = c->stage_up + (size_t)(s & 1) * c->stage_up_doubles;
+    if (s >= 2) MB_CUDA(cudaStreamWaitEvent(c->xs_up, ev_scattered(s - 2), 0));
+    for (int t = 0; t < ntu && rc == 0; ++t)
+      if (table_copies(pu, tu[(size_t)s * ntu + t], blk, true, c->xs_up)) rc = 1;
     for (const XferPlan& p : pu)
-      if (slab_copy(c, p, i1, i2, true, c->xs_up, c->stage_up)) { rc = 1; break; }
+      if (rc == 0 && !fast(p) && slab_copy(c, p, i1, i2, true, c->xs_up, blk)) rc = 1;
+    if (rc) break;
+    MB_CUDA(cudaEventRecord(ev_uploaded(s), c->xs_up));
+    MB_CUDA(cudaStreamWaitEvent(c->xs_unpack, ev_uploaded(s), 0));
+    for (int t = 0; t < ntu; ++t)
+      if (k_slab_copy(*c, tu[(size_t)s * ntu + t], blk, false, c->xs_unpack)) { rc = 1; break; }
+    MB_CUDA(cudaEventRecord(ev_scattered(s), c->xs_unpack));
   }
   // completion on return: host arrays may be reused, later work on the context's
   // stream is enqueued after this point and therefore sees the uploaded slabs
-  MB_CUDA(cudaStreamSynchronize(c->xs_down));
-  MB_CUDA(cudaStreamSynchronize(c->xs_up));
+  for (cudaStream_t st : {c->xs_down, c->xs_pack, c->xs_up, c->xs_unpack}) MB_CUDA(cudaStreamSynchronize(st));
   if (rc == 0) rc = halo_timeout_check(*c);   // the downloaded state is host-visible now
   return rc;
 }

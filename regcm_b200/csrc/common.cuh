@@ -141,11 +141,12 @@ struct Ctx {
   bool async_xfer = false;
   // pipelined physics hand-off (moloch_b200_handoff): one copy stream and one
   // staging buffer per direction, one event per slab
-  cudaStream_t xs_down = nullptr, xs_up = nullptr;
+  cudaStream_t xs_down = nullptr, xs_up = nullptr;       // copy streams (D2H, H2D)
+  cudaStream_t xs_pack = nullptr, xs_unpack = nullptr;   // gather / scatter kernels of the slabs
   cudaEvent_t ev_ready = nullptr;
-  std::vector<cudaEvent_t> ev_slab;
-  double *stage_down = nullptr, *stage_up = nullptr;
-  size_t stage_x_doubles = 0;
+  std::vector<cudaEvent_t> ev_slab;                      // 4 per slab: gathered, arrived, uploaded, scattered
+  double *stage_down = nullptr, *stage_up = nullptr;     // two slab-sized staging blocks per direction
+  size_t stage_down_doubles = 0, stage_up_doubles = 0;   // size of ONE block
 };
 
 extern thread_local std::string g_err;
@@ -276,6 +277,11 @@ int k_status_update(Ctx& c, double dtinc);
 int k_init_static(Ctx& c);
 int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int nj, int ni, int nk, bool pack,
                cudaStream_t on = nullptr);   // on: another stream than the context's (hand-off copy streams)
+// all arrays of one slab of the physics hand-off in one launch: padded device boxes <-> packed staging block
+constexpr int SLAB_MAX_ARRAYS = 60;
+struct SlabArray { double* dev; long long off; int ja, nj, ia, ni, ka, nk, plan, pad; };   // off: doubles into the staging block; plan: host-side index
+struct SlabTable { SlabArray a[SLAB_MAX_ARRAYS]; int n; };
+int k_slab_copy(Ctx& c, const SlabTable& t, double* stage, bool pack, cudaStream_t on);
 // kernels_bdy.cu
 int k_bdyval(Ctx& c, double xbctime);
 int k_bdy_relax(Ctx& c, double xbctime);

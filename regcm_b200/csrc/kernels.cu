@@ -5,6 +5,7 @@
 // Arithmetic is FP64 with the reference's operation order and this file is
 // compiled with -fmad=false, so +,-,*,/ results are bit-identical to a
 // non-contracting CPU evaluation of the Fortran.
+#include <algorithm>
 #include "common.cuh"
 
 namespace mb {
@@ -213,11 +214,13 @@ static int launch_wsolve(Ctx& c, double dts, bool last, long long ncol, const Pu
 }
 int k_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
 int k_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
+int k_wsolve8(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
 int k_wsolve(Ctx& c, double dts, bool last, const PushCtl* pcp, const EdgePush* epp) {
   const PushCtl pc = pcp ? *pcp : PushCtl{};
   const EdgePush ep = epp ? *epp : EdgePush{};
   if (c.wsolve_impl == 5) return k_wsolve5(c, dts, last, pc, ep);
   if (c.wsolve_impl == 6 || c.wsolve_impl == 7) return k_wsolve6(c, dts, last, pc, ep);
+  if (c.wsolve_impl >= 8 && c.wsolve_impl <= 10) return k_wsolve8(c, dts, last, pc, ep);
   const Geo& g = c.g;
   const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
   const bool small = (ncol + 31) / 32 < 148 * 5 * 3;   // fewer than three waves of 32-column CTAs
@@ -533,6 +536,207 @@ static int launch_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, cons
       c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, pc, ep);
   MB_CUDA(cudaGetLastError());
   return 0;
+}
+// ---------------------------------------------------------------------------
+// K7+K8+K9, variant 8 (round 2).  What round 1's variants taught (profiles/): the column kernel is bound by the
+// bytes it keeps in flight -- HBM answers in 2-3 us under load, so a warp that waits for level k while only
+// D levels are under way moves D*2.3 KB per latency -- and the upward pass, which needs two to five values per
+// level, ran at the same levels-per-latency as the downward pass with a fifth of its bytes.  Variant 8 therefore
+//  * feeds the ring with 16-byte cp.async.cg (two columns per copy, L1 bypassed: an in-flight line does not
+//    occupy the small L1 that is left beside 200 KB of shared memory; five copies per lane and level instead of
+//    nine).  A warp's 32 columns are consecutive cells of ONE row starting on a 32-byte boundary (tiles by row),
+//  * re-partitions the same ring memory for the upward pass into DU = 9*D/4 (9*D/6) slots of 4 (6) values:
+//    13+ levels under way instead of 6,
+//  * optionally (ZFS = false) recomputes the finished divergence in the upward pass like variant 6, which buys
+//    a deeper downward ring in the same shared memory.
+// Copies are issued by one lane for two columns, so a warp-level barrier separates a slot's arrival from its
+// use and its use from its refill.  Arithmetic and operation order are those of variants 5/6: bit-identical.
+// ---------------------------------------------------------------------------
+#ifdef MB_HOST_EMU
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) { emu::cp_async_enqueue(smem_dst, gsrc, 16); }
+#else
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+#endif
+
+template <int D, bool ZFS>
+__global__ void __launch_bounds__(32)
+moloch_wsolve8(Geo g, const double* __restrict__ zdiv, double* s, double* w, double* pai,
+               const double* __restrict__ tetav, double* tetavf, const double* __restrict__ fmz,
+               const double* __restrict__ fmzf, const double* __restrict__ bdywtw,
+               const double* __restrict__ ffilt, double dts, double dtrdz, double zcs2, int last, int ntile_j,
+               PushCtl pc, EdgePush ep) {
+  extern __shared__ double sm[];
+  constexpr int UV = ZFS ? 4 : 6;                    // values per level of the upward pass
+  constexpr int DU = (9 * D) / UV;                   // its ring depth in the same memory
+  const int kz = g.kz;
+  double* WP = sm;                                   // w after the downward sweep, rows k = 0..kz
+  double* WW = WP + (kz + 1) * 32;                   // wwkw
+  double* ZF = WW + (kz + 1) * 32;                   // finished divergence (ZFS)
+  double* RING = ZF + (ZFS ? (kz + 1) * 32 : 0);     // D slots x 9 values x 32 lanes
+  const int lane = threadIdx.x;
+  const int tj = blockIdx.x % ntile_j, ti = blockIdx.x / ntile_j;
+  const int i = g.ici1 + ti, jf = g.jde1 + 32 * tj;  // jf - j0 = HJ + 32*tj: a 32-byte boundary
+  const int j = jf + lane;
+  const bool valid = (j >= g.jci1 && j <= g.jci2);
+  const long long pl = g.plane;
+  const long long rowb = gidx(g, jf, i, 1) - pl;     // level k of the tile's first column at rowb + k*pl
+  // copy role of the lane: columns 2c, 2c+1 of the arrays of parity `half`
+  const int half = lane >> 4, c2 = 2 * (lane & 15);
+  const bool cok = (jf + c2 + 1 <= g.j0 + g.NJ - 1);  // the last tile of a row may reach beyond the padded box
+  const double* d0 = half ? zdiv : w;
+  const double* d1 = half ? fmz : bdywtw;
+  const double* d2 = half ? tetav : s;
+  const double* d3 = half ? fmzf : pai;
+  auto fetch = [&](int slot, int k) {               // slot rows: w, zdiv, bdywtw, fmz, s, tetav, pai, fmzf, tetavf
+    if (!cok) return;
+    double* r = RING + slot * (9 * 32) + half * 32 + c2;
+    const long long o = rowb + k * pl + c2;
+    cp_async16(r, d0 + o); cp_async16(r + 64, d1 + o); cp_async16(r + 128, d2 + o); cp_async16(r + 192, d3 + o);
+    if (!half) cp_async16(r + 256, tetavf + o);
+  };
+  // ---- downward pass ----
+#pragma unroll
+  for (int q = 0; q < D; ++q) {
+    if (kz - q >= 1) fetch(q, kz - q);
+    cp_async_commit();
+  }
+  const long long base = rowb + lane;                // this lane's column
+  double wkp1 = w[base + (kz + 1) * pl];   // w(kzp1)
+  const double w_bottom = wkp1;
+  double wwkp1 = 0.0;                       // wwkw(kzp1) :1055-1057
+  double s_below = s[base + (kz + 1) * pl];
+  double p_w = 0.0, p_tf = 0.0, p_ff = 0.0, p_tv = 0.0, p_pa = 0.0, p_fm = 0.0, p_zd = 0.0;  // level m+1
+  double w1 = 0.0;
+  for (int t0 = 0; t0 < kz; t0 += D) {
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      const int m = kz - (t0 + q);
+      cp_async_wait<D - 1>();
+      __syncwarp();                         // the slot was filled by several lanes
+      if (m >= 1) {
+        const double* r = RING + q * (9 * 32) + lane;
+        const double Lw = r[0], Lzdiv = r[32], Lbw = r[64], Lfm = r[96], Ls = r[128], Ltv = r[160],
+                     Lpa = r[192], Lff = r[224], Ltf = r[256];
+        __syncwarp();                       // every lane has read the slot: it may be refilled
+        if (m - D >= 1) fetch(q, m - D);
+        const double zdm = Lzdiv + Lbw * dtrdz * Lfm * (Ls - s_below);
+        s_below = Ls;
+        if (ZFS) ZF[m * 32 + lane] = zdm;
+        if (m < kz) {
+          const int k = m + 1;
+          const double tfn = p_tf - p_w * p_ff * dtrdz * (Ltv - p_tv);
+          if (valid) tetavf[base + k * pl] = tfn;
+          const double zrom1w = cpd * tfn * p_ff;
+          double zwexpl = p_w - zrom1w * dtrdz * (Lpa - p_pa) - egrav * dts;
+          zwexpl = zwexpl + rdrcv * zrom1w * dtrdz * (Lpa * zdm - p_pa * p_zd);
+          const double fk = ffilt[k];
+          const double zu = zcs2 * Lfm * zrom1w * Lpa + fk;
+          const double zd = zcs2 * p_fm * zrom1w * p_pa + fk;
+          const double zrapp = 1.0 / (1.0 + zd + zu - zd * wwkp1);
+          wkp1 = zrapp * (zwexpl + zd * wkp1);
+          wwkp1 = zrapp * zu;
+          WP[k * 32 + lane] = wkp1;
+          WW[k * 32 + lane] = wwkp1;
+        }
+        p_w = Lw; p_tf = Ltf; p_ff = Lff; p_tv = Ltv; p_pa = Lpa; p_fm = Lfm; p_zd = zdm;
+        if (m == 1) w1 = Lw;
+      }
+      cp_async_commit();
+    }
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  // ---- upward pass: level k needs pai, fmz [zdiv, bdywtw] of level k-1 and s [, fmzf] of level k ----
+  const double* u0 = half ? fmz : pai;               // of level k-1
+  const double* u1 = half ? zdiv : s;                // (!ZFS) s of level k / zdiv of level k-1;  (ZFS, last) s / fmzf of level k
+  auto fetchup = [&](int slot, int k) {             // slot rows: pai, fmz, s, (zdiv | fmzf), bdywtw, fmzf
+    if (!cok) return;
+    double* r = RING + slot * (UV * 32) + half * 32 + c2;
+    const long long o = rowb + k * pl + c2;
+    cp_async16(r, u0 + o - pl);
+    if (ZFS) {
+      if (last) cp_async16(r + 64, (half ? fmzf : s) + o);
+    } else {
+      cp_async16(r + 64, u1 + o - (half ? pl : 0));
+      if (!half) cp_async16(r + 128, bdywtw + o - pl);
+      else if (last) cp_async16(r + 128, fmzf + o);
+    }
+  };
+  double s_km1 = s[base + pl];              // s(1), as the downward pass saw it
+#pragma unroll
+  for (int q = 0; q < DU; ++q) {
+    if (2 + q <= kz + 1) fetchup(q, 2 + q);
+    cp_async_commit();
+  }
+  double wkm1 = w1;
+  for (int t0 = 0; t0 < kz; t0 += DU) {
+#pragma unroll
+    for (int q = 0; q < DU; ++q) {
+      const int k = 2 + t0 + q;
+      cp_async_wait<DU - 1>();
+      __syncwarp();
+      if (k <= kz + 1) {
+        const double* r = RING + q * (UV * 32) + lane;
+        const double Upa = r[0], Ufm = r[32];
+        double Us = 0.0, Uff = 0.0, zdm;
+        if (ZFS) {
+          if (last) { Us = r[64]; Uff = r[96]; }
+          zdm = ZF[(k - 1) * 32 + lane];
+        } else {
+          Us = r[64];
+          const double Uzdiv = r[96], Ubw = r[128];
+          if (last) Uff = r[160];
+          // the finished divergence of level k-1, exactly as the downward pass computed it
+          zdm = Uzdiv + Ubw * dtrdz * Ufm * (s_km1 - Us);
+          s_km1 = Us;
+        }
+        __syncwarp();
+        if (k + DU <= kz + 1) fetchup(q, k + DU);
+        const double wk = (k <= kz) ? WP[k * 32 + lane] + WW[k * 32 + lane] * wkm1 : w_bottom;
+        if (valid) {
+          const long long id = base + k * pl;
+          const double pnew = Upa * (1.0 - rdrcv * (zdm + (dtrdz * Ufm * (wkm1 - wk))));
+          pai[id - pl] = pnew;
+          if (pc.mask) edge_push(pc, ep, j, i, k - 1, pnew);
+          if (k <= kz) {
+            w[id] = wk;
+            if (last) s[id] = (wk + Us) * Uff;
+          }
+        }
+        wkm1 = wk;
+      }
+      cp_async_commit();
+    }
+  }
+  cp_async_wait<0>();
+  if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
+}
+template <int D, bool ZFS>
+static int launch_wsolve8(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
+  const Geo& g = c.g;
+  const int ntile_j = (g.jci2 - g.jde1 + 1 + 31) / 32, ni = g.ici2 - g.ici1 + 1;
+  const double dtrdz = dts * c.rdzita;
+  const double zcs2 = (dtrdz * dtrdz) * rdrcv;
+  const size_t smem = (size_t)((ZFS ? 3 : 2) * (g.kz + 1) + D * 9) * 32 * sizeof(double);
+  if (smem > 227 * 1024) return fail("wsolve: kz too large for the shared-memory sweep slots");
+  const double* zsrc = c.cfg.mo_divfilter ? c.zdiv2b : c.f[MB_ZDIV2].p;
+  MB_CUDA(cudaFuncSetAttribute(moloch_wsolve8<D, ZFS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchScope ls(c, KID_WSOLVE);
+  moloch_wsolve8<D, ZFS><<<(unsigned)(ntile_j * ni), 32, smem, c.stream>>>(
+      g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.f[MB_FMZ].p,
+      c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, ntile_j, pc, ep);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+// variant 8: three sweep arrays + ring of 6 (46 KB per warp at kz = 41, 4 warps per SM); variant 9: two sweep
+// arrays (divergence recomputed) + ring of 9 (42 KB, 5 warps per SM); variant 10: two + ring of 12 (49 KB, 4 warps)
+int k_wsolve8(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
+  if (c.wsolve_impl == 9) return launch_wsolve8<9, false>(c, dts, last, pc, ep);
+  if (c.wsolve_impl == 10) return launch_wsolve8<12, false>(c, dts, last, pc, ep);
+  return launch_wsolve8<6, true>(c, dts, last, pc, ep);
 }
 // variant 6: ring of 4 levels (31 KB per warp at kz = 41: 7 warps per SM); variant 7: ring of 6 (36 KB: 6 warps)
 int k_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
@@ -1108,6 +1312,31 @@ int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int n
     LaunchScope ls(c, KID_BOX);
     moloch_box_copy<<<grid, dim3(BX, BY), 0, c.stream>>>(c.g, dev, stage, ja, ia, ka, nj, ni, nk, pack ? 1 : 0);
   }
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// One slab of the physics hand-off: every array's rows [ia, ia+ni) x [ja, ja+nj) x [ka, ka+nk) between its
+// padded device box and its packed (k, i, j) run inside the slab's staging block.  blockIdx.y = array.
+__global__ void moloch_slab_copy(Geo g, SlabTable t, double* __restrict__ stage, int pack) {
+  const SlabArray a = t.a[blockIdx.y];
+  const long long rows = (long long)a.nk * a.ni;
+  double* __restrict__ st = stage + a.off;
+  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
+    const int k = (int)(r / a.ni), i = (int)(r % a.ni);
+    const long long d0 = gidx(g, a.ja, a.ia + i, a.ka + k), s0 = r * a.nj;
+    for (int j = threadIdx.x; j < a.nj; j += blockDim.x) {
+      if (pack) st[s0 + j] = a.dev[d0 + j]; else a.dev[d0 + j] = st[s0 + j];
+    }
+  }
+}
+int k_slab_copy(Ctx& c, const SlabTable& t, double* stage, bool pack, cudaStream_t on) {
+  if (t.n <= 0) return 0;
+  long long rows = 1;
+  for (int q = 0; q < t.n; ++q) rows = std::max(rows, (long long)t.a[q].nk * t.a[q].ni);
+  const unsigned gx = (unsigned)std::min<long long>((rows + 3) / 4, 148 * 4);
+  c.launches++;   // (a hand-off stream: the profiling events belong to the context's stream)
+  moloch_slab_copy<<<dim3(gx, (unsigned)t.n), dim3(64, 4), 0, on>>>(c.g, t, stage, pack ? 1 : 0);
   MB_CUDA(cudaGetLastError());
   return 0;
 }

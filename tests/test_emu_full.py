@@ -332,8 +332,9 @@ def test_full_size_property_checks_at_reduced_size():
     Fz.check_tracer_properties(S.small(S.WORKLOADS["cordex25"], 40, 36, 9, ntr=3, nspgx=5), 2)
 
 
-@pytest.mark.parametrize("impl,case", [("6", "limited_area"), ("6", "tall"), ("2", "limited_area")] if FULL
-                         else [("6", "limited_area")])
+@pytest.mark.parametrize("impl,case", [("6", "limited_area"), ("6", "tall"), ("2", "limited_area"), ("8", "tall"),
+                                       ("9", "tall"), ("10", "limited_area"), ("8", "limited_area"), ("9", "limited_area")]
+                         if FULL else [("6", "limited_area"), ("8", "limited_area"), ("9", "tall")])
 def test_wsolve_variants(impl, case, monkeypatch):
     import test_gpu_zz_variants as V
     V.test_wsolve_variants_bit_exact(impl, case, monkeypatch)

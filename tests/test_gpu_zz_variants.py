@@ -6,6 +6,8 @@ every A/B candidate must be bit-exact before it is timed.
                          6 (two sweep arrays, the finished divergence recomputed in the upward pass; 7 warps per SM;
                             bench.py times the variants and keeps the fastest), 7 (as 6 with a 6-deep ring: 6 warps)
                          2 (CTA = 32 columns x all levels, one-warp sweeps)
+                         8, 9, 10 (round 2: row tiles, 16-byte cp.async.cg ring, re-partitioned ring in the upward
+                            pass; 8 = three sweep arrays + ring of 6, 9 = two + ring of 9, 10 = two + ring of 12)
     MOLOCH_B200_WAF    = 2 (default: field-batched fused WAF kernels) | 1 (one kernel per reference loop nest)
 
 (Sorts after the other GPU test files; the same bodies run on the CPU build of the CUDA sources.)"""
@@ -17,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("case", ["limited_area", "tall"])
-@pytest.mark.parametrize("impl", ["6", "7", "2"])
+@pytest.mark.parametrize("impl", ["6", "7", "2", "8", "9", "10"])
 def test_wsolve_variants_bit_exact(impl, case, monkeypatch):
     monkeypatch.setenv("MOLOCH_B200_WSOLVE", impl)
     P.test_steps_bit_exact(case)
@@ -47,5 +49,7 @@ def test_set_option_switches_variants_of_a_live_context():
         m.set_option("nonsense", 1)
     with pytest.raises(MolochError, match="wsolve must be"):
         m.set_option("wsolve", 3)
+    with pytest.raises(MolochError, match="wsolve must be"):
+        m.set_option("wsolve", 11)
     assert np.isfinite(m.get_global("pai")).all()
     m.close()

@@ -3,6 +3,7 @@
 // (reference call tree: Main/mod_moloch.F90:312-446, 545-736, 767-836,
 // 1085-1141, 1403-1443).
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <utility>
@@ -624,6 +625,7 @@ struct XferPlan {
   double* dev; double* host;
   int jlo, jhi, ilo, ihi, klo;     // host bounds
   int ja, jb, ia, ib, ka, kb;      // part that exists on the device
+  int nkf, khi;                    // levels of the field on the device; last host level
 };
 int plan_xfer(moloch_b200_ctx* c, const moloch_b200_xfer& x, XferPlan& p, bool& empty) {
   if (x.field < 0 || x.field >= MB_NFIELDS) return fail("handoff: unknown field id");
@@ -643,6 +645,7 @@ int plan_xfer(moloch_b200_ctx* c, const moloch_b200_xfer& x, XferPlan& p, bool& 
   p.ja = x.jlo > g.j0 ? x.jlo : g.j0; p.jb = x.jhi < g.j0 + g.NJ - 1 ? x.jhi : g.j0 + g.NJ - 1;
   p.ia = x.ilo > g.i0 ? x.ilo : g.i0; p.ib = x.ihi < g.i0 + g.NI - 1 ? x.ihi : g.i0 + g.NI - 1;
   p.ka = x.klo > 1 ? x.klo : 1; p.kb = x.khi < f.nk ? x.khi : f.nk;
+  p.nkf = f.nk; p.khi = x.khi;
   empty = (p.jb < p.ja || p.ib < p.ia || p.kb < p.ka);
   return 0;
 }
@@ -711,6 +714,30 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
   };
   if (add(down, ndown, pd) || add(up, nup, pu)) return 1;
   if (pd.empty() && pu.empty()) return 0;
+  // Consecutive species of a 4-D array (qx, trac, qxten, chiten: species-major on the host and on the device)
+  // with identical bounds become ONE array with nspec*nk planes: its slab is one copy of nspec times the size
+  // (the copy engines lose a fixed ~10 us per copy, scratch/pcie5.cu).
+  auto merge = [&](std::vector<XferPlan>& v) {
+    std::vector<XferPlan> out;
+    for (const XferPlan& p : v) {
+      if (!out.empty()) {
+        XferPlan& a = out.back();
+        const size_t hplane = (size_t)(a.jhi - a.jlo + 1) * (size_t)(a.ihi - a.ilo + 1);
+        const int nka = a.kb - a.ka + 1;
+        const bool whole = a.ka == a.klo && a.klo == 1 && nka % a.nkf == 0 && a.khi == a.nkf && p.khi == p.nkf &&
+                           p.ka == 1 && p.klo == 1 && p.kb == p.nkf && p.nkf == a.nkf;
+        if (whole && p.jlo == a.jlo && p.jhi == a.jhi && p.ilo == a.ilo && p.ihi == a.ihi && p.ja == a.ja && p.jb == a.jb &&
+            p.ia == a.ia && p.ib == a.ib && p.host == a.host + (size_t)nka * hplane &&
+            p.dev == a.dev + (size_t)nka * c->g.plane) {
+          a.kb += p.nkf;
+          continue;
+        }
+      }
+      out.push_back(p);
+    }
+    v.swap(out);
+  };
+  merge(pd); merge(pu);
   const int rows = I2 - I1 + 1;
   if (nslabs > rows) nslabs = rows;
   const int per = (rows + nslabs - 1) / nslabs;
@@ -722,7 +749,7 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
   // double-buffered so that the pack kernel of slab s+1 runs while slab s travels.  Arrays whose host box is
   // wider than the device box go array by array through the 3-D copy path (slab_copy).
   auto fast = [](const XferPlan& p) { return p.ja == p.jlo && p.jb == p.jhi; };
-  auto slab_tables = [&](const std::vector<XferPlan>& v, std::vector<SlabTable>& tabs, size_t& block) {
+  auto slab_tables = [&](const std::vector<XferPlan>& v, std::vector<SlabTable>& tabs, size_t& block, bool upward) {
     // tabs[s * nt + t]: t-th table (at most SLAB_MAX_ARRAYS arrays) of slab s; block: doubles of the largest slab
     std::vector<int> f;
     for (size_t q = 0; q < v.size(); ++q) if (fast(v[q])) f.push_back((int)q);
@@ -739,8 +766,25 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
         SlabTable& T = tabs[(size_t)s * nt + q / SLAB_MAX_ARRAYS];
         SlabArray& A = T.a[T.n++];
         A.dev = p.dev; A.off = off; A.ja = p.ja; A.nj = p.jb - p.ja + 1; A.ia = ia; A.ni = ib - ia + 1;
-        A.ka = p.ka; A.nk = p.kb - p.ka + 1; A.plan = f[q]; A.pad = 0;
-        off += (long long)A.nj * A.ni * A.nk;
+        A.ka = p.ka; A.nk = p.kb - p.ka + 1; A.plan = f[q];
+        A.w = A.nj * A.ni; A.a0 = 0; A.p8 = 0;
+        if (upward) {
+          // Host -> device reads run at full rate in both directions of the link only when they start on a
+          // 128-byte boundary of host memory (measured: scratch/pcie4.cu, 47+47 GB/s against 37+39).  The planes
+          // of a Fortran array start at multiples of 8 bytes: the copy of a plane therefore begins at the
+          // 128-byte line that holds its first element (`lead` doubles early), and the planes whose starts are
+          // congruent modulo 128 share one 2-D copy (table_copies).
+          const size_t hrow = (size_t)(p.jhi - p.jlo + 1), hplane = hrow * (size_t)(p.ihi - p.ilo + 1);
+          const uintptr_t h0 = (uintptr_t)(p.host + (size_t)(A.ka - p.klo) * hplane + (size_t)(ia - p.ilo) * hrow);
+          int period = 1;
+          while (((size_t)period * hplane * sizeof(double)) & 127) period *= 2;
+          if (period == 1 || (size_t)A.nj * A.ni * sizeof(double) * (size_t)A.nk / period >= ((size_t)3 << 20)) {
+            A.a0 = (int)(h0 & 127); A.p8 = (int)((hplane * sizeof(double)) & 127);
+          }
+          A.w = (A.nj * A.ni + 15 + 15) / 16 * 16;      // room for the largest lead, a multiple of 128 bytes
+        }
+        off += (long long)A.w * A.nk;
+        off = (off + 15) / 16 * 16;
       }
       if ((size_t)off > block) block = (size_t)off;
     }
@@ -748,7 +792,7 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
   };
   std::vector<SlabTable> td, tu;
   size_t need_d = 0, need_u = 0;
-  const int ntd = slab_tables(pd, td, need_d), ntu = slab_tables(pu, tu, need_u);
+  const int ntd = slab_tables(pd, td, need_d, false), ntu = slab_tables(pu, tu, need_u, true);
   size_t need_slow = 0;     // the per-array path reuses the first staging block of its direction
   for (const auto* v : {&pd, &pu})
     for (const XferPlan& p : *v)
@@ -766,9 +810,17 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
     MB_CUDA(cudaStreamCreateWithFlags(&c->xs_unpack, cudaStreamNonBlocking));
     MB_CUDA(cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming));
   }
+  const bool trace = getenv("MOLOCH_B200_HANDOFF_TRACE") != nullptr;   // timeline of the slabs on stderr
+  if (trace && !c->ev_traced) {
+    for (cudaEvent_t e : c->ev_slab) cudaEventDestroy(e);
+    c->ev_slab.clear();
+    cudaEventDestroy(c->ev_ready);
+    MB_CUDA(cudaEventCreate(&c->ev_ready));
+    c->ev_traced = true;
+  }
   while ((int)c->ev_slab.size() < 4 * nslabs) {
     cudaEvent_t e;
-    MB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    MB_CUDA(cudaEventCreateWithFlags(&e, trace ? cudaEventDefault : cudaEventDisableTiming));
     c->ev_slab.push_back(e);
   }
   auto grow = [&](double*& buf, size_t& have, size_t need) -> int {
@@ -795,9 +847,32 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
       const size_t hrow = (size_t)(p.jhi - p.jlo + 1), hplane = hrow * (size_t)(p.ihi - p.ilo + 1);
       double* h0 = p.host + (size_t)(A.ka - p.klo) * hplane + (size_t)(A.ia - p.ilo) * hrow;
       const size_t run = (size_t)A.nj * A.ni * sizeof(double);
-      if (to_device)
-        MB_CUDA(cudaMemcpy2DAsync(stage + A.off, run, h0, hplane * sizeof(double), run, (size_t)A.nk, cudaMemcpyHostToDevice, st));
-      else
+      if (to_device) {
+        const size_t pitch = hplane * sizeof(double);
+        int period = 1;
+        while (((size_t)period * pitch) & 127) period *= 2;          // 1, 2, 4, 8 or 16
+        if (period > 1 && run * (size_t)A.nk / period < ((size_t)3 << 20)) {
+          // too few planes to stay with large copies: one unaligned copy (the kernel's lead formula needs a0 = p8 = 0,
+          // which slab_tables chose by the same rule)
+          MB_CUDA(cudaMemcpy2DAsync(stage + A.off, (size_t)A.w * sizeof(double), h0, pitch, run, (size_t)A.nk,
+                                    cudaMemcpyHostToDevice, st));
+          continue;
+        }
+        for (int r = 0; r < period && r < A.nk; ++r) {
+          int k = r, nrow = (A.nk - r + period - 1) / period;
+          uintptr_t a = (uintptr_t)h0 + (size_t)r * pitch, base = a & ~(uintptr_t)127;
+          if (base < (uintptr_t)p.host) {
+            // the very first plane of the array: its 128-byte line begins before the array (outside what the
+            // caller page-locked): this one plane travels unaligned
+            MB_CUDA(cudaMemcpyAsync(stage + A.off + (size_t)k * A.w + (a - base) / sizeof(double), (const void*)a, run,
+                                    cudaMemcpyHostToDevice, st));
+            k += period; --nrow; a += (size_t)period * pitch; base = a & ~(uintptr_t)127;
+          }
+          if (nrow > 0)
+            MB_CUDA(cudaMemcpy2DAsync(stage + A.off + (size_t)k * A.w, (size_t)period * A.w * sizeof(double), (const void*)base,
+                                      (size_t)period * pitch, (a - base) + run, (size_t)nrow, cudaMemcpyHostToDevice, st));
+        }
+      } else
         MB_CUDA(cudaMemcpy2DAsync(h0, hplane * sizeof(double), stage + A.off, run, run, (size_t)A.nk, cudaMemcpyDeviceToHost, st));
     }
     return 0;
@@ -822,10 +897,17 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
   }
   // ---- slab by slab: wait for the state, run the host physics, send its tendencies up ----
   int rc = 0;
+  const bool nodep = getenv("MOLOCH_B200_HANDOFF_NODEP") != nullptr;   // probe only: both directions unordered
   for (int s = 0; s < nslabs && rc == 0; ++s) {
     const int i1 = I1 + s * per, i2 = (i1 + per - 1 < I2) ? i1 + per - 1 : I2;
-    MB_CUDA(cudaEventSynchronize(ev_arrived(s)));     // slab s of the state is on the host
-    if (physics && physics(user, i1, i2) != 0) { rc = fail("handoff: the physics callback reported an error"); break; }
+    if (physics) {
+      MB_CUDA(cudaEventSynchronize(ev_arrived(s)));   // slab s of the state is on the host
+      if (physics(user, i1, i2) != 0) { rc = fail("handoff: the physics callback reported an error"); break; }
+    } else if (!nodep) {
+      // no host physics in between: the same ordering (tendencies of slab s after the state of slab s) is kept
+      // on the device, without a host round trip per slab
+      MB_CUDA(cudaStreamWaitEvent(c->xs_up, ev_arrived(s), 0));
+    }
     double* blk = c->stage_up + (size_t)(s & 1) * c->stage_up_doubles;
     if (s >= 2) MB_CUDA(cudaStreamWaitEvent(c->xs_up, ev_scattered(s - 2), 0));
     for (int t = 0; t < ntu && rc == 0; ++t)
@@ -842,6 +924,15 @@ int moloch_b200_handoff(moloch_b200_ctx* c, const moloch_b200_xfer* down, int nd
   // completion on return: host arrays may be reused, later work on the context's
   // stream is enqueued after this point and therefore sees the uploaded slabs
   for (cudaStream_t st : {c->xs_down, c->xs_pack, c->xs_up, c->xs_unpack}) MB_CUDA(cudaStreamSynchronize(st));
+  if (trace && rc == 0) {
+    fprintf(stderr, "handoff trace (ms after the start): slab  gathered  arrived  uploaded  scattered\n");
+    for (int s = 0; s < nslabs; ++s) {
+      float t[4] = {-1.f, -1.f, -1.f, -1.f};
+      for (int q = 0; q < 4; ++q) cudaEventElapsedTime(&t[q], c->ev_ready, EV[4 * s + q]);
+      fprintf(stderr, "  %2d  %8.3f %8.3f %8.3f %8.3f\n", s, t[0], t[1], t[2], t[3]);
+    }
+    cudaGetLastError();
+  }
   if (rc == 0) rc = halo_timeout_check(*c);   // the downloaded state is host-visible now
   return rc;
 }

@@ -144,6 +144,7 @@ struct Ctx {
   cudaStream_t xs_down = nullptr, xs_up = nullptr;       // copy streams (D2H, H2D)
   cudaStream_t xs_pack = nullptr, xs_unpack = nullptr;   // gather / scatter kernels of the slabs
   cudaEvent_t ev_ready = nullptr;
+  bool ev_traced = false;
   std::vector<cudaEvent_t> ev_slab;                      // 4 per slab: gathered, arrived, uploaded, scattered
   double *stage_down = nullptr, *stage_up = nullptr;     // two slab-sized staging blocks per direction
   size_t stage_down_doubles = 0, stage_up_doubles = 0;   // size of ONE block
@@ -279,7 +280,10 @@ int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int n
                cudaStream_t on = nullptr);   // on: another stream than the context's (hand-off copy streams)
 // all arrays of one slab of the physics hand-off in one launch: padded device boxes <-> packed staging block
 constexpr int SLAB_MAX_ARRAYS = 60;
-struct SlabArray { double* dev; long long off; int ja, nj, ia, ni, ka, nk, plan, pad; };   // off: doubles into the staging block; plan: host-side index
+// off: doubles into the staging block; plane k of the array sits at off + k*w + lead(k), lead(k) = ((a0 + k*p8) & 127) / 8
+// doubles (upward direction: every host read starts on a 128-byte boundary, see moloch_b200_handoff; downward: w = nj*ni,
+// a0 = p8 = 0); plan: host-side index of the array
+struct SlabArray { double* dev; long long off; int ja, nj, ia, ni, ka, nk, w, a0, p8, plan; };
 struct SlabTable { SlabArray a[SLAB_MAX_ARRAYS]; int n; };
 int k_slab_copy(Ctx& c, const SlabTable& t, double* stage, bool pack, cudaStream_t on);
 // kernels_bdy.cu

@@ -1324,7 +1324,8 @@ __global__ void moloch_slab_copy(Geo g, SlabTable t, double* __restrict__ stage,
   double* __restrict__ st = stage + a.off;
   for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y) {
     const int k = (int)(r / a.ni), i = (int)(r % a.ni);
-    const long long d0 = gidx(g, a.ja, a.ia + i, a.ka + k), s0 = r * a.nj;
+    const long long d0 = gidx(g, a.ja, a.ia + i, a.ka + k);
+    const long long s0 = (long long)k * a.w + (((a.a0 + k * a.p8) & 127) >> 3) + (long long)i * a.nj;
     for (int j = threadIdx.x; j < a.nj; j += blockDim.x) {
       if (pack) st[s0 + j] = a.dev[d0 + j]; else a.dev[d0 + j] = st[s0 + j];
     }

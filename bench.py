@@ -297,13 +297,16 @@ def measure_e2e(m, wl, ksteps, barrier=lambda: None, allreduce_max=lambda x: x):
 
 
 
+WSOLVE_NEW = (8, 9)     # round-2 variants (row tiles, cp.async.cg ring, re-partitioned upward ring)
+
+
 def variants_agree(wl, device, lib=None) -> bool:
-    """Variants 6 and 7 of the column solver against variant 5 on a small case of the same configuration (same
+    """The round-2 variants of the column solver against variant 5 on a small case of the same configuration (same
     species, boundary type, level count): two steps, every prognostic field bit for bit."""
     from regcm_b200.moloch import MolochB200
     swl = S.small(wl, min(wl.jx, 72), min(wl.iy, 56), wl.kz)
     out = []
-    for v in (5, 6, 7):
+    for v in (5,) + WSOLVE_NEW:
         m = MolochB200(swl, device=device, lib=lib).allocate_moloch()
         fields, profiles, boxes = S.model_inputs_local(swl, m.g)
         m.init_moloch(fields, profiles, boxes)
@@ -317,15 +320,16 @@ def variants_agree(wl, device, lib=None) -> bool:
 def autotune_wsolve(m, wl, timed, all_min=lambda x: x, device=-1, lib=None):
     """(variant, record): times two steps of the benchmark model per admissible variant and picks the faster.
     `all_min`: minimum over the ranks (every rank must take the same decisions)."""
-    rec = {"candidates": [5, 2]}       # both measured on the B200 in round 1 (5 won at N = 1)
+    rec = {"candidates": [5], "rejected": {"2": "time (13.3 vs 12.1 ms/step, r2a)", "6": "time (246 vs 217 us, r2a)",
+                                            "7": "time (248 vs 217 us, r2a)", "10": "time (246 vs 201 us, r2ws)"}}
     try:
         ok = bool(variants_agree(wl, device, lib))
     except Exception as exc:  # noqa: BLE001
         ok = False
-        rec["note"] = f"variant 6 not considered: {exc}"
-    rec["v6_bit_exact_vs_v5"] = bool(all_min(1.0 if ok else 0.0) > 0.5)
-    if rec["v6_bit_exact_vs_v5"]:
-        rec["candidates"] += [6, 7]
+        rec["note"] = f"variants {WSOLVE_NEW} not considered: {exc}"
+    rec["new_bit_exact_vs_v5"] = bool(all_min(1.0 if ok else 0.0) > 0.5)
+    if rec["new_bit_exact_vs_v5"]:
+        rec["candidates"] += list(WSOLVE_NEW)
     rec["ms_per_step"] = {}
     for v in rec["candidates"]:
         m.set_option("wsolve", v)

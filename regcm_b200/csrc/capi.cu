@@ -353,6 +353,65 @@ static int do_status_update(Ctx& c) {
   return k_restagger(c, false);
 }
 
+// ---- CUDA graphs -----------------------------------------------------------------
+// A MOLOCH step is 60-100 short launches; on small per-GPU grids (config 2, or cordex25 on 8 GPUs) the host's
+// launch path and the gaps between kernels are a visible part of it.  The call sequences that do not depend on
+// host state are captured once (on their second call: the first one has warmed up every lazy allocation) and
+// replayed.  What changes from step to step -- the halo round numbers -- is relative to a device-side base that
+// the graph's last node advances (Ctx::seq_base).  Not captured: runs with the lateral boundary (host-side time
+// bookkeeping and event-driven nudging), the NCCL transport (it may grow its buffers), profiled runs.
+static void graphs_drop(Ctx& c) {
+  for (auto& gs : c.graph) {
+#ifndef MB_HOST_EMU
+    if (gs.exec) cudaGraphExecDestroy((cudaGraphExec_t)gs.exec);
+#endif
+    gs = Ctx::GraphSlot{};
+  }
+}
+static bool graph_ok(const Ctx& c) {
+  if (!c.use_graph || c.profiling || c.cfg.do_bdy) return false;
+  if (c.cfg.nranks > 1 && !c.p2p) return false;
+  return true;
+}
+template <class F>
+static int run_graphed(Ctx& c, int slot, F&& fn) {
+  if (!graph_ok(c)) return fn();
+  Ctx::GraphSlot& gs = c.graph[slot];
+  if (!gs.exec && gs.calls++ < 1) return fn();
+#ifdef MB_HOST_EMU
+  // tests/emu: launches execute at once, so there is nothing to replay; the call runs eagerly and then advances
+  // the base of the round numbers the way a replayed graph's last node does
+  const unsigned long long seq0 = c.halo_seq;
+  if (fn()) return 1;
+  const unsigned long long rounds = c.halo_seq - seq0;
+  if (rounds) { if (k_seq_bump(c, rounds)) return 1; c.seq_base += rounds; }
+  return 0;
+#else
+  if (!gs.exec) {
+    const unsigned long long seq0 = c.halo_seq;
+    const long long l0 = c.launches;
+    cudaGraph_t graph = nullptr;
+    MB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+    int rc = fn();
+    const unsigned long long rounds = c.halo_seq - seq0;
+    if (rc == 0 && rounds) rc = k_seq_bump(c, rounds);
+    cudaError_t e = cudaStreamEndCapture(c.stream, &graph);
+    gs.rounds = rounds; gs.launches = c.launches - l0;
+    c.halo_seq = seq0; c.launches = l0;      // nothing has run yet
+    if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("graph capture: ") + cudaGetErrorString(e)); }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    gs.exec = exec;
+  }
+  MB_CUDA(cudaGraphLaunch((cudaGraphExec_t)gs.exec, c.stream));
+  c.halo_seq += gs.rounds; c.seq_base += gs.rounds; c.launches += gs.launches;
+  return 0;
+#endif
+}
+
 static int require_init(Ctx* c) {
   if (!c) return fail("null context");
   if (!c->initialised) return fail("moloch_b200_init has not been called");
@@ -450,6 +509,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   c->h_ptrtab = tab;
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
+  if (const char* e = getenv("MOLOCH_B200_GRAPH")) c->use_graph = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_HALO_TIMEOUT_MS")) { if (atoll(e) >= 1) c->halo_timeout_cycles = atoll(e) * 2000000LL; }
   if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || (v >= 6 && v <= 10)) ? v : 5; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -470,6 +530,7 @@ int moloch_b200_destroy(moloch_b200_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& ev : c->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  graphs_drop(*c);
   halo_free(*c);
   for (int q = 0; q < 3; ++q) if (c->ibnd[q]) cudaFree(c->ibnd[q]);
   for (int q = 0; q < MB_NTABLES; ++q) if (c->tab[q]) cudaFree(c->tab[q]);
@@ -512,6 +573,8 @@ int moloch_b200_p2p_connect(moloch_b200_ctx* c, const void* blobs, int nranks) {
 int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
   if (!c || !name) return fail("set_option: null argument");
   const std::string n(name);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  graphs_drop(*c);      // a captured graph froze the variants it was captured with
   if (n == "wsolve") {
     if (value != 2 && (value < 5 || value > 10)) return fail("set_option: wsolve must be 2 or 5..10");
     c->wsolve_impl = value;
@@ -523,6 +586,8 @@ int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
     c->fuse_halo = value != 0;
     c->fuse_level = value >= 2 ? 2 : 1;
     c->adv_wait_valid = false;
+  } else if (n == "graph") {
+    c->use_graph = value != 0;
   } else if (n == "halo_timeout_ms") {
     if (value < 1) return fail("set_option: halo_timeout_ms must be >= 1");
     c->halo_timeout_cycles = (long long)value * 2000000LL;   // clock64 ticks at ~2 GHz
@@ -535,6 +600,7 @@ int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
 int moloch_b200_set_stream(moloch_b200_ctx* c, void* s) {
   if (!c) return fail("null context");
   cudaStreamSynchronize(c->stream);
+  graphs_drop(*c);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   c->stream = (cudaStream_t)s;
   c->own_stream = false;
@@ -1026,9 +1092,15 @@ int moloch_b200_wafone(moloch_b200_ctx* c, int field, int n) {
     if (c->h_ptrtab[q] == want) return do_wafone_range(*c, q, 1);
   return fail("wafone: field is not one of the advected fields");
 }
-int moloch_b200_dynamical_core(moloch_b200_ctx* c) { ENTRY(c) return do_dynamical_core(*c); }
+int moloch_b200_dynamical_core(moloch_b200_ctx* c) {
+  ENTRY(c)
+  return run_graphed(*c, Ctx::G_DYNCORE, [&] { return do_dynamical_core(*c); });
+}
 int moloch_b200_diagnostics(moloch_b200_ctx* c) { ENTRY(c) return k_diagnostics(*c); }
-int moloch_b200_status_update(moloch_b200_ctx* c) { ENTRY(c) return do_status_update(*c); }
+int moloch_b200_status_update(moloch_b200_ctx* c) {
+  ENTRY(c)
+  return run_graphed(*c, Ctx::G_STATUS, [&] { return do_status_update(*c); });
+}
 int moloch_b200_boundary(moloch_b200_ctx* c) {
   ENTRY(c)
   if (require_bdy(*c)) return 1;
@@ -1085,14 +1157,16 @@ int moloch_b200_ps_check(moloch_b200_ctx* c, double maxmin[2], int32_t* nonfinit
 int moloch_b200_step(moloch_b200_ctx* c, int nsteps) {
   ENTRY(c)
   if (c->cfg.do_bdy && require_bdy(*c)) return 1;
-  for (int n = 0; n < nsteps; ++n) {
+  auto one_step = [&]() -> int {
     if (do_reset_tendencies(*c)) return 1;
     if (do_dynamical_core(*c)) return 1;
     if (c->cfg.do_bdy && do_boundary(*c)) return 1;          // :341-343
     if (k_diagnostics(*c)) return 1;
     if (c->cfg.do_slice && k_mkslice(*c)) return 1;          // :356-358
-    if (do_status_update(*c)) return 1;
-  }
+    return do_status_update(*c);
+  };
+  for (int n = 0; n < nsteps; ++n)
+    if (run_graphed(*c, Ctx::G_STEP, one_step)) return 1;
   return 0;
 }
 
@@ -1145,6 +1219,7 @@ int moloch_b200_profile_enable(moloch_b200_ctx* c, int on) {
   c->events.clear();
   for (int q = 0; q < KID_COUNT; ++q) { c->prof_ms[q] = 0.0; c->prof_n_launch[q] = 0; }
   c->profiling = on != 0;
+  graphs_drop(*c);
   return 0;
 }
 

@@ -64,9 +64,9 @@ struct PushCtl {
 };
 struct WaitCtl {
   int mask;                  // remote sides to signal and to wait for
-  unsigned long long seq;
+  unsigned long long seq;         // round number, relative to the base in flags[6] (see Ctx::seq_base)
   unsigned long long* pflag[4];   // neighbour's arrival counter for the side it sees me on
-  unsigned long long* flags;      // own flag block: [0..3] arrival counters, [5] timeout marker
+  unsigned long long* flags;      // own flag block: [0..3] arrival counters, [5] timeout marker, [6] round base
   long long timeout_cycles;
 };
 struct Ctx;
@@ -102,7 +102,11 @@ struct Ctx {
   // halo transport
   Layout layout;
   unsigned long long* flags = nullptr;   // [0..3] arrival counters per side, [4] CTA counter, [5] timeout flag
-  unsigned long long halo_seq = 0;
+  unsigned long long halo_seq = 0;       // rounds opened so far (every rank counts them identically)
+  // Round numbers reach the kernels RELATIVE to a base that lives in device memory (flags[6]): a captured CUDA
+  // graph of the step carries constant offsets and its last node adds the step's number of rounds to the base,
+  // so the same graph can be replayed step after step.  seq_base mirrors flags[6] on the host.
+  unsigned long long seq_base = 0;
   long long halo_timeout_cycles = 60000000000LL;   // ~30 s at 1.97 GHz (MOLOCH_B200_HALO_TIMEOUT_MS, set_option)
   bool p2p = false;
   bool fuse_halo = true;                 // sound-loop exchanges fused into producer/consumer kernels (p2p only)
@@ -117,6 +121,16 @@ struct Ctx {
   bool adv_wait_valid = false;
   double* gather_buf = nullptr;          // row/column reductions: the other members' partial sums
   size_t gather_doubles = 0;
+  // CUDA graphs of the launch-bound call sequences (capi.cu: run_graphed)
+  struct GraphSlot {
+    void* exec = nullptr;                 // cudaGraphExec_t
+    unsigned long long rounds = 0;        // halo rounds one replay opens
+    long long launches = 0;               // kernel launches one replay stands for
+    int calls = 0;                        // eager calls so far (the first one warms up lazy allocations)
+  };
+  enum { G_STEP = 0, G_DYNCORE, G_STATUS, G_COUNT };
+  GraphSlot graph[G_COUNT];
+  int use_graph = 1;                      // MOLOCH_B200_GRAPH=0 / set_option("graph", 0): eager launches
   // profiling
   bool profiling = false;
   std::vector<ProfEvent> events;
@@ -234,20 +248,21 @@ __device__ __forceinline__ void halo_sync(const WaitCtl& w, int reach = 1, int n
   const bool first = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0);
   if (need == 0 && !first) return;
   if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+    const unsigned long long seq = w.seq + w.flags[6];
     if (first) {
       __threadfence_system();
       for (int sd = 0; sd < 4; ++sd)
         if ((w.mask >> sd) & 1)
-          st_release_sys(w.pflag[sd], w.seq);
+          st_release_sys(w.pflag[sd], seq);
     }
     const long long t0 = clock64();
     for (int sd = 0; sd < 4; ++sd) {
       if (!((need >> sd) & 1)) continue;
       for (;;) {
-        if (ld_acquire_sys(w.flags + sd) >= w.seq) break;
+        if (ld_acquire_sys(w.flags + sd) >= seq) break;
         // neighbour never arrived: mark the round (moloch_b200_sync reports it); later waits give up at once
         if (ld_acquire_sys(w.flags + 5) != 0ULL) break;
-        if (clock64() - t0 > w.timeout_cycles) { w.flags[5] = w.seq; break; }
+        if (clock64() - t0 > w.timeout_cycles) { w.flags[5] = seq; break; }
       }
     }
   }
@@ -256,6 +271,7 @@ __device__ __forceinline__ void halo_sync(const WaitCtl& w, int reach = 1, int n
 #endif
 
 // ---- launchers (kernels.cu) ------------------------------------------------
+int k_seq_bump(Ctx& c, unsigned long long rounds);
 int k_reset_tendencies(Ctx& c);
 int k_tetavf_init(Ctx& c);
 // kernels_sound.cu

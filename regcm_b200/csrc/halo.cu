@@ -395,17 +395,18 @@ __global__ void moloch_halo_push(Geo g, PushParams h) {
     const unsigned long long done = atomicAdd(h.flags + 4, 1ULL);
     if (done == (unsigned long long)gridDim.x - 1ULL) {
       h.flags[4] = 0ULL;
+      const unsigned long long seq = h.seq + h.flags[6];
       __threadfence_system();
       for (int sd = 0; sd < 4; ++sd)
         if ((h.mask >> sd) & 1)
-          st_release_sys(h.pflag[sd], h.seq);
+          st_release_sys(h.pflag[sd], seq);
       const long long t0 = clock64();
       for (int sd = 0; sd < 4; ++sd) {
         if (!((h.mask >> sd) & 1)) continue;
         for (;;) {
-          if (ld_acquire_sys(h.flags + sd) >= h.seq) break;
-          if (ld_acquire_sys(h.flags + 5) != 0ULL) break;                         // an earlier round timed out
-          if (clock64() - t0 > h.timeout_cycles) { h.flags[5] = h.seq; break; }  // neighbour never arrived
+          if (ld_acquire_sys(h.flags + sd) >= seq) break;
+          if (ld_acquire_sys(h.flags + 5) != 0ULL) break;                       // an earlier round timed out
+          if (clock64() - t0 > h.timeout_cycles) { h.flags[5] = seq; break; }  // neighbour never arrived
         }
       }
     }
@@ -441,7 +442,7 @@ int halo_exchange_multi(Ctx& c, const HaloSpec* specs, int nspecs) {
     // every rank numbers the rounds identically, whether it takes part or not
     PushParams h;
     memset(&h, 0, sizeof(h));
-    h.seq = ++c.halo_seq;
+    h.seq = ++c.halo_seq - c.seq_base;
     h.flags = c.flags;
     h.timeout_cycles = c.halo_timeout_cycles;
     for (int sd = 0; sd < 4; ++sd) h.mode[sd] = (nbr[sd] < 0) ? 0 : (nbr[sd] == cf.rank ? 1 : 2);
@@ -513,7 +514,7 @@ int halo_fence(Ctx& c) {
   const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
   PushParams h;
   memset(&h, 0, sizeof(h));
-  h.seq = ++c.halo_seq;
+  h.seq = ++c.halo_seq - c.seq_base;
   h.flags = c.flags;
   h.timeout_cycles = c.halo_timeout_cycles;
   for (int sd = 0; sd < 4; ++sd) {
@@ -546,7 +547,7 @@ int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc) {
   const int nbr[4] = {cf.nbr_left, cf.nbr_right, cf.nbr_bottom, cf.nbr_top};
   memset(pc, 0, sizeof(*pc));
   memset(wc, 0, sizeof(*wc));
-  wc->seq = ++c.halo_seq; wc->flags = c.flags; wc->timeout_cycles = c.halo_timeout_cycles;
+  wc->seq = ++c.halo_seq - c.seq_base; wc->flags = c.flags; wc->timeout_cycles = c.halo_timeout_cycles;
   for (int sd = 0; sd < 4; ++sd) {
     if (nbr[sd] < 0 || nbr[sd] == cf.rank) continue;
     const Peer& pr = c.peer[sd];

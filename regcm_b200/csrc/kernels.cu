@@ -1316,6 +1316,14 @@ int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int n
   return 0;
 }
 
+// last node of a captured graph: the rounds the graph opened are added to the device-side base of the round numbers
+__global__ void moloch_seq_bump(unsigned long long* flags, unsigned long long rounds) { flags[6] += rounds; }
+int k_seq_bump(Ctx& c, unsigned long long rounds) {
+  moloch_seq_bump<<<1, 1, 0, c.stream>>>(c.flags, rounds);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // One slab of the physics hand-off: every array's rows [ia, ia+ni) x [ja, ja+nj) x [ka, ka+nk) between its
 // padded device box and its packed (k, i, j) run inside the slab's staging block.  blockIdx.y = array.
 __global__ void moloch_slab_copy(Geo g, SlabTable t, double* __restrict__ stage, int pack) {

@@ -286,8 +286,8 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys, tmp_path):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
     assert line["parity"]["bit_exact"] is True and line["parity"]["inputs_match_golden"] is True, line["parity"]
     tune = line["config"]["variant_tuning"]["wsolve"]
-    assert tune["v6_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 2, 6, 7], tune
-    assert line["config"]["wsolve_variant"] in (5, 2, 6, 7) and set(tune["ms_per_step"]) == {"5", "2", "6", "7"}
+    assert tune["new_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 8, 9], tune
+    assert line["config"]["wsolve_variant"] in (5, 8, 9) and set(tune["ms_per_step"]) == {"5", "8", "9"}
 
 
 def test_halo_timeout_is_reported(_emulated_library):

@@ -510,6 +510,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
   if (const char* e = getenv("MOLOCH_B200_GRAPH")) c->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("MOLOCH_B200_WAF_ZEROSKIP")) c->waf_zero_skip = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_HALO_TIMEOUT_MS")) { if (atoll(e) >= 1) c->halo_timeout_cycles = atoll(e) * 2000000LL; }
   if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || (v >= 6 && v <= 10)) ? v : 5; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -586,6 +587,8 @@ int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
     c->fuse_halo = value != 0;
     c->fuse_level = value >= 2 ? 2 : 1;
     c->adv_wait_valid = false;
+  } else if (n == "waf_zero_skip") {
+    c->waf_zero_skip = value != 0;
   } else if (n == "graph") {
     c->use_graph = value != 0;
   } else if (n == "halo_timeout_ms") {

@@ -88,6 +88,8 @@ struct Ctx {
   double *zdiv2b, *mx2, *rmx, *rmu, *rmv;
   double *zru, *zrd;      // static ratios of the vertical WAF pass
   int waf_impl = 2;       // 1: per-loop kernels, 2: field-batched fused kernels
+  int waf_zero_skip = 1;  // fused kernels: a field that is exactly +0 in a CTA's / warp's window is not advected
+                          // (bit-identical; MOLOCH_B200_WAF_ZEROSKIP=0 / set_option("waf_zero_skip", 0) computes it)
   int wsolve_impl = 5;    // 2: CTA-parallel coefficients + one-warp sweeps, 5: thread per column with a cp.async ring,
                           // 6: as 5 without the divergence slots (recomputed), 7 warps/SM (MOLOCH_B200_WSOLVE)
   double *wzall, *p0all;  // per-field scratch of the batched wafone

@@ -40,10 +40,14 @@ def main():
     ap.add_argument("--massck", action="store_true", help="also time massck + the ps guard once per step")
     ap.add_argument("--diag", action="store_true", help="tendency diagnostics (idiag, ichdiag)")
     ap.add_argument("--crop", type=int, default=0, help="crop the horizontal domain to N x N")
+    ap.add_argument("--jx", type=int, default=0, help="crop to jx x iy columns (e.g. the per-rank grid of a decomposed run)")
+    ap.add_argument("--iy", type=int, default=0)
     args = ap.parse_args()
     wl = S.WORKLOADS[args.workload]
     if args.crop:
         wl = S.small(wl, min(wl.jx, args.crop), min(wl.iy, args.crop), wl.kz)
+    if args.jx or args.iy:
+        wl = S.small(wl, args.jx or wl.jx, args.iy or wl.iy, wl.kz)
     kw = {}
     if args.boundary:
         kw.update(do_bdy=1, present_qc=1, present_qi=1, mo_top_nudge=1, ichebdy=1)

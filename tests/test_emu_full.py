@@ -23,6 +23,7 @@ import emu_lib
 import util
 
 FULL = os.environ.get("EMU_FULL", "0") == "1"
+from regcm_b200.synthetic import small as _small  # noqa: E402
 
 
 @pytest.fixture(autouse=True)
@@ -338,6 +339,13 @@ def test_full_size_property_checks_at_reduced_size():
 def test_wsolve_variants(impl, case, monkeypatch):
     import test_gpu_zz_variants as V
     V.test_wsolve_variants_bit_exact(impl, case, monkeypatch)
+
+
+@pytest.mark.parametrize("skip", ["1", "0"])
+def test_waf_zero_field_skip(skip, monkeypatch):
+    import test_gpu_zz_variants as V
+    monkeypatch.setattr(V.P.S, "small", lambda wl, jx, iy, kz, **kw: _small(wl, min(jx, 72), min(iy, 40), min(kz, 9), **kw))
+    V.test_waf_zero_field_skip_is_bit_identical(skip, monkeypatch)
 
 
 def test_waf_per_loop_kernels(monkeypatch):

@@ -31,6 +31,34 @@ def test_waf_per_loop_kernels_bit_exact(case, monkeypatch):
     P.test_steps_bit_exact(case)
 
 
+@pytest.mark.parametrize("skip", ["1", "0"])
+def test_waf_zero_field_skip_is_bit_identical(skip, monkeypatch):
+    """The fused WAF kernels do not advect a field that is exactly +0 in the whole window of a CTA / warp
+    (MOLOCH_B200_WAF_ZEROSKIP, default on).  A tracer that is zero except for a blob exercises the skipped,
+    the computed and the mixed windows; the result must equal the oracle's BYTE for byte (the sign of a zero
+    included), with the skip and without it."""
+    import numpy as np
+    from util import make_gpu, make_oracle, oracle_inputs
+    monkeypatch.setenv("MOLOCH_B200_WAF_ZEROSKIP", skip)
+    wl = P.S.small(P.S.WORKLOADS["cordex25"], 132, 70, 14, ntr=3, nspgx=6)
+    o, _ = make_oracle(wl)
+    fields, profiles = oracle_inputs(o, wl)
+    tr = np.array(fields["trac"])
+    tr[1] = 0.0
+    j1, j2 = wl.jx // 3, wl.jx // 3 + 18
+    tr[1, 3:8, wl.iy // 3:wl.iy // 3 + 9, j1:j2] = 1.0e-6 * (1.0 + np.arange(j2 - j1)[None, None, :] * 0.01)
+    tr[2] = 0.0                       # identically zero: skipped everywhere
+    fields = dict(fields, trac=tr)
+    o.set("trac", tr)
+    m = make_gpu(wl, fields, profiles)
+    o.step(3); m.moloch(3)
+    for f in ("trac", "qx", "tetav", "pai"):
+        a, b = np.ascontiguousarray(o.get(f)), np.ascontiguousarray(m.get_global(f))
+        assert a.tobytes() == b.tobytes(), f"{f} differs (zero-field skip = {skip})"
+    assert (m.get_global("trac")[2] == 0.0).all() and not np.signbit(m.get_global("trac")[2]).any()
+    m.close()
+
+
 def test_set_option_switches_variants_of_a_live_context():
     """moloch_b200_set_option: the variants can be switched between steps of one context (what bench.py's
     autotuning does) and the run stays bit-exact; unknown names and values are refused."""

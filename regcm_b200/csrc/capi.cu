@@ -8,8 +8,16 @@
 #include <map>
 #include <utility>
 #include "common.cuh"
+#ifndef MB_HOST_EMU
+#include <nvtx3/nvToolsExt.h>
+#endif
 
 namespace mb {
+
+#ifndef MB_HOST_EMU
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
+#endif
 
 thread_local std::string g_err;
 int fail(const std::string& msg) { g_err = msg; return 1; }
@@ -151,6 +159,7 @@ static int exchange_uv_wide(Ctx& c, const HaloItem* extra, int nextra) {
 // for_adv: called from dynamical_core, `advection` follows at once -- with the fused transport the last
 // sub-step's uvupdate then delivers advection's 2-wide u, v ghosts (:1532-1533) and destagger waits for them
 static int do_sound(Ctx& c, bool for_adv = false) {
+  NvtxRange nvtx("sound");
   const double dts = c.dtsound;
   const int kz = c.g.kz;
   const int nsound = c.cfg.mo_nsound;
@@ -243,6 +252,7 @@ static int do_wafone_range(Ctx& c, int first, int count) {
 
 // uv_delivered: called from dynamical_core right after do_sound(c, true)
 static int do_advection(Ctx& c, bool uv_delivered = false) {
+  NvtxRange nvtx("advection");
   const int kz = c.g.kz;
   // Peer-store transport inside dynamical_core: the two exchanges around the advection proper are fused into
   // the kernels.  u, v (:1532-1533) came with the last uvupdate and destagger waits for them; ux, vx
@@ -286,6 +296,7 @@ static int do_advection(Ctx& c, bool uv_delivered = false) {
 }
 
 static int do_dynamical_core(Ctx& c) {
+  NvtxRange nvtx("dynamical_core");
   if (k_diag(c, 0, false)) return 1;              // ten0, qen0, chiten0 :1092-1103
   for (int n = 0; n < c.cfg.mo_nadv; ++n) {
     if (do_sound(c, true)) return 1;
@@ -296,6 +307,7 @@ static int do_dynamical_core(Ctx& c) {
 }
 
 static int do_reset_tendencies(Ctx& c) {
+  NvtxRange nvtx("reset_tendencies");
   if (k_reset_tendencies(c)) return 1;
   if (c.cfg.ibltyp == 2) {   // tketen :1071-1075
     LaunchScope ls(c, KID_RESET);
@@ -306,6 +318,7 @@ static int do_reset_tendencies(Ctx& c) {
 
 // `boundary` (Main/mod_moloch.F90:448-529)
 static int do_boundary(Ctx& c) {
+  NvtxRange nvtx("boundary");
   const int kz = c.g.kz;
   if (k_diag(c, 1, false)) return 1;              // :455-466
   if (k_bdyval(c, c.xbctime)) return 1;
@@ -341,6 +354,7 @@ static int require_bdy(Ctx& c) {
 }
 
 static int do_status_update(Ctx& c) {
+  NvtxRange nvtx("status_update");
   const int kz = c.g.kz;
   if (k_status_update(c, c.cfg.dtsec)) return 1;
   if (c.cfg.ibltyp == 2 && k_tke_update(c, c.cfg.dtsec)) return 1;   // :1419-1424
@@ -1161,11 +1175,12 @@ int moloch_b200_step(moloch_b200_ctx* c, int nsteps) {
   ENTRY(c)
   if (c->cfg.do_bdy && require_bdy(*c)) return 1;
   auto one_step = [&]() -> int {
+    NvtxRange nvtx("moloch");
     if (do_reset_tendencies(*c)) return 1;
     if (do_dynamical_core(*c)) return 1;
     if (c->cfg.do_bdy && do_boundary(*c)) return 1;          // :341-343
     if (k_diagnostics(*c)) return 1;
-    if (c->cfg.do_slice && k_mkslice(*c)) return 1;          // :356-358
+    if (c->cfg.do_slice) { NvtxRange nv2("mkslice"); if (k_mkslice(*c)) return 1; }   // :356-358
     return do_status_update(*c);
   };
   for (int n = 0; n < nsteps; ++n)

@@ -181,6 +181,18 @@ int halo_timeout_check(Ctx& c);
 
 const char* kernel_name(int kid);
 
+// NVTX ranges with the reference's own names ("moloch", "reset_tendencies", "dynamical_core", "sound",
+// "advection", "boundary", "mkslice", "status_update", "real8_3d_exchange_left_right_bottom_top": the !@acc
+// nvtxStartRange calls of Main/mod_moloch.F90:323,356,454,556,775,1048,1090,1408 and
+// Main/mpplib/mod_mppparam.F90:3816), so that an nsys
+// timeline of the library lines up with one of the reference's OpenACC build.  NVTX3 is header-only; without
+// a profiler attached a range costs a few nanoseconds on the host.
+#ifdef MB_HOST_EMU
+struct NvtxRange { explicit NvtxRange(const char*) {} };
+#else
+struct NvtxRange { explicit NvtxRange(const char* name); ~NvtxRange(); };
+#endif
+
 // RAII-less launch bracket used by every launcher: counts the launch and, when
 // profiling, records CUDA events on the launching stream around it.
 struct LaunchScope {

@@ -429,6 +429,8 @@ static double* peer_ptr(Ctx& c, const Peer& pr, double* local) {
 // A round of independent exchanges in one launch (P2P transport); with NCCL the
 // specs are exchanged one after the other.
 int halo_exchange_multi(Ctx& c, const HaloSpec* specs, int nspecs) {
+  // one device round stands for several of the reference's exchanges: named after the widest of them
+  NvtxRange nvtx("real8_3d_exchange_left_right_bottom_top");
   if (!c.p2p) {
     for (int q = 0; q < nspecs; ++q)
       if (halo_exchange(c, specs[q].items, specs[q].n, specs[q].stag, specs[q].nex, specs[q].lr, specs[q].bt,

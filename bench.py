@@ -420,6 +420,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--mode", default="strict", choices=["strict", "fast"],
+                    help="strict: no FMA contraction, bit-identical to the reference arithmetic (the default and the "
+                         "parity build); fast: the FMA-contracting build of the same sources (within the tolerances "
+                         "of tests/test_gpu_zz_fastmode.py)")
     ap.add_argument("--transport", default=os.environ.get("BENCH_TRANSPORT", "p2p"), choices=["p2p", "nccl"])
     ap.add_argument("--px", type=int, default=int(os.environ.get("BENCH_PX", "0")))
     ap.add_argument("--py", type=int, default=int(os.environ.get("BENCH_PY", "0")))
@@ -446,6 +450,9 @@ def main():
         print(json.dumps(line), flush=True)
         return 0
 
+    if args.mode == "fast":      # chosen before the binding module looks for its library
+        os.environ["MOLOCH_B200_LIB"] = os.path.join(ROOT, "regcm_b200", "libmoloch_b200_fast.so")
+        args.no_parity = True    # not bit-identical by construction: its check is the tolerance test
     import torch
     import torch.distributed as dist
     from regcm_b200.moloch import MolochB200, STATE_FIELDS
@@ -676,6 +683,9 @@ def main():
         line = base_line(wl, args, world)
         line["config"]["decomposition"] = f"{m.g.px}x{m.g.py}"
         line["config"]["halo_transport"] = ("none" if world == 1 else args.transport)
+        line["config"]["arith_mode"] = ("strict (-fmad=false: bit-identical to the reference's operation order)"
+                                        if args.mode == "strict" else
+                                        "fast (-fmad=true; tolerances of tests/test_gpu_zz_fastmode.py)")
         line["config"]["wsolve_variant"] = wsolve_variant
         line["config"]["variant_tuning"] = tuning
         if world > 1 and args.transport == "p2p":

@@ -13,6 +13,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmoloch_b200.so")
+# the same sources with FMA contraction allowed ("fast" mode: not bit-identical to the reference's arithmetic,
+# within the tolerances of SURVEY.md 8(c); tests/test_gpu_zz_fastmode.py; bench.py --mode fast)
+LIB_FAST = os.path.join(HERE, "libmoloch_b200_fast.so")
 SOURCES = ["kernels.cu", "kernels_sound.cu", "kernels_waf.cu", "kernels_bdy.cu", "halo.cu", "capi.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "geo.h"), os.path.join(CSRC, "bdy_cells.h"),
            os.path.join(HERE, "..", "include", "moloch_b200.h")]
@@ -84,6 +87,23 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=(), ou
     return target
 
 
+def build_fast(force: bool = False) -> str:
+    """libmoloch_b200_fast.so: -fmad=true instead of -fmad=false, everything else identical."""
+    if not force and os.path.exists(LIB_FAST):
+        t = os.path.getmtime(LIB_FAST)
+        deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+        if not any(os.path.getmtime(d) > t for d in deps):
+            return LIB_FAST
+    keep = list(NVCC_FLAGS)
+    try:
+        NVCC_FLAGS[NVCC_FLAGS.index("-fmad=false")] = "-fmad=true"
+        return build_library(out=LIB_FAST)
+    finally:
+        NVCC_FLAGS[:] = keep
+
+
 if __name__ == "__main__":
     import sys
     print(build_library(force="-f" in sys.argv, verbose="-v" in sys.argv))
+    if "--fast" in sys.argv:
+        print(build_fast(force="-f" in sys.argv))

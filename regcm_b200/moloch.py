@@ -104,6 +104,15 @@ def load_library():
     return _lib
 
 
+def load_fast_library():
+    """The FMA-contracting build (libmoloch_b200_fast.so): same entry points, results within the fast-mode
+    tolerances of SURVEY.md 8(c) instead of bit-identical."""
+    path = os.path.join(_HERE, "libmoloch_b200_fast.so")
+    if not os.path.exists(path):
+        raise MolochError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    return bind_library(C.CDLL(path, mode=C.RTLD_LOCAL), path)
+
+
 def bind_library(lib, path: str = "?"):
     """ctypes signatures of every entry of include/moloch_b200.h on a loaded library object."""
     ctx = C.c_void_p

@@ -297,7 +297,7 @@ def measure_e2e(m, wl, ksteps, barrier=lambda: None, allreduce_max=lambda x: x):
 
 
 
-WSOLVE_NEW = (8, 9)     # round-2 variants (row tiles, cp.async.cg ring, re-partitioned upward ring)
+WSOLVE_NEW = (8, 9, 12)     # round-2 variants (row tiles, cp.async.cg ring, re-partitioned upward ring; 12: sweeps in TMEM)
 
 
 def variants_agree(wl, device, lib=None) -> bool:
@@ -321,7 +321,8 @@ def autotune_wsolve(m, wl, timed, all_min=lambda x: x, device=-1, lib=None):
     """(variant, record): times two steps of the benchmark model per admissible variant and picks the faster.
     `all_min`: minimum over the ranks (every rank must take the same decisions)."""
     rec = {"candidates": [5], "rejected": {"2": "time (13.3 vs 12.1 ms/step, r2a)", "6": "time (246 vs 217 us, r2a)",
-                                            "7": "time (248 vs 217 us, r2a)", "10": "time (246 vs 201 us, r2ws)"}}
+                                            "7": "time (248 vs 217 us, r2a)", "10": "time (246 vs 201 us, r2ws)",
+                                            "11": "time (168 vs 158 us for 12, r2ws3)", "13": "time (160 vs 158 us, r2ws4)"}}
     try:
         ok = bool(variants_agree(wl, device, lib))
     except Exception as exc:  # noqa: BLE001

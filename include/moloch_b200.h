@@ -164,11 +164,15 @@ int moloch_b200_p2p_export(moloch_b200_ctx* ctx, void* blob);
 int moloch_b200_p2p_connect(moloch_b200_ctx* ctx, const void* blobs, int nranks);
 
 /* Kernel-variant switches of an existing context (what the MOLOCH_B200_* environment variables set at create):
- *   "wsolve"    5 | 6 | 7 | 2   implicit-w column solver: three sweep arrays in shared memory (4 warps per SM), two
- *                           (7 warps with a 4-deep ring, 6 warps with a 6-deep ring), or the CTA-parallel variant
+ *   "wsolve"    12 (default) | 11 | 13   implicit-w column solver, thread per column, sweep arrays in tensor memory
+ *               (tcgen05.st/ld), eight warps per SM, cp.async ring of 6 / 8 / 4 levels; kz <= 41, taller grids run 8
+ *               8 | 9 | 10   row tiles, 16-byte cp.async.cg ring, sweep arrays in shared memory (4-5 warps per SM)
+ *               5 | 6 | 7 | 2   round 1: 8-byte cp.async.ca ring (three / two sweep arrays), CTA-parallel variant
  *   "waf"       2 | 1       field-batched fused WAF kernels, or one kernel per reference loop nest
  *   "fuse_halo" 0 | 1 | 2   peer-store transport: exchanges fused into the kernels around them (none / the sound
  *                           loop's sub-steps 2.. / all); every rank must use the same value
+ *   "waf_zero_skip" 1 | 0   fused WAF kernels: a field that is exactly +0 in a CTA's / warp's window is not advected
+ *   "graph"     1 | 0       the step / dynamical_core / status_update sequences replayed as CUDA graphs
  *   "halo_timeout_ms"       how long a kernel of the peer-store transport waits for a neighbour's arrival
  *                           counter before it gives up (default 30 s; MOLOCH_B200_HALO_TIMEOUT_MS at create)
  * All variants give bit-identical results; they exist for measurement (bench.py times them and keeps the faster). */

@@ -526,7 +526,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   if (const char* e = getenv("MOLOCH_B200_GRAPH")) c->use_graph = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_WAF_ZEROSKIP")) c->waf_zero_skip = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_HALO_TIMEOUT_MS")) { if (atoll(e) >= 1) c->halo_timeout_cycles = atoll(e) * 2000000LL; }
-  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || (v >= 6 && v <= 10)) ? v : 5; }
+  if (const char* e = getenv("MOLOCH_B200_WSOLVE")) { const int v = atoi(e); c->wsolve_impl = (v == 2 || (v >= 5 && v <= 13)) ? v : 12; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     c->stream = nullptr;
     return bail("moloch_b200_create: cudaStreamCreate failed");
@@ -591,7 +591,7 @@ int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   graphs_drop(*c);      // a captured graph froze the variants it was captured with
   if (n == "wsolve") {
-    if (value != 2 && (value < 5 || value > 10)) return fail("set_option: wsolve must be 2 or 5..10");
+    if (value != 2 && (value < 5 || value > 13)) return fail("set_option: wsolve must be 2 or 5..13");
     c->wsolve_impl = value;
   } else if (n == "waf") {
     if (value != 1 && value != 2) return fail("set_option: waf must be 1 or 2");

@@ -90,8 +90,9 @@ struct Ctx {
   int waf_impl = 2;       // 1: per-loop kernels, 2: field-batched fused kernels
   int waf_zero_skip = 1;  // fused kernels: a field that is exactly +0 in a CTA's / warp's window is not advected
                           // (bit-identical; MOLOCH_B200_WAF_ZEROSKIP=0 / set_option("waf_zero_skip", 0) computes it)
-  int wsolve_impl = 5;    // 2: CTA-parallel coefficients + one-warp sweeps, 5: thread per column with a cp.async ring,
-                          // 6: as 5 without the divergence slots (recomputed), 7 warps/SM (MOLOCH_B200_WSOLVE)
+  int wsolve_impl = 12;   // 12: thread per column, sweep arrays in tensor memory, 8 warps/SM (kz <= 41; else 8);
+                          // 8..10: row tiles + cp.async.cg ring, sweeps in shared memory; 5..7: round 1's variants;
+                          // 2: CTA-parallel coefficients + one-warp sweeps (MOLOCH_B200_WSOLVE / set_option)
   double *wzall, *p0all;  // per-field scratch of the batched wafone
   double* prof[MB_NPROFILES];
   int prof_n[MB_NPROFILES];

@@ -215,12 +215,14 @@ static int launch_wsolve(Ctx& c, double dts, bool last, long long ncol, const Pu
 int k_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
 int k_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
 int k_wsolve8(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
+int k_wsolve_tm(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep);
 int k_wsolve(Ctx& c, double dts, bool last, const PushCtl* pcp, const EdgePush* epp) {
   const PushCtl pc = pcp ? *pcp : PushCtl{};
   const EdgePush ep = epp ? *epp : EdgePush{};
   if (c.wsolve_impl == 5) return k_wsolve5(c, dts, last, pc, ep);
   if (c.wsolve_impl == 6 || c.wsolve_impl == 7) return k_wsolve6(c, dts, last, pc, ep);
-  if (c.wsolve_impl >= 8 && c.wsolve_impl <= 10) return k_wsolve8(c, dts, last, pc, ep);
+  if (c.wsolve_impl >= 11 && c.wsolve_impl <= 13 && c.g.kz + 1 <= 42) return k_wsolve_tm(c, dts, last, pc, ep);
+  if (c.wsolve_impl >= 8 && c.wsolve_impl <= 13) return k_wsolve8(c, dts, last, pc, ep);
   const Geo& g = c.g;
   const long long ncol = (long long)(g.jci2 - g.jci1 + 1) * (g.ici2 - g.ici1 + 1);
   const bool small = (ncol + 31) / 32 < 148 * 5 * 3;   // fewer than three waves of 32-column CTAs
@@ -730,6 +732,246 @@ static int launch_wsolve8(Ctx& c, double dts, bool last, const PushCtl& pc, cons
       c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, ntile_j, pc, ep);
   MB_CUDA(cudaGetLastError());
   return 0;
+}
+// ---------------------------------------------------------------------------
+// K7+K8+K9, variant 11: the sweep arrays live in TENSOR MEMORY.  Variants 5..10 keep w', wwkw and the finished
+// divergence of a column in shared memory (1 KB per column), which leaves room for four or five warps per SM:
+// one warp per scheduler, and an in-order warp that has its scheduler to itself stalls on every dependent FP64
+// instruction (ncu: 23 % of the issue slots used, "wait" the leading stall).  Blackwell's tensor memory -- 256 KB
+// per SM, 128 lanes x 512 32-bit columns, otherwise idle in this FP64 stencil code -- is a per-thread scratchpad
+// when it is addressed with the 32x32b shape: lane = thread, so a CTA of four warps that allocates 256 columns
+// gives each of its 128 threads 128 doubles: the three sweep arrays of a 41-level column (126).  Shared memory
+// then only holds the cp.async rings, two CTAs = eight warps fit an SM (two per scheduler), and the ring of a
+// warp can be 8 deep.  tcgen05.st in the downward pass, tcgen05.ld one level ahead in the upward pass.
+// Same arithmetic and operation order as variant 8: bit-identical.  kz <= 41 (else variant 8).
+// ---------------------------------------------------------------------------
+constexpr int TM_KZP = 42;          // rows per sweep array in tensor memory
+constexpr int TM_COLS = 256;        // columns allocated per CTA (a power of two >= 2*3*TM_KZP)
+#ifdef MB_HOST_EMU
+struct Tmem {                       // tests/emu: the thread's 128 doubles are a local array
+  double cell[3 * TM_KZP];
+  __device__ void alloc(unsigned*) {}
+  __device__ void release() {}
+  __device__ void st(int idx, double v) { cell[idx] = v; }
+  __device__ void st_done() {}
+  __device__ void ld_issue(int idx, double& dst) { dst = cell[idx]; }
+  __device__ void ld_wait() {}
+};
+#else
+struct Tmem {
+  unsigned base;                    // tensor-memory address of this warp's lane quarter, column 0
+  __device__ __forceinline__ void alloc(unsigned* slot) {   // all threads of the CTA; slot: a word of shared memory
+    if ((threadIdx.x >> 5) == 0) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(slot);
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa), "r"(TM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    base = *slot + (((threadIdx.x >> 5) & 3u) << 21);       // lane field (bits 31:16) = 32 * (warp % 4)
+  }
+  __device__ __forceinline__ void release() {               // all threads of the CTA
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base & 0xffffu), "r"(TM_COLS) : "memory");
+  }
+  __device__ __forceinline__ void st(int idx, double v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(base + 2u * (unsigned)idx),
+                 "r"(__double2loint(v)), "r"(__double2hiint(v)) : "memory");
+  }
+  __device__ __forceinline__ void st_done() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+  // the loaded words may only be read after ld_wait()
+  int lo, hi;
+  __device__ __forceinline__ void ld_issue2(int idx, int& l, int& h) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(l), "=r"(h) : "r"(base + 2u * (unsigned)idx) : "memory");
+  }
+  __device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+};
+#endif
+
+template <int D>
+__global__ void __launch_bounds__(128)
+moloch_wsolve_tm(Geo g, const double* __restrict__ zdiv, double* s, double* w, double* pai,
+                 const double* __restrict__ tetav, double* tetavf, const double* __restrict__ fmz,
+                 const double* __restrict__ fmzf, const double* __restrict__ bdywtw,
+                 const double* __restrict__ ffilt, double dts, double dtrdz, double zcs2, int last, int ntile_j,
+                 int ntiles, PushCtl pc, EdgePush ep) {
+  extern __shared__ double sm[];
+  constexpr int UV = 4;                               // values per level of the upward pass
+  constexpr int DU = (9 * D) / UV;                    // its ring depth in the same memory
+  const int kz = g.kz;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  double* RING = sm + wq * (D * 9 * 32);              // this warp's D slots x 9 values x 32 lanes
+  unsigned* slot = reinterpret_cast<unsigned*>(sm + 4 * (D * 9 * 32));
+  Tmem tm;
+  tm.alloc(slot);
+  const int tile = blockIdx.x * 4 + wq;
+  if (tile < ntiles) {      // (warp-uniform; the warps of the CTA only meet again in tm.release())
+    const int tj = tile % ntile_j, ti = tile / ntile_j;
+    const int i = g.ici1 + ti, jf = g.jde1 + 32 * tj;   // jf - j0 = HJ + 32*tj: a 32-byte boundary
+    const int j = jf + lane;
+    const bool valid = (j >= g.jci1 && j <= g.jci2);
+    const long long pl = g.plane;
+    const long long rowb = gidx(g, jf, i, 1) - pl;      // level k of the tile's first column at rowb + k*pl
+    const int half = lane >> 4, c2 = 2 * (lane & 15);
+    const bool cok = (jf + c2 + 1 <= g.j0 + g.NJ - 1);
+    const double* d0 = half ? zdiv : w;
+    const double* d1 = half ? fmz : bdywtw;
+    const double* d2 = half ? tetav : s;
+    const double* d3 = half ? fmzf : pai;
+    auto fetch = [&](int sl, int k) {                  // slot rows: w, zdiv, bdywtw, fmz, s, tetav, pai, fmzf, tetavf
+      if (!cok) return;
+      double* r = RING + sl * (9 * 32) + half * 32 + c2;
+      const long long o = rowb + k * pl + c2;
+      cp_async16(r, d0 + o); cp_async16(r + 64, d1 + o); cp_async16(r + 128, d2 + o); cp_async16(r + 192, d3 + o);
+      if (!half) cp_async16(r + 256, tetavf + o);
+    };
+    // ---- downward pass ----
+#pragma unroll
+    for (int q = 0; q < D; ++q) {
+      if (kz - q >= 1) fetch(q, kz - q);
+      cp_async_commit();
+    }
+    const long long base = rowb + lane;                // this lane's column
+    double wkp1 = w[base + (kz + 1) * pl];   // w(kzp1)
+    const double w_bottom = wkp1;
+    double wwkp1 = 0.0;                       // wwkw(kzp1) :1055-1057
+    double s_below = s[base + (kz + 1) * pl];
+    double p_w = 0.0, p_tf = 0.0, p_ff = 0.0, p_tv = 0.0, p_pa = 0.0, p_fm = 0.0, p_zd = 0.0;  // level m+1
+    double w1 = 0.0;
+    for (int t0 = 0; t0 < kz; t0 += D) {
+#pragma unroll
+      for (int q = 0; q < D; ++q) {
+        const int m = kz - (t0 + q);
+        cp_async_wait<D - 1>();
+        __syncwarp();                         // the slot was filled by several lanes
+        if (m >= 1) {
+          const double* r = RING + q * (9 * 32) + lane;
+          const double Lw = r[0], Lzdiv = r[32], Lbw = r[64], Lfm = r[96], Ls = r[128], Ltv = r[160],
+                       Lpa = r[192], Lff = r[224], Ltf = r[256];
+          __syncwarp();                       // every lane has read the slot: it may be refilled
+          if (m - D >= 1) fetch(q, m - D);
+          const double zdm = Lzdiv + Lbw * dtrdz * Lfm * (Ls - s_below);
+          s_below = Ls;
+          tm.st(2 * TM_KZP + m, zdm);
+          if (m < kz) {
+            const int k = m + 1;
+            const double tfn = p_tf - p_w * p_ff * dtrdz * (Ltv - p_tv);
+            if (valid) tetavf[base + k * pl] = tfn;
+            const double zrom1w = cpd * tfn * p_ff;
+            double zwexpl = p_w - zrom1w * dtrdz * (Lpa - p_pa) - egrav * dts;
+            zwexpl = zwexpl + rdrcv * zrom1w * dtrdz * (Lpa * zdm - p_pa * p_zd);
+            const double fk = ffilt[k];
+            const double zu = zcs2 * Lfm * zrom1w * Lpa + fk;
+            const double zd = zcs2 * p_fm * zrom1w * p_pa + fk;
+            const double zrapp = 1.0 / (1.0 + zd + zu - zd * wwkp1);
+            wkp1 = zrapp * (zwexpl + zd * wkp1);
+            wwkp1 = zrapp * zu;
+            tm.st(k, wkp1);
+            tm.st(TM_KZP + k, wwkp1);
+          }
+          p_w = Lw; p_tf = Ltf; p_ff = Lff; p_tv = Ltv; p_pa = Lpa; p_fm = Lfm; p_zd = zdm;
+          if (m == 1) w1 = Lw;
+        }
+        cp_async_commit();
+      }
+    }
+    cp_async_wait<0>();
+    tm.st_done();
+    __syncwarp();
+    // ---- upward pass: level k needs pai, fmz of level k-1 and (last) s, fmzf of level k from memory;
+    //      w', wwkw of level k and the divergence of level k-1 from tensor memory, loaded one level ahead ----
+    const double* u0 = half ? fmz : pai;
+    auto fetchup = [&](int sl, int k) {               // slot rows: pai, fmz, s, fmzf
+      if (!cok) return;
+      double* r = RING + sl * (UV * 32) + half * 32 + c2;
+      const long long o = rowb + k * pl + c2;
+      cp_async16(r, u0 + o - pl);
+      if (last) cp_async16(r + 64, (half ? fmzf : s) + o);
+    };
+#pragma unroll
+    for (int q = 0; q < DU; ++q) {
+      if (2 + q <= kz + 1) fetchup(q, 2 + q);
+      cp_async_commit();
+    }
+#ifdef MB_HOST_EMU
+    double n_wp = 0.0, n_ww = 0.0, n_zf = 0.0;
+    if (2 <= kz) { tm.ld_issue(2, n_wp); tm.ld_issue(TM_KZP + 2, n_ww); }
+    tm.ld_issue(2 * TM_KZP + 1, n_zf);
+#else
+    int a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0;
+    if (2 <= kz) { tm.ld_issue2(2, a0, a1); tm.ld_issue2(TM_KZP + 2, b0, b1); }
+    tm.ld_issue2(2 * TM_KZP + 1, c0, c1);
+#endif
+    double wkm1 = w1;
+    for (int t0 = 0; t0 < kz; t0 += DU) {
+#pragma unroll
+      for (int q = 0; q < DU; ++q) {
+        const int k = 2 + t0 + q;
+        cp_async_wait<DU - 1>();
+        __syncwarp();
+        if (k <= kz + 1) {
+          const double* r = RING + q * (UV * 32) + lane;
+          const double Upa = r[0], Ufm = r[32];
+          double Us = 0.0, Uff = 0.0;
+          if (last) { Us = r[64]; Uff = r[96]; }
+          __syncwarp();
+          if (k + DU <= kz + 1) fetchup(q, k + DU);
+          tm.ld_wait();
+#ifdef MB_HOST_EMU
+          const double c_wp = n_wp, c_ww = n_ww, zdm = n_zf;
+          if (k + 1 <= kz) { tm.ld_issue(k + 1, n_wp); tm.ld_issue(TM_KZP + k + 1, n_ww); }
+          if (k + 1 <= kz + 1) tm.ld_issue(2 * TM_KZP + k, n_zf);
+#else
+          const double c_wp = __hiloint2double(a1, a0), c_ww = __hiloint2double(b1, b0), zdm = __hiloint2double(c1, c0);
+          if (k + 1 <= kz) { tm.ld_issue2(k + 1, a0, a1); tm.ld_issue2(TM_KZP + k + 1, b0, b1); }
+          if (k + 1 <= kz + 1) tm.ld_issue2(2 * TM_KZP + k, c0, c1);
+#endif
+          const double wk = (k <= kz) ? c_wp + c_ww * wkm1 : w_bottom;
+          if (valid) {
+            const long long id = base + k * pl;
+            const double pnew = Upa * (1.0 - rdrcv * (zdm + (dtrdz * Ufm * (wkm1 - wk))));
+            pai[id - pl] = pnew;
+            if (pc.mask) edge_push(pc, ep, j, i, k - 1, pnew);
+            if (k <= kz) {
+              w[id] = wk;
+              if (last) s[id] = (wk + Us) * Uff;
+            }
+          }
+          wkm1 = wk;
+        }
+        cp_async_commit();
+      }
+    }
+    cp_async_wait<0>();
+    tm.ld_wait();
+    if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
+  }
+  tm.release();
+}
+template <int D>
+static int launch_wsolve_tm(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
+  const Geo& g = c.g;
+  const int ntile_j = (g.jci2 - g.jde1 + 1 + 31) / 32, ni = g.ici2 - g.ici1 + 1, ntiles = ntile_j * ni;
+  const double dtrdz = dts * c.rdzita;
+  const double zcs2 = (dtrdz * dtrdz) * rdrcv;
+  // at least 78 KB: no more than two CTAs per SM, i.e. no more CTAs than tensor-memory allocations of 256 columns
+  const size_t smem = std::max((size_t)(4 * D * 9) * 32 * sizeof(double) + 16, (size_t)78 * 1024);
+  const double* zsrc = c.cfg.mo_divfilter ? c.zdiv2b : c.f[MB_ZDIV2].p;
+  MB_CUDA(cudaFuncSetAttribute(moloch_wsolve_tm<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LaunchScope ls(c, KID_WSOLVE);
+  moloch_wsolve_tm<D><<<(unsigned)((ntiles + 3) / 4), 128, smem, c.stream>>>(
+      g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.f[MB_FMZ].p,
+      c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, ntile_j, ntiles, pc, ep);
+  MB_CUDA(cudaGetLastError());
+  return 0;
+}
+// variant 11: ring of 8 (74 KB of shared memory per CTA of four warps); variant 12: ring of 6 (55 KB)
+int k_wsolve_tm(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
+  if (c.wsolve_impl == 13) return launch_wsolve_tm<4>(c, dts, last, pc, ep);
+  return c.wsolve_impl == 12 ? launch_wsolve_tm<6>(c, dts, last, pc, ep) : launch_wsolve_tm<8>(c, dts, last, pc, ep);
 }
 // variant 8: three sweep arrays + ring of 6 (46 KB per warp at kz = 41, 4 warps per SM); variant 9: two sweep
 // arrays (divergence recomputed) + ring of 9 (42 KB, 5 warps per SM); variant 10: two + ring of 12 (49 KB, 4 warps)

@@ -287,8 +287,8 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys, tmp_path):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
     assert line["parity"]["bit_exact"] is True and line["parity"]["inputs_match_golden"] is True, line["parity"]
     tune = line["config"]["variant_tuning"]["wsolve"]
-    assert tune["new_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 8, 9], tune
-    assert line["config"]["wsolve_variant"] in (5, 8, 9) and set(tune["ms_per_step"]) == {"5", "8", "9"}
+    assert tune["new_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 8, 9, 12], tune
+    assert line["config"]["wsolve_variant"] in (5, 8, 9, 12) and set(tune["ms_per_step"]) == {"5", "8", "9", "12"}
 
 
 def test_halo_timeout_is_reported(_emulated_library):
@@ -335,7 +335,7 @@ def test_full_size_property_checks_at_reduced_size():
 
 @pytest.mark.parametrize("impl,case", [("6", "limited_area"), ("6", "tall"), ("2", "limited_area"), ("8", "tall"),
                                        ("9", "tall"), ("10", "limited_area"), ("8", "limited_area"), ("9", "limited_area")]
-                         if FULL else [("6", "limited_area"), ("8", "limited_area"), ("9", "tall")])
+                         if FULL else [("6", "limited_area"), ("8", "limited_area"), ("9", "tall"), ("11", "limited_area")])
 def test_wsolve_variants(impl, case, monkeypatch):
     import test_gpu_zz_variants as V
     V.test_wsolve_variants_bit_exact(impl, case, monkeypatch)

@@ -8,6 +8,8 @@ every A/B candidate must be bit-exact before it is timed.
                          2 (CTA = 32 columns x all levels, one-warp sweeps)
                          8, 9, 10 (round 2: row tiles, 16-byte cp.async.cg ring, re-partitioned ring in the upward
                             pass; 8 = three sweep arrays + ring of 6, 9 = two + ring of 9, 10 = two + ring of 12)
+                         11, 12 (sweep arrays in tensor memory via tcgen05.st/ld, eight warps per SM; ring of 8 / 6;
+                            kz <= 41, taller grids run variant 8)
     MOLOCH_B200_WAF    = 2 (default: field-batched fused WAF kernels) | 1 (one kernel per reference loop nest)
 
 (Sorts after the other GPU test files; the same bodies run on the CPU build of the CUDA sources.)"""
@@ -19,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("case", ["limited_area", "tall"])
-@pytest.mark.parametrize("impl", ["6", "7", "2", "8", "9", "10"])
+@pytest.mark.parametrize("impl", ["6", "7", "2", "8", "9", "10", "11", "12"])
 def test_wsolve_variants_bit_exact(impl, case, monkeypatch):
     monkeypatch.setenv("MOLOCH_B200_WSOLVE", impl)
     P.test_steps_bit_exact(case)
@@ -78,6 +80,6 @@ def test_set_option_switches_variants_of_a_live_context():
     with pytest.raises(MolochError, match="wsolve must be"):
         m.set_option("wsolve", 3)
     with pytest.raises(MolochError, match="wsolve must be"):
-        m.set_option("wsolve", 11)
+        m.set_option("wsolve", 14)
     assert np.isfinite(m.get_global("pai")).all()
     m.close()

@@ -80,7 +80,9 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=(), ou
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     target = LIB if out is None else out
-    cmd = [nvcc, "-shared", "-o", target] + objs + ["-ldl"]
+    # -Bsymbolic: the library's own calls bind to its own definitions even when another build of the same
+    # sources (the fast-mode library, a tuning variant) is loaded into the same process
+    cmd = [nvcc, "-shared", "-Xlinker", "-Bsymbolic", "-o", target] + objs + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

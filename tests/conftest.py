@@ -20,6 +20,7 @@ def _built():
     from regcm_b200 import build as B
     try:
         B.build_library()
+        B.build_fast()
     except RuntimeError:
         if not os.path.exists(B.LIB):
             raise

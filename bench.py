@@ -297,6 +297,10 @@ def measure_e2e(m, wl, ksteps, barrier=lambda: None, allreduce_max=lambda x: x):
 
 
 
+WSOLVE_SMALL = 2            # CTA-parallel coefficients + one-warp sweeps out of shared memory: slower than the thread-per-
+                            # column variants on a full GPU (13.3 vs 12.1 ms/step, r2a) but not bound by the latency of one
+                            # column sweep per warp: a candidate where a rank holds few columns (strong scaling, config 2)
+WSOLVE_SMALL_COLUMNS = 60000
 WSOLVE_NEW = (8, 9, 12)     # round-2 variants (row tiles, cp.async.cg ring, re-partitioned upward ring; 12: sweeps in TMEM)
 
 
@@ -306,7 +310,7 @@ def variants_agree(wl, device, lib=None) -> bool:
     from regcm_b200.moloch import MolochB200
     swl = S.small(wl, min(wl.jx, 72), min(wl.iy, 56), wl.kz)
     out = []
-    for v in (5,) + WSOLVE_NEW:
+    for v in (5,) + WSOLVE_NEW + (WSOLVE_SMALL,):
         m = MolochB200(swl, device=device, lib=lib).allocate_moloch()
         fields, profiles, boxes = S.model_inputs_local(swl, m.g)
         m.init_moloch(fields, profiles, boxes)
@@ -320,7 +324,10 @@ def variants_agree(wl, device, lib=None) -> bool:
 def autotune_wsolve(m, wl, timed, all_min=lambda x: x, device=-1, lib=None):
     """(variant, record): times two steps of the benchmark model per admissible variant and picks the faster.
     `all_min`: minimum over the ranks (every rank must take the same decisions)."""
-    rec = {"candidates": [5], "rejected": {"2": "time (13.3 vs 12.1 ms/step, r2a)", "6": "time (246 vs 217 us, r2a)",
+    g = m.g
+    small = (g.jce2 - g.jce1 + 1) * (g.ice2 - g.ice1 + 1) <= WSOLVE_SMALL_COLUMNS
+    rec = {"candidates": [5], "rejected": {"2": "time on a full GPU (13.3 vs 12.1 ms/step, r2a); a candidate again when a "
+                                                 f"rank holds <= {WSOLVE_SMALL_COLUMNS} columns", "6": "time (246 vs 217 us, r2a)",
                                             "7": "time (248 vs 217 us, r2a)", "10": "time (246 vs 201 us, r2ws)",
                                             "11": "time (168 vs 158 us for 12, r2ws3)", "13": "time (160 vs 158 us, r2ws4)"}}
     try:
@@ -330,7 +337,7 @@ def autotune_wsolve(m, wl, timed, all_min=lambda x: x, device=-1, lib=None):
         rec["note"] = f"variants {WSOLVE_NEW} not considered: {exc}"
     rec["new_bit_exact_vs_v5"] = bool(all_min(1.0 if ok else 0.0) > 0.5)
     if rec["new_bit_exact_vs_v5"]:
-        rec["candidates"] += list(WSOLVE_NEW)
+        rec["candidates"] += list(WSOLVE_NEW) + ([WSOLVE_SMALL] if small else [])
     rec["ms_per_step"] = {}
     for v in rec["candidates"]:
         m.set_option("wsolve", v)
@@ -691,6 +698,10 @@ def main():
         line["config"]["variant_tuning"] = tuning
         if world > 1 and args.transport == "p2p":
             line["config"]["halo_fusion_level"] = int(halo_fusion)
+            line["config"]["halo_signal"] = ("consumer's first CTA" if os.environ.get("MOLOCH_B200_PSIGNAL", "1") == "0"
+                                             else "producer's last CTA")
+            line["config"]["halo_wz_fused"] = (os.environ.get("MOLOCH_B200_FUSE_WZ", "1") != "0" and int(halo_fusion) >= 2
+                                               and m.g.px == 1)
             if fusion_note:
                 line["config"]["halo_fusion_note"] = fusion_note
         line.update({"value": value, "ms_per_step": ms / args.steps, "clocks": clocks, "e2e": e2e,

@@ -226,8 +226,23 @@ static int do_wafone_range(Ctx& c, int first, int count) {
     // ghost columns instead of receiving it (:955/:1012), so it needs wz with
     // corner ghosts and pp on two ghost columns: 3 batched messages per side
     // instead of the reference's 2 per field.
-    if (k_waf_z2(c, first, count, dta)) return 1;
     for (int q = 0; q < count; ++q) items[q] = {c.wzall + q * fsz, kz};
+    // Decomposition along i only, peer-store transport, fusion level 2: exchange_bt(wz, 2) (:924) is fused into
+    // the two kernels -- the vertical kernel stores the two edge rows of every field into the neighbours' ghost
+    // rows while it computes them, the horizontal kernel's edge CTAs wait for the neighbours' word.
+    const moloch_b200_config& cf = c.cfg;
+    const bool lr_nbr = cf.nbr_left >= 0 || cf.nbr_right >= 0;
+    const bool bt_nbr = cf.nbr_bottom >= 0 || cf.nbr_top >= 0;
+    if (c.fuse_wz && c.fuse_level >= 2 && halo_fused_available(c) && bt_nbr && !lr_nbr && first == 0) {
+      PushCtl p_wz = {};
+      WaitCtl w_wz = {};
+      EdgePush e_wz = {};
+      if (halo_fused_begin(c, &p_wz, &w_wz)) return 1;
+      if (halo_fused_edge(c, c.wzall, HS_CROSS, false, true, &e_wz, 2, 2)) return 1;
+      if (k_waf_z2(c, first, count, dta, &p_wz, &e_wz)) return 1;
+      return k_waf_yx(c, first, count, dta, &w_wz);
+    }
+    if (k_waf_z2(c, first, count, dta)) return 1;
     if (halo_exchange(c, items.data(), count, HS_CROSS, 2, false, true)) return 1;
     // second round, left/right incl. the ghost rows (corners): wz, the
     // pre-advection pp snapshot written by the vertical kernel, and v (whose
@@ -523,6 +538,8 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   c->h_ptrtab = tab;
   if (const char* e = getenv("MOLOCH_B200_WAF")) c->waf_impl = atoi(e) == 1 ? 1 : 2;
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
+  if (const char* e = getenv("MOLOCH_B200_PSIGNAL")) c->psignal = atoi(e) != 0;
+  if (const char* e = getenv("MOLOCH_B200_FUSE_WZ")) c->fuse_wz = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_GRAPH")) c->use_graph = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_WAF_ZEROSKIP")) c->waf_zero_skip = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_HALO_TIMEOUT_MS")) { if (atoll(e) >= 1) c->halo_timeout_cycles = atoll(e) * 2000000LL; }
@@ -601,6 +618,11 @@ int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
     c->fuse_halo = value != 0;
     c->fuse_level = value >= 2 ? 2 : 1;
     c->adv_wait_valid = false;
+  } else if (n == "halo_psignal") {     // all ranks must agree (like fuse_halo)
+    c->psignal = value != 0;
+    c->adv_wait_valid = false;
+  } else if (n == "fuse_wz") {
+    c->fuse_wz = value != 0;
   } else if (n == "waf_zero_skip") {
     c->waf_zero_skip = value != 0;
   } else if (n == "graph") {

@@ -61,9 +61,16 @@ struct PushCtl {
   int mask;                  // remote sides (0: nothing to push)
   int pNJ[4], pj0[4], pi0[4];
   long long pplane[4];
+  // producer-side signalling (halo_producer_done): the last CTA of the producer grid publishes the round to the
+  // neighbours, so the word travels while the producer drains and the consumer is launched
+  int sig;                        // 0: the consumer's first CTA signals (halo_sync)
+  unsigned long long seq;         // round number, relative to flags[6]
+  unsigned long long* pflag[4];   // neighbour's arrival counter for the side it sees me on
+  unsigned long long* flags;      // own flag block ([4]: CTA counter, [6]: round base)
 };
 struct WaitCtl {
   int mask;                  // remote sides to signal and to wait for
+  int nosig;                 // the round's producer signals (PushCtl::sig): halo_sync only waits
   unsigned long long seq;         // round number, relative to the base in flags[6] (see Ctx::seq_base)
   unsigned long long* pflag[4];   // neighbour's arrival counter for the side it sees me on
   unsigned long long* flags;      // own flag block: [0..3] arrival counters, [5] timeout marker, [6] round base
@@ -113,6 +120,11 @@ struct Ctx {
   long long halo_timeout_cycles = 60000000000LL;   // ~30 s at 1.97 GHz (MOLOCH_B200_HALO_TIMEOUT_MS, set_option)
   bool p2p = false;
   bool fuse_halo = true;                 // sound-loop exchanges fused into producer/consumer kernels (p2p only)
+  int psignal = 1;                       // fused rounds are signalled by the producer's last CTA (halo_producer_done)
+                                         // instead of the consumer's first (MOLOCH_B200_PSIGNAL=0 / set_option("halo_psignal", 0))
+  int fuse_wz = 1;                       // fuse level 2, decomposition along i only: the vertical WAF kernel stores wz's
+                                         // edge rows into the neighbours' ghost rows, the horizontal kernel waits
+                                         // (MOLOCH_B200_FUSE_WZ=0 / set_option("fuse_wz", 0): stand-alone round)
   int fuse_level = 1;                    // 1: sub-steps 2.. of the sound loop only (the GPU-measured configuration);
                                          // 2: also the first sub-step and advection's u,v / ux,vx exchanges
                                          // (MOLOCH_B200_FUSE_HALO=0|1|2, set_option("fuse_halo"); bench.py times 2 vs 1)
@@ -260,7 +272,7 @@ __device__ __forceinline__ void halo_sync(const WaitCtl& w, int reach = 1, int n
     if ((int)(blockIdx.y + 1) * by - 1 + reach >= nrows) need |= 8;
   }
   need &= w.mask;
-  const bool first = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0);
+  const bool first = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) && !w.nosig;
   if (need == 0 && !first) return;
   if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
     const unsigned long long seq = w.seq + w.flags[6];
@@ -282,6 +294,30 @@ __device__ __forceinline__ void halo_sync(const WaitCtl& w, int reach = 1, int n
     }
   }
   __syncthreads();
+}
+// Last statement of a producer kernel of a fused round (every thread of every CTA gets here: no early returns
+// in the kernel).  The CTAs count themselves; the last one publishes the round number to the neighbours:
+// "my edges are in your ghost cells, and every kernel up to this one has completed".  Same meaning as the
+// consumer-side signal of halo_sync (producer and consumer are adjacent in the stream), but the word is on its
+// way while the grid drains and the consumer is launched instead of after the consumer's first CTA has started.
+// Ordering: a CTA's peer stores -> barrier -> device-scope fence + counter increment (thread 0) -> the last
+// CTA's increment -> system-scope fence -> release store of the flag (causality order is transitive over the
+// two scopes, as it is over the kernel boundary + fence of the consumer-side signal).
+__device__ __forceinline__ void halo_producer_done(const PushCtl& pc) {
+  if (!pc.sig) return;
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+    __threadfence();
+    const unsigned long long n = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(pc.flags + 4, 1ULL) == n - 1ULL) {
+      pc.flags[4] = 0ULL;
+      const unsigned long long seq = pc.seq + pc.flags[6];
+      __threadfence_system();
+      for (int sd = 0; sd < 4; ++sd)
+        if ((pc.mask >> sd) & 1)
+          st_release_sys(pc.pflag[sd], seq);
+    }
+  }
 }
 #endif
 
@@ -331,8 +367,8 @@ int k_massck(Ctx& c, int what, double* out7);
 int k_diag(Ctx& c, int which, bool diff);
 // kernels_waf.cu
 int k_waf_ratios(Ctx& c);
-int k_waf_z2(Ctx& c, int first, int count, double dta);
-int k_waf_yx(Ctx& c, int first, int count, double dta);
+int k_waf_z2(Ctx& c, int first, int count, double dta, const PushCtl* pc = nullptr, const EdgePush* ewz = nullptr);
+int k_waf_yx(Ctx& c, int first, int count, double dta, const WaitCtl* wc = nullptr);
 
 // ---- halo exchange (halo.cu) ------------------------------------------------
 enum HaloStag { HS_CROSS = 0, HS_U, HS_V, HS_DOT, HS_P0 };

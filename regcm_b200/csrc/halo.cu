@@ -559,6 +559,11 @@ int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc) {
     pc->mask |= 1 << sd;
   }
   wc->mask = pc->mask;
+  if (c.psignal && pc->mask) {   // the producer's last CTA signals, the consumer only waits
+    pc->sig = 1; pc->seq = wc->seq; pc->flags = c.flags;
+    for (int sd = 0; sd < 4; ++sd) pc->pflag[sd] = wc->pflag[sd];
+    wc->nosig = 1;
+  }
   return 0;
 }
 
@@ -567,6 +572,7 @@ int halo_push_ctl(Ctx& c, PushCtl* pc) {
   const unsigned long long seq = c.halo_seq;
   const int rc = halo_fused_begin(c, pc, &unused);
   c.halo_seq = seq;   // no round is opened
+  pc->sig = 0;        // ... and none is signalled
   return rc;
 }
 

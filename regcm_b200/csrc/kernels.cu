@@ -194,6 +194,7 @@ moloch_wsolve(Geo g, const double* __restrict__ zdiv, double* s, double* __restr
     }
     if (last && row0 == 0) s[base + (long long)kz * pl] = 0.0;
   }
+  halo_producer_done(pc);
 }
 template <int WS_NJ, int WS_THREADS>
 static int launch_wsolve(Ctx& c, double dts, bool last, long long ncol, const PushCtl& pc, const EdgePush& ep) {
@@ -374,6 +375,7 @@ moloch_wsolve5(Geo g, const double* __restrict__ zdiv, double* s, double* w, dou
   }
   cp_async_wait<0>();
   if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
+  halo_producer_done(pc);
 }
 template <int D>
 static int launch_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
@@ -521,6 +523,7 @@ moloch_wsolve6(Geo g, const double* __restrict__ zdiv, double* s, double* w, dou
   }
   cp_async_wait<0>();
   if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
+  halo_producer_done(pc);
 }
 template <int D>
 static int launch_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
@@ -715,6 +718,7 @@ moloch_wsolve8(Geo g, const double* __restrict__ zdiv, double* s, double* w, dou
   }
   cp_async_wait<0>();
   if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
+  halo_producer_done(pc);
 }
 template <int D, bool ZFS>
 static int launch_wsolve8(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
@@ -950,6 +954,7 @@ moloch_wsolve_tm(Geo g, const double* __restrict__ zdiv, double* s, double* w, d
     if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
   }
   tm.release();
+  halo_producer_done(pc);
 }
 template <int D>
 static int launch_wsolve_tm(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
@@ -1282,7 +1287,7 @@ __global__ void moloch_curvature(Geo g, double* __restrict__ ux, double* __restr
                                  const double* __restrict__ mv, const double* __restrict__ rlat, double rdx,
                                  double dta, PushCtl pc, EdgePush eux, EdgePush evx) {
   THREAD_JIK(g.jci1, g.ici1, 1)
-  if (j > g.jci2 || i > g.ici2) return;
+  if (j <= g.jci2 && i <= g.ici2) {
   const long long id = IX(j, i, k);
   const long long i2 = IX2(j, i);
   double tanx, tany;
@@ -1300,6 +1305,8 @@ __global__ void moloch_curvature(Geo g, double* __restrict__ ux, double* __restr
   const double vxn = vx[id] - uxn * uxn * tany * dta;
   vx[id] = vxn;
   if (FUSED && pc.mask) { edge_push(pc, eux, j, i, k, uxn); edge_push(pc, evx, j, i, k, vxn); }
+  }
+  if (FUSED) halo_producer_done(pc);
 }
 int k_curvature(Ctx& c, double dta, const PushCtl* pc, const EdgePush* eux, const EdgePush* evx) {
   const Geo& g = c.g;

@@ -229,17 +229,16 @@ int k_sound_div(Ctx& c, double dts, const WaitCtl* wc) {
 // (tetav, pai, zdiv2: the U-point differences) comes from the lane to the left, lane 0 loads it.
 constexpr int UBX = 32, UBY = 4;      // 64 columns x 4 rows per CTA
 template <bool FUSED>
-__global__ void __launch_bounds__(UBX * UBY)
-moloch_uvupdate2(Geo g, double* __restrict__ u, double* __restrict__ v, const double* __restrict__ zdiv2,
-                 const double* __restrict__ tetav, const double* __restrict__ pai,
-                 const double* __restrict__ bdywtu, const double* __restrict__ bdywtv,
-                 const double* __restrict__ coru, const double* __restrict__ corv,
-                 const double* __restrict__ hx, const double* __restrict__ hy,
-                 const double* __restrict__ mu, const double* __restrict__ mv,
-                 const double* __restrict__ gzitakh, const double* __restrict__ xkdamp, double dts,
-                 double dtrdx, double dtrdy, double dxrdt, int damped, WaitCtl wc, PushCtl pc, EdgePush eu,
-                 EdgePush ev) {
-  if (FUSED) halo_sync(wc);   // pai ghosts of a fused round
+__device__ __forceinline__ void
+uvupdate2_cells(const Geo& g, double* __restrict__ u, double* __restrict__ v, const double* __restrict__ zdiv2,
+                const double* __restrict__ tetav, const double* __restrict__ pai,
+                const double* __restrict__ bdywtu, const double* __restrict__ bdywtv,
+                const double* __restrict__ coru, const double* __restrict__ corv,
+                const double* __restrict__ hx, const double* __restrict__ hy,
+                const double* __restrict__ mu, const double* __restrict__ mv,
+                const double* __restrict__ gzitakh, const double* __restrict__ xkdamp, double dts,
+                double dtrdx, double dtrdy, double dxrdt, int damped, const PushCtl& pc, const EdgePush& eu,
+                const EdgePush& ev) {
   const int lane = threadIdx.x;
   const int ja = g.jde1 + (blockIdx.x * UBX + lane) * 2;
   const int i = g.ide1 + blockIdx.y * UBY + threadIdx.y;
@@ -305,6 +304,23 @@ moloch_uvupdate2(Geo g, double* __restrict__ u, double* __restrict__ v, const do
       if (dvb) edge_push(pc, ev, ja + 1, i, k, vnb);
     }
   }
+}
+template <bool FUSED>
+__global__ void __launch_bounds__(UBX * UBY)
+moloch_uvupdate2(Geo g, double* __restrict__ u, double* __restrict__ v, const double* __restrict__ zdiv2,
+                 const double* __restrict__ tetav, const double* __restrict__ pai,
+                 const double* __restrict__ bdywtu, const double* __restrict__ bdywtv,
+                 const double* __restrict__ coru, const double* __restrict__ corv,
+                 const double* __restrict__ hx, const double* __restrict__ hy,
+                 const double* __restrict__ mu, const double* __restrict__ mv,
+                 const double* __restrict__ gzitakh, const double* __restrict__ xkdamp, double dts,
+                 double dtrdx, double dtrdy, double dxrdt, int damped, WaitCtl wc, PushCtl pc, EdgePush eu,
+                 EdgePush ev) {
+  if (FUSED) halo_sync(wc);   // pai ghosts of a fused round
+  // (the cells return early on rows / columns outside the box; the producer's count below needs every thread)
+  uvupdate2_cells<FUSED>(g, u, v, zdiv2, tetav, pai, bdywtu, bdywtv, coru, corv, hx, hy, mu, mv, gzitakh, xkdamp, dts,
+                         dtrdx, dtrdy, dxrdt, damped, pc, eu, ev);
+  if (FUSED) halo_producer_done(pc);
 }
 
 int k_uvupdate2(Ctx& c, double dts, const WaitCtl* wc, const PushCtl* pc, const EdgePush* eu, const EdgePush* ev) {

@@ -118,11 +118,16 @@ def test_mkslice_massck_tke_misc():
 def _multi_cases():
     M = _gpu_tests()[2]
     keep = None if FULL else {("periodic", "p2p"), ("limited_area_2x2", "p2p"), ("limited_area_2x4", "p2p"),
-                              ("band_2x4", "p2p_unfused"), ("limited_area_2x2", "nccl"), ("limited_area_2x2", "p2p_sound")}
+                              ("band_2x4", "p2p_unfused"), ("limited_area_2x2", "nccl"), ("limited_area_2x2", "p2p_sound"),
+                              ("limited_area_1x4", "p2p"), ("limited_area_1x2", "p2p_csignal"),
+                              ("limited_area_1x4", "p2p_nowz")}
     out = []
-    for tr in ("p2p", "p2p_sound", "p2p_unfused", "nccl"):
+    for tr in ("p2p", "p2p_sound", "p2p_unfused", "nccl", "p2p_csignal", "p2p_nowz"):
         for c in M.CASES:
-            if tr != "p2p" and c[0] not in ("periodic", "limited_area", "limited_area_2x2", "band_2x4"):
+            if tr in ("p2p_csignal", "p2p_nowz"):
+                if c[0] not in M.ROWS_ONLY:
+                    continue
+            elif tr != "p2p" and c[0] not in ("periodic", "limited_area", "limited_area_2x2", "band_2x4"):
                 continue
             if keep is None or (c[0], tr) in keep:
                 out.append(pytest.param(*c, tr, id=f"{c[0]}-{tr}"))
@@ -193,7 +198,8 @@ def test_restart_from_the_save_set():
     Hf.test_restart_from_the_save_set_is_bit_exact()
 
 
-@pytest.mark.parametrize("name,px,py", [("limited_area_2x2", 2, 2), ("band_2x4", 2, 4)] if FULL else [("limited_area_2x2", 2, 2)])
+@pytest.mark.parametrize("name,px,py", [("limited_area_2x2", 2, 2), ("band_2x4", 2, 4), ("limited_area_1x4", 1, 4)] if FULL
+                         else [("limited_area_2x2", 2, 2), ("limited_area_1x4", 1, 4)])
 def test_decomposed_with_drifting_ranks(name, px, py, monkeypatch, _emulated_library):
     """The peer-store transport under rank drift: every launch of every rank thread first sleeps a pseudo-random
     time (one launch in 16, up to 20 ms: a rank is at times several kernels behind its neighbours).  The

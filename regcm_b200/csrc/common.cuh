@@ -252,6 +252,28 @@ __device__ __forceinline__ void edge_push(const PushCtl& pc, const EdgePush& e, 
   if (e.q[3] && i <= e.i2 && i > e.i2 - e.nexi && j >= e.j1 && j <= e.j2)
     e.q[3][(long long)(k - 1) * pc.pplane[3] + (long long)(i + e.di[3] - pc.pi0[3]) * pc.pNJ[3] + (j + e.dj[3] - pc.pj0[3])] = v;
 }
+// The same for a thread that owns one column (j, i) and stores many levels of it (column solver, vertical WAF
+// pass): which sides the column's cells go to, and where, is decided once; a store is then one predicated
+// remote store per side.  Bottom/top sides only (rows-only decompositions; with left/right neighbours the
+// callers use edge_push).
+struct ColPush { double* t2; double* t3; };
+__device__ __forceinline__ ColPush col_push_init(const PushCtl& pc, const EdgePush& e, int j, int i, bool valid) {
+  ColPush c;
+  c.t2 = nullptr; c.t3 = nullptr;
+  if (pc.mask && valid) {
+    if (e.q[2] && i >= e.i1 && i < e.i1 + e.nexi && j >= e.j1 && j <= e.j2) {
+      c.t2 = e.q[2] + (long long)(i + e.di[2] - pc.pi0[2]) * pc.pNJ[2] + (j + e.dj[2] - pc.pj0[2]);
+    }
+    if (e.q[3] && i <= e.i2 && i > e.i2 - e.nexi && j >= e.j1 && j <= e.j2) {
+      c.t3 = e.q[3] + (long long)(i + e.di[3] - pc.pi0[3]) * pc.pNJ[3] + (j + e.dj[3] - pc.pj0[3]);
+    }
+  }
+  return c;
+}
+__device__ __forceinline__ void col_push(const PushCtl& pc, const ColPush& c, long long k, double v) {   // k: 1-based level
+  if (c.t2) c.t2[(k - 1) * pc.pplane[2]] = v;
+  if (c.t3) c.t3[(k - 1) * pc.pplane[3]] = v;
+}
 // First statement of a consumer kernel whose grid tiles the rank's box with
 // blockIdx.x along j and blockIdx.y along i.  Only the CTAs on an edge of the
 // grid read ghost cells of that side, so only they wait for that neighbour; the
@@ -295,20 +317,36 @@ __device__ __forceinline__ void halo_sync(const WaitCtl& w, int reach = 1, int n
   }
   __syncthreads();
 }
-// Last statement of a producer kernel of a fused round (every thread of every CTA gets here: no early returns
-// in the kernel).  The CTAs count themselves; the last one publishes the round number to the neighbours:
-// "my edges are in your ghost cells, and every kernel up to this one has completed".  Same meaning as the
-// consumer-side signal of halo_sync (producer and consumer are adjacent in the stream), but the word is on its
-// way while the grid drains and the consumer is launched instead of after the consumer's first CTA has started.
+// Last statement of a producer kernel of a fused round (every thread of the CTAs concerned gets here: no early
+// returns in the kernel).  The CTAs that hold cells within three rows of the rank's first / last row -- the only
+// ones that store into a neighbour's ghost rows or read the rank's own -- count themselves; the last of them
+// publishes the round number to the neighbours: "my edges are in your ghost cells, and every kernel before this
+// one has completed".  Same meaning as the consumer-side signal of halo_sync (producer and consumer are
+// adjacent in the stream), but the word is on its way while the grid drains and the consumer is launched,
+// instead of after the consumer's first CTA has started.  Interior CTAs do nothing here (a fence and a counter
+// increment in every CTA of a streaming kernel cost more than the signal gains: measured, r2n2b).
+// Rows-only decompositions (no left/right neighbour): halo_fused_begin sets PushCtl::sig only there.
+// A kernel describes its CTAs as runs of `c` consecutive cells of a row-major sequence with rows of `L` cells and
+// `R` rows (2-D grids: c rows per CTA row, L = 1); `b`, `nb`: the CTA's position / count along that sequence,
+// `mult`: CTAs per position (the other grid dimensions).
 // Ordering: a CTA's peer stores -> barrier -> device-scope fence + counter increment (thread 0) -> the last
-// CTA's increment -> system-scope fence -> release store of the flag (causality order is transitive over the
-// two scopes, as it is over the kernel boundary + fence of the consumer-side signal).
-__device__ __forceinline__ void halo_producer_done(const PushCtl& pc) {
+// increment -> system-scope fence -> release store of the flag (causality order is transitive over the two
+// scopes, as it is over the kernel boundary + fence of the consumer-side signal).
+__device__ __forceinline__ void halo_producer_done(const PushCtl& pc, unsigned b, unsigned nb, int c, long long L,
+                                                   long long R, unsigned mult) {
   if (!pc.sig) return;
+  constexpr long long reach = 3;    // two ghost rows + one for the staggered row ranges (a superset costs nothing)
+  const long long lo_n = (reach * L + c - 1) / c;                       // b < lo_n: holds cells of the first rows
+  long long hi = ((R - reach) * L - (c - 1) + (c - 1)) / c;             // b >= hi: holds cells of the last rows
+  if ((R - reach) * L - (c - 1) <= 0) hi = 0;
+  if (!((long long)b < lo_n || (long long)b >= hi)) return;             // (CTA-uniform)
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+    const long long lo_c = lo_n < (long long)nb ? lo_n : (long long)nb;
+    const long long hs = hi > lo_n ? hi : lo_n;
+    const long long n_pos = lo_c + ((long long)nb > hs ? (long long)nb - hs : 0);
+    const unsigned long long n = (unsigned long long)n_pos * mult;
     __threadfence();
-    const unsigned long long n = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
     if (atomicAdd(pc.flags + 4, 1ULL) == n - 1ULL) {
       pc.flags[4] = 0ULL;
       const unsigned long long seq = pc.seq + pc.flags[6];

@@ -559,7 +559,7 @@ int halo_fused_begin(Ctx& c, PushCtl* pc, WaitCtl* wc) {
     pc->mask |= 1 << sd;
   }
   wc->mask = pc->mask;
-  if (c.psignal && pc->mask) {   // the producer's last CTA signals, the consumer only waits
+  if (c.psignal && pc->mask && !(pc->mask & 3)) {   // rows-only: the producer's last edge CTA signals, the consumer only waits
     pc->sig = 1; pc->seq = wc->seq; pc->flags = c.flags;
     for (int sd = 0; sd < 4; ++sd) pc->pflag[sd] = wc->pflag[sd];
     wc->nosig = 1;

@@ -194,7 +194,7 @@ moloch_wsolve(Geo g, const double* __restrict__ zdiv, double* s, double* __restr
     }
     if (last && row0 == 0) s[base + (long long)kz * pl] = 0.0;
   }
-  halo_producer_done(pc);
+  halo_producer_done(pc, blockIdx.x, gridDim.x, WS_NJ, nj, ni, 1);
 }
 template <int WS_NJ, int WS_THREADS>
 static int launch_wsolve(Ctx& c, double dts, bool last, long long ncol, const PushCtl& pc, const EdgePush& ep) {
@@ -375,7 +375,7 @@ moloch_wsolve5(Geo g, const double* __restrict__ zdiv, double* s, double* w, dou
   }
   cp_async_wait<0>();
   if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
-  halo_producer_done(pc);
+  halo_producer_done(pc, blockIdx.x, gridDim.x, 32, g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, 1);
 }
 template <int D>
 static int launch_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
@@ -523,7 +523,7 @@ moloch_wsolve6(Geo g, const double* __restrict__ zdiv, double* s, double* w, dou
   }
   cp_async_wait<0>();
   if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
-  halo_producer_done(pc);
+  halo_producer_done(pc, blockIdx.x, gridDim.x, 32, g.jci2 - g.jci1 + 1, g.ici2 - g.ici1 + 1, 1);
 }
 template <int D>
 static int launch_wsolve6(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
@@ -718,7 +718,7 @@ moloch_wsolve8(Geo g, const double* __restrict__ zdiv, double* s, double* w, dou
   }
   cp_async_wait<0>();
   if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
-  halo_producer_done(pc);
+  halo_producer_done(pc, blockIdx.x, gridDim.x, 1, ntile_j, g.ici2 - g.ici1 + 1, 1);
 }
 template <int D, bool ZFS>
 static int launch_wsolve8(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
@@ -817,6 +817,8 @@ moloch_wsolve_tm(Geo g, const double* __restrict__ zdiv, double* s, double* w, d
     const int i = g.ici1 + ti, jf = g.jde1 + 32 * tj;   // jf - j0 = HJ + 32*tj: a 32-byte boundary
     const int j = jf + lane;
     const bool valid = (j >= g.jci1 && j <= g.jci2);
+    const bool lr_push = (pc.mask & 3) != 0;           // left/right neighbours: the general per-cell push
+    const ColPush cp = col_push_init(pc, ep, j, i, valid && !lr_push);
     const long long pl = g.plane;
     const long long rowb = gidx(g, jf, i, 1) - pl;      // level k of the tile's first column at rowb + k*pl
     const int half = lane >> 4, c2 = 2 * (lane & 15);
@@ -938,7 +940,8 @@ moloch_wsolve_tm(Geo g, const double* __restrict__ zdiv, double* s, double* w, d
             const long long id = base + k * pl;
             const double pnew = Upa * (1.0 - rdrcv * (zdm + (dtrdz * Ufm * (wkm1 - wk))));
             pai[id - pl] = pnew;
-            if (pc.mask) edge_push(pc, ep, j, i, k - 1, pnew);
+            col_push(pc, cp, k - 1, pnew);
+            if (lr_push) edge_push(pc, ep, j, i, k - 1, pnew);
             if (k <= kz) {
               w[id] = wk;
               if (last) s[id] = (wk + Us) * Uff;
@@ -954,7 +957,7 @@ moloch_wsolve_tm(Geo g, const double* __restrict__ zdiv, double* s, double* w, d
     if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
   }
   tm.release();
-  halo_producer_done(pc);
+  halo_producer_done(pc, blockIdx.x, gridDim.x, 4, ntile_j, g.ici2 - g.ici1 + 1, 1);
 }
 template <int D>
 static int launch_wsolve_tm(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
@@ -1306,7 +1309,7 @@ __global__ void moloch_curvature(Geo g, double* __restrict__ ux, double* __restr
   vx[id] = vxn;
   if (FUSED && pc.mask) { edge_push(pc, eux, j, i, k, uxn); edge_push(pc, evx, j, i, k, vxn); }
   }
-  if (FUSED) halo_producer_done(pc);
+  if (FUSED) halo_producer_done(pc, blockIdx.y, gridDim.y, BY, 1, g.ici2 - g.ici1 + 1, gridDim.x * gridDim.z);
 }
 int k_curvature(Ctx& c, double dta, const PushCtl* pc, const EdgePush* eux, const EdgePush* evx) {
   const Geo& g = c.g;

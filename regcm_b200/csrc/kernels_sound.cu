@@ -320,7 +320,7 @@ moloch_uvupdate2(Geo g, double* __restrict__ u, double* __restrict__ v, const do
   // (the cells return early on rows / columns outside the box; the producer's count below needs every thread)
   uvupdate2_cells<FUSED>(g, u, v, zdiv2, tetav, pai, bdywtu, bdywtv, coru, corv, hx, hy, mu, mv, gzitakh, xkdamp, dts,
                          dtrdx, dtrdy, dxrdt, damped, pc, eu, ev);
-  if (FUSED) halo_producer_done(pc);
+  if (FUSED) halo_producer_done(pc, blockIdx.y, gridDim.y, UBY, 1, g.ide2 - g.ide1 + 1, gridDim.x * gridDim.z);
 }
 
 int k_uvupdate2(Ctx& c, double dts, const WaitCtl* wc, const PushCtl* pc, const EdgePush* eu, const EdgePush* ev) {

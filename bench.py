@@ -291,6 +291,8 @@ def measure_e2e(m, wl, ksteps, barrier=lambda: None, allreduce_max=lambda x: x):
            "handoff": handoff_mode, "handoff_slabs": nslabs if handoff_mode == "pipelined" else 1,
            "ms_per_step_by_handoff": {k: v / ksteps * 1e3 for k, v in times.items()},
            "handoff_note": handoff_note,
+           # filled in by main(): the link rate over the hand-off window (e2e step minus the device-resident step)
+           "link_gbs": None,
            "what": "moloch(): device dycore, D2H of u,v,w,ux,vx,pai,tetav,t,tvirt,p,rho,qsat,ps,qx,trac to "
                    "pinned host arrays, H2D of tten,uten,vten,qxten,chiten, device status_update; pipelined: "
                    "rows in slabs, both copy directions overlapped (moloch_b200_handoff)"}
@@ -680,6 +682,12 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
         e2e = measure_e2e(m, wl, max(1, min(args.steps, 5)), barrier, allmax)
+        win = (e2e["ms_per_step"] - ms / args.steps) * 1e-3     # per rank: bytes are this rank's
+        if win > 0:
+            e2e["link_gbs"] = {"d2h": e2e["d2h_bytes_per_step"] / win / 1e9, "h2d": e2e["h2d_bytes_per_step"] / win / 1e9,
+                               "window_ms": win * 1e3,
+                               "note": "bytes of one direction / (e2e step - device-resident step); both directions "
+                                       "run inside the same window when the hand-off is pipelined"}
 
     finite = bool(np.isfinite(m.get_local("pai")).all())
     cpu = None
@@ -698,8 +706,8 @@ def main():
         line["config"]["variant_tuning"] = tuning
         if world > 1 and args.transport == "p2p":
             line["config"]["halo_fusion_level"] = int(halo_fusion)
-            line["config"]["halo_signal"] = ("consumer's first CTA" if os.environ.get("MOLOCH_B200_PSIGNAL", "1") == "0"
-                                             else "producer's last CTA")
+            line["config"]["halo_signal"] = ("producer's last edge CTA" if os.environ.get("MOLOCH_B200_PSIGNAL", "0") == "1"
+                                             else "consumer's first CTA")
             line["config"]["halo_wz_fused"] = (os.environ.get("MOLOCH_B200_FUSE_WZ", "1") != "0" and int(halo_fusion) >= 2
                                                and m.g.px == 1)
             if fusion_note:

@@ -120,8 +120,12 @@ struct Ctx {
   long long halo_timeout_cycles = 60000000000LL;   // ~30 s at 1.97 GHz (MOLOCH_B200_HALO_TIMEOUT_MS, set_option)
   bool p2p = false;
   bool fuse_halo = true;                 // sound-loop exchanges fused into producer/consumer kernels (p2p only)
-  int psignal = 1;                       // fused rounds are signalled by the producer's last CTA (halo_producer_done)
-                                         // instead of the consumer's first (MOLOCH_B200_PSIGNAL=0 / set_option("halo_psignal", 0))
+  int psignal = 0;                       // 1: fused rounds are signalled by the producer's last edge CTA (halo_producer_done)
+                                         // instead of the consumer's first CTA (MOLOCH_B200_PSIGNAL=1 / set_option(
+                                         // "halo_psignal", 1)).  Measured and rejected as the default: cordex25 on 8 GPUs
+                                         // 1.995 vs 1.873 ms/step (r2s8c) -- the fence + flag store at the producer's tail
+                                         // delays the next launch, whereas the consumer-side signal overlaps with the
+                                         // consumer's interior CTAs
   int fuse_wz = 1;                       // fuse level 2, decomposition along i only: the vertical WAF kernel stores wz's
                                          // edge rows into the neighbours' ghost rows, the horizontal kernel waits
                                          // (MOLOCH_B200_FUSE_WZ=0 / set_option("fuse_wz", 0): stand-alone round)

@@ -37,7 +37,7 @@ cases = {c[0]: c for c in Mu.CASES}
 sel = sys.argv[1:] or ["limited_area", "limited_area_2x2", "periodic_2x2", "band_2x4", "limited_area_1x4"]
 for nm in sel:
     name, wl, px, py = cases[nm]
-    for tr in ("p2p", "p2p_sound", "p2p_unfused", "nccl", "p2p_csignal", "p2p_nowz"):
+    for tr in ("p2p", "p2p_sound", "p2p_unfused", "nccl", "p2p_psignal", "p2p_nowz"):
         run(f"{name} {tr}", Mu.test_decomposed_bit_exact, name, wl, px, py, tr, MP())
 run("boundary 2x2", Mu.test_decomposed_boundary_bit_exact, 2, 2, MP())
 run("spectral 2x2", Mu.test_decomposed_spectral_nudging_bit_exact, 2, 2, "p2p+nccl")

@@ -119,12 +119,12 @@ def _multi_cases():
     M = _gpu_tests()[2]
     keep = None if FULL else {("periodic", "p2p"), ("limited_area_2x2", "p2p"), ("limited_area_2x4", "p2p"),
                               ("band_2x4", "p2p_unfused"), ("limited_area_2x2", "nccl"), ("limited_area_2x2", "p2p_sound"),
-                              ("limited_area_1x4", "p2p"), ("limited_area_1x2", "p2p_csignal"),
+                              ("limited_area_1x4", "p2p"), ("limited_area_1x2", "p2p_psignal"),
                               ("limited_area_1x4", "p2p_nowz")}
     out = []
-    for tr in ("p2p", "p2p_sound", "p2p_unfused", "nccl", "p2p_csignal", "p2p_nowz"):
+    for tr in ("p2p", "p2p_sound", "p2p_unfused", "nccl", "p2p_psignal", "p2p_nowz"):
         for c in M.CASES:
-            if tr in ("p2p_csignal", "p2p_nowz"):
+            if tr in ("p2p_psignal", "p2p_nowz"):
                 if c[0] not in M.ROWS_ONLY:
                     continue
             elif tr != "p2p" and c[0] not in ("periodic", "limited_area", "limited_area_2x2", "band_2x4"):
@@ -293,8 +293,10 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys, tmp_path):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
     assert line["parity"]["bit_exact"] is True and line["parity"]["inputs_match_golden"] is True, line["parity"]
     tune = line["config"]["variant_tuning"]["wsolve"]
-    assert tune["new_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 8, 9, 12], tune
-    assert line["config"]["wsolve_variant"] in (5, 8, 9, 12) and set(tune["ms_per_step"]) == {"5", "8", "9", "12"}
+    # the tiny grid is a "small per-rank grid": variant 2 is among the candidates there
+    assert tune["new_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 8, 9, 12, 2], tune
+    assert line["config"]["wsolve_variant"] in (5, 8, 9, 12, 2) and set(tune["ms_per_step"]) == {"5", "8", "9", "12", "2"}
+    assert line["e2e"]["link_gbs"]["d2h"] > 0
 
 
 def test_halo_timeout_is_reported(_emulated_library):

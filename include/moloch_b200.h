@@ -171,6 +171,10 @@ int moloch_b200_p2p_connect(moloch_b200_ctx* ctx, const void* blobs, int nranks)
  *   "waf"       2 | 1       field-batched fused WAF kernels, or one kernel per reference loop nest
  *   "fuse_halo" 0 | 1 | 2   peer-store transport: exchanges fused into the kernels around them (none / the sound
  *                           loop's sub-steps 2.. / all); every rank must use the same value
+ *   "fuse_wz"   1 | 0       fusion level 2 on a rows-only decomposition: exchange_bt(wz, 2) between the two WAF kernels
+ *                           is stored by the vertical kernel and awaited by the horizontal one (every rank alike)
+ *   "halo_psignal" 0 | 1    fused rounds signalled by the consumer's first CTA (default) or by the producer's last
+ *                           edge CTA (measured slower on 8 GPUs; every rank alike)
  *   "waf_zero_skip" 1 | 0   fused WAF kernels: a field that is exactly +0 in a CTA's / warp's window is not advected
  *   "graph"     1 | 0       the step / dynamical_core / status_update sequences replayed as CUDA graphs
  *   "halo_timeout_ms"       how long a kernel of the peer-store transport waits for a neighbour's arrival

@@ -795,7 +795,7 @@ struct Tmem {
 };
 #endif
 
-template <int D>
+template <int D, bool PUSH>   // PUSH: pai's edge cells are stored into the neighbours' ghost cells (fused round)
 __global__ void __launch_bounds__(128)
 moloch_wsolve_tm(Geo g, const double* __restrict__ zdiv, double* s, double* w, double* pai,
                  const double* __restrict__ tetav, double* tetavf, const double* __restrict__ fmz,
@@ -817,8 +817,6 @@ moloch_wsolve_tm(Geo g, const double* __restrict__ zdiv, double* s, double* w, d
     const int i = g.ici1 + ti, jf = g.jde1 + 32 * tj;   // jf - j0 = HJ + 32*tj: a 32-byte boundary
     const int j = jf + lane;
     const bool valid = (j >= g.jci1 && j <= g.jci2);
-    const bool lr_push = (pc.mask & 3) != 0;           // left/right neighbours: the general per-cell push
-    const ColPush cp = col_push_init(pc, ep, j, i, valid && !lr_push);
     const long long pl = g.plane;
     const long long rowb = gidx(g, jf, i, 1) - pl;      // level k of the tile's first column at rowb + k*pl
     const int half = lane >> 4, c2 = 2 * (lane & 15);
@@ -940,8 +938,6 @@ moloch_wsolve_tm(Geo g, const double* __restrict__ zdiv, double* s, double* w, d
             const long long id = base + k * pl;
             const double pnew = Upa * (1.0 - rdrcv * (zdm + (dtrdz * Ufm * (wkm1 - wk))));
             pai[id - pl] = pnew;
-            col_push(pc, cp, k - 1, pnew);
-            if (lr_push) edge_push(pc, ep, j, i, k - 1, pnew);
             if (k <= kz) {
               w[id] = wk;
               if (last) s[id] = (wk + Us) * Uff;
@@ -955,12 +951,23 @@ moloch_wsolve_tm(Geo g, const double* __restrict__ zdiv, double* s, double* w, d
     cp_async_wait<0>();
     tm.ld_wait();
     if (last && valid) { s[base + pl] = 0.0; s[base + (kz + 1) * pl] = 0.0; }
+    // fused exchange of pai (:673): the edge columns store the levels they have just written (own stores: no
+    // fence needed) into the neighbours' ghost cells, after the sweeps so that the sweeps carry no trace of it
+    if (PUSH && valid) {
+      if (pc.mask & 3) {          // left/right neighbours: the general per-cell push
+        for (int k = 1; k <= kz; ++k) edge_push(pc, ep, j, i, k, pai[base + k * pl]);
+      } else {
+        const ColPush cp = col_push_init(pc, ep, j, i, true);
+        if (cp.t2 || cp.t3)
+          for (int k = 1; k <= kz; ++k) col_push(pc, cp, k, pai[base + k * pl]);
+      }
+    }
   }
   tm.release();
-  halo_producer_done(pc, blockIdx.x, gridDim.x, 4, ntile_j, g.ici2 - g.ici1 + 1, 1);
+  if (PUSH) halo_producer_done(pc, blockIdx.x, gridDim.x, 4, ntile_j, g.ici2 - g.ici1 + 1, 1);
 }
-template <int D>
-static int launch_wsolve_tm(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
+template <int D, bool PUSH>
+static int launch_wsolve_tm_t(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
   const Geo& g = c.g;
   const int ntile_j = (g.jci2 - g.jde1 + 1 + 31) / 32, ni = g.ici2 - g.ici1 + 1, ntiles = ntile_j * ni;
   const double dtrdz = dts * c.rdzita;
@@ -968,13 +975,17 @@ static int launch_wsolve_tm(Ctx& c, double dts, bool last, const PushCtl& pc, co
   // at least 78 KB: no more than two CTAs per SM, i.e. no more CTAs than tensor-memory allocations of 256 columns
   const size_t smem = std::max((size_t)(4 * D * 9) * 32 * sizeof(double) + 16, (size_t)78 * 1024);
   const double* zsrc = c.cfg.mo_divfilter ? c.zdiv2b : c.f[MB_ZDIV2].p;
-  MB_CUDA(cudaFuncSetAttribute(moloch_wsolve_tm<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MB_CUDA(cudaFuncSetAttribute(moloch_wsolve_tm<D, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LaunchScope ls(c, KID_WSOLVE);
-  moloch_wsolve_tm<D><<<(unsigned)((ntiles + 3) / 4), 128, smem, c.stream>>>(
+  moloch_wsolve_tm<D, PUSH><<<(unsigned)((ntiles + 3) / 4), 128, smem, c.stream>>>(
       g, zsrc, c.f[MB_S].p, c.f[MB_W].p, c.f[MB_PAI].p, c.f[MB_TETAV].p, c.f[MB_TETAVF].p, c.f[MB_FMZ].p,
       c.f[MB_FMZF].p, c.f[MB_BDYWTW].p, c.prof[MB_FFILT], dts, dtrdz, zcs2, last ? 1 : 0, ntile_j, ntiles, pc, ep);
   MB_CUDA(cudaGetLastError());
   return 0;
+}
+template <int D>
+static int launch_wsolve_tm(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {
+  return pc.mask ? launch_wsolve_tm_t<D, true>(c, dts, last, pc, ep) : launch_wsolve_tm_t<D, false>(c, dts, last, pc, ep);
 }
 // variant 11: ring of 8 (74 KB of shared memory per CTA of four warps); variant 12: ring of 6 (55 KB)
 int k_wsolve_tm(Ctx& c, double dts, bool last, const PushCtl& pc, const EdgePush& ep) {

@@ -1,0 +1,43 @@
+#!/bin/bash
+# 8-GPU box, library defaults: decomposed parity tests, cordex25 / cp3km / tracer40 at N=8, then cordex25 at N=4, 2, 1 side by side.
+T=${1:-r2s8d}
+mkdir -p gpurun_out
+( time timeout 400 python -m pytest tests/test_gpu_multi.py -q -rs --timeout 300 -p no:cacheprovider ) > gpurun_out/${T}_pytest_multi.log 2>&1
+grep -E "passed|failed" gpurun_out/${T}_pytest_multi.log
+run() {  # name ngpu devices port workload steps
+  local name=$1 n=$2 dev=$3 port=$4 wl=$5 steps=$6
+  if [ $n -eq 1 ]; then
+    CUDA_VISIBLE_DEVICES=$dev timeout 500 python bench.py --steps $steps --warmup 3 --no-e2e --no-cpu-baseline --workload $wl \
+      > gpurun_out/${T}_${name}.json 2> gpurun_out/${T}_${name}.err
+  else
+    CUDA_VISIBLE_DEVICES=$dev timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n \
+      --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps $steps --warmup 3 --no-e2e --workload $wl \
+      > gpurun_out/${T}_${name}.json 2> gpurun_out/${T}_${name}.err
+  fi
+}
+show() {
+  python - $T "$@" <<'PY'
+import json, sys
+T = sys.argv[1]
+for name in sys.argv[2:]:
+    try:
+        d = json.loads([l for l in open(f"gpurun_out/{T}_{name}.json") if l.startswith("{")][-1])
+        c = d["config"]
+        print(name, c["workload"], c["decomposition"], "fusion", c.get("halo_fusion_level"), c.get("halo_signal"), "wz", c.get("halo_wz_fused"),
+              "%.3e c-u/s" % d["value"], "%.3f ms/step" % d["ms_per_step"], "launches", d["gpu_launches"], "wsolve", c["wsolve_variant"],
+              {k: round(v, 3) for k, v in c["variant_tuning"]["wsolve"].get("ms_per_step", {}).items()}, c["variant_tuning"].get("fuse_halo"),
+              "parity", d.get("parity") and d["parity"]["bit_exact"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+        print("   ", {k["kernel"]: (round(k["avg_ms"] * 1e3, 1), k["launches_per_step"]) for k in d["kernels"]})
+    except Exception as e:
+        print(name, "FAILED", e)
+PY
+}
+ALL=0,1,2,3,4,5,6,7
+run n8 8 $ALL 29518 cordex25 20;        show n8
+run cp3km_n8 8 $ALL 29521 cp3km 6;      show cp3km_n8
+run tracer40_n8 8 $ALL 29522 tracer40 4; show tracer40_n8
+run n4 4 0,1,2,3 29523 cordex25 20 &
+run n2 2 4,5 29524 cordex25 20 &
+run n1 1 6 0 cordex25 20 &
+wait
+show n4 n2 n1

@@ -345,7 +345,8 @@ def autotune_wsolve(m, wl, timed, all_min=lambda x: x, device=-1, lib=None):
         m.set_option("wsolve", v)
         m.moloch(1)
         m.sync()
-        rec["ms_per_step"][str(v)] = timed(lambda: m.moloch(1), 2) / 2.0     # max over ranks
+        # max over ranks; the better of two short timings (a neighbour process starting up must not decide)
+        rec["ms_per_step"][str(v)] = min(timed(lambda: m.moloch(1), 2), timed(lambda: m.moloch(1), 2)) / 2.0
     best = min(rec["candidates"], key=lambda v: rec["ms_per_step"][str(v)])
     return best, rec
 

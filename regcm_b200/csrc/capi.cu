@@ -371,6 +371,21 @@ static int require_bdy(Ctx& c) {
 static int do_status_update(Ctx& c) {
   NvtxRange nvtx("status_update");
   const int kz = c.g.kz;
+  if (c.fuse_status && c.fuse_level >= 2 && halo_fused_available(c)) {
+    // the synchronisation-only round and the ux, vx round as fused rounds (see moloch_status_update); both are
+    // signalled by their consumers' first CTAs (the first has no producer at all)
+    PushCtl p_f = {}, p_x = {};
+    WaitCtl w_f = {}, w_x = {};
+    EdgePush e_ux = {}, e_vx = {};
+    if (halo_fused_begin(c, &p_f, &w_f)) return 1;
+    if (halo_fused_begin(c, &p_x, &w_x)) return 1;
+    w_f.nosig = 0; p_x.sig = 0; w_x.nosig = 0;
+    if (halo_fused_edge(c, c.f[MB_UX].p, HS_CROSS, true, false, &e_ux, 2)) return 1;
+    if (halo_fused_edge(c, c.f[MB_VX].p, HS_CROSS, false, true, &e_vx, 2)) return 1;
+    if (k_status_update(c, c.cfg.dtsec, &w_f, &p_x, &e_ux, &e_vx)) return 1;
+    if (c.cfg.ibltyp == 2 && k_tke_update(c, c.cfg.dtsec)) return 1;   // :1419-1424
+    return k_restagger(c, false, &w_x);
+  }
   if (k_status_update(c, c.cfg.dtsec)) return 1;
   if (c.cfg.ibltyp == 2 && k_tke_update(c, c.cfg.dtsec)) return 1;   // :1419-1424
   if (halo_fence(c)) return 1;   // ux/vx ghosts of the previous round may still be read by a neighbour
@@ -540,6 +555,7 @@ int moloch_b200_create(const moloch_b200_config* cfg, moloch_b200_ctx** out) {
   if (const char* e = getenv("MOLOCH_B200_FUSE_HALO")) { c->fuse_halo = atoi(e) != 0; c->fuse_level = atoi(e) >= 2 ? 2 : 1; }
   if (const char* e = getenv("MOLOCH_B200_PSIGNAL")) c->psignal = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_FUSE_WZ")) c->fuse_wz = atoi(e) != 0;
+  if (const char* e = getenv("MOLOCH_B200_FUSE_STATUS")) c->fuse_status = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_GRAPH")) c->use_graph = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_WAF_ZEROSKIP")) c->waf_zero_skip = atoi(e) != 0;
   if (const char* e = getenv("MOLOCH_B200_HALO_TIMEOUT_MS")) { if (atoll(e) >= 1) c->halo_timeout_cycles = atoll(e) * 2000000LL; }
@@ -623,6 +639,8 @@ int moloch_b200_set_option(moloch_b200_ctx* c, const char* name, int value) {
     c->adv_wait_valid = false;
   } else if (n == "fuse_wz") {
     c->fuse_wz = value != 0;
+  } else if (n == "fuse_status") {
+    c->fuse_status = value != 0;
   } else if (n == "waf_zero_skip") {
     c->waf_zero_skip = value != 0;
   } else if (n == "graph") {

@@ -126,6 +126,8 @@ struct Ctx {
                                          // 1.995 vs 1.873 ms/step (r2s8c) -- the fence + flag store at the producer's tail
                                          // delays the next launch, whereas the consumer-side signal overlaps with the
                                          // consumer's interior CTAs
+  int fuse_status = 1;                   // fuse level 2: status_update's fence and ux, vx round folded into status_update /
+                                         // uvxtouvstag (MOLOCH_B200_FUSE_STATUS=0 / set_option("fuse_status", 0))
   int fuse_wz = 1;                       // fuse level 2, decomposition along i only: the vertical WAF kernel stores wz's
                                          // edge rows into the neighbours' ghost rows, the horizontal kernel waits
                                          // (MOLOCH_B200_FUSE_WZ=0 / set_option("fuse_wz", 0): stand-alone round)
@@ -383,7 +385,8 @@ int k_curvature(Ctx& c, double dta, const PushCtl* pc = nullptr, const EdgePush*
 int k_restagger(Ctx& c, bool with_w, const WaitCtl* wc = nullptr);
 int k_tvirt_temp(Ctx& c);
 int k_diagnostics(Ctx& c);
-int k_status_update(Ctx& c, double dtinc);
+int k_status_update(Ctx& c, double dtinc, const WaitCtl* wf = nullptr, const PushCtl* pc = nullptr,
+                    const EdgePush* eux = nullptr, const EdgePush* evx = nullptr);
 int k_init_static(Ctx& c);
 int k_box_copy(Ctx& c, double* dev, double* stage, int ja, int ia, int ka, int nj, int ni, int nk, bool pack,
                cudaStream_t on = nullptr);   // on: another stream than the context's (hand-off copy streams)

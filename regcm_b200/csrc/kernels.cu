@@ -1461,6 +1461,13 @@ int k_diagnostics(Ctx& c) {
 // ---------------------------------------------------------------------------
 // K22  status_update (without its trailing uvxtouvstag)             :1410-1438
 // ---------------------------------------------------------------------------
+// FUSED (peer-store transport, fusion level 2): the two stand-alone rounds that follow the kernel in the reference's
+// order -- the synchronisation-only round that keeps a neighbour's uvxtouvstag (end of advection) from reading
+// ux, vx ghosts that are already being overwritten, and exchange of ux, vx (:1485-1486 as called from :1431) --
+// are folded in: the edge CTAs wait for the neighbours' word "everything before my status_update has completed"
+// (wf), every owned edge cell of ux / vx (updated or not: the boundary update may have changed the others) is
+// stored into the neighbours' ghost cells, and uvxtouvstag waits for the neighbours' status_update (wx).
+template <bool FUSED>
 __global__ void moloch_status_update(Geo g, double* __restrict__ t, double* __restrict__ ux,
                                      double* __restrict__ vx, double* __restrict__ qx,
                                      double* __restrict__ trac, const double* __restrict__ tten,
@@ -1468,13 +1475,22 @@ __global__ void moloch_status_update(Geo g, double* __restrict__ t, double* __re
                                      const double* __restrict__ qxten, const double* __restrict__ chiten,
                                      const double* __restrict__ pai, const double* __restrict__ p,
                                      double* __restrict__ tvirt, double* __restrict__ tetav,
-                                     double* __restrict__ rho, double* __restrict__ qsat, double dtinc) {
+                                     double* __restrict__ rho, double* __restrict__ qsat, double dtinc, WaitCtl wf,
+                                     PushCtl pc, EdgePush eux, EdgePush evx) {
+  if (FUSED) halo_sync(wf, 2, g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, BX, BY);
   THREAD_JIK(g.jce1, g.ice1, 1)
   if (j > g.jce2 || i > g.ice2) return;
   const long long id = IX(j, i, k);
   const long long sp = (long long)g.kz * g.plane;
   double tt = t[id];
-  if (in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2)) {
+  const bool inner = in_box(j, i, g.jci1, g.jci2, g.ici1, g.ici2);
+  if (FUSED && pc.mask) {
+    double uxn = ux[id], vxn = vx[id];
+    if (inner) { uxn = uxn + dtinc * uten[id]; vxn = vxn + dtinc * vten[id]; }
+    edge_push(pc, eux, j, i, k, uxn);
+    edge_push(pc, evx, j, i, k, vxn);
+  }
+  if (inner) {
     tt = tt + dtinc * tten[id];
     t[id] = tt;
     ux[id] = ux[id] + dtinc * uten[id];
@@ -1497,13 +1513,19 @@ __global__ void moloch_status_update(Geo g, double* __restrict__ t, double* __re
   rho[id] = pp / (rgas * tt);
   qsat[id] = pfwsat(tt, pp);
 }
-int k_status_update(Ctx& c, double dtinc) {
+int k_status_update(Ctx& c, double dtinc, const WaitCtl* wf, const PushCtl* pc, const EdgePush* eux, const EdgePush* evx) {
   const Geo& g = c.g;
+  const WaitCtl w0 = wf ? *wf : WaitCtl{};
+  const PushCtl p0 = pc ? *pc : PushCtl{};
+  const EdgePush e0 = eux ? *eux : EdgePush{}, e1 = evx ? *evx : EdgePush{};
   LaunchScope ls(c, KID_STATUS);
-  moloch_status_update<<<grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz), dim3(BX, BY), 0, c.stream>>>(
-      g, c.f[MB_T].p, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_QX].p, c.f[MB_TRAC].p, c.f[MB_TTEN].p,
-      c.f[MB_UTEN].p, c.f[MB_VTEN].p, c.f[MB_QXTEN].p, c.f[MB_CHITEN].p, c.f[MB_PAI].p, c.f[MB_P].p,
-      c.f[MB_TVIRT].p, c.f[MB_TETAV].p, c.f[MB_RHO].p, c.f[MB_QSAT].p, dtinc);
+  const dim3 grid = grid3(g.jce2 - g.jce1 + 1, g.ice2 - g.ice1 + 1, g.kz);
+#define SU_ARGS g, c.f[MB_T].p, c.f[MB_UX].p, c.f[MB_VX].p, c.f[MB_QX].p, c.f[MB_TRAC].p, c.f[MB_TTEN].p, c.f[MB_UTEN].p, \
+      c.f[MB_VTEN].p, c.f[MB_QXTEN].p, c.f[MB_CHITEN].p, c.f[MB_PAI].p, c.f[MB_P].p, c.f[MB_TVIRT].p, c.f[MB_TETAV].p, \
+      c.f[MB_RHO].p, c.f[MB_QSAT].p, dtinc, w0, p0, e0, e1
+  if (w0.mask || p0.mask) moloch_status_update<true><<<grid, dim3(BX, BY), 0, c.stream>>>(SU_ARGS);
+  else moloch_status_update<false><<<grid, dim3(BX, BY), 0, c.stream>>>(SU_ARGS);
+#undef SU_ARGS
   MB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -173,6 +173,8 @@ int moloch_b200_p2p_connect(moloch_b200_ctx* ctx, const void* blobs, int nranks)
  *                           loop's sub-steps 2.. / all); every rank must use the same value
  *   "fuse_wz"   1 | 0       fusion level 2 on a rows-only decomposition: exchange_bt(wz, 2) between the two WAF kernels
  *                           is stored by the vertical kernel and awaited by the horizontal one (every rank alike)
+ *   "fuse_status" 1 | 0     fusion level 2: status_update's synchronisation-only round and its ux, vx round folded into
+ *                           status_update / uvxtouvstag (every rank alike)
  *   "halo_psignal" 0 | 1    fused rounds signalled by the consumer's first CTA (default) or by the producer's last
  *                           edge CTA (measured slower on 8 GPUs; every rank alike)
  *   "waf_zero_skip" 1 | 0   fused WAF kernels: a field that is exactly +0 in a CTA's / warp's window is not advected

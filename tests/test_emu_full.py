@@ -119,8 +119,7 @@ def _multi_cases():
     M = _gpu_tests()[2]
     keep = None if FULL else {("periodic", "p2p"), ("limited_area_2x2", "p2p"), ("limited_area_2x4", "p2p"),
                               ("band_2x4", "p2p_unfused"), ("limited_area_2x2", "nccl"), ("limited_area_2x2", "p2p_sound"),
-                              ("limited_area_1x4", "p2p"), ("limited_area_1x2", "p2p_psignal"),
-                              ("limited_area_1x4", "p2p_nowz")}
+                              ("limited_area_1x4", "p2p"), ("limited_area_1x2", "p2p_psignal")}
     out = []
     for tr in ("p2p", "p2p_sound", "p2p_unfused", "nccl", "p2p_psignal", "p2p_nowz"):
         for c in M.CASES:
@@ -199,7 +198,7 @@ def test_restart_from_the_save_set():
 
 
 @pytest.mark.parametrize("name,px,py", [("limited_area_2x2", 2, 2), ("band_2x4", 2, 4), ("limited_area_1x4", 1, 4)] if FULL
-                         else [("limited_area_2x2", 2, 2), ("limited_area_1x4", 1, 4)])
+                         else [("limited_area_1x4", 1, 4)])
 def test_decomposed_with_drifting_ranks(name, px, py, monkeypatch, _emulated_library):
     """The peer-store transport under rank drift: every launch of every rank thread first sleeps a pseudo-random
     time (one launch in 16, up to 20 ms: a rank is at times several kernels behind its neighbours).  The

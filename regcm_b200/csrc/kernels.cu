@@ -1467,6 +1467,10 @@ int k_diagnostics(Ctx& c) {
 // are folded in: the edge CTAs wait for the neighbours' word "everything before my status_update has completed"
 // (wf), every owned edge cell of ux / vx (updated or not: the boundary update may have changed the others) is
 // stored into the neighbours' ghost cells, and uvxtouvstag waits for the neighbours' status_update (wx).
+#ifndef MB_SU_G
+#define MB_SU_G 5
+#endif
+constexpr int SU_G = MB_SU_G;   // species per group of moloch_status_update
 template <bool FUSED>
 __global__ void moloch_status_update(Geo g, double* __restrict__ t, double* __restrict__ ux,
                                      double* __restrict__ vx, double* __restrict__ qx,
@@ -1495,15 +1499,41 @@ __global__ void moloch_status_update(Geo g, double* __restrict__ t, double* __re
     t[id] = tt;
     ux[id] = ux[id] + dtinc * uten[id];
     vx[id] = vx[id] + dtinc * vten[id];
-    for (int n = 0; n < g.nqx; ++n) {
-      double q = qx[id + n * sp] + dtinc * qxten[id + n * sp];
-      if (q < c_qxcheckval[n]) q = c_qxzeroval[n];
-      qx[id + n * sp] = q;
+    // species in groups of SU_G with every load of a group issued before its first store (the compiler cannot move a
+    // load of qx / trac across a store to the same array: one species at a time leaves one load pair in flight)
+#pragma unroll 1
+    for (int n0 = 0; n0 < g.nqx; n0 += SU_G) {
+      double q[SU_G], dq[SU_G];
+#pragma unroll
+      for (int m = 0; m < SU_G; ++m) {
+        const bool on = n0 + m < g.nqx;
+        q[m] = on ? qx[id + (n0 + m) * sp] : 0.0;
+        dq[m] = on ? qxten[id + (n0 + m) * sp] : 0.0;
+      }
+#pragma unroll
+      for (int m = 0; m < SU_G; ++m)
+        if (n0 + m < g.nqx) {
+          double v = q[m] + dtinc * dq[m];
+          if (v < c_qxcheckval[n0 + m]) v = c_qxzeroval[n0 + m];
+          qx[id + (n0 + m) * sp] = v;
+        }
     }
-    for (int n = 0; n < g.ntr; ++n) {
-      double q = trac[id + n * sp] + dtinc * chiten[id + n * sp];
-      if (q < 0.0) q = 0.0;
-      trac[id + n * sp] = q;
+#pragma unroll 1
+    for (int n0 = 0; n0 < g.ntr; n0 += SU_G) {
+      double q[SU_G], dq[SU_G];
+#pragma unroll
+      for (int m = 0; m < SU_G; ++m) {
+        const bool on = n0 + m < g.ntr;
+        q[m] = on ? trac[id + (n0 + m) * sp] : 0.0;
+        dq[m] = on ? chiten[id + (n0 + m) * sp] : 0.0;
+      }
+#pragma unroll
+      for (int m = 0; m < SU_G; ++m)
+        if (n0 + m < g.ntr) {
+          double v = q[m] + dtinc * dq[m];
+          if (v < 0.0) v = 0.0;
+          trac[id + (n0 + m) * sp] = v;
+        }
     }
   }
   const double tv = tt * moist_factor(g, qx, id);

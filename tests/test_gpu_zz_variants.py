@@ -71,7 +71,9 @@ def test_set_option_switches_variants_of_a_live_context():
     o, _ = make_oracle(wl)
     fields, profiles = oracle_inputs(o, wl)
     m = make_gpu(wl, fields, profiles)
-    for opt, v in (("wsolve", 6), ("waf", 1), ("wsolve", 2), ("waf", 2), ("wsolve", 7), ("wsolve", 5)):
+    # (the halo options are accepted on one rank too: they only change what a decomposed run does)
+    for opt, v in (("wsolve", 6), ("waf", 1), ("wsolve", 2), ("waf", 2), ("wsolve", 7), ("wsolve", 5), ("fuse_wz", 0),
+                   ("fuse_status", 0), ("halo_psignal", 1), ("wsolve", 12)):
         m.set_option(opt, v)
         o.step(1); m.moloch(1)
         compare(o, m, PROGNOSTIC + ["trac"], label=f"after set_option({opt}, {v}): ")

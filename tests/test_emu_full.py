@@ -281,6 +281,7 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys, tmp_path):
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     monkeypatch.setenv("MOLOCH_B200_FUSE_HALO", "2")
     monkeypatch.delenv("MOLOCH_B200_WSOLVE", raising=False)
+    monkeypatch.setenv("BENCH_TUNE_REPS", "1")           # one timing per variant is enough on the emulator
     # argparse built its choices from S.WORKLOADS at call time, so "tiny" is accepted
     assert bench.main() == 0
     line = json.loads([x for x in capsys.readouterr().out.splitlines() if x.startswith("{")][-1])

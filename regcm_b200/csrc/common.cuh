@@ -16,6 +16,11 @@
 #include "../../include/moloch_b200.h"
 #include "geo.h"
 
+#ifdef MB_HOST_EMU   // tests/emu: the host build has no vector types
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
+#endif
+
 namespace mb {
 
 enum KernelId {

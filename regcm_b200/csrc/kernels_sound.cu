@@ -27,10 +27,6 @@
 
 namespace mb {
 
-#ifdef MB_HOST_EMU
-struct double2 { double x, y; };
-static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
-#endif
 
 // moloch_sound_div: a warp owns a strip of R rows x 64 columns of one level (lanes 1..30 hold the 60 useful
 // columns, two per lane; lanes 0 and 31 only supply the neighbouring zdiv2 values) and marches through the rows

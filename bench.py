@@ -565,11 +565,11 @@ def main():
         return float(ms.item())
 
     # ---- kernel variants: measured, not guessed ---------------------------------------
-    # The implicit-w column solver exists in two thread-per-column variants (5: three sweep arrays in
-    # shared memory, 4 warps/SM -- the one profiles/ measured; 6: the divergence recomputed, 7 warps/SM --
-    # written without GPU access).  Variant 6 is only considered after it has reproduced variant 5 bit for
-    # bit on a small case on THIS device; then both are timed on the benchmark model and the faster one
-    # runs the timed region.  MOLOCH_B200_WSOLVE fixes the variant instead.
+    # The implicit-w column solver exists in several bit-identical variants (include/moloch_b200.h: set_option
+    # "wsolve").  The candidates are first checked against variant 5 on a small case on THIS device (every
+    # prognostic field bit for bit), then timed on the benchmark model; the fastest runs the timed region and the
+    # record names every variant that was rejected earlier with the reason (config.variant_tuning).
+    # MOLOCH_B200_WSOLVE fixes the variant instead.
     tuning = {"wsolve": {}}
     wsolve_variant = int(os.environ.get("MOLOCH_B200_WSOLVE", "0"))
     if wsolve_variant == 0:
@@ -580,8 +580,9 @@ def main():
             return float(t.item())
         wsolve_variant, tuning["wsolve"] = autotune_wsolve(m, wl, timed, all_min, local_rank)
     m.set_option("wsolve", wsolve_variant)
-    # Same for the halo fusion level at N > 1: level 2 (first sub-step and advection exchanges fused too) was
-    # written without GPU access; it runs the timed region only if it is not slower than level 1 here.
+    # Same for the halo fusion level at N > 1: level 2 (first sub-step, advection, wz and status_update exchanges
+    # fused too) runs the timed region only if it is not slower than level 1 here (they tie at 2 GPUs, level 2
+    # wins at 4 and 8).
     if world > 1 and args.transport == "p2p" and int(halo_fusion) == 2 and "MOLOCH_B200_FUSE_HALO_FIXED" not in os.environ:
         tuning["fuse_halo"] = {}
         for lv in (2, 1):

@@ -395,8 +395,8 @@ static int launch_wsolve5(Ctx& c, double dts, bool last, const PushCtl& pc, cons
   return 0;
 }
 // ---------------------------------------------------------------------------
-// K7+K8+K9, thread-per-column variant 6 (MOLOCH_B200_WSOLVE=6 / set_option("wsolve", 6); written without GPU
-// access at the end of round 1: bench.py times it against moloch_wsolve5 and keeps the faster one).
+// K7+K8+K9, thread-per-column variant 6 (MOLOCH_B200_WSOLVE=6 / set_option("wsolve", 6); measured slower than
+// variant 5 on the B200: 246 vs 217 us, r2a -- kept as a bit-identical A/B candidate).
 // moloch_wsolve5 is bound by the latency of ONE warp per scheduler: its three sweep arrays (w', wwkw and the
 // finished divergence) and the ring take 46 KB of shared memory per warp at kz = 41, so only 4 warps fit an SM.
 // Here the finished divergence is not parked but recomputed in the upward pass from the same operands, in the

@@ -42,6 +42,9 @@ def main():
     ap.add_argument("--crop", type=int, default=0, help="crop the horizontal domain to N x N")
     ap.add_argument("--jx", type=int, default=0, help="crop to jx x iy columns (e.g. the per-rank grid of a decomposed run)")
     ap.add_argument("--iy", type=int, default=0)
+    ap.add_argument("--digest", action="store_true",
+                    help="add the wrap-around sums of the bit patterns of the prognostic fields after the last step "
+                         "(two library builds that print the same digests computed the same bits)")
     args = ap.parse_args()
     wl = S.WORKLOADS[args.workload]
     if args.crop:
@@ -124,6 +127,13 @@ def main():
         if name in alg and avg > 0:
             e["alg_gbs"] = round(alg[name] * 8 * cells / (avg * 1e-3) / 1e9, 1)
         out["kernels"][name] = e
+    if args.digest:
+        out["digest"] = {}
+        for n in ("u", "v", "w", "pai", "tetav", "t", "qx", "trac", "ux", "vx"):
+            if n == "trac" and wl.ntr == 0:
+                continue
+            a = np.ascontiguousarray(m.get_local(n), dtype=np.float64)
+            out["digest"][n] = int(a.view(np.uint64).sum(dtype=np.uint64))
     print(json.dumps(out), flush=True)
     m.close()
 

@@ -30,6 +30,41 @@ def test_library_exports_every_declared_symbol():
     assert M.load_library().moloch_b200_abi_version() == 3
 
 
+def test_plain_c_client_compiles_links_and_gets_the_error_contract(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit (-Wall -Wextra -pedantic -Werror) that includes the header,
+    takes the address of every declared entry point and links against the library; it then runs the calls that
+    need no GPU (version, struct size, device count) and the refusal of an invalid configuration with its message
+    (RegCM's `fatal` text comes from moloch_b200_last_error)."""
+    hdr = open(os.path.join(ROOT, "include", "moloch_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(moloch_b200_[a-z_0-9]+)\s*\(", hdr)))
+    src = tmp_path / "abi_client.c"
+    src.write_text(
+        '#include "moloch_b200.h"\n#include <stdio.h>\n#include <string.h>\n'
+        "typedef void (*any_fn)(void);\n"
+        "int main(void) {\n"
+        "  any_fn tab[] = {" + ", ".join(f"(any_fn){n}" for n in declared) + "};\n"
+        "  size_t n = sizeof tab / sizeof tab[0], q;\n"
+        "  moloch_b200_config cfg;\n  moloch_b200_ctx* ctx = NULL;\n"
+        "  for (q = 0; q < n; ++q) if (!tab[q]) return 1;\n"
+        "  if (moloch_b200_abi_version() != 3) return 2;\n"
+        "  if ((size_t)moloch_b200_config_size() != sizeof cfg) return 3;\n"
+        "  memset(&cfg, 0, sizeof cfg);\n"
+        "  if (moloch_b200_create(&cfg, &ctx) == 0 || ctx != NULL) return 4;   /* an all-zero configuration is refused */\n"
+        '  if (!strstr(moloch_b200_last_error(), "jx, iy, kz")) return 5;\n'
+        "  if (moloch_b200_create(NULL, &ctx) == 0) return 6;\n"
+        '  printf("%d entry points, %d devices\\n", (int)n, moloch_b200_device_count());\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi_client"
+    libdir = os.path.dirname(M.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(M.LIB_PATH),
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith(f"{len(declared)} entry points")
+
+
 def test_enums_match_header():
     hdr = open(os.path.join(ROOT, "include", "moloch_b200.h")).read()
     body = re.sub(r"/\*.*?\*/", "", re.search(r"enum moloch_b200_field \{(.*?)\};", hdr, re.S).group(1), flags=re.S)

@@ -167,25 +167,37 @@ def host_cores() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def run_cpu_reference(wl, steps: int, warmup: int) -> dict:
+def run_cpu_reference(wl, steps: int, warmup: int, budget_s: float | None = None) -> dict:
     """The CPU arm: oracle (C++ restatement of Main/mod_moloch.F90, OpenMP over
-    all host cores) on a bounded sample of the workload."""
+    all host cores) on a bounded sample of the workload.  `budget_s`: wall-clock budget of the whole
+    call; the first warm-up step is timed and the step count is cut (never below 1) when
+    `warmup + steps` steps would not fit -- the record names the counts that were run."""
     from oracle.oracle import Oracle
     swl = cpu_sample_workload(wl)
     o = Oracle(swl)
     o.load_primary(S.make_primary(swl))
     o.set_threads(host_cores())     # omp_set_num_threads: overrides an inherited OMP_NUM_THREADS
     cores = o.get_threads()
-    o.step(max(warmup, 1))
+    warmup = max(warmup, 1)
+    t0 = time.perf_counter()
+    o.step(1)
+    t1 = time.perf_counter() - t0
+    asked = (steps, warmup)
+    if budget_s is not None and (warmup + steps) * t1 > budget_s:
+        warmup = min(warmup, 3 if 4 * t1 <= budget_s else 1)
+        steps = max(1, min(steps, int(budget_s / t1) - warmup))
+    if warmup > 1:
+        o.step(warmup - 1)
     t0 = time.perf_counter()
     o.step(steps)
     dt = time.perf_counter() - t0
     ok = bool(np.isfinite(o.get("pai")).all())
+    cut = "" if (steps, warmup) == asked else f" (asked: {asked[0]} after {asked[1]}; cut to the {budget_s:.0f} s budget)"
     return {"value": swl.cells * steps / dt, "unit": "cell-updates/s", "cores": cores, "kind": "port",
             "sample": f"{wl.name} " + ("full grid " if swl is wl else "cropped to ") +
                       f"{swl.jx}x{swl.iy}x{swl.kz} (F={swl.nfields}), {steps} steps "
-                      f"after {max(warmup, 1)} warm-up, {dt:.2f} s on {cores} OpenMP threads; finite={ok}",
-            "ms_per_step": dt / steps * 1e3, "grid": [swl.jx, swl.iy, swl.kz]}
+                      f"after {warmup} warm-up{cut}, {dt:.2f} s on {cores} OpenMP threads; finite={ok}",
+            "ms_per_step": dt / steps * 1e3, "grid": [swl.jx, swl.iy, swl.kz], "steps": steps, "warmup": warmup}
 
 
 def measure_e2e(m, wl, ksteps, barrier=lambda: None, allreduce_max=lambda x: x):
@@ -448,10 +460,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = max(1, min(args.steps, 6))
-        r = run_cpu_reference(wl, steps, min(args.warmup, 1))
+        # the same --steps K --warmup W as the GPU arm while the whole run stays within a few minutes of host time
+        # (cordex25: 1.3 s per step on 16 cores); a slower host gets fewer steps, and the record says so
+        r = run_cpu_reference(wl, max(1, args.steps), args.warmup,
+                              budget_s=float(os.environ.get("BENCH_CPU_BUDGET_S", "150")))
         line = base_line(wl, args, args.gpus)
-        line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": steps,
+        line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+                     "warmup": r["warmup"],
                      "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                      "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": 0},

@@ -280,3 +280,17 @@ def test_bench_reference_arm_prints_contract_line():
               "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_bench_reference_arm_keeps_the_asked_counts_or_says_what_it_cut():
+    import json
+    env = dict(os.environ)
+    for budget, want in (("600", (3, 2)), ("0.001", (1, 1))):
+        env["BENCH_CPU_BUDGET_S"] = budget
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3",
+                            "--warmup", "2", "--workload", "isc24_small"], capture_output=True, text=True, timeout=600,
+                           env=env)
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        assert (line["steps"], line["warmup"]) == want, line
+        assert ("asked: 3 after 2" in line["cpu_baseline"]["sample"]) == (want != (3, 2))
+

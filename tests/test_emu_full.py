@@ -296,7 +296,8 @@ def test_bench_main_dry_run(_emulated_library, monkeypatch, capsys, tmp_path):
     # the tiny grid is a "small per-rank grid": variant 2 is among the candidates there
     assert tune["new_bit_exact_vs_v5"] is True and tune["candidates"] == [5, 8, 9, 12, 2], tune
     assert line["config"]["wsolve_variant"] in (5, 8, 9, 12, 2) and set(tune["ms_per_step"]) == {"5", "8", "9", "12", "2"}
-    assert line["e2e"]["link_gbs"]["d2h"] > 0
+    lg = line["e2e"]["link_gbs"]     # None only when the hand-off window is not positive (emulator timing noise; never on a GPU)
+    assert (lg is None and line["e2e"]["ms_per_step"] <= line["ms_per_step"]) or lg["d2h"] > 0
 
 
 def test_halo_timeout_is_reported(_emulated_library):
